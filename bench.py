@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — DeepFM train samples/sec (fwd + bwd + sparse Adam) on B200, per BASELINE.json.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl b200|reference]
+
+A "step" is one pass of the hot path (transform -> gather/FM -> tower -> loss -> backward ->
+sorted sparse reduction -> optimizers) over one batch of synthetic input.  `value` times the
+device-resident path (inputs already in HBM); `e2e` times the same steps through the host-buffer
+C-ABI entry point (H2D of the raw columns + D2H of the loss inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "DeepFM train samples/sec (fwd+bwd+sparse Adam)"
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: the DeepFM config quoted for 1 B200
+    "deepfm_ml100k_k16_h256x128_b65536": dict(data="ml100k", k=16, hidden=(256, 128), batch=65536, model="deepfm"),
+    # configs[0] / configs[1]
+    "deepfm_ml100k_k4_h16x16_b32": dict(data="ml100k", k=4, hidden=(16, 16), batch=32, model="deepfm"),
+    "wide_deep_ml100k_k4_h16x16_b4096": dict(data="ml100k", k=4, hidden=(16, 16), batch=4096, model="wide_deep"),
+    # configs[3] on one GPU (26 x 1e7 rows, k=16: 16.6 GB of tables + 33 GB of Adam slots)
+    "deepfm_criteo_1e7_k16_h16x16_b65536": dict(data="criteo", k=16, hidden=(16, 16), batch=65536, model="deepfm",
+                                                buckets=10_000_000),
+    "deepfm_criteo_1e6_k16_h16x16_b65536": dict(data="criteo", k=16, hidden=(16, 16), batch=65536, model="deepfm",
+                                                buckets=1_000_000),
+}
+DEFAULT_WORKLOAD = "deepfm_ml100k_k16_h256x128_b65536"
+
+
+def bytes_per_sample(dc, dn, k, slots_emb, slots_lin):
+    """SURVEY.md §8(d) algorithmic bytes per sample (fp32, int32 ids, no dedup credit)."""
+    inputs = 4 * dc + 4 * dn + 4
+    gather = 4 * dc * (k + 1)
+    update = 2 * 4 * dc * (k * (1 + slots_emb) + (1 + slots_lin))
+    return inputs + gather + update
+
+
+def make_columns(w):
+    from recommender_tensorflow_b200 import synth
+    from recommender_tensorflow_b200.trainers import ml_100k
+    if w["data"] == "ml100k":
+        return ml_100k.get_feature_columns()["linear"], [], ml_100k.FEATURE_DTYPES
+    cats, nums = synth.criteo_columns(w["buckets"])
+    return cats, nums, {}
+
+
+def make_batches(w, n_batches, seed):
+    from recommender_tensorflow_b200 import synth
+    rng = np.random.default_rng(seed)
+    out = []
+    if w["data"] == "ml100k":
+        ml = synth.ML100K()
+        for _ in range(n_batches):
+            out.append(ml.fast_batch(w["batch"], rng))
+    else:
+        for _ in range(n_batches):
+            out.append(synth.criteo_batch(w["batch"], rng))
+    return out
+
+
+def optimizers(w):
+    from recommender_tensorflow_b200.engine import default_optimizer
+    if w["model"] == "wide_deep":   # trainers/linear_deep.py:32-39 canned defaults
+        return dict(use_mf=False, loss_reduction="sum", opt_deep=default_optimizer("Adagrad", 0.001),
+                    opt_linear=default_optimizer("Ftrl", 0.005))
+    return dict(use_mf=True, loss_reduction="mean", opt_deep=default_optimizer("Adam", 0.001),
+                opt_linear=default_optimizer("Adam", 0.001))
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self.stop_flag = gpu_index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def cpu_baseline(w, cats_specs_engine, seconds_target=12.0, threads=None):
+    """Restated reference (torch-CPU oracle, NOT TensorFlow) timed on the host cores on a bounded sample."""
+    import torch
+    from oracle.deepfm import OracleDeepFM, init_weights
+    from tests.util import oracle_cfg
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    eng_like = cats_specs_engine
+    cfg = oracle_cfg(eng_like)
+    nb = sum(int(s["num_buckets"]) for s in cfg["cat"])
+    if nb > 5_000_000:
+        return None, "tables too large for the literal non-lazy CPU oracle"
+    ora = OracleDeepFM(cfg, init_weights(cfg, 0))
+    bs = min(w["batch"], 4096)
+    ww = dict(w, batch=bs)
+    batches = make_batches(ww, 4, 99)
+    feats = []
+    for f, y in batches:   # oracle takes object arrays of bytes for strings
+        ff = {}
+        for k, v in f.items():
+            if isinstance(v, tuple):
+                data, offs = v
+                raw = data.tobytes()
+                ff[k] = np.array([raw[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)], dtype=object)
+            else:
+                ff[k] = v
+        feats.append((ff, y))
+    ora.train_step_raw(*feats[0])
+    t0, n = time.perf_counter(), 0
+    while True:
+        ora.train_step_raw(*feats[n % len(feats)])
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > seconds_target or n >= 200:
+            break
+    return {"value": bs * n / dt, "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": "%d steps of batch %d of the same workload, torch-CPU float32 restatement of the TF-1.12 step "
+                      "(incl. literal non-lazy Adam); not TensorFlow" % (n, bs)}, None
+
+
+def run_reference(args, w, name):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; TF 1.12 is not installable)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from recommender_tensorflow_b200 import feature_column  # noqa: F401  (descriptors only, no CUDA)
+
+    class EngLike:
+        pass
+    cats, nums, dtypes = make_columns(w)
+    e = EngLike()
+    cats = sorted(cats, key=lambda c: c.name + "_embedding")
+    e.specs = []
+    for c in cats:
+        s = c.spec()
+        if s["kind"] == "bucketized":
+            s["dtype"] = dtypes.get(s["source"], "float32")
+        e.specs.append(s)
+    e.num_columns = sorted(nums, key=lambda c: c.name)
+    e.k, e.hidden = w["k"], list(w["hidden"])
+    o = optimizers(w)
+    e.use_linear, e.use_mf, e.use_dnn = True, o["use_mf"], True
+    e.loss_reduction, e.opt_deep, e.opt_linear = o["loss_reduction"], o["opt_deep"], o["opt_linear"]
+    per_step_budget = 60.0 / max(1, args.steps + args.warmup)
+    base, why = cpu_baseline(w, e, seconds_target=max(5.0, min(30.0, per_step_budget * args.steps)))
+    if base is None:
+        print(json.dumps({"impl": "reference", "unavailable": why}))
+        return
+    line = {"metric": METRIC, "value": base["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference", "config": {"workload": name},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-phases", action="store_true", help="print a per-phase device-time breakdown to stderr")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    name = args.workload
+    w = WORKLOADS[name]
+    if args.impl == "reference":
+        run_reference(args, w, name)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from recommender_tensorflow_b200.engine import DeepFMEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    cats, nums, dtypes = make_columns(w)
+    B = w["batch"]
+    eng = DeepFMEngine(cats, nums, embedding_size=w["k"], hidden_units=w["hidden"], max_batch=B, device=local,
+                       feature_dtypes=dtypes, **optimizers(w))
+    eng.init_random(1234 + rank)
+    n_batches = 8
+    host_batches = make_batches(w, n_batches, 777 + rank)
+    packed_host = [eng.pack(f, y) for f, y in host_batches]
+    packed_dev = [eng.pack(f, y, device=True) for f, y in host_batches]
+    h2d_bytes = packed_host[0].nbytes
+
+    stream = torch.cuda.Stream()
+    loss_buf = torch.zeros(1, dtype=torch.float32, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (value)
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            eng.train_step_device(packed_dev[i % n_batches], loss_out=loss_buf, stream=stream.cuda_stream)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for i in range(args.steps):
+            eng.train_step_device(packed_dev[(args.warmup + i) % n_batches], loss_out=loss_buf, stream=stream.cuda_stream)
+        ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.last_step_launches * args.steps
+    eng.sync()
+    last_loss = float(loss_buf.item())
+
+    # ---------------- end-to-end through the host-buffer entry point (e2e)
+    for i in range(3):
+        eng.train_step_async(packed_host[i % n_batches])
+    eng.drain()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        eng.train_step_async(packed_host[i % n_batches])     # H2D + step; returns the previous step's loss (D2H)
+    e2e_loss = eng.drain()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(t[0]), float(t[1])
+
+    phases = None
+    if args.profile_phases or True:
+        eng.set_profiling(True)
+        eng.train_step_device(packed_dev[0], loss_out=loss_buf)
+        eng.sync()
+        phases = eng.phase_ms()
+        eng.set_profiling(False)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        se = {"Adam": 2, "Adagrad": 1, "Ftrl": 2, "SGD": 0}
+        o = optimizers(w)
+        bps = bytes_per_sample(len(cats), len(nums), w["k"], se[o["opt_deep"]["name"]], se[o["opt_linear"]["name"]])
+        total_samples = B * args.steps * world
+        value = total_samples / (ms * 1e-3)
+        achieved = value / world * bps / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "b200",
+            "config": {"workload": name, "batch_per_gpu": B, "embedding_size": w["k"], "hidden_units": list(w["hidden"]),
+                       "n_cat": len(cats), "n_num": len(nums), "table_rows": int(eng.row_offsets[-1]),
+                       "optimizer": o["opt_deep"]["name"] + ("/" + o["opt_linear"]["name"] if w["model"] == "wide_deep" else " (TF non-lazy, exact deferred)"),
+                       "l2": "per-step working set (activations + gradients) exceeds L2; inputs rotate over %d batches" % n_batches,
+                       "parallelism": "single GPU" if world == 1 else "replicas x%d" % world},
+            "gpu_launches": int(launches),
+            "loss_last": last_loss,
+            "e2e": {"value": B * args.steps * world / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / args.steps, "loss_last": e2e_loss,
+                    "how": "dfm_train_step_host_async: pinned host arena -> one H2D copy per step on a copy stream, step, "
+                           "D2H of the loss; double buffered, wall clock with a device sync on both sides"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "bytes_per_sample": bps, "peak_source": peak_kind,
+                         "scope": "whole step (all kernels of one train step; SURVEY.md 8d bytes/sample x batch / step time)"},
+            "phases_ms": phases,
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                base, why = cpu_baseline(w, eng)
+                line["cpu_baseline"] = base if base else {"unavailable": why}
+            except Exception as ex:   # the baseline is a side measurement; never lose the GPU line
+                line["cpu_baseline"] = {"unavailable": repr(ex)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,174 @@
+/*
+ * deepfm_b200.h — C ABI of libdeepfm_b200.so: the B200-native (sm_100a) DeepFM / wide&deep
+ * train step that sits directly beneath the reference's Estimator `model_fn`.
+ *
+ * The reference (leotimus/recommender-tensorflow) has no native seam of its own: every op of
+ *   trainers/deep_fm.py:11-125      model_fn(features, labels, mode, params)
+ *   trainers/linear_deep.py:32-39   DNNLinearCombinedClassifier(...)
+ *   trainers/ml_100k.py:18-39       get_feature_columns()
+ *   trainers/model_utils.py:57-66   get_optimizer()
+ * is a TensorFlow-1.12 graph op.  This header is the seam a TF custom op (or the ctypes host in
+ * recommender_tensorflow_b200/) binds: one handle = one model instance on one device.
+ *
+ * Conventions
+ *  - plain C types only; every function returns an int status (0 = DFM_OK, negative = error) and
+ *    never throws or aborts; dfm_last_error() gives the text of the last failure on a handle.
+ *  - the caller owns every batch / output buffer; the handle owns tables, optimizer slots and
+ *    workspaces.  Device-pointer entry points enqueue on the caller's cudaStream_t (passed as
+ *    void*) and do not synchronise; *_host entry points take host pointers, copy inside and return
+ *    after the result is on the host.
+ *  - calls on one handle must be serialised by the caller.
+ *  - categorical fields are processed in the order given in dfm_config.cat ("model order"; the
+ *    host passes them sorted by column name exactly like tf.feature_column.input_layer /
+ *    linear_model do).
+ */
+#ifndef DEEPFM_B200_H_
+#define DEEPFM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFM_OK                 0
+#define DFM_ERR_INVALID_ARG   -1
+#define DFM_ERR_CUDA          -2
+#define DFM_ERR_OUT_OF_RANGE  -3   /* identity column value outside [0, num_buckets) */
+#define DFM_ERR_UNSUPPORTED   -4
+#define DFM_ERR_NCCL          -5
+#define DFM_ERR_NOT_FOUND     -6
+
+#define DFM_MAX_CAT     64
+#define DFM_MAX_NUM     64
+#define DFM_MAX_HIDDEN   8
+
+/* column kinds — tf.feature_column.categorical_column_with_* (trainers/ml_100k.py:19-35) */
+enum { DFM_COL_HASH = 0, DFM_COL_BUCKETIZED = 1, DFM_COL_VOCAB = 2, DFM_COL_IDENTITY = 3 };
+/* raw column dtypes — what tf.decode_csv yields (trainers/ml_100k.py:11-15,45) */
+enum { DFM_INT32 = 0, DFM_FLOAT32 = 1, DFM_STRING = 2 };
+/* optimizers — trainers/model_utils.py:57-66 */
+enum { DFM_OPT_ADAM = 0, DFM_OPT_ADAGRAD = 1, DFM_OPT_FTRL = 2, DFM_OPT_SGD = 3 };
+/* loss reduction — contrib binary head (mean, trainers/deep_fm.py:118) vs canned head (sum) */
+enum { DFM_LOSS_MEAN = 0, DFM_LOSS_SUM = 1 };
+
+/* One categorical feature column.  Replaces the _HashedCategoricalColumn / _BucketizedColumn /
+ * _VocabularyListCategoricalColumn / _IdentityCategoricalColumn objects built at
+ * trainers/ml_100k.py:19-35. */
+typedef struct {
+    const char*        name;          /* column name (model-order key) */
+    int32_t            kind;          /* DFM_COL_* */
+    int32_t            dtype;         /* DFM_INT32 | DFM_FLOAT32 | DFM_STRING of the raw column */
+    int64_t            num_buckets;   /* hash / identity: N.  bucketized / vocab: derived, may be 0 */
+    const float*       boundaries;    /* bucketized: ascending float32 boundaries */
+    int32_t            n_boundaries;
+    const char* const* vocab;         /* vocab: NUL-terminated strings */
+    int32_t            vocab_size;
+    int32_t            num_oov;       /* vocab: OOV hash buckets appended after the list */
+} dfm_column;
+
+/* tf.train.*Optimizer(learning_rate) hyper-parameters (trainers/model_utils.py:57-66; TF defaults) */
+typedef struct {
+    int32_t kind;       /* DFM_OPT_* */
+    float   lr;
+    float   beta1, beta2, eps;   /* Adam: 0.9 0.999 1e-8 */
+    float   init_acc;            /* Adagrad / FTRL: 0.1 */
+} dfm_optimizer;
+
+/* params of model_fn (trainers/deep_fm.py:13-26) + the column lists it receives */
+typedef struct {
+    int32_t           n_cat;
+    const dfm_column* cat;            /* categorical_columns, model order */
+    int32_t           n_num;          /* numeric_columns (float32 inputs), model order */
+    int32_t           embedding_size; /* k: multiple of 4 dividing 128 */
+    int32_t           n_hidden;
+    const int32_t*    hidden_units;
+    int32_t           use_linear, use_mf, use_dnn;
+    int32_t           loss_reduction; /* DFM_LOSS_* */
+    dfm_optimizer     opt_deep;       /* embeddings, numeric_embeddings, DNN tower */
+    dfm_optimizer     opt_linear;     /* linear tables, numeric linear weights, bias */
+    int32_t           max_batch;      /* workspaces are sized for this many samples */
+    int32_t           device;         /* CUDA device ordinal */
+    /* row sharding: this handle owns rows {id : id mod world == rank} */
+    int32_t           rank, world;
+    void*             nccl_comm;      /* ncclComm_t when world > 1, else NULL */
+} dfm_config;
+
+/* One batch of raw (un-hashed) feature columns = what input_fn's parse_csv yields
+ * (trainers/ml_100k.py:44-49) for the columns the model consumes. */
+typedef struct {
+    int32_t               batch_size;
+    const void* const*    cat_data;     /* [n_cat]: int32[B] | float32[B] | uint8 bytes (strings) */
+    const int32_t* const* cat_offsets;  /* [n_cat]: int32[B+1] byte offsets for string columns, else NULL */
+    const float* const*   num_data;     /* [n_num]: float32[B] */
+    const float*          labels;       /* [B] 0/1 (rating >= cutoff, trainers/ml_100k.py:48); NULL for forward */
+} dfm_raw_batch;
+
+typedef struct dfm_handle dfm_handle;
+
+/* Build a model instance: replaces graph construction inside model_fn (trainers/deep_fm.py:36-125).
+ * Tables are zero-initialised; load weights with dfm_set_tensor or dfm_init_random. */
+int dfm_create(const dfm_config* cfg, dfm_handle** out);
+void dfm_destroy(dfm_handle* h);
+const char* dfm_last_error(const dfm_handle* h);   /* h may be NULL: last dfm_create failure */
+
+/* Variable access = tf.train.Saver / checkpoint surface (trainers/conf_utils.py:6-10).
+ * Names: "emb" [R,k], "lin" [R], "num_emb" [dn,k], "num_lin" [dn], "bias" [1], "W<i>" [in,out],
+ * "b<i>" [out], "Wo" [h,1], "bo" [1]; optimizer slots "<name>/m", "<name>/v" (Adam),
+ * "<name>/acc" (Adagrad, FTRL), "<name>/lin" (FTRL).  R = sum of the per-field bucket counts,
+ * fields concatenated in model order.  Row ranges are in elements of the leading dimension.
+ * dfm_get_tensor materialises any deferred non-lazy-Adam work first (dfm_flush). */
+int dfm_tensor_rows(dfm_handle* h, const char* name, int64_t* rows, int64_t* row_elems);
+int dfm_set_tensor(dfm_handle* h, const char* name, int64_t row_begin, int64_t n_rows, const float* host_src);
+int dfm_get_tensor(dfm_handle* h, const char* name, int64_t row_begin, int64_t n_rows, float* host_dst);
+/* reference initialisers run on the device: tables truncated-normal(0, 1/sqrt(k)),
+ * dense kernels glorot-uniform, linear + biases zero.  Own counter-based generator. */
+int dfm_init_random(dfm_handle* h, uint64_t seed);
+
+/* K1 alone: feature-column transforms (hash / bucketize / vocab / identity) -> ids [B, n_cat]
+ * int32, -1 = empty bag.  Device pointers.  Replaces the _transform_feature calls under
+ * tf.feature_column.linear_model / input_layer (trainers/deep_fm.py:39,54). */
+int dfm_transform(dfm_handle* h, const dfm_raw_batch* dev_batch, int32_t* ids_out_dev, void* stream);
+
+/* One session.run(train_op) (trainers/deep_fm.py:119-125): forward, sigmoid-CE loss, backward,
+ * sparse + dense optimizer apply, global_step += 1.  loss_out_dev [1], logits_out_dev [B] or NULL. */
+int dfm_train_step(dfm_handle* h, const dfm_raw_batch* dev_batch, float* loss_out_dev,
+                   float* logits_out_dev, void* stream);
+/* Same, from host buffers (pinned preferred): H2D of the raw columns, the step, D2H of the loss
+ * (and logits if non-NULL).  Returns after the loss is on the host. */
+int dfm_train_step_host(dfm_handle* h, const dfm_raw_batch* host_batch, float* loss_out_host,
+                        float* logits_out_host);
+/* Pipelined variant: enqueue step i, return the loss of the previously enqueued step in
+ * *prev_loss_host (NaN on the first call).  dfm_train_step_host_drain waits for the last one. */
+int dfm_train_step_host_async(dfm_handle* h, const dfm_raw_batch* host_batch, float* prev_loss_host);
+int dfm_train_step_host_drain(dfm_handle* h, float* last_loss_host);
+
+/* mode == EVAL / PREDICT: logits only, no state change (device pointers). */
+int dfm_forward(dfm_handle* h, const dfm_raw_batch* dev_batch, float* logits_out_dev, void* stream);
+int dfm_forward_host(dfm_handle* h, const dfm_raw_batch* host_batch, float* logits_out_host);
+
+/* Materialise deferred non-lazy Adam decay on every table row (before checkpoint / compare). */
+int dfm_flush(dfm_handle* h, void* stream);
+/* Wait for the handle's work and report sticky device-side errors (e.g. DFM_ERR_OUT_OF_RANGE). */
+int dfm_sync(dfm_handle* h);
+
+int64_t dfm_global_step(const dfm_handle* h);
+/* number of kernels the last train step launched (bench.py's gpu_launches) */
+int64_t dfm_last_step_launches(const dfm_handle* h);
+/* device time (ms) spent in the named phase during the last *timed* step; enable with
+ * dfm_set_profiling(h, 1).  Phases: "transform","sort","segments","catchup","gather","mlp_fwd",
+ * "loss","mlp_bwd","reduce","update","dense". Returns <0 if unknown. */
+int dfm_set_profiling(dfm_handle* h, int32_t on);
+float dfm_phase_ms(dfm_handle* h, const char* phase);
+
+/* Building-block entry points used by the parity tests (device pointers, synchronous). */
+int dfm_test_sort_pairs(uint32_t* keys_dev, uint32_t* vals_dev, int64_t n, int32_t key_bits);
+int dfm_test_fingerprint64(const uint8_t* bytes_dev, const int32_t* offsets_dev, int64_t n,
+                           uint64_t* out_dev);
+
+const char* dfm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* DEEPFM_B200_H_ */

@@ -1,0 +1,1044 @@
+// libdeepfm_b200: C ABI (include/deepfm_b200.h) + step orchestration.
+// One handle = one model instance (tables, optimizer slots, dense tower, workspaces) on one device.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "dfm_types.cuh"
+#include "embed_kernels.cuh"
+#include "mlp_kernels.cuh"
+#include "prims.cuh"
+
+static thread_local std::string g_create_error;
+
+struct DenseT {
+    std::string name;
+    int64_t off, rows, cols;
+};
+
+struct HostStage {          // one in-flight host batch (double buffered)
+    uint8_t* d_arena = nullptr;
+    size_t   cap = 0;
+    cudaEvent_t copied = nullptr, done = nullptr;
+    float*   h_loss = nullptr;   // pinned
+    bool     busy = false;
+};
+
+struct dfm_handle {
+    int dc = 0, dn = 0, K = 0, L = 0;
+    int hidden[DFM_MAX_HIDDEN] = {0};
+    int use_linear = 1, use_mf = 1, use_dnn = 1, need_emb = 1, loss_red = 0;
+    dfm_optimizer od{}, ol{};
+    int max_batch = 0, device = 0, rank = 0, world = 1;
+    std::vector<ColDev> cols;
+    std::vector<std::string> col_names;
+    std::vector<uint32_t> row_off;   // [dc+1]
+    uint64_t R = 0;
+    int key_bits = 1;
+    int emb_slots = 2, emb_stride = 0;
+
+    ColDev* d_cols = nullptr; float* d_bounds = nullptr; uint8_t* d_voc_bytes = nullptr; int32_t* d_voc_offs = nullptr;
+    uint32_t* d_row_off = nullptr;
+    float* emb_rec = nullptr; float4* lin_rec = nullptr;
+
+    std::vector<DenseT> dense;
+    int64_t n_deep = 0, n_dense = 0;
+    float *dw = nullptr, *ds1 = nullptr, *ds2 = nullptr, *dg = nullptr;
+
+    // workspaces
+    int32_t* ids = nullptr;
+    uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
+    void* sort_temp = nullptr;
+    unsigned long long* flags = nullptr; void* scan_temp = nullptr; unsigned long long* seg_total = nullptr;
+    SegCounts* seg_cnt = nullptr;
+    uint32_t *row_start = nullptr, *row_piece0 = nullptr, *piece_start = nullptr, *piece_row = nullptr;
+    float* piece_sum = nullptr;
+    float *h0 = nullptr, *s = nullptr, *zacc = nullptr, *logits = nullptr, *dz = nullptr, *dE = nullptr;
+    float* act[DFM_MAX_HIDDEN + 1] = {nullptr};
+    float* dact[DFM_MAX_HIDDEN + 1] = {nullptr};
+    float* splitk = nullptr; int splits = 1, k_chunk = 0;
+    float* colpart = nullptr; int rows_per_chunk = 512;
+    float* head_part = nullptr; int head_blocks = 0;
+    float* d_loss = nullptr; float* d_dzsum = nullptr;
+    int* d_err = nullptr;
+
+    // step state
+    int64_t step = 0, flushed_step = 0;
+    float b1p_d = 1.f, b2p_d = 1.f, b1p_l = 1.f, b2p_l = 1.f;
+    float *alpha_d = nullptr, *alpha_l = nullptr; int64_t alpha_cap = 0;
+
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    HostStage stage[2];
+    int64_t host_calls = 0; int last_slot = -1;
+    float* h_logits_pinned = nullptr;
+
+    int64_t launches = 0, last_step_launches = 0;
+    bool profiling = false;
+    static constexpr int NPH = 11;
+    cudaEvent_t ph_ev[NPH + 1] = {nullptr};
+    float ph_ms[NPH] = {0};
+    std::string err;
+    int sm_count = 148;
+};
+
+static const char* kPhases[dfm_handle::NPH] = {"transform", "sort", "segments", "catchup", "gather", "mlp_fwd",
+                                               "loss", "mlp_bwd", "reduce", "update", "dense"};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            if (h) h->err = buf_; else g_create_error = buf_;                                      \
+            return DFM_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+#define FAIL(code, msg)                                        \
+    do {                                                       \
+        if (h) h->err = (msg); else g_create_error = (msg);    \
+        return (code);                                         \
+    } while (0)
+
+static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+static int opt_slots(int kind) { return kind == DFM_OPT_ADAM ? 2 : kind == DFM_OPT_ADAGRAD ? 1 : kind == DFM_OPT_FTRL ? 2 : 0; }
+
+static OptDev make_opt(const dfm_optimizer& o, float b1p, float b2p) {
+    OptDev d{};
+    d.kind = o.kind; d.lr = o.lr; d.b1 = o.beta1; d.b2 = o.beta2; d.eps = o.eps;
+    d.omb1 = 1.0f - o.beta1;
+    d.omb2 = 1.0f - o.beta2;
+    d.alpha = 0.f;
+    if (o.kind == DFM_OPT_ADAM) d.alpha = o.lr * sqrtf(1.0f - b2p) / (1.0f - b1p);   // float32 like TF
+    d.safe_early = (o.kind == DFM_OPT_ADAM && o.beta1 < 0.95f * sqrtf(o.beta2)) ? 1 : 0;
+    return d;
+}
+
+template <typename T>
+static int dalloc(dfm_handle* h, T** p, size_t count) {
+    CK(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T)));
+    return DFM_OK;
+}
+
+// ------------------------------------------------------------------------------------- create
+extern "C" const char* dfm_version(void) { return "deepfm_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* dfm_last_error(const dfm_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+static int64_t pad32(int64_t x) { return (x + 31) / 32 * 32; }
+
+static void free_all(dfm_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    void* ptrs[] = {h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, h->d_row_off, h->emb_rec, h->lin_rec, h->dw,
+                    h->ds1, h->ds2, h->dg, h->ids, h->keys[0], h->keys[1], h->vals[0], h->vals[1], h->sort_temp, h->flags,
+                    h->scan_temp, h->seg_total, h->seg_cnt, h->row_start, h->row_piece0, h->piece_start, h->piece_row,
+                    h->piece_sum, h->h0, h->s, h->zacc, h->logits, h->dz, h->dE, h->splitk, h->colpart, h->head_part,
+                    h->d_loss, h->d_dzsum, h->d_err, h->alpha_d, h->alpha_l};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (int i = 1; i <= DFM_MAX_HIDDEN; ++i) { if (h->act[i]) cudaFree(h->act[i]); if (h->dact[i]) cudaFree(h->dact[i]); }
+    for (auto& s : h->stage) {
+        if (s.d_arena) cudaFree(s.d_arena);
+        if (s.copied) cudaEventDestroy(s.copied);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.h_loss) cudaFreeHost(s.h_loss);
+    }
+    if (h->h_logits_pinned) cudaFreeHost(h->h_logits_pinned);
+    for (auto& e : h->ph_ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h;
+}
+
+extern "C" void dfm_destroy(dfm_handle* h) { free_all(h); }
+
+static int create_impl(const dfm_config* cfg, dfm_handle* h) {
+    if (cfg->n_cat < 0 || cfg->n_cat > DFM_MAX_CAT || cfg->n_num < 0 || cfg->n_num > DFM_MAX_NUM)
+        FAIL(DFM_ERR_INVALID_ARG, "too many feature columns");
+    // trainers/deep_fm.py:31-34
+    if (cfg->n_cat + cfg->n_num == 0)
+        FAIL(DFM_ERR_INVALID_ARG, "At least 1 feature column of categorical_columns or numeric_columns must be specified.");
+    if (!(cfg->use_linear || cfg->use_mf || cfg->use_dnn))
+        FAIL(DFM_ERR_INVALID_ARG, "At least 1 of linear, mf or dnn component must be used.");
+    const int K = cfg->embedding_size;
+    if (K < 4 || K > 128 || (K % 4) != 0 || (128 % K) != 0)
+        FAIL(DFM_ERR_UNSUPPORTED, "embedding_size must be one of 4, 8, 16, 32, 64, 128");
+    if (cfg->n_hidden < 0 || cfg->n_hidden > DFM_MAX_HIDDEN) FAIL(DFM_ERR_INVALID_ARG, "too many hidden layers");
+    if (cfg->max_batch <= 0) FAIL(DFM_ERR_INVALID_ARG, "max_batch must be positive");
+    if (cfg->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "row-sharded mode is not built into this library version");
+    h->dc = cfg->n_cat; h->dn = cfg->n_num; h->K = K; h->L = cfg->use_dnn ? cfg->n_hidden : 0;
+    for (int i = 0; i < h->L; ++i) {
+        if (cfg->hidden_units[i] <= 0) FAIL(DFM_ERR_INVALID_ARG, "hidden_units must be positive");
+        h->hidden[i] = cfg->hidden_units[i];
+    }
+    h->use_linear = cfg->use_linear != 0; h->use_mf = cfg->use_mf != 0; h->use_dnn = cfg->use_dnn != 0;
+    h->need_emb = h->use_mf || h->use_dnn;
+    h->loss_red = cfg->loss_reduction;
+    h->od = cfg->opt_deep; h->ol = cfg->opt_linear;
+    for (const dfm_optimizer* o : {&h->od, &h->ol})
+        if (o->kind < DFM_OPT_ADAM || o->kind > DFM_OPT_SGD) FAIL(DFM_ERR_INVALID_ARG, "unknown optimizer kind");
+    h->max_batch = cfg->max_batch; h->device = cfg->device; h->rank = cfg->rank; h->world = std::max(1, cfg->world);
+    CK(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    h->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+
+    // ---- columns
+    std::vector<float> bounds;
+    std::vector<uint8_t> voc_bytes;
+    std::vector<int32_t> voc_offs;
+    h->row_off.assign(h->dc + 1, 0);
+    uint64_t R = 0;
+    for (int f = 0; f < h->dc; ++f) {
+        const dfm_column& c = cfg->cat[f];
+        ColDev d{};
+        d.kind = c.kind; d.dtype = c.dtype;
+        uint64_t nb = 0;
+        switch (c.kind) {
+            case DFM_COL_HASH:
+                if (c.num_buckets <= 0) FAIL(DFM_ERR_INVALID_ARG, "hash column needs num_buckets > 0");
+                if (c.dtype == DFM_FLOAT32) FAIL(DFM_ERR_UNSUPPORTED, "hash column over float32 keys");
+                nb = (uint64_t)c.num_buckets;
+                break;
+            case DFM_COL_IDENTITY:
+                if (c.num_buckets <= 0) FAIL(DFM_ERR_INVALID_ARG, "identity column needs num_buckets > 0");
+                if (c.dtype != DFM_INT32) FAIL(DFM_ERR_UNSUPPORTED, "identity column needs int32 input");
+                nb = (uint64_t)c.num_buckets;
+                break;
+            case DFM_COL_BUCKETIZED:
+                if (c.dtype == DFM_STRING) FAIL(DFM_ERR_INVALID_ARG, "bucketized column needs numeric input");
+                d.bnd_off = (int)bounds.size(); d.bnd_cnt = c.n_boundaries;
+                for (int j = 0; j < c.n_boundaries; ++j) bounds.push_back(c.boundaries[j]);
+                nb = (uint64_t)c.n_boundaries + 1;
+                break;
+            case DFM_COL_VOCAB:
+                if (c.dtype != DFM_STRING) FAIL(DFM_ERR_UNSUPPORTED, "vocabulary column needs string input");
+                d.voc_off = (int)voc_offs.size(); d.voc_cnt = c.vocab_size; d.num_oov = c.num_oov;
+                for (int j = 0; j < c.vocab_size; ++j) {
+                    voc_offs.push_back((int32_t)voc_bytes.size());
+                    size_t len = strlen(c.vocab[j]);
+                    voc_bytes.insert(voc_bytes.end(), c.vocab[j], c.vocab[j] + len);
+                }
+                voc_offs.push_back((int32_t)voc_bytes.size());
+                nb = (uint64_t)c.vocab_size + (uint64_t)c.num_oov;
+                break;
+            default: FAIL(DFM_ERR_INVALID_ARG, "unknown column kind");
+        }
+        d.nb = nb;
+        h->cols.push_back(d);
+        h->col_names.push_back(c.name ? c.name : "");
+        if (R > 0xffffffffull) FAIL(DFM_ERR_UNSUPPORTED, "more than 2^32 table rows on one device");
+        h->row_off[f] = (uint32_t)R;
+        R += nb;
+    }
+    if (R >= 0xfffffff0ull) FAIL(DFM_ERR_UNSUPPORTED, "more than 2^32 table rows on one device");
+    h->row_off[h->dc] = (uint32_t)R;
+    h->R = R;
+    h->key_bits = 1;
+    while ((1ull << h->key_bits) <= R) ++h->key_bits;   // keys take values 0..R
+    if (dalloc(h, &h->d_cols, h->cols.size())) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->d_bounds, bounds.size())) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->d_voc_bytes, voc_bytes.size())) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->d_voc_offs, voc_offs.size())) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->d_row_off, h->row_off.size())) return DFM_ERR_CUDA;
+    if (!h->cols.empty()) CK(cudaMemcpy(h->d_cols, h->cols.data(), h->cols.size() * sizeof(ColDev), cudaMemcpyHostToDevice));
+    if (!bounds.empty()) CK(cudaMemcpy(h->d_bounds, bounds.data(), bounds.size() * 4, cudaMemcpyHostToDevice));
+    if (!voc_bytes.empty()) CK(cudaMemcpy(h->d_voc_bytes, voc_bytes.data(), voc_bytes.size(), cudaMemcpyHostToDevice));
+    if (!voc_offs.empty()) CK(cudaMemcpy(h->d_voc_offs, voc_offs.data(), voc_offs.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_row_off, h->row_off.data(), h->row_off.size() * 4, cudaMemcpyHostToDevice));
+
+    // ---- tables: emb_rec [R][1+S][K], lin_rec [R] float4 {w, s1, s2, last_step}
+    h->emb_slots = opt_slots(h->od.kind);
+    h->emb_stride = (1 + h->emb_slots) * K;
+    const size_t Ralloc = std::max<uint64_t>(R, 1);
+    if (h->need_emb) {
+        if (dalloc(h, &h->emb_rec, Ralloc * h->emb_stride)) return DFM_ERR_CUDA;
+        CK(cudaMemset(h->emb_rec, 0, Ralloc * h->emb_stride * 4));
+    }
+    if (dalloc(h, &h->lin_rec, Ralloc)) return DFM_ERR_CUDA;
+    CK(cudaMemset(h->lin_rec, 0, Ralloc * sizeof(float4)));
+
+    // ---- dense parameters, packed: deep group first, then the linear group
+    const int d = h->dc + h->dn, dK = d * K;
+    int64_t off = 0;
+    auto add = [&](const std::string& nm, int64_t rows, int64_t cols) {
+        h->dense.push_back({nm, off, rows, cols});
+        off += pad32(rows * cols);
+    };
+    if (h->need_emb && h->dn) add("num_emb", h->dn, K);
+    if (h->use_dnn) {
+        int in = dK;
+        for (int i = 0; i < h->L; ++i) {
+            add("W" + std::to_string(i), in, h->hidden[i]);
+            add("b" + std::to_string(i), h->hidden[i], 1);
+            in = h->hidden[i];
+        }
+        add("Wo", in, 1);
+        add("bo", 1, 1);
+    }
+    h->n_deep = off;
+    if (h->use_linear) {
+        if (h->dn) add("num_lin", h->dn, 1);
+        add("bias", 1, 1);
+    }
+    h->n_dense = off;
+    for (float** p : {&h->dw, &h->ds1, &h->ds2, &h->dg}) {
+        if (dalloc(h, p, (size_t)h->n_dense)) return DFM_ERR_CUDA;
+        CK(cudaMemset(*p, 0, std::max<int64_t>(h->n_dense, 1) * 4));
+    }
+
+    // ---- workspaces
+    const int64_t Bm = h->max_batch, n = Bm * std::max(h->dc, 1);
+    if (n >= (1ll << 31)) FAIL(DFM_ERR_UNSUPPORTED, "max_batch * n_cat must be < 2^31");
+    if (dalloc(h, &h->ids, n)) return DFM_ERR_CUDA;
+    for (int i = 0; i < 2; ++i) { if (dalloc(h, &h->keys[i], n)) return DFM_ERR_CUDA; if (dalloc(h, &h->vals[i], n)) return DFM_ERR_CUDA; }
+    CK(cudaMalloc(&h->sort_temp, prims::sort_temp_bytes(n)));
+    if (dalloc(h, &h->flags, n)) return DFM_ERR_CUDA;
+    CK(cudaMalloc(&h->scan_temp, prims::scan_temp_bytes(n, 8) + 64));
+    if (dalloc(h, &h->seg_total, 1)) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->seg_cnt, 1)) return DFM_ERR_CUDA;
+    CK(cudaMemset(h->seg_cnt, 0, sizeof(SegCounts)));
+    if (dalloc(h, &h->row_start, n + 1)) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->row_piece0, n + 1)) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->piece_start, n + 1)) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->piece_row, n)) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->piece_sum, (size_t)(2 * (n / 32 + 2)) * (K + 4))) return DFM_ERR_CUDA;
+    if (h->need_emb) {
+        if (dalloc(h, &h->h0, Bm * dK)) return DFM_ERR_CUDA;
+        if (dalloc(h, &h->s, Bm * K)) return DFM_ERR_CUDA;
+        if (dalloc(h, &h->dE, Bm * dK)) return DFM_ERR_CUDA;
+    }
+    if (dalloc(h, &h->zacc, Bm)) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->logits, Bm)) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->dz, Bm)) return DFM_ERR_CUDA;
+    h->act[0] = h->h0;
+    int64_t max_w = 1, max_n = std::max<int64_t>(dK, 1);
+    {
+        int in = dK;
+        for (int i = 0; i < h->L; ++i) {
+            if (dalloc(h, &h->act[i + 1], Bm * h->hidden[i])) return DFM_ERR_CUDA;
+            if (dalloc(h, &h->dact[i + 1], Bm * h->hidden[i])) return DFM_ERR_CUDA;
+            max_w = std::max<int64_t>(max_w, (int64_t)in * h->hidden[i]);
+            max_n = std::max<int64_t>(max_n, h->hidden[i]);
+            in = h->hidden[i];
+        }
+    }
+    h->splits = (int)std::min<int64_t>(64, std::max<int64_t>(1, (Bm + 1023) / 1024));
+    if (dalloc(h, &h->splitk, (size_t)h->splits * max_w)) return DFM_ERR_CUDA;
+    const int64_t chunks = (Bm + h->rows_per_chunk - 1) / h->rows_per_chunk;
+    if (dalloc(h, &h->colpart, (size_t)chunks * std::max<int64_t>(max_n, (int64_t)h->dn * (K + 1)))) return DFM_ERR_CUDA;
+    h->head_blocks = (int)std::min<int64_t>(h->sm_count * 8, std::max<int64_t>(1, (Bm + 7) / 8));
+    if (dalloc(h, &h->head_part, (size_t)h->head_blocks * 2)) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->d_loss, 1)) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->d_dzsum, 1)) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->d_err, 1)) return DFM_ERR_CUDA;
+    CK(cudaMemset(h->d_err, 0, 4));
+    h->alpha_cap = 1 << 16;
+    if (dalloc(h, &h->alpha_d, (size_t)h->alpha_cap)) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->alpha_l, (size_t)h->alpha_cap)) return DFM_ERR_CUDA;
+    CK(cudaMemset(h->alpha_d, 0, h->alpha_cap * 4));
+    CK(cudaMemset(h->alpha_l, 0, h->alpha_cap * 4));
+    for (auto& s : h->stage) {
+        CK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        CK(cudaMallocHost(&s.h_loss, 64));
+    }
+    for (auto& e : h->ph_ev) CK(cudaEventCreate(&e));
+    CK(cudaFuncSetAttribute(transform_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * DFM_MAX_CAT * 4));
+
+    // optimizer slot initial values (Adagrad / FTRL accumulators start at init_acc)
+    auto init_acc = [&](const dfm_optimizer& o) { return (o.kind == DFM_OPT_ADAGRAD || o.kind == DFM_OPT_FTRL) ? o.init_acc : 0.f; };
+    if (init_acc(h->od) != 0.f) {
+        if (h->need_emb && R)
+            fill_strided_kernel<<<cdiv((int64_t)R * K, 256), 256, 0, h->stream>>>(h->emb_rec + K, R, K, h->emb_stride, init_acc(h->od));
+        if (h->n_deep) fill_strided_kernel<<<cdiv(h->n_deep, 256), 256, 0, h->stream>>>(h->ds1, 1, (int)h->n_deep, 0, init_acc(h->od));
+    }
+    if (init_acc(h->ol) != 0.f) {
+        if (R) fill_strided_kernel<<<cdiv((int64_t)R, 256), 256, 0, h->stream>>>(reinterpret_cast<float*>(h->lin_rec) + 1, R, 1, 4, init_acc(h->ol));
+        if (h->n_dense > h->n_deep)
+            fill_strided_kernel<<<cdiv(h->n_dense - h->n_deep, 256), 256, 0, h->stream>>>(h->ds1 + h->n_deep, 1, (int)(h->n_dense - h->n_deep), 0, init_acc(h->ol));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+extern "C" int dfm_create(const dfm_config* cfg, dfm_handle** out) {
+    g_create_error.clear();
+    if (!cfg || !out) { g_create_error = "null argument"; return DFM_ERR_INVALID_ARG; }
+    *out = nullptr;
+    dfm_handle* h = new dfm_handle();
+    int rc = create_impl(cfg, h);
+    if (rc != DFM_OK) {
+        g_create_error = h->err;
+        free_all(h);
+        return rc;
+    }
+    *out = h;
+    return DFM_OK;
+}
+
+// ------------------------------------------------------------------------------ tensor access
+struct TensorRef {
+    float* base; int64_t rows, row_elems, pitch;   // pitch in floats
+};
+
+static bool resolve(dfm_handle* h, const std::string& full, TensorRef& t) {
+    std::string name = full, slot;
+    size_t p = full.find('/');
+    if (p != std::string::npos) { name = full.substr(0, p); slot = full.substr(p + 1); }
+    auto slot_index = [&](int kind) -> int {
+        if (slot.empty()) return 0;
+        if (kind == DFM_OPT_ADAM) return slot == "m" ? 1 : slot == "v" ? 2 : -1;
+        if (kind == DFM_OPT_ADAGRAD) return slot == "acc" ? 1 : -1;
+        if (kind == DFM_OPT_FTRL) return slot == "acc" ? 1 : slot == "lin" ? 2 : -1;
+        return -1;
+    };
+    if (name == "emb") {
+        if (!h->need_emb) return false;
+        int si = slot_index(h->od.kind);
+        if (si < 0) return false;
+        t = {h->emb_rec + (int64_t)si * h->K, (int64_t)h->R, h->K, h->emb_stride};
+        return true;
+    }
+    if (name == "lin") {
+        if (!h->use_linear) return false;
+        int si = slot_index(h->ol.kind);
+        if (si < 0) return false;
+        t = {reinterpret_cast<float*>(h->lin_rec) + si, (int64_t)h->R, 1, 4};
+        return true;
+    }
+    for (const DenseT& dt : h->dense) {
+        if (dt.name != name) continue;
+        bool deep = dt.off < h->n_deep;
+        int si = slot_index(deep ? h->od.kind : h->ol.kind);
+        if (si < 0) return false;
+        float* b = si == 0 ? h->dw : si == 1 ? h->ds1 : h->ds2;
+        t = {b + dt.off, dt.rows, dt.cols, dt.cols};
+        return true;
+    }
+    return false;
+}
+
+extern "C" int dfm_tensor_rows(dfm_handle* h, const char* name, int64_t* rows, int64_t* row_elems) {
+    if (!h || !name) return DFM_ERR_INVALID_ARG;
+    TensorRef t;
+    if (!resolve(h, name, t)) FAIL(DFM_ERR_NOT_FOUND, std::string("no tensor named ") + name);
+    if (rows) *rows = t.rows;
+    if (row_elems) *row_elems = t.row_elems;
+    return DFM_OK;
+}
+
+extern "C" int dfm_flush(dfm_handle* h, void* stream);
+
+extern "C" int dfm_set_tensor(dfm_handle* h, const char* name, int64_t row_begin, int64_t n_rows, const float* src) {
+    if (!h || !name || !src) return DFM_ERR_INVALID_ARG;
+    TensorRef t;
+    if (!resolve(h, name, t)) FAIL(DFM_ERR_NOT_FOUND, std::string("no tensor named ") + name);
+    if (row_begin < 0 || n_rows < 0 || row_begin + n_rows > t.rows) FAIL(DFM_ERR_INVALID_ARG, "row range out of bounds");
+    CK(cudaSetDevice(h->device));
+    int rc = dfm_flush(h, h->stream);   // rows must be current before they are overwritten piecewise
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    if (n_rows)
+        CK(cudaMemcpy2D(t.base + row_begin * t.pitch, t.pitch * 4, src, t.row_elems * 4, t.row_elems * 4, n_rows, cudaMemcpyHostToDevice));
+    return DFM_OK;
+}
+
+extern "C" int dfm_get_tensor(dfm_handle* h, const char* name, int64_t row_begin, int64_t n_rows, float* dst) {
+    if (!h || !name || !dst) return DFM_ERR_INVALID_ARG;
+    TensorRef t;
+    if (!resolve(h, name, t)) FAIL(DFM_ERR_NOT_FOUND, std::string("no tensor named ") + name);
+    if (row_begin < 0 || n_rows < 0 || row_begin + n_rows > t.rows) FAIL(DFM_ERR_INVALID_ARG, "row range out of bounds");
+    CK(cudaSetDevice(h->device));
+    int rc = dfm_flush(h, h->stream);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    if (n_rows)
+        CK(cudaMemcpy2D(dst, t.row_elems * 4, t.base + row_begin * t.pitch, t.pitch * 4, t.row_elems * 4, n_rows, cudaMemcpyDeviceToHost));
+    return DFM_OK;
+}
+
+extern "C" int dfm_init_random(dfm_handle* h, uint64_t seed) {
+    if (!h) return DFM_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    if (h->need_emb && h->R) {
+        uint64_t tot = h->R * (uint64_t)h->K;
+        init_trunc_normal_kernel<<<cdiv((int64_t)tot, 256), 256, 0, st>>>(h->emb_rec, h->R, h->K, h->emb_stride,
+                                                                          1.0f / sqrtf((float)h->K), seed * 0x9E3779B97F4A7C15ULL + 1);
+    }
+    int idx = 0;
+    for (const DenseT& dt : h->dense) {
+        ++idx;
+        bool kernel = dt.name[0] == 'W' || dt.name == "num_emb";
+        if (!kernel) continue;   // biases, linear weights: zeros
+        float fan_in = (float)dt.rows, fan_out = (float)dt.cols;
+        float lim = sqrtf(6.0f / (fan_in + fan_out));
+        init_uniform_kernel<<<cdiv(dt.rows * dt.cols, 256), 256, 0, st>>>(h->dw + dt.off, dt.rows * dt.cols, lim, seed * 0xD1B54A32D192ED03ULL + idx);
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+// -------------------------------------------------------------------------------- step pieces
+static BatchPtrs make_ptrs(const dfm_handle* h, const dfm_raw_batch* b) {
+    BatchPtrs bp{};
+    for (int f = 0; f < h->dc; ++f) {
+        bp.cat[f] = b->cat_data ? b->cat_data[f] : nullptr;
+        bp.off[f] = b->cat_offsets ? b->cat_offsets[f] : nullptr;
+    }
+    for (int j = 0; j < h->dn; ++j) bp.num[j] = b->num_data ? b->num_data[j] : nullptr;
+    bp.labels = b->labels;
+    return bp;
+}
+
+static int check_batch(dfm_handle* h, const dfm_raw_batch* b, bool need_labels) {
+    if (!b) FAIL(DFM_ERR_INVALID_ARG, "null batch");
+    if (b->batch_size <= 0 || b->batch_size > h->max_batch) FAIL(DFM_ERR_INVALID_ARG, "batch_size outside (0, max_batch]");
+    if (h->dc && !b->cat_data) FAIL(DFM_ERR_INVALID_ARG, "cat_data is null");
+    for (int f = 0; f < h->dc; ++f) {
+        if (!b->cat_data[f]) FAIL(DFM_ERR_INVALID_ARG, "missing feature column: " + h->col_names[f]);
+        if (h->cols[f].dtype == DFM_STRING && (!b->cat_offsets || !b->cat_offsets[f]))
+            FAIL(DFM_ERR_INVALID_ARG, "missing string offsets for column: " + h->col_names[f]);
+    }
+    if (h->dn && !b->num_data) FAIL(DFM_ERR_INVALID_ARG, "num_data is null");
+    for (int j = 0; j < h->dn; ++j)
+        if (!b->num_data[j]) FAIL(DFM_ERR_INVALID_ARG, "missing numeric column");
+    if (need_labels && !b->labels) FAIL(DFM_ERR_INVALID_ARG, "labels are required for a train step");
+    return DFM_OK;
+}
+
+struct Phase {
+    dfm_handle* h; cudaStream_t st; int idx = 0;
+    Phase(dfm_handle* h_, cudaStream_t s) : h(h_), st(s) { if (h->profiling) cudaEventRecord(h->ph_ev[0], st); }
+    void next() { ++idx; if (h->profiling && idx <= dfm_handle::NPH) cudaEventRecord(h->ph_ev[idx], st); }
+};
+
+template <int K>
+static void launch_transform(dfm_handle* h, const BatchPtrs& bp, int B, bool with_keys, int32_t* ids_out, cudaStream_t st) {
+    if (h->dc == 0) return;
+    transform_kernel<128><<<cdiv(B, 128), 128, (size_t)128 * h->dc * 4, st>>>(
+        bp, h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, B, h->dc, h->d_row_off, (uint32_t)h->R, ids_out,
+        with_keys ? h->keys[0] : nullptr, with_keys ? h->vals[0] : nullptr, h->d_err);
+    h->launches++;
+}
+
+template <int K>
+static void launch_gather(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t st) {
+    float* num_emb = nullptr; float* num_lin = nullptr; float* bias = nullptr;
+    for (const DenseT& dt : h->dense) {
+        if (dt.name == "num_emb") num_emb = h->dw + dt.off;
+        if (dt.name == "num_lin") num_lin = h->dw + dt.off;
+        if (dt.name == "bias") bias = h->dw + dt.off;
+    }
+    unsigned grid = std::min<unsigned>(cdiv(B, 8), (unsigned)h->sm_count * 16);
+    gather_fm_kernel<K><<<grid, 256, 0, st>>>(h->ids, B, h->dc, h->dn, h->d_row_off, h->emb_rec, h->emb_stride, h->lin_rec, bp,
+                                              num_emb, num_lin, bias, h->use_linear, h->use_mf, h->need_emb, h->h0, h->s, h->zacc);
+    h->launches++;
+}
+
+static const DenseT* find_dense(const dfm_handle* h, const std::string& nm) {
+    for (const DenseT& dt : h->dense) if (dt.name == nm) return &dt;
+    return nullptr;
+}
+
+static bool vec_ok(const void* a, int lda, const void* b, int ldb, const void* c, int ldc) {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return al(a) && al(b) && al(c) && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0;
+}
+
+template <bool A_KC, bool B_KC, int EPI>
+static void launch_sgemm(dfm_handle* h, const float* A, int lda, const float* Bm, int ldb, float* C, int ldc, int M, int N, int Kd,
+                         int splits, int k_chunk, const EpiArgs& ep, cudaStream_t st) {
+    dim3 grid(cdiv(N, 128), cdiv(M, 128), splits);
+    size_t stride = (size_t)M * ldc;
+    if (vec_ok(A, lda, Bm, ldb, C, ldc) && k_chunk % 4 == 0)
+        sgemm_kernel<A_KC, B_KC, EPI, true><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, C, ldc, M, N, Kd, k_chunk, stride, ep);
+    else
+        sgemm_kernel<A_KC, B_KC, EPI, false><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, C, ldc, M, N, Kd, k_chunk, stride, ep);
+    h->launches++;
+}
+
+// out[N] = sum_b w[b] * X[b, :]  (deterministic two-level)
+static void launch_colsum(dfm_handle* h, const float* X, int ldx, const float* w, int B, int N, float* out, cudaStream_t st) {
+    int chunks = (int)cdiv(B, h->rows_per_chunk);
+    colsum_partial_kernel<<<dim3(cdiv(N, 32), chunks), 256, 0, st>>>(X, ldx, w, B, N, h->rows_per_chunk, h->colpart);
+    reduce_partials_kernel<<<cdiv(N, 256), 256, 0, st>>>(h->colpart, chunks, (size_t)N, N, out);
+    h->launches += 2;
+}
+
+static int ensure_alpha(dfm_handle* h, int64_t t) {
+    if (t + 2 < h->alpha_cap) return DFM_OK;
+    int64_t ncap = h->alpha_cap * 2;
+    while (t + 2 >= ncap) ncap *= 2;
+    CK(cudaStreamSynchronize(h->stream));
+    for (float** p : {&h->alpha_d, &h->alpha_l}) {
+        float* np = nullptr;
+        CK(cudaMalloc(&np, ncap * 4));
+        CK(cudaMemset(np, 0, ncap * 4));
+        CK(cudaMemcpy(np, *p, h->alpha_cap * 4, cudaMemcpyDeviceToDevice));
+        CK(cudaFree(*p));
+        *p = np;
+    }
+    h->alpha_cap = ncap;
+    return DFM_OK;
+}
+
+static bool any_adam(const dfm_handle* h) {
+    return (h->need_emb && h->od.kind == DFM_OPT_ADAM) || (h->use_linear && h->ol.kind == DFM_OPT_ADAM);
+}
+
+template <int K>
+static int flush_impl(dfm_handle* h, cudaStream_t st) {
+    if (!any_adam(h) || h->flushed_step == h->step || h->R == 0) { h->flushed_step = h->step; return DFM_OK; }
+    OptDev od = make_opt(h->od, h->b1p_d, h->b2p_d), ol = make_opt(h->ol, h->b1p_l, h->b2p_l);
+    unsigned grid = (unsigned)std::min<uint64_t>((h->R + (256 / (K / 4)) - 1) / (256 / (K / 4)), (uint64_t)h->sm_count * 16);
+    catchup_all_kernel<K><<<grid, 256, 0, st>>>(h->emb_rec, h->lin_rec, h->R, (int)h->step, h->alpha_d, h->alpha_l, od, ol,
+                                                (bool)h->need_emb, (bool)h->use_linear);
+    h->launches++;
+    CK(cudaGetLastError());
+    h->flushed_step = h->step;
+    return DFM_OK;
+}
+
+template <int K>
+static int forward_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t st, const float* labels, float scale,
+                        float* logits_out, Phase* ph) {
+    const int d = h->dc + h->dn, dK = d * K;
+    launch_gather<K>(h, bp, B, st);
+    if (ph) ph->next();
+    const float* hL = nullptr; int H = 0;
+    const DenseT* Wo = find_dense(h, "Wo"); const DenseT* bo = find_dense(h, "bo");
+    if (h->use_dnn) {
+        int in = dK;
+        for (int i = 0; i < h->L; ++i) {
+            const DenseT* W = find_dense(h, "W" + std::to_string(i));
+            const DenseT* b = find_dense(h, "b" + std::to_string(i));
+            EpiArgs ep{}; ep.bias = h->dw + b->off;
+            launch_sgemm<true, false, EPI_BIAS_RELU>(h, h->act[i], in, h->dw + W->off, h->hidden[i], h->act[i + 1], h->hidden[i], B,
+                                                     h->hidden[i], in, 1, (in + 15) / 16 * 16, ep, st);
+            in = h->hidden[i];
+        }
+        hL = h->act[h->L]; H = in;
+    }
+    if (ph) ph->next();
+    head_kernel<<<h->head_blocks, 256, 0, st>>>((h->use_linear || h->use_mf) ? h->zacc : nullptr, hL, H, Wo ? h->dw + Wo->off : nullptr,
+                                                bo ? h->dw + bo->off : nullptr, labels, B, scale, h->logits, logits_out, h->dz, h->head_part);
+    h->launches++;
+    return DFM_OK;
+}
+
+template <int K>
+static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out, float* logits_out, cudaStream_t st) {
+    const int dc = h->dc, d = dc + h->dn, dK = d * K;
+    const int64_t n = (int64_t)B * dc;
+    const int64_t t = h->step + 1;
+    int rc = ensure_alpha(h, t);
+    if (rc) return rc;
+    const int64_t l0 = h->launches;
+    // beta powers as seen by step t (TF multiplies them after each apply, starting from beta)
+    const float b1p_d = h->b1p_d * h->od.beta1, b2p_d = h->b2p_d * h->od.beta2;
+    const float b1p_l = h->b1p_l * h->ol.beta1, b2p_l = h->b2p_l * h->ol.beta2;
+    const OptDev od = make_opt(h->od, b1p_d, b2p_d), ol = make_opt(h->ol, b1p_l, b2p_l);
+    Phase ph(h, st);
+
+    // K1 transform
+    launch_transform<K>(h, bp, B, true, h->ids, st);
+    ph.next();
+    // sort by global row
+    int cur = 0;
+    if (n > 0) cur = prims::radix_sort_pairs(h->keys, h->vals, n, h->key_bits, h->sort_temp, st, &h->launches);
+    const uint32_t* skeys = h->keys[cur];
+    const uint32_t* svals = h->vals[cur];
+    ph.next();
+    // segments
+    if (n > 0) {
+        seg_flag_kernel<<<cdiv(n, 256), 256, 0, st>>>(skeys, n, (uint32_t)h->R, h->flags, h->seg_cnt);
+        h->launches++;
+        prims::exclusive_scan_u64(reinterpret_cast<const uint64_t*>(h->flags), reinterpret_cast<uint64_t*>(h->flags), n, h->scan_temp,
+                                  reinterpret_cast<uint64_t*>(h->seg_total), st, &h->launches);
+        seg_fill_kernel<<<cdiv(n, 256), 256, 0, st>>>(skeys, n, (uint32_t)h->R, h->flags, h->seg_total, h->seg_cnt, h->row_start,
+                                                      h->row_piece0, h->piece_start, h->piece_row);
+        h->launches++;
+    }
+    ph.next();
+    const unsigned row_grid = (unsigned)h->sm_count * 8;
+    // non-lazy Adam: bring the touched rows up to step t-1
+    if (n > 0 && any_adam(h) && t > 1) {
+        const OptDev pod = make_opt(h->od, h->b1p_d, h->b2p_d), pol = make_opt(h->ol, h->b1p_l, h->b2p_l);
+        catchup_touched_kernel<K><<<row_grid, 256, 0, st>>>(h->emb_rec, h->lin_rec, skeys, h->row_start, h->seg_cnt, (int)(t - 1),
+                                                            h->alpha_d, h->alpha_l, pod, pol, (bool)h->need_emb, (bool)h->use_linear);
+        h->launches++;
+    }
+    ph.next();
+    // forward
+    const float scale = h->loss_red == DFM_LOSS_MEAN ? 1.0f / (float)B : 1.0f;
+    rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, &ph);
+    if (rc) return rc;
+    const DenseT* bo = find_dense(h, "bo"); const DenseT* bias = find_dense(h, "bias");
+    head_final_kernel<<<1, 256, 0, st>>>(h->head_part, h->head_blocks, scale, h->d_loss, h->d_dzsum);
+    h->launches++;
+    if (loss_out) CK(cudaMemcpyAsync(loss_out, h->d_loss, 4, cudaMemcpyDeviceToDevice, st));
+    if (bo) CK(cudaMemcpyAsync(h->dg + bo->off, h->d_dzsum, 4, cudaMemcpyDeviceToDevice, st));
+    if (bias) CK(cudaMemcpyAsync(h->dg + bias->off, h->d_dzsum, 4, cudaMemcpyDeviceToDevice, st));
+    ph.next();
+    // backward through the tower
+    if (h->use_dnn) {
+        const DenseT* Wo = find_dense(h, "Wo");
+        const int L = h->L;
+        const float* hL = h->act[L];
+        const int H = L ? h->hidden[L - 1] : dK;
+        launch_colsum(h, hL, H, h->dz, B, H, h->dg + Wo->off, st);   // gWo = h_L^T dz
+        if (L == 0) {
+            dh_last_kernel<<<cdiv((int64_t)B * H, 256), 256, 0, st>>>(nullptr, h->dw + Wo->off, h->dz, (int64_t)B * H, H, h->dE);
+            h->launches++;
+            if (h->use_mf) {
+                de_fm_kernel<<<cdiv((int64_t)B * dK, 256), 256, 0, st>>>(h->h0, h->s, h->dz, (int64_t)B * dK, dK, K, h->dE, 1);
+                h->launches++;
+            }
+        } else {
+            dh_last_kernel<<<cdiv((int64_t)B * H, 256), 256, 0, st>>>(hL, h->dw + Wo->off, h->dz, (int64_t)B * H, H, h->dact[L]);
+            h->launches++;
+            const int splits = std::max(1, std::min(h->splits, (B + 1023) / 1024));
+            const int k_chunk = ((B + splits - 1) / splits + 15) / 16 * 16;
+            const int nsplit = (B + k_chunk - 1) / k_chunk;
+            for (int i = L - 1; i >= 0; --i) {
+                const int in = i ? h->hidden[i - 1] : dK, out = h->hidden[i];
+                const DenseT* W = find_dense(h, "W" + std::to_string(i));
+                const DenseT* b = find_dense(h, "b" + std::to_string(i));
+                // gW_i [in,out] = act_i^T [in,B] * dh_{i+1} [B,out]   (deterministic split over the batch)
+                EpiArgs none{};
+                launch_sgemm<false, false, EPI_NONE>(h, h->act[i], in, h->dact[i + 1], out, h->splitk, out, in, out, B, nsplit, k_chunk, none, st);
+                reduce_partials_kernel<<<cdiv((int64_t)in * out, 256), 256, 0, st>>>(h->splitk, nsplit, (size_t)in * out, (int64_t)in * out,
+                                                                                     h->dg + W->off);
+                h->launches++;
+                launch_colsum(h, h->dact[i + 1], out, nullptr, B, out, h->dg + b->off, st);
+                // dh_i [B,in] = dh_{i+1} [B,out] * W_i^T
+                if (i > 0) {
+                    EpiArgs ep{}; ep.act = h->act[i]; ep.ld_act = in;
+                    launch_sgemm<true, true, EPI_MASK>(h, h->dact[i + 1], out, h->dw + W->off, out, h->dact[i], in, B, in, out, 1,
+                                                       (out + 15) / 16 * 16, ep, st);
+                } else {
+                    EpiArgs ep{}; ep.act = h->h0; ep.ld_act = dK; ep.dz = h->dz; ep.s = h->use_mf ? h->s : nullptr; ep.K = K;
+                    launch_sgemm<true, true, EPI_DE>(h, h->dact[1], out, h->dw + W->off, out, h->dE, dK, B, dK, out, 1,
+                                                     (out + 15) / 16 * 16, ep, st);
+                }
+            }
+        }
+    } else if (h->use_mf) {
+        de_fm_kernel<<<cdiv((int64_t)B * dK, 256), 256, 0, st>>>(h->h0, h->s, h->dz, (int64_t)B * dK, dK, K, h->dE, 0);
+        h->launches++;
+    }
+    // numeric-feature gradients
+    if (h->dn) {
+        const DenseT* ne = find_dense(h, "num_emb"); const DenseT* nl = find_dense(h, "num_lin");
+        const int chunks = (int)cdiv(B, h->rows_per_chunk), total = h->dn * K + h->dn;
+        numeric_grad_partial_kernel<<<chunks, 256, 0, st>>>(bp, h->need_emb ? h->dE : nullptr, dK, dc, h->dn, K, h->dz, B, h->rows_per_chunk, h->colpart);
+        h->launches++;
+        if (ne) { reduce_partials_kernel<<<cdiv(h->dn * K, 256), 256, 0, st>>>(h->colpart, chunks, (size_t)total, h->dn * K, h->dg + ne->off); h->launches++; }
+        if (nl) { reduce_partials_kernel<<<1, 256, 0, st>>>(h->colpart + h->dn * K, chunks, (size_t)total, h->dn, h->dg + nl->off); h->launches++; }
+    }
+    ph.next();
+    // sparse gradients: sorted segmented reduction + optimizer
+    GradSrc<K> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK};
+    if (n > 0) {
+        piece_reduce_kernel<K><<<row_grid, 256, 0, st>>>(svals, h->piece_start, h->piece_row, h->row_start, h->seg_cnt, src, h->piece_sum);
+        h->launches++;
+    }
+    ph.next();
+    row_update_kernel<K><<<n > 0 ? row_grid : 1, 256, 0, st>>>(skeys, svals, h->row_start, h->row_piece0, h->piece_start, h->seg_cnt, src,
+                                                               h->piece_sum, h->emb_rec, h->emb_slots, h->lin_rec, od, ol, (bool)h->need_emb,
+                                                               (bool)h->use_linear, (int)t, h->alpha_d, h->alpha_l);
+    h->launches++;
+    ph.next();
+    if (h->n_dense) {
+        dense_apply_kernel<<<cdiv(h->n_dense, 256), 256, 0, st>>>(h->dw, h->ds1, h->ds2, h->dg, h->n_deep, h->n_dense, od, ol);
+        h->launches++;
+    }
+    ph.next();
+    CK(cudaGetLastError());
+    h->step = t;
+    h->b1p_d = b1p_d; h->b2p_d = b2p_d; h->b1p_l = b1p_l; h->b2p_l = b2p_l;
+    h->last_step_launches = h->launches - l0;
+    return DFM_OK;
+}
+
+#define DISPATCH_K(h, CALL)                                          \
+    switch ((h)->K) {                                                \
+        case 4: { constexpr int KK = 4; CALL; } break;               \
+        case 8: { constexpr int KK = 8; CALL; } break;               \
+        case 16: { constexpr int KK = 16; CALL; } break;             \
+        case 32: { constexpr int KK = 32; CALL; } break;             \
+        case 64: { constexpr int KK = 64; CALL; } break;             \
+        default: { constexpr int KK = 128; CALL; } break;            \
+    }
+
+// ------------------------------------------------------------------------- device entry points
+extern "C" int dfm_flush(dfm_handle* h, void* stream) {
+    if (!h) return DFM_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    int rc = DFM_OK;
+    DISPATCH_K(h, rc = flush_impl<KK>(h, st));
+    return rc;
+}
+
+extern "C" int dfm_transform(dfm_handle* h, const dfm_raw_batch* b, int32_t* ids_out, void* stream) {
+    if (!h || !ids_out) return DFM_ERR_INVALID_ARG;
+    int rc = check_batch(h, b, false);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    BatchPtrs bp = make_ptrs(h, b);
+    launch_transform<4>(h, bp, b->batch_size, false, ids_out, st);
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+extern "C" int dfm_train_step(dfm_handle* h, const dfm_raw_batch* b, float* loss_out, float* logits_out, void* stream) {
+    if (!h) return DFM_ERR_INVALID_ARG;
+    int rc = check_batch(h, b, true);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    BatchPtrs bp = make_ptrs(h, b);
+    DISPATCH_K(h, rc = train_impl<KK>(h, bp, b->batch_size, loss_out, logits_out, st));
+    return rc;
+}
+
+extern "C" int dfm_forward(dfm_handle* h, const dfm_raw_batch* b, float* logits_out, void* stream) {
+    if (!h || !logits_out) return DFM_ERR_INVALID_ARG;
+    int rc = check_batch(h, b, false);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    BatchPtrs bp = make_ptrs(h, b);
+    bp.labels = nullptr;
+    DISPATCH_K(h, rc = flush_impl<KK>(h, st));
+    if (rc) return rc;
+    launch_transform<4>(h, bp, b->batch_size, false, h->ids, st);
+    DISPATCH_K(h, rc = forward_impl<KK>(h, bp, b->batch_size, st, nullptr, 1.f, logits_out, nullptr));
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+extern "C" int dfm_sync(dfm_handle* h) {
+    if (!h) return DFM_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->copy_stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int e = 0;
+    CK(cudaMemcpy(&e, h->d_err, 4, cudaMemcpyDeviceToHost));
+    if (h->profiling) {
+        for (int i = 0; i < dfm_handle::NPH; ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, h->ph_ev[i], h->ph_ev[i + 1]) == cudaSuccess) h->ph_ms[i] = ms;
+            else cudaGetLastError();
+        }
+    }
+    if (e) {
+        CK(cudaMemset(h->d_err, 0, 4));
+        FAIL(DFM_ERR_OUT_OF_RANGE, "identity column value outside [0, num_buckets)");
+    }
+    return DFM_OK;
+}
+
+extern "C" int64_t dfm_global_step(const dfm_handle* h) { return h ? h->step : -1; }
+extern "C" int64_t dfm_last_step_launches(const dfm_handle* h) { return h ? h->last_step_launches : -1; }
+extern "C" int dfm_set_profiling(dfm_handle* h, int32_t on) { if (!h) return DFM_ERR_INVALID_ARG; h->profiling = on != 0; return DFM_OK; }
+extern "C" float dfm_phase_ms(dfm_handle* h, const char* phase) {
+    if (!h || !phase) return -1.f;
+    for (int i = 0; i < dfm_handle::NPH; ++i) if (!strcmp(phase, kPhases[i])) return h->ph_ms[i];
+    return -1.f;
+}
+
+// --------------------------------------------------------------------------- host entry points
+// Copies the raw columns of a host batch into the stage's device arena.  When the caller laid the
+// columns out back to back in one (pinned) allocation this is a single cudaMemcpyAsync.
+static int stage_batch(dfm_handle* h, const dfm_raw_batch* b, HostStage& sg, bool need_labels, BatchPtrs& out, size_t* h2d_bytes) {
+    struct Seg { const uint8_t* p; size_t bytes; const void** dst; };
+    std::vector<Seg> segs;
+    const int B = b->batch_size;
+    out = BatchPtrs{};
+    for (int f = 0; f < h->dc; ++f) {
+        if (h->cols[f].dtype == DFM_STRING) {
+            const int32_t* off = b->cat_offsets[f];
+            segs.push_back({reinterpret_cast<const uint8_t*>(off), (size_t)(B + 1) * 4, reinterpret_cast<const void**>(&out.off[f])});
+            size_t nbytes = (size_t)off[B];
+            segs.push_back({reinterpret_cast<const uint8_t*>(b->cat_data[f]), std::max<size_t>(nbytes, 1), &out.cat[f]});
+        } else {
+            segs.push_back({reinterpret_cast<const uint8_t*>(b->cat_data[f]), (size_t)B * 4, &out.cat[f]});
+        }
+    }
+    for (int j = 0; j < h->dn; ++j)
+        segs.push_back({reinterpret_cast<const uint8_t*>(b->num_data[j]), (size_t)B * 4, reinterpret_cast<const void**>(&out.num[j])});
+    if (need_labels) segs.push_back({reinterpret_cast<const uint8_t*>(b->labels), (size_t)B * 4, reinterpret_cast<const void**>(&out.labels)});
+    const uint8_t* lo = nullptr; const uint8_t* hi = nullptr; size_t sum = 0;
+    for (const Seg& s : segs) {
+        if (!lo || s.p < lo) lo = s.p;
+        if (!hi || s.p + s.bytes > hi) hi = s.p + s.bytes;
+        sum += (s.bytes + 255) / 256 * 256;
+    }
+    const size_t span = (size_t)(hi - lo);
+    const bool contiguous = span <= sum + 4096;
+    const size_t need = contiguous ? span + 256 : sum + 256;
+    if (sg.cap < need) {
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaStreamSynchronize(h->copy_stream));
+        if (sg.d_arena) CK(cudaFree(sg.d_arena));
+        sg.cap = need + need / 4;
+        CK(cudaMalloc(&sg.d_arena, sg.cap));
+    }
+    size_t bytes = 0;
+    if (contiguous) {
+        // keep the 16-byte phase of the host layout so aligned columns stay aligned
+        size_t phase = reinterpret_cast<uintptr_t>(lo) & 255;
+        CK(cudaMemcpyAsync(sg.d_arena + phase, lo, span, cudaMemcpyHostToDevice, h->copy_stream));
+        for (const Seg& s : segs) *s.dst = sg.d_arena + phase + (s.p - lo);
+        bytes = span;
+    } else {
+        size_t o = 0;
+        for (const Seg& s : segs) {
+            CK(cudaMemcpyAsync(sg.d_arena + o, s.p, s.bytes, cudaMemcpyHostToDevice, h->copy_stream));
+            *s.dst = sg.d_arena + o;
+            o += (s.bytes + 255) / 256 * 256;
+            bytes += s.bytes;
+        }
+    }
+    if (h2d_bytes) *h2d_bytes = bytes;
+    return DFM_OK;
+}
+
+static int enqueue_host_step(dfm_handle* h, const dfm_raw_batch* b, int slot) {
+    HostStage& sg = h->stage[slot];
+    if (sg.busy) { CK(cudaEventSynchronize(sg.done)); sg.busy = false; }
+    BatchPtrs bp;
+    int rc = stage_batch(h, b, sg, true, bp, nullptr);
+    if (rc) return rc;
+    CK(cudaEventRecord(sg.copied, h->copy_stream));
+    CK(cudaStreamWaitEvent(h->stream, sg.copied, 0));
+    DISPATCH_K(h, rc = train_impl<KK>(h, bp, b->batch_size, nullptr, nullptr, h->stream));
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(sg.h_loss, h->d_loss, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(sg.done, h->stream));
+    sg.busy = true;
+    return DFM_OK;
+}
+
+extern "C" int dfm_train_step_host_async(dfm_handle* h, const dfm_raw_batch* b, float* prev_loss) {
+    if (!h) return DFM_ERR_INVALID_ARG;
+    int rc = check_batch(h, b, true);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const int slot = (int)(h->host_calls & 1);
+    const int prev = h->last_slot;
+    rc = enqueue_host_step(h, b, slot);
+    if (rc) return rc;
+    h->host_calls++;
+    h->last_slot = slot;
+    if (prev_loss) {
+        if (prev >= 0 && prev != slot) {
+            CK(cudaEventSynchronize(h->stage[prev].done));
+            h->stage[prev].busy = false;
+            *prev_loss = *h->stage[prev].h_loss;
+        } else {
+            *prev_loss = NAN;
+        }
+    }
+    return DFM_OK;
+}
+
+extern "C" int dfm_train_step_host_drain(dfm_handle* h, float* last_loss) {
+    if (!h) return DFM_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (h->last_slot < 0) { if (last_loss) *last_loss = NAN; return DFM_OK; }
+    HostStage& sg = h->stage[h->last_slot];
+    CK(cudaEventSynchronize(sg.done));
+    sg.busy = false;
+    if (last_loss) *last_loss = *sg.h_loss;
+    h->last_slot = -1;
+    return DFM_OK;
+}
+
+extern "C" int dfm_train_step_host(dfm_handle* h, const dfm_raw_batch* b, float* loss_out, float* logits_out) {
+    if (!h) return DFM_ERR_INVALID_ARG;
+    int rc = check_batch(h, b, true);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const int slot = (int)(h->host_calls & 1);
+    rc = enqueue_host_step(h, b, slot);
+    if (rc) return rc;
+    h->host_calls++;
+    h->last_slot = -1;
+    if (logits_out) CK(cudaMemcpyAsync(logits_out, h->logits, (size_t)b->batch_size * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stage[slot].busy = false;
+    if (loss_out) *loss_out = *h->stage[slot].h_loss;
+    return DFM_OK;
+}
+
+extern "C" int dfm_forward_host(dfm_handle* h, const dfm_raw_batch* b, float* logits_out) {
+    if (!h || !logits_out) return DFM_ERR_INVALID_ARG;
+    int rc = check_batch(h, b, false);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    HostStage& sg = h->stage[0];
+    if (sg.busy) { CK(cudaEventSynchronize(sg.done)); sg.busy = false; }
+    CK(cudaStreamSynchronize(h->stream));
+    BatchPtrs bp;
+    rc = stage_batch(h, b, sg, false, bp, nullptr);
+    if (rc) return rc;
+    CK(cudaEventRecord(sg.copied, h->copy_stream));
+    CK(cudaStreamWaitEvent(h->stream, sg.copied, 0));
+    DISPATCH_K(h, rc = flush_impl<KK>(h, h->stream));
+    if (rc) return rc;
+    launch_transform<4>(h, bp, b->batch_size, false, h->ids, h->stream);
+    DISPATCH_K(h, rc = forward_impl<KK>(h, bp, b->batch_size, h->stream, nullptr, 1.f, nullptr, nullptr));
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(logits_out, h->logits, (size_t)b->batch_size * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+// ------------------------------------------------------------------- building-block test hooks
+extern "C" int dfm_test_sort_pairs(uint32_t* keys_dev, uint32_t* vals_dev, int64_t n, int32_t key_bits) {
+    dfm_handle* h = nullptr;
+    if (n <= 0) return DFM_OK;
+    uint32_t *k[2] = {keys_dev, nullptr}, *v[2] = {vals_dev, nullptr};
+    void* temp = nullptr;
+    CK(cudaMalloc(&k[1], n * 4));
+    CK(cudaMalloc(&v[1], n * 4));
+    CK(cudaMalloc(&temp, prims::sort_temp_bytes(n)));
+    int cur = prims::radix_sort_pairs(k, v, n, key_bits, temp, 0, nullptr);
+    if (cur == 1) {
+        CK(cudaMemcpyAsync(keys_dev, k[1], n * 4, cudaMemcpyDeviceToDevice, 0));
+        CK(cudaMemcpyAsync(vals_dev, v[1], n * 4, cudaMemcpyDeviceToDevice, 0));
+    }
+    CK(cudaDeviceSynchronize());
+    cudaFree(k[1]); cudaFree(v[1]); cudaFree(temp);
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+extern "C" int dfm_test_fingerprint64(const uint8_t* bytes_dev, const int32_t* offsets_dev, int64_t n, uint64_t* out_dev) {
+    dfm_handle* h = nullptr;
+    if (n <= 0) return DFM_OK;
+    fingerprint_kernel<<<cdiv(n, 256), 256>>>(bytes_dev, offsets_dev, n, out_dev);
+    CK(cudaDeviceSynchronize());
+    CK(cudaGetLastError());
+    return DFM_OK;
+}

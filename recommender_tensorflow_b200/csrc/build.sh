@@ -1,0 +1,12 @@
+#!/bin/bash
+# Builds libdeepfm_b200.so in-tree for sm_100a (called by __graft_entry__.build()).
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall"
+mkdir -p build
+$NVCC $FLAGS -c prims.cu -o build/prims.o &
+$NVCC $FLAGS -c api.cu -o build/api.o &
+wait
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libdeepfm_b200.so build/prims.o build/api.o -lcudart
+echo "built $(cd .. && pwd)/libdeepfm_b200.so"

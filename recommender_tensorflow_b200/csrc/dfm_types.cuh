@@ -1,0 +1,45 @@
+// Internal device/host shared types of libdeepfm_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/deepfm_b200.h"
+
+struct ColDev {
+    int32_t  kind, dtype;
+    uint64_t nb;            // bucket count used for the modulo (hash) / range check (identity)
+    int32_t  bnd_off, bnd_cnt;
+    int32_t  voc_off, voc_cnt, num_oov, pad;
+};
+
+// raw batch as kernel parameter (pointer tables by value: no H2D copy of pointer arrays)
+struct BatchPtrs {
+    const void*    cat[DFM_MAX_CAT];
+    const int32_t* off[DFM_MAX_CAT];
+    const float*   num[DFM_MAX_NUM];
+    const float*   labels;
+};
+
+// optimizer constants as seen by one step
+struct OptDev {
+    int32_t kind;
+    float   lr, b1, b2, eps;
+    float   omb1, omb2;     // (1 - beta) evaluated in float32 like TF
+    float   alpha;          // Adam: lr * sqrt(1 - b2^t) / (1 - b1^t) for the current step
+    int32_t safe_early;     // Adam replay may stop once the update no longer changes w
+};
+
+// segment bookkeeping produced by the sort stage
+struct SegCounts {
+    uint32_t n_rows;     // unique table rows touched by the batch
+    uint32_t n_pieces;   // sorted array cut at row changes and multiples of PIECE_C
+    uint32_t n_valid;    // lookups that are not empty bags
+    uint32_t pad;
+};
+
+constexpr int PIECE_C = 256;      // max entries per piece
+constexpr int DIRECT_T = 32;      // rows with <= DIRECT_T lookups are summed directly in the update kernel
+
+// piece -> slot in the piece-sum buffer (collision free for pieces of rows with > DIRECT_T lookups)
+__host__ __device__ __forceinline__ uint32_t piece_slot(uint32_t head_pos) {
+    return (head_pos >> 5) * 2u + ((head_pos % PIECE_C) == 0 ? 0u : 1u);
+}

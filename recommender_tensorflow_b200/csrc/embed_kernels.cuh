@@ -1,0 +1,544 @@
+// Input-path, embedding/linear lookup, FM interaction, sparse-gradient reduction and sparse
+// optimizer kernels (K1, K2, K5, K6 of SURVEY.md §8a).  Hand-written for sm_100a.
+#pragma once
+#include "dfm_types.cuh"
+#include "farmhash.cuh"
+
+// =============================================================================================
+// optimizer arithmetic, in the float32 op order of the TF-1.12 kernels
+// =============================================================================================
+__device__ __forceinline__ float adam_upd(float m, float v, float alpha, float eps) {
+    return __fdiv_rn(__fmul_rn(alpha, m), __fadd_rn(__fsqrt_rn(v), eps));
+}
+// python/training/adam.py::_apply_sparse_shared on one (already de-duplicated) touched element
+__device__ __forceinline__ void adam_sparse_apply(float& w, float& m, float& v, float g, const OptDev& o) {
+    m = __fadd_rn(__fmul_rn(m, o.b1), __fmul_rn(g, o.omb1));
+    v = __fadd_rn(__fmul_rn(v, o.b2), __fmul_rn(__fmul_rn(g, g), o.omb2));
+    w = __fsub_rn(w, adam_upd(m, v, o.alpha, o.eps));
+}
+// core/kernels/training_ops.cc ApplyAdam (dense)
+__device__ __forceinline__ void adam_dense_apply(float& w, float& m, float& v, float g, const OptDev& o) {
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), o.omb1));
+    v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), o.omb2));
+    w = __fsub_rn(w, __fdiv_rn(__fmul_rn(m, o.alpha), __fadd_rn(__fsqrt_rn(v), o.eps)));
+}
+// Adagrad / FTRL(lr_power=-0.5, l1=l2=0) / SGD.  s1 = accumulator, s2 = FTRL "linear" slot.
+__device__ __forceinline__ void other_apply(float& w, float& s1, float& s2, float g, const OptDev& o) {
+    if (o.kind == DFM_OPT_ADAGRAD) {
+        s1 = __fadd_rn(s1, __fmul_rn(g, g));
+        w = __fsub_rn(w, __fdiv_rn(__fmul_rn(o.lr, g), __fsqrt_rn(s1)));
+    } else if (o.kind == DFM_OPT_FTRL) {
+        float na = __fadd_rn(s1, __fmul_rn(g, g));
+        float sna = __fsqrt_rn(na), sa = __fsqrt_rn(s1);
+        float t1 = __fadd_rn(s2, g);
+        float t2 = __fmul_rn(__fdiv_rn(__fsub_rn(sna, sa), o.lr), w);
+        s2 = __fsub_rn(t1, t2);
+        w = __fdiv_rn(-s2, __fdiv_rn(sna, o.lr));
+        s1 = na;
+    } else {  // SGD
+        w = __fsub_rn(w, __fmul_rn(o.lr, g));
+    }
+}
+__device__ __forceinline__ void sparse_apply(float& w, float& s1, float& s2, float g, const OptDev& o) {
+    if (o.kind == DFM_OPT_ADAM) adam_sparse_apply(w, s1, s2, g, o);
+    else other_apply(w, s1, s2, g, o);
+}
+__device__ __forceinline__ void dense_apply(float& w, float& s1, float& s2, float g, const OptDev& o) {
+    if (o.kind == DFM_OPT_ADAM) adam_dense_apply(w, s1, s2, g, o);
+    else other_apply(w, s1, s2, g, o);
+}
+
+// TF's AdamOptimizer applies `m *= b1; v *= b2; w -= alpha_t m/(sqrt(v)+eps)` to EVERY row at every
+// step (non-lazy, SURVEY.md §7 hard part 1).  A row whose last materialised step is `last` is
+// brought up to step `upto` by replaying exactly those skipped steps in registers.  alpha[] holds
+// the per-step alpha_t history.  Once an update is too small to change w in float32 all later ones
+// are too (|update| shrinks by >= 8% per step), so the loop stops early and only m, v keep decaying.
+__device__ __forceinline__ void adam_replay(float& w, float& m, float& v, int last, int upto,
+                                            const float* __restrict__ alpha, const OptDev& o) {
+    if (m == 0.f && v == 0.f) return;
+    int tau = last + 1;
+    for (; tau <= upto; ++tau) {
+        m = __fmul_rn(m, o.b1);
+        v = __fmul_rn(v, o.b2);
+        float wn = __fsub_rn(w, adam_upd(m, v, __ldg(alpha + tau), o.eps));
+        bool same = (wn == w);
+        w = wn;
+        if (same && o.safe_early) { ++tau; break; }
+    }
+    int rem = upto - tau + 1;
+    if (rem > 0) {
+        if (rem <= 256) {
+            for (int j = 0; j < rem; ++j) { m = __fmul_rn(m, o.b1); v = __fmul_rn(v, o.b2); }
+        } else {
+            m = (float)((double)m * pow((double)o.b1, (double)rem));
+            v = (float)((double)v * pow((double)o.b2, (double)rem));
+        }
+    }
+}
+
+// =============================================================================================
+// K1: feature-column transforms -> ids [B, dc] + sort keys (global row index) + payload
+// =============================================================================================
+__device__ __forceinline__ int32_t transform_one(const BatchPtrs& bp, const ColDev& c, int f, int b,
+                                                 const float* __restrict__ bounds,
+                                                 const uint8_t* __restrict__ voc_bytes,
+                                                 const int32_t* __restrict__ voc_offs, int* err) {
+    switch (c.kind) {
+        case DFM_COL_HASH: {
+            if (c.dtype == DFM_STRING) {
+                const int32_t* off = bp.off[f];
+                int s = off[b], e = off[b + 1];
+                int len = e - s;
+                if (len <= 0) return -1;
+                uint64_t h = fh::fp64_mem(reinterpret_cast<const uint8_t*>(bp.cat[f]) + s, len);
+                return (int32_t)(h % c.nb);
+            } else {
+                int32_t v = reinterpret_cast<const int32_t*>(bp.cat[f])[b];
+                if (v == -1) return -1;
+                uint64_t lo, hi;
+                int len = fh::itoa16(v, lo, hi);
+                return (int32_t)(fh::fp64_short(lo, hi, len) % c.nb);
+            }
+        }
+        case DFM_COL_BUCKETIZED: {
+            float x = c.dtype == DFM_FLOAT32 ? reinterpret_cast<const float*>(bp.cat[f])[b]
+                                             : (float)reinterpret_cast<const int32_t*>(bp.cat[f])[b];
+            int cnt = 0;
+            for (int j = 0; j < c.bnd_cnt; ++j) cnt += (bounds[c.bnd_off + j] <= x) ? 1 : 0;
+            return cnt;
+        }
+        case DFM_COL_VOCAB: {
+            const int32_t* off = bp.off[f];
+            int s = off[b], e = off[b + 1];
+            int len = e - s;
+            if (len <= 0) return -1;
+            const uint8_t* p = reinterpret_cast<const uint8_t*>(bp.cat[f]) + s;
+            for (int j = 0; j < c.voc_cnt; ++j) {
+                int vs = voc_offs[c.voc_off + j], ve = voc_offs[c.voc_off + j + 1];
+                if (ve - vs != len) continue;
+                bool eq = true;
+                for (int q = 0; q < len; ++q) eq = eq && (voc_bytes[vs + q] == p[q]);
+                if (eq) return j;
+            }
+            if (c.num_oov > 0) return c.voc_cnt + (int32_t)(fh::fp64_mem(p, len) % (uint64_t)c.num_oov);
+            return -1;
+        }
+        default: {  // identity
+            int32_t v = reinterpret_cast<const int32_t*>(bp.cat[f])[b];
+            if (v == -1) return -1;
+            if (v < 0 || (uint64_t)v >= c.nb) { atomicOr(err, 1); return -1; }
+            return v;
+        }
+    }
+}
+
+// One block = TILE consecutive samples.  Phase 1 walks the columns (coalesced column reads, the
+// column kind is uniform across the block), phase 2 writes ids / keys / payload sample-major.
+template <int TILE>
+__global__ void __launch_bounds__(TILE) transform_kernel(BatchPtrs bp, const ColDev* __restrict__ cols,
+                                                         const float* __restrict__ bounds,
+                                                         const uint8_t* __restrict__ voc_bytes,
+                                                         const int32_t* __restrict__ voc_offs, int B, int dc,
+                                                         const uint32_t* __restrict__ row_off, uint32_t R,
+                                                         int32_t* __restrict__ ids, uint32_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ vals, int* err) {
+    extern __shared__ int32_t sid[];  // [TILE][dc]
+    const int b0 = blockIdx.x * TILE;
+    const int b = b0 + threadIdx.x;
+    if (b < B) {
+        for (int f = 0; f < dc; ++f) {
+            ColDev c = cols[f];
+            sid[threadIdx.x * dc + f] = transform_one(bp, c, f, b, bounds, voc_bytes, voc_offs, err);
+        }
+    }
+    __syncthreads();
+    const int nloc = min(TILE, B - b0) * dc;
+    const int64_t g0 = (int64_t)b0 * dc;
+    for (int w = threadIdx.x; w < nloc; w += TILE) {
+        int32_t id = sid[w];
+        int f = w % dc;
+        ids[g0 + w] = id;
+        if (keys) {
+            keys[g0 + w] = id >= 0 ? row_off[f] + (uint32_t)id : R;
+            vals[g0 + w] = (uint32_t)(g0 + w);
+        }
+    }
+}
+
+// keys/payload from precomputed ids (used when the caller supplies ids directly)
+__global__ void keys_from_ids_kernel(const int32_t* __restrict__ ids, int64_t n, int dc,
+                                     const uint32_t* __restrict__ row_off, uint32_t R,
+                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        int32_t id = ids[i];
+        keys[i] = id >= 0 ? row_off[i % dc] + (uint32_t)id : R;
+        vals[i] = (uint32_t)i;
+    }
+}
+
+__global__ void fingerprint_kernel(const uint8_t* __restrict__ bytes, const int32_t* __restrict__ offs, int64_t n,
+                                   uint64_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fh::fp64_mem(bytes + offs[i], offs[i + 1] - offs[i]);
+}
+
+// =============================================================================================
+// segments of the sorted (row, lookup) list
+// =============================================================================================
+__device__ __forceinline__ void seg_heads(const uint32_t* __restrict__ keys, int64_t i, uint32_t R, bool& rh, bool& ph) {
+    uint32_t k = keys[i];
+    uint32_t prev = i > 0 ? keys[i - 1] : 0xffffffffu;
+    bool valid = k < R;
+    rh = valid && (i == 0 || k != prev);
+    ph = valid && (rh || (i % PIECE_C) == 0);
+}
+
+__global__ void seg_flag_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t R,
+                                unsigned long long* __restrict__ flags, SegCounts* __restrict__ cnt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool rh, ph;
+    seg_heads(keys, i, R, rh, ph);
+    flags[i] = ((unsigned long long)(rh ? 1u : 0u) << 32) | (ph ? 1u : 0u);
+    uint32_t k = keys[i];
+    if (k >= R) {
+        if (i == 0 || keys[i - 1] < R) cnt->n_valid = (uint32_t)i;
+    } else if (i == n - 1) {
+        cnt->n_valid = (uint32_t)n;
+    }
+}
+
+__global__ void seg_fill_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t R,
+                                const unsigned long long* __restrict__ scanned,
+                                const unsigned long long* __restrict__ total, SegCounts* __restrict__ cnt,
+                                uint32_t* __restrict__ row_start, uint32_t* __restrict__ row_piece0,
+                                uint32_t* __restrict__ piece_start, uint32_t* __restrict__ piece_row) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        uint32_t U = (uint32_t)(*total >> 32), P = (uint32_t)(*total & 0xffffffffu);
+        uint32_t nv = cnt->n_valid;
+        cnt->n_rows = U;
+        cnt->n_pieces = P;
+        row_start[U] = nv;
+        row_piece0[U] = P;
+        piece_start[P] = nv;
+    }
+    if (i >= n) return;
+    bool rh, ph;
+    seg_heads(keys, i, R, rh, ph);
+    if (!ph) return;
+    unsigned long long s = scanned[i];
+    uint32_t ridx = (uint32_t)(s >> 32), pidx = (uint32_t)(s & 0xffffffffu);
+    piece_start[pidx] = (uint32_t)i;
+    piece_row[pidx] = rh ? ridx : ridx - 1;
+    if (rh) {
+        row_start[ridx] = (uint32_t)i;
+        row_piece0[ridx] = pidx;
+    }
+}
+
+// =============================================================================================
+// non-lazy Adam catch-up (exact deferred update) of the rows this batch touches, and full flush
+// =============================================================================================
+// table layout: emb_rec[row][1+S][K] floats (w | slot1 | slot2), lin_rec[row] = float4 {w, s1, s2, last_step bits}
+// The two optimizers share the step index, so the one last_step in lin_rec serves both tables.
+template <int K>
+__device__ __forceinline__ void catchup_group(float* __restrict__ emb_rec, float4* __restrict__ lin_rec, size_t row,
+                                              bool act, int sub, int upto, const float* __restrict__ alpha_d,
+                                              const float* __restrict__ alpha_l, const OptDev& od, const OptDev& ol,
+                                              bool has_emb, bool has_lin) {
+    constexpr int LPR = K / 4;
+    float4 lr = make_float4(0.f, 0.f, 0.f, 0.f);
+    int last = upto;
+    if (act) {
+        lr = lin_rec[row];
+        last = __float_as_int(lr.w);
+    }
+    const bool work = act && last < upto;
+    if (work && has_emb && od.kind == DFM_OPT_ADAM) {
+        float4* base = reinterpret_cast<float4*>(emb_rec + row * 3 * K) + sub;
+        float4 w = base[0], m = base[LPR], v = base[2 * LPR];
+        adam_replay(w.x, m.x, v.x, last, upto, alpha_d, od);
+        adam_replay(w.y, m.y, v.y, last, upto, alpha_d, od);
+        adam_replay(w.z, m.z, v.z, last, upto, alpha_d, od);
+        adam_replay(w.w, m.w, v.w, last, upto, alpha_d, od);
+        base[0] = w; base[LPR] = m; base[2 * LPR] = v;
+    }
+    __syncwarp();  // every lane of the group has read last_step before lane 0 rewrites it
+    if (work && sub == 0) {
+        if (has_lin && ol.kind == DFM_OPT_ADAM) adam_replay(lr.x, lr.y, lr.z, last, upto, alpha_l, ol);
+        lr.w = __int_as_float(upto);
+        lin_rec[row] = lr;
+    }
+}
+
+// rows touched by the current batch (unique list from the sort stage): bring them to step `upto`
+template <int K>
+__global__ void __launch_bounds__(256) catchup_touched_kernel(float* __restrict__ emb_rec, float4* __restrict__ lin_rec,
+                                                              const uint32_t* __restrict__ skeys,
+                                                              const uint32_t* __restrict__ row_start,
+                                                              const SegCounts* __restrict__ cnt, int upto,
+                                                              const float* __restrict__ alpha_d,
+                                                              const float* __restrict__ alpha_l, OptDev od, OptDev ol,
+                                                              bool has_emb, bool has_lin) {
+    constexpr int LPR = K / 4;
+    const int sub = threadIdx.x % LPR;
+    const uint32_t U = cnt->n_rows;
+    const uint32_t gpb = blockDim.x / LPR;
+    for (uint32_t base = blockIdx.x * gpb; base < U; base += gridDim.x * gpb) {  // block-uniform trip count
+        uint32_t u = base + threadIdx.x / LPR;
+        bool act = u < U;
+        size_t row = act ? (size_t)skeys[row_start[u]] : 0;
+        catchup_group<K>(emb_rec, lin_rec, row, act, sub, upto, alpha_d, alpha_l, od, ol, has_emb, has_lin);
+    }
+}
+
+// every row of the tables (dfm_flush)
+template <int K>
+__global__ void __launch_bounds__(256) catchup_all_kernel(float* __restrict__ emb_rec, float4* __restrict__ lin_rec,
+                                                          uint64_t R, int upto, const float* __restrict__ alpha_d,
+                                                          const float* __restrict__ alpha_l, OptDev od, OptDev ol,
+                                                          bool has_emb, bool has_lin) {
+    constexpr int LPR = K / 4;
+    const int sub = threadIdx.x % LPR;
+    const uint64_t gpb = blockDim.x / LPR;
+    for (uint64_t base = (uint64_t)blockIdx.x * gpb; base < R; base += (uint64_t)gridDim.x * gpb) {
+        uint64_t row = base + threadIdx.x / LPR;
+        catchup_group<K>(emb_rec, lin_rec, (size_t)row, row < R, sub, upto, alpha_d, alpha_l, od, ol, has_emb, has_lin);
+    }
+}
+
+// =============================================================================================
+// K2: fused embedding + linear gather, FM second-order term, first-order sum, input_layer write
+// =============================================================================================
+// One warp per sample; a table row of K floats is read by K/4 lanes as float4, so one warp round
+// covers 128/K fields and every h0 store is a fully coalesced 512-byte line.
+//   trainers/deep_fm.py:39     linear_model       -> zacc += sum_f w_f[id] + sum_j x_j wn_j + bias
+//   trainers/deep_fm.py:52-73  input_layer        -> h0[b, f*K..]
+//   trainers/deep_fm.py:79-87  FM                 -> zacc += 0.5 * sum_k((sum_f E)^2 - sum_f E^2)
+template <int K>
+__global__ void __launch_bounds__(256) gather_fm_kernel(const int32_t* __restrict__ ids, int B, int dc, int dn,
+                                                        const uint32_t* __restrict__ row_off,
+                                                        const float* __restrict__ emb_rec, int emb_stride,
+                                                        const float4* __restrict__ lin_rec, BatchPtrs bp,
+                                                        const float* __restrict__ num_emb,
+                                                        const float* __restrict__ num_lin,
+                                                        const float* __restrict__ bias, int use_linear, int use_mf,
+                                                        int need_emb, float* __restrict__ h0, float* __restrict__ s_out,
+                                                        float* __restrict__ zacc) {
+    constexpr int LPR = K / 4;       // lanes per row
+    constexpr int FPR = 32 / LPR;    // fields per warp round
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPR, grp = lane / LPR;
+    const int warps_per_block = blockDim.x >> 5;
+    const int d = dc + dn;
+    const float b0 = (use_linear && bias) ? bias[0] : 0.f;
+    for (int b = blockIdx.x * warps_per_block + (threadIdx.x >> 5); b < B; b += gridDim.x * warps_per_block) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+        float lin = 0.f;
+        const int32_t* idrow = ids + (int64_t)b * dc;
+        float4* hrow = reinterpret_cast<float4*>(h0 + (int64_t)b * d * K);
+        for (int f0 = 0; f0 < dc; f0 += FPR) {
+            int f = f0 + grp;
+            if (f < dc) {
+                int32_t id = idrow[f];
+                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (id >= 0) {
+                    size_t row = (size_t)row_off[f] + (uint32_t)id;
+                    if (need_emb) e = __ldg(reinterpret_cast<const float4*>(emb_rec + row * emb_stride) + sub);
+                    if (use_linear && sub == 0) lin += __ldg(reinterpret_cast<const float*>(lin_rec + row));
+                }
+                if (need_emb) {
+                    hrow[f * LPR + sub] = e;
+                    s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w;
+                    q.x += e.x * e.x; q.y += e.y * e.y; q.z += e.z * e.z; q.w += e.w * e.w;
+                }
+            }
+        }
+        for (int j0 = 0; j0 < dn; j0 += FPR) {
+            int j = j0 + grp;
+            if (j < dn) {
+                float x = __ldg(bp.num[j] + b);
+                if (need_emb) {
+                    float4 ve = __ldg(reinterpret_cast<const float4*>(num_emb + j * K) + sub);
+                    float4 e = make_float4(x * ve.x, x * ve.y, x * ve.z, x * ve.w);
+                    hrow[(dc + j) * LPR + sub] = e;
+                    s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w;
+                    q.x += e.x * e.x; q.y += e.y * e.y; q.z += e.z * e.z; q.w += e.w * e.w;
+                }
+                if (use_linear && sub == 0) lin += x * __ldg(num_lin + j);
+            }
+        }
+        // combine the FPR field groups (fixed butterfly -> deterministic)
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+            s.x += __shfl_xor_sync(0xffffffffu, s.x, o); s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+            s.z += __shfl_xor_sync(0xffffffffu, s.z, o); s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+            q.x += __shfl_xor_sync(0xffffffffu, q.x, o); q.y += __shfl_xor_sync(0xffffffffu, q.y, o);
+            q.z += __shfl_xor_sync(0xffffffffu, q.z, o); q.w += __shfl_xor_sync(0xffffffffu, q.w, o);
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) lin += __shfl_xor_sync(0xffffffffu, lin, o);
+        float t = (s.x * s.x - q.x) + (s.y * s.y - q.y) + (s.z * s.z - q.z) + (s.w * s.w - q.w);
+#pragma unroll
+        for (int o = 1; o < LPR; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (need_emb && grp == 0) reinterpret_cast<float4*>(s_out + (int64_t)b * K)[sub] = s;
+        if (lane == 0) {
+            float z = 0.f;
+            if (use_linear) z += lin + b0;
+            if (use_mf) z += 0.5f * t;
+            zacc[b] = z;
+        }
+    }
+}
+
+// =============================================================================================
+// K5/K6: deterministic segmented reduction of the sparse gradients + sparse optimizer apply
+// =============================================================================================
+// gradient of lookup (b, f): dE[b, f*K..] (already = dz*(s-E) + dh0, written by the tower's last
+// backward GEMM epilogue or by de_fm_kernel) and dz[b] for the linear weight.
+template <int K>
+struct GradSrc {
+    const float* dE;    // [B, d*K] or nullptr
+    const float* dz;    // [B]
+    int dc, dK;         // dK = d*K
+    __device__ __forceinline__ void fetch(uint32_t val, int sub, bool want_lin, float4& g, float& gl) const {
+        uint32_t b = val / (uint32_t)dc, f = val - b * (uint32_t)dc;
+        g = dE ? __ldg(reinterpret_cast<const float4*>(dE + (size_t)b * dK + (size_t)f * K) + sub)
+               : make_float4(0.f, 0.f, 0.f, 0.f);
+        gl = want_lin ? __ldg(dz + b) : 0.f;
+    }
+};
+
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+// level 1: one warp per piece of a hot row (row with > DIRECT_T lookups).  The 128/K lane groups
+// stride over the piece's entries, then a fixed butterfly combines them.
+template <int K>
+__global__ void __launch_bounds__(256) piece_reduce_kernel(const uint32_t* __restrict__ svals,
+                                                           const uint32_t* __restrict__ piece_start,
+                                                           const uint32_t* __restrict__ piece_row,
+                                                           const uint32_t* __restrict__ row_start,
+                                                           const SegCounts* __restrict__ cnt, GradSrc<K> src,
+                                                           float* __restrict__ piece_sum /*[slots][K+4]*/) {
+    constexpr int LPR = K / 4, G = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+    const uint32_t P = cnt->n_pieces;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t warp0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // each warp scans 32 candidate pieces at a time and processes the hot ones
+    for (uint32_t p0 = warp0 * 32; p0 < P; p0 += nwarps * 32) {
+        uint32_t p = p0 + lane;
+        bool hot = false;
+        if (p < P) {
+            uint32_t r = piece_row[p];
+            hot = (row_start[r + 1] - row_start[r]) > (uint32_t)DIRECT_T;
+        }
+        uint32_t mask = __ballot_sync(0xffffffffu, hot);
+        while (mask) {
+            int l = __ffs(mask) - 1;
+            mask &= mask - 1;
+            uint32_t pp = p0 + l;
+            uint32_t beg = piece_start[pp], end = piece_start[pp + 1];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float accl = 0.f;
+            for (uint32_t i = beg + grp; i < end; i += G) {
+                float4 g; float gl;
+                src.fetch(__ldg(svals + i), sub, sub == 0, g, gl);
+                add4(acc, g);
+                accl += gl;
+            }
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+                accl += __shfl_xor_sync(0xffffffffu, accl, o);
+            }
+            if (grp == 0) {
+                float* dst = piece_sum + (size_t)piece_slot(beg) * (K + 4);
+                reinterpret_cast<float4*>(dst)[sub] = acc;
+                if (sub == 0) dst[K] = accl;
+            }
+        }
+    }
+}
+
+// level 2 + optimizer: one lane group per unique row.  Rows with <= DIRECT_T lookups sum their
+// gradients straight from dE in sorted (= sample) order; hot rows sum their piece sums in order.
+// Then the sparse optimizer step for that row (Adam: rows were caught up to t-1 beforehand).
+template <int K>
+__global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restrict__ skeys,
+                                                         const uint32_t* __restrict__ svals,
+                                                         const uint32_t* __restrict__ row_start,
+                                                         const uint32_t* __restrict__ row_piece0,
+                                                         const uint32_t* __restrict__ piece_start,
+                                                         const SegCounts* __restrict__ cnt, GradSrc<K> src,
+                                                         const float* __restrict__ piece_sum,
+                                                         float* __restrict__ emb_rec, int emb_slots,
+                                                         float4* __restrict__ lin_rec, OptDev od, OptDev ol,
+                                                         bool has_emb, bool has_lin, int step,
+                                                         float* __restrict__ alpha_d, float* __restrict__ alpha_l) {
+    constexpr int LPR = K / 4;
+    const int sub = threadIdx.x % LPR;
+    const uint32_t gpb = blockDim.x / LPR;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // alpha_t history for later replays
+        alpha_d[step] = od.alpha;
+        alpha_l[step] = ol.alpha;
+    }
+    const uint32_t U = cnt->n_rows;
+    const int stride = (1 + emb_slots) * K;
+    for (uint32_t u = blockIdx.x * gpb + threadIdx.x / LPR; u < U; u += gridDim.x * gpb) {
+        uint32_t beg = row_start[u], end = row_start[u + 1];
+        uint32_t row = skeys[beg];
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        float gl = 0.f;
+        if (end - beg <= (uint32_t)DIRECT_T) {
+            for (uint32_t i = beg; i < end; ++i) {
+                float4 t; float tl;
+                src.fetch(__ldg(svals + i), sub, sub == 0, t, tl);
+                add4(g, t);
+                gl += tl;
+            }
+        } else {
+            uint32_t p0 = row_piece0[u], p1 = row_piece0[u + 1];
+            for (uint32_t p = p0; p < p1; ++p) {
+                const float* ps = piece_sum + (size_t)piece_slot(piece_start[p]) * (K + 4);
+                add4(g, __ldg(reinterpret_cast<const float4*>(ps) + sub));
+                if (sub == 0) gl += __ldg(ps + K);
+            }
+        }
+        if (has_emb) {
+            float4* base = reinterpret_cast<float4*>(emb_rec + (size_t)row * stride) + sub;
+            float4 w = base[0];
+            float4 s1 = emb_slots >= 1 ? base[LPR] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 s2 = emb_slots >= 2 ? base[2 * LPR] : make_float4(0.f, 0.f, 0.f, 0.f);
+            sparse_apply(w.x, s1.x, s2.x, g.x, od);
+            sparse_apply(w.y, s1.y, s2.y, g.y, od);
+            sparse_apply(w.z, s1.z, s2.z, g.z, od);
+            sparse_apply(w.w, s1.w, s2.w, g.w, od);
+            base[0] = w;
+            if (emb_slots >= 1) base[LPR] = s1;
+            if (emb_slots >= 2) base[2 * LPR] = s2;
+        }
+        if (sub == 0) {
+            float4 lr = lin_rec[row];
+            if (has_lin) sparse_apply(lr.x, lr.y, lr.z, gl, ol);
+            lr.w = __int_as_float(step);
+            lin_rec[row] = lr;
+        }
+    }
+}
+
+// dE = dz * (s - E) when there is no DNN tower (otherwise the last backward GEMM epilogue does it);
+// accumulate != 0 adds to an existing dE (hidden_units == [] case).
+__global__ void de_fm_kernel(const float* __restrict__ h0, const float* __restrict__ s, const float* __restrict__ dz,
+                             int64_t total, int dK, int K, float* __restrict__ dE, int accumulate) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) {
+        int64_t b = i / dK;
+        int c = (int)(i - b * dK) % K;
+        float v = dz[b] * (s[b * K + c] - h0[i]);
+        dE[i] = accumulate ? dE[i] + v : v;
+    }
+}

@@ -1,0 +1,348 @@
+"""Host-side driver of the C ABI: one `DeepFMEngine` = one `dfm_handle` (model instance on a GPU).
+
+This is the layer `model_fn` (trainers/deep_fm.py) sits on.  It owns no arithmetic: it sorts the
+feature columns into TF's model order, packs raw feature columns into one pinned arena and calls
+libdeepfm_b200.so.  torch is used only as the pinned/device memory allocator.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DfmError
+
+_ALIGN = 256
+
+
+def default_optimizer(name="Adam", learning_rate=0.001):
+    """Hyper-parameters of tf.train.<name>Optimizer(learning_rate) (trainers/model_utils.py:57-66)."""
+    if name not in _lib.OPT_KIND:
+        raise KeyError(name)   # same failure mode as optimizer_classes[optimizer_name]
+    return dict(name=name, lr=float(learning_rate), beta1=0.9, beta2=0.999, eps=1e-8, init_acc=0.1)
+
+
+def _opt_struct(o):
+    return _lib.Optimizer(_lib.OPT_KIND[o["name"]], o["lr"], o.get("beta1", 0.9), o.get("beta2", 0.999),
+                          o.get("eps", 1e-8), o.get("init_acc", 0.1))
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class PackedBatch:
+    """Raw feature columns of one batch laid out back to back in one arena (host pinned or device)."""
+
+    def __init__(self, arena, base_ptr, raw, keep, nbytes, batch_size, on_device):
+        self.arena, self.base_ptr, self.raw, self._keep = arena, base_ptr, raw, keep
+        self.nbytes, self.batch_size, self.on_device = nbytes, batch_size, on_device
+
+
+class DeepFMEngine:
+    def __init__(self, categorical_columns, numeric_columns=(), embedding_size=4, hidden_units=(16, 16),
+                 use_linear=True, use_mf=True, use_dnn=True, loss_reduction="mean", opt_deep=None,
+                 opt_linear=None, max_batch=65536, device=0, feature_dtypes=None, sort_columns=True):
+        self.lib = _lib.load()
+        cats = list(categorical_columns)
+        nums = list(numeric_columns)
+        if sort_columns:   # tf.feature_column.input_layer / linear_model iterate columns sorted by name
+            cats = sorted(cats, key=lambda c: c.name + "_embedding")
+            nums = sorted(nums, key=lambda c: c.name)
+        self.cat_columns, self.num_columns = cats, nums
+        self.k = int(embedding_size)
+        self.hidden = [int(x) for x in hidden_units]
+        self.use_linear, self.use_mf, self.use_dnn = bool(use_linear), bool(use_mf), bool(use_dnn)
+        self.loss_reduction = loss_reduction
+        self.opt_deep = opt_deep or default_optimizer()
+        self.opt_linear = opt_linear or default_optimizer()
+        self.max_batch, self.device = int(max_batch), int(device)
+        fd = dict(feature_dtypes or {})
+        self.specs = []
+        for c in cats:
+            s = c.spec()
+            if s["kind"] == "bucketized":
+                s["dtype"] = fd.get(s["source"], c.source_column.dtype)
+            self.specs.append(s)
+        self.num_buckets = [int(s["num_buckets"]) for s in self.specs]
+        self.row_offsets = np.concatenate([[0], np.cumsum(self.num_buckets)]).astype(np.int64)
+        self._keep = []
+        cols = (_lib.Column * max(len(cats), 1))()
+        for i, s in enumerate(self.specs):
+            col = cols[i]
+            col.name = s["name"].encode()
+            col.kind = _lib.COL_KIND[s["kind"]]
+            col.dtype = _lib.DTYPE[s["dtype"]]
+            col.num_buckets = s["num_buckets"]
+            if s["kind"] == "bucketized":
+                arr = (C.c_float * len(s["boundaries"]))(*s["boundaries"])
+                self._keep.append(arr)
+                col.boundaries = C.cast(arr, C.POINTER(C.c_float))
+                col.n_boundaries = len(s["boundaries"])
+            if s["kind"] == "vocab":
+                arr = (C.c_char_p * len(s["vocab"]))(*[v.encode() for v in s["vocab"]])
+                self._keep.append(arr)
+                col.vocab = C.cast(arr, C.POINTER(C.c_char_p))
+                col.vocab_size = len(s["vocab"])
+                col.num_oov = s["num_oov"]
+        hid = (C.c_int32 * max(len(self.hidden), 1))(*self.hidden)
+        cfg = _lib.Config(len(cats), C.cast(cols, C.POINTER(_lib.Column)), len(nums), self.k, len(self.hidden),
+                          C.cast(hid, C.POINTER(C.c_int32)), int(self.use_linear), int(self.use_mf), int(self.use_dnn),
+                          _lib.LOSS_RED[loss_reduction], _opt_struct(self.opt_deep), _opt_struct(self.opt_linear),
+                          self.max_batch, self.device, 0, 1, None)
+        self._keep += [cols, hid]
+        handle = C.c_void_p()
+        rc = self.lib.dfm_create(C.byref(cfg), C.byref(handle))
+        if rc != _lib.DFM_OK:
+            msg = (self.lib.dfm_last_error(None) or b"").decode()
+            if rc == -1:
+                raise ValueError(msg)      # same exception type as trainers/deep_fm.py:31-34
+            raise DfmError(rc, msg)
+        self.h = handle
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        if rc != _lib.DFM_OK:
+            raise DfmError(rc, (self.lib.dfm_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dfm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def global_step(self):
+        return int(self.lib.dfm_global_step(self.h))
+
+    @property
+    def last_step_launches(self):
+        return int(self.lib.dfm_last_step_launches(self.h))
+
+    def sync(self):
+        self._check(self.lib.dfm_sync(self.h))
+
+    def flush(self):
+        self._check(self.lib.dfm_flush(self.h, None))
+
+    def set_profiling(self, on=True):
+        self._check(self.lib.dfm_set_profiling(self.h, int(on)))
+
+    def phase_ms(self):
+        names = ["transform", "sort", "segments", "catchup", "gather", "mlp_fwd", "loss", "mlp_bwd", "reduce",
+                 "update", "dense"]
+        return {n: float(self.lib.dfm_phase_ms(self.h, n.encode())) for n in names}
+
+    # ------------------------------------------------------------------ variables
+    def tensor_shape(self, name):
+        r, e = C.c_int64(), C.c_int64()
+        self._check(self.lib.dfm_tensor_rows(self.h, name.encode(), C.byref(r), C.byref(e)))
+        return int(r.value), int(e.value)
+
+    def variable_names(self):
+        names = []
+        if self.use_mf or self.use_dnn:
+            names.append("emb")
+            if self.num_columns:
+                names.append("num_emb")
+        if self.use_dnn:
+            for i in range(len(self.hidden)):
+                names += ["W%d" % i, "b%d" % i]
+            names += ["Wo", "bo"]
+        if self.use_linear:
+            names.append("lin")
+            if self.num_columns:
+                names.append("num_lin")
+            names.append("bias")
+        return names
+
+    def slot_names(self, var):
+        grp = self.opt_linear if var in ("lin", "num_lin", "bias") else self.opt_deep
+        return {"Adam": ["m", "v"], "Adagrad": ["acc"], "Ftrl": ["acc", "lin"], "SGD": []}[grp["name"]]
+
+    def set_tensor(self, name, value, row_begin=0):
+        value = np.ascontiguousarray(value, dtype=np.float32)
+        rows, elems = self.tensor_shape(name)
+        n_rows = value.size // max(elems, 1)
+        self._check(self.lib.dfm_set_tensor(self.h, name.encode(), row_begin, n_rows, value.ctypes.data_as(C.c_void_p)))
+
+    def get_tensor(self, name, row_begin=0, n_rows=None):
+        rows, elems = self.tensor_shape(name)
+        n_rows = rows - row_begin if n_rows is None else n_rows
+        out = np.empty((n_rows, elems), dtype=np.float32)
+        self._check(self.lib.dfm_get_tensor(self.h, name.encode(), row_begin, n_rows, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def set_weights(self, weights):
+        for name, val in weights.items():
+            self.set_tensor(name, val)
+
+    def state(self):
+        """All variables and optimizer slots, keyed like oracle.deepfm.OracleDeepFM.state()."""
+        out = {}
+        for v in self.variable_names():
+            out[v] = self.get_tensor(v)
+            for s in self.slot_names(v):
+                out[v + "/" + s] = self.get_tensor(v + "/" + s)
+        return out
+
+    def init_random(self, seed=0):
+        self._check(self.lib.dfm_init_random(self.h, seed))
+
+    # ------------------------------------------------------------------ batches
+    def _segments(self, features, labels):
+        """-> list of (kind, index, ndarray) in arena order; kind in cat|off|num|lab."""
+        segs = []
+        B = None
+        for f, s in enumerate(self.specs):
+            raw = features[s["source"]]
+            if s["dtype"] == "string":
+                if isinstance(raw, tuple):
+                    data, offs = raw
+                    data = np.ascontiguousarray(data, dtype=np.uint8)
+                    offs = np.ascontiguousarray(offs, dtype=np.int32)
+                else:
+                    vals = [v if isinstance(v, bytes) else str(v).encode() for v in np.asarray(raw, dtype=object).reshape(-1)]
+                    lens = np.fromiter((len(v) for v in vals), dtype=np.int64, count=len(vals))
+                    offs = np.zeros(len(vals) + 1, dtype=np.int32)
+                    np.cumsum(lens, out=offs[1:])
+                    data = np.frombuffer(b"".join(vals) or b"\0", dtype=np.uint8)
+                n = offs.shape[0] - 1
+                segs += [("off", f, offs), ("cat", f, data)]
+            else:
+                arr = np.asarray(raw).reshape(-1)
+                want = np.int32 if s["dtype"] == "int32" else np.float32
+                if arr.dtype != want:
+                    arr = arr.astype(want)
+                n = arr.shape[0]
+                segs.append(("cat", f, np.ascontiguousarray(arr)))
+            if B is None:
+                B = n
+            elif B != n:
+                raise ValueError("feature %s has %d rows, expected %d" % (s["source"], n, B))
+        for j, c in enumerate(self.num_columns):
+            arr = np.ascontiguousarray(np.asarray(features[c.key]).reshape(-1), dtype=np.float32)
+            if B is None:
+                B = arr.shape[0]
+            segs.append(("num", j, arr))
+        if labels is not None:
+            segs.append(("lab", 0, np.ascontiguousarray(np.asarray(labels).reshape(-1), dtype=np.float32)))
+        return segs, B
+
+    def pack(self, features, labels=None, device=False, pinned=True):
+        """Lay the raw columns out in ONE arena so that the H2D transfer is a single copy."""
+        segs, B = self._segments(features, labels)
+        offs, total = [], 0
+        for _, _, a in segs:
+            offs.append(total)
+            total += (a.nbytes + _ALIGN - 1) // _ALIGN * _ALIGN
+        total = max(total, _ALIGN)
+        keep = []
+        if device or pinned:
+            torch = _torch()
+        if pinned and not device and torch.cuda.is_available():
+            host = torch.empty(total, dtype=torch.uint8).pin_memory()
+        elif device:
+            host = torch.empty(total, dtype=torch.uint8)
+        else:
+            host = None
+        if host is not None:
+            hv = host.numpy()
+        else:
+            hv = np.empty(total, dtype=np.uint8)
+        for (kind, idx, a), o in zip(segs, offs):
+            hv[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
+        if device:
+            arena = host.to("cuda:%d" % self.device)
+            base = arena.data_ptr()
+        elif host is not None:
+            arena, base = host, host.data_ptr()
+        else:
+            arena, base = hv, hv.ctypes.data
+        nc, nn = max(len(self.specs), 1), max(len(self.num_columns), 1)
+        cat = (C.c_void_p * nc)()
+        off = (C.c_void_p * nc)()
+        num = (C.c_void_p * nn)()
+        lab = None
+        for (kind, idx, a), o in zip(segs, offs):
+            if kind == "cat":
+                cat[idx] = base + o
+            elif kind == "off":
+                off[idx] = base + o
+            elif kind == "num":
+                num[idx] = base + o
+            else:
+                lab = base + o
+        raw = _lib.RawBatch(B, C.cast(cat, C.POINTER(C.c_void_p)), C.cast(off, C.POINTER(C.c_void_p)),
+                            C.cast(num, C.POINTER(C.c_void_p)), lab)
+        keep += [cat, off, num]
+        return PackedBatch(arena, base, raw, keep, total, B, device)
+
+    def _as_batch(self, features, labels, device=False):
+        if isinstance(features, PackedBatch):
+            return features
+        return self.pack(features, labels, device=device)
+
+    # ------------------------------------------------------------------ the hot path
+    def transform(self, features):
+        """ids [B, n_cat] int32 in model order (-1 = empty bag): K1 alone."""
+        torch = _torch()
+        pb = self._as_batch(features, None, device=True)
+        out = torch.empty((pb.batch_size, len(self.specs)), dtype=torch.int32, device="cuda:%d" % self.device)
+        self._check(self.lib.dfm_transform(self.h, C.byref(pb.raw), C.c_void_p(out.data_ptr()), None))
+        self.sync()
+        return out.cpu().numpy()
+
+    def train_step(self, features, labels=None, return_logits=False):
+        """One train step from HOST buffers (H2D + step + D2H of the loss)."""
+        pb = self._as_batch(features, labels)
+        if pb.on_device:
+            return self.train_step_device(pb, return_logits)
+        loss = C.c_float()
+        logits = np.empty(pb.batch_size, dtype=np.float32) if return_logits else None
+        self._check(self.lib.dfm_train_step_host(self.h, C.byref(pb.raw), C.byref(loss),
+                                                 logits.ctypes.data_as(C.c_void_p) if return_logits else None))
+        return (float(loss.value), logits) if return_logits else float(loss.value)
+
+    def train_step_async(self, pb):
+        """Pipelined host step: returns the loss of the previously enqueued step (NaN on the first)."""
+        prev = C.c_float()
+        self._check(self.lib.dfm_train_step_host_async(self.h, C.byref(pb.raw), C.byref(prev)))
+        return float(prev.value)
+
+    def drain(self):
+        last = C.c_float()
+        self._check(self.lib.dfm_train_step_host_drain(self.h, C.byref(last)))
+        return float(last.value)
+
+    def train_step_device(self, pb, return_logits=False, loss_out=None, stream=None):
+        """One train step on a device-resident PackedBatch; enqueues only (no sync) unless logits are wanted."""
+        torch = _torch()
+        dev = "cuda:%d" % self.device
+        if loss_out is None:
+            loss_out = torch.empty(1, dtype=torch.float32, device=dev)
+        logits = torch.empty(pb.batch_size, dtype=torch.float32, device=dev) if return_logits else None
+        self._check(self.lib.dfm_train_step(self.h, C.byref(pb.raw), C.c_void_p(loss_out.data_ptr()),
+                                            C.c_void_p(logits.data_ptr()) if return_logits else None,
+                                            C.c_void_p(stream) if stream else None))
+        if return_logits:
+            self.sync()
+            return float(loss_out.item()), logits.cpu().numpy()
+        return loss_out
+
+    def predict_logits(self, features):
+        pb = self._as_batch(features, None)
+        out = np.empty(pb.batch_size, dtype=np.float32)
+        if pb.on_device:
+            torch = _torch()
+            t = torch.empty(pb.batch_size, dtype=torch.float32, device="cuda:%d" % self.device)
+            self._check(self.lib.dfm_forward(self.h, C.byref(pb.raw), C.c_void_p(t.data_ptr()), None))
+            self.sync()
+            return t.cpu().numpy()
+        self._check(self.lib.dfm_forward_host(self.h, C.byref(pb.raw), out.ctypes.data_as(C.c_void_p)))
+        return out

@@ -1,0 +1,188 @@
+"""GPU: parity of the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Bars: ids / fingerprints / sort order bit-exact; logits, loss, updated weights and optimizer
+slots within 1e-5 relative (BASELINE.json north_star) with an absolute floor of 1e-7."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import transforms
+from oracle.farmhash import fingerprint64
+from recommender_tensorflow_b200 import feature_column as fc
+from recommender_tensorflow_b200 import synth
+from recommender_tensorflow_b200.engine import DeepFMEngine, default_optimizer
+from tests.util import assert_state_close, make_pair, ml100k_columns, oracle_cfg
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def test_device_fingerprint64_bit_exact():
+    torch = _torch()
+    from recommender_tensorflow_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    strs = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in list(range(0, 130)) * 3 + [200, 255, 256, 1000]]
+    strs += [b"a", b"b", b"c", b"d", b"omar", b"stringer", b"marlo", b"101", b"201", b"301"]
+    data, offs = transforms.pack_strings(strs)
+    d = torch.from_numpy(data).cuda()
+    o = torch.from_numpy(offs).cuda()
+    out = torch.empty(len(strs), dtype=torch.int64, device="cuda")
+    assert lib.dfm_test_fingerprint64(C.c_void_p(d.data_ptr()), C.c_void_p(o.data_ptr()), len(strs), C.c_void_p(out.data_ptr())) == 0
+    got = out.cpu().numpy().view(np.uint64)
+    ref = np.array([fingerprint64(s) for s in strs], dtype=np.uint64)
+    assert (got == ref).all()
+
+
+@pytest.mark.parametrize("n,bits", [(1, 8), (1000, 13), (4097, 13), (200000, 28), (1703936, 13), (300000, 32)])
+def test_radix_sort_stable(n, bits):
+    torch = _torch()
+    from recommender_tensorflow_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << bits, n, dtype=np.uint64).astype(np.uint32)
+    if n > 10:
+        keys[: n // 2] = keys[0]                     # a very hot key
+    vals = np.arange(n, dtype=np.uint32)
+    k = torch.from_numpy(keys.view(np.int32)).cuda()
+    v = torch.from_numpy(vals.view(np.int32)).cuda()
+    assert lib.dfm_test_sort_pairs(C.c_void_p(k.data_ptr()), C.c_void_p(v.data_ptr()), n, bits) == 0
+    order = np.argsort(keys, kind="stable")
+    assert (k.cpu().numpy().view(np.uint32) == keys[order]).all()
+    assert (v.cpu().numpy().view(np.uint32) == vals[order]).all()
+
+
+def _ml_engine(k=4, hidden=(16, 16), max_batch=4096, **kw):
+    cols, dtypes = ml100k_columns()
+    return DeepFMEngine(cols, (), embedding_size=k, hidden_units=hidden, max_batch=max_batch, feature_dtypes=dtypes, **kw)
+
+
+def test_transform_ml100k_bit_exact():
+    eng = _ml_engine()
+    ml = synth.ML100K()
+    feats, _ = ml.batch(3000, np.random.default_rng(5))
+    feats["user_id"][:7] = -1                        # ignored int key -> empty bag
+    feats["zipcode"][3] = b""                        # ignored string key
+    feats["gender"][5] = b"X"                        # OOV bucket
+    feats["occupation"][9] = b"a much longer occupation string than sixteen bytes"
+    feats["occupation"][10] = b"x" * 100
+    ids = eng.transform(feats)
+    ref = transforms.transform(eng.specs, feats)
+    assert ids.dtype == np.int32 and (ids == ref).all()
+    ref_py = transforms.transform(eng.specs, {k: v[:50] for k, v in feats.items()}, use_c=False)
+    assert (ids[:50] == ref_py).all()
+
+
+def test_identity_out_of_range_is_an_error():
+    from recommender_tensorflow_b200._lib import DfmError
+    eng = _ml_engine()
+    feats, _ = synth.ML100K().batch(64, np.random.default_rng(1))
+    feats["war"][3] = 2
+    with pytest.raises(DfmError) as ei:
+        eng.transform(feats)
+    assert ei.value.code == -3
+
+
+def _run_steps(eng, ora, batches, what):
+    for i, (feats, y) in enumerate(batches):
+        loss, logits = eng.train_step(feats, y, return_logits=True)
+        rloss, rlogits = ora.train_step_raw(feats, y)
+        assert abs(loss - rloss) <= RTOL * abs(rloss) + 1e-7, "%s step %d loss %r vs %r" % (what, i, loss, rloss)
+        assert np.allclose(logits, rlogits, rtol=RTOL, atol=2e-6), "%s step %d logits, worst %.3e" % (
+            what, i, np.abs(logits - rlogits).max())
+    assert_state_close(eng.state(), ora.state(), RTOL, 1e-7, what)
+
+
+def test_deepfm_ml100k_cfg1_steps():
+    """configs[0]: DeepFM, ML-100K-shaped, k=4, hidden [16,16], batch 32 — 12 steps, every weight and slot."""
+    eng = _ml_engine()
+    ora, _ = make_pair(eng, seed=1)
+    ml, rng = synth.ML100K(), np.random.default_rng(11)
+    _run_steps(eng, ora, [ml.batch(32, rng) for _ in range(12)], "cfg1")
+    assert eng.global_step == 12
+
+
+def test_deepfm_hot_rows_batch4096():
+    """large batch on tiny tables: every row is hot (piece reduction path)."""
+    eng = _ml_engine(k=16, hidden=(32, 16), max_batch=4096)
+    ora, _ = make_pair(eng, seed=2)
+    ml, rng = synth.ML100K(), np.random.default_rng(12)
+    _run_steps(eng, ora, [ml.batch(4096, rng) for _ in range(4)], "hot")
+
+
+def test_wide_deep_cfg2():
+    """configs[1]: wide&deep = no FM, SUM loss, Adagrad (dnn side) + FTRL (linear side)."""
+    eng = _ml_engine(use_mf=False, loss_reduction="sum", opt_deep=default_optimizer("Adagrad", 0.001),
+                     opt_linear=default_optimizer("Ftrl", 0.005))
+    ora, _ = make_pair(eng, seed=3)
+    ml, rng = synth.ML100K(), np.random.default_rng(13)
+    _run_steps(eng, ora, [ml.batch(4096, rng) for _ in range(4)], "wide&deep")
+
+
+@pytest.mark.parametrize("use", [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (0, 1, 1)])
+def test_component_subsets(use):
+    eng = _ml_engine(use_linear=bool(use[0]), use_mf=bool(use[1]), use_dnn=bool(use[2]), max_batch=512)
+    ora, _ = make_pair(eng, seed=4)
+    ml, rng = synth.ML100K(), np.random.default_rng(14)
+    _run_steps(eng, ora, [ml.batch(257, rng) for _ in range(3)], "subset%r" % (use,))
+
+
+def test_criteo_shaped_small_with_numerics():
+    """Criteo-shaped: hashed string keys + 13 numeric features (numeric_embeddings path), k=16."""
+    cats, nums = synth.criteo_columns(1000, n_cat=26, n_num=13)
+    eng = DeepFMEngine(cats, nums, embedding_size=16, hidden_units=(16, 16), max_batch=2048)
+    ora, _ = make_pair(eng, seed=5)
+    rng = np.random.default_rng(15)
+    _run_steps(eng, ora, [synth.criteo_batch(2048, rng, key_space=5000) for _ in range(4)], "criteo")
+
+
+def test_deferred_adam_equals_literal_nonlazy_long_gaps():
+    """Rows touched once and then left alone for 300 steps must follow TF's non-lazy Adam."""
+    cats = [fc.categorical_column_with_identity("a", 64), fc.categorical_column_with_identity("b", 64)]
+    eng = DeepFMEngine(cats, (), embedding_size=8, hidden_units=(8,), max_batch=16)
+    ora, _ = make_pair(eng, seed=6)
+    rng = np.random.default_rng(16)
+    batches = []
+    for step in range(300):
+        if step == 0:
+            a = np.arange(16, dtype=np.int32)          # rows 0..15 touched at step 1 only
+        else:
+            a = rng.integers(32, 64, 16).astype(np.int32)
+        b = rng.integers(0, 64, 16).astype(np.int32)
+        batches.append(({"a": a, "b": b}, (rng.random(16) < 0.5).astype(np.float32)))
+    _run_steps(eng, ora, batches, "deferred-adam")
+
+
+def test_bit_identical_reruns():
+    """Determinism: two engines fed the same batches end in bit-identical state."""
+    states = []
+    for _ in range(2):
+        eng = _ml_engine(k=16, hidden=(32, 16), max_batch=4096)
+        make_pair(eng, seed=7)
+        ml, rng = synth.ML100K(), np.random.default_rng(17)
+        for _ in range(3):
+            eng.train_step(*ml.batch(4096, rng))
+        states.append(eng.state())
+    for name in states[0]:
+        assert (states[0][name].view(np.uint32) == states[1][name].view(np.uint32)).all(), name
+
+
+def test_eval_forward_matches_oracle():
+    eng = _ml_engine()
+    ora, _ = make_pair(eng, seed=8)
+    ml, rng = synth.ML100K(), np.random.default_rng(18)
+    for _ in range(3):
+        feats, y = ml.batch(64, rng)
+        eng.train_step(feats, y)
+        ora.train_step_raw(feats, y)
+    feats, _ = ml.batch(100, rng)
+    z = eng.predict_logits(feats)
+    ref = ora.forward(transforms.transform(eng.specs, feats)).numpy()
+    assert np.allclose(z, ref, rtol=RTOL, atol=2e-6)
+    assert eng.global_step == 3
