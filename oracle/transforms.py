@@ -33,8 +33,17 @@ def pack_strings(values):
     return data, offsets
 
 
+def unpack_strings(col):
+    """(uint8 data, int32 offsets) -> list of bytes; anything else -> list of its elements."""
+    if isinstance(col, tuple):
+        data, offs = col
+        raw = np.asarray(data, dtype=np.uint8).tobytes()
+        return [raw[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+    return list(col)
+
+
 def hash_strings(values, num_buckets, use_c=True):
-    values = list(values)
+    values = unpack_strings(values)
     out = np.empty(len(values), dtype=np.int32)
     if use_c:
         data, offsets = pack_strings(values)
@@ -68,6 +77,7 @@ def bucketize(x, boundaries):
 
 
 def vocab_lookup(values, vocab, num_oov):
+    values = unpack_strings(values)
     table = {v if isinstance(v, bytes) else v.encode(): i for i, v in enumerate(vocab)}
     out = np.empty(len(values), dtype=np.int32)
     for i, v in enumerate(values):

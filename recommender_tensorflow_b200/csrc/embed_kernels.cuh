@@ -414,7 +414,8 @@ struct GradSrc {
 __device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
 // level 1: one warp per piece of a hot row (row with > DIRECT_T lookups).  The 128/K lane groups
-// stride over the piece's entries, then a fixed butterfly combines them.
+// stride over the piece's entries (4 independent loads in flight per group), then a fixed
+// butterfly combines them -> the summation order is a function of the sorted order only.
 template <int K>
 __global__ void __launch_bounds__(256) piece_reduce_kernel(const uint32_t* __restrict__ svals,
                                                            const uint32_t* __restrict__ piece_start,
@@ -427,39 +428,37 @@ __global__ void __launch_bounds__(256) piece_reduce_kernel(const uint32_t* __res
     const uint32_t P = cnt->n_pieces;
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
     const uint32_t warp0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    // each warp scans 32 candidate pieces at a time and processes the hot ones
-    for (uint32_t p0 = warp0 * 32; p0 < P; p0 += nwarps * 32) {
-        uint32_t p = p0 + lane;
-        bool hot = false;
-        if (p < P) {
-            uint32_t r = piece_row[p];
-            hot = (row_start[r + 1] - row_start[r]) > (uint32_t)DIRECT_T;
-        }
-        uint32_t mask = __ballot_sync(0xffffffffu, hot);
-        while (mask) {
-            int l = __ffs(mask) - 1;
-            mask &= mask - 1;
-            uint32_t pp = p0 + l;
-            uint32_t beg = piece_start[pp], end = piece_start[pp + 1];
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            float accl = 0.f;
-            for (uint32_t i = beg + grp; i < end; i += G) {
-                float4 g; float gl;
-                src.fetch(__ldg(svals + i), sub, sub == 0, g, gl);
-                add4(acc, g);
-                accl += gl;
+    for (uint32_t pp = warp0; pp < P; pp += nwarps) {
+        const uint32_t r = __ldg(piece_row + pp);
+        if (__ldg(row_start + r + 1) - __ldg(row_start + r) <= (uint32_t)DIRECT_T) continue;   // warp-uniform
+        const uint32_t beg = __ldg(piece_start + pp), end = __ldg(piece_start + pp + 1);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float accl = 0.f;
+        for (uint32_t i = beg + grp; i < end; i += 4 * G) {
+            uint32_t v[4];
+            float4 g[4];
+            float gl[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (i + u * G < end) ? __ldg(svals + i + u * G) : 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                gl[u] = 0.f;
+                if (v[u] != 0xffffffffu) src.fetch(v[u], sub, sub == 0, g[u], gl[u]);
             }
 #pragma unroll
-            for (int o = LPR; o < 32; o <<= 1) {
-                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-                accl += __shfl_xor_sync(0xffffffffu, accl, o);
-            }
-            if (grp == 0) {
-                float* dst = piece_sum + (size_t)piece_slot(beg) * (K + 4);
-                reinterpret_cast<float4*>(dst)[sub] = acc;
-                if (sub == 0) dst[K] = accl;
-            }
+            for (int u = 0; u < 4; ++u) { add4(acc, g[u]); accl += gl[u]; }
+        }
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+            accl += __shfl_xor_sync(0xffffffffu, accl, o);
+        }
+        if (grp == 0) {
+            float* dst = piece_sum + (size_t)piece_slot(beg) * (K + 4);
+            reinterpret_cast<float4*>(dst)[sub] = acc;
+            if (sub == 0) dst[K] = accl;
         }
     }
 }
@@ -494,18 +493,38 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         float gl = 0.f;
         if (end - beg <= (uint32_t)DIRECT_T) {
-            for (uint32_t i = beg; i < end; ++i) {
-                float4 t; float tl;
-                src.fetch(__ldg(svals + i), sub, sub == 0, t, tl);
-                add4(g, t);
-                gl += tl;
+            for (uint32_t i = beg; i < end; i += 4) {
+                uint32_t v[4];
+                float4 t[4];
+                float tl[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = (i + q < end) ? __ldg(svals + i + q) : 0xffffffffu;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    t[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    tl[q] = 0.f;
+                    if (v[q] != 0xffffffffu) src.fetch(v[q], sub, sub == 0, t[q], tl[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { add4(g, t[q]); gl += tl[q]; }
             }
         } else {
             uint32_t p0 = row_piece0[u], p1 = row_piece0[u + 1];
-            for (uint32_t p = p0; p < p1; ++p) {
-                const float* ps = piece_sum + (size_t)piece_slot(piece_start[p]) * (K + 4);
-                add4(g, __ldg(reinterpret_cast<const float4*>(ps) + sub));
-                if (sub == 0) gl += __ldg(ps + K);
+            for (uint32_t p = p0; p < p1; p += 4) {
+                float4 t[4];
+                float tl[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    t[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    tl[q] = 0.f;
+                    if (p + q < p1) {
+                        const float* ps = piece_sum + (size_t)piece_slot(__ldg(piece_start + p + q)) * (K + 4);
+                        t[q] = __ldg(reinterpret_cast<const float4*>(ps) + sub);
+                        if (sub == 0) tl[q] = __ldg(ps + K);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { add4(g, t[q]); gl += tl[q]; }
             }
         }
         if (has_emb) {

@@ -12,7 +12,7 @@ from oracle.farmhash import fingerprint64
 from recommender_tensorflow_b200 import feature_column as fc
 from recommender_tensorflow_b200 import synth
 from recommender_tensorflow_b200.engine import DeepFMEngine, default_optimizer
-from tests.util import assert_state_close, make_pair, ml100k_columns, oracle_cfg
+from tests.util import assert_state_close, assert_step_close, make_pair, ml100k_columns
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5
@@ -93,10 +93,8 @@ def _run_steps(eng, ora, batches, what):
     for i, (feats, y) in enumerate(batches):
         loss, logits = eng.train_step(feats, y, return_logits=True)
         rloss, rlogits = ora.train_step_raw(feats, y)
-        assert abs(loss - rloss) <= RTOL * abs(rloss) + 1e-7, "%s step %d loss %r vs %r" % (what, i, loss, rloss)
-        assert np.allclose(logits, rlogits, rtol=RTOL, atol=2e-6), "%s step %d logits, worst %.3e" % (
-            what, i, np.abs(logits - rlogits).max())
-    assert_state_close(eng.state(), ora.state(), RTOL, 1e-7, what)
+        assert_step_close(loss, logits, ora, rloss, rlogits, RTOL, "%s step %d" % (what, i))
+    assert_state_close(eng.state(), ora.state(), RTOL, 1e-7, what, ora.state64())
 
 
 def test_deepfm_ml100k_cfg1_steps():
