@@ -166,6 +166,12 @@ int dfm_test_sort_pairs(uint32_t* keys_dev, uint32_t* vals_dev, int64_t n, int32
 int dfm_test_fingerprint64(const uint8_t* bytes_dev, const int32_t* offsets_dev, int64_t n,
                            uint64_t* out_dev);
 
+/* 3xTF32 tcgen05 GEMM of the DNN tower in isolation (device pointers, synchronous):
+ * mode 0: C[M,N] = A[M,K] * B[N,K]^T;  mode 2: same, B pre-split into tf32 hi/lo (weight path);
+ * mode 1: C[M,N] = A[K,M]^T * B[K,N] through `splits` ordered partials (weight-gradient path). */
+int dfm_test_tc_gemm(int32_t mode, const float* A_dev, const float* B_dev, float* C_dev, int32_t M, int32_t N,
+                     int32_t K, int32_t splits);
+
 const char* dfm_version(void);
 
 #ifdef __cplusplus

@@ -67,6 +67,7 @@ _SIGS = {
     "dfm_phase_ms": (C.c_float, [C.c_void_p, C.c_char_p]),
     "dfm_test_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]),
     "dfm_test_fingerprint64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "dfm_test_tc_gemm": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dfm_version": (C.c_char_p, []),
 }
 EXPORTS = sorted(_SIGS)

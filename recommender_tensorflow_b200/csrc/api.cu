@@ -14,6 +14,8 @@
 #include "embed_kernels.cuh"
 #include "mlp_kernels.cuh"
 #include "prims.cuh"
+#include "small_mlp.cuh"
+#include "tc_gemm.cuh"
 
 static thread_local std::string g_create_error;
 
@@ -57,7 +59,7 @@ struct dfm_handle {
     void* sort_temp = nullptr;
     unsigned long long* flags = nullptr; void* scan_temp = nullptr; unsigned long long* seg_total = nullptr;
     SegCounts* seg_cnt = nullptr;
-    uint32_t *row_start = nullptr, *row_piece0 = nullptr, *piece_start = nullptr, *piece_row = nullptr;
+    uint32_t *row_start = nullptr, *row_piece0 = nullptr, *piece_start = nullptr, *piece_row = nullptr, *hot_list = nullptr;
     float* piece_sum = nullptr;
     float *h0 = nullptr, *s = nullptr, *zacc = nullptr, *logits = nullptr, *dz = nullptr, *dE = nullptr;
     float* act[DFM_MAX_HIDDEN + 1] = {nullptr};
@@ -65,6 +67,8 @@ struct dfm_handle {
     float* splitk = nullptr; int splits = 1, k_chunk = 0;
     float* colpart = nullptr; int rows_per_chunk = 512;
     float* head_part = nullptr; int head_blocks = 0;
+    bool small_mlp = false; SmallMlpDesc sm{}; int small_grid = 0; size_t small_smem = 0;
+    float *up_partial = nullptr, *w0_partial = nullptr;
     float* d_loss = nullptr; float* d_dzsum = nullptr;
     int* d_err = nullptr;
 
@@ -142,7 +146,7 @@ static void free_all(dfm_handle* h) {
                     h->ds1, h->ds2, h->dg, h->ids, h->keys[0], h->keys[1], h->vals[0], h->vals[1], h->sort_temp, h->flags,
                     h->scan_temp, h->seg_total, h->seg_cnt, h->row_start, h->row_piece0, h->piece_start, h->piece_row,
                     h->piece_sum, h->h0, h->s, h->zacc, h->logits, h->dz, h->dE, h->splitk, h->colpart, h->head_part,
-                    h->d_loss, h->d_dzsum, h->d_err, h->alpha_d, h->alpha_l};
+                    h->d_loss, h->d_dzsum, h->d_err, h->alpha_d, h->alpha_l, h->up_partial, h->w0_partial, h->hot_list};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 1; i <= DFM_MAX_HIDDEN; ++i) { if (h->act[i]) cudaFree(h->act[i]); if (h->dact[i]) cudaFree(h->dact[i]); }
     for (auto& s : h->stage) {
@@ -312,6 +316,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     if (dalloc(h, &h->row_piece0, n + 1)) return DFM_ERR_CUDA;
     if (dalloc(h, &h->piece_start, n + 1)) return DFM_ERR_CUDA;
     if (dalloc(h, &h->piece_row, n)) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->hot_list, (size_t)(2 * (n / 32 + 2)))) return DFM_ERR_CUDA;
     if (dalloc(h, &h->piece_sum, (size_t)(2 * (n / 32 + 2)) * (K + 4))) return DFM_ERR_CUDA;
     if (h->need_emb) {
         if (dalloc(h, &h->h0, Bm * dK)) return DFM_ERR_CUDA;
@@ -339,6 +344,45 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     if (dalloc(h, &h->colpart, (size_t)chunks * std::max<int64_t>(max_n, (int64_t)h->dn * (K + 1)))) return DFM_ERR_CUDA;
     h->head_blocks = (int)std::min<int64_t>(h->sm_count * 8, std::max<int64_t>(1, (Bm + 7) / 8));
     if (dalloc(h, &h->head_part, (size_t)h->head_blocks * 2)) return DFM_ERR_CUDA;
+    // fused small-MLP path: every hidden layer <= 32 wide (not a real GEMM)
+    if (h->use_dnn && h->L >= 1 && h->L <= SM_MAXL && getenv("DFM_NO_SMALL_MLP") == nullptr) {
+        bool ok = (h->hidden[0] == 8 || h->hidden[0] == 16 || h->hidden[0] == 32);
+        int sum = 0;
+        for (int i = 0; i < h->L; ++i) { ok = ok && h->hidden[i] <= SM_MAXH; sum += h->hidden[i]; }
+        if (ok) {
+            SmallMlpDesc& m = h->sm;
+            m.L = h->L; m.D = dK;
+            for (int i = 0; i < h->L; ++i) {
+                m.H[i] = h->hidden[i];
+                for (const DenseT& dt : h->dense) {
+                    if (dt.name == "W" + std::to_string(i)) m.off_W[i] = (int)dt.off;
+                    if (dt.name == "b" + std::to_string(i)) m.off_b[i] = (int)dt.off;
+                }
+            }
+            for (const DenseT& dt : h->dense) { if (dt.name == "Wo") m.off_Wo = (int)dt.off; if (dt.name == "bo") m.off_bo = (int)dt.off; }
+            m.up_begin = m.off_b[0];
+            m.up_count = m.off_bo + 32 - m.off_b[0];
+            m.act_stride = sum | 1;
+            h->small_smem = small_mlp_fwd_smem(m);
+            if (h->small_smem <= 200 * 1024) {
+                h->small_mlp = true;
+                const int tiles = (int)((Bm + SM_TB - 1) / SM_TB);
+                h->small_grid = std::min(tiles, 2 * h->sm_count);
+                if (dalloc(h, &h->up_partial, (size_t)h->small_grid * m.up_count)) return DFM_ERR_CUDA;
+                if (dalloc(h, &h->w0_partial, (size_t)std::min(tiles, 4 * h->sm_count) * dK * m.H[0])) return DFM_ERR_CUDA;
+                if (h->head_blocks < h->small_grid) {
+                    CK(cudaFree(h->head_part)); h->head_part = nullptr;
+                    if (dalloc(h, &h->head_part, (size_t)h->small_grid * 2)) return DFM_ERR_CUDA;
+                }
+                CK(cudaFuncSetAttribute(small_mlp_fwd_bwd_top_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->small_smem));
+                CK(cudaFuncSetAttribute(small_mlp_fwd_bwd_top_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->small_smem));
+                CK(cudaFuncSetAttribute(small_mlp_fwd_bwd_top_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->small_smem));
+                CK(cudaFuncSetAttribute(small_mlp_bwd_input_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_mlp_bwd_smem<8>()));
+                CK(cudaFuncSetAttribute(small_mlp_bwd_input_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_mlp_bwd_smem<16>()));
+                CK(cudaFuncSetAttribute(small_mlp_bwd_input_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_mlp_bwd_smem<32>()));
+            }
+        }
+    }
     if (dalloc(h, &h->d_loss, 1)) return DFM_ERR_CUDA;
     if (dalloc(h, &h->d_dzsum, 1)) return DFM_ERR_CUDA;
     if (dalloc(h, &h->d_err, 1)) return DFM_ERR_CUDA;
@@ -621,6 +665,18 @@ static int forward_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t 
     if (ph) ph->next();
     const float* hL = nullptr; int H = 0;
     const DenseT* Wo = find_dense(h, "Wo"); const DenseT* bo = find_dense(h, "bo");
+    if (h->small_mlp) {
+        const float* za = (h->use_linear || h->use_mf) ? h->zacc : nullptr;
+        const int train = labels ? 1 : 0;
+        const int grid = std::min((B + SM_TB - 1) / SM_TB, h->small_grid);
+#define SMALL_FWD(HH) small_mlp_fwd_bwd_top_kernel<HH><<<grid, 256, h->small_smem, st>>>(h->sm, h->dw, h->h0, za, labels, B, scale, train, \
+            h->logits, logits_out, h->dz, h->dact[1], h->up_partial, h->head_part)
+        if (h->sm.H[0] == 8) SMALL_FWD(8); else if (h->sm.H[0] == 16) SMALL_FWD(16); else SMALL_FWD(32);
+#undef SMALL_FWD
+        h->launches++;
+        if (ph) { ph->next(); }
+        return DFM_OK;
+    }
     if (h->use_dnn) {
         int in = dK;
         for (int i = 0; i < h->L; ++i) {
@@ -688,14 +744,28 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
     rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, &ph);
     if (rc) return rc;
     const DenseT* bo = find_dense(h, "bo"); const DenseT* bias = find_dense(h, "bias");
-    head_final_kernel<<<1, 256, 0, st>>>(h->head_part, h->head_blocks, scale, h->d_loss, h->d_dzsum);
+    const int small_blocks = std::min((B + SM_TB - 1) / SM_TB, h->small_grid);
+    head_final_kernel<<<1, 256, 0, st>>>(h->head_part, h->small_mlp ? small_blocks : h->head_blocks, scale, h->d_loss, h->d_dzsum);
     h->launches++;
     if (loss_out) CK(cudaMemcpyAsync(loss_out, h->d_loss, 4, cudaMemcpyDeviceToDevice, st));
-    if (bo) CK(cudaMemcpyAsync(h->dg + bo->off, h->d_dzsum, 4, cudaMemcpyDeviceToDevice, st));
+    if (bo && !h->small_mlp) CK(cudaMemcpyAsync(h->dg + bo->off, h->d_dzsum, 4, cudaMemcpyDeviceToDevice, st));
     if (bias) CK(cudaMemcpyAsync(h->dg + bias->off, h->d_dzsum, 4, cudaMemcpyDeviceToDevice, st));
     ph.next();
     // backward through the tower
-    if (h->use_dnn) {
+    if (h->small_mlp) {
+        const SmallMlpDesc& m = h->sm;
+        const int tiles = (B + SM_TB - 1) / SM_TB;
+        reduce_partials_kernel<<<cdiv(m.up_count, 256), 256, 0, st>>>(h->up_partial, small_blocks, (size_t)m.up_count, m.up_count, h->dg + m.up_begin);
+        const int chunks = (int)cdiv(dK, SM_BC);
+        const int groups = std::max(1, std::min(tiles, (4 * h->sm_count + chunks - 1) / chunks));
+        dim3 grid(groups, chunks);
+        const float* sv = h->use_mf ? h->s : nullptr;
+#define SMALL_BWD(HH) small_mlp_bwd_input_kernel<HH><<<grid, 256, small_mlp_bwd_smem<HH>(), st>>>(h->dw + m.off_W[0], h->h0, h->dact[1], h->dz, sv, K, B, dK, h->dE, h->w0_partial)
+        if (m.H[0] == 8) SMALL_BWD(8); else if (m.H[0] == 16) SMALL_BWD(16); else SMALL_BWD(32);
+#undef SMALL_BWD
+        reduce_partials_kernel<<<cdiv((int64_t)dK * m.H[0], 256), 256, 0, st>>>(h->w0_partial, groups, (size_t)dK * m.H[0], (int64_t)dK * m.H[0], h->dg + m.off_W[0]);
+        h->launches += 3;
+    } else if (h->use_dnn) {
         const DenseT* Wo = find_dense(h, "Wo");
         const int L = h->L;
         const float* hL = h->act[L];
@@ -754,8 +824,9 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
     // sparse gradients: sorted segmented reduction + optimizer
     GradSrc<K> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK};
     if (n > 0) {
-        piece_reduce_kernel<K><<<row_grid, 256, 0, st>>>(svals, h->piece_start, h->piece_row, h->row_start, h->seg_cnt, src, h->piece_sum);
-        h->launches++;
+        hot_pieces_kernel<<<row_grid, 256, 0, st>>>(h->row_start, h->row_piece0, h->seg_cnt, h->hot_list);
+        piece_reduce_kernel<K><<<row_grid, 256, 0, st>>>(svals, h->piece_start, h->hot_list, h->seg_cnt, src, h->piece_sum);
+        h->launches += 2;
     }
     ph.next();
     row_update_kernel<K><<<n > 0 ? row_grid : 1, 256, 0, st>>>(skeys, svals, h->row_start, h->row_piece0, h->piece_start, h->seg_cnt, src,
@@ -1038,6 +1109,91 @@ extern "C" int dfm_test_fingerprint64(const uint8_t* bytes_dev, const int32_t* o
     dfm_handle* h = nullptr;
     if (n <= 0) return DFM_OK;
     fingerprint_kernel<<<cdiv(n, 256), 256>>>(bytes_dev, offsets_dev, n, out_dev);
+    CK(cudaDeviceSynchronize());
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+// ------------------------------------------------------------------------- tensor-core GEMM host
+// C[M,N] = A[M,K] * B[N,K]^T  (both K-major).  A_lo / B_lo == nullptr -> the operand is split into
+// tf32 hi/lo inside the kernel; otherwise hi/lo were produced beforehand (weights).
+static int tc_gemm_kmajor(dfm_handle* h, const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
+                          float* C, int ldc, int M, int N, int K, int epi, const EpiArgs& ep, cudaStream_t st) {
+    const int BN = N > 128 ? 256 : 128;
+    CUtensorMap ma, mal, mb, mbl;
+    bool ok = tc::make_map_2d(&ma, A_hi, M, K, lda, tc::BM) && tc::make_map_2d(&mal, A_lo ? A_lo : A_hi, M, K, lda, tc::BM) &&
+              tc::make_map_2d(&mb, B_hi, N, K, ldb, BN) && tc::make_map_2d(&mbl, B_lo ? B_lo : B_hi, N, K, ldb, BN);
+    if (!ok) FAIL(DFM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    tc::Params p{};
+    p.M = M; p.N = N; p.K = K; p.k_per_split = K; p.C = C; p.ldc = ldc; p.c_split_stride = 0; p.epi = epi; p.ep = ep;
+    p.split_a = A_lo ? 0 : 1; p.split_b = B_lo ? 0 : 1;
+    dim3 grid(cdiv(N, BN), cdiv(M, tc::BM), 1);
+    if (BN == 256) tc::gemm_kernel<256, 0><<<grid, tc::NTHREADS, tc::Smem<256>::TOTAL, st>>>(ma, mal, mb, mbl, p);
+    else tc::gemm_kernel<128, 0><<<grid, tc::NTHREADS, tc::Smem<128>::TOTAL, st>>>(ma, mal, mb, mbl, p);
+    if (h) h->launches++;
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+// Cpartial[z][M,N] = sum over k in split z of A[k,M]^T * B[k,N]  (both MN-major, reduction over rows = batch)
+static int tc_gemm_mnmajor(dfm_handle* h, const float* A, int lda, const float* B, int ldb, float* Cpart, int M, int N, int K, int splits,
+                           int* k_per_split_out, cudaStream_t st) {
+    if (M % 32 || N % 32 || N > 256) FAIL(DFM_ERR_UNSUPPORTED, "tc_gemm_mnmajor needs M, N multiples of 32 and N <= 256");
+    const int BN = N > 128 ? 256 : 128;
+    CUtensorMap ma, mb;
+    bool ok = tc::make_map_3d(&ma, A, K, M, lda, tc::BK, tc::BM / 32) && tc::make_map_3d(&mb, B, K, N, ldb, tc::BK, BN / 32);
+    if (!ok) FAIL(DFM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    int kps = ((K + splits - 1) / splits + tc::BK - 1) / tc::BK * tc::BK;
+    int nz = (K + kps - 1) / kps;
+    if (k_per_split_out) *k_per_split_out = nz;
+    tc::Params p{};
+    p.M = M; p.N = N; p.K = K; p.k_per_split = kps; p.C = Cpart; p.ldc = N; p.c_split_stride = (size_t)M * N; p.epi = EPI_NONE;
+    p.split_a = 1; p.split_b = 1;
+    dim3 grid(cdiv(N, BN), cdiv(M, tc::BM), nz);
+    if (BN == 256) tc::gemm_kernel<256, 1><<<grid, tc::NTHREADS, tc::Smem<256>::TOTAL, st>>>(ma, ma, mb, mb, p);
+    else tc::gemm_kernel<128, 1><<<grid, tc::NTHREADS, tc::Smem<128>::TOTAL, st>>>(ma, ma, mb, mb, p);
+    if (h) h->launches++;
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+static int tc_setup_once() {
+    static int done = 0;
+    if (done) return done;
+    cudaError_t e = cudaSuccess;
+    e = cudaFuncSetAttribute(tc::gemm_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<256>::TOTAL); if (e) return done = -1;
+    e = cudaFuncSetAttribute(tc::gemm_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<128>::TOTAL); if (e) return done = -1;
+    e = cudaFuncSetAttribute(tc::gemm_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<256>::TOTAL); if (e) return done = -1;
+    e = cudaFuncSetAttribute(tc::gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<128>::TOTAL); if (e) return done = -1;
+    return done = 1;
+}
+
+// test hook: mode 0: C[M,N] = A[M,K] B[N,K]^T (both split in-kernel); mode 2: same with B pre-split on the host side of
+// the call; mode 1: C[M,N] = A[K,M]^T B[K,N] through `splits` deterministic partials.
+extern "C" int dfm_test_tc_gemm(int32_t mode, const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t splits) {
+    dfm_handle* h = nullptr;
+    if (tc_setup_once() < 0) FAIL(DFM_ERR_CUDA, "tc setup failed");
+    EpiArgs ep{};
+    int rc = DFM_OK;
+    if (mode == 0) {
+        rc = tc_gemm_kmajor(nullptr, A, nullptr, K, B, nullptr, K, C, N, M, N, K, EPI_NONE, ep, 0);
+    } else if (mode == 2) {
+        float *bh = nullptr, *bl = nullptr;
+        CK(cudaMalloc(&bh, (size_t)N * K * 4)); CK(cudaMalloc(&bl, (size_t)N * K * 4));
+        tc::split_tf32_kernel<<<cdiv((int64_t)N * K, 256), 256>>>(B, (int64_t)N * K, bh, bl);
+        rc = tc_gemm_kmajor(nullptr, A, nullptr, K, bh, bl, K, C, N, M, N, K, EPI_NONE, ep, 0);
+        CK(cudaDeviceSynchronize());
+        cudaFree(bh); cudaFree(bl);
+    } else {
+        float* part = nullptr;
+        int nz = 0;
+        CK(cudaMalloc(&part, (size_t)std::max(splits, 1) * M * N * 4 + 16));
+        rc = tc_gemm_mnmajor(nullptr, A, M, B, N, part, M, N, K, std::max(splits, 1), &nz, 0);
+        if (rc == DFM_OK) reduce_partials_kernel<<<cdiv((int64_t)M * N, 256), 256>>>(part, nz, (size_t)M * N, (int64_t)M * N, C);
+        CK(cudaDeviceSynchronize());
+        cudaFree(part);
+    }
+    if (rc) return rc;
     CK(cudaDeviceSynchronize());
     CK(cudaGetLastError());
     return DFM_OK;

@@ -33,7 +33,7 @@ struct SegCounts {
     uint32_t n_rows;     // unique table rows touched by the batch
     uint32_t n_pieces;   // sorted array cut at row changes and multiples of PIECE_C
     uint32_t n_valid;    // lookups that are not empty bags
-    uint32_t pad;
+    uint32_t n_hot;      // pieces that belong to rows with > DIRECT_T lookups
 };
 
 constexpr int PIECE_C = 256;      // max entries per piece

@@ -220,6 +220,7 @@ __global__ void seg_fill_kernel(const uint32_t* __restrict__ keys, int64_t n, ui
         uint32_t nv = cnt->n_valid;
         cnt->n_rows = U;
         cnt->n_pieces = P;
+        cnt->n_hot = 0;
         row_start[U] = nv;
         row_piece0[U] = P;
         piece_start[P] = nv;
@@ -413,24 +414,34 @@ struct GradSrc {
 
 __device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
-// level 1: one warp per piece of a hot row (row with > DIRECT_T lookups).  The 128/K lane groups
-// stride over the piece's entries (4 independent loads in flight per group), then a fixed
-// butterfly combines them -> the summation order is a function of the sorted order only.
+// list the pieces of hot rows (rows with > DIRECT_T lookups); order is irrelevant, every piece sum goes to its own slot
+__global__ void __launch_bounds__(256) hot_pieces_kernel(const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ row_piece0,
+                                                         SegCounts* __restrict__ cnt, uint32_t* __restrict__ hot_list) {
+    const uint32_t U = cnt->n_rows;
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += gridDim.x * blockDim.x) {
+        if (row_start[u + 1] - row_start[u] <= (uint32_t)DIRECT_T) continue;
+        const uint32_t p0 = row_piece0[u], p1 = row_piece0[u + 1];
+        uint32_t base = atomicAdd(&cnt->n_hot, p1 - p0);
+        for (uint32_t p = p0; p < p1; ++p) hot_list[base + (p - p0)] = p;
+    }
+}
+
+// level 1: one warp per piece of a hot row.  The 128/K lane groups stride over the piece's entries
+// (4 independent loads in flight per group), then a fixed butterfly combines them -> the summation
+// order is a function of the sorted order only.
 template <int K>
 __global__ void __launch_bounds__(256) piece_reduce_kernel(const uint32_t* __restrict__ svals,
                                                            const uint32_t* __restrict__ piece_start,
-                                                           const uint32_t* __restrict__ piece_row,
-                                                           const uint32_t* __restrict__ row_start,
+                                                           const uint32_t* __restrict__ hot_list,
                                                            const SegCounts* __restrict__ cnt, GradSrc<K> src,
                                                            float* __restrict__ piece_sum /*[slots][K+4]*/) {
     constexpr int LPR = K / 4, G = 32 / LPR;
     const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
-    const uint32_t P = cnt->n_pieces;
+    const uint32_t NH = cnt->n_hot;
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
     const uint32_t warp0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    for (uint32_t pp = warp0; pp < P; pp += nwarps) {
-        const uint32_t r = __ldg(piece_row + pp);
-        if (__ldg(row_start + r + 1) - __ldg(row_start + r) <= (uint32_t)DIRECT_T) continue;   // warp-uniform
+    for (uint32_t hp = warp0; hp < NH; hp += nwarps) {
+        const uint32_t pp = __ldg(hot_list + hp);
         const uint32_t beg = __ldg(piece_start + pp), end = __ldg(piece_start + pp + 1);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         float accl = 0.f;

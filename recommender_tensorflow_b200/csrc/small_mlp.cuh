@@ -1,0 +1,323 @@
+// Fused small-MLP tower (trainers/deep_fm.py:93-112 with the reference default hidden_units
+// [16,16] and friends): when every hidden layer is <= 32 wide the tower is ~10 kFLOP/sample and
+// not a real GEMM, so it runs on CUDA cores with the weights resident in shared memory
+// (BASELINE.json north_star: "tensor cores only when hidden_units make it a real GEMM").
+//
+//   small_mlp_fwd_bwd_top_kernel   one CTA = 128 samples per tile (persistent over tiles):
+//        h1 = relu(h0 W0 + b0) ... z = zacc + h_L Wo + bo, sigmoid-CE loss, dz, then the backward
+//        pass through every layer ABOVE the input layer, all without leaving the SM.  Emits
+//        logits, dz, dh1' [B,H1] and per-CTA partial gradients of b0, W1, b1, ..., Wo, bo.
+//   small_mlp_bwd_input_kernel     grid (sample tiles, 64-column chunks of the input layer):
+//        dE = dh1' W0^T + dz (s - E)   and the per-tile partial of   dW0 = h0^T dh1'.
+// Partials are reduced in a fixed order afterwards (deterministic).
+#pragma once
+#include "dfm_types.cuh"
+
+constexpr int SM_TB = 128;        // samples per tile
+constexpr int SM_DC = 32;         // input-layer columns per staged chunk (forward)
+constexpr int SM_BC = 64;         // input-layer columns per CTA (backward)
+constexpr int SM_MAXH = 32;
+constexpr int SM_MAXL = 4;
+
+struct SmallMlpDesc {
+    int L;                        // hidden layers (1..SM_MAXL)
+    int H[SM_MAXL];               // widths
+    int D;                        // input width d*K
+    int off_W[SM_MAXL], off_b[SM_MAXL], off_Wo, off_bo;   // offsets in the packed dense buffer
+    int up_begin, up_count;       // [b0 .. bo] range (everything above W0) in the packed buffer
+    int act_stride;               // floats per sample row in the per-sample scratch (odd)
+};
+
+static inline size_t small_mlp_fwd_smem(const SmallMlpDesc& m) {
+    size_t f = (size_t)m.D * m.H[0] + 2 * (size_t)m.up_count + (size_t)SM_TB * (SM_DC + 1) + 2 * (size_t)SM_TB * m.act_stride +
+               2 * SM_TB + 64;
+    return f * sizeof(float);
+}
+
+// per-sample scratch row layout: [h_1 | h_2 | ... | h_L]; gradients use a second array of the same shape
+template <int H1>
+__global__ void __launch_bounds__(256, 2) small_mlp_fwd_bwd_top_kernel(
+    SmallMlpDesc m, const float* __restrict__ dw, const float* __restrict__ h0, const float* __restrict__ zacc,
+    const float* __restrict__ labels, int B, float scale, int train, float* __restrict__ logits,
+    float* __restrict__ logits_out, float* __restrict__ dz_out, float* __restrict__ dh1_out,
+    float* __restrict__ up_partial /*[grid][up_count]*/, float* __restrict__ head_part /*[grid][2]*/) {
+    extern __shared__ __align__(16) float smem[];
+    float* W0s = smem;                                   // [D][H1]
+    float* ups = W0s + (size_t)m.D * H1;                 // packed params above W0
+    float* gup = ups + m.up_count;                       // per-CTA gradient accumulators (same layout)
+    float* hs = gup + m.up_count;                        // [SM_TB][SM_DC+1] staged input chunk
+    float* acts = hs + SM_TB * (SM_DC + 1);              // [SM_TB][act_stride]
+    float* dacts = acts + SM_TB * m.act_stride;          // [SM_TB][act_stride]
+    float* dzs = dacts + SM_TB * m.act_stride;           // [SM_TB]
+    float* red = dzs + SM_TB;                            // [SM_TB] loss terms
+    const int tid = threadIdx.x;
+    const int D = m.D;
+    for (int i = tid; i < D * H1; i += 256) W0s[i] = dw[m.off_W[0] + i];
+    for (int i = tid; i < m.up_count; i += 256) { ups[i] = dw[m.up_begin + i]; gup[i] = 0.f; }
+    __syncthreads();
+    auto UP = [&](int packed_off) { return ups + (packed_off - m.up_begin); };
+    auto GUP = [&](int packed_off) { return gup + (packed_off - m.up_begin); };
+    const int s = tid & (SM_TB - 1), half = tid >> 7;
+    constexpr int HJ = H1 / 2;
+    const int j0 = half * HJ;
+    float loss_acc = 0.f, dz_acc = 0.f;
+    const int ntiles = (B + SM_TB - 1) / SM_TB;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b0 = tile * SM_TB;
+        const int b = b0 + s;
+        // ---- layer 0: h1 = relu(h0 W0 + b0), input staged chunk by chunk (coalesced)
+        float acc[HJ];
+#pragma unroll
+        for (int j = 0; j < HJ; ++j) acc[j] = 0.f;
+        // chunk c+1 is fetched into registers while chunk c is being multiplied (hides the global latency)
+        constexpr int NPF = SM_TB * (SM_DC / 4) / 256;
+        float4 pf[NPF];
+        auto fetch = [&](int c0) {
+#pragma unroll
+            for (int u = 0; u < NPF; ++u) {
+                int q = tid + u * 256;
+                int r = q / (SM_DC / 4), cc = (q % (SM_DC / 4)) * 4;
+                pf[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (b0 + r < B && c0 + cc < D) pf[u] = __ldg(reinterpret_cast<const float4*>(h0 + (size_t)(b0 + r) * D + c0 + cc));
+            }
+        };
+        fetch(0);
+        for (int c0 = 0; c0 < D; c0 += SM_DC) {
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < NPF; ++u) {
+                int q = tid + u * 256;
+                int r = q / (SM_DC / 4), cc = (q % (SM_DC / 4)) * 4;
+                float* d = hs + r * (SM_DC + 1) + cc;
+                d[0] = pf[u].x; d[1] = pf[u].y; d[2] = pf[u].z; d[3] = pf[u].w;
+            }
+            __syncthreads();
+            if (c0 + SM_DC < D) fetch(c0 + SM_DC);
+            const int cmax = min(SM_DC, D - c0);
+            const float* hrow = hs + s * (SM_DC + 1);
+#pragma unroll 4
+            for (int c = 0; c < cmax; ++c) {
+                float a = hrow[c];
+                const float4* w = reinterpret_cast<const float4*>(W0s + (size_t)(c0 + c) * H1 + j0);
+#pragma unroll
+                for (int j4 = 0; j4 < HJ / 4; ++j4) {
+                    float4 ww = w[j4];
+                    acc[j4 * 4 + 0] = fmaf(a, ww.x, acc[j4 * 4 + 0]);
+                    acc[j4 * 4 + 1] = fmaf(a, ww.y, acc[j4 * 4 + 1]);
+                    acc[j4 * 4 + 2] = fmaf(a, ww.z, acc[j4 * 4 + 2]);
+                    acc[j4 * 4 + 3] = fmaf(a, ww.w, acc[j4 * 4 + 3]);
+                }
+            }
+        }
+        float* arow = acts + s * m.act_stride;
+        float* drow = dacts + s * m.act_stride;
+        {
+            const float* bb = UP(m.off_b[0]);
+#pragma unroll
+            for (int j = 0; j < HJ; ++j) arow[j0 + j] = fmaxf(acc[j] + bb[j0 + j], 0.f);
+        }
+        __syncthreads();
+        // ---- upper layers, head and their backward: one thread per sample
+        if (half == 0) {
+            int aoff = 0;
+            for (int l = 1; l < m.L; ++l) {
+                const int Hin = m.H[l - 1], Hout = m.H[l];
+                const float* W = UP(m.off_W[l]);
+                const float* bb = UP(m.off_b[l]);
+                for (int o = 0; o < Hout; ++o) {
+                    float a = bb[o];
+                    for (int j = 0; j < Hin; ++j) a = fmaf(arow[aoff + j], W[j * Hout + o], a);
+                    arow[aoff + Hin + o] = fmaxf(a, 0.f);
+                }
+                aoff += Hin;
+            }
+            const int HL = m.H[m.L - 1];
+            const float* Wo = UP(m.off_Wo);
+            float z = UP(m.off_bo)[0];
+            for (int j = 0; j < HL; ++j) z = fmaf(arow[aoff + j], Wo[j], z);
+            if (zacc && b < B) z += zacc[b];
+            float g = 0.f, lterm = 0.f;
+            if (b < B) {
+                logits[b] = z;
+                if (logits_out) logits_out[b] = z;
+                if (train) {
+                    float y = labels[b];
+                    lterm = fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));
+                    g = (1.f / (1.f + expf(-z)) - y) * scale;
+                    dz_out[b] = g;
+                }
+            }
+            dzs[s] = g;
+            red[s] = lterm;
+            if (train) {
+                // dh_L' = dz * Wo * relu'(h_L); walk down to dh_1'
+                for (int j = 0; j < HL; ++j) drow[aoff + j] = arow[aoff + j] > 0.f ? g * Wo[j] : 0.f;
+                for (int l = m.L - 1; l >= 1; --l) {
+                    const int Hin = m.H[l - 1], Hout = m.H[l];
+                    const float* W = UP(m.off_W[l]);
+                    const int in_off = aoff - Hin;
+                    for (int j = 0; j < Hin; ++j) {
+                        float a = 0.f;
+                        for (int o = 0; o < Hout; ++o) a = fmaf(drow[aoff + o], W[j * Hout + o], a);
+                        drow[in_off + j] = arow[in_off + j] > 0.f ? a : 0.f;
+                    }
+                    aoff = in_off;
+                }
+                if (b < B) {
+                    float4* dst = reinterpret_cast<float4*>(dh1_out + (size_t)b * H1);
+#pragma unroll
+                    for (int j4 = 0; j4 < H1 / 4; ++j4) dst[j4] = make_float4(drow[j4 * 4], drow[j4 * 4 + 1], drow[j4 * 4 + 2], drow[j4 * 4 + 3]);
+                }
+            }
+        }
+        __syncthreads();
+        if (train) {
+            // ---- per-CTA gradient accumulation for everything above W0 (each output owned by one thread,
+            //      samples walked in order -> deterministic)
+            int aoff = 0;
+            for (int l = 0; l < m.L; ++l) {
+                const int Hl = m.H[l];
+                // bias l: sum_s dact_l[s][j]
+                for (int j = tid; j < Hl; j += 256) {
+                    float a = 0.f;
+                    for (int r = 0; r < SM_TB; ++r) a += dacts[r * m.act_stride + aoff + j];
+                    GUP(m.off_b[l])[j] += a;
+                }
+                if (l + 1 < m.L) {
+                    const int Hn = m.H[l + 1];
+                    for (int q = tid; q < Hl * Hn; q += 256) {
+                        int j = q / Hn, o = q % Hn;
+                        float a = 0.f;
+                        for (int r = 0; r < SM_TB; ++r) a = fmaf(acts[r * m.act_stride + aoff + j], dacts[r * m.act_stride + aoff + Hl + o], a);
+                        GUP(m.off_W[l + 1])[q] += a;
+                    }
+                } else {
+                    for (int j = tid; j < Hl; j += 256) {
+                        float a = 0.f;
+                        for (int r = 0; r < SM_TB; ++r) a = fmaf(acts[r * m.act_stride + aoff + j], dzs[r], a);
+                        GUP(m.off_Wo)[j] += a;
+                    }
+                }
+                aoff += Hl;
+            }
+            if (tid == 0) {
+                float a = 0.f, c = 0.f;
+                for (int r = 0; r < SM_TB; ++r) { a += red[r]; c += dzs[r]; }
+                loss_acc += a;
+                dz_acc += c;
+            }
+        }
+        __syncthreads();
+        // zero the rows for the next tile's out-of-range samples is unnecessary: g = 0 and h = relu(b) only
+        // enter sums through dacts (0 when g == 0) and acts * dacts / acts * dzs (0 as well).
+    }
+    if (train) {
+        __syncthreads();
+        if (tid == 0) GUP(m.off_bo)[0] = dz_acc;
+        __syncthreads();
+        for (int i = tid; i < m.up_count; i += 256) up_partial[(size_t)blockIdx.x * m.up_count + i] = gup[i];
+        if (tid == 0) { head_part[blockIdx.x * 2] = loss_acc; head_part[blockIdx.x * 2 + 1] = dz_acc; }
+    }
+}
+
+template <int H1>
+constexpr size_t small_mlp_bwd_smem() { return (size_t)(SM_TB * (H1 + 4) + SM_BC * H1 + SM_TB * (SM_BC + 1) + SM_TB * (SM_BC + 1)) * sizeof(float); }
+
+// grid (sample groups, ceil(D/SM_BC)).  A CTA walks the sample tiles g, g+G, ... of its group and keeps
+// its slice of dW0 = h0^T dh1' in registers; it also writes the dE chunk of every tile it visits.
+template <int H1>
+__global__ void __launch_bounds__(256) small_mlp_bwd_input_kernel(
+    const float* __restrict__ W0 /*[D][H1]*/, const float* __restrict__ h0, const float* __restrict__ dh1 /*[B][H1]*/,
+    const float* __restrict__ dz, const float* __restrict__ svec /*[B][K] or null*/, int K, int B, int D,
+    float* __restrict__ dE, float* __restrict__ w0_partial /*[gridDim.x][D*H1]*/) {
+    extern __shared__ __align__(16) float smem_b[];
+    float (*ds)[H1 + 4] = reinterpret_cast<float (*)[H1 + 4]>(smem_b);                                  // [SM_TB][H1+4]
+    float (*ws)[H1] = reinterpret_cast<float (*)[H1]>(smem_b + SM_TB * (H1 + 4));                        // [SM_BC][H1]
+    float (*hs)[SM_BC + 1] = reinterpret_cast<float (*)[SM_BC + 1]>(smem_b + SM_TB * (H1 + 4) + SM_BC * H1);   // [SM_TB][SM_BC+1]
+    float (*fm)[SM_BC + 1] = reinterpret_cast<float (*)[SM_BC + 1]>(smem_b + SM_TB * (H1 + 4) + SM_BC * H1 + SM_TB * (SM_BC + 1));
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.y * SM_BC;
+    const int cw = min(SM_BC, D - c0);
+    constexpr int NQ = (SM_BC * (H1 / 4) + 255) / 256;     // (c, 4 j) items per thread
+    float4 wacc[NQ];
+#pragma unroll
+    for (int u = 0; u < NQ; ++u) wacc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = tid; q < SM_BC * H1; q += 256) ws[q / H1][q % H1] = (q / H1) < cw ? W0[(size_t)c0 * H1 + q] : 0.f;
+    const int ntiles = (B + SM_TB - 1) / SM_TB;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b0 = tile * SM_TB;
+        __syncthreads();
+        for (int q = tid; q < SM_TB * (SM_BC / 4); q += 256) {
+            int r = q / (SM_BC / 4), cc = (q % (SM_BC / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b0 + r < B && cc < cw) {
+                v = __ldg(reinterpret_cast<const float4*>(h0 + (size_t)(b0 + r) * D + c0 + cc));
+                if (svec) {   // FM part of the gradient: dz * (S - E); (c0 + cc) % K is a multiple of 4 -> one float4 of S
+                    float g = __ldg(dz + b0 + r);
+                    float4 sv = __ldg(reinterpret_cast<const float4*>(svec + (size_t)(b0 + r) * K + ((c0 + cc) % K)));
+                    t = make_float4(g * (sv.x - v.x), g * (sv.y - v.y), g * (sv.z - v.z), g * (sv.w - v.w));
+                }
+            }
+            hs[r][cc] = v.x; hs[r][cc + 1] = v.y; hs[r][cc + 2] = v.z; hs[r][cc + 3] = v.w;
+            fm[r][cc] = t.x; fm[r][cc + 1] = t.y; fm[r][cc + 2] = t.z; fm[r][cc + 3] = t.w;
+        }
+        for (int q = tid; q < SM_TB * (H1 / 4); q += 256) {
+            int r = q / (H1 / 4), jj = (q % (H1 / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b0 + r < B) v = __ldg(reinterpret_cast<const float4*>(dh1 + (size_t)(b0 + r) * H1 + jj));
+            *reinterpret_cast<float4*>(&ds[r][jj]) = v;
+        }
+        __syncthreads();
+        // (b) dW0[c][j] += sum_s h0[s][c] * dh1[s][j]   (samples walked in order -> deterministic)
+#pragma unroll
+        for (int u = 0; u < NQ; ++u) {
+            int q = tid + u * 256;
+            if (q < SM_BC * (H1 / 4)) {
+                int c = q / (H1 / 4), j4 = (q % (H1 / 4)) * 4;
+                float4 a4 = wacc[u];
+#pragma unroll 8
+                for (int r = 0; r < SM_TB; ++r) {
+                    float a = hs[r][c];
+                    float4 d = *reinterpret_cast<const float4*>(&ds[r][j4]);
+                    a4.x = fmaf(a, d.x, a4.x); a4.y = fmaf(a, d.y, a4.y); a4.z = fmaf(a, d.z, a4.z); a4.w = fmaf(a, d.w, a4.w);
+                }
+                wacc[u] = a4;
+            }
+        }
+        __syncthreads();
+        // (a) dE[s][c] = sum_j dh1[s][j] W0[c][j] + dz[s] * (S[s][c % K] - h0[s][c])   (in place in hs)
+        {
+            const int s = tid & (SM_TB - 1), half = tid >> 7;
+            const int b = b0 + s;
+            float d[H1];
+#pragma unroll
+            for (int j = 0; j < H1; ++j) d[j] = ds[s][j];
+#pragma unroll 4
+            for (int c = half * (SM_BC / 2); c < (half + 1) * (SM_BC / 2); ++c) {
+                float a = fm[s][c];
+#pragma unroll
+                for (int j4 = 0; j4 < H1 / 4; ++j4) {
+                    float4 w = *reinterpret_cast<const float4*>(&ws[c][j4 * 4]);
+                    a = fmaf(d[j4 * 4], w.x, a); a = fmaf(d[j4 * 4 + 1], w.y, a);
+                    a = fmaf(d[j4 * 4 + 2], w.z, a); a = fmaf(d[j4 * 4 + 3], w.w, a);
+                }
+                hs[s][c] = a;
+            }
+        }
+        __syncthreads();
+        for (int q = tid; q < SM_TB * (SM_BC / 4); q += 256) {
+            int r = q / (SM_BC / 4), cc = (q % (SM_BC / 4)) * 4;
+            if (b0 + r < B && cc < cw)
+                *reinterpret_cast<float4*>(dE + (size_t)(b0 + r) * D + c0 + cc) = make_float4(hs[r][cc], hs[r][cc + 1], hs[r][cc + 2], hs[r][cc + 3]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NQ; ++u) {
+        int q = tid + u * 256;
+        if (q < SM_BC * (H1 / 4)) {
+            int c = q / (H1 / 4), j4 = (q % (H1 / 4)) * 4;
+            if (c < cw) *reinterpret_cast<float4*>(w0_partial + (size_t)blockIdx.x * D * H1 + (size_t)(c0 + c) * H1 + j4) = wacc[u];
+        }
+    }
+}

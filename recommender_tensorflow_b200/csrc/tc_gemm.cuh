@@ -1,0 +1,376 @@
+// Tensor-core path of the DNN tower for hidden_units that make it a real GEMM (BASELINE.json
+// configs[2]: hidden [256,128], batch 65536 -> 55 GFLOP per step).
+//
+// fp32 parity (1e-5 relative) rules out plain TF32 (10-bit mantissa), so every product is formed
+// as a 3xTF32 split accumulated in fp32 in tensor memory:
+//        a*b  ~=  a_hi*b_hi + a_lo*b_hi + a_hi*b_lo ,   x_hi = tf32_rn(x), x_lo = tf32_rn(x - x_hi)
+// (relative error <= ~2^-21 per product, measured against the fp64 oracle in the tests).
+//
+// Blackwell mapping (one CTA per 128 x BN output tile, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles (SWIZZLE_128B) of A and B into a ring of
+//               shared-memory stages, completion on "full" mbarriers
+//   warps 2..7  splitters: rewrite each landed fp32 tile in place as x_hi and write x_lo beside it
+//               (element-wise, so the swizzle pattern is preserved), fence.proxy.async, arrive on
+//               "split" mbarriers
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma kind::tf32 (M=128, N=BN, K=8), three
+//               per k-step, accumulating in TMEM; tcgen05.commit releases the stage ("empty") and
+//               finally signals the epilogue
+//   warps 4..7  (after the main loop) epilogue: tcgen05.ld the fp32 accumulator (32 TMEM lanes per warp), apply the fused
+//               epilogue (bias+ReLU / ReLU mask / FM-gradient add / split-K partial) and store
+// Operand layouts: K-major (row-major [rows, K]) for the forward and backward-data GEMMs;
+// MN-major (row-major [K, rows]) for the weight-gradient GEMM whose reduction runs over the batch.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mlp_kernels.cuh"
+
+namespace tc {
+
+constexpr int BM = 128;          // output rows per CTA (= TMEM lanes)
+constexpr int BK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;        // tf32 K per tcgen05.mma
+constexpr int NTHREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (spins > (1u << 26)) __trap();   // a protocol bug must fault, not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B
+//   K-major : rows of 128 B (32 fp32 of K), 8-row atoms 1024 B apart (SBO); LBO unused
+//   MN-major (32-bit operands must use SWIZZLE_128B_BASE32B, TMA mode 128B_ATOM_32B): rows of 128 B
+//             (32 fp32 of M/N), row index = k; 4-k-row atoms SBO = 512 B apart, 32-wide M/N chunks LBO apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;      // descriptor version (Blackwell)
+    d |= (uint64_t)layout_type << 61;   // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+    return d;
+}
+// instruction descriptor: D fp32, A/B tf32, dense, M=128, N
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// round-to-nearest (ties away) to tf32: hi keeps 11 significant bits, so |x - hi| <= 2^-12 |x| and the
+// second split leaves a residual of ~2^-24 |x| (fp32 level); the low 13 bits are zero so the tensor core
+// sees exactly representable operands whatever its own input rounding is.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
+struct Params {
+    int M, N, K;              // C[M,N] = A(M,K) * B(K,N); K-major mode: K % 32 == 0 not required (TMA zero-fills)
+    int k_per_split;          // MN-major (weight-gradient) mode: K range per blockIdx.z
+    float* C; int ldc; size_t c_split_stride;
+    int epi;                  // EPI_*
+    EpiArgs ep;
+    int split_a, split_b;     // 1: operand is raw fp32, split in the kernel; 0: hi/lo come from two tensor maps
+};
+
+template <int BN>
+struct Smem {
+    static constexpr int A_BYTES = BM * BK * 4;          // 16 KB
+    static constexpr int B_BYTES = BN * BK * 4;
+    static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = (BN > 128) ? 2 : 3;
+    static constexpr int TOTAL = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// MODE 0: A K-major [M,K], B K-major [N,K].   MODE 1: A MN-major [K,M], B MN-major [K,N] (3-D maps, see host).
+template <int BN, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                                                           const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
+                                                           Params p) {
+    using S = Smem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE);
+    uint64_t* full = bars;                       // [STAGES] TMA landed
+    uint64_t* split = bars + S::STAGES;          // [STAGES] hi/lo ready
+    uint64_t* empty = bars + 2 * S::STAGES;      // [STAGES] MMAs that read the stage retired
+    uint64_t* accum = bars + 3 * S::STAGES;      // accumulator complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S::STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = MODE == 1 ? blockIdx.z * p.k_per_split : 0;
+    const int kend = MODE == 1 ? min(p.K, kbeg + p.k_per_split) : p.K;
+    const int nkb = (kend - kbeg + BK - 1) / BK;
+    constexpr uint32_t TMEM_COLS = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+    constexpr int n_split_threads = 192;   // warps 2..7 split; warps 4..7 then run the epilogue
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&split[s], n_split_threads);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            const uint32_t bytes = (p.split_a ? S::A_BYTES : 2 * S::A_BYTES) + (p.split_b ? S::B_BYTES : 2 * S::B_BYTES);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % S::STAGES;
+                if (kb >= S::STAGES) mbar_wait(&empty[s], ((kb / S::STAGES) - 1) & 1);
+                uint8_t* st = smem + s * S::STAGE;
+                uint8_t *a_hi = st, *a_lo = st + S::A_BYTES, *b_hi = st + 2 * S::A_BYTES, *b_lo = st + 2 * S::A_BYTES + S::B_BYTES;
+                mbar_expect_tx(&full[s], bytes);
+                const int k0 = kbeg + kb * BK;
+                if (MODE == 0) {
+                    tma_load_2d(a_hi, &mapA_hi, &full[s], k0, m0);
+                    if (!p.split_a) tma_load_2d(a_lo, &mapA_lo, &full[s], k0, m0);
+                    tma_load_2d(b_hi, &mapB_hi, &full[s], k0, n0);
+                    if (!p.split_b) tma_load_2d(b_lo, &mapB_lo, &full[s], k0, n0);
+                } else {
+                    tma_load_3d(a_hi, &mapA_hi, &full[s], 0, k0, m0 / 32);
+                    tma_load_3d(b_hi, &mapB_hi, &full[s], 0, k0, n0 / 32);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, MODE == 1, MODE == 1);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % S::STAGES;
+                mbar_wait(&split[s], (kb / S::STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_u32(smem + s * S::STAGE);
+                const uint32_t a_hi = st, a_lo = st + S::A_BYTES, b_hi = st + 2 * S::A_BYTES, b_lo = st + 2 * S::A_BYTES + S::B_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                    // K-major: +32 bytes inside the 128-byte swizzle row; MN-major: next 8-row (1024 B) atom
+                    const uint32_t adv = MODE == 0 ? ks * UMMA_K * 4 : ks * 1024;
+                    const uint32_t lbo = MODE == 0 ? 16 : BK * 128, sbo = MODE == 0 ? 1024 : 512, lt = MODE == 0 ? 2 : 1;
+                    const uint64_t dah = make_desc(a_hi + adv, lbo, sbo, lt), dal = make_desc(a_lo + adv, lbo, sbo, lt);
+                    const uint64_t dbh = make_desc(b_hi + adv, lbo, sbo, lt), dbl = make_desc(b_lo + adv, lbo, sbo, lt);
+                    // The tensor core truncates when it folds a product group into the fp32 accumulator, so the
+                    // large hi*hi sum and the small cross terms live in separate accumulators (columns [0,BN) and
+                    // [BN,2BN)) and are added with round-to-nearest in the epilogue.
+                    umma_tf32(tmem_base, dah, dbh, idesc, (kb | ks) != 0);
+                    umma_tf32(tmem_base + BN, dal, dbh, idesc, (kb | ks) != 0);
+                    umma_tf32(tmem_base + BN, dah, dbl, idesc, 1);
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(accum);
+        }
+    } else {
+        // ------------------------------------------------------------------ splitters (warps 2..7, 192 threads)
+        const int t = threadIdx.x - 64;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % S::STAGES;
+            mbar_wait(&full[s], (kb / S::STAGES) & 1);
+            uint8_t* st = smem + s * S::STAGE;
+            if (p.split_a) {
+                float4* hi = reinterpret_cast<float4*>(st);
+                float4* lo = reinterpret_cast<float4*>(st + S::A_BYTES);
+#pragma unroll 4
+                for (int i = t; i < S::A_BYTES / 16; i += n_split_threads) {
+                    float4 x = hi[i];
+                    float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+                    float4 l = make_float4(tf32_hi(x.x - h.x), tf32_hi(x.y - h.y), tf32_hi(x.z - h.z), tf32_hi(x.w - h.w));
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+            }
+            if (p.split_b) {
+                float4* hi = reinterpret_cast<float4*>(st + 2 * S::A_BYTES);
+                float4* lo = reinterpret_cast<float4*>(st + 2 * S::A_BYTES + S::B_BYTES);
+#pragma unroll 4
+                for (int i = t; i < S::B_BYTES / 16; i += n_split_threads) {
+                    float4 x = hi[i];
+                    float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+                    float4 l = make_float4(tf32_hi(x.x - h.x), tf32_hi(x.y - h.y), tf32_hi(x.z - h.z), tf32_hi(x.w - h.w));
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+            mbar_arrive(&split[s]);
+        }
+    }
+    if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue (warps 4..7)
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        mbar_wait(accum, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int gm = m0 + q * 32 + lane;
+        float* Cz = p.C + (size_t)blockIdx.z * p.c_split_stride;
+        const float dzm = (p.epi == EPI_DE && gm < p.M) ? p.ep.dz[gm] : 0.f;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32], vx[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), vx);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += vx[i];
+            if (gm < p.M) {
+#pragma unroll
+                for (int c4 = 0; c4 < 32; c4 += 4) {
+                    const int gn = n0 + c0 + c4;
+                    if (gn >= p.N) break;
+                    float o[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float x = v[c4 + c];
+                        const int n = gn + c;
+                        if (n < p.N) {
+                            if (p.epi == EPI_BIAS_RELU) x = fmaxf(x + __ldg(p.ep.bias + n), 0.f);
+                            else if (p.epi == EPI_MASK) x = __ldg(p.ep.act + (size_t)gm * p.ep.ld_act + n) > 0.f ? x : 0.f;
+                            else if (p.epi == EPI_DE && p.ep.s)
+                                x += dzm * (__ldg(p.ep.s + (size_t)gm * p.ep.K + (n % p.ep.K)) - __ldg(p.ep.act + (size_t)gm * p.ep.ld_act + n));
+                        }
+                        o[c] = x;
+                    }
+                    float* cp = Cz + (size_t)gm * p.ldc + gn;
+                    if (gn + 3 < p.N) *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
+                    else
+                        for (int c = 0; c < 4; ++c)
+                            if (gn + c < p.N) cp[c] = o[c];
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+// x -> (hi, lo) element-wise over a weight tensor (weights are static within a step)
+__global__ void split_tf32_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        float v = x[i], h = tf32_hi(v);
+        hi[i] = h;
+        lo[i] = tf32_hi(v - h);
+    }
+}
+// W [rows, cols] -> W^T hi / lo [cols, rows]
+__global__ void split_tf32_transpose_kernel(const float* __restrict__ x, int rows, int cols, float* __restrict__ hi, float* __restrict__ lo) {
+    __shared__ float tile[32][33];
+    int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int r = r0 + j;
+        tile[j][threadIdx.x] = (r < rows && c < cols) ? x[(size_t)r * cols + c] : 0.f;
+    }
+    __syncthreads();
+    int r = r0 + threadIdx.x;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int cc = blockIdx.x * 32 + j;
+        if (cc < cols && r < rows) {
+            float v = tile[threadIdx.x][j], h = tf32_hi(v);
+            hi[(size_t)cc * rows + r] = h;
+            lo[(size_t)cc * rows + r] = tf32_hi(v - h);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// row-major [rows, cols] fp32 (cols contiguous, leading dimension ld): box = 32 cols x box_rows, SWIZZLE_128B
+inline bool make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 4};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// row-major [krows, cols] viewed as [cols/32][krows][32]: box = 32 x box_k x chunks  (MN-major operand tiles)
+inline bool make_map_3d(CUtensorMap* m, const float* base, uint64_t krows, uint64_t cols, uint64_t ld, uint32_t box_k, uint32_t chunks) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {32, krows, cols / 32};
+    cuuint64_t strides[2] = {ld * 4, 32 * 4};
+    cuuint32_t box[3] = {32, box_k, chunks};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace tc

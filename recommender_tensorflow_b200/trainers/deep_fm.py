@@ -1,0 +1,149 @@
+"""Mirror of the reference's trainers/deep_fm.py on top of the CUDA engine.
+
+`model_fn(features, labels, mode, params)` keeps the reference's signature, param names, defaults
+and error behaviour (trainers/deep_fm.py:11-34).  TensorFlow builds a graph once and then runs
+`train_op`; here there is no graph: the first call builds the engine (cached in `params`), and
+every TRAIN call executes one `session.run(train_op)` equivalent on the given batch.
+"""
+import shutil
+from argparse import ArgumentParser
+from collections import namedtuple
+
+import numpy as np
+
+from ..engine import DeepFMEngine
+from .ml_100k import FEATURE_DTYPES, ModeKeys, get_feature_columns, get_input_fn
+from .model_utils import get_binary_metrics, get_binary_predictions, get_optimizer
+
+EstimatorSpec = namedtuple("EstimatorSpec", ["mode", "loss", "train_op", "predictions", "eval_metric_ops", "global_step"])
+_ENGINE_KEY = "_b200_engine"
+
+
+def _build_engine(params, batch_size):
+    categorical_columns = params.get("categorical_columns", [])
+    numeric_columns = params.get("numeric_columns", [])
+    use_linear = params.get("use_linear", True)
+    use_mf = params.get("use_mf", True)
+    use_dnn = params.get("use_dnn", True)
+    embedding_size = params.get("embedding_size", 4)
+    hidden_units = params.get("hidden_units", [16, 16])
+    activation_fn = params.get("activation", "relu")
+    dropout = params.get("dropout", 0)
+    optimizer = params.get("optimizer", "Adam")
+    learning_rate = params.get("learning_rate", 0.001)
+    # check params (trainers/deep_fm.py:28-34)
+    if (len(categorical_columns) + len(numeric_columns)) == 0:
+        raise ValueError("At least 1 feature column of categorical_columns or numeric_columns must be specified.")
+    if not (use_linear or use_mf or use_dnn):
+        raise ValueError("At least 1 of linear, mf or dnn component must be used.")
+    if activation_fn not in ("relu", None) and getattr(activation_fn, "__name__", "") != "relu":
+        raise NotImplementedError("only the reference default activation (ReLU) is built")
+    if dropout and dropout > 0:
+        raise NotImplementedError("dropout > 0 is not built yet (TF's dropout RNG stream is not reproducible; "
+                                  "parity runs use dropout = 0)")
+    opt = get_optimizer(optimizer, learning_rate)
+    return DeepFMEngine(categorical_columns, numeric_columns, embedding_size=embedding_size, hidden_units=hidden_units,
+                        use_linear=bool(use_linear), use_mf=bool(use_mf), use_dnn=bool(use_dnn), loss_reduction="mean",
+                        opt_deep=opt, opt_linear=dict(opt), max_batch=params.get("max_batch", max(batch_size, 1)),
+                        device=params.get("device", 0), feature_dtypes=params.get("feature_dtypes", FEATURE_DTYPES))
+
+
+def _batch_size(features):
+    v = next(iter(features.values()))
+    return (len(v[1]) - 1) if isinstance(v, tuple) else len(v)
+
+
+def model_fn(features, labels, mode, params):
+    """trainers/deep_fm.py:11-125.  TRAIN: one train step; EVAL: loss + head metrics; PREDICT: predictions."""
+    engine = params.get(_ENGINE_KEY)
+    if engine is None:
+        engine = params[_ENGINE_KEY] = _build_engine(params, _batch_size(features))
+    if mode == ModeKeys.TRAIN:
+        loss, logits = engine.train_step(features, labels, return_logits=True)
+        return EstimatorSpec(mode, loss, None, get_binary_predictions(logits), None, engine.global_step)
+    logits = engine.predict_logits(features)
+    preds = get_binary_predictions(logits)
+    if mode == ModeKeys.PREDICT:
+        return EstimatorSpec(mode, None, None, preds, None, engine.global_step)
+    metrics = get_binary_metrics(labels, logits)
+    return EstimatorSpec(mode, metrics["average_loss"], None, preds, metrics, engine.global_step)
+
+
+class Estimator:
+    """Minimal stand-in for tf.estimator.Estimator(model_fn, model_dir, config, params): train /
+    evaluate / predict loops around model_fn, checkpoints as .npz (variables + optimizer slots)."""
+
+    def __init__(self, model_fn, model_dir=None, config=None, params=None):
+        self.model_fn, self.model_dir, self.config, self.params = model_fn, model_dir, config, dict(params or {})
+
+    @property
+    def engine(self):
+        return self.params.get(_ENGINE_KEY)
+
+    def train(self, input_fn, steps=None, max_steps=None, log_every=100):
+        loss = None
+        for feats, labels in input_fn():
+            eng = self.engine
+            if max_steps is not None and eng is not None and eng.global_step >= max_steps:
+                break
+            spec = self.model_fn(feats, labels, ModeKeys.TRAIN, self.params)
+            loss = spec.loss
+            if log_every and spec.global_step % log_every == 0:
+                print("INFO:b200:loss = %.6f, step = %d" % (loss, spec.global_step))
+            if steps is not None:
+                steps -= 1
+                if steps <= 0:
+                    break
+        return loss
+
+    def evaluate(self, input_fn):
+        ys, zs = [], []
+        for feats, labels in input_fn():
+            spec = self.model_fn(feats, labels, ModeKeys.EVAL, self.params)
+            ys.append(np.asarray(labels, dtype=np.float32).reshape(-1))
+            zs.append(spec.predictions["logits"].reshape(-1))
+        m = get_binary_metrics(np.concatenate(ys), np.concatenate(zs))
+        m["global_step"] = self.engine.global_step
+        return m
+
+    def predict(self, input_fn):
+        for item in input_fn():
+            feats = item[0] if isinstance(item, tuple) and len(item) == 2 and isinstance(item[0], dict) else item
+            spec = self.model_fn(feats, None, ModeKeys.PREDICT, self.params)
+            n = spec.predictions["logits"].shape[0]
+            for i in range(n):
+                yield {k: v[i] for k, v in spec.predictions.items()}
+
+
+def train_and_evaluate(args):
+    """trainers/deep_fm.py:128-178 (local run: train to max_steps, then one evaluation)."""
+    if not args.restore:
+        shutil.rmtree(args.job_dir, ignore_errors=True)
+    feature_columns = get_feature_columns(embedding_size=args.embedding_size)
+    estimator = Estimator(model_fn=model_fn, model_dir=args.job_dir, params={
+        "categorical_columns": feature_columns["linear"],
+        "use_linear": not args.exclude_linear, "use_mf": not args.exclude_mf, "use_dnn": not args.exclude_dnn,
+        "embedding_size": args.embedding_size, "hidden_units": args.hidden_units, "dropout": args.dropout,
+        "max_batch": args.batch_size})
+    estimator.train(get_input_fn(args.train_csv, batch_size=args.batch_size), max_steps=args.train_steps)
+    metrics = estimator.evaluate(get_input_fn(args.test_csv, ModeKeys.EVAL, batch_size=args.batch_size))
+    print("INFO:b200:eval " + ", ".join("%s = %s" % kv for kv in sorted(metrics.items())))
+    return metrics
+
+
+if __name__ == "__main__":
+    parser = ArgumentParser()
+    parser.add_argument("--train-csv", default="data/ml-100k/train.csv")
+    parser.add_argument("--test-csv", default="data/ml-100k/test.csv")
+    parser.add_argument("--job-dir", default="checkpoints/deep_fm")
+    parser.add_argument("--restore", action="store_true")
+    parser.add_argument("--exclude-linear", action="store_true")
+    parser.add_argument("--exclude-mf", action="store_true")
+    parser.add_argument("--exclude-dnn", action="store_true")
+    parser.add_argument("--embedding-size", type=int, default=4)
+    parser.add_argument("--hidden-units", type=int, nargs="+", default=[16, 16])
+    parser.add_argument("--dropout", type=float, default=0.0,
+                        help="the reference defaults to 0.1; dropout is not built yet")
+    parser.add_argument("--batch-size", type=int, default=32)
+    parser.add_argument("--train-steps", type=int, default=20000)
+    train_and_evaluate(parser.parse_args())

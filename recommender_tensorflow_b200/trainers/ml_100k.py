@@ -38,3 +38,100 @@ def get_feature_columns(embedding_size=4):
     linear_columns = [user_fc, item_fc, age_buckets, gender_fc, occupation_fc, zipcode_fc, release_year_buckets] + genre_fc
     deep_columns = [fc.embedding_column(c, embedding_size) for c in linear_columns]
     return {"linear": linear_columns, "deep": deep_columns}
+
+
+class ModeKeys:
+    """tf.estimator.ModeKeys"""
+    TRAIN, EVAL, PREDICT = "train", "eval", "infer"
+
+
+def _parse_rows(csv_path):
+    """tf.data.TextLineDataset(csv).skip(1) + tf.decode_csv(value, DEFAULTS) (trainers/ml_100k.py:44-52):
+    RFC-4180 quoting, empty fields take the column default."""
+    with open(csv_path, newline="") as fh:
+        reader = csv.reader(fh)
+        next(reader, None)   # header
+        for row in reader:
+            if len(row) != len(COLUMNS):
+                raise ValueError("Expect %d fields but have %d in record" % (len(COLUMNS), len(row)))
+            yield row
+
+
+def _to_batch(rows, cutoff):
+    feats = {}
+    for j, (name, default) in enumerate(zip(COLUMNS, DEFAULTS)):
+        col = [r[j] for r in rows]
+        if isinstance(default[0], int):
+            feats[name] = np.array([int(v) if v != "" else default[0] for v in col], dtype=np.int32)
+        else:
+            feats[name] = np.array([(v if v != "" else default[0]).encode() for v in col], dtype=object)
+    label = feats.pop(LABEL_COL)
+    return feats, (label >= cutoff).astype(np.float32)   # tf.math.greater_equal(label, cutoff)
+
+
+def get_input_fn(csv_path, mode=ModeKeys.TRAIN, batch_size=32, cutoff=5, seed=None):
+    """trainers/ml_100k.py:42-61: skip header; TRAIN: shuffle(16*batch_size).repeat(); batch(batch_size).
+    Returns a callable producing an iterator of (features dict, label float32 [B])."""
+    def input_fn():
+        rng = np.random.default_rng(seed)
+        if mode == ModeKeys.TRAIN:
+            buf, cap = [], 16 * batch_size
+            batch = []
+            while True:                                   # repeat()
+                n_rows = 0
+                for row in _parse_rows(csv_path):
+                    n_rows += 1
+                    if len(buf) < cap:                    # shuffle buffer
+                        buf.append(row)
+                        continue
+                    j = int(rng.integers(0, cap))
+                    batch.append(buf[j])
+                    buf[j] = row
+                    if len(batch) == batch_size:
+                        yield _to_batch(batch, cutoff)
+                        batch = []
+                if n_rows == 0:
+                    return
+                # the shuffle buffer drains at the end of each epoch (shuffle precedes repeat)
+                rng.shuffle(buf)
+                for row in buf:
+                    batch.append(row)
+                    if len(batch) == batch_size:
+                        yield _to_batch(batch, cutoff)
+                        batch = []
+                buf = []
+        else:
+            batch = []
+            for row in _parse_rows(csv_path):
+                batch.append(row)
+                if len(batch) == batch_size:
+                    yield _to_batch(batch, cutoff)
+                    batch = []
+            if batch:
+                yield _to_batch(batch, cutoff)
+    return input_fn
+
+
+def write_synthetic_csv(path, n_rows, seed=20260101):
+    """ML-100K-shaped CSV with the exact 42-column header of COLUMNS."""
+    from .. import synth
+    ml = synth.ML100K(seed)
+    rng = np.random.default_rng(seed + 1)
+    feats, _ = ml.batch(n_rows, rng)
+    rating = rng.choice(np.arange(1, 6), size=n_rows, p=[.061, .114, .271, .342, .212])
+    with open(path, "w", newline="") as fh:
+        wr = csv.writer(fh)
+        wr.writerow(COLUMNS)
+        for i in range(n_rows):
+            row = []
+            for name, default in zip(COLUMNS, DEFAULTS):
+                if name == LABEL_COL:
+                    row.append(int(rating[i]))
+                elif name in feats:
+                    v = feats[name][i]
+                    row.append(v.decode() if isinstance(v, bytes) else int(v))
+                elif name == "title":
+                    row.append("Movie, The (%d)" % (1900 + i % 100))      # exercises quoting
+                else:
+                    row.append(0 if isinstance(default[0], int) else "null")
+            wr.writerow(row)

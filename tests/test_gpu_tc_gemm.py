@@ -1,0 +1,45 @@
+"""GPU: the 3xTF32 tcgen05 GEMM of the tower against float64 matmul (fp32-level accuracy required)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(mode, M, N, K, splits=1, seed=0):
+    import torch
+    from recommender_tensorflow_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    if mode == 1:
+        A = torch.randn(K, M, generator=g)
+        B = torch.randn(K, N, generator=g)
+        ref = A.double().t() @ B.double()
+    else:
+        A = torch.randn(M, K, generator=g)
+        B = torch.randn(N, K, generator=g)
+        ref = A.double() @ B.double().t()
+    Ad, Bd = A.cuda(), B.cuda()
+    Cd = torch.full((M, N), float("nan"), device="cuda")
+    rc = lib.dfm_test_tc_gemm(mode, C.c_void_p(Ad.data_ptr()), C.c_void_p(Bd.data_ptr()), C.c_void_p(Cd.data_ptr()), M, N, K, splits)
+    assert rc == 0, lib.dfm_last_error(None)
+    got = Cd.cpu().double()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    ref32 = (A @ B.t() if mode != 1 else A.t() @ B).double()
+    err32 = (ref32 - ref).abs().max().item()
+    return err, scale, err32
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 128, 64), (1000, 416, 256), (4096, 256, 416), (512, 128, 256)])
+def test_kmajor_fp32_accuracy(mode, M, N, K):
+    err, scale, err32 = _run(mode, M, N, K)
+    assert err <= max(4 * err32, 3e-6 * scale), (err, scale, err32)
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(128, 128, 64, 1), (128, 256, 4096, 4), (416, 256, 8192, 8), (256, 128, 1000, 3)])
+def test_mnmajor_weight_gradient(M, N, K, splits):
+    err, scale, err32 = _run(1, M, N, K, splits)
+    assert err <= max(4 * err32, 3e-6 * scale), (err, scale, err32)
