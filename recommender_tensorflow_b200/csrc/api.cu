@@ -18,6 +18,13 @@
 #include "tc_gemm.cuh"
 
 static thread_local std::string g_create_error;
+struct dfm_handle;
+struct EpiArgs;
+static int tc_setup_once();
+static int tc_gemm_kmajor(dfm_handle* h, const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
+                          float* C, int ldc, int M, int N, int K, int epi, const EpiArgs& ep, cudaStream_t st);
+static int tc_gemm_mnmajor(dfm_handle* h, const float* A, int lda, const float* B, int ldb, float* Cpart, int M, int N, int K, int splits,
+                           int* k_per_split_out, cudaStream_t st);
 
 struct DenseT {
     std::string name;
@@ -67,6 +74,7 @@ struct dfm_handle {
     float* splitk = nullptr; int splits = 1, k_chunk = 0;
     float* colpart = nullptr; int rows_per_chunk = 512;
     float* head_part = nullptr; int head_blocks = 0;
+    bool tc_mlp = false; float* tc_w = nullptr; int64_t tc_off[DFM_MAX_HIDDEN] = {0}; int tc_nz[DFM_MAX_HIDDEN] = {0};
     bool small_mlp = false; SmallMlpDesc sm{}; int small_grid = 0; size_t small_smem = 0;
     float *up_partial = nullptr, *w0_partial = nullptr;
     float* d_loss = nullptr; float* d_dzsum = nullptr;
@@ -146,7 +154,7 @@ static void free_all(dfm_handle* h) {
                     h->ds1, h->ds2, h->dg, h->ids, h->keys[0], h->keys[1], h->vals[0], h->vals[1], h->sort_temp, h->flags,
                     h->scan_temp, h->seg_total, h->seg_cnt, h->row_start, h->row_piece0, h->piece_start, h->piece_row,
                     h->piece_sum, h->h0, h->s, h->zacc, h->logits, h->dz, h->dE, h->splitk, h->colpart, h->head_part,
-                    h->d_loss, h->d_dzsum, h->d_err, h->alpha_d, h->alpha_l, h->up_partial, h->w0_partial, h->hot_list};
+                    h->d_loss, h->d_dzsum, h->d_err, h->alpha_d, h->alpha_l, h->up_partial, h->w0_partial, h->hot_list, h->tc_w};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 1; i <= DFM_MAX_HIDDEN; ++i) { if (h->act[i]) cudaFree(h->act[i]); if (h->dact[i]) cudaFree(h->dact[i]); }
     for (auto& s : h->stage) {
@@ -339,7 +347,27 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
         }
     }
     h->splits = (int)std::min<int64_t>(64, std::max<int64_t>(1, (Bm + 1023) / 1024));
-    if (dalloc(h, &h->splitk, (size_t)h->splits * max_w)) return DFM_ERR_CUDA;
+    size_t splitk_elems = (size_t)h->splits * max_w;
+    // tensor-core tower (3xTF32 tcgen05): every hidden width a multiple of 32 and at least one >= 64
+    if (h->use_dnn && h->L >= 1 && getenv("DFM_NO_TC") == nullptr && prop.major == 10) {
+        bool ok = true, big = false;
+        for (int i = 0; i < h->L; ++i) { ok = ok && (h->hidden[i] % 32 == 0); big = big || h->hidden[i] >= 64; }
+        if (ok && big && tc_setup_once() > 0) {
+            h->tc_mlp = true;
+            int64_t off_w = 0;
+            int in = dK;
+            for (int i = 0; i < h->L; ++i) {
+                h->tc_off[i] = off_w;
+                off_w += 4 * (int64_t)pad32((int64_t)in * h->hidden[i]);     // W hi, W lo, W^T hi, W^T lo
+                const int m_tiles = (in + 127) / 128, n_tiles = (h->hidden[i] + 255) / 256;
+                h->tc_nz[i] = std::max(1, std::min(128, h->sm_count / std::max(1, m_tiles * n_tiles)));
+                splitk_elems = std::max(splitk_elems, (size_t)h->tc_nz[i] * in * h->hidden[i]);
+                in = h->hidden[i];
+            }
+            if (dalloc(h, &h->tc_w, (size_t)off_w)) return DFM_ERR_CUDA;
+        }
+    }
+    if (dalloc(h, &h->splitk, splitk_elems)) return DFM_ERR_CUDA;
     const int64_t chunks = (Bm + h->rows_per_chunk - 1) / h->rows_per_chunk;
     if (dalloc(h, &h->colpart, (size_t)chunks * std::max<int64_t>(max_n, (int64_t)h->dn * (K + 1)))) return DFM_ERR_CUDA;
     h->head_blocks = (int)std::min<int64_t>(h->sm_count * 8, std::max<int64_t>(1, (Bm + 7) / 8));
@@ -677,7 +705,25 @@ static int forward_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t 
         if (ph) { ph->next(); }
         return DFM_OK;
     }
-    if (h->use_dnn) {
+    if (h->use_dnn && h->tc_mlp) {
+        int in = dK;
+        for (int i = 0; i < h->L; ++i) {
+            const DenseT* W = find_dense(h, "W" + std::to_string(i));
+            const DenseT* b = find_dense(h, "b" + std::to_string(i));
+            const int out = h->hidden[i];
+            const int64_t wsz = pad32((int64_t)in * out);
+            float* wt = h->tc_w + h->tc_off[i];
+            (void)wsz;
+            // forward needs W^T [out, in] (K-major B operand); both operands are split into tf32 hi/lo in the kernel
+            tc::split_tf32_transpose_kernel<<<dim3(cdiv(out, 32), cdiv(in, 32)), dim3(32, 8), 0, st>>>(h->dw + W->off, in, out, wt, nullptr);
+            h->launches += 1;
+            EpiArgs ep{}; ep.bias = h->dw + b->off;
+            int rc = tc_gemm_kmajor(h, h->act[i], nullptr, in, wt, nullptr, in, h->act[i + 1], out, B, out, in, EPI_BIAS_RELU, ep, st);
+            if (rc) return rc;
+            in = out;
+        }
+        hL = h->act[h->L]; H = in;
+    } else if (h->use_dnn) {
         int in = dK;
         for (int i = 0; i < h->L; ++i) {
             const DenseT* W = find_dense(h, "W" + std::to_string(i));
@@ -790,13 +836,32 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
                 const DenseT* b = find_dense(h, "b" + std::to_string(i));
                 // gW_i [in,out] = act_i^T [in,B] * dh_{i+1} [B,out]   (deterministic split over the batch)
                 EpiArgs none{};
-                launch_sgemm<false, false, EPI_NONE>(h, h->act[i], in, h->dact[i + 1], out, h->splitk, out, in, out, B, nsplit, k_chunk, none, st);
-                reduce_partials_kernel<<<cdiv((int64_t)in * out, 256), 256, 0, st>>>(h->splitk, nsplit, (size_t)in * out, (int64_t)in * out,
+                const bool tc_wgrad = h->tc_mlp && in % 32 == 0 && B >= 1024;
+                int nparts = nsplit;
+                if (tc_wgrad) {
+                    int rc2 = tc_gemm_mnmajor(h, h->act[i], in, h->dact[i + 1], out, h->splitk, in, out, B, h->tc_nz[i], &nparts, st);
+                    if (rc2) return rc2;
+                } else {
+                    launch_sgemm<false, false, EPI_NONE>(h, h->act[i], in, h->dact[i + 1], out, h->splitk, out, in, out, B, nsplit, k_chunk, none, st);
+                }
+                reduce_partials_kernel<<<cdiv((int64_t)in * out, 256), 256, 0, st>>>(h->splitk, nparts, (size_t)in * out, (int64_t)in * out,
                                                                                      h->dg + W->off);
                 h->launches++;
                 launch_colsum(h, h->dact[i + 1], out, nullptr, B, out, h->dg + b->off, st);
                 // dh_i [B,in] = dh_{i+1} [B,out] * W_i^T
-                if (i > 0) {
+                if (h->tc_mlp) {
+                    const float* w_hi = h->dw + W->off; const float* w_lo = nullptr;   // W [in, out] is already K-major for this GEMM
+                    EpiArgs ep{};
+                    int rc2;
+                    if (i > 0) {
+                        ep.act = h->act[i]; ep.ld_act = in;
+                        rc2 = tc_gemm_kmajor(h, h->dact[i + 1], nullptr, out, w_hi, w_lo, out, h->dact[i], in, B, in, out, EPI_MASK, ep, st);
+                    } else {
+                        ep.act = h->h0; ep.ld_act = dK; ep.dz = h->dz; ep.s = h->use_mf ? h->s : nullptr; ep.K = K;
+                        rc2 = tc_gemm_kmajor(h, h->dact[1], nullptr, out, w_hi, w_lo, out, h->dE, dK, B, dK, out, EPI_DE, ep, st);
+                    }
+                    if (rc2) return rc2;
+                } else if (i > 0) {
                     EpiArgs ep{}; ep.act = h->act[i]; ep.ld_act = in;
                     launch_sgemm<true, true, EPI_MASK>(h, h->dact[i + 1], out, h->dw + W->off, out, h->dact[i], in, B, in, out, 1,
                                                        (out + 15) / 16 * 16, ep, st);
@@ -1138,7 +1203,7 @@ static int tc_gemm_kmajor(dfm_handle* h, const float* A_hi, const float* A_lo, i
 // Cpartial[z][M,N] = sum over k in split z of A[k,M]^T * B[k,N]  (both MN-major, reduction over rows = batch)
 static int tc_gemm_mnmajor(dfm_handle* h, const float* A, int lda, const float* B, int ldb, float* Cpart, int M, int N, int K, int splits,
                            int* k_per_split_out, cudaStream_t st) {
-    if (M % 32 || N % 32 || N > 256) FAIL(DFM_ERR_UNSUPPORTED, "tc_gemm_mnmajor needs M, N multiples of 32 and N <= 256");
+    if (M % 32 || N % 32) FAIL(DFM_ERR_UNSUPPORTED, "tc_gemm_mnmajor needs M, N multiples of 32");
     const int BN = N > 128 ? 256 : 128;
     CUtensorMap ma, mb;
     bool ok = tc::make_map_3d(&ma, A, K, M, lda, tc::BK, tc::BM / 32) && tc::make_map_3d(&mb, B, K, N, ldb, tc::BK, BN / 32);

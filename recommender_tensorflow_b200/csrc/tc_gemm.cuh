@@ -256,45 +256,69 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
             mbar_arrive(&split[s]);
         }
     }
-    if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue (warps 4..7)
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    {
+        // ------------------------------------------------------------------ epilogue (all 8 warps)
+        // Warp w may read TMEM lanes [32*(w%4), +32); warps w and w+4 share a lane quarter and take alternate
+        // 32-column chunks.  All MMAs have retired, so the operand stages are free: each 32x32 block is
+        // transposed through shared memory (TMEM yields one row per lane) so that every global access of the
+        // fused epilogue is a coalesced 16-byte-per-lane access, with all loads of a block issued up front.
+        __syncwarp();
+        const int q = warp & 3, half = warp >> 2;
         mbar_wait(accum, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int gm = m0 + q * 32 + lane;
         float* Cz = p.C + (size_t)blockIdx.z * p.c_split_stride;
-        const float dzm = (p.epi == EPI_DE && gm < p.M) ? p.ep.dz[gm] : 0.f;
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            float v[32], vx[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), vx);
+        float* tb = reinterpret_cast<float*>(smem) + warp * (32 * 36);
+        const int row0 = m0 + q * 32;
+        const int rsub = lane >> 3, cg = lane & 7;
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+            if (n0 + c0 >= p.N) break;
+            {
+                float v[32], vx[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), vx);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += vx[i];
-            if (gm < p.M) {
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(tb + lane * 36 + 4 * j) =
+                        make_float4(v[4 * j] + vx[4 * j], v[4 * j + 1] + vx[4 * j + 1], v[4 * j + 2] + vx[4 * j + 2], v[4 * j + 3] + vx[4 * j + 3]);
+            }
+            __syncwarp();
+            const int n = n0 + c0 + cg * 4;
+            const bool nok = n < p.N;           // N % 4 == 0 on this path
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.epi == EPI_BIAS_RELU && nok) bias4 = __ldg(reinterpret_cast<const float4*>(p.ep.bias + n));
+            const int nk = (p.epi == EPI_DE) ? (n % p.ep.K) : 0;
+            float4 xa[8], xs[8];
+            float xd[8];
 #pragma unroll
-                for (int c4 = 0; c4 < 32; c4 += 4) {
-                    const int gn = n0 + c0 + c4;
-                    if (gn >= p.N) break;
-                    float o[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float x = v[c4 + c];
-                        const int n = gn + c;
-                        if (n < p.N) {
-                            if (p.epi == EPI_BIAS_RELU) x = fmaxf(x + __ldg(p.ep.bias + n), 0.f);
-                            else if (p.epi == EPI_MASK) x = __ldg(p.ep.act + (size_t)gm * p.ep.ld_act + n) > 0.f ? x : 0.f;
-                            else if (p.epi == EPI_DE && p.ep.s)
-                                x += dzm * (__ldg(p.ep.s + (size_t)gm * p.ep.K + (n % p.ep.K)) - __ldg(p.ep.act + (size_t)gm * p.ep.ld_act + n));
-                        }
-                        o[c] = x;
+            for (int it = 0; it < 8; ++it) {
+                const int gm = row0 + it * 4 + rsub;
+                xa[it] = make_float4(0.f, 0.f, 0.f, 0.f); xs[it] = xa[it]; xd[it] = 0.f;
+                if (nok && gm < p.M) {
+                    if (p.epi == EPI_MASK) xa[it] = __ldg(reinterpret_cast<const float4*>(p.ep.act + (size_t)gm * p.ep.ld_act + n));
+                    else if (p.epi == EPI_DE && p.ep.s) {
+                        xa[it] = __ldg(reinterpret_cast<const float4*>(p.ep.act + (size_t)gm * p.ep.ld_act + n));
+                        xs[it] = __ldg(reinterpret_cast<const float4*>(p.ep.s + (size_t)gm * p.ep.K + nk));
+                        xd[it] = __ldg(p.ep.dz + gm);
                     }
-                    float* cp = Cz + (size_t)gm * p.ldc + gn;
-                    if (gn + 3 < p.N) *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
-                    else
-                        for (int c = 0; c < 4; ++c)
-                            if (gn + c < p.N) cp[c] = o[c];
                 }
             }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + rsub, gm = row0 + r;
+                float4 x = *reinterpret_cast<const float4*>(tb + r * 36 + cg * 4);
+                if (p.epi == EPI_BIAS_RELU) {
+                    x.x = fmaxf(x.x + bias4.x, 0.f); x.y = fmaxf(x.y + bias4.y, 0.f);
+                    x.z = fmaxf(x.z + bias4.z, 0.f); x.w = fmaxf(x.w + bias4.w, 0.f);
+                } else if (p.epi == EPI_MASK) {
+                    x.x = xa[it].x > 0.f ? x.x : 0.f; x.y = xa[it].y > 0.f ? x.y : 0.f;
+                    x.z = xa[it].z > 0.f ? x.z : 0.f; x.w = xa[it].w > 0.f ? x.w : 0.f;
+                } else if (p.epi == EPI_DE && p.ep.s) {
+                    x.x += xd[it] * (xs[it].x - xa[it].x); x.y += xd[it] * (xs[it].y - xa[it].y);
+                    x.z += xd[it] * (xs[it].z - xa[it].z); x.w += xd[it] * (xs[it].w - xa[it].w);
+                }
+                if (nok && gm < p.M) *reinterpret_cast<float4*>(Cz + (size_t)gm * p.ldc + n) = x;
+            }
+            __syncwarp();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -327,9 +351,14 @@ __global__ void split_tf32_transpose_kernel(const float* __restrict__ x, int row
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         int cc = blockIdx.x * 32 + j;
         if (cc < cols && r < rows) {
-            float v = tile[threadIdx.x][j], h = tf32_hi(v);
-            hi[(size_t)cc * rows + r] = h;
-            lo[(size_t)cc * rows + r] = tf32_hi(v - h);
+            float v = tile[threadIdx.x][j];
+            if (lo) {
+                float h = tf32_hi(v);
+                hi[(size_t)cc * rows + r] = h;
+                lo[(size_t)cc * rows + r] = tf32_hi(v - h);
+            } else {
+                hi[(size_t)cc * rows + r] = v;     // plain transpose
+            }
         }
     }
 }

@@ -114,6 +114,15 @@ def test_deepfm_hot_rows_batch4096():
     _run_steps(eng, ora, [ml.batch(4096, rng) for _ in range(4)], "hot")
 
 
+@pytest.mark.parametrize("hidden,batch", [((256, 128), 4096), ((64, 32), 1500), ((128,), 2048)])
+def test_deepfm_tensor_core_tower(hidden, batch):
+    """configs[2] shape: k=16, hidden [256,128] -> 3xTF32 tcgen05 GEMM tower, fp32-level parity."""
+    eng = _ml_engine(k=16, hidden=hidden, max_batch=batch)
+    ora, _ = make_pair(eng, seed=9)
+    ml, rng = synth.ML100K(), np.random.default_rng(19)
+    _run_steps(eng, ora, [ml.batch(batch, rng) for _ in range(3)], "tc-tower%r" % (hidden,))
+
+
 def test_wide_deep_cfg2():
     """configs[1]: wide&deep = no FM, SUM loss, Adagrad (dnn side) + FTRL (linear side)."""
     eng = _ml_engine(use_mf=False, loss_reduction="sum", opt_deep=default_optimizer("Adagrad", 0.001),
