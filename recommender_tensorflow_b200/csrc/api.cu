@@ -17,6 +17,10 @@
 #include "small_mlp.cuh"
 #include "tc_gemm.cuh"
 
+#ifndef TC_BK
+#define TC_BK 32   // k-block depth of the tcgen05 GEMMs (16 gives a deeper TMA ring; measured equal, smem bandwidth is the limit)
+#endif
+
 static thread_local std::string g_create_error;
 struct dfm_handle;
 struct EpiArgs;
@@ -1185,16 +1189,17 @@ extern "C" int dfm_test_fingerprint64(const uint8_t* bytes_dev, const int32_t* o
 static int tc_gemm_kmajor(dfm_handle* h, const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
                           float* C, int ldc, int M, int N, int K, int epi, const EpiArgs& ep, cudaStream_t st) {
     const int BN = N > 128 ? 256 : 128;
+    const int bk = TC_BK;
     CUtensorMap ma, mal, mb, mbl;
-    bool ok = tc::make_map_2d(&ma, A_hi, M, K, lda, tc::BM) && tc::make_map_2d(&mal, A_lo ? A_lo : A_hi, M, K, lda, tc::BM) &&
-              tc::make_map_2d(&mb, B_hi, N, K, ldb, BN) && tc::make_map_2d(&mbl, B_lo ? B_lo : B_hi, N, K, ldb, BN);
+    bool ok = tc::make_map_2d(&ma, A_hi, M, K, lda, tc::BM, bk) && tc::make_map_2d(&mal, A_lo ? A_lo : A_hi, M, K, lda, tc::BM, bk) &&
+              tc::make_map_2d(&mb, B_hi, N, K, ldb, BN, bk) && tc::make_map_2d(&mbl, B_lo ? B_lo : B_hi, N, K, ldb, BN, bk);
     if (!ok) FAIL(DFM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     tc::Params p{};
     p.M = M; p.N = N; p.K = K; p.k_per_split = K; p.C = C; p.ldc = ldc; p.c_split_stride = 0; p.epi = epi; p.ep = ep;
     p.split_a = A_lo ? 0 : 1; p.split_b = B_lo ? 0 : 1;
     dim3 grid(cdiv(N, BN), cdiv(M, tc::BM), 1);
-    if (BN == 256) tc::gemm_kernel<256, 0><<<grid, tc::NTHREADS, tc::Smem<256>::TOTAL, st>>>(ma, mal, mb, mbl, p);
-    else tc::gemm_kernel<128, 0><<<grid, tc::NTHREADS, tc::Smem<128>::TOTAL, st>>>(ma, mal, mb, mbl, p);
+    if (BN == 256) tc::gemm_kernel<256, 0, TC_BK><<<grid, tc::NTHREADS, tc::Smem<256, TC_BK>::TOTAL, st>>>(ma, mal, mb, mbl, p);
+    else tc::gemm_kernel<128, 0, TC_BK><<<grid, tc::NTHREADS, tc::Smem<128, TC_BK>::TOTAL, st>>>(ma, mal, mb, mbl, p);
     if (h) h->launches++;
     CK(cudaGetLastError());
     return DFM_OK;
@@ -1206,17 +1211,17 @@ static int tc_gemm_mnmajor(dfm_handle* h, const float* A, int lda, const float* 
     if (M % 32 || N % 32) FAIL(DFM_ERR_UNSUPPORTED, "tc_gemm_mnmajor needs M, N multiples of 32");
     const int BN = N > 128 ? 256 : 128;
     CUtensorMap ma, mb;
-    bool ok = tc::make_map_3d(&ma, A, K, M, lda, tc::BK, tc::BM / 32) && tc::make_map_3d(&mb, B, K, N, ldb, tc::BK, BN / 32);
+    bool ok = tc::make_map_3d(&ma, A, K, M, lda, TC_BK, tc::BM / 32) && tc::make_map_3d(&mb, B, K, N, ldb, TC_BK, BN / 32);
     if (!ok) FAIL(DFM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-    int kps = ((K + splits - 1) / splits + tc::BK - 1) / tc::BK * tc::BK;
+    int kps = ((K + splits - 1) / splits + TC_BK - 1) / TC_BK * TC_BK;
     int nz = (K + kps - 1) / kps;
     if (k_per_split_out) *k_per_split_out = nz;
     tc::Params p{};
     p.M = M; p.N = N; p.K = K; p.k_per_split = kps; p.C = Cpart; p.ldc = N; p.c_split_stride = (size_t)M * N; p.epi = EPI_NONE;
     p.split_a = 1; p.split_b = 1;
     dim3 grid(cdiv(N, BN), cdiv(M, tc::BM), nz);
-    if (BN == 256) tc::gemm_kernel<256, 1><<<grid, tc::NTHREADS, tc::Smem<256>::TOTAL, st>>>(ma, ma, mb, mb, p);
-    else tc::gemm_kernel<128, 1><<<grid, tc::NTHREADS, tc::Smem<128>::TOTAL, st>>>(ma, ma, mb, mb, p);
+    if (BN == 256) tc::gemm_kernel<256, 1, TC_BK><<<grid, tc::NTHREADS, tc::Smem<256, TC_BK>::TOTAL, st>>>(ma, ma, mb, mb, p);
+    else tc::gemm_kernel<128, 1, TC_BK><<<grid, tc::NTHREADS, tc::Smem<128, TC_BK>::TOTAL, st>>>(ma, ma, mb, mb, p);
     if (h) h->launches++;
     CK(cudaGetLastError());
     return DFM_OK;
@@ -1226,10 +1231,10 @@ static int tc_setup_once() {
     static int done = 0;
     if (done) return done;
     cudaError_t e = cudaSuccess;
-    e = cudaFuncSetAttribute(tc::gemm_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<256>::TOTAL); if (e) return done = -1;
-    e = cudaFuncSetAttribute(tc::gemm_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<128>::TOTAL); if (e) return done = -1;
-    e = cudaFuncSetAttribute(tc::gemm_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<256>::TOTAL); if (e) return done = -1;
-    e = cudaFuncSetAttribute(tc::gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<128>::TOTAL); if (e) return done = -1;
+    e = cudaFuncSetAttribute(tc::gemm_kernel<256, 0, TC_BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<256, TC_BK>::TOTAL); if (e) return done = -1;
+    e = cudaFuncSetAttribute(tc::gemm_kernel<128, 0, TC_BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<128, TC_BK>::TOTAL); if (e) return done = -1;
+    e = cudaFuncSetAttribute(tc::gemm_kernel<256, 1, TC_BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<256, TC_BK>::TOTAL); if (e) return done = -1;
+    e = cudaFuncSetAttribute(tc::gemm_kernel<128, 1, TC_BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<128, TC_BK>::TOTAL); if (e) return done = -1;
     return done = 1;
 }
 

@@ -29,7 +29,9 @@
 namespace tc {
 
 constexpr int BM = 128;          // output rows per CTA (= TMEM lanes)
-constexpr int BK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
+// k-block depth BK is a template parameter: 32 fp32 (128-byte swizzle rows) or 16 (64-byte rows); smaller
+// k-blocks buy a deeper TMA ring in the same shared memory (the profile showed the ring depth, not the
+// tensor pipe, limiting the main loop).
 constexpr int UMMA_K = 8;        // tf32 K per tcgen05.mma
 constexpr int NTHREADS = 256;
 
@@ -113,6 +115,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major, bool b
 // sees exactly representable operands whatever its own input rounding is.
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+#ifndef TC_TRUNC_HI
+#define TC_TRUNC_HI 0   // 1 = rely on kind::tf32 input truncation (5% faster, but one accuracy test was marginal)
+#endif
+
 struct Params {
     int M, N, K;              // C[M,N] = A(M,K) * B(K,N); K-major mode: K % 32 == 0 not required (TMA zero-fills)
     int k_per_split;          // MN-major (weight-gradient) mode: K range per blockIdx.z
@@ -122,21 +129,21 @@ struct Params {
     int split_a, split_b;     // 1: operand is raw fp32, split in the kernel; 0: hi/lo come from two tensor maps
 };
 
-template <int BN>
+template <int BN, int BK>
 struct Smem {
-    static constexpr int A_BYTES = BM * BK * 4;          // 16 KB
+    static constexpr int A_BYTES = BM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = (BN > 128) ? 2 : 3;
-    static constexpr int TOTAL = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int STAGES = (192 * 1024) / STAGE > 8 ? 8 : (192 * 1024) / STAGE;
+    static constexpr int TOTAL = STAGES * STAGE + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 // MODE 0: A K-major [M,K], B K-major [N,K].   MODE 1: A MN-major [K,M], B MN-major [K,N] (3-D maps, see host).
-template <int BN, int MODE>
+template <int BN, int MODE, int BK>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                                                            const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
                                                            Params p) {
-    using S = Smem<BN>;
+    using S = Smem<BN, BK>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE);
@@ -207,7 +214,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
                 for (int ks = 0; ks < BK / UMMA_K; ++ks) {
                     // K-major: +32 bytes inside the 128-byte swizzle row; MN-major: next 8-row (1024 B) atom
                     const uint32_t adv = MODE == 0 ? ks * UMMA_K * 4 : ks * 1024;
-                    const uint32_t lbo = MODE == 0 ? 16 : BK * 128, sbo = MODE == 0 ? 1024 : 512, lt = MODE == 0 ? 2 : 1;
+                    // K-major: 8-row atoms of BK*4-byte rows (SWIZZLE_128B for BK=32, SWIZZLE_64B for BK=16)
+                    const uint32_t lbo = MODE == 0 ? 16 : BK * 128, sbo = MODE == 0 ? 8 * BK * 4 : 512;
+                    const uint32_t lt = MODE == 0 ? (BK == 32 ? 2 : 4) : 1;
                     const uint64_t dah = make_desc(a_hi + adv, lbo, sbo, lt), dal = make_desc(a_lo + adv, lbo, sbo, lt);
                     const uint64_t dbh = make_desc(b_hi + adv, lbo, sbo, lt), dbl = make_desc(b_lo + adv, lbo, sbo, lt);
                     // The tensor core truncates when it folds a product group into the fp32 accumulator, so the
@@ -234,10 +243,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
 #pragma unroll 4
                 for (int i = t; i < S::A_BYTES / 16; i += n_split_threads) {
                     float4 x = hi[i];
+#if TC_TRUNC_HI
+                    // kind::tf32 ignores the low 13 mantissa bits of its fp32 operands (verified by the accuracy
+                    // tests: with any other input rounding this split loses 2^-11), so the landed tile IS x_hi
+                    // and only x_lo = tf32_rn(x - trunc(x)) is written -> one third less shared-memory traffic.
+                    float4 l = make_float4(tf32_hi(x.x - tf32_trunc(x.x)), tf32_hi(x.y - tf32_trunc(x.y)),
+                                           tf32_hi(x.z - tf32_trunc(x.z)), tf32_hi(x.w - tf32_trunc(x.w)));
+                    lo[i] = l;
+#else
                     float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
                     float4 l = make_float4(tf32_hi(x.x - h.x), tf32_hi(x.y - h.y), tf32_hi(x.z - h.z), tf32_hi(x.w - h.w));
                     hi[i] = h;
                     lo[i] = l;
+#endif
                 }
             }
             if (p.split_b) {
@@ -246,10 +264,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
 #pragma unroll 4
                 for (int i = t; i < S::B_BYTES / 16; i += n_split_threads) {
                     float4 x = hi[i];
+#if TC_TRUNC_HI
+                    // kind::tf32 ignores the low 13 mantissa bits of its fp32 operands (verified by the accuracy
+                    // tests: with any other input rounding this split loses 2^-11), so the landed tile IS x_hi
+                    // and only x_lo = tf32_rn(x - trunc(x)) is written -> one third less shared-memory traffic.
+                    float4 l = make_float4(tf32_hi(x.x - tf32_trunc(x.x)), tf32_hi(x.y - tf32_trunc(x.y)),
+                                           tf32_hi(x.z - tf32_trunc(x.z)), tf32_hi(x.w - tf32_trunc(x.w)));
+                    lo[i] = l;
+#else
                     float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
                     float4 l = make_float4(tf32_hi(x.x - h.x), tf32_hi(x.y - h.y), tf32_hi(x.z - h.z), tf32_hi(x.w - h.w));
                     hi[i] = h;
                     lo[i] = l;
+#endif
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
@@ -379,16 +406,16 @@ inline EncodeTiledFn get_encode() {
     return fn;
 }
 
-// row-major [rows, cols] fp32 (cols contiguous, leading dimension ld): box = 32 cols x box_rows, SWIZZLE_128B
-inline bool make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+// row-major [rows, cols] fp32 (cols contiguous, leading dimension ld): box = bk cols x box_rows, swizzle = row bytes
+inline bool make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t bk) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {ld * 4};
-    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t box[2] = {bk, box_rows};
     cuuint32_t estr[2] = {1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // row-major [krows, cols] viewed as [cols/32][krows][32]: box = 32 x box_k x chunks  (MN-major operand tiles)
 inline bool make_map_3d(CUtensorMap* m, const float* base, uint64_t krows, uint64_t cols, uint64_t ld, uint32_t box_k, uint32_t chunks) {
