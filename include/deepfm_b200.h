@@ -89,9 +89,9 @@ typedef struct {
     dfm_optimizer     opt_linear;     /* linear tables, numeric linear weights, bias */
     int32_t           max_batch;      /* workspaces are sized for this many samples */
     int32_t           device;         /* CUDA device ordinal */
-    /* row sharding: this handle owns rows {id : id mod world == rank} */
+    /* row sharding: this handle owns global rows {g : g mod world == rank} */
     int32_t           rank, world;
-    void*             nccl_comm;      /* ncclComm_t when world > 1, else NULL */
+    void*             nccl_comm;      /* reserved (the host owns the communicator); pass NULL */
 } dfm_config;
 
 /* One batch of raw (un-hashed) feature columns = what input_fn's parse_csv yields
@@ -160,6 +160,31 @@ int64_t dfm_last_step_launches(const dfm_handle* h);
  * "loss","mlp_bwd","reduce","update","dense". Returns <0 if unknown. */
 int dfm_set_profiling(dfm_handle* h, int32_t on);
 float dfm_phase_ms(dfm_handle* h, const char* phase);
+
+/* ---- Row sharding over the GPUs of one box (BASELINE.json configs[3], configs[4]).
+ * A handle created with world > 1 owns global rows {g : g % world == rank} (local index g / world) of
+ * the concatenated embedding + linear tables; the dense tower is replicated.  One train step is the
+ * four calls below on every rank, with the collectives between them done by the host over
+ * NCCL / NVLink (torch.distributed): all_to_all(counts), all_to_all(row ids), all_to_all(rows),
+ * all_to_all(gradient rows), all_reduce(dense gradients, loss).  Row payloads are K+4 floats
+ * {emb[K], linear weight, pad} (dfm_shard_row_width).
+ *   dfm_shard_requests          K1 + sort + unique rows of the local batch; req_rows_out_dev (capacity
+ *                               batch*n_cat) receives the owner-major unique local-row ids, counts_host[world]
+ *                               the number per owner.  Synchronises the stream (the host needs the counts).
+ *   dfm_shard_serve             owner side: sort the received ids, bring those rows up to date (non-lazy
+ *                               Adam), reply_dev[i] = row payload of recv_rows_dev[i]
+ *   dfm_shard_forward_backward  forward / loss / backward of the local batch from rowbuf_dev[U, K+4];
+ *                               writes gsum_dev[U, K+4] (per unique row, deterministic order), the local
+ *                               dense gradients (dfm_dense_size floats) and loss = local sum / global_batch
+ *   dfm_shard_apply             owner side: ordered reduction of grecv_dev[n_recv, K+4] by row + sparse
+ *                               optimizer; dense optimizer with the all-reduced dense gradients; step += 1 */
+int dfm_shard_row_width(const dfm_handle* h);
+int64_t dfm_dense_size(const dfm_handle* h);
+int dfm_shard_requests(dfm_handle* h, const dfm_raw_batch* dev_batch, uint32_t* req_rows_out_dev, int32_t* counts_host, void* stream);
+int dfm_shard_serve(dfm_handle* h, const uint32_t* recv_rows_dev, int64_t n_recv, float* reply_dev, void* stream);
+int dfm_shard_forward_backward(dfm_handle* h, const dfm_raw_batch* dev_batch, const float* rowbuf_dev, int64_t global_batch,
+                               float* loss_dev, float* logits_dev, float* gsum_dev, float* dense_grad_dev, void* stream);
+int dfm_shard_apply(dfm_handle* h, const float* grecv_dev, const float* dense_grad_dev, void* stream);
 
 /* Building-block entry points used by the parity tests (device pointers, synchronous). */
 int dfm_test_sort_pairs(uint32_t* keys_dev, uint32_t* vals_dev, int64_t n, int32_t key_bits);

@@ -65,6 +65,13 @@ _SIGS = {
     "dfm_last_step_launches": (C.c_int64, [C.c_void_p]),
     "dfm_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "dfm_phase_ms": (C.c_float, [C.c_void_p, C.c_char_p]),
+    "dfm_shard_row_width": (C.c_int, [C.c_void_p]),
+    "dfm_dense_size": (C.c_int64, [C.c_void_p]),
+    "dfm_shard_requests": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
+    "dfm_shard_serve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "dfm_shard_forward_backward": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dfm_shard_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfm_test_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]),
     "dfm_test_fingerprint64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "dfm_test_tc_gemm": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

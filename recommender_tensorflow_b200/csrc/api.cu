@@ -30,6 +30,20 @@ static int tc_gemm_kmajor(dfm_handle* h, const float* A_hi, const float* A_lo, i
 static int tc_gemm_mnmajor(dfm_handle* h, const float* A, int lda, const float* B, int ldb, float* Cpart, int M, int N, int K, int splits,
                            int* k_per_split_out, cudaStream_t st);
 
+// sort + segment workspace for one list of (row key, payload) pairs
+struct SegWS {
+    int64_t cap = 0;
+    uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
+    void* sort_temp = nullptr;
+    unsigned long long* flags = nullptr; void* scan_temp = nullptr; unsigned long long* seg_total = nullptr;
+    SegCounts* seg_cnt = nullptr;
+    uint32_t *row_start = nullptr, *row_piece0 = nullptr, *piece_start = nullptr, *piece_row = nullptr, *hot_list = nullptr;
+    float* piece_sum = nullptr;
+    int cur = 0;     // which keys/vals buffer holds the sorted list
+    const uint32_t* skeys() const { return keys[cur]; }
+    const uint32_t* svals() const { return vals[cur]; }
+};
+
 struct DenseT {
     std::string name;
     int64_t off, rows, cols;
@@ -66,12 +80,15 @@ struct dfm_handle {
 
     // workspaces
     int32_t* ids = nullptr;
-    uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
-    void* sort_temp = nullptr;
-    unsigned long long* flags = nullptr; void* scan_temp = nullptr; unsigned long long* seg_total = nullptr;
-    SegCounts* seg_cnt = nullptr;
-    uint32_t *row_start = nullptr, *row_piece0 = nullptr, *piece_start = nullptr, *piece_row = nullptr, *hot_list = nullptr;
-    float* piece_sum = nullptr;
+    SegWS ws;        // lookups of the local batch (requester side when sharded)
+    SegWS ws_own;    // sharded mode: lookups received from all ranks for the rows this rank owns
+    uint64_t R_loc = 0;          // rows stored on this rank (= R when world == 1)
+    uint32_t Rl = 0;             // ceil(R / world): key space per owner
+    uint32_t* uidx = nullptr;    // lookup -> index in the unique-row list of the local batch
+    uint32_t* req_rows = nullptr;   // unique rows of the local batch as local indices at their owners (owner-major order)
+    int32_t* d_counts = nullptr; int32_t* h_counts = nullptr;   // [world] unique rows per owner, [world] = total
+    int64_t shard_n_req = 0, shard_n_recv = 0; int shard_B = 0; float shard_scale = 0.f;
+    OptDev shard_od{}, shard_ol{};
     float *h0 = nullptr, *s = nullptr, *zacc = nullptr, *logits = nullptr, *dz = nullptr, *dE = nullptr;
     float* act[DFM_MAX_HIDDEN + 1] = {nullptr};
     float* dact[DFM_MAX_HIDDEN + 1] = {nullptr};
@@ -144,6 +161,30 @@ static int dalloc(dfm_handle* h, T** p, size_t count) {
     return DFM_OK;
 }
 
+static int alloc_ws(dfm_handle* h, SegWS& ws, int64_t n, int K) {
+    ws.cap = n;
+    for (int i = 0; i < 2; ++i) { if (dalloc(h, &ws.keys[i], n)) return DFM_ERR_CUDA; if (dalloc(h, &ws.vals[i], n)) return DFM_ERR_CUDA; }
+    CK(cudaMalloc(&ws.sort_temp, prims::sort_temp_bytes(n)));
+    if (dalloc(h, &ws.flags, n)) return DFM_ERR_CUDA;
+    CK(cudaMalloc(&ws.scan_temp, prims::scan_temp_bytes(n, 8) + 64));
+    if (dalloc(h, &ws.seg_total, 1)) return DFM_ERR_CUDA;
+    if (dalloc(h, &ws.seg_cnt, 1)) return DFM_ERR_CUDA;
+    CK(cudaMemset(ws.seg_cnt, 0, sizeof(SegCounts)));
+    if (dalloc(h, &ws.row_start, n + 1)) return DFM_ERR_CUDA;
+    if (dalloc(h, &ws.row_piece0, n + 1)) return DFM_ERR_CUDA;
+    if (dalloc(h, &ws.piece_start, n + 1)) return DFM_ERR_CUDA;
+    if (dalloc(h, &ws.piece_row, n)) return DFM_ERR_CUDA;
+    if (dalloc(h, &ws.hot_list, (size_t)(2 * (n / 32 + 2)))) return DFM_ERR_CUDA;
+    if (dalloc(h, &ws.piece_sum, (size_t)(2 * (n / 32 + 2)) * (K + 4))) return DFM_ERR_CUDA;
+    return DFM_OK;
+}
+
+static void free_ws(SegWS& ws) {
+    void* ptrs[] = {ws.keys[0], ws.keys[1], ws.vals[0], ws.vals[1], ws.sort_temp, ws.flags, ws.scan_temp, ws.seg_total, ws.seg_cnt,
+                    ws.row_start, ws.row_piece0, ws.piece_start, ws.piece_row, ws.hot_list, ws.piece_sum};
+    for (void* p : ptrs) if (p) cudaFree(p);
+}
+
 // ------------------------------------------------------------------------------------- create
 extern "C" const char* dfm_version(void) { return "deepfm_b200 0.1 (sm_100a)"; }
 
@@ -155,11 +196,13 @@ static void free_all(dfm_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, h->d_row_off, h->emb_rec, h->lin_rec, h->dw,
-                    h->ds1, h->ds2, h->dg, h->ids, h->keys[0], h->keys[1], h->vals[0], h->vals[1], h->sort_temp, h->flags,
-                    h->scan_temp, h->seg_total, h->seg_cnt, h->row_start, h->row_piece0, h->piece_start, h->piece_row,
-                    h->piece_sum, h->h0, h->s, h->zacc, h->logits, h->dz, h->dE, h->splitk, h->colpart, h->head_part,
-                    h->d_loss, h->d_dzsum, h->d_err, h->alpha_d, h->alpha_l, h->up_partial, h->w0_partial, h->hot_list, h->tc_w};
+                    h->ds1, h->ds2, h->dg, h->ids, h->h0, h->s, h->zacc, h->logits, h->dz, h->dE, h->splitk, h->colpart, h->head_part,
+                    h->d_loss, h->d_dzsum, h->d_err, h->alpha_d, h->alpha_l, h->up_partial, h->w0_partial, h->tc_w, h->uidx,
+                    h->req_rows, h->d_counts};
     for (void* p : ptrs) if (p) cudaFree(p);
+    free_ws(h->ws);
+    free_ws(h->ws_own);
+    if (h->h_counts) cudaFreeHost(h->h_counts);
     for (int i = 1; i <= DFM_MAX_HIDDEN; ++i) { if (h->act[i]) cudaFree(h->act[i]); if (h->dact[i]) cudaFree(h->dact[i]); }
     for (auto& s : h->stage) {
         if (s.d_arena) cudaFree(s.d_arena);
@@ -189,7 +232,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
         FAIL(DFM_ERR_UNSUPPORTED, "embedding_size must be one of 4, 8, 16, 32, 64, 128");
     if (cfg->n_hidden < 0 || cfg->n_hidden > DFM_MAX_HIDDEN) FAIL(DFM_ERR_INVALID_ARG, "too many hidden layers");
     if (cfg->max_batch <= 0) FAIL(DFM_ERR_INVALID_ARG, "max_batch must be positive");
-    if (cfg->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "row-sharded mode is not built into this library version");
+    if (cfg->world > 1 && (cfg->rank < 0 || cfg->rank >= cfg->world)) FAIL(DFM_ERR_INVALID_ARG, "rank must be in [0, world)");
     h->dc = cfg->n_cat; h->dn = cfg->n_num; h->K = K; h->L = cfg->use_dnn ? cfg->n_hidden : 0;
     for (int i = 0; i < h->L; ++i) {
         if (cfg->hidden_units[i] <= 0) FAIL(DFM_ERR_INVALID_ARG, "hidden_units must be positive");
@@ -260,8 +303,12 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     if (R >= 0xfffffff0ull) FAIL(DFM_ERR_UNSUPPORTED, "more than 2^32 table rows on one device");
     h->row_off[h->dc] = (uint32_t)R;
     h->R = R;
+    h->Rl = (uint32_t)((R + h->world - 1) / h->world);
+    h->R_loc = h->world > 1 ? (R > (uint64_t)h->rank ? (R - h->rank + h->world - 1) / h->world : 0) : R;
+    if ((uint64_t)h->Rl * h->world >= 0xfffffff0ull) FAIL(DFM_ERR_UNSUPPORTED, "sharded key space exceeds 32 bits");
     h->key_bits = 1;
-    while ((1ull << h->key_bits) <= R) ++h->key_bits;   // keys take values 0..R
+    const uint64_t key_max = h->world > 1 ? (uint64_t)h->Rl * h->world : R;   // keys take values 0..key_max
+    while ((1ull << h->key_bits) <= key_max) ++h->key_bits;
     if (dalloc(h, &h->d_cols, h->cols.size())) return DFM_ERR_CUDA;
     if (dalloc(h, &h->d_bounds, bounds.size())) return DFM_ERR_CUDA;
     if (dalloc(h, &h->d_voc_bytes, voc_bytes.size())) return DFM_ERR_CUDA;
@@ -276,7 +323,8 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     // ---- tables: emb_rec [R][1+S][K], lin_rec [R] float4 {w, s1, s2, last_step}
     h->emb_slots = opt_slots(h->od.kind);
     h->emb_stride = (1 + h->emb_slots) * K;
-    const size_t Ralloc = std::max<uint64_t>(R, 1);
+    const size_t Ralloc = std::max<uint64_t>(h->R_loc, 1);
+    R = h->R_loc;   // from here on: rows stored on this rank
     if (h->need_emb) {
         if (dalloc(h, &h->emb_rec, Ralloc * h->emb_stride)) return DFM_ERR_CUDA;
         CK(cudaMemset(h->emb_rec, 0, Ralloc * h->emb_stride * 4));
@@ -317,19 +365,15 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     const int64_t Bm = h->max_batch, n = Bm * std::max(h->dc, 1);
     if (n >= (1ll << 31)) FAIL(DFM_ERR_UNSUPPORTED, "max_batch * n_cat must be < 2^31");
     if (dalloc(h, &h->ids, n)) return DFM_ERR_CUDA;
-    for (int i = 0; i < 2; ++i) { if (dalloc(h, &h->keys[i], n)) return DFM_ERR_CUDA; if (dalloc(h, &h->vals[i], n)) return DFM_ERR_CUDA; }
-    CK(cudaMalloc(&h->sort_temp, prims::sort_temp_bytes(n)));
-    if (dalloc(h, &h->flags, n)) return DFM_ERR_CUDA;
-    CK(cudaMalloc(&h->scan_temp, prims::scan_temp_bytes(n, 8) + 64));
-    if (dalloc(h, &h->seg_total, 1)) return DFM_ERR_CUDA;
-    if (dalloc(h, &h->seg_cnt, 1)) return DFM_ERR_CUDA;
-    CK(cudaMemset(h->seg_cnt, 0, sizeof(SegCounts)));
-    if (dalloc(h, &h->row_start, n + 1)) return DFM_ERR_CUDA;
-    if (dalloc(h, &h->row_piece0, n + 1)) return DFM_ERR_CUDA;
-    if (dalloc(h, &h->piece_start, n + 1)) return DFM_ERR_CUDA;
-    if (dalloc(h, &h->piece_row, n)) return DFM_ERR_CUDA;
-    if (dalloc(h, &h->hot_list, (size_t)(2 * (n / 32 + 2)))) return DFM_ERR_CUDA;
-    if (dalloc(h, &h->piece_sum, (size_t)(2 * (n / 32 + 2)) * (K + 4))) return DFM_ERR_CUDA;
+    if (alloc_ws(h, h->ws, n, K)) return DFM_ERR_CUDA;
+    if (h->world > 1) {
+        // owner side: every rank may send up to its whole unique list; 2x the per-rank lookups + slack, checked at run time
+        if (alloc_ws(h, h->ws_own, 2 * n + 4096, K)) return DFM_ERR_CUDA;
+        if (dalloc(h, &h->uidx, n)) return DFM_ERR_CUDA;
+        if (dalloc(h, &h->req_rows, n)) return DFM_ERR_CUDA;
+        if (dalloc(h, &h->d_counts, (size_t)h->world + 1)) return DFM_ERR_CUDA;
+        CK(cudaMallocHost(&h->h_counts, ((size_t)h->world + 1) * sizeof(int32_t)));
+    }
     if (h->need_emb) {
         if (dalloc(h, &h->h0, Bm * dK)) return DFM_ERR_CUDA;
         if (dalloc(h, &h->s, Bm * K)) return DFM_ERR_CUDA;
@@ -484,14 +528,14 @@ static bool resolve(dfm_handle* h, const std::string& full, TensorRef& t) {
         if (!h->need_emb) return false;
         int si = slot_index(h->od.kind);
         if (si < 0) return false;
-        t = {h->emb_rec + (int64_t)si * h->K, (int64_t)h->R, h->K, h->emb_stride};
+        t = {h->emb_rec + (int64_t)si * h->K, (int64_t)h->R_loc, h->K, h->emb_stride};
         return true;
     }
     if (name == "lin") {
         if (!h->use_linear) return false;
         int si = slot_index(h->ol.kind);
         if (si < 0) return false;
-        t = {reinterpret_cast<float*>(h->lin_rec) + si, (int64_t)h->R, 1, 4};
+        t = {reinterpret_cast<float*>(h->lin_rec) + si, (int64_t)h->R_loc, 1, 4};
         return true;
     }
     for (const DenseT& dt : h->dense) {
@@ -549,9 +593,9 @@ extern "C" int dfm_init_random(dfm_handle* h, uint64_t seed) {
     if (!h) return DFM_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
-    if (h->need_emb && h->R) {
-        uint64_t tot = h->R * (uint64_t)h->K;
-        init_trunc_normal_kernel<<<cdiv((int64_t)tot, 256), 256, 0, st>>>(h->emb_rec, h->R, h->K, h->emb_stride,
+    if (h->need_emb && h->R_loc) {
+        uint64_t tot = h->R_loc * (uint64_t)h->K;
+        init_trunc_normal_kernel<<<cdiv((int64_t)tot, 256), 256, 0, st>>>(h->emb_rec, h->R_loc, h->K, h->emb_stride,
                                                                           1.0f / sqrtf((float)h->K), seed * 0x9E3779B97F4A7C15ULL + 1);
     }
     int idx = 0;
@@ -607,12 +651,12 @@ static void launch_transform(dfm_handle* h, const BatchPtrs& bp, int B, bool wit
     if (h->dc == 0) return;
     transform_kernel<128><<<cdiv(B, 128), 128, (size_t)128 * h->dc * 4, st>>>(
         bp, h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, B, h->dc, h->d_row_off, (uint32_t)h->R, ids_out,
-        with_keys ? h->keys[0] : nullptr, with_keys ? h->vals[0] : nullptr, h->d_err);
+        with_keys ? h->ws.keys[0] : nullptr, with_keys ? h->ws.vals[0] : nullptr, h->d_err);
     h->launches++;
 }
 
 template <int K>
-static void launch_gather(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t st) {
+static void launch_gather(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t st, const float* rowbuf = nullptr) {
     float* num_emb = nullptr; float* num_lin = nullptr; float* bias = nullptr;
     for (const DenseT& dt : h->dense) {
         if (dt.name == "num_emb") num_emb = h->dw + dt.off;
@@ -621,7 +665,8 @@ static void launch_gather(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_
     }
     unsigned grid = std::min<unsigned>(cdiv(B, 8), (unsigned)h->sm_count * 16);
     gather_fm_kernel<K><<<grid, 256, 0, st>>>(h->ids, B, h->dc, h->dn, h->d_row_off, h->emb_rec, h->emb_stride, h->lin_rec, bp,
-                                              num_emb, num_lin, bias, h->use_linear, h->use_mf, h->need_emb, h->h0, h->s, h->zacc);
+                                              num_emb, num_lin, bias, h->use_linear, h->use_mf, h->need_emb, h->h0, h->s, h->zacc,
+                                              rowbuf ? h->uidx : nullptr, rowbuf, K + 4);
     h->launches++;
 }
 
@@ -678,10 +723,10 @@ static bool any_adam(const dfm_handle* h) {
 
 template <int K>
 static int flush_impl(dfm_handle* h, cudaStream_t st) {
-    if (!any_adam(h) || h->flushed_step == h->step || h->R == 0) { h->flushed_step = h->step; return DFM_OK; }
+    if (!any_adam(h) || h->flushed_step == h->step || h->R_loc == 0) { h->flushed_step = h->step; return DFM_OK; }
     OptDev od = make_opt(h->od, h->b1p_d, h->b2p_d), ol = make_opt(h->ol, h->b1p_l, h->b2p_l);
-    unsigned grid = (unsigned)std::min<uint64_t>((h->R + (256 / (K / 4)) - 1) / (256 / (K / 4)), (uint64_t)h->sm_count * 16);
-    catchup_all_kernel<K><<<grid, 256, 0, st>>>(h->emb_rec, h->lin_rec, h->R, (int)h->step, h->alpha_d, h->alpha_l, od, ol,
+    unsigned grid = (unsigned)std::min<uint64_t>((h->R_loc + (256 / (K / 4)) - 1) / (256 / (K / 4)), (uint64_t)h->sm_count * 16);
+    catchup_all_kernel<K><<<grid, 256, 0, st>>>(h->emb_rec, h->lin_rec, h->R_loc, (int)h->step, h->alpha_d, h->alpha_l, od, ol,
                                                 (bool)h->need_emb, (bool)h->use_linear);
     h->launches++;
     CK(cudaGetLastError());
@@ -691,9 +736,9 @@ static int flush_impl(dfm_handle* h, cudaStream_t st) {
 
 template <int K>
 static int forward_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t st, const float* labels, float scale,
-                        float* logits_out, Phase* ph) {
+                        float* logits_out, Phase* ph, const float* rowbuf = nullptr) {
     const int d = h->dc + h->dn, dK = d * K;
-    launch_gather<K>(h, bp, B, st);
+    launch_gather<K>(h, bp, B, st, rowbuf);
     if (ph) ph->next();
     const float* hL = nullptr; int H = 0;
     const DenseT* Wo = find_dense(h, "Wo"); const DenseT* bo = find_dense(h, "bo");
@@ -746,53 +791,30 @@ static int forward_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t 
     return DFM_OK;
 }
 
-template <int K>
-static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out, float* logits_out, cudaStream_t st) {
-    const int dc = h->dc, d = dc + h->dn, dK = d * K;
-    const int64_t n = (int64_t)B * dc;
-    const int64_t t = h->step + 1;
-    int rc = ensure_alpha(h, t);
-    if (rc) return rc;
-    const int64_t l0 = h->launches;
-    // beta powers as seen by step t (TF multiplies them after each apply, starting from beta)
-    const float b1p_d = h->b1p_d * h->od.beta1, b2p_d = h->b2p_d * h->od.beta2;
-    const float b1p_l = h->b1p_l * h->ol.beta1, b2p_l = h->b2p_l * h->ol.beta2;
-    const OptDev od = make_opt(h->od, b1p_d, b2p_d), ol = make_opt(h->ol, b1p_l, b2p_l);
-    Phase ph(h, st);
-
-    // K1 transform
-    launch_transform<K>(h, bp, B, true, h->ids, st);
-    ph.next();
-    // sort by global row
-    int cur = 0;
-    if (n > 0) cur = prims::radix_sort_pairs(h->keys, h->vals, n, h->key_bits, h->sort_temp, st, &h->launches);
-    const uint32_t* skeys = h->keys[cur];
-    const uint32_t* svals = h->vals[cur];
-    ph.next();
-    // segments
+// sort the (key, payload) pairs in ws.keys[0]/vals[0] and derive unique rows / pieces
+static int build_segments(dfm_handle* h, SegWS& ws, int64_t n, uint32_t limit, int bits, cudaStream_t st, Phase* ph) {
+    ws.cur = 0;
+    if (n > 0) ws.cur = prims::radix_sort_pairs(ws.keys, ws.vals, n, bits, ws.sort_temp, st, &h->launches);
+    if (ph) ph->next();
     if (n > 0) {
-        seg_flag_kernel<<<cdiv(n, 256), 256, 0, st>>>(skeys, n, (uint32_t)h->R, h->flags, h->seg_cnt);
+        seg_flag_kernel<<<cdiv(n, 256), 256, 0, st>>>(ws.skeys(), n, limit, ws.flags, ws.seg_cnt);
         h->launches++;
-        prims::exclusive_scan_u64(reinterpret_cast<const uint64_t*>(h->flags), reinterpret_cast<uint64_t*>(h->flags), n, h->scan_temp,
-                                  reinterpret_cast<uint64_t*>(h->seg_total), st, &h->launches);
-        seg_fill_kernel<<<cdiv(n, 256), 256, 0, st>>>(skeys, n, (uint32_t)h->R, h->flags, h->seg_total, h->seg_cnt, h->row_start,
-                                                      h->row_piece0, h->piece_start, h->piece_row);
+        prims::exclusive_scan_u64(reinterpret_cast<const uint64_t*>(ws.flags), reinterpret_cast<uint64_t*>(ws.flags), n, ws.scan_temp,
+                                  reinterpret_cast<uint64_t*>(ws.seg_total), st, &h->launches);
+        seg_fill_kernel<<<cdiv(n, 256), 256, 0, st>>>(ws.skeys(), n, limit, ws.flags, ws.seg_total, ws.seg_cnt, ws.row_start, ws.row_piece0,
+                                                      ws.piece_start, ws.piece_row);
         h->launches++;
+    } else {
+        CK(cudaMemsetAsync(ws.seg_cnt, 0, sizeof(SegCounts), st));
     }
-    ph.next();
-    const unsigned row_grid = (unsigned)h->sm_count * 8;
-    // non-lazy Adam: bring the touched rows up to step t-1
-    if (n > 0 && any_adam(h) && t > 1) {
-        const OptDev pod = make_opt(h->od, h->b1p_d, h->b2p_d), pol = make_opt(h->ol, h->b1p_l, h->b2p_l);
-        catchup_touched_kernel<K><<<row_grid, 256, 0, st>>>(h->emb_rec, h->lin_rec, skeys, h->row_start, h->seg_cnt, (int)(t - 1),
-                                                            h->alpha_d, h->alpha_l, pod, pol, (bool)h->need_emb, (bool)h->use_linear);
-        h->launches++;
-    }
-    ph.next();
-    // forward
-    const float scale = h->loss_red == DFM_LOSS_MEAN ? 1.0f / (float)B : 1.0f;
-    rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, &ph);
-    if (rc) return rc;
+    if (ph) ph->next();
+    return DFM_OK;
+}
+
+// loss reduction + backward through the tower + numeric-feature gradients -> h->dg, h->dE
+template <int K>
+static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale, float* loss_out, cudaStream_t st, Phase* ph) {
+    const int dc = h->dc, d = dc + h->dn, dK = d * K;
     const DenseT* bo = find_dense(h, "bo"); const DenseT* bias = find_dense(h, "bias");
     const int small_blocks = std::min((B + SM_TB - 1) / SM_TB, h->small_grid);
     head_final_kernel<<<1, 256, 0, st>>>(h->head_part, h->small_mlp ? small_blocks : h->head_blocks, scale, h->d_loss, h->d_dzsum);
@@ -800,7 +822,7 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
     if (loss_out) CK(cudaMemcpyAsync(loss_out, h->d_loss, 4, cudaMemcpyDeviceToDevice, st));
     if (bo && !h->small_mlp) CK(cudaMemcpyAsync(h->dg + bo->off, h->d_dzsum, 4, cudaMemcpyDeviceToDevice, st));
     if (bias) CK(cudaMemcpyAsync(h->dg + bias->off, h->d_dzsum, 4, cudaMemcpyDeviceToDevice, st));
-    ph.next();
+    if (ph) ph->next();
     // backward through the tower
     if (h->small_mlp) {
         const SmallMlpDesc& m = h->sm;
@@ -889,28 +911,84 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
         if (ne) { reduce_partials_kernel<<<cdiv(h->dn * K, 256), 256, 0, st>>>(h->colpart, chunks, (size_t)total, h->dn * K, h->dg + ne->off); h->launches++; }
         if (nl) { reduce_partials_kernel<<<1, 256, 0, st>>>(h->colpart + h->dn * K, chunks, (size_t)total, h->dn, h->dg + nl->off); h->launches++; }
     }
-    ph.next();
-    // sparse gradients: sorted segmented reduction + optimizer
-    GradSrc<K> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK};
+    if (ph) ph->next();
+    return DFM_OK;
+}
+
+// deterministic segmented reduction of the sparse gradients (+ optimizer, or gradient rows out when gsum != nullptr)
+template <int K>
+static int sparse_update(dfm_handle* h, SegWS& ws, int64_t n, const GradSrc<K>& src, const OptDev& od, const OptDev& ol, int64_t t,
+                         float* gsum, cudaStream_t st, Phase* ph) {
+    const unsigned row_grid = (unsigned)h->sm_count * 8;
     if (n > 0) {
-        hot_pieces_kernel<<<row_grid, 256, 0, st>>>(h->row_start, h->row_piece0, h->seg_cnt, h->hot_list);
-        piece_reduce_kernel<K><<<row_grid, 256, 0, st>>>(svals, h->piece_start, h->hot_list, h->seg_cnt, src, h->piece_sum);
+        hot_pieces_kernel<<<row_grid, 256, 0, st>>>(ws.row_start, ws.row_piece0, ws.seg_cnt, ws.hot_list);
+        piece_reduce_kernel<K><<<row_grid, 256, 0, st>>>(ws.svals(), ws.piece_start, ws.hot_list, ws.seg_cnt, src, ws.piece_sum);
         h->launches += 2;
     }
-    ph.next();
-    row_update_kernel<K><<<n > 0 ? row_grid : 1, 256, 0, st>>>(skeys, svals, h->row_start, h->row_piece0, h->piece_start, h->seg_cnt, src,
-                                                               h->piece_sum, h->emb_rec, h->emb_slots, h->lin_rec, od, ol, (bool)h->need_emb,
-                                                               (bool)h->use_linear, (int)t, h->alpha_d, h->alpha_l);
+    if (ph) ph->next();
+    row_update_kernel<K><<<n > 0 ? row_grid : 1, 256, 0, st>>>(ws.skeys(), ws.svals(), ws.row_start, ws.row_piece0, ws.piece_start, ws.seg_cnt, src,
+                                                               ws.piece_sum, h->emb_rec, h->emb_slots, h->lin_rec, od, ol, (bool)h->need_emb,
+                                                               (bool)h->use_linear, (int)t, h->alpha_d, h->alpha_l, gsum, K + 4);
     h->launches++;
+    if (ph) ph->next();
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+struct StepOpts { float b1p_d, b2p_d, b1p_l, b2p_l; OptDev od, ol; };
+static StepOpts step_opts(const dfm_handle* h) {
+    StepOpts o;
+    // beta powers as seen by step t (TF multiplies them after each apply, starting from beta)
+    o.b1p_d = h->b1p_d * h->od.beta1; o.b2p_d = h->b2p_d * h->od.beta2;
+    o.b1p_l = h->b1p_l * h->ol.beta1; o.b2p_l = h->b2p_l * h->ol.beta2;
+    o.od = make_opt(h->od, o.b1p_d, o.b2p_d); o.ol = make_opt(h->ol, o.b1p_l, o.b2p_l);
+    return o;
+}
+static void commit_step(dfm_handle* h, const StepOpts& o, int64_t t) {
+    h->step = t;
+    h->b1p_d = o.b1p_d; h->b2p_d = o.b2p_d; h->b1p_l = o.b1p_l; h->b2p_l = o.b2p_l;
+}
+
+template <int K>
+static int catchup_touched(dfm_handle* h, SegWS& ws, int64_t n, int64_t t, cudaStream_t st) {
+    // non-lazy Adam: bring the touched rows up to step t-1
+    if (n > 0 && any_adam(h) && t > 1) {
+        const OptDev pod = make_opt(h->od, h->b1p_d, h->b2p_d), pol = make_opt(h->ol, h->b1p_l, h->b2p_l);
+        catchup_touched_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(h->emb_rec, h->lin_rec, ws.skeys(), ws.row_start, ws.seg_cnt, (int)(t - 1),
+                                                                             h->alpha_d, h->alpha_l, pod, pol, (bool)h->need_emb, (bool)h->use_linear);
+        h->launches++;
+    }
+    return DFM_OK;
+}
+
+template <int K>
+static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out, float* logits_out, cudaStream_t st) {
+    if (h->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "row-sharded handle: drive the step with the dfm_shard_* entry points");
+    const int dc = h->dc, d = dc + h->dn, dK = d * K;
+    const int64_t n = (int64_t)B * dc;
+    const int64_t t = h->step + 1;
+    int rc = ensure_alpha(h, t);
+    if (rc) return rc;
+    const int64_t l0 = h->launches;
+    const StepOpts so = step_opts(h);
+    Phase ph(h, st);
+    launch_transform<K>(h, bp, B, true, h->ids, st);                                        // K1
     ph.next();
+    if ((rc = build_segments(h, h->ws, n, (uint32_t)h->R, h->key_bits, st, &ph))) return rc;   // sort + segments
+    if ((rc = catchup_touched<K>(h, h->ws, n, t, st))) return rc;
+    ph.next();
+    const float scale = h->loss_red == DFM_LOSS_MEAN ? 1.0f / (float)B : 1.0f;
+    if ((rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, &ph))) return rc;
+    if ((rc = tower_backward<K>(h, bp, B, scale, loss_out, st, &ph))) return rc;
+    GradSrc<K> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0};
+    if ((rc = sparse_update<K>(h, h->ws, n, src, so.od, so.ol, t, nullptr, st, &ph))) return rc;
     if (h->n_dense) {
-        dense_apply_kernel<<<cdiv(h->n_dense, 256), 256, 0, st>>>(h->dw, h->ds1, h->ds2, h->dg, h->n_deep, h->n_dense, od, ol);
+        dense_apply_kernel<<<cdiv(h->n_dense, 256), 256, 0, st>>>(h->dw, h->ds1, h->ds2, h->dg, h->n_deep, h->n_dense, so.od, so.ol);
         h->launches++;
     }
     ph.next();
     CK(cudaGetLastError());
-    h->step = t;
-    h->b1p_d = b1p_d; h->b2p_d = b2p_d; h->b1p_l = b1p_l; h->b2p_l = b2p_l;
+    commit_step(h, so, t);
     h->last_step_launches = h->launches - l0;
     return DFM_OK;
 }
@@ -960,6 +1038,7 @@ extern "C" int dfm_train_step(dfm_handle* h, const dfm_raw_batch* b, float* loss
 
 extern "C" int dfm_forward(dfm_handle* h, const dfm_raw_batch* b, float* logits_out, void* stream) {
     if (!h || !logits_out) return DFM_ERR_INVALID_ARG;
+    if (h->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "forward-only entry point is not built for row-sharded handles yet");
     int rc = check_batch(h, b, false);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
@@ -1003,6 +1082,149 @@ extern "C" float dfm_phase_ms(dfm_handle* h, const char* phase) {
     if (!h || !phase) return -1.f;
     for (int i = 0; i < dfm_handle::NPH; ++i) if (!strcmp(phase, kPhases[i])) return h->ph_ms[i];
     return -1.f;
+}
+
+// ------------------------------------------------------------------------------- row sharding
+// One handle per rank; rank r owns global rows {g : g % world == r} (local index g / world).  The four
+// calls below are the per-rank compute of one sharded step; the host performs the collectives
+// between them (all_to_all of row ids, rows and gradient rows; all_reduce of dense gradients).
+extern "C" int dfm_shard_row_width(const dfm_handle* h) { return h ? h->K + 4 : -1; }
+extern "C" int64_t dfm_dense_size(const dfm_handle* h) { return h ? h->n_dense : -1; }
+
+template <int K>
+static int shard_requests_impl(dfm_handle* h, const BatchPtrs& bp, int B, uint32_t* req_rows_out, int32_t* counts_host, cudaStream_t st) {
+    const int64_t n = (int64_t)B * h->dc;
+    const int64_t t = h->step + 1;
+    int rc = ensure_alpha(h, t);
+    if (rc) return rc;
+    h->last_step_launches = 0;
+    const int64_t l0 = h->launches;
+    const uint32_t W = (uint32_t)h->world, limit = W * h->Rl;
+    launch_transform<K>(h, bp, B, true, h->ids, st);
+    if (n > 0) { shard_rekey_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->ws.keys[0], n, (uint32_t)h->R, W, h->Rl); h->launches++; }
+    if ((rc = build_segments(h, h->ws, n, limit, h->key_bits, st, nullptr))) return rc;
+    CK(cudaMemsetAsync(h->d_counts, 0, ((size_t)W + 1) * 4, st));
+    if (n > 0) {
+        shard_uniq_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->ws.skeys(), h->ws.svals(), n, limit, h->Rl, h->ws.flags, h->uidx, h->req_rows, h->d_counts);
+        h->launches++;
+    }
+    CK(cudaMemcpyAsync(h->h_counts, h->d_counts, (size_t)W * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int64_t U = 0;
+    for (uint32_t o = 0; o < W; ++o) { counts_host[o] = h->h_counts[o]; U += h->h_counts[o]; }
+    if (U && req_rows_out) CK(cudaMemcpyAsync(req_rows_out, h->req_rows, (size_t)U * 4, cudaMemcpyDeviceToDevice, st));
+    h->shard_n_req = U; h->shard_B = B;
+    h->last_step_launches += h->launches - l0;
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+extern "C" int dfm_shard_requests(dfm_handle* h, const dfm_raw_batch* b, uint32_t* req_rows_out_dev, int32_t* counts_host, void* stream) {
+    if (!h || !counts_host) return DFM_ERR_INVALID_ARG;
+    if (h->world < 2) FAIL(DFM_ERR_INVALID_ARG, "handle was not created with world > 1");
+    int rc = check_batch(h, b, true);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    BatchPtrs bp = make_ptrs(h, b);
+    DISPATCH_K(h, rc = shard_requests_impl<KK>(h, bp, b->batch_size, req_rows_out_dev, counts_host, st));
+    return rc;
+}
+
+template <int K>
+static int shard_serve_impl(dfm_handle* h, const uint32_t* recv_rows, int64_t n_recv, float* reply, cudaStream_t st) {
+    if (n_recv > h->ws_own.cap) FAIL(DFM_ERR_UNSUPPORTED, "more row requests than the owner workspace holds (raise max_batch)");
+    const int64_t l0 = h->launches;
+    const int64_t t = h->step + 1;
+    int bits = 1;
+    while ((1ull << bits) <= h->R_loc) ++bits;
+    if (n_recv > 0) {
+        CK(cudaMemcpyAsync(h->ws_own.keys[0], recv_rows, (size_t)n_recv * 4, cudaMemcpyDeviceToDevice, st));
+        iota_kernel<<<cdiv(n_recv, 256), 256, 0, st>>>(h->ws_own.vals[0], n_recv);
+        h->launches++;
+    }
+    int rc = build_segments(h, h->ws_own, n_recv, (uint32_t)h->R_loc, bits, st, nullptr);
+    if (rc) return rc;
+    if ((rc = catchup_touched<K>(h, h->ws_own, n_recv, t, st))) return rc;
+    if (n_recv > 0) {
+        shard_serve_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(recv_rows, n_recv, h->emb_rec, h->emb_stride, h->lin_rec, (bool)h->need_emb,
+                                                                          (bool)h->use_linear, reply, K + 4);
+        h->launches++;
+    }
+    h->shard_n_recv = n_recv;
+    h->last_step_launches += h->launches - l0;
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+extern "C" int dfm_shard_serve(dfm_handle* h, const uint32_t* recv_rows_dev, int64_t n_recv, float* reply_dev, void* stream) {
+    if (!h || n_recv < 0 || (n_recv > 0 && (!recv_rows_dev || !reply_dev))) return DFM_ERR_INVALID_ARG;
+    if (h->world < 2) FAIL(DFM_ERR_INVALID_ARG, "handle was not created with world > 1");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    int rc = DFM_OK;
+    DISPATCH_K(h, rc = shard_serve_impl<KK>(h, recv_rows_dev, n_recv, reply_dev, st));
+    return rc;
+}
+
+template <int K>
+static int shard_fb_impl(dfm_handle* h, const BatchPtrs& bp, int B, const float* rowbuf, int64_t global_batch, float* loss_out,
+                         float* logits_out, float* gsum, float* dense_grad, cudaStream_t st) {
+    const int dc = h->dc, dK = (dc + h->dn) * K;
+    const int64_t n = (int64_t)B * dc, t = h->step + 1;
+    const int64_t l0 = h->launches;
+    const StepOpts so = step_opts(h);
+    const float scale = h->loss_red == DFM_LOSS_MEAN ? 1.0f / (float)global_batch : 1.0f;
+    int rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, nullptr, rowbuf);
+    if (rc) return rc;
+    if ((rc = tower_backward<K>(h, bp, B, scale, loss_out, st, nullptr))) return rc;
+    GradSrc<K> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0};
+    if ((rc = sparse_update<K>(h, h->ws, n, src, so.od, so.ol, t, gsum, st, nullptr))) return rc;
+    if (h->n_dense && dense_grad) CK(cudaMemcpyAsync(dense_grad, h->dg, (size_t)h->n_dense * 4, cudaMemcpyDeviceToDevice, st));
+    h->last_step_launches += h->launches - l0;
+    return DFM_OK;
+}
+
+extern "C" int dfm_shard_forward_backward(dfm_handle* h, const dfm_raw_batch* b, const float* rowbuf_dev, int64_t global_batch,
+                                          float* loss_dev, float* logits_dev, float* gsum_dev, float* dense_grad_dev, void* stream) {
+    if (!h || global_batch <= 0) return DFM_ERR_INVALID_ARG;
+    if (h->world < 2) FAIL(DFM_ERR_INVALID_ARG, "handle was not created with world > 1");
+    int rc = check_batch(h, b, true);
+    if (rc) return rc;
+    if (b->batch_size != h->shard_B) FAIL(DFM_ERR_INVALID_ARG, "batch differs from the one given to dfm_shard_requests");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    BatchPtrs bp = make_ptrs(h, b);
+    DISPATCH_K(h, rc = shard_fb_impl<KK>(h, bp, b->batch_size, rowbuf_dev, global_batch, loss_dev, logits_dev, gsum_dev, dense_grad_dev, st));
+    return rc;
+}
+
+template <int K>
+static int shard_apply_impl(dfm_handle* h, const float* grecv, const float* dense_grad, cudaStream_t st) {
+    const int64_t t = h->step + 1;
+    const int64_t l0 = h->launches;
+    const StepOpts so = step_opts(h);
+    GradSrc<K> src{nullptr, nullptr, 1, 0, grecv, K + 4};
+    int rc = sparse_update<K>(h, h->ws_own, h->shard_n_recv, src, so.od, so.ol, t, nullptr, st, nullptr);
+    if (rc) return rc;
+    if (h->n_dense) {
+        dense_apply_kernel<<<cdiv(h->n_dense, 256), 256, 0, st>>>(h->dw, h->ds1, h->ds2, dense_grad ? dense_grad : h->dg, h->n_deep, h->n_dense, so.od, so.ol);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    commit_step(h, so, t);
+    h->last_step_launches += h->launches - l0;
+    return DFM_OK;
+}
+
+extern "C" int dfm_shard_apply(dfm_handle* h, const float* grecv_dev, const float* dense_grad_dev, void* stream) {
+    if (!h) return DFM_ERR_INVALID_ARG;
+    if (h->world < 2) FAIL(DFM_ERR_INVALID_ARG, "handle was not created with world > 1");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    int rc = DFM_OK;
+    DISPATCH_K(h, rc = shard_apply_impl<KK>(h, grecv_dev, dense_grad_dev, st));
+    return rc;
 }
 
 // --------------------------------------------------------------------------- host entry points
@@ -1132,6 +1354,7 @@ extern "C" int dfm_train_step_host(dfm_handle* h, const dfm_raw_batch* b, float*
 
 extern "C" int dfm_forward_host(dfm_handle* h, const dfm_raw_batch* b, float* logits_out) {
     if (!h || !logits_out) return DFM_ERR_INVALID_ARG;
+    if (h->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "forward-only entry point is not built for row-sharded handles yet");
     int rc = check_batch(h, b, false);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));

@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(256) gather_fm_kernel(const int32_t* __restric
                                                         const float* __restrict__ num_lin,
                                                         const float* __restrict__ bias, int use_linear, int use_mf,
                                                         int need_emb, float* __restrict__ h0, float* __restrict__ s_out,
-                                                        float* __restrict__ zacc) {
+                                                        float* __restrict__ zacc, const uint32_t* __restrict__ uidx,
+                                                        const float* __restrict__ rowbuf, int rowbuf_stride) {
     constexpr int LPR = K / 4;       // lanes per row
     constexpr int FPR = 32 / LPR;    // fields per warp round
     const int lane = threadIdx.x & 31;
@@ -346,9 +347,15 @@ __global__ void __launch_bounds__(256) gather_fm_kernel(const int32_t* __restric
                 int32_t id = idrow[f];
                 float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (id >= 0) {
-                    size_t row = (size_t)row_off[f] + (uint32_t)id;
-                    if (need_emb) e = __ldg(reinterpret_cast<const float4*>(emb_rec + row * emb_stride) + sub);
-                    if (use_linear && sub == 0) lin += __ldg(reinterpret_cast<const float*>(lin_rec + row));
+                    if (rowbuf) {   // sharded: rows were fetched from their owners into rowbuf[unique index]
+                        const float* rp = rowbuf + (size_t)__ldg(uidx + (int64_t)b * dc + f) * rowbuf_stride;
+                        if (need_emb) e = __ldg(reinterpret_cast<const float4*>(rp) + sub);
+                        if (use_linear && sub == 0) lin += __ldg(rp + K);
+                    } else {
+                        size_t row = (size_t)row_off[f] + (uint32_t)id;
+                        if (need_emb) e = __ldg(reinterpret_cast<const float4*>(emb_rec + row * emb_stride) + sub);
+                        if (use_linear && sub == 0) lin += __ldg(reinterpret_cast<const float*>(lin_rec + row));
+                    }
                 }
                 if (need_emb) {
                     hrow[f * LPR + sub] = e;
@@ -404,7 +411,15 @@ struct GradSrc {
     const float* dE;    // [B, d*K] or nullptr
     const float* dz;    // [B]
     int dc, dK;         // dK = d*K
+    const float* flat;  // sharded owner side: gradient rows [n][flat_stride] = {g[K], g_lin, pad}, payload = row of `flat`
+    int flat_stride;
     __device__ __forceinline__ void fetch(uint32_t val, int sub, bool want_lin, float4& g, float& gl) const {
+        if (flat) {
+            const float* rp = flat + (size_t)val * flat_stride;
+            g = __ldg(reinterpret_cast<const float4*>(rp) + sub);
+            gl = want_lin ? __ldg(rp + K) : 0.f;
+            return;
+        }
         uint32_t b = val / (uint32_t)dc, f = val - b * (uint32_t)dc;
         g = dE ? __ldg(reinterpret_cast<const float4*>(dE + (size_t)b * dK + (size_t)f * K) + sub)
                : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -488,11 +503,12 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
                                                          float* __restrict__ emb_rec, int emb_slots,
                                                          float4* __restrict__ lin_rec, OptDev od, OptDev ol,
                                                          bool has_emb, bool has_lin, int step,
-                                                         float* __restrict__ alpha_d, float* __restrict__ alpha_l) {
+                                                         float* __restrict__ alpha_d, float* __restrict__ alpha_l,
+                                                         float* __restrict__ gsum_out, int gsum_stride) {
     constexpr int LPR = K / 4;
     const int sub = threadIdx.x % LPR;
     const uint32_t gpb = blockDim.x / LPR;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {  // alpha_t history for later replays
+    if (!gsum_out && blockIdx.x == 0 && threadIdx.x == 0) {  // alpha_t history for later replays
         alpha_d[step] = od.alpha;
         alpha_l[step] = ol.alpha;
     }
@@ -538,6 +554,12 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
                 for (int q = 0; q < 4; ++q) { add4(g, t[q]); gl += tl[q]; }
             }
         }
+        if (gsum_out) {   // sharded requester side: emit the per-row gradient sum, the owner applies it
+            float* gp = gsum_out + (size_t)u * gsum_stride;
+            reinterpret_cast<float4*>(gp)[sub] = g;
+            if (sub == 0) gp[K] = gl;
+            continue;
+        }
         if (has_emb) {
             float4* base = reinterpret_cast<float4*>(emb_rec + (size_t)row * stride) + sub;
             float4 w = base[0];
@@ -570,5 +592,55 @@ __global__ void de_fm_kernel(const float* __restrict__ h0, const float* __restri
         int c = (int)(i - b * dK) % K;
         float v = dz[b] * (s[b * K + c] - h0[i]);
         dE[i] = accumulate ? dE[i] + v : v;
+    }
+}
+
+// =============================================================================================
+// row sharding: rank r owns global rows {g : g % W == r}, stored at local index g / W
+// =============================================================================================
+// global-row sort key -> owner-major key  owner * Rl + local  (Rl = ceil(R / W)); empty bags -> W * Rl
+__global__ void shard_rekey_kernel(uint32_t* __restrict__ keys, int64_t n, uint32_t R, uint32_t W, uint32_t Rl) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        uint32_t g = keys[i];
+        keys[i] = g < R ? (g % W) * Rl + g / W : W * Rl;
+    }
+}
+// per sorted position: lookup -> unique index; per unique row: local row id for its owner + per-owner counts
+__global__ void shard_uniq_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svals, int64_t n, uint32_t limit,
+                                  uint32_t Rl, const unsigned long long* __restrict__ scanned, uint32_t* __restrict__ uidx,
+                                  uint32_t* __restrict__ req_rows, int32_t* __restrict__ counts) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = skeys[i];
+    if (k >= limit) { uidx[svals[i]] = 0xffffffffu; return; }
+    bool rh = (i == 0) || (k != skeys[i - 1]);
+    uint32_t ridx = (uint32_t)(scanned[i] >> 32);
+    if (!rh) ridx -= 1;
+    uidx[svals[i]] = ridx;
+    if (rh) {
+        req_rows[ridx] = k % Rl;
+        atomicAdd(&counts[k / Rl], 1);
+    }
+}
+__global__ void iota_kernel(uint32_t* __restrict__ v, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (uint32_t)i;
+}
+// owner side: reply[i] = {emb w[K], lin w, pad} of local row recv_rows[i]
+template <int K>
+__global__ void __launch_bounds__(256) shard_serve_kernel(const uint32_t* __restrict__ recv_rows, int64_t n,
+                                                          const float* __restrict__ emb_rec, int emb_stride,
+                                                          const float4* __restrict__ lin_rec, bool has_emb, bool has_lin,
+                                                          float* __restrict__ reply, int reply_stride) {
+    constexpr int LPR = K / 4;
+    const int sub = threadIdx.x % LPR;
+    const int64_t gpb = blockDim.x / LPR;
+    for (int64_t i = (int64_t)blockIdx.x * gpb + threadIdx.x / LPR; i < n; i += (int64_t)gridDim.x * gpb) {
+        size_t row = recv_rows[i];
+        float* rp = reply + (size_t)i * reply_stride;
+        float4 e = has_emb ? __ldg(reinterpret_cast<const float4*>(emb_rec + row * emb_stride) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<float4*>(rp)[sub] = e;
+        if (sub == 0) rp[K] = has_lin ? __ldg(reinterpret_cast<const float*>(lin_rec + row)) : 0.f;
     }
 }

@@ -42,7 +42,7 @@ class PackedBatch:
 class DeepFMEngine:
     def __init__(self, categorical_columns, numeric_columns=(), embedding_size=4, hidden_units=(16, 16),
                  use_linear=True, use_mf=True, use_dnn=True, loss_reduction="mean", opt_deep=None,
-                 opt_linear=None, max_batch=65536, device=0, feature_dtypes=None, sort_columns=True):
+                 opt_linear=None, max_batch=65536, device=0, feature_dtypes=None, sort_columns=True, rank=0, world=1):
         self.lib = _lib.load()
         cats = list(categorical_columns)
         nums = list(numeric_columns)
@@ -57,6 +57,7 @@ class DeepFMEngine:
         self.opt_deep = opt_deep or default_optimizer()
         self.opt_linear = opt_linear or default_optimizer()
         self.max_batch, self.device = int(max_batch), int(device)
+        self.rank, self.world = int(rank), int(world)
         fd = dict(feature_dtypes or {})
         self.specs = []
         for c in cats:
@@ -89,7 +90,7 @@ class DeepFMEngine:
         cfg = _lib.Config(len(cats), C.cast(cols, C.POINTER(_lib.Column)), len(nums), self.k, len(self.hidden),
                           C.cast(hid, C.POINTER(C.c_int32)), int(self.use_linear), int(self.use_mf), int(self.use_dnn),
                           _lib.LOSS_RED[loss_reduction], _opt_struct(self.opt_deep), _opt_struct(self.opt_linear),
-                          self.max_batch, self.device, 0, 1, None)
+                          self.max_batch, self.device, self.rank, self.world, None)
         self._keep += [cols, hid]
         handle = C.c_void_p()
         rc = self.lib.dfm_create(C.byref(cfg), C.byref(handle))
@@ -346,3 +347,38 @@ class DeepFMEngine:
             return t.cpu().numpy()
         self._check(self.lib.dfm_forward_host(self.h, C.byref(pb.raw), out.ctypes.data_as(C.c_void_p)))
         return out
+
+    # ------------------------------------------------------------------ row sharding (world > 1)
+    @property
+    def row_width(self):
+        return int(self.lib.dfm_shard_row_width(self.h))
+
+    @property
+    def dense_size(self):
+        return int(self.lib.dfm_dense_size(self.h))
+
+    def shard_requests(self, pb, req_rows_out):
+        """-> counts per owner (list of ints); req_rows_out (int32 cuda tensor) receives the unique local-row ids."""
+        counts = (C.c_int32 * self.world)()
+        self._check(self.lib.dfm_shard_requests(self.h, C.byref(pb.raw), C.c_void_p(req_rows_out.data_ptr()), counts, None))
+        return list(counts)
+
+    def shard_serve(self, recv_rows, n_recv, reply):
+        self._check(self.lib.dfm_shard_serve(self.h, C.c_void_p(recv_rows.data_ptr()), int(n_recv), C.c_void_p(reply.data_ptr()), None))
+
+    def shard_forward_backward(self, pb, rowbuf, global_batch, loss, logits, gsum, dense_grad):
+        self._check(self.lib.dfm_shard_forward_backward(
+            self.h, C.byref(pb.raw), C.c_void_p(rowbuf.data_ptr()), int(global_batch), C.c_void_p(loss.data_ptr()),
+            C.c_void_p(logits.data_ptr()) if logits is not None else None, C.c_void_p(gsum.data_ptr()),
+            C.c_void_p(dense_grad.data_ptr()), None))
+
+    def shard_apply(self, grecv, dense_grad):
+        self._check(self.lib.dfm_shard_apply(self.h, C.c_void_p(grecv.data_ptr()), C.c_void_p(dense_grad.data_ptr()), None))
+
+    def set_weights_sharded(self, weights):
+        """Load GLOBAL arrays: table rows are sliced to the rows this rank owns (g % world == rank)."""
+        for name, val in weights.items():
+            base = name.split("/")[0]
+            if base in ("emb", "lin"):
+                val = np.asarray(val)[self.rank::self.world]
+            self.set_tensor(name, val)

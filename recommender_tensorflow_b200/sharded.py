@@ -1,0 +1,151 @@
+"""Row-sharded DeepFM step over the GPUs of one box.
+
+Tables are row-sharded (global row g lives on rank g % world at local index g / world), the dense
+tower is replicated and the batch is data-parallel.  Per step every rank runs the four C-ABI phases
+(`dfm_shard_requests / serve / forward_backward / apply`); between them this module performs the
+collectives with `torch.distributed` (NCCL over NVLink on the GPUs, gloo in the CPU tests of the
+routing logic):
+
+    all_to_all(counts) -> all_to_all(row ids) -> [serve] -> all_to_all(rows) -> [forward/backward]
+    -> all_to_all(gradient rows) + all_reduce(dense grads, loss) -> [apply]
+
+`VirtualCluster` runs the same phases for `world` engines inside ONE process on one GPU, routing the
+buffers with plain tensor copies; it is how the sharded path is checked against the single-GPU
+result without a multi-GPU box (B200_PROFILING.md: emulate ranks in one process, never as
+co-running kernels that wait on each other).
+"""
+import numpy as np
+
+
+def split_sizes(counts, width=1):
+    return [int(c) * width for c in counts]
+
+
+def route_all_to_all(send_bufs, send_counts, width=1):
+    """Pure routing used by VirtualCluster and by the CPU tests: send_bufs[r] is rank r's send buffer laid
+    out by destination (send_counts[r][dst] items of `width` elements each).  Returns (recv_bufs, recv_counts)
+    where recv_bufs[dst] is the concatenation over source ranks, in rank order."""
+    import torch
+    W = len(send_bufs)
+    recv_counts = [[int(send_counts[src][dst]) for src in range(W)] for dst in range(W)]
+    offs = [np.concatenate([[0], np.cumsum(send_counts[r])]).astype(np.int64) for r in range(W)]
+    recv = []
+    for dst in range(W):
+        parts = [send_bufs[src][int(offs[src][dst]) * width:int(offs[src][dst + 1]) * width] for src in range(W)]
+        recv.append(torch.cat(parts) if parts else send_bufs[0][:0])
+    return recv, recv_counts
+
+
+class ShardedTrainer:
+    """One process per GPU (torchrun); `engine` was created with rank / world of the process group."""
+
+    def __init__(self, engine, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.eng, self.group = engine, group
+        self.W, self.rank = engine.world, engine.rank
+        dev = "cuda:%d" % engine.device
+        n = engine.max_batch * max(len(engine.specs), 1)
+        rw = engine.row_width
+        self.req_rows = torch.empty(n, dtype=torch.int32, device=dev)
+        self.recv_rows = torch.empty(2 * n + 4096, dtype=torch.int32, device=dev)
+        self.reply = torch.empty((2 * n + 4096) * rw, dtype=torch.float32, device=dev)
+        self.rowbuf = torch.empty(n * rw, dtype=torch.float32, device=dev)
+        self.gsum = torch.empty(n * rw, dtype=torch.float32, device=dev)
+        self.grecv = torch.empty((2 * n + 4096) * rw, dtype=torch.float32, device=dev)
+        self.dense = torch.zeros(max(engine.dense_size, 1) + 1, dtype=torch.float32, device=dev)   # [+1]: loss rides along
+        self.cnt_send = torch.empty(self.W, dtype=torch.int32, device=dev)
+        self.cnt_recv = torch.empty(self.W, dtype=torch.int32, device=dev)
+        self.rw = rw
+
+    def train_step(self, pb, global_batch):
+        """One sharded train step on a device-resident PackedBatch; returns the global loss (0-dim cuda tensor)."""
+        torch, dist, eng, rw = self.torch, self.dist, self.eng, self.rw
+        send_counts = eng.shard_requests(pb, self.req_rows)
+        self.cnt_send.copy_(torch.tensor(send_counts, dtype=torch.int32))
+        dist.all_to_all_single(self.cnt_recv, self.cnt_send, group=self.group)
+        recv_counts = self.cnt_recv.tolist()
+        U, n_recv = sum(send_counts), sum(recv_counts)
+        dist.all_to_all_single(self.recv_rows[:n_recv], self.req_rows[:U], recv_counts, send_counts, group=self.group)
+        torch.cuda.current_stream().synchronize()
+        eng.shard_serve(self.recv_rows, n_recv, self.reply)
+        eng.sync()
+        dist.all_to_all_single(self.rowbuf[:U * rw], self.reply[:n_recv * rw], split_sizes(send_counts, rw),
+                               split_sizes(recv_counts, rw), group=self.group)
+        torch.cuda.current_stream().synchronize()
+        nd = eng.dense_size
+        eng.shard_forward_backward(pb, self.rowbuf, global_batch, self.dense[nd:nd + 1], None, self.gsum, self.dense)
+        eng.sync()
+        dist.all_to_all_single(self.grecv[:n_recv * rw], self.gsum[:U * rw], split_sizes(recv_counts, rw),
+                               split_sizes(send_counts, rw), group=self.group)
+        dist.all_reduce(self.dense, group=self.group)
+        torch.cuda.current_stream().synchronize()
+        eng.shard_apply(self.grecv, self.dense)
+        return self.dense[nd]
+
+
+class VirtualCluster:
+    """`world` engines in one process on one GPU; same phases, routing by tensor copies."""
+
+    def __init__(self, engines):
+        import torch
+        self.torch = torch
+        self.engs = engines
+        self.W = len(engines)
+
+    def train_step(self, pbs, return_logits=False):
+        torch, W = self.torch, self.W
+        dev = "cuda:%d" % self.engs[0].device
+        rw = self.engs[0].row_width
+        global_batch = sum(pb.batch_size for pb in pbs)
+        req, counts = [], []
+        for e, pb in zip(self.engs, pbs):
+            buf = torch.empty(pb.batch_size * max(len(e.specs), 1), dtype=torch.int32, device=dev)
+            counts.append(e.shard_requests(pb, buf))
+            req.append(buf[:sum(counts[-1])])
+        recv_rows, recv_counts = route_all_to_all(req, counts)
+        replies = []
+        for e, rr in zip(self.engs, recv_rows):
+            rep = torch.empty(max(rr.numel(), 1) * rw, dtype=torch.float32, device=dev)
+            e.shard_serve(rr.contiguous(), rr.numel(), rep)
+            e.sync()
+            replies.append(rep[:rr.numel() * rw])
+        rowbufs, _ = route_all_to_all(replies, recv_counts, rw)
+        gsums, denses, logits = [], [], []
+        nd = self.engs[0].dense_size
+        for e, pb, rb, c in zip(self.engs, pbs, rowbufs, counts):
+            U = sum(c)
+            gs = torch.empty(max(U, 1) * rw, dtype=torch.float32, device=dev)
+            dn = torch.zeros(nd + 1, dtype=torch.float32, device=dev)
+            lg = torch.empty(pb.batch_size, dtype=torch.float32, device=dev)
+            rbc = rb.contiguous() if rb.numel() else torch.zeros(rw, dtype=torch.float32, device=dev)
+            e.shard_forward_backward(pb, rbc, global_batch, dn[nd:nd + 1], lg, gs, dn)
+            e.sync()
+            gsums.append(gs[:U * rw]); denses.append(dn); logits.append(lg)
+        grecv, _ = route_all_to_all(gsums, counts, rw)
+        total = torch.stack(denses).sum(0)            # all_reduce (rank order)
+        for e, gr in zip(self.engs, grecv):
+            grc = gr.contiguous() if gr.numel() else torch.zeros(rw, dtype=torch.float32, device=dev)
+            e.shard_apply(grc, total)
+            e.sync()
+        loss = float(total[nd].item())
+        if return_logits:
+            return loss, torch.cat(logits).cpu().numpy()
+        return loss
+
+    def state(self, names_with_slots):
+        """Global arrays reassembled from the shards (dense variables from rank 0)."""
+        out = {}
+        for name in names_with_slots:
+            base = name.split("/")[0]
+            if base in ("emb", "lin"):
+                parts = [e.get_tensor(name) for e in self.engs]
+                R = sum(p.shape[0] for p in parts)
+                full = np.empty((R,) + parts[0].shape[1:], dtype=np.float32)
+                for r, p in enumerate(parts):
+                    full[r::self.W] = p
+                out[name] = full
+            else:
+                out[name] = self.engs[0].get_tensor(name)
+        return out
