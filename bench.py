@@ -36,6 +36,7 @@ WORKLOADS = {
                                                 buckets=1_000_000),
 }
 DEFAULT_WORKLOAD = "deepfm_ml100k_k16_h256x128_b65536"
+DEFAULT_SHARDED = "deepfm_criteo_1e7_k16_h16x16_b65536"
 
 
 def bytes_per_sample(dc, dn, k, slots_emb, slots_lin):
@@ -118,8 +119,12 @@ def cpu_baseline(w, cats_specs_engine, seconds_target=12.0, threads=None):
     eng_like = cats_specs_engine
     cfg = oracle_cfg(eng_like)
     nb = sum(int(s["num_buckets"]) for s in cfg["cat"])
-    if nb > 5_000_000:
-        return None, "tables too large for the literal non-lazy CPU oracle"
+    shrunk = ""
+    if nb > 5_000_000:   # the literal non-lazy CPU step walks the whole table every step: bound the sample
+        for s in cfg["cat"]:
+            if s["kind"] == "hash":
+                s["num_buckets"] = min(int(s["num_buckets"]), 100_000)
+        shrunk = "; hash buckets capped at 1e5/field for the CPU sample (the literal non-lazy Adam walks whole tables)"
     ora = OracleDeepFM(cfg, init_weights(cfg, 0))
     bs = min(w["batch"], 4096)
     ww = dict(w, batch=bs)
@@ -145,7 +150,7 @@ def cpu_baseline(w, cats_specs_engine, seconds_target=12.0, threads=None):
             break
     return {"value": bs * n / dt, "unit": "samples/s", "cores": threads, "kind": "port",
             "sample": "%d steps of batch %d of the same workload, torch-CPU float32 restatement of the TF-1.12 step "
-                      "(incl. literal non-lazy Adam); not TensorFlow" % (n, bs)}, None
+                      "(incl. literal non-lazy Adam); not TensorFlow%s" % (n, bs, shrunk)}, None
 
 
 def run_reference(args, w, name):
@@ -189,13 +194,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--workload", default=None, help="default: %s at N=1, %s (row-sharded, weak scaling) at N>1"
+                    % (DEFAULT_WORKLOAD, DEFAULT_SHARDED))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-phases", action="store_true", help="print a per-phase device-time breakdown to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    name = args.workload
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    name = args.workload or (DEFAULT_SHARDED if max(world_env, args.gpus) > 1 else DEFAULT_WORKLOAD)
     w = WORKLOADS[name]
     if args.impl == "reference":
         run_reference(args, w, name)
@@ -214,9 +221,19 @@ def main():
 
     cats, nums, dtypes = make_columns(w)
     B = w["batch"]
+    sharded = world > 1 and w["data"] == "criteo"
     eng = DeepFMEngine(cats, nums, embedding_size=w["k"], hidden_units=w["hidden"], max_batch=B, device=local,
-                       feature_dtypes=dtypes, **optimizers(w))
+                       feature_dtypes=dtypes, rank=rank if sharded else 0, world=world if sharded else 1, **optimizers(w))
     eng.init_random(1234 + rank)
+    if sharded:
+        # the replicated dense tower must start identical on every rank
+        for nm in eng.variable_names():
+            if nm not in ("emb", "lin"):
+                t = torch.from_numpy(eng.get_tensor(nm)).cuda()
+                dist.broadcast(t, 0)
+                eng.set_tensor(nm, t.cpu().numpy())
+        from recommender_tensorflow_b200.sharded import ShardedTrainer
+        trainer = ShardedTrainer(eng)
     n_batches = 8
     host_batches = make_batches(w, n_batches, 777 + rank)
     packed_host = [eng.pack(f, y) for f, y in host_batches]
@@ -231,10 +248,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def dev_step(i):
+        if sharded:
+            loss_buf.copy_(trainer.train_step(packed_dev[i % n_batches], B * world).reshape(1))
+        else:
+            eng.train_step_device(packed_dev[i % n_batches], loss_out=loss_buf, stream=stream.cuda_stream)
+
     # ---------------- device-resident timing (value)
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
-            eng.train_step_device(packed_dev[i % n_batches], loss_out=loss_buf, stream=stream.cuda_stream)
+            dev_step(i)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -242,25 +265,42 @@ def main():
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for i in range(args.steps):
-            eng.train_step_device(packed_dev[(args.warmup + i) % n_batches], loss_out=loss_buf, stream=stream.cuda_stream)
+            dev_step(args.warmup + i)
         ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = eng.last_step_launches * args.steps
     eng.sync()
+    torch.cuda.synchronize()
     last_loss = float(loss_buf.item())
 
     # ---------------- end-to-end through the host-buffer entry point (e2e)
-    for i in range(3):
-        eng.train_step_async(packed_host[i % n_batches])
-    eng.drain()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        eng.train_step_async(packed_host[i % n_batches])     # H2D + step; returns the previous step's loss (D2H)
-    e2e_loss = eng.drain()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    if sharded:
+        def e2e_step(i):
+            j = i % n_batches
+            packed_dev[j].arena.copy_(packed_host[j].arena, non_blocking=True)     # H2D of the raw columns
+            return trainer.train_step(packed_dev[j], B * world)
+        with torch.cuda.stream(stream):
+            for i in range(2):
+                e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            for i in range(args.steps):
+                e2e_loss = float(e2e_step(i).item())                                # D2H of the loss every step
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    else:
+        for i in range(3):
+            eng.train_step_async(packed_host[i % n_batches])
+        eng.drain()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            eng.train_step_async(packed_host[i % n_batches])     # H2D + step; returns the previous step's loss (D2H)
+        e2e_loss = eng.drain()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -270,7 +310,7 @@ def main():
     ms, e2e_s = float(t[0]), float(t[1])
 
     phases = None
-    if args.profile_phases or True:
+    if not sharded:
         eng.set_profiling(True)
         eng.train_step_device(packed_dev[0], loss_out=loss_buf)
         eng.sync()
@@ -299,13 +339,17 @@ def main():
                        "n_cat": len(cats), "n_num": len(nums), "table_rows": int(eng.row_offsets[-1]),
                        "optimizer": o["opt_deep"]["name"] + ("/" + o["opt_linear"]["name"] if w["model"] == "wide_deep" else " (TF non-lazy, exact deferred)"),
                        "l2": "per-step working set (activations + gradients) exceeds L2; inputs rotate over %d batches" % n_batches,
-                       "parallelism": "single GPU" if world == 1 else "replicas x%d" % world},
+                       "parallelism": "single GPU" if world == 1 else (
+                           "tables row-sharded over %d GPUs (all_to_all ids / rows / gradient rows), data-parallel tower "
+                           "(all_reduce); global batch %d" % (world, B * world) if sharded else "replicas x%d" % world)},
             "gpu_launches": int(launches),
             "loss_last": last_loss,
             "e2e": {"value": B * args.steps * world / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / args.steps, "loss_last": e2e_loss,
-                    "how": "dfm_train_step_host_async: pinned host arena -> one H2D copy per step on a copy stream, step, "
-                           "D2H of the loss; double buffered, wall clock with a device sync on both sides"},
+                    "how": ("pinned host arena -> H2D copy, sharded step, loss.item() every step; wall clock, device sync on both sides"
+                            if sharded else
+                            "dfm_train_step_host_async: pinned host arena -> one H2D copy per step on a copy stream, step, "
+                            "D2H of the loss; double buffered, wall clock with a device sync on both sides")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "bytes_per_sample": bps, "peak_source": peak_kind,
                          "scope": "whole step (all kernels of one train step; SURVEY.md 8d bytes/sample x batch / step time)"},

@@ -357,23 +357,26 @@ class DeepFMEngine:
     def dense_size(self):
         return int(self.lib.dfm_dense_size(self.h))
 
-    def shard_requests(self, pb, req_rows_out):
+    def shard_requests(self, pb, req_rows_out, stream=None):
         """-> counts per owner (list of ints); req_rows_out (int32 cuda tensor) receives the unique local-row ids."""
         counts = (C.c_int32 * self.world)()
-        self._check(self.lib.dfm_shard_requests(self.h, C.byref(pb.raw), C.c_void_p(req_rows_out.data_ptr()), counts, None))
+        self._check(self.lib.dfm_shard_requests(self.h, C.byref(pb.raw), C.c_void_p(req_rows_out.data_ptr()), counts,
+                                                C.c_void_p(stream) if stream else None))
         return list(counts)
 
-    def shard_serve(self, recv_rows, n_recv, reply):
-        self._check(self.lib.dfm_shard_serve(self.h, C.c_void_p(recv_rows.data_ptr()), int(n_recv), C.c_void_p(reply.data_ptr()), None))
+    def shard_serve(self, recv_rows, n_recv, reply, stream=None):
+        self._check(self.lib.dfm_shard_serve(self.h, C.c_void_p(recv_rows.data_ptr()), int(n_recv), C.c_void_p(reply.data_ptr()),
+                                             C.c_void_p(stream) if stream else None))
 
-    def shard_forward_backward(self, pb, rowbuf, global_batch, loss, logits, gsum, dense_grad):
+    def shard_forward_backward(self, pb, rowbuf, global_batch, loss, logits, gsum, dense_grad, stream=None):
         self._check(self.lib.dfm_shard_forward_backward(
             self.h, C.byref(pb.raw), C.c_void_p(rowbuf.data_ptr()), int(global_batch), C.c_void_p(loss.data_ptr()),
             C.c_void_p(logits.data_ptr()) if logits is not None else None, C.c_void_p(gsum.data_ptr()),
-            C.c_void_p(dense_grad.data_ptr()), None))
+            C.c_void_p(dense_grad.data_ptr()), C.c_void_p(stream) if stream else None))
 
-    def shard_apply(self, grecv, dense_grad):
-        self._check(self.lib.dfm_shard_apply(self.h, C.c_void_p(grecv.data_ptr()), C.c_void_p(dense_grad.data_ptr()), None))
+    def shard_apply(self, grecv, dense_grad, stream=None):
+        self._check(self.lib.dfm_shard_apply(self.h, C.c_void_p(grecv.data_ptr()), C.c_void_p(dense_grad.data_ptr()),
+                                             C.c_void_p(stream) if stream else None))
 
     def set_weights_sharded(self, weights):
         """Load GLOBAL arrays: table rows are sliced to the rows this rank owns (g % world == rank)."""

@@ -60,28 +60,26 @@ class ShardedTrainer:
         self.rw = rw
 
     def train_step(self, pb, global_batch):
-        """One sharded train step on a device-resident PackedBatch; returns the global loss (0-dim cuda tensor)."""
+        """One sharded train step on a device-resident PackedBatch; everything is enqueued on torch's current
+        stream (the only host sync is the per-owner counts inside dfm_shard_requests).  Returns the global
+        loss as a 0-dim cuda tensor."""
         torch, dist, eng, rw = self.torch, self.dist, self.eng, self.rw
-        send_counts = eng.shard_requests(pb, self.req_rows)
-        self.cnt_send.copy_(torch.tensor(send_counts, dtype=torch.int32))
+        st = torch.cuda.current_stream().cuda_stream
+        send_counts = eng.shard_requests(pb, self.req_rows, st)
+        self.cnt_send.copy_(torch.tensor(send_counts, dtype=torch.int32), non_blocking=True)
         dist.all_to_all_single(self.cnt_recv, self.cnt_send, group=self.group)
         recv_counts = self.cnt_recv.tolist()
         U, n_recv = sum(send_counts), sum(recv_counts)
         dist.all_to_all_single(self.recv_rows[:n_recv], self.req_rows[:U], recv_counts, send_counts, group=self.group)
-        torch.cuda.current_stream().synchronize()
-        eng.shard_serve(self.recv_rows, n_recv, self.reply)
-        eng.sync()
+        eng.shard_serve(self.recv_rows, n_recv, self.reply, st)
         dist.all_to_all_single(self.rowbuf[:U * rw], self.reply[:n_recv * rw], split_sizes(send_counts, rw),
                                split_sizes(recv_counts, rw), group=self.group)
-        torch.cuda.current_stream().synchronize()
         nd = eng.dense_size
-        eng.shard_forward_backward(pb, self.rowbuf, global_batch, self.dense[nd:nd + 1], None, self.gsum, self.dense)
-        eng.sync()
+        eng.shard_forward_backward(pb, self.rowbuf, global_batch, self.dense[nd:nd + 1], None, self.gsum, self.dense, st)
         dist.all_to_all_single(self.grecv[:n_recv * rw], self.gsum[:U * rw], split_sizes(recv_counts, rw),
                                split_sizes(send_counts, rw), group=self.group)
         dist.all_reduce(self.dense, group=self.group)
-        torch.cuda.current_stream().synchronize()
-        eng.shard_apply(self.grecv, self.dense)
+        eng.shard_apply(self.grecv, self.dense, st)
         return self.dense[nd]
 
 
