@@ -453,9 +453,9 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
                 CK(cudaFuncSetAttribute(small_mlp_fwd_bwd_top_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->small_smem));
                 CK(cudaFuncSetAttribute(small_mlp_fwd_bwd_top_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->small_smem));
                 CK(cudaFuncSetAttribute(small_mlp_fwd_bwd_top_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->small_smem));
-                CK(cudaFuncSetAttribute(small_mlp_bwd_input_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_mlp_bwd_smem<8>()));
-                CK(cudaFuncSetAttribute(small_mlp_bwd_input_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_mlp_bwd_smem<16>()));
-                CK(cudaFuncSetAttribute(small_mlp_bwd_input_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_mlp_bwd_smem<32>()));
+                CK(cudaFuncSetAttribute(small_mlp_bwd_input_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_mlp_bwd_smem<8>(K)));
+                CK(cudaFuncSetAttribute(small_mlp_bwd_input_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_mlp_bwd_smem<16>(K)));
+                CK(cudaFuncSetAttribute(small_mlp_bwd_input_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_mlp_bwd_smem<32>(K)));
             }
         }
     }
@@ -475,6 +475,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     }
     for (auto& e : h->ph_ev) CK(cudaEventCreate(&e));
     CK(cudaFuncSetAttribute(transform_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * DFM_MAX_CAT * 4));
+    CK(cudaFuncSetAttribute(numeric_grad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->rows_per_chunk * (DFM_MAX_NUM + 1) * 4));
 
     // optimizer slot initial values (Adagrad / FTRL accumulators start at init_acc)
     auto init_acc = [&](const dfm_optimizer& o) { return (o.kind == DFM_OPT_ADAGRAD || o.kind == DFM_OPT_FTRL) ? o.init_acc : 0.f; };
@@ -832,7 +833,7 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
         const int groups = std::max(1, std::min(tiles, (4 * h->sm_count + chunks - 1) / chunks));
         dim3 grid(groups, chunks);
         const float* sv = h->use_mf ? h->s : nullptr;
-#define SMALL_BWD(HH) small_mlp_bwd_input_kernel<HH><<<grid, 256, small_mlp_bwd_smem<HH>(), st>>>(h->dw + m.off_W[0], h->h0, h->dact[1], h->dz, sv, K, B, dK, h->dE, h->w0_partial)
+#define SMALL_BWD(HH) small_mlp_bwd_input_kernel<HH><<<grid, 256, small_mlp_bwd_smem<HH>(K), st>>>(h->dw + m.off_W[0], h->h0, h->dact[1], h->dz, sv, K, B, dK, h->dE, h->w0_partial)
         if (m.H[0] == 8) SMALL_BWD(8); else if (m.H[0] == 16) SMALL_BWD(16); else SMALL_BWD(32);
 #undef SMALL_BWD
         reduce_partials_kernel<<<cdiv((int64_t)dK * m.H[0], 256), 256, 0, st>>>(h->w0_partial, groups, (size_t)dK * m.H[0], (int64_t)dK * m.H[0], h->dg + m.off_W[0]);
@@ -906,7 +907,7 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
     if (h->dn) {
         const DenseT* ne = find_dense(h, "num_emb"); const DenseT* nl = find_dense(h, "num_lin");
         const int chunks = (int)cdiv(B, h->rows_per_chunk), total = h->dn * K + h->dn;
-        numeric_grad_partial_kernel<<<chunks, 256, 0, st>>>(bp, h->need_emb ? h->dE : nullptr, dK, dc, h->dn, K, h->dz, B, h->rows_per_chunk, h->colpart);
+        numeric_grad_partial_kernel<<<chunks, 256, (size_t)h->rows_per_chunk * (h->dn + 1) * 4, st>>>(bp, h->need_emb ? h->dE : nullptr, dK, dc, h->dn, K, h->dz, B, h->rows_per_chunk, h->colpart);
         h->launches++;
         if (ne) { reduce_partials_kernel<<<cdiv(h->dn * K, 256), 256, 0, st>>>(h->colpart, chunks, (size_t)total, h->dn * K, h->dg + ne->off); h->launches++; }
         if (nl) { reduce_partials_kernel<<<1, 256, 0, st>>>(h->colpart + h->dn * K, chunks, (size_t)total, h->dn, h->dg + nl->off); h->launches++; }

@@ -76,6 +76,53 @@ __device__ __forceinline__ void adam_replay(float& w, float& m, float& v, int la
     }
 }
 
+// Replay of a whole float4 lane slice in ONE loop (shared trip count, 4-way ILP) with MUFU-based
+// sqrt / reciprocal: the replayed updates add up to at most ~1e-2 and each carries <= 2^-21 relative
+// error, i.e. < 1e-8 absolute on w - far inside the 1e-5 parity bar - while the exact IEEE sequence
+// costs ~5x more instructions and made the catch-up compute-bound on Criteo-sized tables.
+__device__ __forceinline__ float fast_upd(float m, float v, float alpha, float eps) {
+    float sq, rc;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(sq + eps));
+    return alpha * m * rc;
+}
+__device__ __forceinline__ void adam_replay4(float4& w, float4& m, float4& v, int last, int upto,
+                                             const float* __restrict__ alpha, const OptDev& o) {
+    int tau = last + 1;
+    for (; tau <= upto; ++tau) {
+        const float a = __ldg(alpha + tau);
+        m.x *= o.b1; m.y *= o.b1; m.z *= o.b1; m.w *= o.b1;
+        v.x *= o.b2; v.y *= o.b2; v.z *= o.b2; v.w *= o.b2;
+        float4 wn;
+        wn.x = w.x - fast_upd(m.x, v.x, a, o.eps); wn.y = w.y - fast_upd(m.y, v.y, a, o.eps);
+        wn.z = w.z - fast_upd(m.z, v.z, a, o.eps); wn.w = w.w - fast_upd(m.w, v.w, a, o.eps);
+        const bool same = wn.x == w.x && wn.y == w.y && wn.z == w.z && wn.w == w.w;
+        w = wn;
+        if (same && o.safe_early) { ++tau; break; }
+    }
+    int rem = upto - tau + 1;
+    if (rem > 0) {
+        float d1, d2;
+        if (rem <= 64) {
+            d1 = 1.f; d2 = 1.f;
+            for (int j = 0; j < rem; ++j) { d1 *= o.b1; d2 *= o.b2; }
+        } else {
+            d1 = (float)pow((double)o.b1, (double)rem);
+            d2 = (float)pow((double)o.b2, (double)rem);
+        }
+        m.x *= d1; m.y *= d1; m.z *= d1; m.w *= d1;
+        v.x *= d2; v.y *= d2; v.z *= d2; v.w *= d2;
+    }
+}
+
+__device__ __forceinline__ void adam_replay1(float& w, float& m, float& v, int last, int upto,
+                                             const float* __restrict__ alpha, const OptDev& o) {
+    if (m == 0.f && v == 0.f) return;
+    float4 w4 = make_float4(w, 0.f, 0.f, 0.f), m4 = make_float4(m, 0.f, 0.f, 0.f), v4 = make_float4(v, 1.f, 1.f, 1.f);
+    adam_replay4(w4, m4, v4, last, upto, alpha, o);
+    w = w4.x; m = m4.x; v = v4.x;
+}
+
 // =============================================================================================
 // K1: feature-column transforms -> ids [B, dc] + sort keys (global row index) + payload
 // =============================================================================================
@@ -259,22 +306,28 @@ __device__ __forceinline__ void catchup_group(float* __restrict__ emb_rec, float
     const bool work = act && last < upto;
     if (work && has_emb && od.kind == DFM_OPT_ADAM) {
         float4* base = reinterpret_cast<float4*>(emb_rec + row * 3 * K) + sub;
-        float4 w = base[0], m = base[LPR], v = base[2 * LPR];
-        adam_replay(w.x, m.x, v.x, last, upto, alpha_d, od);
-        adam_replay(w.y, m.y, v.y, last, upto, alpha_d, od);
-        adam_replay(w.z, m.z, v.z, last, upto, alpha_d, od);
-        adam_replay(w.w, m.w, v.w, last, upto, alpha_d, od);
-        base[0] = w; base[LPR] = m; base[2 * LPR] = v;
+        float4 m = base[LPR], v = base[2 * LPR];
+        // rows that were never touched (m = v = 0) do not move under non-lazy Adam: nothing to read or write
+        const bool idle = m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f && v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f;
+        if (!idle) {
+            float4 w = base[0];
+            adam_replay4(w, m, v, last, upto, alpha_d, od);
+            base[0] = w; base[LPR] = m; base[2 * LPR] = v;
+        }
     }
     __syncwarp();  // every lane of the group has read last_step before lane 0 rewrites it
     if (work && sub == 0) {
-        if (has_lin && ol.kind == DFM_OPT_ADAM) adam_replay(lr.x, lr.y, lr.z, last, upto, alpha_l, ol);
+        // NOTE: last_step is always advanced, also for idle rows, so that a later replay never starts before
+        // the step at which the row first receives a gradient.
+        if (has_lin && ol.kind == DFM_OPT_ADAM) adam_replay1(lr.x, lr.y, lr.z, last, upto, alpha_l, ol);
         lr.w = __int_as_float(upto);
         lin_rec[row] = lr;
     }
 }
 
-// rows touched by the current batch (unique list from the sort stage): bring them to step `upto`
+// rows touched by the current batch (unique list from the sort stage): bring them to step `upto`.
+// Each lane group handles RPG rows per trip and issues the loads of all of them level by level
+// (row index -> last_step record -> m, v) so that several dependent random accesses are in flight.
 template <int K>
 __global__ void __launch_bounds__(256) catchup_touched_kernel(float* __restrict__ emb_rec, float4* __restrict__ lin_rec,
                                                               const uint32_t* __restrict__ skeys,
@@ -284,14 +337,62 @@ __global__ void __launch_bounds__(256) catchup_touched_kernel(float* __restrict_
                                                               const float* __restrict__ alpha_l, OptDev od, OptDev ol,
                                                               bool has_emb, bool has_lin) {
     constexpr int LPR = K / 4;
+    constexpr int RPG = 4;
     const int sub = threadIdx.x % LPR;
     const uint32_t U = cnt->n_rows;
     const uint32_t gpb = blockDim.x / LPR;
-    for (uint32_t base = blockIdx.x * gpb; base < U; base += gridDim.x * gpb) {  // block-uniform trip count
-        uint32_t u = base + threadIdx.x / LPR;
-        bool act = u < U;
-        size_t row = act ? (size_t)skeys[row_start[u]] : 0;
-        catchup_group<K>(emb_rec, lin_rec, row, act, sub, upto, alpha_d, alpha_l, od, ol, has_emb, has_lin);
+    const uint32_t stride = gridDim.x * gpb;
+    const bool emb_adam = has_emb && od.kind == DFM_OPT_ADAM;
+    for (uint32_t base = blockIdx.x * gpb; base < U; base += stride * RPG) {  // block-uniform trip count
+        bool act[RPG], work[RPG], idle[RPG];
+        size_t row[RPG];
+        uint32_t rs[RPG];
+        float4 lr[RPG], m[RPG], v[RPG];
+        int last[RPG];
+#pragma unroll
+        for (int j = 0; j < RPG; ++j) {
+            uint32_t u = base + j * stride + threadIdx.x / LPR;
+            act[j] = u < U;
+            rs[j] = act[j] ? __ldg(row_start + u) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < RPG; ++j) row[j] = act[j] ? (size_t)__ldg(skeys + rs[j]) : 0;
+#pragma unroll
+        for (int j = 0; j < RPG; ++j) {
+            lr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (act[j]) lr[j] = lin_rec[row[j]];
+            last[j] = act[j] ? __float_as_int(lr[j].w) : upto;
+            work[j] = act[j] && last[j] < upto;
+        }
+#pragma unroll
+        for (int j = 0; j < RPG; ++j) {
+            m[j] = make_float4(0.f, 0.f, 0.f, 0.f); v[j] = m[j];
+            if (work[j] && emb_adam) {
+                const float4* bp4 = reinterpret_cast<const float4*>(emb_rec + row[j] * 3 * K) + sub;
+                m[j] = bp4[LPR]; v[j] = bp4[2 * LPR];
+            }
+            // rows that were never touched (m = v = 0) do not move under non-lazy Adam: nothing more to read or write
+            idle[j] = m[j].x == 0.f && m[j].y == 0.f && m[j].z == 0.f && m[j].w == 0.f && v[j].x == 0.f && v[j].y == 0.f &&
+                      v[j].z == 0.f && v[j].w == 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < RPG; ++j) {
+            if (work[j] && emb_adam && !idle[j]) {
+                float4* bp4 = reinterpret_cast<float4*>(emb_rec + row[j] * 3 * K) + sub;
+                float4 w = bp4[0];
+                adam_replay4(w, m[j], v[j], last[j], upto, alpha_d, od);
+                bp4[0] = w; bp4[LPR] = m[j]; bp4[2 * LPR] = v[j];
+            }
+        }
+        __syncwarp();  // every lane of a group has read last_step before lane 0 rewrites it
+#pragma unroll
+        for (int j = 0; j < RPG; ++j) {
+            if (work[j] && sub == 0) {
+                if (has_lin && ol.kind == DFM_OPT_ADAM) adam_replay1(lr[j].x, lr[j].y, lr[j].z, last[j], upto, alpha_l, ol);
+                lr[j].w = __int_as_float(upto);
+                lin_rec[row[j]] = lr[j];
+            }
+        }
     }
 }
 
@@ -517,6 +618,18 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
     for (uint32_t u = blockIdx.x * gpb + threadIdx.x / LPR; u < U; u += gridDim.x * gpb) {
         uint32_t beg = row_start[u], end = row_start[u + 1];
         uint32_t row = skeys[beg];
+        // issue the table-record loads now: they only depend on the row id and overlap the gradient gather below
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f), s1 = w, s2 = w, lr = w;
+        float4* base = nullptr;
+        if (!gsum_out) {
+            if (has_emb) {
+                base = reinterpret_cast<float4*>(emb_rec + (size_t)row * stride) + sub;
+                w = base[0];
+                if (emb_slots >= 1) s1 = base[LPR];
+                if (emb_slots >= 2) s2 = base[2 * LPR];
+            }
+            if (sub == 0) lr = lin_rec[row];
+        }
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         float gl = 0.f;
         if (end - beg <= (uint32_t)DIRECT_T) {
@@ -561,10 +674,6 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
             continue;
         }
         if (has_emb) {
-            float4* base = reinterpret_cast<float4*>(emb_rec + (size_t)row * stride) + sub;
-            float4 w = base[0];
-            float4 s1 = emb_slots >= 1 ? base[LPR] : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 s2 = emb_slots >= 2 ? base[2 * LPR] : make_float4(0.f, 0.f, 0.f, 0.f);
             sparse_apply(w.x, s1.x, s2.x, g.x, od);
             sparse_apply(w.y, s1.y, s2.y, g.y, od);
             sparse_apply(w.z, s1.z, s2.z, g.z, od);
@@ -574,7 +683,6 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
             if (emb_slots >= 2) base[2 * LPR] = s2;
         }
         if (sub == 0) {
-            float4 lr = lin_rec[row];
             if (has_lin) sparse_apply(lr.x, lr.y, lr.z, gl, ol);
             lr.w = __int_as_float(step);
             lin_rec[row] = lr;

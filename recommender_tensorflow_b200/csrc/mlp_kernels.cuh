@@ -228,22 +228,34 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
 
 // numeric-feature gradients (trainers/deep_fm.py:62-67 backward):
 //   g_num_emb[j, c] = sum_b x[b,j] * dE[b, (dc+j)*K + c]      g_num_lin[j] = sum_b x[b,j] * dz[b]
-// part layout per chunk: [dn*K] then [dn]
+// part layout per chunk: [dn*K] then [dn].  One CTA per chunk of rows: the x columns of the chunk are staged in
+// shared memory, thread t owns output t and walks the rows in order (deterministic); the numeric part of a dE row
+// is contiguous, so the dn*K threads read it coalesced.
 __global__ void __launch_bounds__(256) numeric_grad_partial_kernel(BatchPtrs bp, const float* __restrict__ dE, int dK, int dc, int dn,
                                                                    int K, const float* __restrict__ dz, int B, int rows_per_chunk,
                                                                    float* __restrict__ part) {
+    extern __shared__ float xs[];           // [rows_per_chunk][dn + 1]: x columns, then dz
     const int total = dn * K + dn;
     const int r0 = blockIdx.x * rows_per_chunk;
-    const int r1 = min(B, r0 + rows_per_chunk);
+    const int nr = min(B, r0 + rows_per_chunk) - r0;
+    const int ldx = dn + 1;
+    for (int q = threadIdx.x; q < nr * ldx; q += blockDim.x) {
+        int j = q / nr, r = q - j * nr;      // column-major walk: coalesced reads of each x column
+        xs[r * ldx + j] = j < dn ? bp.num[j][r0 + r] : dz[r0 + r];
+    }
+    __syncthreads();
     for (int o = threadIdx.x; o < total; o += blockDim.x) {
         float s = 0.f;
         if (o < dn * K) {
-            int j = o / K, c = o % K;
-            if (dE)
-                for (int r = r0; r < r1; ++r) s += bp.num[j][r] * dE[(size_t)r * dK + (size_t)(dc + j) * K + c];
+            const int j = o / K;
+            if (dE) {
+                const float* p = dE + (size_t)r0 * dK + (size_t)dc * K + o;
+#pragma unroll 8
+                for (int r = 0; r < nr; ++r) s = fmaf(xs[r * ldx + j], __ldg(p + (size_t)r * dK), s);
+            }
         } else {
-            int j = o - dn * K;
-            for (int r = r0; r < r1; ++r) s += bp.num[j][r] * dz[r];
+            const int j = o - dn * K;
+            for (int r = 0; r < nr; ++r) s = fmaf(xs[r * ldx + j], xs[r * ldx + dn], s);
         }
         part[(size_t)blockIdx.x * total + o] = s;
     }

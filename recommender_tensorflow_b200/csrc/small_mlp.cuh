@@ -221,10 +221,11 @@ __global__ void __launch_bounds__(256, 2) small_mlp_fwd_bwd_top_kernel(
 }
 
 template <int H1>
-constexpr size_t small_mlp_bwd_smem() { return (size_t)(SM_TB * (H1 + 4) + SM_BC * H1 + SM_TB * (SM_BC + 1) + SM_TB * (SM_BC + 1)) * sizeof(float); }
+constexpr size_t small_mlp_bwd_smem(int K) { return (size_t)(SM_TB * (H1 + 4) + SM_BC * H1 + SM_TB * (SM_BC + 1) + SM_TB * (K + 1) + SM_TB) * sizeof(float); }
 
 // grid (sample groups, ceil(D/SM_BC)).  A CTA walks the sample tiles g, g+G, ... of its group and keeps
 // its slice of dW0 = h0^T dh1' in registers; it also writes the dE chunk of every tile it visits.
+// The next tile's h0 / dh1' / S rows are fetched into registers while the current tile is processed.
 template <int H1>
 __global__ void __launch_bounds__(256) small_mlp_bwd_input_kernel(
     const float* __restrict__ W0 /*[D][H1]*/, const float* __restrict__ h0, const float* __restrict__ dh1 /*[B][H1]*/,
@@ -234,41 +235,73 @@ __global__ void __launch_bounds__(256) small_mlp_bwd_input_kernel(
     float (*ds)[H1 + 4] = reinterpret_cast<float (*)[H1 + 4]>(smem_b);                                  // [SM_TB][H1+4]
     float (*ws)[H1] = reinterpret_cast<float (*)[H1]>(smem_b + SM_TB * (H1 + 4));                        // [SM_BC][H1]
     float (*hs)[SM_BC + 1] = reinterpret_cast<float (*)[SM_BC + 1]>(smem_b + SM_TB * (H1 + 4) + SM_BC * H1);   // [SM_TB][SM_BC+1]
-    float (*fm)[SM_BC + 1] = reinterpret_cast<float (*)[SM_BC + 1]>(smem_b + SM_TB * (H1 + 4) + SM_BC * H1 + SM_TB * (SM_BC + 1));
+    float* ss = smem_b + SM_TB * (H1 + 4) + SM_BC * H1 + SM_TB * (SM_BC + 1);                            // [SM_TB][K+1] field sums
+    float* gs = ss + SM_TB * (K + 1);                                                                    // [SM_TB] dz
     const int tid = threadIdx.x;
     const int c0 = blockIdx.y * SM_BC;
     const int cw = min(SM_BC, D - c0);
     constexpr int NQ = (SM_BC * (H1 / 4) + 255) / 256;     // (c, 4 j) items per thread
+    constexpr int NH = SM_TB * (SM_BC / 4) / 256;          // h0 float4 per thread per tile (8)
+    constexpr int ND = (SM_TB * (H1 / 4) + 255) / 256;     // dh1 float4 per thread per tile
     float4 wacc[NQ];
 #pragma unroll
     for (int u = 0; u < NQ; ++u) wacc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int q = tid; q < SM_BC * H1; q += 256) ws[q / H1][q % H1] = (q / H1) < cw ? W0[(size_t)c0 * H1 + q] : 0.f;
     const int ntiles = (B + SM_TB - 1) / SM_TB;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int KS = K / 4;                                  // float4 per S row
+    float4 ph[NH], pd[ND], ps;
+    float pg;
+    auto fetch = [&](int tile) {
+        const int b0 = tile * SM_TB;
+#pragma unroll
+        for (int u = 0; u < NH; ++u) {
+            int q = tid + u * 256;
+            int r = q / (SM_BC / 4), cc = (q % (SM_BC / 4)) * 4;
+            ph[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b0 + r < B && cc < cw) ph[u] = __ldg(reinterpret_cast<const float4*>(h0 + (size_t)(b0 + r) * D + c0 + cc));
+        }
+#pragma unroll
+        for (int u = 0; u < ND; ++u) {
+            int q = tid + u * 256;
+            int r = q / (H1 / 4), jj = (q % (H1 / 4)) * 4;
+            pd[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < SM_TB * (H1 / 4) && b0 + r < B) pd[u] = __ldg(reinterpret_cast<const float4*>(dh1 + (size_t)(b0 + r) * H1 + jj));
+        }
+        ps = make_float4(0.f, 0.f, 0.f, 0.f);
+        pg = 0.f;
+        if (svec) {   // S rows: SM_TB * K/4 float4, at most 2 per thread for K <= 16 -> loop in the store phase for larger K
+            if (tid < SM_TB && b0 + tid < B) pg = __ldg(dz + b0 + tid);
+        }
+    };
+    int tile = blockIdx.x;
+    if (tile < ntiles) fetch(tile);
+    for (; tile < ntiles; tile += gridDim.x) {
         const int b0 = tile * SM_TB;
         __syncthreads();
-        for (int q = tid; q < SM_TB * (SM_BC / 4); q += 256) {
+#pragma unroll
+        for (int u = 0; u < NH; ++u) {
+            int q = tid + u * 256;
             int r = q / (SM_BC / 4), cc = (q % (SM_BC / 4)) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (b0 + r < B && cc < cw) {
-                v = __ldg(reinterpret_cast<const float4*>(h0 + (size_t)(b0 + r) * D + c0 + cc));
-                if (svec) {   // FM part of the gradient: dz * (S - E); (c0 + cc) % K is a multiple of 4 -> one float4 of S
-                    float g = __ldg(dz + b0 + r);
-                    float4 sv = __ldg(reinterpret_cast<const float4*>(svec + (size_t)(b0 + r) * K + ((c0 + cc) % K)));
-                    t = make_float4(g * (sv.x - v.x), g * (sv.y - v.y), g * (sv.z - v.z), g * (sv.w - v.w));
-                }
-            }
-            hs[r][cc] = v.x; hs[r][cc + 1] = v.y; hs[r][cc + 2] = v.z; hs[r][cc + 3] = v.w;
-            fm[r][cc] = t.x; fm[r][cc + 1] = t.y; fm[r][cc + 2] = t.z; fm[r][cc + 3] = t.w;
+            hs[r][cc] = ph[u].x; hs[r][cc + 1] = ph[u].y; hs[r][cc + 2] = ph[u].z; hs[r][cc + 3] = ph[u].w;
         }
-        for (int q = tid; q < SM_TB * (H1 / 4); q += 256) {
+#pragma unroll
+        for (int u = 0; u < ND; ++u) {
+            int q = tid + u * 256;
             int r = q / (H1 / 4), jj = (q % (H1 / 4)) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (b0 + r < B) v = __ldg(reinterpret_cast<const float4*>(dh1 + (size_t)(b0 + r) * H1 + jj));
-            *reinterpret_cast<float4*>(&ds[r][jj]) = v;
+            if (q < SM_TB * (H1 / 4)) *reinterpret_cast<float4*>(&ds[r][jj]) = pd[u];
+        }
+        if (svec) {
+            if (tid < SM_TB) gs[tid] = pg;
+            for (int q = tid; q < SM_TB * KS; q += 256) {
+                int r = q / KS, k4 = (q % KS) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (b0 + r < B) v = __ldg(reinterpret_cast<const float4*>(svec + (size_t)(b0 + r) * K + k4));
+                float* d = ss + r * (K + 1) + k4;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
         }
         __syncthreads();
+        if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);   // in flight during (b) and (a)
         // (b) dW0[c][j] += sum_s h0[s][c] * dh1[s][j]   (samples walked in order -> deterministic)
 #pragma unroll
         for (int u = 0; u < NQ; ++u) {
@@ -289,13 +322,16 @@ __global__ void __launch_bounds__(256) small_mlp_bwd_input_kernel(
         // (a) dE[s][c] = sum_j dh1[s][j] W0[c][j] + dz[s] * (S[s][c % K] - h0[s][c])   (in place in hs)
         {
             const int s = tid & (SM_TB - 1), half = tid >> 7;
-            const int b = b0 + s;
             float d[H1];
 #pragma unroll
             for (int j = 0; j < H1; ++j) d[j] = ds[s][j];
+            const float g = svec ? gs[s] : 0.f;
+            const float* srow = ss + s * (K + 1);
+            int kk = (c0 + half * (SM_BC / 2)) % K;
 #pragma unroll 4
             for (int c = half * (SM_BC / 2); c < (half + 1) * (SM_BC / 2); ++c) {
-                float a = fm[s][c];
+                float a = svec ? g * (srow[kk] - hs[s][c]) : 0.f;
+                kk = (kk + 1 == K) ? 0 : kk + 1;
 #pragma unroll
                 for (int j4 = 0; j4 < H1 / 4; ++j4) {
                     float4 w = *reinterpret_cast<const float4*>(&ws[c][j4 * 4]);
