@@ -153,6 +153,9 @@ int dfm_flush(dfm_handle* h, void* stream);
 int dfm_sync(dfm_handle* h);
 
 int64_t dfm_global_step(const dfm_handle* h);
+/* Checkpoint restore (trainers/deep_fm.py:147-148 --restore; tf.train.Saver restores global_step and the
+ * Adam beta powers): call after loading every variable and slot with dfm_set_tensor. */
+int dfm_set_global_step(dfm_handle* h, int64_t step);
 /* number of kernels the last train step launched (bench.py's gpu_launches) */
 int64_t dfm_last_step_launches(const dfm_handle* h);
 /* device time (ms) spent in the named phase during the last *timed* step; enable with

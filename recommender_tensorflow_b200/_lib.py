@@ -62,6 +62,7 @@ _SIGS = {
     "dfm_flush": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dfm_sync": (C.c_int, [C.c_void_p]),
     "dfm_global_step": (C.c_int64, [C.c_void_p]),
+    "dfm_set_global_step": (C.c_int, [C.c_void_p, C.c_int64]),
     "dfm_last_step_launches": (C.c_int64, [C.c_void_p]),
     "dfm_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "dfm_phase_ms": (C.c_float, [C.c_void_p, C.c_char_p]),

@@ -141,6 +141,7 @@ static const char* kPhases[dfm_handle::NPH] = {"transform", "sort", "segments", 
     } while (0)
 
 static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+static inline float __int_as_float_host(int v) { float f; memcpy(&f, &v, 4); return f; }
 
 static int opt_slots(int kind) { return kind == DFM_OPT_ADAM ? 2 : kind == DFM_OPT_ADAGRAD ? 1 : kind == DFM_OPT_FTRL ? 2 : 0; }
 
@@ -1077,6 +1078,28 @@ extern "C" int dfm_sync(dfm_handle* h) {
 }
 
 extern "C" int64_t dfm_global_step(const dfm_handle* h) { return h ? h->step : -1; }
+
+// Restore point: variables + slots were loaded with dfm_set_tensor from a checkpoint taken at `step`
+// (tables fully materialised, i.e. after dfm_flush).  Rebuilds what TF keeps in beta1_power / beta2_power /
+// global_step and marks every row as current.
+extern "C" int dfm_set_global_step(dfm_handle* h, int64_t step) {
+    if (!h || step < 0) return DFM_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    int rc = ensure_alpha(h, step + 1);
+    if (rc) return rc;
+    float b1d = 1.f, b2d = 1.f, b1l = 1.f, b2l = 1.f;
+    for (int64_t i = 0; i < step; ++i) { b1d *= h->od.beta1; b2d *= h->od.beta2; b1l *= h->ol.beta1; b2l *= h->ol.beta2; }
+    h->b1p_d = b1d; h->b2p_d = b2d; h->b1p_l = b1l; h->b2p_l = b2l;
+    h->step = step; h->flushed_step = step;
+    if (h->R_loc) {
+        fill_strided_kernel<<<cdiv((int64_t)h->R_loc, 256), 256, 0, h->stream>>>(reinterpret_cast<float*>(h->lin_rec) + 3, h->R_loc, 1, 4,
+                                                                                  __int_as_float_host((int)step));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
 extern "C" int64_t dfm_last_step_launches(const dfm_handle* h) { return h ? h->last_step_launches : -1; }
 extern "C" int dfm_set_profiling(dfm_handle* h, int32_t on) { if (!h) return DFM_ERR_INVALID_ARG; h->profiling = on != 0; return DFM_OK; }
 extern "C" float dfm_phase_ms(dfm_handle* h, const char* phase) {

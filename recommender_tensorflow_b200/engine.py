@@ -192,6 +192,64 @@ class DeepFMEngine:
                 out[v + "/" + s] = self.get_tensor(v + "/" + s)
         return out
 
+    # ------------------------------------------------------------------ checkpoints (tf.train.Saver surface)
+    def tf_variable_map(self, scheme="deep_fm"):
+        """TF-1.12 checkpoint variable name -> (generic tensor name, row_begin, n_rows, shape).
+        scheme 'deep_fm': names created by trainers/deep_fm.py::model_fn; 'canned': DNNLinearCombinedClassifier."""
+        m = {}
+        emb_fmt = ("input_layer/input_layer/%s_embedding/embedding_weights" if scheme == "deep_fm"
+                   else "dnn/input_from_feature_columns/input_layer/%s_embedding/embedding_weights")
+        for f, s in enumerate(self.specs):
+            r0, n = int(self.row_offsets[f]), int(self.num_buckets[f])
+            if self.use_mf or self.use_dnn:
+                m[emb_fmt % s["name"]] = ("emb", r0, n, (n, self.k))
+            if self.use_linear:
+                m["linear/linear_model/%s/weights" % s["name"]] = ("lin", r0, n, (n, 1))
+        dn = len(self.num_columns)
+        if dn and (self.use_mf or self.use_dnn):
+            m["input_layer/numeric_embeddings"] = ("num_emb", 0, dn, (1, dn, self.k))
+        if self.use_linear:
+            for j, c in enumerate(self.num_columns):
+                m["linear/linear_model/%s/weights" % c.key] = ("num_lin", j, 1, (1, 1))
+            m["linear/linear_model/bias_weights"] = ("bias", 0, 1, (1,))
+        if self.use_dnn:
+            pre = "dnn/dnn/" if scheme == "deep_fm" else "dnn/"
+            mid = "/dense" if scheme == "deep_fm" else ""
+            fan_in = (len(self.specs) + dn) * self.k
+            for i, hsz in enumerate(self.hidden):
+                m["%shiddenlayer_%d%s/kernel" % (pre, i, mid)] = ("W%d" % i, 0, fan_in, (fan_in, hsz))
+                m["%shiddenlayer_%d%s/bias" % (pre, i, mid)] = ("b%d" % i, 0, hsz, (hsz,))
+                fan_in = hsz
+            m["%slogits%s/kernel" % (pre, mid)] = ("Wo", 0, fan_in, (fan_in, 1))
+            m["%slogits%s/bias" % (pre, mid)] = ("bo", 0, 1, (1,))
+        return m
+
+    _SLOT_TF = {"m": "Adam", "v": "Adam_1", "acc": {"Adagrad": "Adagrad", "Ftrl": "accum"}, "lin": "linear"}
+
+    def save_checkpoint(self, path, scheme="deep_fm"):
+        """Variables + optimizer slots + global_step under TF-1.12 names, as one .npz (flushes deferred Adam)."""
+        out = {"global_step": np.int64(self.global_step)}
+        for tf_name, (g, r0, n, shape) in self.tf_variable_map(scheme).items():
+            out[tf_name] = self.get_tensor(g, r0, n).reshape(shape)
+            grp = self.opt_linear if g in ("lin", "num_lin", "bias") else self.opt_deep
+            for sl in self.slot_names(g):
+                t = self._SLOT_TF[sl]
+                t = t[grp["name"]] if isinstance(t, dict) else t
+                out[tf_name + "/" + t] = self.get_tensor(g + "/" + sl, r0, n).reshape(shape)
+        np.savez(path, **out)
+        return path
+
+    def load_checkpoint(self, path, scheme="deep_fm"):
+        data = np.load(path)
+        for tf_name, (g, r0, n, shape) in self.tf_variable_map(scheme).items():
+            self.set_tensor(g, data[tf_name].reshape(n, -1), r0)
+            grp = self.opt_linear if g in ("lin", "num_lin", "bias") else self.opt_deep
+            for sl in self.slot_names(g):
+                t = self._SLOT_TF[sl]
+                t = t[grp["name"]] if isinstance(t, dict) else t
+                self.set_tensor(g + "/" + sl, data[tf_name + "/" + t].reshape(n, -1), r0)
+        self._check(self.lib.dfm_set_global_step(self.h, int(data["global_step"])))
+
     def init_random(self, seed=0):
         self._check(self.lib.dfm_init_random(self.h, seed))
 

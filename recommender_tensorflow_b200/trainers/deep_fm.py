@@ -5,6 +5,8 @@ and error behaviour (trainers/deep_fm.py:11-34).  TensorFlow builds a graph once
 `train_op`; here there is no graph: the first call builds the engine (cached in `params`), and
 every TRAIN call executes one `session.run(train_op)` equivalent on the given batch.
 """
+import glob
+import os
 import shutil
 from argparse import ArgumentParser
 from collections import namedtuple
@@ -73,8 +75,39 @@ class Estimator:
     """Minimal stand-in for tf.estimator.Estimator(model_fn, model_dir, config, params): train /
     evaluate / predict loops around model_fn, checkpoints as .npz (variables + optimizer slots)."""
 
+    KEEP_CHECKPOINT_MAX = 5      # trainers/conf_utils.py:6-10
+
     def __init__(self, model_fn, model_dir=None, config=None, params=None):
         self.model_fn, self.model_dir, self.config, self.params = model_fn, model_dir, config, dict(params or {})
+        self._restored = False
+
+    # -- checkpoints: tf.train.Saver equivalents (variables + slots under TF-1.12 names, .npz container)
+    def latest_checkpoint(self):
+        if not self.model_dir:
+            return None
+        found = glob.glob(os.path.join(self.model_dir, "model.ckpt-*.npz"))
+        return max(found, key=lambda p: int(p.rsplit("-", 1)[1].split(".")[0])) if found else None
+
+    def save_checkpoint(self):
+        if not self.model_dir or self.engine is None:
+            return None
+        os.makedirs(self.model_dir, exist_ok=True)
+        path = os.path.join(self.model_dir, "model.ckpt-%d.npz" % self.engine.global_step)
+        self.engine.save_checkpoint(path)
+        old = sorted(glob.glob(os.path.join(self.model_dir, "model.ckpt-*.npz")),
+                     key=lambda p: int(p.rsplit("-", 1)[1].split(".")[0]))
+        for p in old[:-self.KEEP_CHECKPOINT_MAX]:
+            os.remove(p)
+        return path
+
+    def _maybe_restore(self):
+        """Estimator semantics: a model_dir that already holds a checkpoint is resumed (the trainer wipes it
+        first unless --restore is given, trainers/deep_fm.py:147-148)."""
+        if not self._restored and self.engine is not None:
+            self._restored = True
+            ck = self.latest_checkpoint()
+            if ck:
+                self.engine.load_checkpoint(ck)
 
     @property
     def engine(self):
@@ -83,8 +116,11 @@ class Estimator:
     def train(self, input_fn, steps=None, max_steps=None, log_every=100):
         loss = None
         for feats, labels in input_fn():
+            if self.engine is None:
+                self.params[_ENGINE_KEY] = _build_engine(self.params, _batch_size(feats))
+            self._maybe_restore()
             eng = self.engine
-            if max_steps is not None and eng is not None and eng.global_step >= max_steps:
+            if max_steps is not None and eng.global_step >= max_steps:
                 break
             spec = self.model_fn(feats, labels, ModeKeys.TRAIN, self.params)
             loss = spec.loss
@@ -94,11 +130,15 @@ class Estimator:
                 steps -= 1
                 if steps <= 0:
                     break
+        self.save_checkpoint()
         return loss
 
     def evaluate(self, input_fn):
         ys, zs = [], []
         for feats, labels in input_fn():
+            if self.engine is None:
+                self.params[_ENGINE_KEY] = _build_engine(self.params, _batch_size(feats))
+            self._maybe_restore()
             spec = self.model_fn(feats, labels, ModeKeys.EVAL, self.params)
             ys.append(np.asarray(labels, dtype=np.float32).reshape(-1))
             zs.append(spec.predictions["logits"].reshape(-1))

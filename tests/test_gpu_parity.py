@@ -193,3 +193,51 @@ def test_eval_forward_matches_oracle():
     ref = ora.forward(transforms.transform(eng.specs, feats)).numpy()
     assert np.allclose(z, ref, rtol=RTOL, atol=2e-6)
     assert eng.global_step == 3
+
+
+def test_checkpoint_round_trip_tf_names(tmp_path):
+    """save (TF-1.12 variable names, slots, global_step) -> fresh engine -> load -> continue == uninterrupted."""
+    a = _ml_engine()
+    make_pair(a, seed=30)
+    ml, rng = synth.ML100K(), np.random.default_rng(31)
+    batches = [ml.batch(64, rng) for _ in range(9)]
+    for f, y in batches[:5]:
+        a.train_step(f, y)
+    path = a.save_checkpoint(str(tmp_path / "model.ckpt-5.npz"))
+    data = np.load(path)
+    assert int(data["global_step"]) == 5
+    assert data["input_layer/input_layer/user_id_embedding/embedding_weights"].shape == (1000, 4)
+    assert data["linear/linear_model/age_bucketized/weights/Adam_1"].shape == (7, 1)
+    assert data["dnn/dnn/hiddenlayer_0/dense/kernel"].shape == (104, 16)
+    b = _ml_engine()
+    b.load_checkpoint(path)
+    assert b.global_step == 5
+    for f, y in batches[5:]:
+        la, lb = a.train_step(f, y), b.train_step(f, y)
+        assert abs(la - lb) <= 1e-6 * abs(la) + 1e-7
+    sa, sb = a.state(), b.state()
+    for name in sa:
+        assert np.allclose(sa[name], sb[name], rtol=2e-6, atol=1e-8), name
+
+
+def test_estimator_model_fn_facade(tmp_path):
+    """model_fn / Estimator keep the reference's call shape (trainers/deep_fm.py:11, 153-178)."""
+    from recommender_tensorflow_b200.trainers import deep_fm, ml_100k
+    csv_path = str(tmp_path / "train.csv")
+    ml_100k.write_synthetic_csv(csv_path, 600)
+    fc_ = ml_100k.get_feature_columns(embedding_size=4)
+    est = deep_fm.Estimator(model_fn=deep_fm.model_fn, model_dir=str(tmp_path / "ckpt"), params={
+        "categorical_columns": fc_["linear"], "use_linear": True, "use_mf": True, "use_dnn": True,
+        "embedding_size": 4, "hidden_units": [16, 16], "dropout": 0, "max_batch": 64})
+    loss = est.train(ml_100k.get_input_fn(csv_path, batch_size=32, seed=0), max_steps=20, log_every=0)
+    assert np.isfinite(loss) and est.engine.global_step == 20
+    m = est.evaluate(ml_100k.get_input_fn(csv_path, ml_100k.ModeKeys.EVAL, batch_size=64))
+    assert set(["accuracy", "auc", "auc_precision_recall", "average_loss", "label/mean", "prediction/mean"]) <= set(m)
+    assert est.latest_checkpoint().endswith("model.ckpt-20.npz")
+    # a second estimator on the same model_dir resumes from step 20
+    est2 = deep_fm.Estimator(model_fn=deep_fm.model_fn, model_dir=str(tmp_path / "ckpt"), params=dict(est.params, **{deep_fm._ENGINE_KEY: None}))
+    est2.train(ml_100k.get_input_fn(csv_path, batch_size=32, seed=1), max_steps=25, log_every=0)
+    assert est2.engine.global_step == 25
+    with pytest.raises(ValueError):
+        deep_fm.model_fn({"user_id": np.zeros(4, np.int32)}, np.zeros(4), ml_100k.ModeKeys.TRAIN,
+                         {"categorical_columns": [], "numeric_columns": []})
