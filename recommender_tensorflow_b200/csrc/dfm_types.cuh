@@ -37,6 +37,7 @@ struct SegCounts {
 };
 
 constexpr int PIECE_C = 256;      // max entries per piece
+constexpr int COOP_PIECES = 8;    // rows with more pieces than this are summed by a whole warp in the update kernel
 constexpr int DIRECT_T = 32;      // rows with <= DIRECT_T lookups are summed directly in the update kernel
 
 // piece -> slot in the piece-sum buffer (collision free for pieces of rows with > DIRECT_T lookups)

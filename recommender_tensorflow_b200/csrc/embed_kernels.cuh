@@ -615,13 +615,21 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
     }
     const uint32_t U = cnt->n_rows;
     const int stride = (1 + emb_slots) * K;
-    for (uint32_t u = blockIdx.x * gpb + threadIdx.x / LPR; u < U; u += gridDim.x * gpb) {
-        uint32_t beg = row_start[u], end = row_start[u + 1];
-        uint32_t row = skeys[beg];
+    // row mapping: within one trip the lane groups of a warp take rows n_warps apart
+    const uint32_t TG = gridDim.x * gpb, gid = blockIdx.x * gpb + threadIdx.x / LPR;
+    const uint32_t gpw = 32 / LPR, n_warps = TG / gpw;
+    const uint32_t uoff = (gid % gpw) * n_warps + gid / gpw;
+    for (uint32_t ubase = 0; ubase < U; ubase += TG) {   // block-uniform trip count
+        const uint32_t u = ubase + uoff;
+        bool coop = false;
+        const bool act = u < U;
+        uint32_t beg = 0, end = 0;
+        if (act) { beg = row_start[u]; end = row_start[u + 1]; }
+        uint32_t row = act ? skeys[beg] : 0u;
         // issue the table-record loads now: they only depend on the row id and overlap the gradient gather below
         float4 w = make_float4(0.f, 0.f, 0.f, 0.f), s1 = w, s2 = w, lr = w;
         float4* base = nullptr;
-        if (!gsum_out) {
+        if (act && !gsum_out) {
             if (has_emb) {
                 base = reinterpret_cast<float4*>(emb_rec + (size_t)row * stride) + sub;
                 w = base[0];
@@ -632,7 +640,8 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
         }
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         float gl = 0.f;
-        if (end - beg <= (uint32_t)DIRECT_T) {
+        if (!act) {
+        } else if (end - beg <= (uint32_t)DIRECT_T) {
             for (uint32_t i = beg; i < end; i += 4) {
                 uint32_t v[4];
                 float4 t[4];
@@ -650,23 +659,71 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
             }
         } else {
             uint32_t p0 = row_piece0[u], p1 = row_piece0[u + 1];
-            for (uint32_t p = p0; p < p1; p += 4) {
-                float4 t[4];
-                float tl[4];
+            if (p1 - p0 > (uint32_t)COOP_PIECES) {
+                coop = true;      // summed below by the whole warp
+            } else {
+                for (uint32_t p = p0; p < p1; p += 4) {
+                    float4 t[4];
+                    float tl[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    t[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    tl[q] = 0.f;
-                    if (p + q < p1) {
-                        const float* ps = piece_sum + (size_t)piece_slot(__ldg(piece_start + p + q)) * (K + 4);
-                        t[q] = __ldg(reinterpret_cast<const float4*>(ps) + sub);
-                        if (sub == 0) tl[q] = __ldg(ps + K);
+                    for (int q = 0; q < 4; ++q) {
+                        t[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        tl[q] = 0.f;
+                        if (p + q < p1) {
+                            const float* ps = piece_sum + (size_t)piece_slot(__ldg(piece_start + p + q)) * (K + 4);
+                            t[q] = __ldg(reinterpret_cast<const float4*>(ps) + sub);
+                            if (sub == 0) tl[q] = __ldg(ps + K);
+                        }
                     }
-                }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { add4(g, t[q]); gl += tl[q]; }
+                    for (int q = 0; q < 4; ++q) { add4(g, t[q]); gl += tl[q]; }
+                }
             }
         }
+        // very hot rows (thousands of lookups -> many pieces): the lane groups of the warp take the pieces
+        // round-robin (4 loads in flight each) and a fixed butterfly combines them, instead of one group
+        // walking them all.  Rows are interleaved across warps (see the row mapping above) so that the
+        // adjacent hot rows of one small field land in different warps.
+        {
+            const int lane = threadIdx.x & 31, grp = lane / LPR;
+            constexpr int G = 32 / LPR;
+            uint32_t cmask = __ballot_sync(0xffffffffu, coop && sub == 0);
+            while (cmask) {
+                const int src_lane = __ffs(cmask) - 1;
+                cmask &= cmask - 1;
+                const uint32_t cu = __shfl_sync(0xffffffffu, u, src_lane);
+                const uint32_t p0 = __ldg(row_piece0 + cu), p1 = __ldg(row_piece0 + cu + 1);
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                float al = 0.f;
+                for (uint32_t p = p0 + grp; p < p1; p += 4 * G) {
+                    float4 t[4];
+                    float tl[4];
+                    uint32_t slot[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) slot[q] = (p + q * G < p1) ? piece_slot(__ldg(piece_start + p + q * G)) : 0xffffffffu;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        t[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        tl[q] = 0.f;
+                        if (slot[q] != 0xffffffffu) {
+                            const float* ps = piece_sum + (size_t)slot[q] * (K + 4);
+                            t[q] = __ldg(reinterpret_cast<const float4*>(ps) + sub);
+                            if (sub == 0) tl[q] = __ldg(ps + K);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { add4(a, t[q]); al += tl[q]; }
+                }
+#pragma unroll
+                for (int o = LPR; o < 32; o <<= 1) {
+                    a.x += __shfl_xor_sync(0xffffffffu, a.x, o); a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+                    a.z += __shfl_xor_sync(0xffffffffu, a.z, o); a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+                    al += __shfl_xor_sync(0xffffffffu, al, o);
+                }
+                if (lane / LPR == src_lane / LPR) { g = a; gl = al; }
+            }
+        }
+        if (!act) continue;
         if (gsum_out) {   // sharded requester side: emit the per-row gradient sum, the owner applies it
             float* gp = gsum_out + (size_t)u * gsum_stride;
             reinterpret_cast<float4*>(gp)[sub] = g;
