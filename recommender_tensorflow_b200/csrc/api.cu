@@ -95,6 +95,7 @@ struct dfm_handle {
     float* splitk = nullptr; int splits = 1, k_chunk = 0;
     float* colpart = nullptr; int rows_per_chunk = 512;
     float* head_part = nullptr; int head_blocks = 0;
+    bool fused_head = false; float* head_gpart = nullptr; int fused_head_blocks = 0;
     bool tc_mlp = false; float* tc_w = nullptr; int64_t tc_off[DFM_MAX_HIDDEN] = {0}; int tc_nz[DFM_MAX_HIDDEN] = {0};
     bool small_mlp = false; SmallMlpDesc sm{}; int small_grid = 0; size_t small_smem = 0;
     float *up_partial = nullptr, *w0_partial = nullptr;
@@ -198,7 +199,7 @@ static void free_all(dfm_handle* h) {
     cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, h->d_row_off, h->emb_rec, h->lin_rec, h->dw,
                     h->ds1, h->ds2, h->dg, h->ids, h->h0, h->s, h->zacc, h->logits, h->dz, h->dE, h->splitk, h->colpart, h->head_part,
-                    h->d_loss, h->d_dzsum, h->d_err, h->alpha_d, h->alpha_l, h->up_partial, h->w0_partial, h->tc_w, h->uidx,
+                    h->d_loss, h->d_dzsum, h->d_err, h->alpha_d, h->alpha_l, h->up_partial, h->w0_partial, h->tc_w, h->head_gpart, h->uidx,
                     h->req_rows, h->d_counts};
     for (void* p : ptrs) if (p) cudaFree(p);
     free_ws(h->ws);
@@ -459,6 +460,12 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
                 CK(cudaFuncSetAttribute(small_mlp_bwd_input_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_mlp_bwd_smem<32>(K)));
             }
         }
+    }
+    if (h->use_dnn && !h->small_mlp && h->L >= 1 && h->hidden[h->L - 1] % 32 == 0 && h->hidden[h->L - 1] <= 256 &&
+        getenv("DFM_NO_FUSED_HEAD") == nullptr) {
+        h->fused_head = true;
+        h->fused_head_blocks = std::min(h->head_blocks, 2 * h->sm_count);
+        if (dalloc(h, &h->head_gpart, (size_t)h->fused_head_blocks * 2 * h->hidden[h->L - 1])) return DFM_ERR_CUDA;
     }
     if (dalloc(h, &h->d_loss, 1)) return DFM_ERR_CUDA;
     if (dalloc(h, &h->d_dzsum, 1)) return DFM_ERR_CUDA;
@@ -787,7 +794,20 @@ static int forward_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t 
         hL = h->act[h->L]; H = in;
     }
     if (ph) ph->next();
-    head_kernel<<<h->head_blocks, 256, 0, st>>>((h->use_linear || h->use_mf) ? h->zacc : nullptr, hL, H, Wo ? h->dw + Wo->off : nullptr,
+    const float* za = (h->use_linear || h->use_mf) ? h->zacc : nullptr;
+    if (h->fused_head && labels) {
+        const int grid = std::min(h->fused_head_blocks, (B + 7) / 8);
+#define HEAD_BWD(NHH) head_bwd_kernel<NHH><<<grid, 256, 0, st>>>(za, hL, h->dw + Wo->off, h->dw + bo->off, labels, B, scale, h->logits, logits_out, \
+                                                             h->dz, h->dact[h->L], h->head_part, h->head_gpart)
+        switch (H / 32) {
+            case 1: HEAD_BWD(1); break; case 2: HEAD_BWD(2); break; case 3: HEAD_BWD(3); break; case 4: HEAD_BWD(4); break;
+            case 5: HEAD_BWD(5); break; case 6: HEAD_BWD(6); break; case 7: HEAD_BWD(7); break; default: HEAD_BWD(8); break;
+        }
+#undef HEAD_BWD
+        h->launches++;
+        return DFM_OK;
+    }
+    head_kernel<<<std::min(h->head_blocks, (B + 7) / 8), 256, 0, st>>>(za, hL, H, Wo ? h->dw + Wo->off : nullptr,
                                                 bo ? h->dw + bo->off : nullptr, labels, B, scale, h->logits, logits_out, h->dz, h->head_part);
     h->launches++;
     return DFM_OK;
@@ -819,7 +839,8 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
     const int dc = h->dc, d = dc + h->dn, dK = d * K;
     const DenseT* bo = find_dense(h, "bo"); const DenseT* bias = find_dense(h, "bias");
     const int small_blocks = std::min((B + SM_TB - 1) / SM_TB, h->small_grid);
-    head_final_kernel<<<1, 256, 0, st>>>(h->head_part, h->small_mlp ? small_blocks : h->head_blocks, scale, h->d_loss, h->d_dzsum);
+    const int head_blocks = h->small_mlp ? small_blocks : std::min(h->fused_head ? h->fused_head_blocks : h->head_blocks, (B + 7) / 8);
+    head_final_kernel<<<1, 256, 0, st>>>(h->head_part, head_blocks, scale, h->d_loss, h->d_dzsum);
     h->launches++;
     if (loss_out) CK(cudaMemcpyAsync(loss_out, h->d_loss, 4, cudaMemcpyDeviceToDevice, st));
     if (bo && !h->small_mlp) CK(cudaMemcpyAsync(h->dg + bo->off, h->d_dzsum, 4, cudaMemcpyDeviceToDevice, st));
@@ -844,7 +865,14 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
         const int L = h->L;
         const float* hL = h->act[L];
         const int H = L ? h->hidden[L - 1] : dK;
-        launch_colsum(h, hL, H, h->dz, B, H, h->dg + Wo->off, st);   // gWo = h_L^T dz
+        if (h->fused_head) {   // head_bwd_kernel already produced dh_L', gWo and gb_L partials
+            const DenseT* bL = find_dense(h, "b" + std::to_string(L - 1));
+            reduce_partials_kernel<<<cdiv(H, 256), 256, 0, st>>>(h->head_gpart, head_blocks, (size_t)2 * H, H, h->dg + Wo->off);
+            reduce_partials_kernel<<<cdiv(H, 256), 256, 0, st>>>(h->head_gpart + H, head_blocks, (size_t)2 * H, H, h->dg + bL->off);
+            h->launches += 2;
+        } else {
+            launch_colsum(h, hL, H, h->dz, B, H, h->dg + Wo->off, st);   // gWo = h_L^T dz
+        }
         if (L == 0) {
             dh_last_kernel<<<cdiv((int64_t)B * H, 256), 256, 0, st>>>(nullptr, h->dw + Wo->off, h->dz, (int64_t)B * H, H, h->dE);
             h->launches++;
@@ -853,8 +881,10 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
                 h->launches++;
             }
         } else {
-            dh_last_kernel<<<cdiv((int64_t)B * H, 256), 256, 0, st>>>(hL, h->dw + Wo->off, h->dz, (int64_t)B * H, H, h->dact[L]);
-            h->launches++;
+            if (!h->fused_head) {
+                dh_last_kernel<<<cdiv((int64_t)B * H, 256), 256, 0, st>>>(hL, h->dw + Wo->off, h->dz, (int64_t)B * H, H, h->dact[L]);
+                h->launches++;
+            }
             const int splits = std::max(1, std::min(h->splits, (B + 1023) / 1024));
             const int k_chunk = ((B + splits - 1) / splits + 15) / 16 * 16;
             const int nsplit = (B + k_chunk - 1) / k_chunk;
@@ -875,7 +905,7 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
                 reduce_partials_kernel<<<cdiv((int64_t)in * out, 256), 256, 0, st>>>(h->splitk, nparts, (size_t)in * out, (int64_t)in * out,
                                                                                      h->dg + W->off);
                 h->launches++;
-                launch_colsum(h, h->dact[i + 1], out, nullptr, B, out, h->dg + b->off, st);
+                if (!(h->fused_head && i == L - 1)) launch_colsum(h, h->dact[i + 1], out, nullptr, B, out, h->dg + b->off, st);
                 // dh_i [B,in] = dh_{i+1} [B,out] * W_i^T
                 if (h->tc_mlp) {
                     const float* w_hi = h->dw + W->off; const float* w_lo = nullptr;   // W [in, out] is already K-major for this GEMM
@@ -1444,6 +1474,7 @@ static int tc_gemm_kmajor(dfm_handle* h, const float* A_hi, const float* A_lo, i
     tc::Params p{};
     p.M = M; p.N = N; p.K = K; p.k_per_split = K; p.C = C; p.ldc = ldc; p.c_split_stride = 0; p.epi = epi; p.ep = ep;
     p.split_a = A_lo ? 0 : 1; p.split_b = B_lo ? 0 : 1;
+    if (const char* e = getenv("DFM_TC_DBG")) p.dbg = atoi(e);
     dim3 grid(cdiv(N, BN), cdiv(M, tc::BM), 1);
     if (BN == 256) tc::gemm_kernel<256, 0, TC_BK><<<grid, tc::NTHREADS, tc::Smem<256, TC_BK>::TOTAL, st>>>(ma, mal, mb, mbl, p);
     else tc::gemm_kernel<128, 0, TC_BK><<<grid, tc::NTHREADS, tc::Smem<128, TC_BK>::TOTAL, st>>>(ma, mal, mb, mbl, p);
@@ -1466,6 +1497,7 @@ static int tc_gemm_mnmajor(dfm_handle* h, const float* A, int lda, const float* 
     tc::Params p{};
     p.M = M; p.N = N; p.K = K; p.k_per_split = kps; p.C = Cpart; p.ldc = N; p.c_split_stride = (size_t)M * N; p.epi = EPI_NONE;
     p.split_a = 1; p.split_b = 1;
+    if (const char* e = getenv("DFM_TC_DBG")) p.dbg = atoi(e);
     dim3 grid(cdiv(N, BN), cdiv(M, tc::BM), nz);
     if (BN == 256) tc::gemm_kernel<256, 1, TC_BK><<<grid, tc::NTHREADS, tc::Smem<256, TC_BK>::TOTAL, st>>>(ma, ma, mb, mb, p);
     else tc::gemm_kernel<128, 1, TC_BK><<<grid, tc::NTHREADS, tc::Smem<128, TC_BK>::TOTAL, st>>>(ma, ma, mb, mb, p);

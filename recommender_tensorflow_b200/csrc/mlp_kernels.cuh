@@ -306,6 +306,72 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ zac
     }
 }
 
+// Fused head + top of the backward pass for towers whose last hidden layer is H = 32*NH wide (NH <= 8):
+// per sample (one warp): z = zacc + h_L . Wo + bo, loss, dz, and immediately dh_L' = dz * Wo * relu'(h_L)
+// while h_L is still in registers; per-block partial sums (fixed order) of the loss, dz,
+// gWo = h_L^T dz and gb_L = column sums of dh_L'.  Replaces head_kernel + dh_last_kernel + two column-sum
+// launches (and one re-read of h_L).   gpart layout: [grid][2*H] = {gWo | gb_L}
+template <int NH>
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ zacc, const float* __restrict__ hL,
+                                                       const float* __restrict__ Wo, const float* __restrict__ bo,
+                                                       const float* __restrict__ labels, int B, float scale,
+                                                       float* __restrict__ logits, float* __restrict__ logits_out,
+                                                       float* __restrict__ dz, float* __restrict__ dh,
+                                                       float* __restrict__ part /*[grid][2]*/, float* __restrict__ gpart) {
+    constexpr int H = 32 * NH;
+    __shared__ float sl[8], sd[8];
+    __shared__ float sg[8][2 * H];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float wo[NH], gw[NH], gb[NH];
+#pragma unroll
+    for (int i = 0; i < NH; ++i) { wo[i] = __ldg(Wo + lane + 32 * i); gw[i] = 0.f; gb[i] = 0.f; }
+    const float b0 = bo[0];
+    float lsum = 0.f, dsum = 0.f;
+    for (int b = blockIdx.x * 8 + warp; b < B; b += gridDim.x * 8) {
+        float h[NH];
+        float z = 0.f;
+#pragma unroll
+        for (int i = 0; i < NH; ++i) { h[i] = hL[(size_t)b * H + lane + 32 * i]; z = fmaf(h[i], wo[i], z); }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+        z += b0;
+        if (zacc) z += zacc[b];
+        const float y = labels[b];
+        const float g = (1.f / (1.f + expf(-z)) - y) * scale;
+        if (lane == 0) {
+            logits[b] = z;
+            if (logits_out) logits_out[b] = z;
+            dz[b] = g;
+            lsum += fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));
+            dsum += g;
+        }
+#pragma unroll
+        for (int i = 0; i < NH; ++i) {
+            const float d = h[i] > 0.f ? g * wo[i] : 0.f;
+            dh[(size_t)b * H + lane + 32 * i] = d;
+            gw[i] = fmaf(h[i], g, gw[i]);
+            gb[i] += d;
+        }
+    }
+    if (lane == 0) { sl[warp] = lsum; sd[warp] = dsum; }
+#pragma unroll
+    for (int i = 0; i < NH; ++i) { sg[warp][lane + 32 * i] = gw[i]; sg[warp][H + lane + 32 * i] = gb[i]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, c = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { a += sl[w]; c += sd[w]; }
+        part[blockIdx.x * 2] = a;
+        part[blockIdx.x * 2 + 1] = c;
+    }
+    for (int j = threadIdx.x; j < 2 * H; j += 256) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += sg[w][j];
+        gpart[(size_t)blockIdx.x * 2 * H + j] = a;
+    }
+}
+
 // loss = (sum of block partials) * loss_scale ; dzsum = sum of dz  (single thread block, fixed order)
 __global__ void head_final_kernel(const float* __restrict__ part, int nblocks, float loss_scale, float* __restrict__ loss_out,
                                   float* __restrict__ dzsum_out) {

@@ -127,6 +127,7 @@ struct Params {
     int epi;                  // EPI_*
     EpiArgs ep;
     int split_a, split_b;     // 1: operand is raw fp32, split in the kernel; 0: hi/lo come from two tensor maps
+    int dbg;                  // experiments only: 1 = skip the split work, 2 = skip the MMAs
 };
 
 template <int BN, int BK>
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
                 const uint32_t st = smem_u32(smem + s * S::STAGE);
                 const uint32_t a_hi = st, a_lo = st + S::A_BYTES, b_hi = st + 2 * S::A_BYTES, b_lo = st + 2 * S::A_BYTES + S::B_BYTES;
 #pragma unroll
-                for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                for (int ks = 0; ks < ((p.dbg & 2) ? 0 : BK / UMMA_K); ++ks) {
                     // K-major: +32 bytes inside the 128-byte swizzle row; MN-major: next 8-row (1024 B) atom
                     const uint32_t adv = MODE == 0 ? ks * UMMA_K * 4 : ks * 1024;
                     // K-major: 8-row atoms of BK*4-byte rows (SWIZZLE_128B for BK=32, SWIZZLE_64B for BK=16)
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
             const int s = kb % S::STAGES;
             mbar_wait(&full[s], (kb / S::STAGES) & 1);
             uint8_t* st = smem + s * S::STAGE;
-            if (p.split_a) {
+            if (p.split_a && !(p.dbg & 1)) {
                 float4* hi = reinterpret_cast<float4*>(st);
                 float4* lo = reinterpret_cast<float4*>(st + S::A_BYTES);
 #pragma unroll 4
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
 #endif
                 }
             }
-            if (p.split_b) {
+            if (p.split_b && !(p.dbg & 1)) {
                 float4* hi = reinterpret_cast<float4*>(st + 2 * S::A_BYTES);
                 float4* lo = reinterpret_cast<float4*>(st + 2 * S::A_BYTES + S::B_BYTES);
 #pragma unroll 4
