@@ -1159,7 +1159,7 @@ static int shard_requests_impl(dfm_handle* h, const BatchPtrs& bp, int B, uint32
     if ((rc = build_segments(h, h->ws, n, limit, h->key_bits, st, nullptr))) return rc;
     CK(cudaMemsetAsync(h->d_counts, 0, ((size_t)W + 1) * 4, st));
     if (n > 0) {
-        shard_uniq_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->ws.skeys(), h->ws.svals(), n, limit, h->Rl, h->ws.flags, h->uidx, h->req_rows, h->d_counts);
+        shard_uniq_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->ws.skeys(), h->ws.svals(), n, limit, h->Rl, W, h->ws.flags, h->uidx, h->req_rows, h->d_counts);
         h->launches++;
     }
     CK(cudaMemcpyAsync(h->h_counts, h->d_counts, (size_t)W * 4, cudaMemcpyDeviceToHost, st));

@@ -772,21 +772,34 @@ __global__ void shard_rekey_kernel(uint32_t* __restrict__ keys, int64_t n, uint3
     }
 }
 // per sorted position: lookup -> unique index; per unique row: local row id for its owner + per-owner counts
-__global__ void shard_uniq_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svals, int64_t n, uint32_t limit,
-                                  uint32_t Rl, const unsigned long long* __restrict__ scanned, uint32_t* __restrict__ uidx,
-                                  uint32_t* __restrict__ req_rows, int32_t* __restrict__ counts) {
+__global__ void __launch_bounds__(256) shard_uniq_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svals, int64_t n,
+                                                         uint32_t limit, uint32_t Rl, uint32_t W,
+                                                         const unsigned long long* __restrict__ scanned, uint32_t* __restrict__ uidx,
+                                                         uint32_t* __restrict__ req_rows, int32_t* __restrict__ counts) {
+    // per-owner counts are aggregated per block in shared memory first: the sorted keys put (almost) every
+    // lookup of a block on the same owner, and same-address global atomics serialise in L2
+    __shared__ int sc[64];
+    if (threadIdx.x < 64) sc[threadIdx.x] = 0;
+    __syncthreads();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t k = skeys[i];
-    if (k >= limit) { uidx[svals[i]] = 0xffffffffu; return; }
-    bool rh = (i == 0) || (k != skeys[i - 1]);
-    uint32_t ridx = (uint32_t)(scanned[i] >> 32);
-    if (!rh) ridx -= 1;
-    uidx[svals[i]] = ridx;
-    if (rh) {
-        req_rows[ridx] = k % Rl;
-        atomicAdd(&counts[k / Rl], 1);
+    if (i < n) {
+        uint32_t k = skeys[i];
+        if (k >= limit) {
+            uidx[svals[i]] = 0xffffffffu;
+        } else {
+            bool rh = (i == 0) || (k != skeys[i - 1]);
+            uint32_t ridx = (uint32_t)(scanned[i] >> 32);
+            if (!rh) ridx -= 1;
+            uidx[svals[i]] = ridx;
+            if (rh) {
+                req_rows[ridx] = k % Rl;
+                uint32_t o = k / Rl;
+                if (W <= 64) atomicAdd(&sc[o], 1); else atomicAdd(&counts[o], 1);
+            }
+        }
     }
+    __syncthreads();
+    if (W <= 64 && threadIdx.x < W && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sc[threadIdx.x]);
 }
 __global__ void iota_kernel(uint32_t* __restrict__ v, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

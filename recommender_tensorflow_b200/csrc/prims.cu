@@ -112,8 +112,10 @@ void exclusive_scan_u64(const uint64_t* in, uint64_t* out, int64_t n, void* temp
 // Tile layout shared by the histogram and scatter kernels: warp w of a block owns the contiguous
 // index range [tile + w*32*ITEMS, +32*ITEMS); item j of lane l is index base + j*32 + l, so the
 // stable order inside a warp is (j, lane) lexicographic and warps / blocks follow index order.
+template <int RB>
 __global__ void __launch_bounds__(SORT_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift,
                                                                   uint32_t* __restrict__ counts, int64_t nblocks) {
+    constexpr int RADIX = 1 << RB;
     __shared__ uint32_t hist[RADIX];
     for (int i = threadIdx.x; i < RADIX; i += SORT_THREADS) hist[i] = 0;
     __syncthreads();
@@ -128,10 +130,12 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_hist_kernel(const uint32_t
     for (int i = threadIdx.x; i < RADIX; i += SORT_THREADS) counts[(int64_t)i * nblocks + blockIdx.x] = hist[i];
 }
 
+template <int RB>
 __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                                      int64_t n, int shift, const uint32_t* __restrict__ offsets,
                                                                      int64_t nblocks) {
+    constexpr int RADIX = 1 << RB;
     constexpr int NW = SORT_THREADS / 32;
     __shared__ uint32_t wcnt[NW][RADIX];
     for (int i = threadIdx.x; i < NW * RADIX; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
@@ -187,24 +191,33 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(const uint3
     }
 }
 
-int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], int64_t n, int bits, void* temp, cudaStream_t st, int64_t* launches) {
-    if (n <= 1 || bits <= 0) return 0;
+template <int RB>
+static int radix_sort_rb(uint32_t* keys[2], uint32_t* vals[2], int64_t n, int bits, void* temp, cudaStream_t st, int64_t* launches) {
     const int64_t nb = sort_blocks(n);
-    const int64_t cnt = (int64_t)RADIX * nb;
+    const int64_t cnt = (int64_t)(1 << RB) * nb;
     uint32_t* counts = reinterpret_cast<uint32_t*>(temp);
-    uint32_t* offsets = counts + cnt;
-    void* scan_temp = reinterpret_cast<void*>(offsets + cnt);
+    uint32_t* offsets = counts + (int64_t)MAX_RADIX * nb;
+    void* scan_temp = reinterpret_cast<void*>(offsets + (int64_t)MAX_RADIX * nb);
     int cur = 0;
-    for (int shift = 0; shift < bits; shift += RADIX_BITS) {
-        radix_hist_kernel<<<(unsigned)nb, SORT_THREADS, 0, st>>>(keys[cur], n, shift, counts, nb);
+    for (int shift = 0; shift < bits; shift += RB) {
+        radix_hist_kernel<RB><<<(unsigned)nb, SORT_THREADS, 0, st>>>(keys[cur], n, shift, counts, nb);
         if (launches) *launches += 1;
         exclusive_scan_u32(counts, offsets, cnt, scan_temp, nullptr, st, launches);
-        radix_scatter_kernel<<<(unsigned)nb, SORT_THREADS, 0, st>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift,
-                                                                    offsets, nb);
+        radix_scatter_kernel<RB><<<(unsigned)nb, SORT_THREADS, 0, st>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift,
+                                                                        offsets, nb);
         if (launches) *launches += 1;
         cur ^= 1;
     }
     return cur;
+}
+
+int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], int64_t n, int bits, void* temp, cudaStream_t st, int64_t* launches) {
+    if (n <= 1 || bits <= 0) return 0;
+    // fewest passes first, then the narrowest digit (smaller histograms)
+    const int p8 = (bits + 7) / 8, p9 = (bits + 8) / 9, p10 = (bits + 9) / 10;
+    if (p8 <= p9 && p8 <= p10) return radix_sort_rb<8>(keys, vals, n, bits, temp, st, launches);
+    if (p9 <= p10) return radix_sort_rb<9>(keys, vals, n, bits, temp, st, launches);
+    return radix_sort_rb<10>(keys, vals, n, bits, temp, st, launches);
 }
 
 }  // namespace prims

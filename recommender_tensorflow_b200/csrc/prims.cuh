@@ -11,8 +11,8 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
-constexpr int RADIX_BITS = 8;
-constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int MAX_RADIX_BITS = 10;     // digit width is chosen per sort (8, 9 or 10 bits) to minimise the passes
+constexpr int MAX_RADIX = 1 << MAX_RADIX_BITS;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 8;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
@@ -24,7 +24,7 @@ inline int64_t sort_blocks(int64_t n) { return (n + SORT_TILE - 1) / SORT_TILE; 
 inline size_t scan_temp_bytes(int64_t n, size_t elem) { return (size_t)(scan_blocks(n) + 1) * elem; }
 // temp bytes for radix_sort_pairs of n pairs
 inline size_t sort_temp_bytes(int64_t n) {
-    int64_t cnt = (int64_t)RADIX * sort_blocks(n);
+    int64_t cnt = (int64_t)MAX_RADIX * sort_blocks(n);
     return (size_t)cnt * 4 * 2 + scan_temp_bytes(cnt, 4) + 256;
 }
 

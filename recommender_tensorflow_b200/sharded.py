@@ -59,27 +59,48 @@ class ShardedTrainer:
         self.cnt_recv = torch.empty(self.W, dtype=torch.int32, device=dev)
         self.rw = rw
 
-    def train_step(self, pb, global_batch):
+    def train_step(self, pb, global_batch, timings=None):
         """One sharded train step on a device-resident PackedBatch; everything is enqueued on torch's current
-        stream (the only host sync is the per-owner counts inside dfm_shard_requests).  Returns the global
-        loss as a 0-dim cuda tensor."""
+        stream (the only host syncs are the two count exchanges).  Returns the global loss as a 0-dim cuda
+        tensor.  `timings` (dict) collects per-phase device milliseconds when given (debug)."""
         torch, dist, eng, rw = self.torch, self.dist, self.eng, self.rw
         st = torch.cuda.current_stream().cuda_stream
+        marks = []
+
+        def mark(name):
+            if timings is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+        mark("start")
         send_counts = eng.shard_requests(pb, self.req_rows, st)
+        mark("requests")
         self.cnt_send.copy_(torch.tensor(send_counts, dtype=torch.int32), non_blocking=True)
         dist.all_to_all_single(self.cnt_recv, self.cnt_send, group=self.group)
         recv_counts = self.cnt_recv.tolist()
+        mark("counts")
         U, n_recv = sum(send_counts), sum(recv_counts)
         dist.all_to_all_single(self.recv_rows[:n_recv], self.req_rows[:U], recv_counts, send_counts, group=self.group)
+        mark("a2a_ids")
         eng.shard_serve(self.recv_rows, n_recv, self.reply, st)
+        mark("serve")
         dist.all_to_all_single(self.rowbuf[:U * rw], self.reply[:n_recv * rw], split_sizes(send_counts, rw),
                                split_sizes(recv_counts, rw), group=self.group)
+        mark("a2a_rows")
         nd = eng.dense_size
         eng.shard_forward_backward(pb, self.rowbuf, global_batch, self.dense[nd:nd + 1], None, self.gsum, self.dense, st)
+        mark("fwd_bwd")
         dist.all_to_all_single(self.grecv[:n_recv * rw], self.gsum[:U * rw], split_sizes(recv_counts, rw),
                                split_sizes(send_counts, rw), group=self.group)
+        mark("a2a_grads")
         dist.all_reduce(self.dense, group=self.group)
+        mark("allreduce")
         eng.shard_apply(self.grecv, self.dense, st)
+        mark("apply")
+        if timings is not None:
+            torch.cuda.synchronize()
+            for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+                timings[n1] = timings.get(n1, 0.0) + e0.elapsed_time(e1)
         return self.dense[nd]
 
 
