@@ -364,6 +364,22 @@ def main():
             "phases_ms": phases,
             "clocks": sampler.summary(),
         }
+        if sharded:
+            # algorithmic NVLink bytes per sample of the sharded step (ids out, rows back, gradient rows out)
+            nvb = len(cats) * (4 + 2 * 4 * (w["k"] + 1)) * (world - 1) / world
+            ach = value / world * nvb / 1e9
+            line["roofline_nvlink"] = {"bound": "nvlink", "achieved": ach, "peak": 770.0, "unit": "GB/s per GPU per direction", "frac": ach / 770.0,
+                                       "bytes_per_sample": nvb, "peak_source": "B200_PROFILING.md measured peer copy (770 GB/s per direction)"}
+        if w["hidden"] and max(w["hidden"]) >= 64 and phases and not sharded:
+            # the tower GEMMs (3xTF32 on tcgen05): algorithmic fp32 flops of the tower vs the tf32 tensor peak / 3
+            d_in = (len(cats) + len(nums)) * w["k"]
+            dims = [d_in] + list(w["hidden"])
+            fl = 3 * 2 * B * (sum(a * b for a, b in zip(dims[:-1], dims[1:])) + dims[-1])
+            t = (phases["mlp_fwd"] + phases["mlp_bwd"]) * 1e-3
+            bf16 = float(peaks.get("bf16_tflops", 1590.0))
+            line["roofline_tower"] = {"bound": "tensor", "achieved": fl / t / 1e12, "peak": bf16 / 2 / 3, "unit": "TFLOP/s (fp32-equivalent)",
+                                      "frac": fl / t / 1e12 / (bf16 / 6), "flops_per_step": fl,
+                                      "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (tf32 rate) / 3 (three TF32 MMAs per fp32-accurate product)"}
         if not args.no_cpu_baseline and world == 1:
             try:
                 base, why = cpu_baseline(w, eng)
