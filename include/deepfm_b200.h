@@ -48,7 +48,7 @@ enum { DFM_COL_HASH = 0, DFM_COL_BUCKETIZED = 1, DFM_COL_VOCAB = 2, DFM_COL_IDEN
 /* raw column dtypes — what tf.decode_csv yields (trainers/ml_100k.py:11-15,45) */
 enum { DFM_INT32 = 0, DFM_FLOAT32 = 1, DFM_STRING = 2 };
 /* optimizers — trainers/model_utils.py:57-66 */
-enum { DFM_OPT_ADAM = 0, DFM_OPT_ADAGRAD = 1, DFM_OPT_FTRL = 2, DFM_OPT_SGD = 3 };
+enum { DFM_OPT_ADAM = 0, DFM_OPT_ADAGRAD = 1, DFM_OPT_FTRL = 2, DFM_OPT_SGD = 3, DFM_OPT_RMSPROP = 4 };
 /* loss reduction — contrib binary head (mean, trainers/deep_fm.py:118) vs canned head (sum) */
 enum { DFM_LOSS_MEAN = 0, DFM_LOSS_SUM = 1 };
 
@@ -71,8 +71,8 @@ typedef struct {
 typedef struct {
     int32_t kind;       /* DFM_OPT_* */
     float   lr;
-    float   beta1, beta2, eps;   /* Adam: 0.9 0.999 1e-8 */
-    float   init_acc;            /* Adagrad / FTRL: 0.1 */
+    float   beta1, beta2, eps;   /* Adam: 0.9 0.999 1e-8.  RMSProp: beta1 = momentum (0), beta2 = decay (0.9), eps = 1e-10 */
+    float   init_acc;            /* Adagrad / FTRL accumulators: 0.1.  RMSProp rms slot: 1.0 */
 } dfm_optimizer;
 
 /* params of model_fn (trainers/deep_fm.py:13-26) + the column lists it receives */
@@ -115,7 +115,7 @@ const char* dfm_last_error(const dfm_handle* h);   /* h may be NULL: last dfm_cr
 /* Variable access = tf.train.Saver / checkpoint surface (trainers/conf_utils.py:6-10).
  * Names: "emb" [R,k], "lin" [R], "num_emb" [dn,k], "num_lin" [dn], "bias" [1], "W<i>" [in,out],
  * "b<i>" [out], "Wo" [h,1], "bo" [1]; optimizer slots "<name>/m", "<name>/v" (Adam),
- * "<name>/acc" (Adagrad, FTRL), "<name>/lin" (FTRL).  R = sum of the per-field bucket counts,
+ * "<name>/acc" (Adagrad, FTRL), "<name>/lin" (FTRL), "<name>/rms", "<name>/mom" (RMSProp).  R = sum of the per-field bucket counts,
  * fields concatenated in model order.  Row ranges are in elements of the leading dimension.
  * dfm_get_tensor materialises any deferred non-lazy-Adam work first (dfm_flush). */
 int dfm_tensor_rows(dfm_handle* h, const char* name, int64_t* rows, int64_t* row_elems);

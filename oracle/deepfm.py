@@ -32,6 +32,8 @@ def default_opt(name="Adam", lr=0.001):
         d.update(init_acc=0.1)
     elif name == "Ftrl":
         d.update(init_acc=0.1, lr_power=-0.5, l1=0.0, l2=0.0)
+    elif name == "RMSProp":   # tf.train.RMSPropOptimizer defaults (python/training/rmsprop.py)
+        d.update(beta1=0.0, beta2=0.9, eps=1e-10, init_acc=1.0)
     return d
 
 
@@ -78,6 +80,8 @@ class OracleDeepFM:
                 v.slots = {"acc": torch.full_like(v.w, o["init_acc"])}
             elif o["name"] == "Ftrl":
                 v.slots = {"acc": torch.full_like(v.w, o["init_acc"]), "lin": torch.zeros_like(v.w)}
+            elif o["name"] == "RMSProp":
+                v.slots = {"rms": torch.full_like(v.w, o["init_acc"]), "mom": torch.zeros_like(v.w)}
             elif o["name"] == "SGD":
                 v.slots = {}
             else:
@@ -221,6 +225,14 @@ class OracleDeepFM:
             lin[idx] = lin[idx] + gg - (new_acc.sqrt() - acc[idx].sqrt()) / lr * var.w[idx]
             var.w[idx] = -lin[idx] / (new_acc.sqrt() / lr)
             acc[idx] = new_acc
+        elif name == "RMSProp":   # core/kernels/training_ops.cc ApplyRMSProp / SparseApplyRMSProp (touched rows only)
+            rms, mom = var.slots["rms"], var.slots["mom"]
+            idx = uniq if sparse else slice(None)
+            gg = gsum if sparse else grad
+            omr = float(np.float32(1) - np.float32(o["beta2"])) if self.dt == torch.float32 else 1 - o["beta2"]
+            rms[idx] = rms[idx] + (gg * gg - rms[idx]) * omr
+            mom[idx] = mom[idx] * o["beta1"] + (gg * o["lr"]) / (rms[idx] + o["eps"]).sqrt()
+            var.w[idx] = var.w[idx] - mom[idx]
         elif name == "SGD":
             if sparse:
                 var.w[uniq] -= o["lr"] * gsum

@@ -14,7 +14,7 @@ MAX_CAT, MAX_NUM, MAX_HIDDEN = 64, 64, 8
 
 COL_KIND = {"hash": 0, "bucketized": 1, "vocab": 2, "identity": 3}
 DTYPE = {"int32": 0, "float32": 1, "string": 2}
-OPT_KIND = {"Adam": 0, "Adagrad": 1, "Ftrl": 2, "SGD": 3}
+OPT_KIND = {"Adam": 0, "Adagrad": 1, "Ftrl": 2, "SGD": 3, "RMSProp": 4}
 LOSS_RED = {"mean": 0, "sum": 1}
 
 

@@ -144,7 +144,7 @@ static const char* kPhases[dfm_handle::NPH] = {"transform", "sort", "segments", 
 static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 static inline float __int_as_float_host(int v) { float f; memcpy(&f, &v, 4); return f; }
 
-static int opt_slots(int kind) { return kind == DFM_OPT_ADAM ? 2 : kind == DFM_OPT_ADAGRAD ? 1 : kind == DFM_OPT_FTRL ? 2 : 0; }
+static int opt_slots(int kind) { return kind == DFM_OPT_ADAM ? 2 : kind == DFM_OPT_ADAGRAD ? 1 : kind == DFM_OPT_FTRL ? 2 : kind == DFM_OPT_RMSPROP ? 2 : 0; }
 
 static OptDev make_opt(const dfm_optimizer& o, float b1p, float b2p) {
     OptDev d{};
@@ -245,7 +245,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     h->loss_red = cfg->loss_reduction;
     h->od = cfg->opt_deep; h->ol = cfg->opt_linear;
     for (const dfm_optimizer* o : {&h->od, &h->ol})
-        if (o->kind < DFM_OPT_ADAM || o->kind > DFM_OPT_SGD) FAIL(DFM_ERR_INVALID_ARG, "unknown optimizer kind");
+        if (o->kind < DFM_OPT_ADAM || o->kind > DFM_OPT_RMSPROP) FAIL(DFM_ERR_INVALID_ARG, "unknown optimizer kind");
     h->max_batch = cfg->max_batch; h->device = cfg->device; h->rank = cfg->rank; h->world = std::max(1, cfg->world);
     CK(cudaSetDevice(h->device));
     cudaDeviceProp prop;
@@ -486,7 +486,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     CK(cudaFuncSetAttribute(numeric_grad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->rows_per_chunk * (DFM_MAX_NUM + 1) * 4));
 
     // optimizer slot initial values (Adagrad / FTRL accumulators start at init_acc)
-    auto init_acc = [&](const dfm_optimizer& o) { return (o.kind == DFM_OPT_ADAGRAD || o.kind == DFM_OPT_FTRL) ? o.init_acc : 0.f; };
+    auto init_acc = [&](const dfm_optimizer& o) { return (o.kind == DFM_OPT_ADAGRAD || o.kind == DFM_OPT_FTRL || o.kind == DFM_OPT_RMSPROP) ? o.init_acc : 0.f; };
     if (init_acc(h->od) != 0.f) {
         if (h->need_emb && R)
             fill_strided_kernel<<<cdiv((int64_t)R * K, 256), 256, 0, h->stream>>>(h->emb_rec + K, R, K, h->emb_stride, init_acc(h->od));
@@ -531,6 +531,7 @@ static bool resolve(dfm_handle* h, const std::string& full, TensorRef& t) {
         if (kind == DFM_OPT_ADAM) return slot == "m" ? 1 : slot == "v" ? 2 : -1;
         if (kind == DFM_OPT_ADAGRAD) return slot == "acc" ? 1 : -1;
         if (kind == DFM_OPT_FTRL) return slot == "acc" ? 1 : slot == "lin" ? 2 : -1;
+        if (kind == DFM_OPT_RMSPROP) return slot == "rms" ? 1 : slot == "mom" ? 2 : -1;
         return -1;
     };
     if (name == "emb") {

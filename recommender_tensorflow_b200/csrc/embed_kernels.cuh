@@ -35,6 +35,10 @@ __device__ __forceinline__ void other_apply(float& w, float& s1, float& s2, floa
         s2 = __fsub_rn(t1, t2);
         w = __fdiv_rn(-s2, __fdiv_rn(sna, o.lr));
         s1 = na;
+    } else if (o.kind == DFM_OPT_RMSPROP) {   // training_ops.cc ApplyRMSProp: s1 = ms, s2 = mom, b2 = rho, b1 = momentum
+        s1 = __fadd_rn(s1, __fmul_rn(__fsub_rn(__fmul_rn(g, g), s1), __fsub_rn(1.0f, o.b2)));
+        s2 = __fadd_rn(__fmul_rn(s2, o.b1), __fdiv_rn(__fmul_rn(g, o.lr), __fsqrt_rn(__fadd_rn(s1, o.eps))));
+        w = __fsub_rn(w, s2);
     } else {  // SGD
         w = __fsub_rn(w, __fmul_rn(o.lr, g));
     }

@@ -18,6 +18,8 @@ def default_optimizer(name="Adam", learning_rate=0.001):
     """Hyper-parameters of tf.train.<name>Optimizer(learning_rate) (trainers/model_utils.py:57-66)."""
     if name not in _lib.OPT_KIND:
         raise KeyError(name)   # same failure mode as optimizer_classes[optimizer_name]
+    if name == "RMSProp":   # tf.train.RMSPropOptimizer defaults: decay 0.9, momentum 0, epsilon 1e-10, rms slot = ones
+        return dict(name=name, lr=float(learning_rate), beta1=0.0, beta2=0.9, eps=1e-10, init_acc=1.0)
     return dict(name=name, lr=float(learning_rate), beta1=0.9, beta2=0.999, eps=1e-8, init_acc=0.1)
 
 
@@ -164,7 +166,7 @@ class DeepFMEngine:
 
     def slot_names(self, var):
         grp = self.opt_linear if var in ("lin", "num_lin", "bias") else self.opt_deep
-        return {"Adam": ["m", "v"], "Adagrad": ["acc"], "Ftrl": ["acc", "lin"], "SGD": []}[grp["name"]]
+        return {"Adam": ["m", "v"], "Adagrad": ["acc"], "Ftrl": ["acc", "lin"], "SGD": [], "RMSProp": ["rms", "mom"]}[grp["name"]]
 
     def set_tensor(self, name, value, row_begin=0):
         value = np.ascontiguousarray(value, dtype=np.float32)
@@ -224,7 +226,8 @@ class DeepFMEngine:
             m["%slogits%s/bias" % (pre, mid)] = ("bo", 0, 1, (1,))
         return m
 
-    _SLOT_TF = {"m": "Adam", "v": "Adam_1", "acc": {"Adagrad": "Adagrad", "Ftrl": "accum"}, "lin": "linear"}
+    _SLOT_TF = {"m": "Adam", "v": "Adam_1", "acc": {"Adagrad": "Adagrad", "Ftrl": "accum"}, "lin": "linear",
+                "rms": "RMSProp", "mom": "RMSProp_1"}
 
     def save_checkpoint(self, path, scheme="deep_fm"):
         """Variables + optimizer slots + global_step under TF-1.12 names, as one .npz (flushes deferred Adam)."""

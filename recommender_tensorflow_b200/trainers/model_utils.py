@@ -5,8 +5,8 @@ from ..engine import default_optimizer
 
 
 def get_optimizer(optimizer_name="Adam", learning_rate=0.001):
-    """trainers/model_utils.py:57-66 — Adagrad | Adam | Ftrl | SGD with `learning_rate` only
-    (RMSProp is not built yet: KeyError, like an unknown name in the reference)."""
+    """trainers/model_utils.py:57-66 — Adagrad | Adam | Ftrl | RMSProp | SGD with `learning_rate` only
+    (an unknown name raises KeyError, like optimizer_classes[optimizer_name] in the reference)."""
     return default_optimizer(optimizer_name, learning_rate)
 
 

@@ -123,6 +123,17 @@ def test_deepfm_tensor_core_tower(hidden, batch):
     _run_steps(eng, ora, [ml.batch(batch, rng) for _ in range(3)], "tc-tower%r" % (hidden,))
 
 
+@pytest.mark.parametrize("name", ["RMSProp", "SGD", "Adagrad", "Ftrl"])
+def test_other_optimizers_of_get_optimizer(name):
+    """trainers/model_utils.py:57-66: every optimizer name the reference accepts."""
+    from recommender_tensorflow_b200.trainers.model_utils import get_optimizer
+    opt = get_optimizer(name, 0.01)
+    eng = _ml_engine(opt_deep=opt, opt_linear=dict(opt), max_batch=512)
+    ora, _ = make_pair(eng, seed=40)
+    ml, rng = synth.ML100K(), np.random.default_rng(41)
+    _run_steps(eng, ora, [ml.batch(300, rng) for _ in range(4)], "opt-" + name)
+
+
 def test_wide_deep_cfg2():
     """configs[1]: wide&deep = no FM, SUM loss, Adagrad (dnn side) + FTRL (linear side)."""
     eng = _ml_engine(use_mf=False, loss_reduction="sum", opt_deep=default_optimizer("Adagrad", 0.001),

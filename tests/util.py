@@ -16,7 +16,7 @@ def oracle_cfg(engine, **over):
     def o(d):
         r = default_opt(d["name"], d["lr"])
         for k in ("beta1", "beta2", "eps", "init_acc"):
-            if k in r and k in d:
+            if k in d and (k in r or d["name"] == "RMSProp"):
                 r[k] = d[k]
         return r
     cfg = dict(cat=[dict(s) for s in engine.specs], num=[c.key for c in engine.num_columns], k=engine.k,
