@@ -92,6 +92,11 @@ typedef struct {
     /* row sharding: this handle owns global rows {g : g mod world == rank} */
     int32_t           rank, world;
     void*             nccl_comm;      /* reserved (the host owns the communicator); pass NULL */
+    /* tf.layers.dropout(net, rate=dropout, training=True) after every hidden layer in TRAIN mode
+     * (trainers/deep_fm.py:102-103).  Own counter-based generator keyed on (seed, step, layer, element);
+     * TF's RNG stream is not reproducible, the oracle restates this one. */
+    float             dropout;
+    uint64_t          dropout_seed;
 } dfm_config;
 
 /* One batch of raw (un-hashed) feature columns = what input_fn's parse_csv yields

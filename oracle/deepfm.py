@@ -37,6 +37,27 @@ def default_opt(name="Adam", lr=0.001):
     return d
 
 
+def _mix64(x):
+    """splitmix64 finaliser on uint64 arrays (the product's dropout generator, mlp_kernels.cuh::dfm_mix64)."""
+    x = np.asarray(x, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+def dropout_mask(seed, step, layer, rows, width, keep):
+    """keep ? 1/keep : 0 for every element (row-major index) of a [rows, width] activation.  Restates
+    tf.layers.dropout(net, rate, training=True) (trainers/deep_fm.py:102-103) with the product's own
+    counter-based generator - TF's stream is not reproducible."""
+    with np.errstate(over="ignore"):
+        key = _mix64(_mix64(np.uint64(seed)) ^ np.uint64(step * 64 + layer))
+        idx = np.arange(rows * width, dtype=np.uint64)
+        u = (_mix64(key ^ idx) >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return np.where(u < np.float32(keep), np.float32(1.0 / np.float32(keep)), np.float32(0)).reshape(rows, width)
+
+
 class Var:
     def __init__(self, value, group):
         self.w = value
@@ -58,6 +79,8 @@ class OracleDeepFM:
         self.use_mf = bool(cfg.get("use_mf", True))
         self.use_dnn = bool(cfg.get("use_dnn", True))
         self.red = cfg.get("loss_reduction", "mean")
+        self.dropout = float(cfg.get("dropout", 0.0))
+        self.dropout_seed = int(cfg.get("dropout_seed", 0))
         self.opt = {"deep": cfg.get("opt_deep", default_opt()),
                     "linear": cfg.get("opt_linear", default_opt())}
         self.nb = [num_buckets(s) for s in self.cat]
@@ -95,7 +118,7 @@ class OracleDeepFM:
         rows = ids.clamp(min=0) + torch.as_tensor(self.off[:-1])[None, :]
         return rows, valid
 
-    def forward(self, ids, x=None, keep=False):
+    def forward(self, ids, x=None, keep=False, train=False):
         W = {n: v.w for n, v in self.vars.items()}
         rows, valid = self.rows(ids)
         B = rows.shape[0]
@@ -123,6 +146,10 @@ class OracleDeepFM:
             acts = [h]
             for i in range(len(self.hidden)):
                 h = torch.relu(h @ W["W%d" % i] + W["b%d" % i])
+                if train and self.dropout > 0:
+                    keepp = np.float32(1.0) - np.float32(self.dropout)
+                    mk = dropout_mask(self.dropout_seed, self.t + 1, i, B, h.shape[1], keepp)
+                    h = h * torch.as_tensor(mk, dtype=dt)
                 acts.append(h)
             z = z + (h @ W["Wo"])[:, 0] + W["bo"][0]
             cache["acts"] = acts
@@ -134,7 +161,7 @@ class OracleDeepFM:
 
     # ---------------------------------------------------------------- backward
     def grads(self, ids, x, y):
-        z, c = self.forward(ids, x, keep=True)
+        z, c = self.forward(ids, x, keep=True, train=True)
         y = torch.as_tensor(np.asarray(y), dtype=self.dt)
         B = z.shape[0]
         lv = self.loss_vec(z, y)
@@ -162,8 +189,10 @@ class OracleDeepFM:
                 dh = dz[:, None] * W["Wo"][:, 0][None, :]
                 g["Wo"] = acts[L].t() @ dz[:, None]
                 g["bo"] = dz.sum().reshape(1)
+                dscale = 1.0 / float(np.float32(1.0) - np.float32(self.dropout)) if self.dropout > 0 else 1.0
                 for i in reversed(range(L)):
-                    dh = dh * (acts[i + 1] > 0).to(self.dt)
+                    # acts[i+1] is post-dropout: > 0 means ReLU active AND kept; kept elements carry 1/keep
+                    dh = dh * (acts[i + 1] > 0).to(self.dt) * dscale
                     g["W%d" % i] = acts[i].t() @ dh
                     g["b%d" % i] = dh.sum(0)
                     dh = dh @ W["W%d" % i].t()

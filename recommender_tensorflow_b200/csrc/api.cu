@@ -63,6 +63,7 @@ struct dfm_handle {
     int use_linear = 1, use_mf = 1, use_dnn = 1, need_emb = 1, loss_red = 0;
     dfm_optimizer od{}, ol{};
     int max_batch = 0, device = 0, rank = 0, world = 1;
+    float dropout = 0.f; uint64_t dropout_seed = 0;
     std::vector<ColDev> cols;
     std::vector<std::string> col_names;
     std::vector<uint32_t> row_off;   // [dc+1]
@@ -247,6 +248,8 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     for (const dfm_optimizer* o : {&h->od, &h->ol})
         if (o->kind < DFM_OPT_ADAM || o->kind > DFM_OPT_RMSPROP) FAIL(DFM_ERR_INVALID_ARG, "unknown optimizer kind");
     h->max_batch = cfg->max_batch; h->device = cfg->device; h->rank = cfg->rank; h->world = std::max(1, cfg->world);
+    if (!(cfg->dropout >= 0.f && cfg->dropout < 1.f)) FAIL(DFM_ERR_INVALID_ARG, "dropout must be in [0, 1)");
+    h->dropout = cfg->dropout; h->dropout_seed = cfg->dropout_seed;
     CK(cudaSetDevice(h->device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
@@ -744,6 +747,14 @@ static int flush_impl(dfm_handle* h, cudaStream_t st) {
     return DFM_OK;
 }
 
+static void set_dropout(const dfm_handle* h, EpiArgs& ep, bool train, int layer) {
+    if (train && h->dropout > 0.f) {
+        ep.drop_keep = 1.f - h->dropout; ep.drop_inv = 1.f / (1.f - h->dropout);
+        ep.drop_key = dfm_drop_key(h->dropout_seed, (uint64_t)(h->step + 1), (uint64_t)layer);
+        ep.drop_row0 = (int64_t)h->rank * h->max_batch;
+    }
+}
+
 template <int K>
 static int forward_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t st, const float* labels, float scale,
                         float* logits_out, Phase* ph, const float* rowbuf = nullptr) {
@@ -756,7 +767,12 @@ static int forward_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t 
         const float* za = (h->use_linear || h->use_mf) ? h->zacc : nullptr;
         const int train = labels ? 1 : 0;
         const int grid = std::min((B + SM_TB - 1) / SM_TB, h->small_grid);
-#define SMALL_FWD(HH) small_mlp_fwd_bwd_top_kernel<HH><<<grid, 256, h->small_smem, st>>>(h->sm, h->dw, h->h0, za, labels, B, scale, train, \
+        SmallMlpDesc smd = h->sm;
+        if (train && h->dropout > 0.f) {
+            smd.drop_keep = 1.f - h->dropout; smd.drop_inv = 1.f / (1.f - h->dropout);
+            smd.drop_seed = h->dropout_seed; smd.drop_step = (uint64_t)(h->step + 1); smd.drop_row0 = (int64_t)h->rank * h->max_batch;
+        }
+#define SMALL_FWD(HH) small_mlp_fwd_bwd_top_kernel<HH><<<grid, 256, h->small_smem, st>>>(smd, h->dw, h->h0, za, labels, B, scale, train, \
             h->logits, logits_out, h->dz, h->dact[1], h->up_partial, h->head_part)
         if (h->sm.H[0] == 8) SMALL_FWD(8); else if (h->sm.H[0] == 16) SMALL_FWD(16); else SMALL_FWD(32);
 #undef SMALL_FWD
@@ -777,6 +793,7 @@ static int forward_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t 
             tc::split_tf32_transpose_kernel<<<dim3(cdiv(out, 32), cdiv(in, 32)), dim3(32, 8), 0, st>>>(h->dw + W->off, in, out, wt, nullptr);
             h->launches += 1;
             EpiArgs ep{}; ep.bias = h->dw + b->off;
+            set_dropout(h, ep, labels != nullptr, i);
             int rc = tc_gemm_kmajor(h, h->act[i], nullptr, in, wt, nullptr, in, h->act[i + 1], out, B, out, in, EPI_BIAS_RELU, ep, st);
             if (rc) return rc;
             in = out;
@@ -788,6 +805,7 @@ static int forward_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t 
             const DenseT* W = find_dense(h, "W" + std::to_string(i));
             const DenseT* b = find_dense(h, "b" + std::to_string(i));
             EpiArgs ep{}; ep.bias = h->dw + b->off;
+            set_dropout(h, ep, labels != nullptr, i);
             launch_sgemm<true, false, EPI_BIAS_RELU>(h, h->act[i], in, h->dw + W->off, h->hidden[i], h->act[i + 1], h->hidden[i], B,
                                                      h->hidden[i], in, 1, (in + 15) / 16 * 16, ep, st);
             in = h->hidden[i];
@@ -799,7 +817,7 @@ static int forward_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t 
     if (h->fused_head && labels) {
         const int grid = std::min(h->fused_head_blocks, (B + 7) / 8);
 #define HEAD_BWD(NHH) head_bwd_kernel<NHH><<<grid, 256, 0, st>>>(za, hL, h->dw + Wo->off, h->dw + bo->off, labels, B, scale, h->logits, logits_out, \
-                                                             h->dz, h->dact[h->L], h->head_part, h->head_gpart)
+                                                             h->dz, h->dact[h->L], h->head_part, h->head_gpart, h->dropout > 0.f ? 1.f / (1.f - h->dropout) : 1.f)
         switch (H / 32) {
             case 1: HEAD_BWD(1); break; case 2: HEAD_BWD(2); break; case 3: HEAD_BWD(3); break; case 4: HEAD_BWD(4); break;
             case 5: HEAD_BWD(5); break; case 6: HEAD_BWD(6); break; case 7: HEAD_BWD(7); break; default: HEAD_BWD(8); break;
@@ -875,7 +893,7 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
             launch_colsum(h, hL, H, h->dz, B, H, h->dg + Wo->off, st);   // gWo = h_L^T dz
         }
         if (L == 0) {
-            dh_last_kernel<<<cdiv((int64_t)B * H, 256), 256, 0, st>>>(nullptr, h->dw + Wo->off, h->dz, (int64_t)B * H, H, h->dE);
+            dh_last_kernel<<<cdiv((int64_t)B * H, 256), 256, 0, st>>>(nullptr, h->dw + Wo->off, h->dz, (int64_t)B * H, H, h->dE, 1.f);
             h->launches++;
             if (h->use_mf) {
                 de_fm_kernel<<<cdiv((int64_t)B * dK, 256), 256, 0, st>>>(h->h0, h->s, h->dz, (int64_t)B * dK, dK, K, h->dE, 1);
@@ -883,7 +901,8 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
             }
         } else {
             if (!h->fused_head) {
-                dh_last_kernel<<<cdiv((int64_t)B * H, 256), 256, 0, st>>>(hL, h->dw + Wo->off, h->dz, (int64_t)B * H, H, h->dact[L]);
+                dh_last_kernel<<<cdiv((int64_t)B * H, 256), 256, 0, st>>>(hL, h->dw + Wo->off, h->dz, (int64_t)B * H, H, h->dact[L],
+                                                                          h->dropout > 0.f ? 1.f / (1.f - h->dropout) : 1.f);
                 h->launches++;
             }
             const int splits = std::max(1, std::min(h->splits, (B + 1023) / 1024));
@@ -914,6 +933,7 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
                     int rc2;
                     if (i > 0) {
                         ep.act = h->act[i]; ep.ld_act = in;
+                        ep.bwd_scale = h->dropout > 0.f ? 1.f / (1.f - h->dropout) : 0.f;
                         rc2 = tc_gemm_kmajor(h, h->dact[i + 1], nullptr, out, w_hi, w_lo, out, h->dact[i], in, B, in, out, EPI_MASK, ep, st);
                     } else {
                         ep.act = h->h0; ep.ld_act = dK; ep.dz = h->dz; ep.s = h->use_mf ? h->s : nullptr; ep.K = K;
@@ -922,6 +942,7 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
                     if (rc2) return rc2;
                 } else if (i > 0) {
                     EpiArgs ep{}; ep.act = h->act[i]; ep.ld_act = in;
+                    ep.bwd_scale = h->dropout > 0.f ? 1.f / (1.f - h->dropout) : 0.f;
                     launch_sgemm<true, true, EPI_MASK>(h, h->dact[i + 1], out, h->dw + W->off, out, h->dact[i], in, B, in, out, 1,
                                                        (out + 15) / 16 * 16, ep, st);
                 } else {

@@ -8,7 +8,27 @@
 
 enum { EPI_NONE = 0, EPI_BIAS_RELU = 1, EPI_MASK = 2, EPI_DE = 3 };
 
+// dropout mask of element idx of one layer at one step: keep ? 1/keep : 0   (counter-based, restated by the oracle)
+__host__ __device__ __forceinline__ uint64_t dfm_mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t dfm_drop_key(uint64_t seed, uint64_t step, uint64_t layer) {
+    return dfm_mix64(dfm_mix64(seed) ^ (step * 64 + layer));
+}
+__device__ __forceinline__ float dfm_drop(uint64_t key, uint64_t idx, float keep, float inv_keep) {
+    const float u = (float)(dfm_mix64(key ^ idx) >> 40) * (1.0f / 16777216.0f);
+    return u < keep ? inv_keep : 0.f;
+}
+
 struct EpiArgs {
+    float    drop_keep;  // EPI_BIAS_RELU: > 0 -> dropout after the activation (keep probability)
+    float    drop_inv;   //                1 / keep
+    uint64_t drop_key;
+    int64_t  drop_row0;  // global index of row 0 (sample offset of this rank)
+    float    bwd_scale;  // EPI_MASK: gradient scale of the dropout in front (1 / keep), 0 = none
     const float* bias;   // EPI_BIAS_RELU: [N]
     const float* act;    // EPI_MASK: forward activation [M, ld_act]; EPI_DE: h0 [M, ld_act]
     int          ld_act;
@@ -176,8 +196,10 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
                 int n = gn + c;
                 if (n >= N) continue;
                 float x = v[c];
-                if (EPI == EPI_BIAS_RELU) x = fmaxf(x + ep.bias[n], 0.f);
-                else if (EPI == EPI_MASK) x = ep.act[(size_t)gm * ep.ld_act + n] > 0.f ? x : 0.f;
+                if (EPI == EPI_BIAS_RELU) {
+                    x = fmaxf(x + ep.bias[n], 0.f);
+                    if (ep.drop_keep > 0.f) x *= dfm_drop(ep.drop_key, (uint64_t)(ep.drop_row0 + gm) * N + n, ep.drop_keep, ep.drop_inv);
+                } else if (EPI == EPI_MASK) x = ep.act[(size_t)gm * ep.ld_act + n] > 0.f ? (ep.bwd_scale > 0.f ? x * ep.bwd_scale : x) : 0.f;
                 else if (EPI == EPI_DE) {
                     if (ep.s) x += dzm * (ep.s[(size_t)gm * ep.K + (n % ep.K)] - ep.act[(size_t)gm * ep.ld_act + n]);
                 }
@@ -317,7 +339,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ labels, int B, float scale,
                                                        float* __restrict__ logits, float* __restrict__ logits_out,
                                                        float* __restrict__ dz, float* __restrict__ dh,
-                                                       float* __restrict__ part /*[grid][2]*/, float* __restrict__ gpart) {
+                                                       float* __restrict__ part /*[grid][2]*/, float* __restrict__ gpart,
+                                                       float drop_scale /* 1/keep of the dropout after h_L, or 1 */) {
     constexpr int H = 32 * NH;
     __shared__ float sl[8], sd[8];
     __shared__ float sg[8][2 * H];
@@ -347,7 +370,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
         }
 #pragma unroll
         for (int i = 0; i < NH; ++i) {
-            const float d = h[i] > 0.f ? g * wo[i] : 0.f;
+            const float d = h[i] > 0.f ? g * wo[i] * drop_scale : 0.f;
             dh[(size_t)b * H + lane + 32 * i] = d;
             gw[i] = fmaf(h[i], g, gw[i]);
             gb[i] += d;
@@ -392,12 +415,12 @@ __global__ void head_final_kernel(const float* __restrict__ part, int nblocks, f
 
 // dh_L'[b,j] = dz[b] * Wo[j] * (h_L[b,j] > 0)
 __global__ void dh_last_kernel(const float* __restrict__ hL, const float* __restrict__ Wo, const float* __restrict__ dz,
-                               int64_t total, int H, float* __restrict__ dh) {
+                               int64_t total, int H, float* __restrict__ dh, float drop_scale) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < total) {
         int64_t b = i / H;
         int j = (int)(i - b * H);
-        dh[i] = (!hL || hL[i] > 0.f) ? dz[b] * Wo[j] : 0.f;   // hL == nullptr: no ReLU in front (hidden_units == [])
+        dh[i] = !hL ? dz[b] * Wo[j] : (hL[i] > 0.f ? dz[b] * Wo[j] * drop_scale : 0.f);   // hL == nullptr: no ReLU in front (hidden_units == [])
     }
 }
 

@@ -12,6 +12,7 @@
 // Partials are reduced in a fixed order afterwards (deterministic).
 #pragma once
 #include "dfm_types.cuh"
+#include "mlp_kernels.cuh"
 
 constexpr int SM_TB = 128;        // samples per tile
 constexpr int SM_DC = 32;         // input-layer columns per staged chunk (forward)
@@ -26,6 +27,9 @@ struct SmallMlpDesc {
     int off_W[SM_MAXL], off_b[SM_MAXL], off_Wo, off_bo;   // offsets in the packed dense buffer
     int up_begin, up_count;       // [b0 .. bo] range (everything above W0) in the packed buffer
     int act_stride;               // floats per sample row in the per-sample scratch (odd)
+    float drop_keep, drop_inv;    // dropout after every hidden layer (keep probability, 1/keep); keep == 0 -> off
+    uint64_t drop_seed, drop_step;
+    int64_t drop_row0;
 };
 
 static inline size_t small_mlp_fwd_smem(const SmallMlpDesc& m) {
@@ -115,6 +119,12 @@ __global__ void __launch_bounds__(256, 2) small_mlp_fwd_bwd_top_kernel(
             const float* bb = UP(m.off_b[0]);
 #pragma unroll
             for (int j = 0; j < HJ; ++j) arow[j0 + j] = fmaxf(acc[j] + bb[j0 + j], 0.f);
+            if (train && m.drop_keep > 0.f) {
+                const uint64_t key = dfm_drop_key(m.drop_seed, m.drop_step, 0);
+#pragma unroll
+                for (int j = 0; j < HJ; ++j)
+                    arow[j0 + j] *= dfm_drop(key, (uint64_t)(m.drop_row0 + b) * H1 + j0 + j, m.drop_keep, m.drop_inv);
+            }
         }
         __syncthreads();
         // ---- upper layers, head and their backward: one thread per sample
@@ -127,7 +137,10 @@ __global__ void __launch_bounds__(256, 2) small_mlp_fwd_bwd_top_kernel(
                 for (int o = 0; o < Hout; ++o) {
                     float a = bb[o];
                     for (int j = 0; j < Hin; ++j) a = fmaf(arow[aoff + j], W[j * Hout + o], a);
-                    arow[aoff + Hin + o] = fmaxf(a, 0.f);
+                    a = fmaxf(a, 0.f);
+                    if (train && m.drop_keep > 0.f)
+                        a *= dfm_drop(dfm_drop_key(m.drop_seed, m.drop_step, l), (uint64_t)(m.drop_row0 + b) * Hout + o, m.drop_keep, m.drop_inv);
+                    arow[aoff + Hin + o] = a;
                 }
                 aoff += Hin;
             }
@@ -151,7 +164,8 @@ __global__ void __launch_bounds__(256, 2) small_mlp_fwd_bwd_top_kernel(
             red[s] = lterm;
             if (train) {
                 // dh_L' = dz * Wo * relu'(h_L); walk down to dh_1'
-                for (int j = 0; j < HL; ++j) drow[aoff + j] = arow[aoff + j] > 0.f ? g * Wo[j] : 0.f;
+                const float dsc = m.drop_keep > 0.f ? m.drop_inv : 1.f;   // gradient through the dropout after each ReLU
+                for (int j = 0; j < HL; ++j) drow[aoff + j] = arow[aoff + j] > 0.f ? g * Wo[j] * dsc : 0.f;
                 for (int l = m.L - 1; l >= 1; --l) {
                     const int Hin = m.H[l - 1], Hout = m.H[l];
                     const float* W = UP(m.off_W[l]);
@@ -159,7 +173,7 @@ __global__ void __launch_bounds__(256, 2) small_mlp_fwd_bwd_top_kernel(
                     for (int j = 0; j < Hin; ++j) {
                         float a = 0.f;
                         for (int o = 0; o < Hout; ++o) a = fmaf(drow[aoff + o], W[j * Hout + o], a);
-                        drow[in_off + j] = arow[in_off + j] > 0.f ? a : 0.f;
+                        drow[in_off + j] = arow[in_off + j] > 0.f ? a * dsc : 0.f;
                     }
                     aoff = in_off;
                 }

@@ -337,9 +337,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
                 if (p.epi == EPI_BIAS_RELU) {
                     x.x = fmaxf(x.x + bias4.x, 0.f); x.y = fmaxf(x.y + bias4.y, 0.f);
                     x.z = fmaxf(x.z + bias4.z, 0.f); x.w = fmaxf(x.w + bias4.w, 0.f);
+                    if (p.ep.drop_keep > 0.f) {
+                        const uint64_t e0 = (uint64_t)(p.ep.drop_row0 + gm) * p.N + n;
+                        x.x *= dfm_drop(p.ep.drop_key, e0, p.ep.drop_keep, p.ep.drop_inv);
+                        x.y *= dfm_drop(p.ep.drop_key, e0 + 1, p.ep.drop_keep, p.ep.drop_inv);
+                        x.z *= dfm_drop(p.ep.drop_key, e0 + 2, p.ep.drop_keep, p.ep.drop_inv);
+                        x.w *= dfm_drop(p.ep.drop_key, e0 + 3, p.ep.drop_keep, p.ep.drop_inv);
+                    }
                 } else if (p.epi == EPI_MASK) {
-                    x.x = xa[it].x > 0.f ? x.x : 0.f; x.y = xa[it].y > 0.f ? x.y : 0.f;
-                    x.z = xa[it].z > 0.f ? x.z : 0.f; x.w = xa[it].w > 0.f ? x.w : 0.f;
+                    const float sc = p.ep.bwd_scale > 0.f ? p.ep.bwd_scale : 1.f;
+                    x.x = xa[it].x > 0.f ? x.x * sc : 0.f; x.y = xa[it].y > 0.f ? x.y * sc : 0.f;
+                    x.z = xa[it].z > 0.f ? x.z * sc : 0.f; x.w = xa[it].w > 0.f ? x.w * sc : 0.f;
                 } else if (p.epi == EPI_DE && p.ep.s) {
                     x.x += xd[it] * (xs[it].x - xa[it].x); x.y += xd[it] * (xs[it].y - xa[it].y);
                     x.z += xd[it] * (xs[it].z - xa[it].z); x.w += xd[it] * (xs[it].w - xa[it].w);

@@ -44,7 +44,7 @@ class PackedBatch:
 class DeepFMEngine:
     def __init__(self, categorical_columns, numeric_columns=(), embedding_size=4, hidden_units=(16, 16),
                  use_linear=True, use_mf=True, use_dnn=True, loss_reduction="mean", opt_deep=None,
-                 opt_linear=None, max_batch=65536, device=0, feature_dtypes=None, sort_columns=True, rank=0, world=1):
+                 opt_linear=None, max_batch=65536, device=0, feature_dtypes=None, sort_columns=True, rank=0, world=1, dropout=0.0, dropout_seed=0):
         self.lib = _lib.load()
         cats = list(categorical_columns)
         nums = list(numeric_columns)
@@ -60,6 +60,7 @@ class DeepFMEngine:
         self.opt_linear = opt_linear or default_optimizer()
         self.max_batch, self.device = int(max_batch), int(device)
         self.rank, self.world = int(rank), int(world)
+        self.dropout, self.dropout_seed = float(dropout or 0.0), int(dropout_seed)
         fd = dict(feature_dtypes or {})
         self.specs = []
         for c in cats:
@@ -92,7 +93,7 @@ class DeepFMEngine:
         cfg = _lib.Config(len(cats), C.cast(cols, C.POINTER(_lib.Column)), len(nums), self.k, len(self.hidden),
                           C.cast(hid, C.POINTER(C.c_int32)), int(self.use_linear), int(self.use_mf), int(self.use_dnn),
                           _lib.LOSS_RED[loss_reduction], _opt_struct(self.opt_deep), _opt_struct(self.opt_linear),
-                          self.max_batch, self.device, self.rank, self.world, None)
+                          self.max_batch, self.device, self.rank, self.world, None, self.dropout, self.dropout_seed)
         self._keep += [cols, hid]
         handle = C.c_void_p()
         rc = self.lib.dfm_create(C.byref(cfg), C.byref(handle))

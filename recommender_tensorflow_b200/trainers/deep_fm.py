@@ -40,14 +40,12 @@ def _build_engine(params, batch_size):
         raise ValueError("At least 1 of linear, mf or dnn component must be used.")
     if activation_fn not in ("relu", None) and getattr(activation_fn, "__name__", "") != "relu":
         raise NotImplementedError("only the reference default activation (ReLU) is built")
-    if dropout and dropout > 0:
-        raise NotImplementedError("dropout > 0 is not built yet (TF's dropout RNG stream is not reproducible; "
-                                  "parity runs use dropout = 0)")
     opt = get_optimizer(optimizer, learning_rate)
     return DeepFMEngine(categorical_columns, numeric_columns, embedding_size=embedding_size, hidden_units=hidden_units,
                         use_linear=bool(use_linear), use_mf=bool(use_mf), use_dnn=bool(use_dnn), loss_reduction="mean",
                         opt_deep=opt, opt_linear=dict(opt), max_batch=params.get("max_batch", max(batch_size, 1)),
-                        device=params.get("device", 0), feature_dtypes=params.get("feature_dtypes", FEATURE_DTYPES))
+                        device=params.get("device", 0), feature_dtypes=params.get("feature_dtypes", FEATURE_DTYPES),
+                        dropout=float(dropout or 0.0), dropout_seed=int(params.get("dropout_seed", 0)))
 
 
 def _batch_size(features):
@@ -182,8 +180,7 @@ if __name__ == "__main__":
     parser.add_argument("--exclude-dnn", action="store_true")
     parser.add_argument("--embedding-size", type=int, default=4)
     parser.add_argument("--hidden-units", type=int, nargs="+", default=[16, 16])
-    parser.add_argument("--dropout", type=float, default=0.0,
-                        help="the reference defaults to 0.1; dropout is not built yet")
+    parser.add_argument("--dropout", type=float, default=0.1, help="dropout rate (default: %(default)s)")
     parser.add_argument("--batch-size", type=int, default=32)
     parser.add_argument("--train-steps", type=int, default=20000)
     train_and_evaluate(parser.parse_args())

@@ -21,8 +21,6 @@ class DNNLinearCombinedClassifier:
         dnn_feature_columns = list(dnn_feature_columns or [])
         if not linear_feature_columns and not dnn_feature_columns:
             raise ValueError("Either linear_feature_columns or dnn_feature_columns must be defined.")
-        if dnn_dropout:
-            raise NotImplementedError("dnn_dropout > 0 is not built yet (parity runs use dropout = 0)")
         cats = [c.categorical_column for c in dnn_feature_columns] or linear_feature_columns
         if linear_feature_columns and dnn_feature_columns and [c.name for c in cats] != [c.name for c in linear_feature_columns]:
             raise NotImplementedError("linear and dnn sides must be built on the same categorical columns "
@@ -36,6 +34,7 @@ class DNNLinearCombinedClassifier:
                                    use_mf=False, use_dnn=bool(dnn_feature_columns), loss_reduction="sum",
                                    opt_deep=default_optimizer("Adagrad", _DNN_LEARNING_RATE),
                                    opt_linear=default_optimizer("Ftrl", lin_lr), max_batch=max_batch, device=device,
+                                   dropout=float(dnn_dropout or 0.0),
                                    feature_dtypes=feature_dtypes)
         self.model_dir = model_dir
 

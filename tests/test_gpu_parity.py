@@ -134,6 +134,20 @@ def test_other_optimizers_of_get_optimizer(name):
     _run_steps(eng, ora, [ml.batch(300, rng) for _ in range(4)], "opt-" + name)
 
 
+@pytest.mark.parametrize("hidden", [(16, 16), (64, 32), (20, 12)])
+def test_dropout_all_tower_paths(hidden):
+    """trainers/deep_fm.py:102-103 dropout after every hidden layer (reference CLI default 0.1): fused small-MLP,
+    tcgen05 and SGEMM towers against the oracle's restatement of the same counter-based mask."""
+    eng = _ml_engine(k=16, hidden=hidden, max_batch=1024, dropout=0.3, dropout_seed=77)
+    ora, _ = make_pair(eng, seed=50)
+    ml, rng = synth.ML100K(), np.random.default_rng(51)
+    _run_steps(eng, ora, [ml.batch(1024, rng) for _ in range(3)], "dropout%r" % (hidden,))
+    feats, _ = ml.batch(64, rng)                       # EVAL / PREDICT: no dropout
+    z = eng.predict_logits(feats)
+    ref = ora.forward(transforms.transform(eng.specs, feats)).numpy()
+    assert np.allclose(z, ref, rtol=1e-5, atol=2e-6)
+
+
 def test_wide_deep_cfg2():
     """configs[1]: wide&deep = no FM, SUM loss, Adagrad (dnn side) + FTRL (linear side)."""
     eng = _ml_engine(use_mf=False, loss_reduction="sum", opt_deep=default_optimizer("Adagrad", 0.001),

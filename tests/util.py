@@ -22,7 +22,8 @@ def oracle_cfg(engine, **over):
     cfg = dict(cat=[dict(s) for s in engine.specs], num=[c.key for c in engine.num_columns], k=engine.k,
                hidden=list(engine.hidden), use_linear=engine.use_linear, use_mf=engine.use_mf,
                use_dnn=engine.use_dnn, loss_reduction=engine.loss_reduction, opt_deep=o(engine.opt_deep),
-               opt_linear=o(engine.opt_linear))
+               opt_linear=o(engine.opt_linear), dropout=getattr(engine, "dropout", 0.0),
+               dropout_seed=getattr(engine, "dropout_seed", 0))
     cfg.update(over)
     return cfg
 
