@@ -1489,15 +1489,18 @@ static int tc_gemm_kmajor(dfm_handle* h, const float* A_hi, const float* A_lo, i
                           float* C, int ldc, int M, int N, int K, int epi, const EpiArgs& ep, cudaStream_t st) {
     const int BN = N > 128 ? 256 : 128;
     const int bk = TC_BK;
+    const int ntile = (N + BN - 1) / BN;
+    const int bn = std::min(BN, ((N + ntile - 1) / ntile + 15) / 16 * 16);   // equal tiles, multiple of 16 (UMMA N granularity)
     CUtensorMap ma, mal, mb, mbl;
     bool ok = tc::make_map_2d(&ma, A_hi, M, K, lda, tc::BM, bk) && tc::make_map_2d(&mal, A_lo ? A_lo : A_hi, M, K, lda, tc::BM, bk) &&
-              tc::make_map_2d(&mb, B_hi, N, K, ldb, BN, bk) && tc::make_map_2d(&mbl, B_lo ? B_lo : B_hi, N, K, ldb, BN, bk);
+              tc::make_map_2d(&mb, B_hi, N, K, ldb, bn, bk) && tc::make_map_2d(&mbl, B_lo ? B_lo : B_hi, N, K, ldb, bn, bk);
     if (!ok) FAIL(DFM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     tc::Params p{};
     p.M = M; p.N = N; p.K = K; p.k_per_split = K; p.C = C; p.ldc = ldc; p.c_split_stride = 0; p.epi = epi; p.ep = ep;
     p.split_a = A_lo ? 0 : 1; p.split_b = B_lo ? 0 : 1;
+    p.bn = bn;
     if (const char* e = getenv("DFM_TC_DBG")) p.dbg = atoi(e);
-    dim3 grid(cdiv(N, BN), cdiv(M, tc::BM), 1);
+    dim3 grid(cdiv(N, bn), cdiv(M, tc::BM), 1);
     if (BN == 256) tc::gemm_kernel<256, 0, TC_BK><<<grid, tc::NTHREADS, tc::Smem<256, TC_BK>::TOTAL, st>>>(ma, mal, mb, mbl, p);
     else tc::gemm_kernel<128, 0, TC_BK><<<grid, tc::NTHREADS, tc::Smem<128, TC_BK>::TOTAL, st>>>(ma, mal, mb, mbl, p);
     if (h) h->launches++;
@@ -1519,6 +1522,7 @@ static int tc_gemm_mnmajor(dfm_handle* h, const float* A, int lda, const float* 
     tc::Params p{};
     p.M = M; p.N = N; p.K = K; p.k_per_split = kps; p.C = Cpart; p.ldc = N; p.c_split_stride = (size_t)M * N; p.epi = EPI_NONE;
     p.split_a = 1; p.split_b = 1;
+    p.bn = BN;
     if (const char* e = getenv("DFM_TC_DBG")) p.dbg = atoi(e);
     dim3 grid(cdiv(N, BN), cdiv(M, tc::BM), nz);
     if (BN == 256) tc::gemm_kernel<256, 1, TC_BK><<<grid, tc::NTHREADS, tc::Smem<256, TC_BK>::TOTAL, st>>>(ma, ma, mb, mb, p);

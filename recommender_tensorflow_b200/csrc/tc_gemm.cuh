@@ -128,6 +128,8 @@ struct Params {
     EpiArgs ep;
     int split_a, split_b;     // 1: operand is raw fp32, split in the kernel; 0: hi/lo come from two tensor maps
     int dbg;                  // experiments only: 1 = skip the split work, 2 = skip the MMAs
+    int bn;                   // output columns per CTA (multiple of 16, <= BN): N is cut into equal tiles so that
+                              // e.g. N = 416 runs as 2 x 208 instead of 256 + 160 (37% of the second tile wasted)
 };
 
 template <int BN, int BK>
@@ -154,7 +156,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
     uint64_t* accum = bars + 3 * S::STAGES;      // accumulator complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S::STAGES + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int bn = p.bn;      // runtime tile width; BN is the capacity (stage / TMEM sizing)
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * bn;
     const int kbeg = MODE == 1 ? blockIdx.z * p.k_per_split : 0;
     const int kend = MODE == 1 ? min(p.K, kbeg + p.k_per_split) : p.K;
     const int nkb = (kend - kbeg + BK - 1) / BK;
@@ -182,7 +185,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            const uint32_t bytes = (p.split_a ? S::A_BYTES : 2 * S::A_BYTES) + (p.split_b ? S::B_BYTES : 2 * S::B_BYTES);
+            const uint32_t b_bytes = (uint32_t)bn * BK * 4;
+            const uint32_t bytes = (p.split_a ? S::A_BYTES : 2 * S::A_BYTES) + (p.split_b ? b_bytes : 2 * b_bytes);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % S::STAGES;
                 if (kb >= S::STAGES) mbar_wait(&empty[s], ((kb / S::STAGES) - 1) & 1);
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN, MODE == 1, MODE == 1);
+            const uint32_t idesc = make_idesc(bn, MODE == 1, MODE == 1);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % S::STAGES;
                 mbar_wait(&split[s], (kb / S::STAGES) & 1);
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
                 float4* hi = reinterpret_cast<float4*>(st + 2 * S::A_BYTES);
                 float4* lo = reinterpret_cast<float4*>(st + 2 * S::A_BYTES + S::B_BYTES);
 #pragma unroll 4
-                for (int i = t; i < S::B_BYTES / 16; i += n_split_threads) {
+                for (int i = t; i < bn * BK * 4 / 16; i += n_split_threads) {
                     float4 x = hi[i];
 #if TC_TRUNC_HI
                     // kind::tf32 ignores the low 13 mantissa bits of its fp32 operands (verified by the accuracy
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
         float* tb = reinterpret_cast<float*>(smem) + warp * (32 * 36);
         const int row0 = m0 + q * 32;
         const int rsub = lane >> 3, cg = lane & 7;
-        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        for (int c0 = half * 32; c0 < bn; c0 += 64) {
             if (n0 + c0 >= p.N) break;
             {
                 float v[32], vx[32];
