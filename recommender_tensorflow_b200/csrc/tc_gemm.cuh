@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
             }
             __syncwarp();
             const int n = n0 + c0 + cg * 4;
-            const bool nok = n < p.N;           // N % 4 == 0 on this path
+            const bool nok = n < p.N && (c0 + cg * 4) < bn;   // N % 4 == 0 and bn % 16 == 0 on this path
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.epi == EPI_BIAS_RELU && nok) bias4 = __ldg(reinterpret_cast<const float4*>(p.ep.bias + n));
             const int nk = (p.epi == EPI_DE) ? (n % p.ep.K) : 0;
