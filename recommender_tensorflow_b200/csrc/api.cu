@@ -485,7 +485,6 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
         CK(cudaMallocHost(&s.h_loss, 64));
     }
     for (auto& e : h->ph_ev) CK(cudaEventCreate(&e));
-    CK(cudaFuncSetAttribute(transform_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * DFM_MAX_CAT * 4));
     CK(cudaFuncSetAttribute(numeric_grad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->rows_per_chunk * (DFM_MAX_NUM + 1) * 4));
 
     // optimizer slot initial values (Adagrad / FTRL accumulators start at init_acc)
@@ -662,7 +661,7 @@ struct Phase {
 template <int K>
 static void launch_transform(dfm_handle* h, const BatchPtrs& bp, int B, bool with_keys, int32_t* ids_out, cudaStream_t st) {
     if (h->dc == 0) return;
-    transform_kernel<64><<<cdiv(B, 64), 64, (size_t)64 * h->dc * 4, st>>>(
+    transform_kernel<32><<<cdiv(B, 32), 256, (size_t)32 * h->dc * 4, st>>>(
         bp, h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, B, h->dc, h->d_row_off, (uint32_t)h->R, ids_out,
         with_keys ? h->ws.keys[0] : nullptr, with_keys ? h->ws.vals[0] : nullptr, h->d_err);
     h->launches++;

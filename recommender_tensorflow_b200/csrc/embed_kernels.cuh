@@ -183,29 +183,32 @@ __device__ __forceinline__ int32_t transform_one(const BatchPtrs& bp, const ColD
     }
 }
 
-// One block = TILE consecutive samples.  Phase 1 walks the columns (coalesced column reads, the
-// column kind is uniform across the block), phase 2 writes ids / keys / payload sample-major.
+// One block = TILE consecutive samples x all columns.  Phase 1: work item w -> (column w / TILE, sample w % TILE),
+// so a warp reads 32 consecutive elements of ONE column (coalesced, uniform column kind) and the columns of a
+// sample are transformed in parallel by different warps (a hashed string column costs ~100x an identity column;
+// one thread per sample serialised all of them).  Phase 2 writes ids / keys / payload sample-major.
 template <int TILE>
-__global__ void __launch_bounds__(TILE) transform_kernel(BatchPtrs bp, const ColDev* __restrict__ cols,
-                                                         const float* __restrict__ bounds,
-                                                         const uint8_t* __restrict__ voc_bytes,
-                                                         const int32_t* __restrict__ voc_offs, int B, int dc,
-                                                         const uint32_t* __restrict__ row_off, uint32_t R,
-                                                         int32_t* __restrict__ ids, uint32_t* __restrict__ keys,
-                                                         uint32_t* __restrict__ vals, int* err) {
+__global__ void __launch_bounds__(256) transform_kernel(BatchPtrs bp, const ColDev* __restrict__ cols,
+                                                        const float* __restrict__ bounds,
+                                                        const uint8_t* __restrict__ voc_bytes,
+                                                        const int32_t* __restrict__ voc_offs, int B, int dc,
+                                                        const uint32_t* __restrict__ row_off, uint32_t R,
+                                                        int32_t* __restrict__ ids, uint32_t* __restrict__ keys,
+                                                        uint32_t* __restrict__ vals, int* err) {
     extern __shared__ int32_t sid[];  // [TILE][dc]
     const int b0 = blockIdx.x * TILE;
-    const int b = b0 + threadIdx.x;
-    if (b < B) {
-        for (int f = 0; f < dc; ++f) {
+    const int nb = min(TILE, B - b0);
+    for (int w = threadIdx.x; w < TILE * dc; w += blockDim.x) {
+        const int f = w / TILE, t = w - f * TILE;
+        if (t < nb) {
             ColDev c = cols[f];
-            sid[threadIdx.x * dc + f] = transform_one(bp, c, f, b, bounds, voc_bytes, voc_offs, err);
+            sid[t * dc + f] = transform_one(bp, c, f, b0 + t, bounds, voc_bytes, voc_offs, err);
         }
     }
     __syncthreads();
-    const int nloc = min(TILE, B - b0) * dc;
+    const int nloc = nb * dc;
     const int64_t g0 = (int64_t)b0 * dc;
-    for (int w = threadIdx.x; w < nloc; w += TILE) {
+    for (int w = threadIdx.x; w < nloc; w += blockDim.x) {
         int32_t id = sid[w];
         int f = w % dc;
         ids[g0 + w] = id;

@@ -14,29 +14,9 @@ _DNN_LEARNING_RATE = 0.001
 _LINEAR_LEARNING_RATE = 0.005
 
 
-class DNNLinearCombinedClassifier:
-    def __init__(self, model_dir=None, linear_feature_columns=None, dnn_feature_columns=None, dnn_hidden_units=None,
-                 dnn_dropout=None, config=None, max_batch=4096, device=0, feature_dtypes=FEATURE_DTYPES):
-        linear_feature_columns = list(linear_feature_columns or [])
-        dnn_feature_columns = list(dnn_feature_columns or [])
-        if not linear_feature_columns and not dnn_feature_columns:
-            raise ValueError("Either linear_feature_columns or dnn_feature_columns must be defined.")
-        cats = [c.categorical_column for c in dnn_feature_columns] or linear_feature_columns
-        if linear_feature_columns and dnn_feature_columns and [c.name for c in cats] != [c.name for c in linear_feature_columns]:
-            raise NotImplementedError("linear and dnn sides must be built on the same categorical columns "
-                                      "(as in trainers/ml_100k.py:37-38)")
-        dims = {c.dimension for c in dnn_feature_columns}
-        if len(dims) > 1:
-            raise NotImplementedError("all embedding columns must share one dimension")
-        lin_lr = min(_LINEAR_LEARNING_RATE, 1.0 / math.sqrt(max(len(linear_feature_columns), 1)))
-        self.engine = DeepFMEngine(cats, (), embedding_size=(dims.pop() if dims else 4),
-                                   hidden_units=list(dnn_hidden_units or []), use_linear=bool(linear_feature_columns),
-                                   use_mf=False, use_dnn=bool(dnn_feature_columns), loss_reduction="sum",
-                                   opt_deep=default_optimizer("Adagrad", _DNN_LEARNING_RATE),
-                                   opt_linear=default_optimizer("Ftrl", lin_lr), max_batch=max_batch, device=device,
-                                   dropout=float(dnn_dropout or 0.0),
-                                   feature_dtypes=feature_dtypes)
-        self.model_dir = model_dir
+class _CannedBase:
+    """train / evaluate / predict loops shared by the canned-estimator mirrors."""
+    engine = None
 
     def train(self, input_fn, steps=None, max_steps=None):
         loss = None
@@ -65,3 +45,28 @@ class DNNLinearCombinedClassifier:
             preds = get_binary_predictions(self.engine.predict_logits(feats))
             for i in range(preds["logits"].shape[0]):
                 yield {k: v[i] for k, v in preds.items()}
+
+
+class DNNLinearCombinedClassifier(_CannedBase):
+    def __init__(self, model_dir=None, linear_feature_columns=None, dnn_feature_columns=None, dnn_hidden_units=None,
+                 dnn_dropout=None, config=None, max_batch=4096, device=0, feature_dtypes=FEATURE_DTYPES):
+        linear_feature_columns = list(linear_feature_columns or [])
+        dnn_feature_columns = list(dnn_feature_columns or [])
+        if not linear_feature_columns and not dnn_feature_columns:
+            raise ValueError("Either linear_feature_columns or dnn_feature_columns must be defined.")
+        cats = [c.categorical_column for c in dnn_feature_columns] or linear_feature_columns
+        if linear_feature_columns and dnn_feature_columns and [c.name for c in cats] != [c.name for c in linear_feature_columns]:
+            raise NotImplementedError("linear and dnn sides must be built on the same categorical columns "
+                                      "(as in trainers/ml_100k.py:37-38)")
+        dims = {c.dimension for c in dnn_feature_columns}
+        if len(dims) > 1:
+            raise NotImplementedError("all embedding columns must share one dimension")
+        lin_lr = min(_LINEAR_LEARNING_RATE, 1.0 / math.sqrt(max(len(linear_feature_columns), 1)))
+        self.engine = DeepFMEngine(cats, (), embedding_size=(dims.pop() if dims else 4),
+                                   hidden_units=list(dnn_hidden_units or []), use_linear=bool(linear_feature_columns),
+                                   use_mf=False, use_dnn=bool(dnn_feature_columns), loss_reduction="sum",
+                                   opt_deep=default_optimizer("Adagrad", _DNN_LEARNING_RATE),
+                                   opt_linear=default_optimizer("Ftrl", lin_lr), max_batch=max_batch, device=device,
+                                   dropout=float(dnn_dropout or 0.0),
+                                   feature_dtypes=feature_dtypes)
+        self.model_dir = model_dir

@@ -4,6 +4,13 @@ import numpy as np
 from ..engine import default_optimizer
 
 
+def layer_summary(value):
+    """trainers/model_utils.py:4-6: tf.nn.zero_fraction scalar + activation histogram of a tensor, host side."""
+    v = np.asarray(value, dtype=np.float32).reshape(-1)
+    hist, edges = np.histogram(v, bins=30) if v.size else (np.zeros(30, int), np.zeros(31))
+    return {"fraction_of_zero_values": float((v == 0).mean()) if v.size else 0.0, "activation": (hist, edges)}
+
+
 def get_optimizer(optimizer_name="Adam", learning_rate=0.001):
     """trainers/model_utils.py:57-66 — Adagrad | Adam | Ftrl | RMSProp | SGD with `learning_rate` only
     (an unknown name raises KeyError, like optimizer_classes[optimizer_name] in the reference)."""

@@ -266,3 +266,19 @@ def test_estimator_model_fn_facade(tmp_path):
     with pytest.raises(ValueError):
         deep_fm.model_fn({"user_id": np.zeros(4, np.int32)}, np.zeros(4), ml_100k.ModeKeys.TRAIN,
                          {"categorical_columns": [], "numeric_columns": []})
+
+
+def test_canned_estimator_mirrors(tmp_path):
+    """trainers/linear.py, trainers/deep.py, trainers/linear_deep.py: the canned estimators' train/evaluate loops."""
+    from recommender_tensorflow_b200.trainers import deep, linear, linear_deep, ml_100k
+    csv_path = str(tmp_path / "train.csv")
+    ml_100k.write_synthetic_csv(csv_path, 400)
+    fcs = ml_100k.get_feature_columns(embedding_size=4)
+    for est in (linear.LinearClassifier(fcs["linear"], max_batch=64),
+                deep.DNNClassifier([16, 16], fcs["deep"], max_batch=64),
+                linear_deep.DNNLinearCombinedClassifier(linear_feature_columns=fcs["linear"], dnn_feature_columns=fcs["deep"],
+                                                        dnn_hidden_units=[16, 16], max_batch=64)):
+        loss = est.train(ml_100k.get_input_fn(csv_path, batch_size=32, seed=0), max_steps=10)
+        assert np.isfinite(loss) and est.engine.global_step == 10
+        m = est.evaluate(ml_100k.get_input_fn(csv_path, ml_100k.ModeKeys.EVAL, batch_size=64))
+        assert 0.0 <= m["auc"] <= 1.0 and np.isfinite(m["average_loss"])
