@@ -153,7 +153,7 @@ def cpu_baseline(w, cats_specs_engine, seconds_target=12.0, threads=None):
         dt = time.perf_counter() - t0
         if dt > seconds_target or n >= 200:
             break
-    return {"value": bs * n / dt, "unit": "samples/s", "cores": threads, "kind": "port",
+    return {"value": bs * n / dt, "unit": "samples/s", "cores": threads, "kind": "port", "ms_per_cpu_step": dt / n * 1e3, "cpu_batch": bs,
             "sample": "%d steps of batch %d of the same workload, torch-CPU float32 restatement of the TF-1.12 step "
                       "(incl. literal non-lazy Adam); not TensorFlow%s" % (n, bs, shrunk)}, None
 
@@ -187,8 +187,11 @@ def run_reference(args, w, name):
         print(json.dumps({"impl": "reference", "unavailable": why}))
         return
     line = {"metric": METRIC, "value": base["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "impl": "reference", "config": {"workload": name},
+            "warmup": args.warmup, "ms_per_step": base["ms_per_cpu_step"] * w["batch"] / base["cpu_batch"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": name, "batch_per_gpu": w["batch"], "embedding_size": w["k"], "hidden_units": list(w["hidden"]),
+                       "note": "CPU arm: restated reference (oracle port, torch-CPU); TensorFlow 1.12 is not installable in this image; "
+                               "ms_per_step is the CPU time for one batch of the workload's size extrapolated from the bounded sample"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
