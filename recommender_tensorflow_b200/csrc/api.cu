@@ -37,7 +37,7 @@ struct SegWS {
     void* sort_temp = nullptr;
     unsigned long long* flags = nullptr; void* scan_temp = nullptr; unsigned long long* seg_total = nullptr;
     SegCounts* seg_cnt = nullptr;
-    uint32_t *row_start = nullptr, *row_piece0 = nullptr, *piece_start = nullptr, *piece_row = nullptr, *hot_list = nullptr;
+    uint32_t *row_start = nullptr, *row_piece0 = nullptr, *piece_start = nullptr, *urow = nullptr, *uval = nullptr, *hot_list = nullptr;
     float* piece_sum = nullptr;
     int cur = 0;     // which keys/vals buffer holds the sorted list
     const uint32_t* skeys() const { return keys[cur]; }
@@ -69,11 +69,11 @@ struct dfm_handle {
     std::vector<uint32_t> row_off;   // [dc+1]
     uint64_t R = 0;
     int key_bits = 1;
-    int emb_slots = 2, emb_stride = 0;
+    int emb_slots = 2;
+    Table tb{};               // one record per row: w | {lin w, s1, s2, last_step} | slot1 | slot2 (dfm_types.cuh)
 
     ColDev* d_cols = nullptr; float* d_bounds = nullptr; uint8_t* d_voc_bytes = nullptr; int32_t* d_voc_offs = nullptr;
     uint32_t* d_row_off = nullptr;
-    float* emb_rec = nullptr; float4* lin_rec = nullptr;
 
     std::vector<DenseT> dense;
     int64_t n_deep = 0, n_dense = 0;
@@ -176,7 +176,8 @@ static int alloc_ws(dfm_handle* h, SegWS& ws, int64_t n, int K) {
     if (dalloc(h, &ws.row_start, n + 1)) return DFM_ERR_CUDA;
     if (dalloc(h, &ws.row_piece0, n + 1)) return DFM_ERR_CUDA;
     if (dalloc(h, &ws.piece_start, n + 1)) return DFM_ERR_CUDA;
-    if (dalloc(h, &ws.piece_row, n)) return DFM_ERR_CUDA;
+    if (dalloc(h, &ws.urow, n + 1)) return DFM_ERR_CUDA;
+    if (dalloc(h, &ws.uval, n + 1)) return DFM_ERR_CUDA;
     if (dalloc(h, &ws.hot_list, (size_t)(2 * (n / 32 + 2)))) return DFM_ERR_CUDA;
     if (dalloc(h, &ws.piece_sum, (size_t)(2 * (n / 32 + 2)) * (K + 4))) return DFM_ERR_CUDA;
     return DFM_OK;
@@ -184,7 +185,7 @@ static int alloc_ws(dfm_handle* h, SegWS& ws, int64_t n, int K) {
 
 static void free_ws(SegWS& ws) {
     void* ptrs[] = {ws.keys[0], ws.keys[1], ws.vals[0], ws.vals[1], ws.sort_temp, ws.flags, ws.scan_temp, ws.seg_total, ws.seg_cnt,
-                    ws.row_start, ws.row_piece0, ws.piece_start, ws.piece_row, ws.hot_list, ws.piece_sum};
+                    ws.row_start, ws.row_piece0, ws.piece_start, ws.urow, ws.uval, ws.hot_list, ws.piece_sum};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -198,7 +199,7 @@ static int64_t pad32(int64_t x) { return (x + 31) / 32 * 32; }
 static void free_all(dfm_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    void* ptrs[] = {h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, h->d_row_off, h->emb_rec, h->lin_rec, h->dw,
+    void* ptrs[] = {h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, h->d_row_off, h->tb.rec, h->dw,
                     h->ds1, h->ds2, h->dg, h->ids, h->h0, h->s, h->zacc, h->logits, h->dz, h->dE, h->splitk, h->colpart, h->head_part,
                     h->d_loss, h->d_dzsum, h->d_err, h->alpha_d, h->alpha_l, h->up_partial, h->w0_partial, h->tc_w, h->head_gpart, h->uidx,
                     h->req_rows, h->d_counts};
@@ -325,17 +326,18 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     if (!voc_offs.empty()) CK(cudaMemcpy(h->d_voc_offs, voc_offs.data(), voc_offs.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_row_off, h->row_off.data(), h->row_off.size() * 4, cudaMemcpyHostToDevice));
 
-    // ---- tables: emb_rec [R][1+S][K], lin_rec [R] float4 {w, s1, s2, last_step}
+    // ---- tables: one record per row (see Table)
     h->emb_slots = opt_slots(h->od.kind);
-    h->emb_stride = (1 + h->emb_slots) * K;
     const size_t Ralloc = std::max<uint64_t>(h->R_loc, 1);
     R = h->R_loc;   // from here on: rows stored on this rank
     if (h->need_emb) {
-        if (dalloc(h, &h->emb_rec, Ralloc * h->emb_stride)) return DFM_ERR_CUDA;
-        CK(cudaMemset(h->emb_rec, 0, Ralloc * h->emb_stride * 4));
+        h->tb.lin_off = K; h->tb.s1_off = K + 4; h->tb.s2_off = 2 * K + 4;
+        h->tb.stride = (K + 4 + h->emb_slots * K + 15) / 16 * 16;
+    } else {
+        h->tb.lin_off = 0; h->tb.s1_off = 0; h->tb.s2_off = 0; h->tb.stride = 4;
     }
-    if (dalloc(h, &h->lin_rec, Ralloc)) return DFM_ERR_CUDA;
-    CK(cudaMemset(h->lin_rec, 0, Ralloc * sizeof(float4)));
+    if (dalloc(h, &h->tb.rec, Ralloc * h->tb.stride)) return DFM_ERR_CUDA;
+    CK(cudaMemset(h->tb.rec, 0, Ralloc * h->tb.stride * 4));
 
     // ---- dense parameters, packed: deep group first, then the linear group
     const int d = h->dc + h->dn, dK = d * K;
@@ -491,11 +493,11 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     auto init_acc = [&](const dfm_optimizer& o) { return (o.kind == DFM_OPT_ADAGRAD || o.kind == DFM_OPT_FTRL || o.kind == DFM_OPT_RMSPROP) ? o.init_acc : 0.f; };
     if (init_acc(h->od) != 0.f) {
         if (h->need_emb && R)
-            fill_strided_kernel<<<cdiv((int64_t)R * K, 256), 256, 0, h->stream>>>(h->emb_rec + K, R, K, h->emb_stride, init_acc(h->od));
+            fill_strided_kernel<<<cdiv((int64_t)R * K, 256), 256, 0, h->stream>>>(h->tb.rec + h->tb.s1_off, R, K, h->tb.stride, init_acc(h->od));
         if (h->n_deep) fill_strided_kernel<<<cdiv(h->n_deep, 256), 256, 0, h->stream>>>(h->ds1, 1, (int)h->n_deep, 0, init_acc(h->od));
     }
     if (init_acc(h->ol) != 0.f) {
-        if (R) fill_strided_kernel<<<cdiv((int64_t)R, 256), 256, 0, h->stream>>>(reinterpret_cast<float*>(h->lin_rec) + 1, R, 1, 4, init_acc(h->ol));
+        if (R) fill_strided_kernel<<<cdiv((int64_t)R, 256), 256, 0, h->stream>>>(h->tb.rec + h->tb.lin_off + 1, R, 1, h->tb.stride, init_acc(h->ol));
         if (h->n_dense > h->n_deep)
             fill_strided_kernel<<<cdiv(h->n_dense - h->n_deep, 256), 256, 0, h->stream>>>(h->ds1 + h->n_deep, 1, (int)(h->n_dense - h->n_deep), 0, init_acc(h->ol));
     }
@@ -540,14 +542,14 @@ static bool resolve(dfm_handle* h, const std::string& full, TensorRef& t) {
         if (!h->need_emb) return false;
         int si = slot_index(h->od.kind);
         if (si < 0) return false;
-        t = {h->emb_rec + (int64_t)si * h->K, (int64_t)h->R_loc, h->K, h->emb_stride};
+        t = {h->tb.rec + (si == 0 ? 0 : si == 1 ? h->tb.s1_off : h->tb.s2_off), (int64_t)h->R_loc, h->K, h->tb.stride};
         return true;
     }
     if (name == "lin") {
         if (!h->use_linear) return false;
         int si = slot_index(h->ol.kind);
         if (si < 0) return false;
-        t = {reinterpret_cast<float*>(h->lin_rec) + si, (int64_t)h->R_loc, 1, 4};
+        t = {h->tb.rec + h->tb.lin_off + si, (int64_t)h->R_loc, 1, h->tb.stride};
         return true;
     }
     for (const DenseT& dt : h->dense) {
@@ -607,7 +609,7 @@ extern "C" int dfm_init_random(dfm_handle* h, uint64_t seed) {
     cudaStream_t st = h->stream;
     if (h->need_emb && h->R_loc) {
         uint64_t tot = h->R_loc * (uint64_t)h->K;
-        init_trunc_normal_kernel<<<cdiv((int64_t)tot, 256), 256, 0, st>>>(h->emb_rec, h->R_loc, h->K, h->emb_stride,
+        init_trunc_normal_kernel<<<cdiv((int64_t)tot, 256), 256, 0, st>>>(h->tb.rec, h->R_loc, h->K, h->tb.stride,
                                                                           1.0f / sqrtf((float)h->K), seed * 0x9E3779B97F4A7C15ULL + 1);
     }
     int idx = 0;
@@ -676,7 +678,7 @@ static void launch_gather(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_
         if (dt.name == "bias") bias = h->dw + dt.off;
     }
     unsigned grid = std::min<unsigned>(cdiv(B, 8), (unsigned)h->sm_count * 16);
-    gather_fm_kernel<K><<<grid, 256, 0, st>>>(h->ids, B, h->dc, h->dn, h->d_row_off, h->emb_rec, h->emb_stride, h->lin_rec, bp,
+    gather_fm_kernel<K><<<grid, 256, 0, st>>>(h->ids, B, h->dc, h->dn, h->d_row_off, h->tb, bp,
                                               num_emb, num_lin, bias, h->use_linear, h->use_mf, h->need_emb, h->h0, h->s, h->zacc,
                                               rowbuf ? h->uidx : nullptr, rowbuf, K + 4);
     h->launches++;
@@ -738,7 +740,7 @@ static int flush_impl(dfm_handle* h, cudaStream_t st) {
     if (!any_adam(h) || h->flushed_step == h->step || h->R_loc == 0) { h->flushed_step = h->step; return DFM_OK; }
     OptDev od = make_opt(h->od, h->b1p_d, h->b2p_d), ol = make_opt(h->ol, h->b1p_l, h->b2p_l);
     unsigned grid = (unsigned)std::min<uint64_t>((h->R_loc + (256 / (K / 4)) - 1) / (256 / (K / 4)), (uint64_t)h->sm_count * 16);
-    catchup_all_kernel<K><<<grid, 256, 0, st>>>(h->emb_rec, h->lin_rec, h->R_loc, (int)h->step, h->alpha_d, h->alpha_l, od, ol,
+    catchup_all_kernel<K><<<grid, 256, 0, st>>>(h->tb, h->R_loc, (int)h->step, h->alpha_d, h->alpha_l, od, ol,
                                                 (bool)h->need_emb, (bool)h->use_linear);
     h->launches++;
     CK(cudaGetLastError());
@@ -841,8 +843,8 @@ static int build_segments(dfm_handle* h, SegWS& ws, int64_t n, uint32_t limit, i
         h->launches++;
         prims::exclusive_scan_u64(reinterpret_cast<const uint64_t*>(ws.flags), reinterpret_cast<uint64_t*>(ws.flags), n, ws.scan_temp,
                                   reinterpret_cast<uint64_t*>(ws.seg_total), st, &h->launches);
-        seg_fill_kernel<<<cdiv(n, 256), 256, 0, st>>>(ws.skeys(), n, limit, ws.flags, ws.seg_total, ws.seg_cnt, ws.row_start, ws.row_piece0,
-                                                      ws.piece_start, ws.piece_row);
+        seg_fill_kernel<<<cdiv(n, 256), 256, 0, st>>>(ws.skeys(), ws.svals(), n, limit, ws.flags, ws.seg_total, ws.seg_cnt, ws.row_start,
+                                                      ws.row_piece0, ws.piece_start, ws.urow, ws.uval);
         h->launches++;
     } else {
         CK(cudaMemsetAsync(ws.seg_cnt, 0, sizeof(SegCounts), st));
@@ -979,8 +981,8 @@ static int sparse_update(dfm_handle* h, SegWS& ws, int64_t n, const GradSrc<K>& 
         h->launches += 2;
     }
     if (ph) ph->next();
-    row_update_kernel<K><<<n > 0 ? row_grid : 1, 256, 0, st>>>(ws.skeys(), ws.svals(), ws.row_start, ws.row_piece0, ws.piece_start, ws.seg_cnt, src,
-                                                               ws.piece_sum, h->emb_rec, h->emb_slots, h->lin_rec, od, ol, (bool)h->need_emb,
+    row_update_kernel<K><<<n > 0 ? row_grid : 1, 256, 0, st>>>(ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0, ws.piece_start, ws.seg_cnt, src,
+                                                               ws.piece_sum, h->tb, h->emb_slots, od, ol, (bool)h->need_emb,
                                                                (bool)h->use_linear, (int)t, h->alpha_d, h->alpha_l, gsum, K + 4);
     h->launches++;
     if (ph) ph->next();
@@ -1007,7 +1009,7 @@ static int catchup_touched(dfm_handle* h, SegWS& ws, int64_t n, int64_t t, cudaS
     // non-lazy Adam: bring the touched rows up to step t-1
     if (n > 0 && any_adam(h) && t > 1) {
         const OptDev pod = make_opt(h->od, h->b1p_d, h->b2p_d), pol = make_opt(h->ol, h->b1p_l, h->b2p_l);
-        catchup_touched_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(h->emb_rec, h->lin_rec, ws.skeys(), ws.row_start, ws.seg_cnt, (int)(t - 1),
+        catchup_touched_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(h->tb, ws.urow, ws.seg_cnt, (int)(t - 1),
                                                                              h->alpha_d, h->alpha_l, pod, pol, (bool)h->need_emb, (bool)h->use_linear);
         h->launches++;
     }
@@ -1144,7 +1146,7 @@ extern "C" int dfm_set_global_step(dfm_handle* h, int64_t step) {
     h->b1p_d = b1d; h->b2p_d = b2d; h->b1p_l = b1l; h->b2p_l = b2l;
     h->step = step; h->flushed_step = step;
     if (h->R_loc) {
-        fill_strided_kernel<<<cdiv((int64_t)h->R_loc, 256), 256, 0, h->stream>>>(reinterpret_cast<float*>(h->lin_rec) + 3, h->R_loc, 1, 4,
+        fill_strided_kernel<<<cdiv((int64_t)h->R_loc, 256), 256, 0, h->stream>>>(h->tb.rec + h->tb.lin_off + 3, h->R_loc, 1, h->tb.stride,
                                                                                   __int_as_float_host((int)step));
     }
     CK(cudaStreamSynchronize(h->stream));
@@ -1222,7 +1224,7 @@ static int shard_serve_impl(dfm_handle* h, const uint32_t* recv_rows, int64_t n_
     if (rc) return rc;
     if ((rc = catchup_touched<K>(h, h->ws_own, n_recv, t, st))) return rc;
     if (n_recv > 0) {
-        shard_serve_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(recv_rows, n_recv, h->emb_rec, h->emb_stride, h->lin_rec, (bool)h->need_emb,
+        shard_serve_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(recv_rows, n_recv, h->tb, (bool)h->need_emb,
                                                                           (bool)h->use_linear, reply, K + 4);
         h->launches++;
     }

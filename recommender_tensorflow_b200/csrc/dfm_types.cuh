@@ -44,3 +44,20 @@ constexpr int DIRECT_T = 32;      // rows with <= DIRECT_T lookups are summed di
 __host__ __device__ __forceinline__ uint32_t piece_slot(uint32_t head_pos) {
     return (head_pos >> 5) * 2u + ((head_pos % PIECE_C) == 0 ? 0u : 1u);
 }
+
+// One record per table row, 64-byte aligned:  [ w[K] | {lin_w, lin_s1, lin_s2, last_step} | s1[K] | s2[K] | pad ]
+// (K = 16, Adam: 256 bytes).  The forward reads w and the linear weight from ONE 128-byte line; the catch-up and
+// the optimizer touch two adjacent lines (ncu showed 8 sectors fetched per lookup when the embedding record and
+// the linear record lived in separate arrays).  Without embeddings (linear-only model) the record is the float4.
+struct Table {
+    float* rec;
+    int stride;             // floats per row
+    int lin_off;            // float offset of the {w, s1, s2, last_step} float4
+    int s1_off, s2_off;     // float offsets of the embedding optimizer slots
+};
+__device__ __forceinline__ float4* tab_lin(const Table& t, size_t row) {
+    return reinterpret_cast<float4*>(t.rec + row * t.stride + t.lin_off);
+}
+__device__ __forceinline__ float4* tab_w(const Table& t, size_t row) { return reinterpret_cast<float4*>(t.rec + row * t.stride); }
+__device__ __forceinline__ float4* tab_s1(const Table& t, size_t row) { return reinterpret_cast<float4*>(t.rec + row * t.stride + t.s1_off); }
+__device__ __forceinline__ float4* tab_s2(const Table& t, size_t row) { return reinterpret_cast<float4*>(t.rec + row * t.stride + t.s2_off); }

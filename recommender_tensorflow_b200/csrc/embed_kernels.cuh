@@ -263,11 +263,11 @@ __global__ void seg_flag_kernel(const uint32_t* __restrict__ keys, int64_t n, ui
     }
 }
 
-__global__ void seg_fill_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t R,
+__global__ void seg_fill_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n, uint32_t R,
                                 const unsigned long long* __restrict__ scanned,
                                 const unsigned long long* __restrict__ total, SegCounts* __restrict__ cnt,
                                 uint32_t* __restrict__ row_start, uint32_t* __restrict__ row_piece0,
-                                uint32_t* __restrict__ piece_start, uint32_t* __restrict__ piece_row) {
+                                uint32_t* __restrict__ piece_start, uint32_t* __restrict__ urow, uint32_t* __restrict__ uval) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         uint32_t U = (uint32_t)(*total >> 32), P = (uint32_t)(*total & 0xffffffffu);
@@ -286,20 +286,21 @@ __global__ void seg_fill_kernel(const uint32_t* __restrict__ keys, int64_t n, ui
     unsigned long long s = scanned[i];
     uint32_t ridx = (uint32_t)(s >> 32), pidx = (uint32_t)(s & 0xffffffffu);
     piece_start[pidx] = (uint32_t)i;
-    piece_row[pidx] = rh ? ridx : ridx - 1;
     if (rh) {
         row_start[ridx] = (uint32_t)i;
         row_piece0[ridx] = pidx;
+        urow[ridx] = keys[i];      // compact (coalesced) copies of the row id and of the first lookup of every
+        uval[ridx] = vals[i];      // unique row: they remove one dependent-load level from the row kernels
     }
 }
 
 // =============================================================================================
 // non-lazy Adam catch-up (exact deferred update) of the rows this batch touches, and full flush
 // =============================================================================================
-// table layout: emb_rec[row][1+S][K] floats (w | slot1 | slot2), lin_rec[row] = float4 {w, s1, s2, last_step bits}
-// The two optimizers share the step index, so the one last_step in lin_rec serves both tables.
+// table layout: see Table (dfm_types.cuh).  The two optimizers share the step index, so the one last_step
+// in the linear float4 serves both the embedding row and the linear weight.
 template <int K>
-__device__ __forceinline__ void catchup_group(float* __restrict__ emb_rec, float4* __restrict__ lin_rec, size_t row,
+__device__ __forceinline__ void catchup_group(const Table& tb, size_t row,
                                               bool act, int sub, int upto, const float* __restrict__ alpha_d,
                                               const float* __restrict__ alpha_l, const OptDev& od, const OptDev& ol,
                                               bool has_emb, bool has_lin) {
@@ -307,19 +308,19 @@ __device__ __forceinline__ void catchup_group(float* __restrict__ emb_rec, float
     float4 lr = make_float4(0.f, 0.f, 0.f, 0.f);
     int last = upto;
     if (act) {
-        lr = lin_rec[row];
+        lr = *tab_lin(tb, row);
         last = __float_as_int(lr.w);
     }
     const bool work = act && last < upto;
     if (work && has_emb && od.kind == DFM_OPT_ADAM) {
-        float4* base = reinterpret_cast<float4*>(emb_rec + row * 3 * K) + sub;
-        float4 m = base[LPR], v = base[2 * LPR];
+        float4 *pw = tab_w(tb, row) + sub, *pm = tab_s1(tb, row) + sub, *pv = tab_s2(tb, row) + sub;
+        float4 m = *pm, v = *pv;
         // rows that were never touched (m = v = 0) do not move under non-lazy Adam: nothing to read or write
         const bool idle = m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f && v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f;
         if (!idle) {
-            float4 w = base[0];
+            float4 w = *pw;
             adam_replay4(w, m, v, last, upto, alpha_d, od);
-            base[0] = w; base[LPR] = m; base[2 * LPR] = v;
+            *pw = w; *pm = m; *pv = v;
         }
     }
     __syncwarp();  // every lane of the group has read last_step before lane 0 rewrites it
@@ -328,23 +329,22 @@ __device__ __forceinline__ void catchup_group(float* __restrict__ emb_rec, float
         // the step at which the row first receives a gradient.
         if (has_lin && ol.kind == DFM_OPT_ADAM) adam_replay1(lr.x, lr.y, lr.z, last, upto, alpha_l, ol);
         lr.w = __int_as_float(upto);
-        lin_rec[row] = lr;
+        *tab_lin(tb, row) = lr;
     }
 }
 
 // rows touched by the current batch (unique list from the sort stage): bring them to step `upto`.
-// Each lane group handles RPG rows per trip and issues the loads of all of them level by level
-// (row index -> last_step record -> m, v) so that several dependent random accesses are in flight.
+// Each lane group handles RPG rows per trip; the last_step record and the m, v slots of a row are requested
+// together (both depend only on the compact row id), so one dependent-load level covers the whole row.
 template <int K>
-__global__ void __launch_bounds__(256) catchup_touched_kernel(float* __restrict__ emb_rec, float4* __restrict__ lin_rec,
-                                                              const uint32_t* __restrict__ skeys,
-                                                              const uint32_t* __restrict__ row_start,
+__global__ void __launch_bounds__(256) catchup_touched_kernel(Table tb,
+                                                              const uint32_t* __restrict__ urow,
                                                               const SegCounts* __restrict__ cnt, int upto,
                                                               const float* __restrict__ alpha_d,
                                                               const float* __restrict__ alpha_l, OptDev od, OptDev ol,
                                                               bool has_emb, bool has_lin) {
     constexpr int LPR = K / 4;
-    constexpr int RPG = 4;
+    constexpr int RPG = 2;
     const int sub = threadIdx.x % LPR;
     const uint32_t U = cnt->n_rows;
     const uint32_t gpb = blockDim.x / LPR;
@@ -353,31 +353,27 @@ __global__ void __launch_bounds__(256) catchup_touched_kernel(float* __restrict_
     for (uint32_t base = blockIdx.x * gpb; base < U; base += stride * RPG) {  // block-uniform trip count
         bool act[RPG], work[RPG], idle[RPG];
         size_t row[RPG];
-        uint32_t rs[RPG];
         float4 lr[RPG], m[RPG], v[RPG];
         int last[RPG];
 #pragma unroll
         for (int j = 0; j < RPG; ++j) {
             uint32_t u = base + j * stride + threadIdx.x / LPR;
             act[j] = u < U;
-            rs[j] = act[j] ? __ldg(row_start + u) : 0u;
+            row[j] = act[j] ? (size_t)__ldg(urow + u) : 0;
         }
-#pragma unroll
-        for (int j = 0; j < RPG; ++j) row[j] = act[j] ? (size_t)__ldg(skeys + rs[j]) : 0;
 #pragma unroll
         for (int j = 0; j < RPG; ++j) {
             lr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (act[j]) lr[j] = lin_rec[row[j]];
-            last[j] = act[j] ? __float_as_int(lr[j].w) : upto;
-            work[j] = act[j] && last[j] < upto;
+            m[j] = lr[j]; v[j] = lr[j];
+            if (act[j]) {
+                lr[j] = *tab_lin(tb, row[j]);
+                if (emb_adam) { m[j] = tab_s1(tb, row[j])[sub]; v[j] = tab_s2(tb, row[j])[sub]; }
+            }
         }
 #pragma unroll
         for (int j = 0; j < RPG; ++j) {
-            m[j] = make_float4(0.f, 0.f, 0.f, 0.f); v[j] = m[j];
-            if (work[j] && emb_adam) {
-                const float4* bp4 = reinterpret_cast<const float4*>(emb_rec + row[j] * 3 * K) + sub;
-                m[j] = bp4[LPR]; v[j] = bp4[2 * LPR];
-            }
+            last[j] = act[j] ? __float_as_int(lr[j].w) : upto;
+            work[j] = act[j] && last[j] < upto;
             // rows that were never touched (m = v = 0) do not move under non-lazy Adam: nothing more to read or write
             idle[j] = m[j].x == 0.f && m[j].y == 0.f && m[j].z == 0.f && m[j].w == 0.f && v[j].x == 0.f && v[j].y == 0.f &&
                       v[j].z == 0.f && v[j].w == 0.f;
@@ -385,10 +381,9 @@ __global__ void __launch_bounds__(256) catchup_touched_kernel(float* __restrict_
 #pragma unroll
         for (int j = 0; j < RPG; ++j) {
             if (work[j] && emb_adam && !idle[j]) {
-                float4* bp4 = reinterpret_cast<float4*>(emb_rec + row[j] * 3 * K) + sub;
-                float4 w = bp4[0];
+                float4 w = tab_w(tb, row[j])[sub];
                 adam_replay4(w, m[j], v[j], last[j], upto, alpha_d, od);
-                bp4[0] = w; bp4[LPR] = m[j]; bp4[2 * LPR] = v[j];
+                tab_w(tb, row[j])[sub] = w; tab_s1(tb, row[j])[sub] = m[j]; tab_s2(tb, row[j])[sub] = v[j];
             }
         }
         __syncwarp();  // every lane of a group has read last_step before lane 0 rewrites it
@@ -397,7 +392,7 @@ __global__ void __launch_bounds__(256) catchup_touched_kernel(float* __restrict_
             if (work[j] && sub == 0) {
                 if (has_lin && ol.kind == DFM_OPT_ADAM) adam_replay1(lr[j].x, lr[j].y, lr[j].z, last[j], upto, alpha_l, ol);
                 lr[j].w = __int_as_float(upto);
-                lin_rec[row[j]] = lr[j];
+                *tab_lin(tb, row[j]) = lr[j];
             }
         }
     }
@@ -405,7 +400,7 @@ __global__ void __launch_bounds__(256) catchup_touched_kernel(float* __restrict_
 
 // every row of the tables (dfm_flush)
 template <int K>
-__global__ void __launch_bounds__(256) catchup_all_kernel(float* __restrict__ emb_rec, float4* __restrict__ lin_rec,
+__global__ void __launch_bounds__(256) catchup_all_kernel(Table tb,
                                                           uint64_t R, int upto, const float* __restrict__ alpha_d,
                                                           const float* __restrict__ alpha_l, OptDev od, OptDev ol,
                                                           bool has_emb, bool has_lin) {
@@ -414,7 +409,7 @@ __global__ void __launch_bounds__(256) catchup_all_kernel(float* __restrict__ em
     const uint64_t gpb = blockDim.x / LPR;
     for (uint64_t base = (uint64_t)blockIdx.x * gpb; base < R; base += (uint64_t)gridDim.x * gpb) {
         uint64_t row = base + threadIdx.x / LPR;
-        catchup_group<K>(emb_rec, lin_rec, (size_t)row, row < R, sub, upto, alpha_d, alpha_l, od, ol, has_emb, has_lin);
+        catchup_group<K>(tb, (size_t)row, row < R, sub, upto, alpha_d, alpha_l, od, ol, has_emb, has_lin);
     }
 }
 
@@ -429,8 +424,7 @@ __global__ void __launch_bounds__(256) catchup_all_kernel(float* __restrict__ em
 template <int K>
 __global__ void __launch_bounds__(256) gather_fm_kernel(const int32_t* __restrict__ ids, int B, int dc, int dn,
                                                         const uint32_t* __restrict__ row_off,
-                                                        const float* __restrict__ emb_rec, int emb_stride,
-                                                        const float4* __restrict__ lin_rec, BatchPtrs bp,
+                                                        Table tb, BatchPtrs bp,
                                                         const float* __restrict__ num_emb,
                                                         const float* __restrict__ num_lin,
                                                         const float* __restrict__ bias, int use_linear, int use_mf,
@@ -461,8 +455,8 @@ __global__ void __launch_bounds__(256) gather_fm_kernel(const int32_t* __restric
                         if (use_linear && sub == 0) lin += __ldg(rp + K);
                     } else {
                         size_t row = (size_t)row_off[f] + (uint32_t)id;
-                        if (need_emb) e = __ldg(reinterpret_cast<const float4*>(emb_rec + row * emb_stride) + sub);
-                        if (use_linear && sub == 0) lin += __ldg(reinterpret_cast<const float*>(lin_rec + row));
+                        if (need_emb) e = __ldg(tab_w(tb, row) + sub);
+                        if (use_linear && sub == 0) lin += __ldg(reinterpret_cast<const float*>(tab_lin(tb, row)));
                     }
                 }
                 if (need_emb) {
@@ -601,15 +595,14 @@ __global__ void __launch_bounds__(256) piece_reduce_kernel(const uint32_t* __res
 // gradients straight from dE in sorted (= sample) order; hot rows sum their piece sums in order.
 // Then the sparse optimizer step for that row (Adam: rows were caught up to t-1 beforehand).
 template <int K>
-__global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restrict__ skeys,
+__global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restrict__ urow, const uint32_t* __restrict__ uval,
                                                          const uint32_t* __restrict__ svals,
                                                          const uint32_t* __restrict__ row_start,
                                                          const uint32_t* __restrict__ row_piece0,
                                                          const uint32_t* __restrict__ piece_start,
                                                          const SegCounts* __restrict__ cnt, GradSrc<K> src,
                                                          const float* __restrict__ piece_sum,
-                                                         float* __restrict__ emb_rec, int emb_slots,
-                                                         float4* __restrict__ lin_rec, OptDev od, OptDev ol,
+                                                         Table tb, int emb_slots, OptDev od, OptDev ol,
                                                          bool has_emb, bool has_lin, int step,
                                                          float* __restrict__ alpha_d, float* __restrict__ alpha_l,
                                                          float* __restrict__ gsum_out, int gsum_stride) {
@@ -621,7 +614,6 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
         alpha_l[step] = ol.alpha;
     }
     const uint32_t U = cnt->n_rows;
-    const int stride = (1 + emb_slots) * K;
     // row mapping: within one trip the lane groups of a warp take rows n_warps apart
     const uint32_t TG = gridDim.x * gpb, gid = blockIdx.x * gpb + threadIdx.x / LPR;
     const uint32_t gpw = 32 / LPR, n_warps = TG / gpw;
@@ -630,26 +622,24 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
         const uint32_t u = ubase + uoff;
         bool coop = false;
         const bool act = u < U;
-        uint32_t beg = 0, end = 0;
-        if (act) { beg = row_start[u]; end = row_start[u + 1]; }
-        uint32_t row = act ? skeys[beg] : 0u;
+        uint32_t beg = 0, end = 0, row = 0, v0 = 0xffffffffu;
+        if (act) { beg = row_start[u]; end = row_start[u + 1]; row = __ldg(urow + u); v0 = __ldg(uval + u); }
         // issue the table-record loads now: they only depend on the row id and overlap the gradient gather below
         float4 w = make_float4(0.f, 0.f, 0.f, 0.f), s1 = w, s2 = w, lr = w;
-        float4* base = nullptr;
         if (act && !gsum_out) {
             if (has_emb) {
-                base = reinterpret_cast<float4*>(emb_rec + (size_t)row * stride) + sub;
-                w = base[0];
-                if (emb_slots >= 1) s1 = base[LPR];
-                if (emb_slots >= 2) s2 = base[2 * LPR];
+                w = tab_w(tb, row)[sub];
+                if (emb_slots >= 1) s1 = tab_s1(tb, row)[sub];
+                if (emb_slots >= 2) s2 = tab_s2(tb, row)[sub];
             }
-            if (sub == 0) lr = lin_rec[row];
+            if (sub == 0) lr = *tab_lin(tb, row);
         }
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         float gl = 0.f;
         if (!act) {
         } else if (end - beg <= (uint32_t)DIRECT_T) {
-            for (uint32_t i = beg; i < end; i += 4) {
+            src.fetch(v0, sub, sub == 0, g, gl);      // first lookup of the row: its payload came with the row id
+            for (uint32_t i = beg + 1; i < end; i += 4) {
                 uint32_t v[4];
                 float4 t[4];
                 float tl[4];
@@ -742,14 +732,14 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
             sparse_apply(w.y, s1.y, s2.y, g.y, od);
             sparse_apply(w.z, s1.z, s2.z, g.z, od);
             sparse_apply(w.w, s1.w, s2.w, g.w, od);
-            base[0] = w;
-            if (emb_slots >= 1) base[LPR] = s1;
-            if (emb_slots >= 2) base[2 * LPR] = s2;
+            tab_w(tb, row)[sub] = w;
+            if (emb_slots >= 1) tab_s1(tb, row)[sub] = s1;
+            if (emb_slots >= 2) tab_s2(tb, row)[sub] = s2;
         }
         if (sub == 0) {
             if (has_lin) sparse_apply(lr.x, lr.y, lr.z, gl, ol);
             lr.w = __int_as_float(step);
-            lin_rec[row] = lr;
+            *tab_lin(tb, row) = lr;
         }
     }
 }
@@ -815,8 +805,7 @@ __global__ void iota_kernel(uint32_t* __restrict__ v, int64_t n) {
 // owner side: reply[i] = {emb w[K], lin w, pad} of local row recv_rows[i]
 template <int K>
 __global__ void __launch_bounds__(256) shard_serve_kernel(const uint32_t* __restrict__ recv_rows, int64_t n,
-                                                          const float* __restrict__ emb_rec, int emb_stride,
-                                                          const float4* __restrict__ lin_rec, bool has_emb, bool has_lin,
+                                                          Table tb, bool has_emb, bool has_lin,
                                                           float* __restrict__ reply, int reply_stride) {
     constexpr int LPR = K / 4;
     const int sub = threadIdx.x % LPR;
@@ -824,8 +813,8 @@ __global__ void __launch_bounds__(256) shard_serve_kernel(const uint32_t* __rest
     for (int64_t i = (int64_t)blockIdx.x * gpb + threadIdx.x / LPR; i < n; i += (int64_t)gridDim.x * gpb) {
         size_t row = recv_rows[i];
         float* rp = reply + (size_t)i * reply_stride;
-        float4 e = has_emb ? __ldg(reinterpret_cast<const float4*>(emb_rec + row * emb_stride) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 e = has_emb ? __ldg(tab_w(tb, row) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
         reinterpret_cast<float4*>(rp)[sub] = e;
-        if (sub == 0) rp[K] = has_lin ? __ldg(reinterpret_cast<const float*>(lin_rec + row)) : 0.f;
+        if (sub == 0) rp[K] = has_lin ? __ldg(reinterpret_cast<const float*>(tab_lin(tb, row))) : 0.f;
     }
 }
