@@ -254,12 +254,17 @@ __global__ void __launch_bounds__(256) small_mlp_bwd_input_kernel(
     const int tid = threadIdx.x;
     const int c0 = blockIdx.y * SM_BC;
     const int cw = min(SM_BC, D - c0);
-    constexpr int NQ = (SM_BC * (H1 / 4) + 255) / 256;     // (c, 4 j) items per thread
+    constexpr int TQ = (SM_BC / 4) * (H1 / 4);             // 4x4 register tiles of the dW0 slice
+    constexpr int NT = (TQ + 63) / 64;                     // tiles per thread (64 threads per sample quarter)
     constexpr int NH = SM_TB * (SM_BC / 4) / 256;          // h0 float4 per thread per tile (8)
     constexpr int ND = (SM_TB * (H1 / 4) + 255) / 256;     // dh1 float4 per thread per tile
-    float4 wacc[NQ];
+    float wacc[NT][4][4];
 #pragma unroll
-    for (int u = 0; u < NQ; ++u) wacc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < NT; ++u)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wacc[u][i][j] = 0.f;
     for (int q = tid; q < SM_BC * H1; q += 256) ws[q / H1][q % H1] = (q / H1) < cw ? W0[(size_t)c0 * H1 + q] : 0.f;
     const int ntiles = (B + SM_TB - 1) / SM_TB;
     const int KS = K / 4;                                  // float4 per S row
@@ -316,43 +321,62 @@ __global__ void __launch_bounds__(256) small_mlp_bwd_input_kernel(
         }
         __syncthreads();
         if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);   // in flight during (b) and (a)
-        // (b) dW0[c][j] += sum_s h0[s][c] * dh1[s][j]   (samples walked in order -> deterministic)
+        // (b) dW0[c][j] += sum_s h0[s][c] * dh1[s][j].  Register tiles of 4 columns x 4 units; the 128 samples of the
+        //     tile are split over 4 thread quarters (32 samples each, walked in order), the quarters are combined in a
+        //     fixed order at the end of the kernel -> deterministic.  16 FMA per 5 shared-memory loads.
+        {
+            const int qs = tid >> 6, t64 = tid & 63;
 #pragma unroll
-        for (int u = 0; u < NQ; ++u) {
-            int q = tid + u * 256;
-            if (q < SM_BC * (H1 / 4)) {
-                int c = q / (H1 / 4), j4 = (q % (H1 / 4)) * 4;
-                float4 a4 = wacc[u];
-#pragma unroll 8
-                for (int r = 0; r < SM_TB; ++r) {
-                    float a = hs[r][c];
-                    float4 d = *reinterpret_cast<const float4*>(&ds[r][j4]);
-                    a4.x = fmaf(a, d.x, a4.x); a4.y = fmaf(a, d.y, a4.y); a4.z = fmaf(a, d.z, a4.z); a4.w = fmaf(a, d.w, a4.w);
+            for (int u = 0; u < NT; ++u) {
+                const int tile = t64 + 64 * u;
+                if (tile < TQ) {
+                    const int c4 = (tile / (H1 / 4)) * 4, j4 = (tile % (H1 / 4)) * 4;
+                    float acc[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = wacc[u][i][j];
+#pragma unroll 4
+                    for (int r = qs * 32; r < qs * 32 + 32; ++r) {
+                        const float a0 = hs[r][c4], a1 = hs[r][c4 + 1], a2 = hs[r][c4 + 2], a3 = hs[r][c4 + 3];
+                        const float4 d = *reinterpret_cast<const float4*>(&ds[r][j4]);
+                        acc[0][0] = fmaf(a0, d.x, acc[0][0]); acc[0][1] = fmaf(a0, d.y, acc[0][1]); acc[0][2] = fmaf(a0, d.z, acc[0][2]); acc[0][3] = fmaf(a0, d.w, acc[0][3]);
+                        acc[1][0] = fmaf(a1, d.x, acc[1][0]); acc[1][1] = fmaf(a1, d.y, acc[1][1]); acc[1][2] = fmaf(a1, d.z, acc[1][2]); acc[1][3] = fmaf(a1, d.w, acc[1][3]);
+                        acc[2][0] = fmaf(a2, d.x, acc[2][0]); acc[2][1] = fmaf(a2, d.y, acc[2][1]); acc[2][2] = fmaf(a2, d.z, acc[2][2]); acc[2][3] = fmaf(a2, d.w, acc[2][3]);
+                        acc[3][0] = fmaf(a3, d.x, acc[3][0]); acc[3][1] = fmaf(a3, d.y, acc[3][1]); acc[3][2] = fmaf(a3, d.z, acc[3][2]); acc[3][3] = fmaf(a3, d.w, acc[3][3]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) wacc[u][i][j] = acc[i][j];
                 }
-                wacc[u] = a4;
             }
         }
         __syncthreads();
-        // (a) dE[s][c] = sum_j dh1[s][j] W0[c][j] + dz[s] * (S[s][c % K] - h0[s][c])   (in place in hs)
+        // (a) dE[s][c] = sum_j dh1[s][j] W0[c][j] + dz[s] * (S[s][c % K] - h0[s][c])   (in place in hs).
+        //     Thread = 2 samples (s, s+64) x 16 columns: every W0 row fetched from shared memory feeds 2 x H1 FMAs.
         {
-            const int s = tid & (SM_TB - 1), half = tid >> 7;
-            float d[H1];
+            const int sp = tid & 63, cg = tid >> 6;
+            float d0[H1], d1[H1];
 #pragma unroll
-            for (int j = 0; j < H1; ++j) d[j] = ds[s][j];
-            const float g = svec ? gs[s] : 0.f;
-            const float* srow = ss + s * (K + 1);
-            int kk = (c0 + half * (SM_BC / 2)) % K;
-#pragma unroll 4
-            for (int c = half * (SM_BC / 2); c < (half + 1) * (SM_BC / 2); ++c) {
-                float a = svec ? g * (srow[kk] - hs[s][c]) : 0.f;
+            for (int j = 0; j < H1; ++j) { d0[j] = ds[sp][j]; d1[j] = ds[sp + 64][j]; }
+            const float g0 = svec ? gs[sp] : 0.f, g1 = svec ? gs[sp + 64] : 0.f;
+            const float* srow0 = ss + sp * (K + 1);
+            const float* srow1 = ss + (sp + 64) * (K + 1);
+            int kk = (c0 + cg * (SM_BC / 4)) % K;
+#pragma unroll 2
+            for (int c = cg * (SM_BC / 4); c < (cg + 1) * (SM_BC / 4); ++c) {
+                float x0 = svec ? g0 * (srow0[kk] - hs[sp][c]) : 0.f;
+                float x1 = svec ? g1 * (srow1[kk] - hs[sp + 64][c]) : 0.f;
                 kk = (kk + 1 == K) ? 0 : kk + 1;
 #pragma unroll
                 for (int j4 = 0; j4 < H1 / 4; ++j4) {
-                    float4 w = *reinterpret_cast<const float4*>(&ws[c][j4 * 4]);
-                    a = fmaf(d[j4 * 4], w.x, a); a = fmaf(d[j4 * 4 + 1], w.y, a);
-                    a = fmaf(d[j4 * 4 + 2], w.z, a); a = fmaf(d[j4 * 4 + 3], w.w, a);
+                    const float4 w = *reinterpret_cast<const float4*>(&ws[c][j4 * 4]);
+                    x0 = fmaf(d0[j4 * 4], w.x, x0); x0 = fmaf(d0[j4 * 4 + 1], w.y, x0); x0 = fmaf(d0[j4 * 4 + 2], w.z, x0); x0 = fmaf(d0[j4 * 4 + 3], w.w, x0);
+                    x1 = fmaf(d1[j4 * 4], w.x, x1); x1 = fmaf(d1[j4 * 4 + 1], w.y, x1); x1 = fmaf(d1[j4 * 4 + 2], w.z, x1); x1 = fmaf(d1[j4 * 4 + 3], w.w, x1);
                 }
-                hs[s][c] = a;
+                hs[sp][c] = x0;
+                hs[sp + 64][c] = x1;
             }
         }
         __syncthreads();
@@ -362,12 +386,32 @@ __global__ void __launch_bounds__(256) small_mlp_bwd_input_kernel(
                 *reinterpret_cast<float4*>(dE + (size_t)(b0 + r) * D + c0 + cc) = make_float4(hs[r][cc], hs[r][cc + 1], hs[r][cc + 2], hs[r][cc + 3]);
         }
     }
+    // combine the four sample quarters in a fixed order (reusing the input tile as scratch) and emit the partial
+    __syncthreads();
+    {
+        float* scratch = &hs[0][0];                        // 4 * SM_BC * H1 floats <= SM_TB * (SM_BC + 1)
+        const int qs = tid >> 6, t64 = tid & 63;
 #pragma unroll
-    for (int u = 0; u < NQ; ++u) {
-        int q = tid + u * 256;
-        if (q < SM_BC * (H1 / 4)) {
-            int c = q / (H1 / 4), j4 = (q % (H1 / 4)) * 4;
-            if (c < cw) *reinterpret_cast<float4*>(w0_partial + (size_t)blockIdx.x * D * H1 + (size_t)(c0 + c) * H1 + j4) = wacc[u];
+        for (int u = 0; u < NT; ++u) {
+            const int tile = t64 + 64 * u;
+            if (tile < TQ) {
+                const int c4 = (tile / (H1 / 4)) * 4, j4 = (tile % (H1 / 4)) * 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<float4*>(scratch + (size_t)qs * SM_BC * H1 + (c4 + i) * H1 + j4) =
+                        make_float4(wacc[u][i][0], wacc[u][i][1], wacc[u][i][2], wacc[u][i][3]);
+            }
+        }
+        __syncthreads();
+        for (int q = tid; q < SM_BC * (H1 / 4); q += 256) {
+            const int c = q / (H1 / 4), j4 = (q % (H1 / 4)) * 4;
+            float4 a = *reinterpret_cast<const float4*>(scratch + c * H1 + j4);
+#pragma unroll
+            for (int z = 1; z < 4; ++z) {
+                const float4 t = *reinterpret_cast<const float4*>(scratch + (size_t)z * SM_BC * H1 + c * H1 + j4);
+                a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+            }
+            if (c < cw) *reinterpret_cast<float4*>(w0_partial + (size_t)blockIdx.x * D * H1 + (size_t)(c0 + c) * H1 + j4) = a;
         }
     }
 }
