@@ -94,7 +94,7 @@ struct dfm_handle {
     float* act[DFM_MAX_HIDDEN + 1] = {nullptr};
     float* dact[DFM_MAX_HIDDEN + 1] = {nullptr};
     float* splitk = nullptr; int splits = 1, k_chunk = 0;
-    float* colpart = nullptr; int rows_per_chunk = 512;
+    float* colpart = nullptr; int rows_per_chunk = 512; int num_rows_per_chunk = 128;   // numeric-gradient chunks are smaller: more CTAs
     float* head_part = nullptr; int head_blocks = 0;
     bool fused_head = false; float* head_gpart = nullptr; int fused_head_blocks = 0;
     bool tc_mlp = false; float* tc_w = nullptr; int64_t tc_off[DFM_MAX_HIDDEN] = {0}; int tc_nz[DFM_MAX_HIDDEN] = {0};
@@ -424,7 +424,8 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     }
     if (dalloc(h, &h->splitk, splitk_elems)) return DFM_ERR_CUDA;
     const int64_t chunks = (Bm + h->rows_per_chunk - 1) / h->rows_per_chunk;
-    if (dalloc(h, &h->colpart, (size_t)chunks * std::max<int64_t>(max_n, (int64_t)h->dn * (K + 1)))) return DFM_ERR_CUDA;
+    const int64_t nchunks = (Bm + h->num_rows_per_chunk - 1) / h->num_rows_per_chunk;
+    if (dalloc(h, &h->colpart, std::max<size_t>((size_t)chunks * max_n, (size_t)nchunks * h->dn * (K + 1)))) return DFM_ERR_CUDA;
     h->head_blocks = (int)std::min<int64_t>(h->sm_count * 8, std::max<int64_t>(1, (Bm + 7) / 8));
     if (dalloc(h, &h->head_part, (size_t)h->head_blocks * 2)) return DFM_ERR_CUDA;
     // fused small-MLP path: every hidden layer <= 32 wide (not a real GEMM)
@@ -487,7 +488,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
         CK(cudaMallocHost(&s.h_loss, 64));
     }
     for (auto& e : h->ph_ev) CK(cudaEventCreate(&e));
-    CK(cudaFuncSetAttribute(numeric_grad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->rows_per_chunk * (DFM_MAX_NUM + 1) * 4));
+    CK(cudaFuncSetAttribute(numeric_grad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->num_rows_per_chunk * (DFM_MAX_NUM + 1) * 4));
 
     // optimizer slot initial values (Adagrad / FTRL accumulators start at init_acc)
     auto init_acc = [&](const dfm_optimizer& o) { return (o.kind == DFM_OPT_ADAGRAD || o.kind == DFM_OPT_FTRL || o.kind == DFM_OPT_RMSPROP) ? o.init_acc : 0.f; };
@@ -960,8 +961,8 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
     // numeric-feature gradients
     if (h->dn) {
         const DenseT* ne = find_dense(h, "num_emb"); const DenseT* nl = find_dense(h, "num_lin");
-        const int chunks = (int)cdiv(B, h->rows_per_chunk), total = h->dn * K + h->dn;
-        numeric_grad_partial_kernel<<<chunks, 256, (size_t)h->rows_per_chunk * (h->dn + 1) * 4, st>>>(bp, h->need_emb ? h->dE : nullptr, dK, dc, h->dn, K, h->dz, B, h->rows_per_chunk, h->colpart);
+        const int chunks = (int)cdiv(B, h->num_rows_per_chunk), total = h->dn * K + h->dn;
+        numeric_grad_partial_kernel<<<chunks, 256, (size_t)h->num_rows_per_chunk * (h->dn + 1) * 4, st>>>(bp, h->need_emb ? h->dE : nullptr, dK, dc, h->dn, K, h->dz, B, h->num_rows_per_chunk, h->colpart);
         h->launches++;
         if (ne) { reduce_partials_kernel<<<cdiv(h->dn * K, 256), 256, 0, st>>>(h->colpart, chunks, (size_t)total, h->dn * K, h->dg + ne->off); h->launches++; }
         if (nl) { reduce_partials_kernel<<<1, 256, 0, st>>>(h->colpart + h->dn * K, chunks, (size_t)total, h->dn, h->dg + nl->off); h->launches++; }

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256) numeric_grad_partial_kernel(BatchPtrs bp,
             const int j = o / K;
             if (dE) {
                 const float* p = dE + (size_t)r0 * dK + (size_t)dc * K + o;
-#pragma unroll 8
+#pragma unroll 16
                 for (int r = 0; r < nr; ++r) s = fmaf(xs[r * ldx + j], __ldg(p + (size_t)r * dK), s);
             }
         } else {
