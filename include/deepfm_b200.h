@@ -65,6 +65,11 @@ typedef struct {
     const char* const* vocab;         /* vocab: NUL-terminated strings */
     int32_t            vocab_size;
     int32_t            num_oov;       /* vocab: OOV hash buckets appended after the list */
+    /* multivalent ("multi-hot") column: every sample carries `width` value slots (raw column = [B, width]
+     * row-major; int32 slots padded with -1, string slots with ''); the embedding of the field is the MEAN of
+     * the present slots (embedding_column combiner='mean'), the linear term their SUM (linear_model
+     * sparse_combiner='sum'); an empty bag contributes zeros.  0 or 1 = single-valued. */
+    int32_t            width;
 } dfm_column;
 
 /* tf.train.*Optimizer(learning_rate) hyper-parameters (trainers/model_utils.py:57-66; TF defaults) */
@@ -130,8 +135,8 @@ int dfm_get_tensor(dfm_handle* h, const char* name, int64_t row_begin, int64_t n
  * dense kernels glorot-uniform, linear + biases zero.  Own counter-based generator. */
 int dfm_init_random(dfm_handle* h, uint64_t seed);
 
-/* K1 alone: feature-column transforms (hash / bucketize / vocab / identity) -> ids [B, n_cat]
- * int32, -1 = empty bag.  Device pointers.  Replaces the _transform_feature calls under
+/* K1 alone: feature-column transforms (hash / bucketize / vocab / identity) -> ids [B, n_slots]
+ * int32 (n_slots = sum of the column widths = n_cat when every column is single-valued), -1 = empty slot.  Device pointers.  Replaces the _transform_feature calls under
  * tf.feature_column.linear_model / input_layer (trainers/deep_fm.py:39,54). */
 int dfm_transform(dfm_handle* h, const dfm_raw_batch* dev_batch, int32_t* ids_out_dev, void* stream);
 
@@ -187,6 +192,7 @@ float dfm_phase_ms(dfm_handle* h, const char* phase);
  *   dfm_shard_apply             owner side: ordered reduction of grecv_dev[n_recv, K+4] by row + sparse
  *                               optimizer; dense optimizer with the all-reduced dense gradients; step += 1 */
 int dfm_shard_row_width(const dfm_handle* h);
+int dfm_num_slots(const dfm_handle* h);      /* value slots per sample = sum of the column widths */
 int64_t dfm_dense_size(const dfm_handle* h);
 int dfm_shard_requests(dfm_handle* h, const dfm_raw_batch* dev_batch, uint32_t* req_rows_out_dev, int32_t* counts_host, void* stream);
 int dfm_shard_serve(dfm_handle* h, const uint32_t* recv_rows_dev, int64_t n_recv, float* reply_dev, void* stream);

@@ -87,6 +87,12 @@ class OracleDeepFM:
         self.off = np.concatenate([[0], np.cumsum(self.nb)]).astype(np.int64)
         self.R = int(self.off[-1])
         self.dc, self.dn = len(self.cat), len(self.num)
+        # multivalent columns: slot -> field; embedding of a field = mean of its present slots, linear = sum
+        self.width = [int(s.get("width", 1)) for s in self.cat]
+        self.slot_field = np.repeat(np.arange(self.dc), self.width)
+        self.n_slots = int(self.slot_field.shape[0])
+        self.P = torch.zeros(self.n_slots, self.dc, dtype=dtype)     # slot -> field pooling matrix
+        self.P[torch.arange(self.n_slots), torch.as_tensor(self.slot_field)] = 1
         self.vars = {}
         group = {"lin": "linear", "num_lin": "linear", "bias": "linear"}
         for name, val in weights.items():
@@ -115,7 +121,7 @@ class OracleDeepFM:
         """ids [B,dc] int (-1 empty) -> global row index [B,dc] (clamped) and validity mask."""
         ids = torch.as_tensor(np.asarray(ids), dtype=torch.int64)
         valid = ids >= 0
-        rows = ids.clamp(min=0) + torch.as_tensor(self.off[:-1])[None, :]
+        rows = ids.clamp(min=0) + torch.as_tensor(self.off[:-1][self.slot_field])[None, :]
         return rows, valid
 
     def forward(self, ids, x=None, keep=False, train=False):
@@ -127,13 +133,17 @@ class OracleDeepFM:
         x = torch.zeros(B, 0, dtype=dt) if x is None else torch.as_tensor(np.asarray(x), dtype=dt)
         z = torch.zeros(B, dtype=dt)
         cache = dict(rows=rows, valid=valid, x=x)
+        cnt = vm @ self.P                                     # [B, dc] present slots per field
+        inv = torch.where(cnt > 0, 1.0 / cnt.clamp(min=1), torch.zeros_like(cnt))
+        cache["inv"] = inv
         if self.use_linear:
             z_lin = (W["lin"][rows] * vm).sum(1)
             if self.dn:
                 z_lin = z_lin + x @ W["num_lin"]
             z = z + (z_lin + W["bias"][0])
         if self.use_mf or self.use_dnn:
-            E = W["emb"][rows] * vm[:, :, None]                       # [B,dc,k]
+            Es = W["emb"][rows] * vm[:, :, None]                      # [B,n_slots,k]
+            E = torch.einsum("bsk,sf->bfk", Es, self.P) * inv[:, :, None]   # mean over the present slots -> [B,dc,k]
             if self.dn:
                 E = torch.cat([E, x[:, :, None] * W["num_emb"][None]], 1)   # [B,d,k]
             cache["E"] = E
@@ -174,7 +184,7 @@ class OracleDeepFM:
         rows, valid, x = c["rows"], c["valid"], c["x"]
         flat_rows = rows[valid]
         if self.use_linear:
-            g["lin"] = ("sparse", flat_rows, dz[:, None].expand(B, self.dc)[valid])
+            g["lin"] = ("sparse", flat_rows, dz[:, None].expand(B, self.n_slots)[valid])
             g["bias"] = dz.sum().reshape(1)
             if self.dn:
                 g["num_lin"] = x.t() @ dz
@@ -197,7 +207,8 @@ class OracleDeepFM:
                     g["b%d" % i] = dh.sum(0)
                     dh = dh @ W["W%d" % i].t()
                 dE = dE + dh.reshape(E.shape)
-            g["emb"] = ("sparse", flat_rows, dE[:, :self.dc][valid])
+            dEs = (dE[:, :self.dc] * c["inv"][:, :, None])[:, self.slot_field]      # every present slot gets dE_field / count
+            g["emb"] = ("sparse", flat_rows, dEs[valid])
             if self.dn:
                 g["num_emb"] = (x[:, :, None] * dE[:, self.dc:]).sum(0)
         return loss, z, g

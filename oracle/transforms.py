@@ -117,8 +117,21 @@ def transform_column(spec, features, use_c=True):
 
 
 def transform(cat_specs, features, use_c=True):
-    """-> ids [B, d_c] int32 in the order of cat_specs (caller passes model order)."""
-    return np.stack([transform_column(s, features, use_c) for s in cat_specs], axis=1)
+    """-> ids [B, n_slots] int32 in the order of cat_specs (caller passes model order).  A multivalent column
+    (spec["width"] = M > 1, raw feature [B, M] with -1 / '' padding) contributes M consecutive slots."""
+    cols = []
+    for s in cat_specs:
+        w = int(s.get("width", 1))
+        ids = transform_column(s, features if w == 1 else {s.get("source", s["name"]): _flat(features[s.get("source", s["name"])])}, use_c)
+        cols.append(ids.reshape(-1, w))
+    return np.concatenate(cols, axis=1)
+
+
+def _flat(raw):
+    if isinstance(raw, tuple):
+        return raw
+    a = np.asarray(raw)
+    return a.reshape(-1)
 
 
 def num_buckets(spec):

@@ -21,7 +21,7 @@ LOSS_RED = {"mean": 0, "sum": 1}
 class Column(C.Structure):
     _fields_ = [("name", C.c_char_p), ("kind", C.c_int32), ("dtype", C.c_int32), ("num_buckets", C.c_int64),
                 ("boundaries", C.POINTER(C.c_float)), ("n_boundaries", C.c_int32),
-                ("vocab", C.POINTER(C.c_char_p)), ("vocab_size", C.c_int32), ("num_oov", C.c_int32)]
+                ("vocab", C.POINTER(C.c_char_p)), ("vocab_size", C.c_int32), ("num_oov", C.c_int32), ("width", C.c_int32)]
 
 
 class Optimizer(C.Structure):
@@ -67,6 +67,7 @@ _SIGS = {
     "dfm_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "dfm_phase_ms": (C.c_float, [C.c_void_p, C.c_char_p]),
     "dfm_shard_row_width": (C.c_int, [C.c_void_p]),
+    "dfm_num_slots": (C.c_int, [C.c_void_p]),
     "dfm_dense_size": (C.c_int64, [C.c_void_p]),
     "dfm_shard_requests": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "dfm_shard_serve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

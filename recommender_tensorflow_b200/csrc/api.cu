@@ -59,6 +59,9 @@ struct HostStage {          // one in-flight host batch (double buffered)
 
 struct dfm_handle {
     int dc = 0, dn = 0, K = 0, L = 0;
+    int dcs = 0;                 // value slots per sample = sum of column widths (== dc without multivalent columns)
+    bool has_bags = false;
+    int32_t *d_slot_col = nullptr, *d_slot_j = nullptr, *d_field_slot0 = nullptr; float* inv_cnt = nullptr;
     int hidden[DFM_MAX_HIDDEN] = {0};
     int use_linear = 1, use_mf = 1, use_dnn = 1, need_emb = 1, loss_red = 0;
     dfm_optimizer od{}, ol{};
@@ -201,7 +204,7 @@ static void free_all(dfm_handle* h) {
     cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, h->d_row_off, h->tb.rec, h->dw,
                     h->ds1, h->ds2, h->dg, h->ids, h->h0, h->s, h->zacc, h->logits, h->dz, h->dE, h->splitk, h->colpart, h->head_part,
-                    h->d_loss, h->d_dzsum, h->d_err, h->alpha_d, h->alpha_l, h->up_partial, h->w0_partial, h->tc_w, h->head_gpart, h->uidx,
+                    h->d_loss, h->d_dzsum, h->d_err, h->alpha_d, h->alpha_l, h->up_partial, h->w0_partial, h->tc_w, h->head_gpart, h->d_slot_col, h->d_slot_j, h->d_field_slot0, h->inv_cnt, h->uidx,
                     h->req_rows, h->d_counts};
     for (void* p : ptrs) if (p) cudaFree(p);
     free_ws(h->ws);
@@ -263,11 +266,16 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     std::vector<uint8_t> voc_bytes;
     std::vector<int32_t> voc_offs;
     h->row_off.assign(h->dc + 1, 0);
+    std::vector<int32_t> slot_col, slot_j, field_slot0;
     uint64_t R = 0;
     for (int f = 0; f < h->dc; ++f) {
         const dfm_column& c = cfg->cat[f];
         ColDev d{};
         d.kind = c.kind; d.dtype = c.dtype;
+        d.width = std::max(1, c.width);
+        if (d.width > 1) h->has_bags = true;
+        for (int j = 0; j < d.width; ++j) { slot_col.push_back(f); slot_j.push_back(j); }
+        field_slot0.push_back((int32_t)slot_col.size() - d.width);
         uint64_t nb = 0;
         switch (c.kind) {
             case DFM_COL_HASH:
@@ -309,6 +317,17 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     if (R >= 0xfffffff0ull) FAIL(DFM_ERR_UNSUPPORTED, "more than 2^32 table rows on one device");
     h->row_off[h->dc] = (uint32_t)R;
     h->R = R;
+    field_slot0.push_back((int32_t)slot_col.size());
+    h->dcs = (int)slot_col.size();
+    if (h->dcs > 4 * DFM_MAX_CAT) FAIL(DFM_ERR_UNSUPPORTED, "too many value slots (sum of column widths)");
+    if (dalloc(h, &h->d_slot_col, slot_col.size())) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->d_slot_j, slot_j.size())) return DFM_ERR_CUDA;
+    if (dalloc(h, &h->d_field_slot0, field_slot0.size())) return DFM_ERR_CUDA;
+    if (!slot_col.empty()) {
+        CK(cudaMemcpy(h->d_slot_col, slot_col.data(), slot_col.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_slot_j, slot_j.data(), slot_j.size() * 4, cudaMemcpyHostToDevice));
+    }
+    CK(cudaMemcpy(h->d_field_slot0, field_slot0.data(), field_slot0.size() * 4, cudaMemcpyHostToDevice));
     h->Rl = (uint32_t)((R + h->world - 1) / h->world);
     h->R_loc = h->world > 1 ? (R > (uint64_t)h->rank ? (R - h->rank + h->world - 1) / h->world : 0) : R;
     if ((uint64_t)h->Rl * h->world >= 0xfffffff0ull) FAIL(DFM_ERR_UNSUPPORTED, "sharded key space exceeds 32 bits");
@@ -369,7 +388,9 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     }
 
     // ---- workspaces
-    const int64_t Bm = h->max_batch, n = Bm * std::max(h->dc, 1);
+    const int64_t Bm = h->max_batch, n = Bm * std::max(h->dcs, 1);
+    if (h->has_bags && dalloc(h, &h->inv_cnt, (size_t)Bm * h->dc)) return DFM_ERR_CUDA;
+    CK(cudaFuncSetAttribute(transform_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 4 * DFM_MAX_CAT * 4));
     if (n >= (1ll << 31)) FAIL(DFM_ERR_UNSUPPORTED, "max_batch * n_cat must be < 2^31");
     if (dalloc(h, &h->ids, n)) return DFM_ERR_CUDA;
     if (alloc_ws(h, h->ws, n, K)) return DFM_ERR_CUDA;
@@ -664,8 +685,9 @@ struct Phase {
 template <int K>
 static void launch_transform(dfm_handle* h, const BatchPtrs& bp, int B, bool with_keys, int32_t* ids_out, cudaStream_t st) {
     if (h->dc == 0) return;
-    transform_kernel<32><<<cdiv(B, 32), 256, (size_t)32 * h->dc * 4, st>>>(
-        bp, h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, B, h->dc, h->d_row_off, (uint32_t)h->R, ids_out,
+    transform_kernel<32><<<cdiv(B, 32), 256, (size_t)32 * h->dcs * 4, st>>>(
+        bp, h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, B, h->dcs, h->has_bags ? h->d_slot_col : nullptr,
+        h->has_bags ? h->d_slot_j : nullptr, h->d_row_off, (uint32_t)h->R, ids_out,
         with_keys ? h->ws.keys[0] : nullptr, with_keys ? h->ws.vals[0] : nullptr, h->d_err);
     h->launches++;
 }
@@ -679,7 +701,9 @@ static void launch_gather(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_
         if (dt.name == "bias") bias = h->dw + dt.off;
     }
     unsigned grid = std::min<unsigned>(cdiv(B, 8), (unsigned)h->sm_count * 16);
-    gather_fm_kernel<K><<<grid, 256, 0, st>>>(h->ids, B, h->dc, h->dn, h->d_row_off, h->tb, bp,
+    auto kern = h->has_bags ? gather_fm_kernel<K, true> : gather_fm_kernel<K, false>;
+    kern<<<grid, 256, 0, st>>>(h->ids, B, h->dc, h->dn, h->dcs, h->has_bags ? h->d_field_slot0 : nullptr,
+                                              h->has_bags ? h->inv_cnt : nullptr, h->d_row_off, h->tb, bp,
                                               num_emb, num_lin, bias, h->use_linear, h->use_mf, h->need_emb, h->h0, h->s, h->zacc,
                                               rowbuf ? h->uidx : nullptr, rowbuf, K + 4);
     h->launches++;
@@ -972,17 +996,17 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
 }
 
 // deterministic segmented reduction of the sparse gradients (+ optimizer, or gradient rows out when gsum != nullptr)
-template <int K>
-static int sparse_update(dfm_handle* h, SegWS& ws, int64_t n, const GradSrc<K>& src, const OptDev& od, const OptDev& ol, int64_t t,
+template <int K, bool BAGS>
+static int sparse_update(dfm_handle* h, SegWS& ws, int64_t n, const GradSrc<K, BAGS>& src, const OptDev& od, const OptDev& ol, int64_t t,
                          float* gsum, cudaStream_t st, Phase* ph) {
     const unsigned row_grid = (unsigned)h->sm_count * 8;
     if (n > 0) {
         hot_pieces_kernel<<<row_grid, 256, 0, st>>>(ws.row_start, ws.row_piece0, ws.seg_cnt, ws.hot_list);
-        piece_reduce_kernel<K><<<row_grid, 256, 0, st>>>(ws.svals(), ws.piece_start, ws.hot_list, ws.seg_cnt, src, ws.piece_sum);
+        piece_reduce_kernel<K, BAGS><<<row_grid, 256, 0, st>>>(ws.svals(), ws.piece_start, ws.hot_list, ws.seg_cnt, src, ws.piece_sum);
         h->launches += 2;
     }
     if (ph) ph->next();
-    row_update_kernel<K><<<n > 0 ? row_grid : 1, 256, 0, st>>>(ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0, ws.piece_start, ws.seg_cnt, src,
+    row_update_kernel<K, BAGS><<<n > 0 ? row_grid : 1, 256, 0, st>>>(ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0, ws.piece_start, ws.seg_cnt, src,
                                                                ws.piece_sum, h->tb, h->emb_slots, od, ol, (bool)h->need_emb,
                                                                (bool)h->use_linear, (int)t, h->alpha_d, h->alpha_l, gsum, K + 4);
     h->launches++;
@@ -1021,7 +1045,7 @@ template <int K>
 static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out, float* logits_out, cudaStream_t st) {
     if (h->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "row-sharded handle: drive the step with the dfm_shard_* entry points");
     const int dc = h->dc, d = dc + h->dn, dK = d * K;
-    const int64_t n = (int64_t)B * dc;
+    const int64_t n = (int64_t)B * h->dcs;
     const int64_t t = h->step + 1;
     int rc = ensure_alpha(h, t);
     if (rc) return rc;
@@ -1036,8 +1060,14 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
     const float scale = h->loss_red == DFM_LOSS_MEAN ? 1.0f / (float)B : 1.0f;
     if ((rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, &ph))) return rc;
     if ((rc = tower_backward<K>(h, bp, B, scale, loss_out, st, &ph))) return rc;
-    GradSrc<K> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0};
-    if ((rc = sparse_update<K>(h, h->ws, n, src, so.od, so.ol, t, nullptr, st, &ph))) return rc;
+    if (h->has_bags) {
+        GradSrc<K, true> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0, h->dcs, h->d_slot_col, h->inv_cnt};
+        rc = sparse_update<K, true>(h, h->ws, n, src, so.od, so.ol, t, nullptr, st, &ph);
+    } else {
+        GradSrc<K, false> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0, h->dcs, nullptr, nullptr};
+        rc = sparse_update<K, false>(h, h->ws, n, src, so.od, so.ol, t, nullptr, st, &ph);
+    }
+    if (rc) return rc;
     if (h->n_dense) {
         dense_apply_kernel<<<cdiv(h->n_dense, 256), 256, 0, st>>>(h->dw, h->ds1, h->ds2, h->dg, h->n_deep, h->n_dense, so.od, so.ol);
         h->launches++;
@@ -1167,11 +1197,12 @@ extern "C" float dfm_phase_ms(dfm_handle* h, const char* phase) {
 // calls below are the per-rank compute of one sharded step; the host performs the collectives
 // between them (all_to_all of row ids, rows and gradient rows; all_reduce of dense gradients).
 extern "C" int dfm_shard_row_width(const dfm_handle* h) { return h ? h->K + 4 : -1; }
+extern "C" int dfm_num_slots(const dfm_handle* h) { return h ? h->dcs : -1; }
 extern "C" int64_t dfm_dense_size(const dfm_handle* h) { return h ? h->n_dense : -1; }
 
 template <int K>
 static int shard_requests_impl(dfm_handle* h, const BatchPtrs& bp, int B, uint32_t* req_rows_out, int32_t* counts_host, cudaStream_t st) {
-    const int64_t n = (int64_t)B * h->dc;
+    const int64_t n = (int64_t)B * h->dcs;
     const int64_t t = h->step + 1;
     int rc = ensure_alpha(h, t);
     if (rc) return rc;
@@ -1249,15 +1280,21 @@ template <int K>
 static int shard_fb_impl(dfm_handle* h, const BatchPtrs& bp, int B, const float* rowbuf, int64_t global_batch, float* loss_out,
                          float* logits_out, float* gsum, float* dense_grad, cudaStream_t st) {
     const int dc = h->dc, dK = (dc + h->dn) * K;
-    const int64_t n = (int64_t)B * dc, t = h->step + 1;
+    const int64_t n = (int64_t)B * h->dcs, t = h->step + 1;
     const int64_t l0 = h->launches;
     const StepOpts so = step_opts(h);
     const float scale = h->loss_red == DFM_LOSS_MEAN ? 1.0f / (float)global_batch : 1.0f;
     int rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, nullptr, rowbuf);
     if (rc) return rc;
     if ((rc = tower_backward<K>(h, bp, B, scale, loss_out, st, nullptr))) return rc;
-    GradSrc<K> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0};
-    if ((rc = sparse_update<K>(h, h->ws, n, src, so.od, so.ol, t, gsum, st, nullptr))) return rc;
+    if (h->has_bags) {
+        GradSrc<K, true> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0, h->dcs, h->d_slot_col, h->inv_cnt};
+        rc = sparse_update<K, true>(h, h->ws, n, src, so.od, so.ol, t, gsum, st, nullptr);
+    } else {
+        GradSrc<K, false> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0, h->dcs, nullptr, nullptr};
+        rc = sparse_update<K, false>(h, h->ws, n, src, so.od, so.ol, t, gsum, st, nullptr);
+    }
+    if (rc) return rc;
     if (h->n_dense && dense_grad) CK(cudaMemcpyAsync(dense_grad, h->dg, (size_t)h->n_dense * 4, cudaMemcpyDeviceToDevice, st));
     h->last_step_launches += h->launches - l0;
     return DFM_OK;
@@ -1282,8 +1319,8 @@ static int shard_apply_impl(dfm_handle* h, const float* grecv, const float* dens
     const int64_t t = h->step + 1;
     const int64_t l0 = h->launches;
     const StepOpts so = step_opts(h);
-    GradSrc<K> src{nullptr, nullptr, 1, 0, grecv, K + 4};
-    int rc = sparse_update<K>(h, h->ws_own, h->shard_n_recv, src, so.od, so.ol, t, nullptr, st, nullptr);
+    GradSrc<K, false> src{nullptr, nullptr, 1, 0, grecv, K + 4, 1, nullptr, nullptr};
+    int rc = sparse_update<K, false>(h, h->ws_own, h->shard_n_recv, src, so.od, so.ol, t, nullptr, st, nullptr);
     if (rc) return rc;
     if (h->n_dense) {
         dense_apply_kernel<<<cdiv(h->n_dense, 256), 256, 0, st>>>(h->dw, h->ds1, h->ds2, dense_grad ? dense_grad : h->dg, h->n_deep, h->n_dense, so.od, so.ol);
@@ -1314,13 +1351,14 @@ static int stage_batch(dfm_handle* h, const dfm_raw_batch* b, HostStage& sg, boo
     const int B = b->batch_size;
     out = BatchPtrs{};
     for (int f = 0; f < h->dc; ++f) {
+        const size_t nv = (size_t)B * h->cols[f].width;      // values of this column in the batch (multivalent: B * width)
         if (h->cols[f].dtype == DFM_STRING) {
             const int32_t* off = b->cat_offsets[f];
-            segs.push_back({reinterpret_cast<const uint8_t*>(off), (size_t)(B + 1) * 4, reinterpret_cast<const void**>(&out.off[f])});
-            size_t nbytes = (size_t)off[B];
+            segs.push_back({reinterpret_cast<const uint8_t*>(off), (nv + 1) * 4, reinterpret_cast<const void**>(&out.off[f])});
+            size_t nbytes = (size_t)off[nv];
             segs.push_back({reinterpret_cast<const uint8_t*>(b->cat_data[f]), std::max<size_t>(nbytes, 1), &out.cat[f]});
         } else {
-            segs.push_back({reinterpret_cast<const uint8_t*>(b->cat_data[f]), (size_t)B * 4, &out.cat[f]});
+            segs.push_back({reinterpret_cast<const uint8_t*>(b->cat_data[f]), nv * 4, &out.cat[f]});
         }
     }
     for (int j = 0; j < h->dn; ++j)

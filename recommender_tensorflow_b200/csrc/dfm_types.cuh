@@ -8,7 +8,7 @@ struct ColDev {
     int32_t  kind, dtype;
     uint64_t nb;            // bucket count used for the modulo (hash) / range check (identity)
     int32_t  bnd_off, bnd_cnt;
-    int32_t  voc_off, voc_cnt, num_oov, pad;
+    int32_t  voc_off, voc_cnt, num_oov, width;   // width: value slots per sample (multivalent column), >= 1
 };
 
 // raw batch as kernel parameter (pointer tables by value: no H2D copy of pointer arrays)

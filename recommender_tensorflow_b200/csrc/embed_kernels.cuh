@@ -4,6 +4,8 @@
 #include "dfm_types.cuh"
 #include "farmhash.cuh"
 
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
 // =============================================================================================
 // optimizer arithmetic, in the float32 op order of the TF-1.12 kernels
 // =============================================================================================
@@ -183,51 +185,43 @@ __device__ __forceinline__ int32_t transform_one(const BatchPtrs& bp, const ColD
     }
 }
 
-// One block = TILE consecutive samples x all columns.  Phase 1: work item w -> (column w / TILE, sample w % TILE),
-// so a warp reads 32 consecutive elements of ONE column (coalesced, uniform column kind) and the columns of a
-// sample are transformed in parallel by different warps (a hashed string column costs ~100x an identity column;
-// one thread per sample serialised all of them).  Phase 2 writes ids / keys / payload sample-major.
+// One block = TILE consecutive samples x all value slots (a single-valued column has one slot, a multivalent
+// column `width`).  Phase 1: work item w -> (slot w / TILE, sample w % TILE), so a warp reads 32 consecutive
+// samples of ONE column (coalesced for single-valued columns, uniform column kind) and the columns of a sample are
+// transformed in parallel by different warps (a hashed string column costs ~100x an identity column).
+// Phase 2 writes ids / keys / payload sample-major: ids [B, n_slots], payload = b * n_slots + slot.
 template <int TILE>
 __global__ void __launch_bounds__(256) transform_kernel(BatchPtrs bp, const ColDev* __restrict__ cols,
                                                         const float* __restrict__ bounds,
                                                         const uint8_t* __restrict__ voc_bytes,
-                                                        const int32_t* __restrict__ voc_offs, int B, int dc,
+                                                        const int32_t* __restrict__ voc_offs, int B, int n_slots,
+                                                        const int32_t* __restrict__ slot_col, const int32_t* __restrict__ slot_j,
                                                         const uint32_t* __restrict__ row_off, uint32_t R,
                                                         int32_t* __restrict__ ids, uint32_t* __restrict__ keys,
                                                         uint32_t* __restrict__ vals, int* err) {
-    extern __shared__ int32_t sid[];  // [TILE][dc]
+    extern __shared__ int32_t sid[];  // [TILE][n_slots]
     const int b0 = blockIdx.x * TILE;
     const int nb = min(TILE, B - b0);
-    for (int w = threadIdx.x; w < TILE * dc; w += blockDim.x) {
-        const int f = w / TILE, t = w - f * TILE;
+    for (int w = threadIdx.x; w < TILE * n_slots; w += blockDim.x) {
+        const int slot = w / TILE, t = w - slot * TILE;
         if (t < nb) {
+            const int f = slot_col ? slot_col[slot] : slot;      // null slot tables: every column single-valued
             ColDev c = cols[f];
-            sid[t * dc + f] = transform_one(bp, c, f, b0 + t, bounds, voc_bytes, voc_offs, err);
+            const int vi = slot_col ? (b0 + t) * c.width + slot_j[slot] : b0 + t;
+            sid[t * n_slots + slot] = transform_one(bp, c, f, vi, bounds, voc_bytes, voc_offs, err);
         }
     }
     __syncthreads();
-    const int nloc = nb * dc;
-    const int64_t g0 = (int64_t)b0 * dc;
+    const int nloc = nb * n_slots;
+    const int64_t g0 = (int64_t)b0 * n_slots;
     for (int w = threadIdx.x; w < nloc; w += blockDim.x) {
         int32_t id = sid[w];
-        int f = w % dc;
+        int slot = w % n_slots;
         ids[g0 + w] = id;
         if (keys) {
-            keys[g0 + w] = id >= 0 ? row_off[f] + (uint32_t)id : R;
+            keys[g0 + w] = id >= 0 ? row_off[slot_col ? slot_col[slot] : slot] + (uint32_t)id : R;
             vals[g0 + w] = (uint32_t)(g0 + w);
         }
-    }
-}
-
-// keys/payload from precomputed ids (used when the caller supplies ids directly)
-__global__ void keys_from_ids_kernel(const int32_t* __restrict__ ids, int64_t n, int dc,
-                                     const uint32_t* __restrict__ row_off, uint32_t R,
-                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        int32_t id = ids[i];
-        keys[i] = id >= 0 ? row_off[i % dc] + (uint32_t)id : R;
-        vals[i] = (uint32_t)i;
     }
 }
 
@@ -421,8 +415,10 @@ __global__ void __launch_bounds__(256) catchup_all_kernel(Table tb,
 //   trainers/deep_fm.py:39     linear_model       -> zacc += sum_f w_f[id] + sum_j x_j wn_j + bias
 //   trainers/deep_fm.py:52-73  input_layer        -> h0[b, f*K..]
 //   trainers/deep_fm.py:79-87  FM                 -> zacc += 0.5 * sum_k((sum_f E)^2 - sum_f E^2)
-template <int K>
-__global__ void __launch_bounds__(256) gather_fm_kernel(const int32_t* __restrict__ ids, int B, int dc, int dn,
+template <int K, bool BAGS>
+__global__ void __launch_bounds__(256) gather_fm_kernel(const int32_t* __restrict__ ids, int B, int dc, int dn, int n_slots,
+                                                        const int32_t* __restrict__ field_slot0 /*[dc+1] or null: 1 slot per field*/,
+                                                        float* __restrict__ inv_cnt /*[B, dc] or null*/,
                                                         const uint32_t* __restrict__ row_off,
                                                         Table tb, BatchPtrs bp,
                                                         const float* __restrict__ num_emb,
@@ -441,24 +437,35 @@ __global__ void __launch_bounds__(256) gather_fm_kernel(const int32_t* __restric
     for (int b = blockIdx.x * warps_per_block + (threadIdx.x >> 5); b < B; b += gridDim.x * warps_per_block) {
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
         float lin = 0.f;
-        const int32_t* idrow = ids + (int64_t)b * dc;
+        const int32_t* idrow = ids + (int64_t)b * n_slots;
         float4* hrow = reinterpret_cast<float4*>(h0 + (int64_t)b * d * K);
         for (int f0 = 0; f0 < dc; f0 += FPR) {
             int f = f0 + grp;
             if (f < dc) {
-                int32_t id = idrow[f];
+                const int s0 = BAGS ? field_slot0[f] : f, s1 = BAGS ? field_slot0[f + 1] : f + 1;
                 float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (id >= 0) {
-                    if (rowbuf) {   // sharded: rows were fetched from their owners into rowbuf[unique index]
-                        const float* rp = rowbuf + (size_t)__ldg(uidx + (int64_t)b * dc + f) * rowbuf_stride;
-                        if (need_emb) e = __ldg(reinterpret_cast<const float4*>(rp) + sub);
-                        if (use_linear && sub == 0) lin += __ldg(rp + K);
-                    } else {
-                        size_t row = (size_t)row_off[f] + (uint32_t)id;
-                        if (need_emb) e = __ldg(tab_w(tb, row) + sub);
-                        if (use_linear && sub == 0) lin += __ldg(reinterpret_cast<const float*>(tab_lin(tb, row)));
+                float lsum = 0.f;
+                int cnt = 0;
+                for (int sl = s0; sl < s1; ++sl) {      // one slot for a single-valued column; a multi-hot bag is mean-pooled
+                    int32_t id = idrow[sl];
+                    if (id >= 0) {
+                        ++cnt;
+                        if (rowbuf) {   // sharded: rows were fetched from their owners into rowbuf[unique index]
+                            const float* rp = rowbuf + (size_t)__ldg(uidx + (int64_t)b * n_slots + sl) * rowbuf_stride;
+                            if (need_emb) add4(e, __ldg(reinterpret_cast<const float4*>(rp) + sub));
+                            if (use_linear && sub == 0) lsum += __ldg(rp + K);
+                        } else {
+                            size_t row = (size_t)row_off[f] + (uint32_t)id;
+                            if (need_emb) add4(e, __ldg(tab_w(tb, row) + sub));
+                            if (use_linear && sub == 0) lsum += __ldg(reinterpret_cast<const float*>(tab_lin(tb, row)));
+                        }
                     }
                 }
+                if (BAGS) {
+                    if (cnt > 1) { const float ic = 1.0f / (float)cnt; e.x *= ic; e.y *= ic; e.z *= ic; e.w *= ic; }
+                    if (sub == 0) inv_cnt[(int64_t)b * dc + f] = cnt ? 1.0f / (float)cnt : 0.f;
+                }
+                lin += lsum;
                 if (need_emb) {
                     hrow[f * LPR + sub] = e;
                     s.x += e.x; s.y += e.y; s.z += e.z; s.w += e.w;
@@ -508,13 +515,16 @@ __global__ void __launch_bounds__(256) gather_fm_kernel(const int32_t* __restric
 // =============================================================================================
 // gradient of lookup (b, f): dE[b, f*K..] (already = dz*(s-E) + dh0, written by the tower's last
 // backward GEMM epilogue or by de_fm_kernel) and dz[b] for the linear weight.
-template <int K>
+template <int K, bool BAGS>
 struct GradSrc {
     const float* dE;    // [B, d*K] or nullptr
     const float* dz;    // [B]
     int dc, dK;         // dK = d*K
     const float* flat;  // sharded owner side: gradient rows [n][flat_stride] = {g[K], g_lin, pad}, payload = row of `flat`
     int flat_stride;
+    int n_slots;                // lookups per sample (payload = b * n_slots + slot)
+    const int32_t* slot_field;  // BAGS: slot -> field
+    const float* inv_cnt;       // BAGS: [B, dc] 1 / (present slots) of every field
     __device__ __forceinline__ void fetch(uint32_t val, int sub, bool want_lin, float4& g, float& gl) const {
         if (flat) {
             const float* rp = flat + (size_t)val * flat_stride;
@@ -522,14 +532,17 @@ struct GradSrc {
             gl = want_lin ? __ldg(rp + K) : 0.f;
             return;
         }
-        uint32_t b = val / (uint32_t)dc, f = val - b * (uint32_t)dc;
+        uint32_t b = val / (uint32_t)n_slots, f = val - b * (uint32_t)n_slots;
+        if (BAGS) f = (uint32_t)__ldg(slot_field + f);
         g = dE ? __ldg(reinterpret_cast<const float4*>(dE + (size_t)b * dK + (size_t)f * K) + sub)
                : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (BAGS) {   // mean combiner: every present slot of the bag receives dE / count
+            const float ic = __ldg(inv_cnt + (size_t)b * dc + f);
+            g.x *= ic; g.y *= ic; g.z *= ic; g.w *= ic;
+        }
         gl = want_lin ? __ldg(dz + b) : 0.f;
     }
 };
-
-__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
 // list the pieces of hot rows (rows with > DIRECT_T lookups); order is irrelevant, every piece sum goes to its own slot
 __global__ void __launch_bounds__(256) hot_pieces_kernel(const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ row_piece0,
@@ -546,11 +559,11 @@ __global__ void __launch_bounds__(256) hot_pieces_kernel(const uint32_t* __restr
 // level 1: one warp per piece of a hot row.  The 128/K lane groups stride over the piece's entries
 // (4 independent loads in flight per group), then a fixed butterfly combines them -> the summation
 // order is a function of the sorted order only.
-template <int K>
+template <int K, bool BAGS>
 __global__ void __launch_bounds__(256) piece_reduce_kernel(const uint32_t* __restrict__ svals,
                                                            const uint32_t* __restrict__ piece_start,
                                                            const uint32_t* __restrict__ hot_list,
-                                                           const SegCounts* __restrict__ cnt, GradSrc<K> src,
+                                                           const SegCounts* __restrict__ cnt, GradSrc<K, BAGS> src,
                                                            float* __restrict__ piece_sum /*[slots][K+4]*/) {
     constexpr int LPR = K / 4, G = 32 / LPR;
     const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
@@ -594,13 +607,13 @@ __global__ void __launch_bounds__(256) piece_reduce_kernel(const uint32_t* __res
 // level 2 + optimizer: one lane group per unique row.  Rows with <= DIRECT_T lookups sum their
 // gradients straight from dE in sorted (= sample) order; hot rows sum their piece sums in order.
 // Then the sparse optimizer step for that row (Adam: rows were caught up to t-1 beforehand).
-template <int K>
+template <int K, bool BAGS>
 __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restrict__ urow, const uint32_t* __restrict__ uval,
                                                          const uint32_t* __restrict__ svals,
                                                          const uint32_t* __restrict__ row_start,
                                                          const uint32_t* __restrict__ row_piece0,
                                                          const uint32_t* __restrict__ piece_start,
-                                                         const SegCounts* __restrict__ cnt, GradSrc<K> src,
+                                                         const SegCounts* __restrict__ cnt, GradSrc<K, BAGS> src,
                                                          const float* __restrict__ piece_sum,
                                                          Table tb, int emb_slots, OptDev od, OptDev ol,
                                                          bool has_emb, bool has_lin, int step,

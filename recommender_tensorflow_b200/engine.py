@@ -44,7 +44,8 @@ class PackedBatch:
 class DeepFMEngine:
     def __init__(self, categorical_columns, numeric_columns=(), embedding_size=4, hidden_units=(16, 16),
                  use_linear=True, use_mf=True, use_dnn=True, loss_reduction="mean", opt_deep=None,
-                 opt_linear=None, max_batch=65536, device=0, feature_dtypes=None, sort_columns=True, rank=0, world=1, dropout=0.0, dropout_seed=0):
+                 opt_linear=None, max_batch=65536, device=0, feature_dtypes=None, sort_columns=True, rank=0, world=1, dropout=0.0, dropout_seed=0,
+                 multivalent=None):
         self.lib = _lib.load()
         cats = list(categorical_columns)
         nums = list(numeric_columns)
@@ -62,13 +63,16 @@ class DeepFMEngine:
         self.rank, self.world = int(rank), int(world)
         self.dropout, self.dropout_seed = float(dropout or 0.0), int(dropout_seed)
         fd = dict(feature_dtypes or {})
+        mv = dict(multivalent or {})      # raw feature key -> value slots per sample (multi-hot / multivalent column)
         self.specs = []
         for c in cats:
             s = c.spec()
+            s["width"] = int(mv.get(s["source"], 1))
             if s["kind"] == "bucketized":
                 s["dtype"] = fd.get(s["source"], c.source_column.dtype)
             self.specs.append(s)
         self.num_buckets = [int(s["num_buckets"]) for s in self.specs]
+        self.n_slots = sum(s["width"] for s in self.specs)
         self.row_offsets = np.concatenate([[0], np.cumsum(self.num_buckets)]).astype(np.int64)
         self._keep = []
         cols = (_lib.Column * max(len(cats), 1))()
@@ -78,6 +82,7 @@ class DeepFMEngine:
             col.kind = _lib.COL_KIND[s["kind"]]
             col.dtype = _lib.DTYPE[s["dtype"]]
             col.num_buckets = s["num_buckets"]
+            col.width = s["width"]
             if s["kind"] == "bucketized":
                 arr = (C.c_float * len(s["boundaries"]))(*s["boundaries"])
                 self._keep.append(arr)
@@ -275,14 +280,14 @@ class DeepFMEngine:
                     offs = np.zeros(len(vals) + 1, dtype=np.int32)
                     np.cumsum(lens, out=offs[1:])
                     data = np.frombuffer(b"".join(vals) or b"\0", dtype=np.uint8)
-                n = offs.shape[0] - 1
+                n = (offs.shape[0] - 1) // s["width"]
                 segs += [("off", f, offs), ("cat", f, data)]
             else:
-                arr = np.asarray(raw).reshape(-1)
+                arr = np.asarray(raw).reshape(-1)          # multivalent: [B, width] row-major
                 want = np.int32 if s["dtype"] == "int32" else np.float32
                 if arr.dtype != want:
                     arr = arr.astype(want)
-                n = arr.shape[0]
+                n = arr.shape[0] // s["width"]
                 segs.append(("cat", f, np.ascontiguousarray(arr)))
             if B is None:
                 B = n
@@ -356,7 +361,7 @@ class DeepFMEngine:
         """ids [B, n_cat] int32 in model order (-1 = empty bag): K1 alone."""
         torch = _torch()
         pb = self._as_batch(features, None, device=True)
-        out = torch.empty((pb.batch_size, len(self.specs)), dtype=torch.int32, device="cuda:%d" % self.device)
+        out = torch.empty((pb.batch_size, self.n_slots), dtype=torch.int32, device="cuda:%d" % self.device)
         self._check(self.lib.dfm_transform(self.h, C.byref(pb.raw), C.c_void_p(out.data_ptr()), None))
         self.sync()
         return out.cpu().numpy()

@@ -46,7 +46,7 @@ class ShardedTrainer:
         self.eng, self.group = engine, group
         self.W, self.rank = engine.world, engine.rank
         dev = "cuda:%d" % engine.device
-        n = engine.max_batch * max(len(engine.specs), 1)
+        n = engine.max_batch * max(engine.n_slots, 1)
         rw = engine.row_width
         self.req_rows = torch.empty(n, dtype=torch.int32, device=dev)
         self.recv_rows = torch.empty(2 * n + 4096, dtype=torch.int32, device=dev)
@@ -120,7 +120,7 @@ class VirtualCluster:
         global_batch = sum(pb.batch_size for pb in pbs)
         req, counts = [], []
         for e, pb in zip(self.engs, pbs):
-            buf = torch.empty(pb.batch_size * max(len(e.specs), 1), dtype=torch.int32, device=dev)
+            buf = torch.empty(pb.batch_size * max(e.n_slots, 1), dtype=torch.int32, device=dev)
             counts.append(e.shard_requests(pb, buf))
             req.append(buf[:sum(counts[-1])])
         recv_rows, recv_counts = route_all_to_all(req, counts)

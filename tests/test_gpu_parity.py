@@ -89,6 +89,14 @@ def test_identity_out_of_range_is_an_error():
     assert ei.value.code == -3
 
 
+def _assert_eval_logits(z, ora, ids):
+    """forward-only logits against the oracle pair (float64 twin calibrates the FM cancellation noise)."""
+    z32 = ora.o32.forward(ids).numpy().astype(np.float64)
+    z64 = ora.o64.forward(ids).numpy()
+    tol = 1e-6 + RTOL * np.abs(z64) + 4.0 * np.abs(z32 - z64).max()
+    assert (np.abs(z.astype(np.float64) - z64) <= tol).all(), np.abs(z - z64).max()
+
+
 def _run_steps(eng, ora, batches, what):
     for i, (feats, y) in enumerate(batches):
         loss, logits = eng.train_step(feats, y, return_logits=True)
@@ -144,8 +152,7 @@ def test_dropout_all_tower_paths(hidden):
     _run_steps(eng, ora, [ml.batch(1024, rng) for _ in range(3)], "dropout%r" % (hidden,))
     feats, _ = ml.batch(64, rng)                       # EVAL / PREDICT: no dropout
     z = eng.predict_logits(feats)
-    ref = ora.forward(transforms.transform(eng.specs, feats)).numpy()
-    assert np.allclose(z, ref, rtol=1e-5, atol=2e-6)
+    _assert_eval_logits(z, ora, transforms.transform(eng.specs, feats))
 
 
 def test_wide_deep_cfg2():
@@ -215,8 +222,7 @@ def test_eval_forward_matches_oracle():
         ora.train_step_raw(feats, y)
     feats, _ = ml.batch(100, rng)
     z = eng.predict_logits(feats)
-    ref = ora.forward(transforms.transform(eng.specs, feats)).numpy()
-    assert np.allclose(z, ref, rtol=RTOL, atol=2e-6)
+    _assert_eval_logits(z, ora, transforms.transform(eng.specs, feats))
     assert eng.global_step == 3
 
 
@@ -346,3 +352,44 @@ def test_full_size_step_determinism_and_fm_identity():
     pair = 0.5 * ((E.sum(1) ** 2).sum(1) - (E ** 2).sum((1, 2)))
     z = w["lin"].astype(np.float64)[rows].sum(1) + float(w["bias"][0]) + pair
     assert np.allclose(res[0][1][:200], z, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------ multi-hot (multivalent) columns
+def _bag_setup(B, rng, ml):
+    """ML-100K-shaped features where the 19 one-hot genre columns are ONE multi-hot `genres` column (identity, 19
+    buckets, up to 6 ids per sample, -1 padded) plus a multivalent string column `tags` (hashed, 3 slots, '' padded)."""
+    from recommender_tensorflow_b200.trainers import ml_100k
+    base = [c for c in ml_100k.get_feature_columns()["linear"] if c.key not in synth.GENRE]
+    cols = base + [fc.categorical_column_with_identity("genres", 19), fc.categorical_column_with_hash_bucket("tags", 50)]
+    feats, y = ml.batch(B, rng)
+    g = np.full((B, 6), -1, np.int32)
+    for j, name in enumerate(synth.GENRE):
+        on = feats.pop(name) > 0
+        pos = (g >= 0).sum(1)
+        ok = on & (pos < 6)
+        g[np.where(ok)[0], pos[ok]] = j
+    feats["genres"] = g
+    words = [b"", b"noir", b"cult", b"classic", b"indie", b"blockbuster-of-the-year-long-tag"]
+    tags = [words[i] for i in rng.integers(0, len(words), B * 3)]
+    for i in range(0, B * 3, 7):
+        tags[i] = b""                                  # some empty slots, some fully empty bags
+    feats["tags"] = np.array(tags, dtype=object).reshape(B, 3)
+    return cols, feats, y
+
+
+def test_multi_hot_pooling_matches_oracle():
+    """embedding_column mean / linear_model sum over a multivalent column (BASELINE north_star: multi-hot genre pooling)."""
+    from recommender_tensorflow_b200.trainers import ml_100k
+    ml, rng = synth.ML100K(), np.random.default_rng(70)
+    cols, _, _ = _bag_setup(4, rng, ml)
+    eng = DeepFMEngine(cols, (), embedding_size=8, hidden_units=(16, 16), max_batch=600, feature_dtypes=ml_100k.FEATURE_DTYPES,
+                       multivalent={"genres": 6, "tags": 3})
+    assert eng.n_slots == len(cols) - 2 + 6 + 3
+    ora, _ = make_pair(eng, seed=71)
+    batches = []
+    for _ in range(4):
+        _, feats, y = _bag_setup(600, rng, ml)
+        batches.append((feats, y))
+    ids = eng.transform(batches[0][0])
+    assert ids.shape == (600, eng.n_slots) and (ids == transforms.transform(eng.specs, batches[0][0])).all()
+    _run_steps(eng, ora, batches, "multi-hot")
