@@ -70,3 +70,26 @@ def test_sharded_ml100k_hot_rows_world2():
         rloss, rlogits = ora.train_step_raw(feats, y)
         assert_step_close(loss, logits, ora, rloss, rlogits, 1e-5, "sharded-ml step %d" % step)
     assert_state_close(vc.state(_names(engs[0])), ora.state(), 1e-5, 1e-7, "sharded-ml", ora.state64())
+
+
+def test_sharded_multi_hot_world2():
+    """multivalent columns through the row-sharded path (slots are looked up at their owners, pooled locally)."""
+    from recommender_tensorflow_b200.trainers import ml_100k
+    from tests.test_gpu_parity import _bag_setup
+    ml, rng = synth.ML100K(), np.random.default_rng(80)
+    cols, _, _ = _bag_setup(4, rng, ml)
+    kw = dict(embedding_size=8, hidden_units=(16, 16), feature_dtypes=ml_100k.FEATURE_DTYPES, multivalent={"genres": 6, "tags": 3})
+    ref = DeepFMEngine(cols, (), max_batch=512, **kw)
+    ora, w = make_pair(ref, seed=81)
+    engs = [DeepFMEngine(cols, (), max_batch=256, rank=r, world=2, **kw) for r in range(2)]
+    for e in engs:
+        e.set_weights_sharded(w)
+    vc = VirtualCluster(engs)
+    for step in range(3):
+        _, feats, y = _bag_setup(512, rng, ml)
+        pbs = [e.pack({k: v[r * 256:(r + 1) * 256] for k, v in feats.items()}, y[r * 256:(r + 1) * 256], device=True)
+               for r, e in enumerate(engs)]
+        loss, logits = vc.train_step(pbs, return_logits=True)
+        rloss, rlogits = ora.train_step_raw(feats, y)
+        assert_step_close(loss, logits, ora, rloss, rlogits, 1e-5, "sharded-bags step %d" % step)
+    assert_state_close(vc.state(_names(engs[0])), ora.state(), 1e-5, 1e-7, "sharded-bags", ora.state64())
