@@ -242,8 +242,9 @@ def main():
                 t = torch.from_numpy(eng.get_tensor(nm)).cuda()
                 dist.broadcast(t, 0)
                 eng.set_tensor(nm, t.cpu().numpy())
-        from recommender_tensorflow_b200.sharded import ShardedTrainer
-        trainer = ShardedTrainer(eng)
+        from recommender_tensorflow_b200.sharded import P2PShardedTrainer, ShardedTrainer
+        exchange = os.environ.get("DFM_SHARD_EXCHANGE", "p2p")     # "p2p": stores over IPC-mapped peer memory; "nccl": all_to_all
+        trainer = P2PShardedTrainer(eng) if exchange == "p2p" else ShardedTrainer(eng)
     n_batches = 8
     host_batches = make_batches(w, n_batches, 777 + rank)
     packed_host = [eng.pack(f, y) for f, y in host_batches]
@@ -356,8 +357,9 @@ def main():
                        "optimizer": o["opt_deep"]["name"] + ("/" + o["opt_linear"]["name"] if w["model"] == "wide_deep" else " (TF non-lazy, exact deferred)"),
                        "l2": "per-step working set (activations + gradients) exceeds L2; inputs rotate over %d batches" % n_batches,
                        "parallelism": "single GPU" if world == 1 else (
-                           "tables row-sharded over %d GPUs (all_to_all ids / rows / gradient rows), data-parallel tower "
-                           "(all_reduce); global batch %d" % (world, B * world) if sharded else "replicas x%d" % world)},
+                           "tables row-sharded over %d GPUs (ids / rows / gradient rows exchanged by %s), data-parallel tower "
+                           "(all_reduce); global batch %d" % (world, "kernel stores into IPC-mapped peer memory over NVLink"
+                                                              if exchange == "p2p" else "NCCL all_to_all", B * world) if sharded else "replicas x%d" % world)},
             "gpu_launches": int(launches),
             "loss_last": last_loss,
             "e2e": {"value": B * args.steps * world / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes),

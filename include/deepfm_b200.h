@@ -200,6 +200,27 @@ int dfm_shard_forward_backward(dfm_handle* h, const dfm_raw_batch* dev_batch, co
                                float* loss_dev, float* logits_dev, float* gsum_dev, float* dense_grad_dev, void* stream);
 int dfm_shard_apply(dfm_handle* h, const float* grecv_dev, const float* dense_grad_dev, void* stream);
 
+/* ---- The same sharded step with the three exchanges FUSED into the kernels over NVLink peer memory.
+ * Every rank's receive buffers (row ids, rows, gradient rows) live in the library and are mapped into the
+ * other ranks through CUDA IPC (dfm_shard_ipc_export / _import, handles exchanged by the host once).  Per step:
+ *   dfm_shard_requests -> all_gather(counts) -> dfm_shard_p2p_plan        (W x W count matrix -> routing table)
+ *   dfm_shard_p2p_push_ids            requesters store their unique row ids into the owners' buffers    | barrier
+ *   dfm_shard_p2p_serve               owners catch up and store each row into the requester's row buffer | barrier
+ *   dfm_shard_p2p_forward_backward    gradient rows are stored straight into the owners' buffers         | all_reduce(dense)
+ *   dfm_shard_p2p_apply
+ * "barrier" = any stream-ordered collective (the host uses a 4-byte all_reduce); no payload goes through NCCL. */
+int dfm_shard_ipc_export(dfm_handle* h, unsigned char* handles_out /* 3 * 64 bytes */);
+int dfm_shard_ipc_import(dfm_handle* h, const unsigned char* all_handles /* world * 3 * 64 bytes, rank-major */);
+/* single-process hosts (several ranks on one GPU, as the tests do) wire the handles with raw pointers instead of IPC */
+int dfm_shard_p2p_buffers(dfm_handle* h, void** out3 /* {rows, gradient rows, row ids} */);
+int dfm_shard_p2p_set_peers(dfm_handle* h, void* const* ptrs /* world * 3, rank-major */);
+int dfm_shard_p2p_plan(dfm_handle* h, const int32_t* counts /* [world * world], source-major */, int64_t* n_recv_out, void* stream);
+int dfm_shard_p2p_push_ids(dfm_handle* h, void* stream);
+int dfm_shard_p2p_serve(dfm_handle* h, void* stream);
+int dfm_shard_p2p_forward_backward(dfm_handle* h, const dfm_raw_batch* dev_batch, int64_t global_batch, float* loss_dev,
+                                   float* logits_dev, float* dense_grad_dev, void* stream);
+int dfm_shard_p2p_apply(dfm_handle* h, const float* dense_grad_dev, void* stream);
+
 /* Building-block entry points used by the parity tests (device pointers, synchronous). */
 int dfm_test_sort_pairs(uint32_t* keys_dev, uint32_t* vals_dev, int64_t n, int32_t key_bits);
 int dfm_test_fingerprint64(const uint8_t* bytes_dev, const int32_t* offsets_dev, int64_t n,

@@ -74,6 +74,15 @@ _SIGS = {
     "dfm_shard_forward_backward": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfm_shard_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dfm_shard_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dfm_shard_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dfm_shard_p2p_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dfm_shard_p2p_set_peers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dfm_shard_p2p_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "dfm_shard_p2p_push_ids": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dfm_shard_p2p_serve": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dfm_shard_p2p_forward_backward": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dfm_shard_p2p_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfm_test_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]),
     "dfm_test_fingerprint64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "dfm_test_tc_gemm": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

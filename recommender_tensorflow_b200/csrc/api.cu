@@ -92,6 +92,10 @@ struct dfm_handle {
     uint32_t* req_rows = nullptr;   // unique rows of the local batch as local indices at their owners (owner-major order)
     int32_t* d_counts = nullptr; int32_t* h_counts = nullptr;   // [world] unique rows per owner, [world] = total
     int64_t shard_n_req = 0, shard_n_recv = 0; int shard_B = 0; float shard_scale = 0.f;
+    // fused exchange over peer memory (CUDA IPC): own receive buffers + mapped peer buffers + routing table
+    float *p2p_rowbuf = nullptr, *p2p_grecv = nullptr; uint32_t* p2p_recv_rows = nullptr;
+    PeerRoute* h_route = nullptr; PeerRoute* d_route = nullptr; bool p2p_ready = false;
+    void* p2p_opened[3 * MAX_PEERS] = {nullptr};
     OptDev shard_od{}, shard_ol{};
     float *h0 = nullptr, *s = nullptr, *zacc = nullptr, *logits = nullptr, *dz = nullptr, *dE = nullptr;
     float* act[DFM_MAX_HIDDEN + 1] = {nullptr};
@@ -210,6 +214,12 @@ static void free_all(dfm_handle* h) {
     free_ws(h->ws);
     free_ws(h->ws_own);
     if (h->h_counts) cudaFreeHost(h->h_counts);
+    for (void* p : h->p2p_opened) if (p) cudaIpcCloseMemHandle(p);
+    if (h->p2p_rowbuf) cudaFree(h->p2p_rowbuf);
+    if (h->p2p_grecv) cudaFree(h->p2p_grecv);
+    if (h->p2p_recv_rows) cudaFree(h->p2p_recv_rows);
+    if (h->d_route) cudaFree(h->d_route);
+    if (h->h_route) cudaFreeHost(h->h_route);
     for (int i = 1; i <= DFM_MAX_HIDDEN; ++i) { if (h->act[i]) cudaFree(h->act[i]); if (h->dact[i]) cudaFree(h->dact[i]); }
     for (auto& s : h->stage) {
         if (s.d_arena) cudaFree(s.d_arena);
@@ -401,6 +411,15 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
         if (dalloc(h, &h->req_rows, n)) return DFM_ERR_CUDA;
         if (dalloc(h, &h->d_counts, (size_t)h->world + 1)) return DFM_ERR_CUDA;
         CK(cudaMallocHost(&h->h_counts, ((size_t)h->world + 1) * sizeof(int32_t)));
+        if (h->world <= MAX_PEERS) {
+            const size_t rw = (size_t)K + 4;
+            if (dalloc(h, &h->p2p_rowbuf, (size_t)n * rw)) return DFM_ERR_CUDA;
+            if (dalloc(h, &h->p2p_grecv, (size_t)h->ws_own.cap * rw)) return DFM_ERR_CUDA;
+            if (dalloc(h, &h->p2p_recv_rows, (size_t)h->ws_own.cap)) return DFM_ERR_CUDA;
+            if (dalloc(h, &h->d_route, 1)) return DFM_ERR_CUDA;
+            CK(cudaMallocHost(&h->h_route, sizeof(PeerRoute)));
+            memset(h->h_route, 0, sizeof(PeerRoute));
+        }
     }
     if (h->need_emb) {
         if (dalloc(h, &h->h0, Bm * dK)) return DFM_ERR_CUDA;
@@ -998,7 +1017,7 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
 // deterministic segmented reduction of the sparse gradients (+ optimizer, or gradient rows out when gsum != nullptr)
 template <int K, bool BAGS>
 static int sparse_update(dfm_handle* h, SegWS& ws, int64_t n, const GradSrc<K, BAGS>& src, const OptDev& od, const OptDev& ol, int64_t t,
-                         float* gsum, cudaStream_t st, Phase* ph) {
+                         float* gsum, cudaStream_t st, Phase* ph, const PeerRoute* route = nullptr) {
     const unsigned row_grid = (unsigned)h->sm_count * 8;
     if (n > 0) {
         hot_pieces_kernel<<<row_grid, 256, 0, st>>>(ws.row_start, ws.row_piece0, ws.seg_cnt, ws.hot_list);
@@ -1008,7 +1027,7 @@ static int sparse_update(dfm_handle* h, SegWS& ws, int64_t n, const GradSrc<K, B
     if (ph) ph->next();
     row_update_kernel<K, BAGS><<<n > 0 ? row_grid : 1, 256, 0, st>>>(ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0, ws.piece_start, ws.seg_cnt, src,
                                                                ws.piece_sum, h->tb, h->emb_slots, od, ol, (bool)h->need_emb,
-                                                               (bool)h->use_linear, (int)t, h->alpha_d, h->alpha_l, gsum, K + 4);
+                                                               (bool)h->use_linear, (int)t, h->alpha_d, h->alpha_l, gsum, K + 4, route);
     h->launches++;
     if (ph) ph->next();
     CK(cudaGetLastError());
@@ -1241,7 +1260,8 @@ extern "C" int dfm_shard_requests(dfm_handle* h, const dfm_raw_batch* b, uint32_
 }
 
 template <int K>
-static int shard_serve_impl(dfm_handle* h, const uint32_t* recv_rows, int64_t n_recv, float* reply, cudaStream_t st) {
+static int shard_serve_impl(dfm_handle* h, const uint32_t* recv_rows, int64_t n_recv, float* reply, cudaStream_t st,
+                            const PeerRoute* route = nullptr) {
     if (n_recv > h->ws_own.cap) FAIL(DFM_ERR_UNSUPPORTED, "more row requests than the owner workspace holds (raise max_batch)");
     const int64_t l0 = h->launches;
     const int64_t t = h->step + 1;
@@ -1257,7 +1277,7 @@ static int shard_serve_impl(dfm_handle* h, const uint32_t* recv_rows, int64_t n_
     if ((rc = catchup_touched<K>(h, h->ws_own, n_recv, t, st))) return rc;
     if (n_recv > 0) {
         shard_serve_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(recv_rows, n_recv, h->tb, (bool)h->need_emb,
-                                                                          (bool)h->use_linear, reply, K + 4);
+                                                                          (bool)h->use_linear, reply, K + 4, route);
         h->launches++;
     }
     h->shard_n_recv = n_recv;
@@ -1278,7 +1298,7 @@ extern "C" int dfm_shard_serve(dfm_handle* h, const uint32_t* recv_rows_dev, int
 
 template <int K>
 static int shard_fb_impl(dfm_handle* h, const BatchPtrs& bp, int B, const float* rowbuf, int64_t global_batch, float* loss_out,
-                         float* logits_out, float* gsum, float* dense_grad, cudaStream_t st) {
+                         float* logits_out, float* gsum, float* dense_grad, cudaStream_t st, const PeerRoute* route = nullptr) {
     const int dc = h->dc, dK = (dc + h->dn) * K;
     const int64_t n = (int64_t)B * h->dcs, t = h->step + 1;
     const int64_t l0 = h->launches;
@@ -1289,10 +1309,10 @@ static int shard_fb_impl(dfm_handle* h, const BatchPtrs& bp, int B, const float*
     if ((rc = tower_backward<K>(h, bp, B, scale, loss_out, st, nullptr))) return rc;
     if (h->has_bags) {
         GradSrc<K, true> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0, h->dcs, h->d_slot_col, h->inv_cnt};
-        rc = sparse_update<K, true>(h, h->ws, n, src, so.od, so.ol, t, gsum, st, nullptr);
+        rc = sparse_update<K, true>(h, h->ws, n, src, so.od, so.ol, t, gsum, st, nullptr, route);
     } else {
         GradSrc<K, false> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0, h->dcs, nullptr, nullptr};
-        rc = sparse_update<K, false>(h, h->ws, n, src, so.od, so.ol, t, gsum, st, nullptr);
+        rc = sparse_update<K, false>(h, h->ws, n, src, so.od, so.ol, t, gsum, st, nullptr, route);
     }
     if (rc) return rc;
     if (h->n_dense && dense_grad) CK(cudaMemcpyAsync(dense_grad, h->dg, (size_t)h->n_dense * 4, cudaMemcpyDeviceToDevice, st));
@@ -1339,6 +1359,139 @@ extern "C" int dfm_shard_apply(dfm_handle* h, const float* grecv_dev, const floa
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     int rc = DFM_OK;
     DISPATCH_K(h, rc = shard_apply_impl<KK>(h, grecv_dev, dense_grad_dev, st));
+    return rc;
+}
+
+// ---- fused exchange over NVLink peer memory -------------------------------------------------------
+// The three receive buffers of every rank (row ids, rows, gradient rows) are cudaMalloc'ed by the library and
+// mapped into every other rank's address space through CUDA IPC.  The requests, the served rows and the
+// gradient rows are then STORED by the producing kernel directly at their destination on the peer GPU; the
+// host only exchanges the W x W count matrix and places stream-ordered barriers (a tiny all-reduce).
+extern "C" int dfm_shard_ipc_export(dfm_handle* h, unsigned char* out /* 3 * 64 bytes */) {
+    if (!h || !out) return DFM_ERR_INVALID_ARG;
+    if (h->world < 2 || !h->p2p_rowbuf) FAIL(DFM_ERR_UNSUPPORTED, "handle has no peer-exchange buffers");
+    CK(cudaSetDevice(h->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* bufs[3] = {h->p2p_rowbuf, h->p2p_grecv, h->p2p_recv_rows};
+    for (int i = 0; i < 3; ++i) {
+        cudaIpcMemHandle_t mh;
+        CK(cudaIpcGetMemHandle(&mh, bufs[i]));
+        memcpy(out + 64 * i, &mh, 64);
+    }
+    return DFM_OK;
+}
+
+// Raw device pointers of this rank's receive buffers {rows, gradient rows, row ids} and the peer table.  A host that
+// runs several ranks inside ONE process (the single-GPU emulation used by the tests) wires the handles together with
+// these two calls; separate processes use the IPC pair, which ends in the same table.
+extern "C" int dfm_shard_p2p_buffers(dfm_handle* h, void** out3) {
+    if (!h || !out3) return DFM_ERR_INVALID_ARG;
+    if (h->world < 2 || !h->p2p_rowbuf) FAIL(DFM_ERR_UNSUPPORTED, "handle has no peer-exchange buffers");
+    out3[0] = h->p2p_rowbuf; out3[1] = h->p2p_grecv; out3[2] = h->p2p_recv_rows;
+    return DFM_OK;
+}
+
+extern "C" int dfm_shard_p2p_set_peers(dfm_handle* h, void* const* ptrs /* world * 3, rank-major */) {
+    if (!h || !ptrs) return DFM_ERR_INVALID_ARG;
+    if (h->world < 2 || !h->p2p_rowbuf) FAIL(DFM_ERR_UNSUPPORTED, "handle has no peer-exchange buffers");
+    PeerRoute* r = h->h_route;
+    r->W = h->world; r->me = h->rank;
+    for (int p = 0; p < h->world; ++p) {
+        const bool me = p == h->rank;
+        r->peer_rowbuf[p] = me ? h->p2p_rowbuf : reinterpret_cast<float*>(ptrs[p * 3 + 0]);
+        r->peer_grecv[p] = me ? h->p2p_grecv : reinterpret_cast<float*>(ptrs[p * 3 + 1]);
+        r->peer_recv_rows[p] = me ? h->p2p_recv_rows : reinterpret_cast<uint32_t*>(ptrs[p * 3 + 2]);
+        if (!r->peer_rowbuf[p] || !r->peer_grecv[p] || !r->peer_recv_rows[p]) FAIL(DFM_ERR_INVALID_ARG, "null peer buffer");
+    }
+    h->p2p_ready = true;
+    return DFM_OK;
+}
+
+extern "C" int dfm_shard_ipc_import(dfm_handle* h, const unsigned char* all /* world * 3 * 64 bytes, rank-major */) {
+    if (!h || !all) return DFM_ERR_INVALID_ARG;
+    if (h->world < 2 || !h->p2p_rowbuf) FAIL(DFM_ERR_UNSUPPORTED, "handle has no peer-exchange buffers");
+    CK(cudaSetDevice(h->device));
+    void* ptrs[3 * MAX_PEERS] = {nullptr};
+    for (int p = 0; p < h->world; ++p) {
+        if (p == h->rank) continue;
+        for (int i = 0; i < 3; ++i) {
+            cudaIpcMemHandle_t mh;
+            memcpy(&mh, all + ((size_t)p * 3 + i) * 64, 64);
+            if (h->p2p_opened[p * 3 + i]) { ptrs[p * 3 + i] = h->p2p_opened[p * 3 + i]; continue; }
+            CK(cudaIpcOpenMemHandle(&ptrs[p * 3 + i], mh, cudaIpcMemLazyEnablePeerAccess));
+            h->p2p_opened[p * 3 + i] = ptrs[p * 3 + i];
+        }
+    }
+    ptrs[h->rank * 3 + 0] = h->p2p_rowbuf; ptrs[h->rank * 3 + 1] = h->p2p_grecv; ptrs[h->rank * 3 + 2] = h->p2p_recv_rows;
+    return dfm_shard_p2p_set_peers(h, ptrs);
+}
+
+// counts[s * W + o] = unique rows source s requests from owner o (all_gather of every rank's dfm_shard_requests counts)
+extern "C" int dfm_shard_p2p_plan(dfm_handle* h, const int32_t* counts, int64_t* n_recv_out, void* stream) {
+    if (!h || !counts) return DFM_ERR_INVALID_ARG;
+    if (!h->p2p_ready) FAIL(DFM_ERR_INVALID_ARG, "call dfm_shard_ipc_import first");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const int W = h->world, me = h->rank;
+    PeerRoute* r = h->h_route;
+    CK(cudaStreamSynchronize(st));     // the previous step's copy of the table must have been consumed
+    uint32_t acc = 0;
+    for (int o = 0; o < W; ++o) { r->send_off[o] = acc; acc += (uint32_t)counts[me * W + o]; }
+    r->send_off[W] = acc;
+    for (int o = 0; o < W; ++o) { uint32_t d = 0; for (int s2 = 0; s2 < me; ++s2) d += (uint32_t)counts[s2 * W + o]; r->dst_off[o] = d; }
+    acc = 0;
+    for (int s2 = 0; s2 < W; ++s2) { r->recv_off[s2] = acc; acc += (uint32_t)counts[s2 * W + me]; }
+    r->recv_off[W] = acc;
+    for (int s2 = 0; s2 < W; ++s2) { uint32_t d = 0; for (int o = 0; o < me; ++o) d += (uint32_t)counts[s2 * W + o]; r->reply_off[s2] = d; }
+    if ((int64_t)acc > h->ws_own.cap) FAIL(DFM_ERR_UNSUPPORTED, "more row requests than the owner workspace holds (raise max_batch)");
+    if ((int64_t)r->send_off[W] != h->shard_n_req) FAIL(DFM_ERR_INVALID_ARG, "count matrix does not match dfm_shard_requests");
+    CK(cudaMemcpyAsync(h->d_route, r, sizeof(PeerRoute), cudaMemcpyHostToDevice, st));
+    h->shard_n_recv = acc;
+    if (n_recv_out) *n_recv_out = acc;
+    return DFM_OK;
+}
+
+extern "C" int dfm_shard_p2p_push_ids(dfm_handle* h, void* stream) {
+    if (!h || !h->p2p_ready) return DFM_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (h->shard_n_req > 0) {
+        p2p_push_ids_kernel<<<cdiv(h->shard_n_req, 256), 256, 0, st>>>(h->req_rows, (uint32_t)h->shard_n_req, h->d_route);
+        h->launches++; h->last_step_launches++;
+    }
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+extern "C" int dfm_shard_p2p_serve(dfm_handle* h, void* stream) {
+    if (!h || !h->p2p_ready) return DFM_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    int rc = DFM_OK;
+    DISPATCH_K(h, rc = shard_serve_impl<KK>(h, h->p2p_recv_rows, h->shard_n_recv, nullptr, st, h->d_route));
+    return rc;
+}
+
+extern "C" int dfm_shard_p2p_forward_backward(dfm_handle* h, const dfm_raw_batch* b, int64_t global_batch, float* loss_dev,
+                                              float* logits_dev, float* dense_grad_dev, void* stream) {
+    if (!h || global_batch <= 0 || !h->p2p_ready) return DFM_ERR_INVALID_ARG;
+    int rc = check_batch(h, b, true);
+    if (rc) return rc;
+    if (b->batch_size != h->shard_B) FAIL(DFM_ERR_INVALID_ARG, "batch differs from the one given to dfm_shard_requests");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    BatchPtrs bp = make_ptrs(h, b);
+    DISPATCH_K(h, rc = shard_fb_impl<KK>(h, bp, b->batch_size, h->p2p_rowbuf, global_batch, loss_dev, logits_dev, h->p2p_grecv /*non-null: gsum mode*/,
+                                         dense_grad_dev, st, h->d_route));
+    return rc;
+}
+
+extern "C" int dfm_shard_p2p_apply(dfm_handle* h, const float* dense_grad_dev, void* stream) {
+    if (!h || !h->p2p_ready) return DFM_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    int rc = DFM_OK;
+    DISPATCH_K(h, rc = shard_apply_impl<KK>(h, h->p2p_grecv, dense_grad_dev, st));
     return rc;
 }
 

@@ -61,3 +61,23 @@ __device__ __forceinline__ float4* tab_lin(const Table& t, size_t row) {
 __device__ __forceinline__ float4* tab_w(const Table& t, size_t row) { return reinterpret_cast<float4*>(t.rec + row * t.stride); }
 __device__ __forceinline__ float4* tab_s1(const Table& t, size_t row) { return reinterpret_cast<float4*>(t.rec + row * t.stride + t.s1_off); }
 __device__ __forceinline__ float4* tab_s2(const Table& t, size_t row) { return reinterpret_cast<float4*>(t.rec + row * t.stride + t.s2_off); }
+
+// Row-sharded step with the exchanges fused into the kernels over NVLink peer memory (CUDA IPC mappings of
+// every rank's receive buffers): routing table of one step, computed on the host from the W x W matrix of
+// per-(source, owner) unique-row counts.
+constexpr int MAX_PEERS = 16;
+struct PeerRoute {
+    int32_t  W, me;
+    uint32_t send_off[MAX_PEERS + 1];   // my unique-row list is owner-major: rows for owner o = [send_off[o], send_off[o+1])
+    uint32_t dst_off[MAX_PEERS];        // start of my segment inside owner o's receive buffers (recv_rows / grecv)
+    uint32_t recv_off[MAX_PEERS + 1];   // as owner: entries received from source s = [recv_off[s], recv_off[s+1])
+    uint32_t reply_off[MAX_PEERS];      // start, inside source s's row buffer, of the rows I serve for it (= s's send_off[me])
+    float*    peer_rowbuf[MAX_PEERS];   // mapped pointers, own buffers at index `me`
+    float*    peer_grecv[MAX_PEERS];
+    uint32_t* peer_recv_rows[MAX_PEERS];
+};
+__device__ __forceinline__ int route_find(const uint32_t* off, int W, uint32_t i) {
+    int o = 0;
+    while (o + 1 < W && i >= off[o + 1]) ++o;
+    return o;
+}

@@ -618,7 +618,8 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
                                                          Table tb, int emb_slots, OptDev od, OptDev ol,
                                                          bool has_emb, bool has_lin, int step,
                                                          float* __restrict__ alpha_d, float* __restrict__ alpha_l,
-                                                         float* __restrict__ gsum_out, int gsum_stride) {
+                                                         float* __restrict__ gsum_out, int gsum_stride,
+                                                         const PeerRoute* __restrict__ rt) {
     constexpr int LPR = K / 4;
     const int sub = threadIdx.x % LPR;
     const uint32_t gpb = blockDim.x / LPR;
@@ -735,7 +736,13 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
         }
         if (!act) continue;
         if (gsum_out) {   // sharded requester side: emit the per-row gradient sum, the owner applies it
-            float* gp = gsum_out + (size_t)u * gsum_stride;
+            float* gp;
+            if (rt) {   // fused exchange: the gradient row goes straight into its owner's receive buffer over NVLink
+                const int o = route_find(rt->send_off, rt->W, u);
+                gp = rt->peer_grecv[o] + (size_t)(rt->dst_off[o] + (u - rt->send_off[o])) * gsum_stride;
+            } else {
+                gp = gsum_out + (size_t)u * gsum_stride;
+            }
             reinterpret_cast<float4*>(gp)[sub] = g;
             if (sub == 0) gp[K] = gl;
             continue;
@@ -819,15 +826,31 @@ __global__ void iota_kernel(uint32_t* __restrict__ v, int64_t n) {
 template <int K>
 __global__ void __launch_bounds__(256) shard_serve_kernel(const uint32_t* __restrict__ recv_rows, int64_t n,
                                                           Table tb, bool has_emb, bool has_lin,
-                                                          float* __restrict__ reply, int reply_stride) {
+                                                          float* __restrict__ reply, int reply_stride,
+                                                          const PeerRoute* __restrict__ rt) {
     constexpr int LPR = K / 4;
     const int sub = threadIdx.x % LPR;
     const int64_t gpb = blockDim.x / LPR;
     for (int64_t i = (int64_t)blockIdx.x * gpb + threadIdx.x / LPR; i < n; i += (int64_t)gridDim.x * gpb) {
         size_t row = recv_rows[i];
-        float* rp = reply + (size_t)i * reply_stride;
+        float* rp;
+        if (rt) {   // fused exchange: store the row straight into the requester's row buffer over NVLink
+            const int sr = route_find(rt->recv_off, rt->W, (uint32_t)i);
+            rp = rt->peer_rowbuf[sr] + (size_t)(rt->reply_off[sr] + ((uint32_t)i - rt->recv_off[sr])) * reply_stride;
+        } else {
+            rp = reply + (size_t)i * reply_stride;
+        }
         float4 e = has_emb ? __ldg(tab_w(tb, row) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
         reinterpret_cast<float4*>(rp)[sub] = e;
         if (sub == 0) rp[K] = has_lin ? __ldg(reinterpret_cast<const float*>(tab_lin(tb, row))) : 0.f;
+    }
+}
+
+// fused exchange, step 1: every requester stores its unique local-row ids into the owners' receive buffers
+__global__ void p2p_push_ids_kernel(const uint32_t* __restrict__ req_rows, uint32_t U, const PeerRoute* __restrict__ rt) {
+    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < U) {
+        const int o = route_find(rt->send_off, rt->W, u);
+        rt->peer_recv_rows[o][rt->dst_off[o] + (u - rt->send_off[o])] = req_rows[u];
     }
 }

@@ -445,6 +445,54 @@ class DeepFMEngine:
         self._check(self.lib.dfm_shard_apply(self.h, C.c_void_p(grecv.data_ptr()), C.c_void_p(dense_grad.data_ptr()),
                                              C.c_void_p(stream) if stream else None))
 
+    # ---- fused exchange over peer memory (include/deepfm_b200.h: dfm_shard_p2p_*) ----
+    def shard_requests_counts(self, pb, stream=None):
+        counts = (C.c_int32 * self.world)()
+        self._check(self.lib.dfm_shard_requests(self.h, C.byref(pb.raw), None, counts, C.c_void_p(stream) if stream else None))
+        return list(counts)
+
+    def shard_ipc_export(self):
+        buf = (C.c_ubyte * 192)()
+        self._check(self.lib.dfm_shard_ipc_export(self.h, buf))
+        return bytes(buf)
+
+    def shard_ipc_import(self, all_handles):
+        assert len(all_handles) == self.world * 192
+        buf = (C.c_ubyte * len(all_handles)).from_buffer_copy(all_handles)
+        self._check(self.lib.dfm_shard_ipc_import(self.h, buf))
+
+    def shard_p2p_buffers(self):
+        out = (C.c_void_p * 3)()
+        self._check(self.lib.dfm_shard_p2p_buffers(self.h, out))
+        return [int(p) for p in out]
+
+    def shard_p2p_set_peers(self, ptrs):
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        self._check(self.lib.dfm_shard_p2p_set_peers(self.h, arr))
+
+    def shard_p2p_plan(self, counts_matrix, stream=None):
+        """counts_matrix: [world, world] int32, [s, o] = unique rows rank s requests from owner o. -> n_recv"""
+        m = np.ascontiguousarray(counts_matrix, dtype=np.int32)
+        assert m.shape == (self.world, self.world)
+        n = C.c_int64(0)
+        self._check(self.lib.dfm_shard_p2p_plan(self.h, m.ctypes.data_as(C.c_void_p), C.byref(n), C.c_void_p(stream) if stream else None))
+        return n.value
+
+    def shard_p2p_push_ids(self, stream=None):
+        self._check(self.lib.dfm_shard_p2p_push_ids(self.h, C.c_void_p(stream) if stream else None))
+
+    def shard_p2p_serve(self, stream=None):
+        self._check(self.lib.dfm_shard_p2p_serve(self.h, C.c_void_p(stream) if stream else None))
+
+    def shard_p2p_forward_backward(self, pb, global_batch, loss, logits, dense_grad, stream=None):
+        self._check(self.lib.dfm_shard_p2p_forward_backward(
+            self.h, C.byref(pb.raw), int(global_batch), C.c_void_p(loss.data_ptr()),
+            C.c_void_p(logits.data_ptr()) if logits is not None else None, C.c_void_p(dense_grad.data_ptr()),
+            C.c_void_p(stream) if stream else None))
+
+    def shard_p2p_apply(self, dense_grad, stream=None):
+        self._check(self.lib.dfm_shard_p2p_apply(self.h, C.c_void_p(dense_grad.data_ptr()), C.c_void_p(stream) if stream else None))
+
     def set_weights_sharded(self, weights):
         """Load GLOBAL arrays: table rows are sliced to the rows this rank owns (g % world == rank)."""
         for name, val in weights.items():

@@ -36,6 +36,26 @@ def route_all_to_all(send_bufs, send_counts, width=1):
     return recv, recv_counts
 
 
+def _on_real_stream(step):
+    """The C ABI treats a NULL stream as "the handle's own stream", so a step issued while torch's current stream is
+    the legacy default stream (handle 0) would run the kernels and the collectives on two unordered streams.  Run
+    such a step on a private stream, ordered after / before the default stream."""
+    def wrapped(self, *a, **kw):
+        torch = self.torch
+        cur = torch.cuda.current_stream()
+        if cur.cuda_stream != 0:
+            return step(self, *a, **kw)
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            out = step(self, *a, **kw)
+        cur.wait_stream(self._side)
+        return out
+    wrapped.__doc__ = step.__doc__
+    return wrapped
+
+
 class ShardedTrainer:
     """One process per GPU (torchrun); `engine` was created with rank / world of the process group."""
 
@@ -59,6 +79,7 @@ class ShardedTrainer:
         self.cnt_recv = torch.empty(self.W, dtype=torch.int32, device=dev)
         self.rw = rw
 
+    @_on_real_stream
     def train_step(self, pb, global_batch, timings=None):
         """One sharded train step on a device-resident PackedBatch; everything is enqueued on torch's current
         stream (the only host syncs are the two count exchanges).  Returns the global loss as a 0-dim cuda
@@ -104,16 +125,120 @@ class ShardedTrainer:
         return self.dense[nd]
 
 
-class VirtualCluster:
-    """`world` engines in one process on one GPU; same phases, routing by tensor copies."""
+class P2PShardedTrainer:
+    """Same step with the three payload exchanges fused into the kernels: every rank's receive buffers are
+    mapped into its peers through CUDA IPC, and the requesting / serving / gradient kernels store straight
+    into the destination GPU over NVLink.  NCCL carries only the W x W count matrix, two 4-byte barriers and
+    the dense-gradient all_reduce (which doubles as the barrier before `apply`)."""
 
-    def __init__(self, engines):
+    def __init__(self, engine, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.eng, self.group = engine, group
+        self.W, self.rank = engine.world, engine.rank
+        dev = "cuda:%d" % engine.device
+        mine = torch.frombuffer(bytearray(engine.shard_ipc_export()), dtype=torch.uint8).to(dev)
+        allh = torch.empty(self.W * 192, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        engine.shard_ipc_import(bytes(allh.cpu().numpy().tobytes()))
+        self.dense = torch.zeros(max(engine.dense_size, 1) + 1, dtype=torch.float32, device=dev)
+        self.cnt_mine = torch.empty(self.W, dtype=torch.int32, device=dev)
+        self.cnt_all = torch.empty(self.W * self.W, dtype=torch.int32, device=dev)
+        self.flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        dist.barrier(group=group)
+
+    @_on_real_stream
+    def train_step(self, pb, global_batch, timings=None):
+        torch, dist, eng = self.torch, self.dist, self.eng
+        st = torch.cuda.current_stream().cuda_stream
+        marks = []
+
+        def mark(name):
+            if timings is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+        mark("start")
+        counts = eng.shard_requests_counts(pb, st)
+        mark("requests")
+        self.cnt_mine.copy_(torch.tensor(counts, dtype=torch.int32), non_blocking=True)
+        dist.all_gather_into_tensor(self.cnt_all, self.cnt_mine, group=self.group)
+        eng.shard_p2p_plan(self.cnt_all.cpu().numpy().reshape(self.W, self.W), st)
+        mark("counts")
+        eng.shard_p2p_push_ids(st)
+        dist.all_reduce(self.flag, group=self.group)          # barrier: every owner has all its requests
+        mark("push_ids")
+        eng.shard_p2p_serve(st)
+        dist.all_reduce(self.flag, group=self.group)          # barrier: every requester has all its rows
+        mark("serve")
+        nd = eng.dense_size
+        eng.shard_p2p_forward_backward(pb, global_batch, self.dense[nd:nd + 1], None, self.dense, st)
+        mark("fwd_bwd")
+        dist.all_reduce(self.dense, group=self.group)         # dense grads + loss; also the barrier before apply
+        mark("allreduce")
+        eng.shard_p2p_apply(self.dense, st)
+        mark("apply")
+        if timings is not None:
+            torch.cuda.synchronize()
+            for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+                timings[n1] = timings.get(n1, 0.0) + e0.elapsed_time(e1)
+        return self.dense[nd]
+
+
+class VirtualCluster:
+    """`world` engines in one process on one GPU; same phases, routing by tensor copies (or, with p2p=True,
+    by the fused peer-memory stores — the handles are wired with raw pointers since they share a process)."""
+
+    def __init__(self, engines, p2p=False):
         import torch
         self.torch = torch
         self.engs = engines
         self.W = len(engines)
+        self.p2p = p2p
+        if p2p:
+            ptrs = []
+            for e in engines:
+                ptrs += e.shard_p2p_buffers()
+            for e in engines:
+                e.shard_p2p_set_peers(ptrs)
+
+    def _train_step_p2p(self, pbs, return_logits):
+        torch, W = self.torch, self.W
+        dev = "cuda:%d" % self.engs[0].device
+        global_batch = sum(pb.batch_size for pb in pbs)
+        nd = self.engs[0].dense_size
+        counts = np.array([e.shard_requests_counts(pb) for e, pb in zip(self.engs, pbs)], dtype=np.int32)
+        for e in self.engs:
+            e.shard_p2p_plan(counts)
+        for e in self.engs:
+            e.shard_p2p_push_ids()
+        for e in self.engs:
+            e.sync()
+        for e in self.engs:
+            e.shard_p2p_serve()
+        for e in self.engs:
+            e.sync()
+        denses, logits = [], []
+        for e, pb in zip(self.engs, pbs):
+            dn = torch.zeros(nd + 1, dtype=torch.float32, device=dev)
+            lg = torch.empty(pb.batch_size, dtype=torch.float32, device=dev)
+            e.shard_p2p_forward_backward(pb, global_batch, dn[nd:nd + 1], lg, dn)
+            denses.append(dn); logits.append(lg)
+        for e in self.engs:
+            e.sync()
+        total = torch.stack(denses).sum(0)
+        for e in self.engs:
+            e.shard_p2p_apply(total)
+            e.sync()
+        loss = float(total[nd].item())
+        if return_logits:
+            return loss, torch.cat(logits).cpu().numpy()
+        return loss
 
     def train_step(self, pbs, return_logits=False):
+        if self.p2p:
+            return self._train_step_p2p(pbs, return_logits)
         torch, W = self.torch, self.W
         dev = "cuda:%d" % self.engs[0].device
         rw = self.engs[0].row_width

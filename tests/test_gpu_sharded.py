@@ -20,8 +20,9 @@ def _names(eng):
     return out
 
 
+@pytest.mark.parametrize("p2p", [False, True])
 @pytest.mark.parametrize("world", [2, 4])
-def test_sharded_criteo_equals_oracle(world):
+def test_sharded_criteo_equals_oracle(world, p2p):
     cats, nums = synth.criteo_columns(500, n_cat=26, n_num=13)
     kw = dict(embedding_size=16, hidden_units=(16, 16))
     ref = DeepFMEngine(cats, nums, max_batch=1024, **kw)
@@ -29,7 +30,7 @@ def test_sharded_criteo_equals_oracle(world):
     engs = [DeepFMEngine(cats, nums, max_batch=1024 // world, rank=r, world=world, **kw) for r in range(world)]
     for e in engs:
         e.set_weights_sharded(w)
-    vc = VirtualCluster(engs)
+    vc = VirtualCluster(engs, p2p=p2p)
     rng = np.random.default_rng(22)
     per = 1024 // world
     for step in range(4):
@@ -52,7 +53,8 @@ def test_sharded_criteo_equals_oracle(world):
     assert all(e.global_step == 4 for e in engs)
 
 
-def test_sharded_ml100k_hot_rows_world2():
+@pytest.mark.parametrize("p2p", [False, True])
+def test_sharded_ml100k_hot_rows_world2(p2p):
     cols, dtypes = ml100k_columns()
     kw = dict(embedding_size=4, hidden_units=(16, 16), feature_dtypes=dtypes)
     ref = DeepFMEngine(cols, (), max_batch=2048, **kw)
@@ -60,7 +62,7 @@ def test_sharded_ml100k_hot_rows_world2():
     engs = [DeepFMEngine(cols, (), max_batch=1024, rank=r, world=2, **kw) for r in range(2)]
     for e in engs:
         e.set_weights_sharded(w)
-    vc = VirtualCluster(engs)
+    vc = VirtualCluster(engs, p2p=p2p)
     ml, rng = synth.ML100K(), np.random.default_rng(24)
     for step in range(3):
         feats, y = ml.batch(2048, rng)
@@ -72,7 +74,8 @@ def test_sharded_ml100k_hot_rows_world2():
     assert_state_close(vc.state(_names(engs[0])), ora.state(), 1e-5, 1e-7, "sharded-ml", ora.state64())
 
 
-def test_sharded_multi_hot_world2():
+@pytest.mark.parametrize("p2p", [False, True])
+def test_sharded_multi_hot_world2(p2p):
     """multivalent columns through the row-sharded path (slots are looked up at their owners, pooled locally)."""
     from recommender_tensorflow_b200.trainers import ml_100k
     from tests.test_gpu_parity import _bag_setup
@@ -84,7 +87,7 @@ def test_sharded_multi_hot_world2():
     engs = [DeepFMEngine(cols, (), max_batch=256, rank=r, world=2, **kw) for r in range(2)]
     for e in engs:
         e.set_weights_sharded(w)
-    vc = VirtualCluster(engs)
+    vc = VirtualCluster(engs, p2p=p2p)
     for step in range(3):
         _, feats, y = _bag_setup(512, rng, ml)
         pbs = [e.pack({k: v[r * 256:(r + 1) * 256] for k, v in feats.items()}, y[r * 256:(r + 1) * 256], device=True)
@@ -93,3 +96,57 @@ def test_sharded_multi_hot_world2():
         rloss, rlogits = ora.train_step_raw(feats, y)
         assert_step_close(loss, logits, ora, rloss, rlogits, 1e-5, "sharded-bags step %d" % step)
     assert_state_close(vc.state(_names(engs[0])), ora.state(), 1e-5, 1e-7, "sharded-bags", ora.state64())
+
+
+def test_p2p_exchange_bit_identical_to_collectives():
+    """The fused peer-memory exchange only changes WHERE rows travel, never a value: after the same steps the
+    shards of a p2p cluster equal the shards of the all_to_all cluster bit for bit."""
+    cats, nums = synth.criteo_columns(2000, n_cat=8, n_num=4)
+    kw = dict(embedding_size=16, hidden_units=(32, 16))
+    world, per = 4, 512
+    clusters = []
+    for p2p in (False, True):
+        engs = [DeepFMEngine(cats, nums, max_batch=per, rank=r, world=world, **kw) for r in range(world)]
+        for e in engs:
+            e.init_random(5)
+        clusters.append(VirtualCluster(engs, p2p=p2p))
+    rng = np.random.default_rng(90)
+    for step in range(5):
+        feats, y = synth.criteo_batch(world * per, rng, key_space=4000)
+        losses = []
+        for vc in clusters:
+            pbs = []
+            for r, e in enumerate(vc.engs):
+                fr = {}
+                for k, v in feats.items():
+                    if isinstance(v, tuple):
+                        data, offs = v
+                        o = offs[r * per:(r + 1) * per + 1]
+                        fr[k] = (data[o[0]:o[-1]].copy(), (o - o[0]).astype(np.int32))
+                    else:
+                        fr[k] = v[r * per:(r + 1) * per]
+                pbs.append(e.pack(fr, y[r * per:(r + 1) * per], device=True))
+            losses.append(vc.train_step(pbs))
+        assert losses[0] == losses[1], step
+    for ea, eb in zip(clusters[0].engs, clusters[1].engs):
+        ea.flush(); eb.flush()
+        for n in _names(ea):
+            assert np.array_equal(ea.get_tensor(n), eb.get_tensor(n)), n
+
+
+def test_p2p_ipc_two_processes():
+    """Real thing: two processes, two GPUs, receive buffers mapped through CUDA IPC; the P2P trainer must match
+    the NCCL all_to_all trainer bit for bit (tests/p2p_worker.py).  Needs >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29531", os.path.join(root, "tests", "p2p_worker.py")]
+    env = dict(os.environ, NCCL_DEBUG="WARN", PYTHONPATH=root)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "P2P_OK" in r.stdout
