@@ -1678,10 +1678,12 @@ extern "C" int dfm_test_fingerprint64(const uint8_t* bytes_dev, const int32_t* o
 // ------------------------------------------------------------------------- tensor-core GEMM host
 // C[M,N] = A[M,K] * B[N,K]^T  (both K-major).  A_lo / B_lo == nullptr -> the operand is split into
 // tf32 hi/lo inside the kernel; otherwise hi/lo were produced beforehand (weights).
+static unsigned long long* g_tc_ts = nullptr;   // experiments only (DFM_TC_TS in dfm_test_tc_gemm)
 static int tc_gemm_kmajor(dfm_handle* h, const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
                           float* C, int ldc, int M, int N, int K, int epi, const EpiArgs& ep, cudaStream_t st) {
-    const int BN = N > 128 ? 256 : 128;
-    const int bk = TC_BK;
+    static const int persist = getenv("DFM_TC_PERSIST") ? atoi(getenv("DFM_TC_PERSIST")) : 1;   // 0: one CTA per tile (A/B runs)
+    const int BN = persist ? tc::P_BN : N > 128 ? 256 : 128;
+    const int bk = persist ? tc::P_BK : TC_BK;
     const int ntile = (N + BN - 1) / BN;
     const int bn = std::min(BN, ((N + ntile - 1) / ntile + 15) / 16 * 16);   // equal tiles, multiple of 16 (UMMA N granularity)
     CUtensorMap ma, mal, mb, mbl;
@@ -1693,8 +1695,14 @@ static int tc_gemm_kmajor(dfm_handle* h, const float* A_hi, const float* A_lo, i
     p.split_a = A_lo ? 0 : 1; p.split_b = B_lo ? 0 : 1;
     p.bn = bn;
     if (const char* e = getenv("DFM_TC_DBG")) p.dbg = atoi(e);
+    p.ts = g_tc_ts;
     dim3 grid(cdiv(N, bn), cdiv(M, tc::BM), 1);
-    if (BN == 256) tc::gemm_kernel<256, 0, TC_BK><<<grid, tc::NTHREADS, tc::Smem<256, TC_BK>::TOTAL, st>>>(ma, mal, mb, mbl, p);
+    if (persist) {
+        static int sms = 0;
+        if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+        const int tiles = cdiv(N, bn) * cdiv(M, tc::BM);
+        tc::gemm_persist_kernel<tc::P_BK><<<std::min(tiles, sms), tc::P_THREADS, tc::PSmem<tc::P_BK>::TOTAL, st>>>(ma, mal, mb, mbl, p);
+    } else if (BN == 256) tc::gemm_kernel<256, 0, TC_BK><<<grid, tc::NTHREADS, tc::Smem<256, TC_BK>::TOTAL, st>>>(ma, mal, mb, mbl, p);
     else tc::gemm_kernel<128, 0, TC_BK><<<grid, tc::NTHREADS, tc::Smem<128, TC_BK>::TOTAL, st>>>(ma, mal, mb, mbl, p);
     if (h) h->launches++;
     CK(cudaGetLastError());
@@ -1733,6 +1741,7 @@ static int tc_setup_once() {
     e = cudaFuncSetAttribute(tc::gemm_kernel<128, 0, TC_BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<128, TC_BK>::TOTAL); if (e) return done = -1;
     e = cudaFuncSetAttribute(tc::gemm_kernel<256, 1, TC_BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<256, TC_BK>::TOTAL); if (e) return done = -1;
     e = cudaFuncSetAttribute(tc::gemm_kernel<128, 1, TC_BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<128, TC_BK>::TOTAL); if (e) return done = -1;
+    e = cudaFuncSetAttribute(tc::gemm_persist_kernel<tc::P_BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::PSmem<tc::P_BK>::TOTAL); if (e) return done = -1;
     return done = 1;
 }
 
@@ -1751,6 +1760,67 @@ extern "C" int dfm_test_tc_gemm(int32_t mode, const float* A, const float* B, fl
         tc::split_tf32_kernel<<<cdiv((int64_t)N * K, 256), 256>>>(B, (int64_t)N * K, bh, bl);
         rc = tc_gemm_kmajor(nullptr, A, nullptr, K, bh, bl, K, C, N, M, N, K, EPI_NONE, ep, 0);
         CK(cudaDeviceSynchronize());
+        if (getenv("DFM_TC_TS") && rc == DFM_OK) {
+            // per-CTA phase timeline of one warm launch (ns, globaltimer), printed as a summary on stderr
+            const int nct = cdiv(M, tc::BM) * 4;
+            unsigned long long* ts = nullptr;
+            CK(cudaMalloc(&ts, (size_t)nct * 8 * 8));
+            CK(cudaMemset(ts, 0, (size_t)nct * 8 * 8));
+            if (getenv("DFM_TC_FLUSH")) {     // evict the operands from L2 first (the in-step situation)
+                void* junk = nullptr;
+                CK(cudaMalloc(&junk, (size_t)512 << 20));
+                CK(cudaMemset(junk, 1, (size_t)512 << 20));
+                CK(cudaDeviceSynchronize());
+                cudaFree(junk);
+            }
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            g_tc_ts = ts;
+            cudaEventRecord(e0, 0);
+            rc = tc_gemm_kmajor(nullptr, A, nullptr, K, bh, bl, K, C, N, M, N, K, EPI_NONE, ep, 0);
+            cudaEventRecord(e1, 0);
+            g_tc_ts = nullptr;
+            CK(cudaDeviceSynchronize());
+            float ems = 0.f;
+            cudaEventElapsedTime(&ems, e0, e1);
+            fprintf(stderr, "[tc-ts] launch %.1f us (events)%s\n", ems * 1e3, getenv("DFM_TC_FLUSH") ? " after L2 flush" : "");
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            std::vector<unsigned long long> hts((size_t)nct * 8);
+            CK(cudaMemcpy(hts.data(), ts, hts.size() * 8, cudaMemcpyDeviceToHost));
+            cudaFree(ts);
+            static const int persist = getenv("DFM_TC_PERSIST") ? atoi(getenv("DFM_TC_PERSIST")) : 1;
+            if (persist) {
+                double acc[8] = {0}; int n = 0;
+                for (int c = 0; c < 148 && c < nct; ++c) {
+                    const unsigned long long* e = &hts[(size_t)c * 8];
+                    if (!e[0]) continue;
+                    ++n;
+                    for (int k = 0; k < 8; ++k) acc[k] += (double)e[k];
+                }
+                fprintf(stderr, "[tc-ts persist] M=%d N=%d K=%d ctas=%d mean cycles: total=%.0f | tma wait_empty=%.0f | mma wait_split=%.0f wait_acc_empty=%.0f | "
+                                "split wait_full=%.0f busy=%.0f | epi wait_acc_full=%.0f busy=%.0f\n",
+                        M, N, K, n, acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[6] / n, acc[5] / n, acc[7] / n);
+            } else {
+            unsigned long long t0 = ~0ull, t1 = 0; int n = 0;
+            double acc[7] = {0};
+            for (int c = 0; c < nct; ++c) {
+                const unsigned long long* e = &hts[(size_t)c * 8];
+                if (!e[0]) continue;
+                ++n; t0 = std::min(t0, e[0]); t1 = std::max(t1, e[6]);
+                for (int k = 1; k < 7; ++k) acc[k] += (double)(e[k] - e[0]);
+            }
+            fprintf(stderr, "[tc-ts] M=%d N=%d K=%d ctas=%d makespan=%.1f us | mean ns since CTA start: tma_issued=%.0f mma_issued=%.0f first_split=%.0f last_split=%.0f accum_done=%.0f end=%.0f\n",
+                    M, N, K, n, (t1 - t0) * 1e-3, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n, acc[6] / n);
+            // CTAs per SM and the idle gaps between consecutive CTAs of SM 0's timeline
+            std::vector<std::pair<unsigned long long, unsigned long long>> sm0;
+            const unsigned long long sm_first = hts[7];
+            for (int c = 0; c < nct; ++c) if (hts[(size_t)c * 8] && hts[(size_t)c * 8 + 7] == sm_first) sm0.push_back({hts[(size_t)c * 8], hts[(size_t)c * 8 + 6]});
+            std::sort(sm0.begin(), sm0.end());
+            fprintf(stderr, "[tc-ts] SM %llu timeline (start,end us rel.):", sm_first);
+            for (auto& pr : sm0) fprintf(stderr, " (%.1f,%.1f)", (pr.first - t0) * 1e-3, (pr.second - t0) * 1e-3);
+            fprintf(stderr, "\n");
+            }
+        }
         cudaFree(bh); cudaFree(bl);
     } else {
         float* part = nullptr;

@@ -128,9 +128,77 @@ struct Params {
     EpiArgs ep;
     int split_a, split_b;     // 1: operand is raw fp32, split in the kernel; 0: hi/lo come from two tensor maps
     int dbg;                  // experiments only: 1 = skip the split work, 2 = skip the MMAs
+    unsigned long long* ts;   // experiments only: per-CTA phase timestamps (8 per CTA), see dfm_test_tc_gemm mode 2
     int bn;                   // output columns per CTA (multiple of 16, <= BN): N is cut into equal tiles so that
                               // e.g. N = 416 runs as 2 x 208 instead of 256 + 160 (37% of the second tile wasted)
 };
+
+// Fused epilogue of one 128 x bn output tile.  Warp (q, half): TMEM lanes [32q, 32q+32), 32-column chunks half, half+2, ...
+// Each 32x32 block is transposed through the warp's shared-memory staging area `tb` (TMEM yields one row per lane) so
+// that every global access is a coalesced 16-byte-per-lane access, with all loads of a block issued up front.
+__device__ __forceinline__ void epilogue_tile(const Params& p, float* __restrict__ Cz, float* tb, uint32_t tmem_main, uint32_t tmem_cross,
+                                              int m0, int n0, int bn, int q, int half, int lane) {
+    const int row0 = m0 + q * 32;
+    const int rsub = lane >> 3, cg = lane & 7;
+    for (int c0 = half * 32; c0 < bn; c0 += 64) {
+        if (n0 + c0 >= p.N) break;
+        {
+            float v[32], vx[32];
+            tmem_ld32(tmem_main + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld32(tmem_cross + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, vx);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(tb + lane * 36 + 4 * j) =
+                    make_float4(v[4 * j] + vx[4 * j], v[4 * j + 1] + vx[4 * j + 1], v[4 * j + 2] + vx[4 * j + 2], v[4 * j + 3] + vx[4 * j + 3]);
+        }
+        __syncwarp();
+        const int n = n0 + c0 + cg * 4;
+        const bool nok = n < p.N && (c0 + cg * 4) < bn;   // N % 4 == 0 and bn % 16 == 0 on this path
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.epi == EPI_BIAS_RELU && nok) bias4 = __ldg(reinterpret_cast<const float4*>(p.ep.bias + n));
+        const int nk = (p.epi == EPI_DE) ? (n % p.ep.K) : 0;
+        float4 xa[8], xs[8];
+        float xd[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int gm = row0 + it * 4 + rsub;
+            xa[it] = make_float4(0.f, 0.f, 0.f, 0.f); xs[it] = xa[it]; xd[it] = 0.f;
+            if (nok && gm < p.M) {
+                if (p.epi == EPI_MASK) xa[it] = __ldg(reinterpret_cast<const float4*>(p.ep.act + (size_t)gm * p.ep.ld_act + n));
+                else if (p.epi == EPI_DE && p.ep.s) {
+                    xa[it] = __ldg(reinterpret_cast<const float4*>(p.ep.act + (size_t)gm * p.ep.ld_act + n));
+                    xs[it] = __ldg(reinterpret_cast<const float4*>(p.ep.s + (size_t)gm * p.ep.K + nk));
+                    xd[it] = __ldg(p.ep.dz + gm);
+                }
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + rsub, gm = row0 + r;
+            float4 x = *reinterpret_cast<const float4*>(tb + r * 36 + cg * 4);
+            if (p.epi == EPI_BIAS_RELU) {
+                x.x = fmaxf(x.x + bias4.x, 0.f); x.y = fmaxf(x.y + bias4.y, 0.f);
+                x.z = fmaxf(x.z + bias4.z, 0.f); x.w = fmaxf(x.w + bias4.w, 0.f);
+                if (p.ep.drop_keep > 0.f) {
+                    const uint64_t e0 = (uint64_t)(p.ep.drop_row0 + gm) * p.N + n;
+                    x.x *= dfm_drop(p.ep.drop_key, e0, p.ep.drop_keep, p.ep.drop_inv);
+                    x.y *= dfm_drop(p.ep.drop_key, e0 + 1, p.ep.drop_keep, p.ep.drop_inv);
+                    x.z *= dfm_drop(p.ep.drop_key, e0 + 2, p.ep.drop_keep, p.ep.drop_inv);
+                    x.w *= dfm_drop(p.ep.drop_key, e0 + 3, p.ep.drop_keep, p.ep.drop_inv);
+                }
+            } else if (p.epi == EPI_MASK) {
+                const float sc = p.ep.bwd_scale > 0.f ? p.ep.bwd_scale : 1.f;
+                x.x = xa[it].x > 0.f ? x.x * sc : 0.f; x.y = xa[it].y > 0.f ? x.y * sc : 0.f;
+                x.z = xa[it].z > 0.f ? x.z * sc : 0.f; x.w = xa[it].w > 0.f ? x.w * sc : 0.f;
+            } else if (p.epi == EPI_DE && p.ep.s) {
+                x.x += xd[it] * (xs[it].x - xa[it].x); x.y += xd[it] * (xs[it].y - xa[it].y);
+                x.z += xd[it] * (xs[it].z - xa[it].z); x.w += xd[it] * (xs[it].w - xa[it].w);
+            }
+            if (nok && gm < p.M) *reinterpret_cast<float4*>(Cz + (size_t)gm * p.ldc + n) = x;
+        }
+        __syncwarp();
+    }
+}
 
 template <int BN, int BK>
 struct Smem {
@@ -138,6 +206,8 @@ struct Smem {
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = (192 * 1024) / STAGE > 8 ? 8 : (192 * 1024) / STAGE;
+    static_assert(STAGES >= 2, "operand ring needs two stages");
+    static_assert(STAGES * STAGE >= 8 * 32 * 36 * 4, "epilogue transposes through the operand stages");
     static constexpr int TOTAL = STAGES * STAGE + 1024 /*align*/ + 512 /*barriers*/;
 };
 
@@ -181,6 +251,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    auto stamp = [&](int slot) {
+        if (p.ts) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.ts[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+        }
+    };
+    if (threadIdx.x == 0) {
+        stamp(0);
+        if (p.ts) { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); p.ts[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + 7] = smid; }
+    }
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -204,6 +285,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
                     tma_load_3d(b_hi, &mapB_hi, &full[s], 0, k0, n0 / 32);
                 }
             }
+            stamp(1);      // last TMA issued
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
@@ -234,6 +316,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
                 umma_commit(&empty[s]);
             }
             umma_commit(accum);
+            stamp(2);      // last MMA issued
         }
     } else {
         // ------------------------------------------------------------------ splitters (warps 2..7, 192 threads)
@@ -286,7 +369,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
             mbar_arrive(&split[s]);
+            if (t == 0 && kb == 0) stamp(3);          // first stage landed and split
         }
+        if (t == 0) stamp(4);                         // last split done
     }
     {
         // ------------------------------------------------------------------ epilogue (all 8 warps)
@@ -297,75 +382,217 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
         __syncwarp();
         const int q = warp & 3, half = warp >> 2;
         mbar_wait(accum, 0);
+        if (threadIdx.x == 64) stamp(5);              // accumulator complete
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* Cz = p.C + (size_t)blockIdx.z * p.c_split_stride;
         float* tb = reinterpret_cast<float*>(smem) + warp * (32 * 36);
-        const int row0 = m0 + q * 32;
-        const int rsub = lane >> 3, cg = lane & 7;
-        for (int c0 = half * 32; c0 < bn; c0 += 64) {
-            if (n0 + c0 >= p.N) break;
-            {
-                float v[32], vx[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), vx);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(tb + lane * 36 + 4 * j) =
-                        make_float4(v[4 * j] + vx[4 * j], v[4 * j + 1] + vx[4 * j + 1], v[4 * j + 2] + vx[4 * j + 2], v[4 * j + 3] + vx[4 * j + 3]);
-            }
-            __syncwarp();
-            const int n = n0 + c0 + cg * 4;
-            const bool nok = n < p.N && (c0 + cg * 4) < bn;   // N % 4 == 0 and bn % 16 == 0 on this path
-            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.epi == EPI_BIAS_RELU && nok) bias4 = __ldg(reinterpret_cast<const float4*>(p.ep.bias + n));
-            const int nk = (p.epi == EPI_DE) ? (n % p.ep.K) : 0;
-            float4 xa[8], xs[8];
-            float xd[8];
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int gm = row0 + it * 4 + rsub;
-                xa[it] = make_float4(0.f, 0.f, 0.f, 0.f); xs[it] = xa[it]; xd[it] = 0.f;
-                if (nok && gm < p.M) {
-                    if (p.epi == EPI_MASK) xa[it] = __ldg(reinterpret_cast<const float4*>(p.ep.act + (size_t)gm * p.ep.ld_act + n));
-                    else if (p.epi == EPI_DE && p.ep.s) {
-                        xa[it] = __ldg(reinterpret_cast<const float4*>(p.ep.act + (size_t)gm * p.ep.ld_act + n));
-                        xs[it] = __ldg(reinterpret_cast<const float4*>(p.ep.s + (size_t)gm * p.ep.K + nk));
-                        xd[it] = __ldg(p.ep.dz + gm);
-                    }
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int r = it * 4 + rsub, gm = row0 + r;
-                float4 x = *reinterpret_cast<const float4*>(tb + r * 36 + cg * 4);
-                if (p.epi == EPI_BIAS_RELU) {
-                    x.x = fmaxf(x.x + bias4.x, 0.f); x.y = fmaxf(x.y + bias4.y, 0.f);
-                    x.z = fmaxf(x.z + bias4.z, 0.f); x.w = fmaxf(x.w + bias4.w, 0.f);
-                    if (p.ep.drop_keep > 0.f) {
-                        const uint64_t e0 = (uint64_t)(p.ep.drop_row0 + gm) * p.N + n;
-                        x.x *= dfm_drop(p.ep.drop_key, e0, p.ep.drop_keep, p.ep.drop_inv);
-                        x.y *= dfm_drop(p.ep.drop_key, e0 + 1, p.ep.drop_keep, p.ep.drop_inv);
-                        x.z *= dfm_drop(p.ep.drop_key, e0 + 2, p.ep.drop_keep, p.ep.drop_inv);
-                        x.w *= dfm_drop(p.ep.drop_key, e0 + 3, p.ep.drop_keep, p.ep.drop_inv);
-                    }
-                } else if (p.epi == EPI_MASK) {
-                    const float sc = p.ep.bwd_scale > 0.f ? p.ep.bwd_scale : 1.f;
-                    x.x = xa[it].x > 0.f ? x.x * sc : 0.f; x.y = xa[it].y > 0.f ? x.y * sc : 0.f;
-                    x.z = xa[it].z > 0.f ? x.z * sc : 0.f; x.w = xa[it].w > 0.f ? x.w * sc : 0.f;
-                } else if (p.epi == EPI_DE && p.ep.s) {
-                    x.x += xd[it] * (xs[it].x - xa[it].x); x.y += xd[it] * (xs[it].y - xa[it].y);
-                    x.z += xd[it] * (xs[it].z - xa[it].z); x.w += xd[it] * (xs[it].w - xa[it].w);
-                }
-                if (nok && gm < p.M) *reinterpret_cast<float4*>(Cz + (size_t)gm * p.ldc + n) = x;
-            }
-            __syncwarp();
-        }
+        epilogue_tile(p, Cz, tb, tmem_base, tmem_base + BN, m0, n0, bn, q, half, lane);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
+    if (threadIdx.x == 0) stamp(6);                   // epilogue done
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Persistent variant for the K-major GEMMs (forward and backward-data of the tower).  The per-CTA timeline of the
+// kernel above (globaltimer stamps, M=65536 N=256 K=160) is: 1.1 us launch gap, 1.8 us until the first stage is
+// usable, 6 us main loop, 5.8 us epilogue, strictly one after the other and in lock-step on all SMs, so HBM sees a
+// read burst followed by a write burst.  Here one CTA per SM walks over the output tiles and the phases overlap:
+//   * tiles are 128 x bn with bn <= 128, so TMEM holds TWO accumulator sets (main + cross, 2 x 256 columns): the
+//     MMA warp fills set (j+1)&1 while the epilogue warps drain set j&1 ("acc_full" / "acc_empty" mbarriers);
+//   * the operand ring keeps running across tile boundaries (TMA, split and MMA never drain between tiles);
+//   * the epilogue has its own 8 warps and its own staging memory.
+// Warps: 0 TMA, 1 MMA, 2..5 splitters (128 threads), 6..13 epilogue (warp w: TMEM lane quarter w % 4).
+constexpr int P_BN = 128;
+constexpr int P_BK = 16;        // 32 KB stages -> a 5-deep operand ring (the 2-deep ring of BK = 32 left every role waiting)
+constexpr int P_THREADS = 448;
+constexpr int P_SPLIT_THREADS = 128;
+constexpr int P_EPI_WARPS = 8;
+
+// In-place hi/lo split of one landed operand tile by the P_SPLIT_THREADS splitter threads.  All loads of a thread are
+// issued before its first store: hi[] is read and written, so the compiler would otherwise order every load behind the
+// previous store and the loop would run at one shared-memory round trip per element group.
+template <int CAP4>
+__device__ __forceinline__ void split_tile(uint8_t* hi_bytes, uint8_t* lo_bytes, int n4, int tt) {
+    constexpr int PER = (CAP4 + P_SPLIT_THREADS - 1) / P_SPLIT_THREADS;
+    float4* hi = reinterpret_cast<float4*>(hi_bytes);
+    float4* lo = reinterpret_cast<float4*>(lo_bytes);
+    float4 x[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int i = tt + u * P_SPLIT_THREADS;
+        if (i < n4) x[u] = hi[i];
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int i = tt + u * P_SPLIT_THREADS;
+        if (i < n4) {
+            const float4 h = make_float4(tf32_hi(x[u].x), tf32_hi(x[u].y), tf32_hi(x[u].z), tf32_hi(x[u].w));
+            hi[i] = h;
+            lo[i] = make_float4(tf32_hi(x[u].x - h.x), tf32_hi(x[u].y - h.y), tf32_hi(x[u].z - h.z), tf32_hi(x[u].w - h.w));
+        }
+    }
+}
+
+template <int BK>
+struct PSmem {
+    static constexpr int A_BYTES = BM * BK * 4;
+    static constexpr int B_BYTES = P_BN * BK * 4;
+    static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGING = P_EPI_WARPS * 32 * 36 * 4;
+    static constexpr int STAGES = (224 * 1024 - STAGING - 2048) / STAGE;
+    static_assert(STAGES >= 2, "operand ring needs two stages");
+    static constexpr int TOTAL = STAGES * STAGE + STAGING + 1024 /*align*/ + 512 /*barriers*/;
+};
+
+template <int BK>
+__global__ void __launch_bounds__(P_THREADS, 1) gemm_persist_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                                                                    const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
+                                                                    Params p) {
+    using S = PSmem<BK>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* staging = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE + S::STAGING);
+    uint64_t* full = bars;                          // [STAGES] TMA landed
+    uint64_t* split = bars + S::STAGES;             // [STAGES] hi/lo ready
+    uint64_t* empty = bars + 2 * S::STAGES;         // [STAGES] MMAs that read the stage retired
+    uint64_t* acc_full = bars + 3 * S::STAGES;      // [2] accumulator set complete
+    uint64_t* acc_empty = bars + 3 * S::STAGES + 2; // [2] accumulator set drained by the epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S::STAGES + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bn = p.bn;
+    const int ntile = (p.N + bn - 1) / bn;
+    const int total = ((p.M + BM - 1) / BM) * ntile;
+    const int nkb = (p.K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&split[s], P_SPLIT_THREADS);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], P_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    // experiments only (p.ts != nullptr): cycles each role spends waiting, per CTA
+    unsigned long long* ts = p.ts ? p.ts + (size_t)blockIdx.x * 8 : nullptr;
+    long long w0 = 0, w1 = 0, c_begin = clock64();
+#define TS_WAIT(acc, stmt) do { if (ts) { long long c0_ = clock64(); stmt; acc += clock64() - c0_; } else { stmt; } } while (0)
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            const uint32_t b_bytes = (uint32_t)bn * BK * 4;
+            const uint32_t bytes = (p.split_a ? S::A_BYTES : 2 * S::A_BYTES) + (p.split_b ? b_bytes : 2 * b_bytes);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int m0 = (t / ntile) * BM, n0 = (t % ntile) * bn;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t s = it % S::STAGES;
+                    TS_WAIT(w0, mbar_wait(&empty[s], ((it / S::STAGES) & 1) ^ 1));     // passes at once on the first lap
+                    uint8_t* st = smem + s * S::STAGE;
+                    uint8_t *a_hi = st, *a_lo = st + S::A_BYTES, *b_hi = st + 2 * S::A_BYTES, *b_lo = st + 2 * S::A_BYTES + S::B_BYTES;
+                    mbar_expect_tx(&full[s], bytes);
+                    const int k0 = kb * BK;
+                    tma_load_2d(a_hi, &mapA_hi, &full[s], k0, m0);
+                    if (!p.split_a) tma_load_2d(a_lo, &mapA_lo, &full[s], k0, m0);
+                    tma_load_2d(b_hi, &mapB_hi, &full[s], k0, n0);
+                    if (!p.split_b) tma_load_2d(b_lo, &mapB_lo, &full[s], k0, n0);
+                }
+            }
+            if (ts) { ts[1] = w0; }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(bn, false, false);
+            uint32_t it = 0, j = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+                const uint32_t buf = j & 1;
+                TS_WAIT(w1, mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1));           // the epilogue drained this set (first use: free)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_main = tmem_base + buf * (2 * P_BN), d_cross = d_main + P_BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t s = it % S::STAGES;
+                    TS_WAIT(w0, mbar_wait(&split[s], (it / S::STAGES) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = smem_u32(smem + s * S::STAGE);
+                    const uint32_t a_hi = st, a_lo = st + S::A_BYTES, b_hi = st + 2 * S::A_BYTES, b_lo = st + 2 * S::A_BYTES + S::B_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < ((p.dbg & 2) ? 0 : BK / UMMA_K); ++ks) {
+                        const uint32_t adv = ks * UMMA_K * 4;
+                        const uint32_t lbo = 16, sbo = 8 * BK * 4, lt = BK == 32 ? 2 : 4;
+                        const uint64_t dah = make_desc(a_hi + adv, lbo, sbo, lt), dal = make_desc(a_lo + adv, lbo, sbo, lt);
+                        const uint64_t dbh = make_desc(b_hi + adv, lbo, sbo, lt), dbl = make_desc(b_lo + adv, lbo, sbo, lt);
+                        umma_tf32(d_main, dah, dbh, idesc, (kb | ks) != 0);
+                        umma_tf32(d_cross, dal, dbh, idesc, (kb | ks) != 0);
+                        umma_tf32(d_cross, dah, dbl, idesc, 1);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&acc_full[buf]);
+            }
+            if (ts) { ts[2] = w0; ts[3] = w1; }
+        }
+    } else if (warp < 2 + P_SPLIT_THREADS / 32) {
+        // ------------------------------------------------------------------ splitters
+        const int tt = threadIdx.x - 64;
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const uint32_t s = it % S::STAGES;
+                TS_WAIT(w0, mbar_wait(&full[s], (it / S::STAGES) & 1));
+                uint8_t* st = smem + s * S::STAGE;
+                if (p.split_a && !(p.dbg & 1)) split_tile<S::A_BYTES / 16>(st, st + S::A_BYTES, S::A_BYTES / 16, tt);
+                if (p.split_b && !(p.dbg & 1)) split_tile<S::B_BYTES / 16>(st + 2 * S::A_BYTES, st + 2 * S::A_BYTES + S::B_BYTES, bn * BK * 4 / 16, tt);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+                mbar_arrive(&split[s]);
+            }
+        }
+        if (ts && tt == 0) { ts[4] = w0; ts[6] = clock64() - c_begin - w0; }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 6..13)
+        const int ew = warp - (2 + P_SPLIT_THREADS / 32);
+        const int q = warp & 3, half = ew >> 2;      // TMEM lane quarter is fixed by warp % 4
+        float* tb = staging + ew * (32 * 36);
+        uint32_t j = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+            const int m0 = (t / ntile) * BM, n0 = (t % ntile) * bn;
+            const uint32_t buf = j & 1;
+            TS_WAIT(w0, mbar_wait(&acc_full[buf], (j >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_main = tmem_base + buf * (2 * P_BN);
+            epilogue_tile(p, p.C, tb, d_main, d_main + P_BN, m0, n0, bn, q, half, lane);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        if (ts && ew == 0 && lane == 0) { ts[5] = w0; ts[7] = clock64() - c_begin - w0; }
+    }
+#undef TS_WAIT
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (ts && threadIdx.x == 0) ts[0] = clock64() - c_begin;
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
     }
 }
 
