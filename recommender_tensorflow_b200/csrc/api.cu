@@ -1276,8 +1276,10 @@ static int shard_serve_impl(dfm_handle* h, const uint32_t* recv_rows, int64_t n_
     if (rc) return rc;
     if ((rc = catchup_touched<K>(h, h->ws_own, n_recv, t, st))) return rc;
     if (n_recv > 0) {
-        shard_serve_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(recv_rows, n_recv, h->tb, (bool)h->need_emb,
-                                                                          (bool)h->use_linear, reply, K + 4, route);
+        if (route) shard_serve_p2p_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(recv_rows, n_recv, h->tb, (bool)h->need_emb,
+                                                                                        (bool)h->use_linear, route);
+        else shard_serve_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(recv_rows, n_recv, h->tb, (bool)h->need_emb,
+                                                                              (bool)h->use_linear, reply, K + 4);
         h->launches++;
     }
     h->shard_n_recv = n_recv;

@@ -607,6 +607,9 @@ __global__ void __launch_bounds__(256) piece_reduce_kernel(const uint32_t* __res
 // level 2 + optimizer: one lane group per unique row.  Rows with <= DIRECT_T lookups sum their
 // gradients straight from dE in sorted (= sample) order; hot rows sum their piece sums in order.
 // Then the sparse optimizer step for that row (Adam: rows were caught up to t-1 beforehand).
+template <int K>
+__host__ __device__ constexpr int rt_tile_floats() { return 8 * (32 / (K / 4)) * (K + 4); }   // 8 warps x rows per warp x row width
+
 template <int K, bool BAGS>
 __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restrict__ urow, const uint32_t* __restrict__ uval,
                                                          const uint32_t* __restrict__ svals,
@@ -631,7 +634,10 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
     // row mapping: within one trip the lane groups of a warp take rows n_warps apart
     const uint32_t TG = gridDim.x * gpb, gid = blockIdx.x * gpb + threadIdx.x / LPR;
     const uint32_t gpw = 32 / LPR, n_warps = TG / gpw;
-    const uint32_t uoff = (gid % gpw) * n_warps + gid / gpw;
+    // fused exchange (rt): consecutive rows go to consecutive addresses of one peer, so there the warp keeps
+    // consecutive rows and emits them as one contiguous store through shared memory
+    const uint32_t uoff = rt ? gid : (gid % gpw) * n_warps + gid / gpw;
+    __shared__ __align__(16) float gtile[rt_tile_floats<K>()];
     for (uint32_t ubase = 0; ubase < U; ubase += TG) {   // block-uniform trip count
         const uint32_t u = ubase + uoff;
         bool coop = false;
@@ -734,15 +740,36 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
                 if (lane / LPR == src_lane / LPR) { g = a; gl = al; }
             }
         }
+        if (rt) {   // fused exchange: the gradient rows go straight into their owners' receive buffers over NVLink
+            constexpr int RW = K + 4, RW4 = RW / 4;
+            const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+            float* tl = gtile + wib * (gpw * RW);
+            const int r = lane / LPR;
+            reinterpret_cast<float4*>(tl + r * RW)[sub] = g;
+            if (sub == 0) *reinterpret_cast<float4*>(tl + r * RW + K) = make_float4(gl, 0.f, 0.f, 0.f);
+            __syncwarp();
+            const uint32_t u0 = ubase + (blockIdx.x * gpb + wib * gpw);       // first row of this warp
+            if (u0 < U) {
+                const uint32_t cnt = min(gpw, U - u0);
+                const int o0 = route_find(rt->send_off, rt->W, u0), o1 = route_find(rt->send_off, rt->W, u0 + cnt - 1);
+                if (o0 == o1) {
+                    float4* dst = reinterpret_cast<float4*>(rt->peer_grecv[o0] + (size_t)(rt->dst_off[o0] + (u0 - rt->send_off[o0])) * RW);
+                    for (uint32_t j = lane; j < cnt * RW4; j += 32) dst[j] = reinterpret_cast<const float4*>(tl)[j];
+                } else {
+                    for (uint32_t q = 0; q < cnt; ++q) {
+                        const uint32_t uu = u0 + q;
+                        const int o = route_find(rt->send_off, rt->W, uu);
+                        float4* dst = reinterpret_cast<float4*>(rt->peer_grecv[o] + (size_t)(rt->dst_off[o] + (uu - rt->send_off[o])) * RW);
+                        if (lane < RW4) dst[lane] = reinterpret_cast<const float4*>(tl + q * RW)[lane];
+                    }
+                }
+            }
+            __syncwarp();
+            continue;
+        }
         if (!act) continue;
         if (gsum_out) {   // sharded requester side: emit the per-row gradient sum, the owner applies it
-            float* gp;
-            if (rt) {   // fused exchange: the gradient row goes straight into its owner's receive buffer over NVLink
-                const int o = route_find(rt->send_off, rt->W, u);
-                gp = rt->peer_grecv[o] + (size_t)(rt->dst_off[o] + (u - rt->send_off[o])) * gsum_stride;
-            } else {
-                gp = gsum_out + (size_t)u * gsum_stride;
-            }
+            float* gp = gsum_out + (size_t)u * gsum_stride;
             reinterpret_cast<float4*>(gp)[sub] = g;
             if (sub == 0) gp[K] = gl;
             continue;
@@ -826,23 +853,70 @@ __global__ void iota_kernel(uint32_t* __restrict__ v, int64_t n) {
 template <int K>
 __global__ void __launch_bounds__(256) shard_serve_kernel(const uint32_t* __restrict__ recv_rows, int64_t n,
                                                           Table tb, bool has_emb, bool has_lin,
-                                                          float* __restrict__ reply, int reply_stride,
-                                                          const PeerRoute* __restrict__ rt) {
+                                                          float* __restrict__ reply, int reply_stride) {
     constexpr int LPR = K / 4;
     const int sub = threadIdx.x % LPR;
     const int64_t gpb = blockDim.x / LPR;
     for (int64_t i = (int64_t)blockIdx.x * gpb + threadIdx.x / LPR; i < n; i += (int64_t)gridDim.x * gpb) {
         size_t row = recv_rows[i];
-        float* rp;
-        if (rt) {   // fused exchange: store the row straight into the requester's row buffer over NVLink
-            const int sr = route_find(rt->recv_off, rt->W, (uint32_t)i);
-            rp = rt->peer_rowbuf[sr] + (size_t)(rt->reply_off[sr] + ((uint32_t)i - rt->recv_off[sr])) * reply_stride;
-        } else {
-            rp = reply + (size_t)i * reply_stride;
-        }
+        float* rp = reply + (size_t)i * reply_stride;
         float4 e = has_emb ? __ldg(tab_w(tb, row) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
         reinterpret_cast<float4*>(rp)[sub] = e;
         if (sub == 0) rp[K] = has_lin ? __ldg(reinterpret_cast<const float*>(tab_lin(tb, row))) : 0.f;
+    }
+}
+
+// Owner side of the fused exchange: same rows, but stored straight into the requesters' row buffers over NVLink.
+// Entry i of the receive list goes to row (reply_off[src] + i - recv_off[src]) of source src's buffer, so consecutive
+// entries of one source are CONTIGUOUS at the destination.  A warp therefore stages 32 rows in shared memory and
+// writes them as full 512-byte store instructions (32 rows per chunk; 16 at K = 64) (NVLink moves 64-byte row fragments with holes at a fraction of the
+// bandwidth of full lines); only the chunks that straddle two sources take the row-by-row path.
+template <int K>
+__global__ void __launch_bounds__(256) shard_serve_p2p_kernel(const uint32_t* __restrict__ recv_rows, int64_t n,
+                                                              Table tb, bool has_emb, bool has_lin,
+                                                              const PeerRoute* __restrict__ rt) {
+    constexpr int LPR = K / 4, RPP = 32 / LPR, CH = (1024 / K < 32 ? 1024 / K : 32) /* rows per chunk, bounded by shared memory */, PASSES = CH / RPP, RW = K + 4, RW4 = RW / 4;
+    __shared__ __align__(16) float tile[8][CH * RW];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+    float* tl = tile[warp];
+    const int64_t n_chunks = (n + CH - 1) / CH;
+    for (int64_t chunk = (int64_t)blockIdx.x * 8 + warp; chunk < n_chunks; chunk += (int64_t)gridDim.x * 8) {
+        const int64_t i0 = chunk * CH;
+        const int cnt = (int)min((int64_t)CH, n - i0);
+        float4 e[PASSES];
+        float l[PASSES];
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+            const int r = p * RPP + grp;
+            e[p] = make_float4(0.f, 0.f, 0.f, 0.f); l[p] = 0.f;
+            if (r < cnt) {
+                const size_t row = __ldg(recv_rows + i0 + r);
+                if (has_emb) e[p] = __ldg(tab_w(tb, row) + sub);
+                if (sub == 0 && has_lin) l[p] = __ldg(reinterpret_cast<const float*>(tab_lin(tb, row)));
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+            const int r = p * RPP + grp;
+            reinterpret_cast<float4*>(tl + r * RW)[sub] = e[p];
+            if (sub == 0) *reinterpret_cast<float4*>(tl + r * RW + K) = make_float4(l[p], 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+        const int s_first = route_find(rt->recv_off, rt->W, (uint32_t)i0);
+        const int s_last = route_find(rt->recv_off, rt->W, (uint32_t)(i0 + cnt - 1));
+        if (s_first == s_last) {
+            float4* dst = reinterpret_cast<float4*>(rt->peer_rowbuf[s_first] + (size_t)(rt->reply_off[s_first] + ((uint32_t)i0 - rt->recv_off[s_first])) * RW);
+            const float4* src4 = reinterpret_cast<const float4*>(tl);
+            for (int j = lane; j < cnt * RW4; j += 32) dst[j] = src4[j];
+        } else {
+            for (int r = 0; r < cnt; ++r) {
+                const uint32_t i = (uint32_t)(i0 + r);
+                const int sr = route_find(rt->recv_off, rt->W, i);
+                float4* dst = reinterpret_cast<float4*>(rt->peer_rowbuf[sr] + (size_t)(rt->reply_off[sr] + (i - rt->recv_off[sr])) * RW);
+                if (lane < RW4) dst[lane] = reinterpret_cast<const float4*>(tl + r * RW)[lane];
+            }
+        }
+        __syncwarp();
     }
 }
 
