@@ -203,12 +203,14 @@ int dfm_shard_apply(dfm_handle* h, const float* grecv_dev, const float* dense_gr
 /* ---- The same sharded step with the three exchanges FUSED into the kernels over NVLink peer memory.
  * Every rank's receive buffers (row ids, rows, gradient rows) live in the library and are mapped into the
  * other ranks through CUDA IPC (dfm_shard_ipc_export / _import, handles exchanged by the host once).  Per step:
- *   dfm_shard_requests -> all_gather(counts) -> dfm_shard_p2p_plan        (W x W count matrix -> routing table)
+ *   dfm_shard_requests_dev -> all_gather(counts) -> dfm_shard_p2p_plan    (W x W count matrix -> routing table; the
+ *                                     matrix read-back is the only host synchronisation of the step)
  *   dfm_shard_p2p_push_ids            requesters store their unique row ids into the owners' buffers    | barrier
  *   dfm_shard_p2p_serve               owners catch up and store each row into the requester's row buffer | barrier
  *   dfm_shard_p2p_forward_backward    gradient rows are stored straight into the owners' buffers         | all_reduce(dense)
  *   dfm_shard_p2p_apply
  * "barrier" = any stream-ordered collective (the host uses a 4-byte all_reduce); no payload goes through NCCL. */
+int dfm_shard_requests_dev(dfm_handle* h, const dfm_raw_batch* dev_batch, int32_t* counts_dev_out /* device int32[world] */, void* stream);
 int dfm_shard_ipc_export(dfm_handle* h, unsigned char* handles_out /* 3 * 64 bytes */);
 int dfm_shard_ipc_import(dfm_handle* h, const unsigned char* all_handles /* world * 3 * 64 bytes, rank-major */);
 /* single-process hosts (several ranks on one GPU, as the tests do) wire the handles with raw pointers instead of IPC */

@@ -1220,7 +1220,8 @@ extern "C" int dfm_num_slots(const dfm_handle* h) { return h ? h->dcs : -1; }
 extern "C" int64_t dfm_dense_size(const dfm_handle* h) { return h ? h->n_dense : -1; }
 
 template <int K>
-static int shard_requests_impl(dfm_handle* h, const BatchPtrs& bp, int B, uint32_t* req_rows_out, int32_t* counts_host, cudaStream_t st) {
+static int shard_requests_impl(dfm_handle* h, const BatchPtrs& bp, int B, uint32_t* req_rows_out, int32_t* counts_host, cudaStream_t st,
+                               int32_t* counts_dev_out = nullptr) {
     const int64_t n = (int64_t)B * h->dcs;
     const int64_t t = h->step + 1;
     int rc = ensure_alpha(h, t);
@@ -1235,6 +1236,13 @@ static int shard_requests_impl(dfm_handle* h, const BatchPtrs& bp, int B, uint32
     if (n > 0) {
         shard_uniq_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->ws.skeys(), h->ws.svals(), n, limit, h->Rl, W, h->ws.flags, h->uidx, h->req_rows, h->d_counts);
         h->launches++;
+    }
+    if (!counts_host) {    // asynchronous variant: the counts stay on the device, dfm_shard_p2p_plan learns them from the matrix
+        CK(cudaMemcpyAsync(counts_dev_out, h->d_counts, (size_t)W * 4, cudaMemcpyDeviceToDevice, st));
+        h->shard_n_req = -1; h->shard_B = B;
+        h->last_step_launches += h->launches - l0;
+        CK(cudaGetLastError());
+        return DFM_OK;
     }
     CK(cudaMemcpyAsync(h->h_counts, h->d_counts, (size_t)W * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1364,6 +1372,20 @@ extern "C" int dfm_shard_apply(dfm_handle* h, const float* grecv_dev, const floa
     return rc;
 }
 
+// Same as dfm_shard_requests without the host round trip: the per-owner counts are left in counts_dev_out (device,
+// int32[world]) for the host's all_gather; the fused-exchange path reads them back once, as the W x W matrix.
+extern "C" int dfm_shard_requests_dev(dfm_handle* h, const dfm_raw_batch* b, int32_t* counts_dev_out, void* stream) {
+    if (!h || !counts_dev_out) return DFM_ERR_INVALID_ARG;
+    if (h->world < 2) FAIL(DFM_ERR_INVALID_ARG, "handle was not created with world > 1");
+    int rc = check_batch(h, b, true);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    BatchPtrs bp = make_ptrs(h, b);
+    DISPATCH_K(h, rc = shard_requests_impl<KK>(h, bp, b->batch_size, nullptr, nullptr, st, counts_dev_out));
+    return rc;
+}
+
 // ---- fused exchange over NVLink peer memory -------------------------------------------------------
 // The three receive buffers of every rank (row ids, rows, gradient rows) are cudaMalloc'ed by the library and
 // mapped into every other rank's address space through CUDA IPC.  The requests, the served rows and the
@@ -1446,7 +1468,9 @@ extern "C" int dfm_shard_p2p_plan(dfm_handle* h, const int32_t* counts, int64_t*
     r->recv_off[W] = acc;
     for (int s2 = 0; s2 < W; ++s2) { uint32_t d = 0; for (int o = 0; o < me; ++o) d += (uint32_t)counts[s2 * W + o]; r->reply_off[s2] = d; }
     if ((int64_t)acc > h->ws_own.cap) FAIL(DFM_ERR_UNSUPPORTED, "more row requests than the owner workspace holds (raise max_batch)");
+    if (h->shard_n_req < 0) h->shard_n_req = r->send_off[W];      // dfm_shard_requests_dev: the matrix is the first the host sees
     if ((int64_t)r->send_off[W] != h->shard_n_req) FAIL(DFM_ERR_INVALID_ARG, "count matrix does not match dfm_shard_requests");
+    if (h->shard_n_req > (int64_t)h->ws.cap) FAIL(DFM_ERR_INVALID_ARG, "count matrix exceeds the batch workspace");
     CK(cudaMemcpyAsync(h->d_route, r, sizeof(PeerRoute), cudaMemcpyHostToDevice, st));
     h->shard_n_recv = acc;
     if (n_recv_out) *n_recv_out = acc;

@@ -451,6 +451,11 @@ class DeepFMEngine:
         self._check(self.lib.dfm_shard_requests(self.h, C.byref(pb.raw), None, counts, C.c_void_p(stream) if stream else None))
         return list(counts)
 
+    def shard_requests_dev(self, pb, counts_dev, stream=None):
+        """asynchronous: per-owner counts land in counts_dev (int32 cuda tensor [world]); no host sync"""
+        self._check(self.lib.dfm_shard_requests_dev(self.h, C.byref(pb.raw), C.c_void_p(counts_dev.data_ptr()),
+                                                    C.c_void_p(stream) if stream else None))
+
     def shard_ipc_export(self):
         buf = (C.c_ubyte * 192)()
         self._check(self.lib.dfm_shard_ipc_export(self.h, buf))

@@ -160,9 +160,8 @@ class P2PShardedTrainer:
                 e.record()
                 marks.append((name, e))
         mark("start")
-        counts = eng.shard_requests_counts(pb, st)
+        eng.shard_requests_dev(pb, self.cnt_mine, st)
         mark("requests")
-        self.cnt_mine.copy_(torch.tensor(counts, dtype=torch.int32), non_blocking=True)
         dist.all_gather_into_tensor(self.cnt_all, self.cnt_mine, group=self.group)
         eng.shard_p2p_plan(self.cnt_all.cpu().numpy().reshape(self.W, self.W), st)
         mark("counts")
