@@ -129,7 +129,17 @@ class P2PShardedTrainer:
     """Same step with the three payload exchanges fused into the kernels: every rank's receive buffers are
     mapped into its peers through CUDA IPC, and the requesting / serving / gradient kernels store straight
     into the destination GPU over NVLink.  NCCL carries only the W x W count matrix, two 4-byte barriers and
-    the dense-gradient all_reduce (which doubles as the barrier before `apply`)."""
+    the dense-gradient all_reduce (which doubles as the barrier before `apply`).
+
+    Ordering (every call below is stream-ordered; "bar" = a collective every rank must enter):
+        push_ids | bar1 | serve | bar2 | forward_backward | all_reduce(dense) | apply
+    * within a step: a rank reads its id buffer only after bar1, its row buffer only after bar2 and its gradient
+      buffer only after the dense all_reduce, i.e. after every peer has finished the kernel that stores into it
+      (a peer enters the collective only after that kernel, and kernel completion makes its peer stores visible);
+    * across steps: a peer's push_ids(t+1) follows its all_reduce(t), which completes only after I entered it, i.e.
+      after my serve(t) read the ids; its serve(t+1) follows bar1(t+1), which I enter after my forward_backward(t)
+      read the rows; its forward_backward(t+1) follows bar2(t+1), which I enter after my apply(t) read the
+      gradient rows.  So no buffer is overwritten before its reader is done and no double buffering is needed."""
 
     def __init__(self, engine, group=None):
         import torch
