@@ -412,6 +412,8 @@ constexpr int P_BN = 128;
 constexpr int P_BK = 16;        // 32 KB stages -> a 5-deep operand ring (the 2-deep ring of BK = 32 left every role waiting)
 constexpr int P_THREADS = 448;
 constexpr int P_SPLIT_THREADS = 128;
+constexpr int P_SPLIT_GROUPS = 1;     // >1: groups of splitter warps take alternate stages (measured: no gain, the split is
+constexpr int P_SPLIT_GROUP = P_SPLIT_THREADS / P_SPLIT_GROUPS;   // throughput-bound on shared memory, not a latency chain)
 constexpr int P_EPI_WARPS = 8;
 
 // In-place hi/lo split of one landed operand tile by the P_SPLIT_THREADS splitter threads.  All loads of a thread are
@@ -419,18 +421,18 @@ constexpr int P_EPI_WARPS = 8;
 // previous store and the loop would run at one shared-memory round trip per element group.
 template <int CAP4>
 __device__ __forceinline__ void split_tile(uint8_t* hi_bytes, uint8_t* lo_bytes, int n4, int tt) {
-    constexpr int PER = (CAP4 + P_SPLIT_THREADS - 1) / P_SPLIT_THREADS;
+    constexpr int PER = (CAP4 + P_SPLIT_GROUP - 1) / P_SPLIT_GROUP;
     float4* hi = reinterpret_cast<float4*>(hi_bytes);
     float4* lo = reinterpret_cast<float4*>(lo_bytes);
     float4 x[PER];
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
-        const int i = tt + u * P_SPLIT_THREADS;
+        const int i = tt + u * P_SPLIT_GROUP;
         if (i < n4) x[u] = hi[i];
     }
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
-        const int i = tt + u * P_SPLIT_THREADS;
+        const int i = tt + u * P_SPLIT_GROUP;
         if (i < n4) {
             const float4 h = make_float4(tf32_hi(x[u].x), tf32_hi(x[u].y), tf32_hi(x[u].z), tf32_hi(x[u].w));
             hi[i] = h;
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_persist_kernel(const __grid
     if (threadIdx.x == 0) {
         for (int s = 0; s < S::STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&split[s], P_SPLIT_THREADS);
+            mbar_init(&split[s], P_SPLIT_GROUP);
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -508,7 +510,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_persist_kernel(const __grid
                     const uint32_t s = it % S::STAGES;
                     TS_WAIT(w0, mbar_wait(&empty[s], ((it / S::STAGES) & 1) ^ 1));     // passes at once on the first lap
                     uint8_t* st = smem + s * S::STAGE;
-                    uint8_t *a_hi = st, *a_lo = st + S::A_BYTES, *b_hi = st + 2 * S::A_BYTES, *b_lo = st + 2 * S::A_BYTES + S::B_BYTES;
+                    uint8_t *a_hi = st, *a_lo = st + S::A_BYTES, *b_hi = st + 2 * S::A_BYTES, *b_lo = b_hi + b_bytes;   // [B_hi ; B_lo] = one 2bn-row operand
                     mbar_expect_tx(&full[s], bytes);
                     const int k0 = kb * BK;
                     tma_load_2d(a_hi, &mapA_hi, &full[s], k0, m0);
@@ -522,28 +524,30 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_persist_kernel(const __grid
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(bn, false, false);
+            const uint32_t idesc = make_idesc(bn, false, false), idesc2 = make_idesc(2 * bn, false, false);
             uint32_t it = 0, j = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
                 const uint32_t buf = j & 1;
                 TS_WAIT(w1, mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1));           // the epilogue drained this set (first use: free)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_main = tmem_base + buf * (2 * P_BN), d_cross = d_main + P_BN;
+                const uint32_t d_main = tmem_base + buf * (2 * P_BN), d_cross = d_main + bn;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t s = it % S::STAGES;
                     TS_WAIT(w0, mbar_wait(&split[s], (it / S::STAGES) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = smem_u32(smem + s * S::STAGE);
-                    const uint32_t a_hi = st, a_lo = st + S::A_BYTES, b_hi = st + 2 * S::A_BYTES, b_lo = st + 2 * S::A_BYTES + S::B_BYTES;
+                    const uint32_t a_hi = st, a_lo = st + S::A_BYTES, b_hi = st + 2 * S::A_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < ((p.dbg & 2) ? 0 : BK / UMMA_K); ++ks) {
                         const uint32_t adv = ks * UMMA_K * 4;
                         const uint32_t lbo = 16, sbo = 8 * BK * 4, lt = BK == 32 ? 2 : 4;
                         const uint64_t dah = make_desc(a_hi + adv, lbo, sbo, lt), dal = make_desc(a_lo + adv, lbo, sbo, lt);
-                        const uint64_t dbh = make_desc(b_hi + adv, lbo, sbo, lt), dbl = make_desc(b_lo + adv, lbo, sbo, lt);
-                        umma_tf32(d_main, dah, dbh, idesc, (kb | ks) != 0);
-                        umma_tf32(d_cross, dal, dbh, idesc, (kb | ks) != 0);
-                        umma_tf32(d_cross, dah, dbl, idesc, 1);
+                        const uint64_t dbh = make_desc(b_hi + adv, lbo, sbo, lt);
+                        // B_lo sits right behind the bn rows of B_hi, so hi*hi (columns [0,bn)) and hi*lo (columns
+                        // [bn,2bn), the cross accumulator) are ONE N = 2bn instruction that reads A_hi once: five
+                        // operand-tile reads per k-step instead of six (shared-memory bandwidth is the bound)
+                        umma_tf32(d_main, dah, dbh, idesc2, (kb | ks) != 0);
+                        umma_tf32(d_cross, dal, dbh, idesc, 1);
                     }
                     umma_commit(&empty[s]);
                 }
@@ -553,20 +557,21 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_persist_kernel(const __grid
         }
     } else if (warp < 2 + P_SPLIT_THREADS / 32) {
         // ------------------------------------------------------------------ splitters
-        const int tt = threadIdx.x - 64;
+        const int grp = (threadIdx.x - 64) / P_SPLIT_GROUP, tt = (threadIdx.x - 64) % P_SPLIT_GROUP;
         uint32_t it = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             for (int kb = 0; kb < nkb; ++kb, ++it) {
+                if ((int)(it % P_SPLIT_GROUPS) != grp) continue;
                 const uint32_t s = it % S::STAGES;
                 TS_WAIT(w0, mbar_wait(&full[s], (it / S::STAGES) & 1));
                 uint8_t* st = smem + s * S::STAGE;
                 if (p.split_a && !(p.dbg & 1)) split_tile<S::A_BYTES / 16>(st, st + S::A_BYTES, S::A_BYTES / 16, tt);
-                if (p.split_b && !(p.dbg & 1)) split_tile<S::B_BYTES / 16>(st + 2 * S::A_BYTES, st + 2 * S::A_BYTES + S::B_BYTES, bn * BK * 4 / 16, tt);
+                if (p.split_b && !(p.dbg & 1)) split_tile<S::B_BYTES / 16>(st + 2 * S::A_BYTES, st + 2 * S::A_BYTES + bn * BK * 4, bn * BK * 4 / 16, tt);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
                 mbar_arrive(&split[s]);
             }
         }
-        if (ts && tt == 0) { ts[4] = w0; ts[6] = clock64() - c_begin - w0; }
+        if (ts && tt == 0 && grp == 0) { ts[4] = w0; ts[6] = clock64() - c_begin - w0; }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 6..13)
         const int ew = warp - (2 + P_SPLIT_THREADS / 32);
@@ -579,7 +584,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_persist_kernel(const __grid
             TS_WAIT(w0, mbar_wait(&acc_full[buf], (j >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d_main = tmem_base + buf * (2 * P_BN);
-            epilogue_tile(p, p.C, tb, d_main, d_main + P_BN, m0, n0, bn, q, half, lane);
+            epilogue_tile(p, p.C, tb, d_main, d_main + bn, m0, n0, bn, q, half, lane);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
