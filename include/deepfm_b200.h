@@ -38,6 +38,7 @@ extern "C" {
 #define DFM_ERR_UNSUPPORTED   -4
 #define DFM_ERR_NCCL          -5
 #define DFM_ERR_NOT_FOUND     -6
+#define DFM_ERR_PARSE         -7   /* malformed CSV record (dfm_csv_decode) */
 
 #define DFM_MAX_CAT     64
 #define DFM_MAX_NUM     64
@@ -233,6 +234,47 @@ int dfm_test_fingerprint64(const uint8_t* bytes_dev, const int32_t* offsets_dev,
  * mode 1: C[M,N] = A[K,M]^T * B[K,N] through `splits` ordered partials (weight-gradient path). */
 int dfm_test_tc_gemm(int32_t mode, const float* A_dev, const float* B_dev, float* C_dev, int32_t M, int32_t N,
                      int32_t K, int32_t splits);
+
+/* ---- GPU CSV record decoder: replaces tf.data.TextLineDataset(csv) + tf.decode_csv(value, DEFAULTS) of the
+ * reference's input_fn (trainers/ml_100k.py:44-58; schema COLUMNS / DEFAULTS, trainers/ml_100k.py:3-15) for the
+ * fields the model consumes.  The host hands over whole records (lines); field splitting, RFC-4180 unquoting
+ * ('""' inside a quoted field), int32 parsing, default substitution for empty fields and the label threshold
+ * (rating >= cutoff, trainers/ml_100k.py:47-48) run on the device.  The decoded columns stay in the reader's
+ * device buffers in the layout dfm_raw_batch takes: int32[n] columns, Arrow-style string columns
+ * (int32 offsets[n+1] + bytes), float labels[n].  Errors follow tf.decode_csv: wrong field count, a field that
+ * is not a valid int32, a quote inside an unquoted field or an unterminated quote -> DFM_ERR_PARSE, with the
+ * first offending record in dfm_csv_last_error. */
+#define DFM_CSV_SKIP    0          /* parsed for structure only (15 of the 42 ML-100K fields are never consumed) */
+#define DFM_CSV_INT32   1          /* record_defaults [0]      */
+#define DFM_CSV_STRING  2          /* record_defaults ["null"] */
+#define DFM_CSV_ERR_FIELDS 1
+#define DFM_CSV_ERR_INT    2
+#define DFM_CSV_ERR_QUOTE  3
+typedef struct {
+    int32_t            n_fields;       /* fields per record (42) */
+    const int32_t*     kind;           /* [n_fields] DFM_CSV_* */
+    const int32_t*     int_default;    /* [n_fields] value of an empty int32 field (NULL: 0) */
+    const char* const* str_default;    /* [n_fields] value of an empty string field (NULL entries: "") */
+    int32_t            label_field;    /* int32 field the label is derived from, -1: none */
+    int32_t            label_min;      /* label = value >= label_min */
+    int32_t            max_records;    /* per decode call */
+    int64_t            max_bytes;      /* per decode call, < 4 GiB */
+    int32_t            device;
+} dfm_csv_config;
+typedef struct dfm_csv_reader dfm_csv_reader;
+int dfm_csv_create(const dfm_csv_config* cfg, dfm_csv_reader** out);
+void dfm_csv_destroy(dfm_csv_reader* r);
+const char* dfm_csv_last_error(const dfm_csv_reader* r);
+/* text: whole records, '\n'-terminated ('\r\n' tolerated, the last record may lack the newline).  Device variant:
+ * 16-byte aligned and readable up to the next multiple of 16.  Both return after the decode finished (the record
+ * count and the parse status need one synchronisation of the stream). */
+int dfm_csv_decode(dfm_csv_reader* r, const char* text_dev, int64_t n_bytes, int32_t* n_records_out, void* stream);
+int dfm_csv_decode_host(dfm_csv_reader* r, const char* text_host, int64_t n_bytes, int32_t* n_records_out, void* stream);
+int32_t dfm_csv_num_records(const dfm_csv_reader* r);
+const int32_t* dfm_csv_int_column(const dfm_csv_reader* r, int32_t field);     /* device int32[n_records] */
+const char*    dfm_csv_str_bytes(const dfm_csv_reader* r, int32_t field);      /* device bytes */
+const int32_t* dfm_csv_str_offsets(const dfm_csv_reader* r, int32_t field);    /* device int32[n_records + 1] */
+const float*   dfm_csv_labels(const dfm_csv_reader* r);                        /* device float[n_records] */
 
 const char* dfm_version(void);
 

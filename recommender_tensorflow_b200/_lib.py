@@ -84,6 +84,16 @@ _SIGS = {
     "dfm_shard_p2p_serve": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dfm_shard_p2p_forward_backward": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfm_shard_p2p_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dfm_csv_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dfm_csv_destroy": (None, [C.c_void_p]),
+    "dfm_csv_last_error": (C.c_char_p, [C.c_void_p]),
+    "dfm_csv_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.c_void_p]),
+    "dfm_csv_decode_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.c_void_p]),
+    "dfm_csv_num_records": (C.c_int32, [C.c_void_p]),
+    "dfm_csv_int_column": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "dfm_csv_str_bytes": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "dfm_csv_str_offsets": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "dfm_csv_labels": (C.c_void_p, [C.c_void_p]),
     "dfm_test_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]),
     "dfm_test_fingerprint64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "dfm_test_tc_gemm": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

@@ -5,12 +5,15 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall"
 mkdir -p build
-rm -f build/prims.o build/api.o
+rm -f build/prims.o build/api.o build/csv.o
 $NVCC $FLAGS -c prims.cu -o build/prims.o &
 p1=$!
 $NVCC $FLAGS -c api.cu -o build/api.o &
 p2=$!
+$NVCC $FLAGS -c csv.cu -o build/csv.o &
+p3=$!
 wait $p1    # a bare `wait` would swallow a failed compile and link stale objects
 wait $p2
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libdeepfm_b200.so build/prims.o build/api.o -lcudart
+wait $p3
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libdeepfm_b200.so build/prims.o build/api.o build/csv.o -lcudart
 echo "built $(cd .. && pwd)/libdeepfm_b200.so"

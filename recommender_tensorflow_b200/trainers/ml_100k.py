@@ -135,3 +135,65 @@ def write_synthetic_csv(path, n_rows, seed=20260101):
                 else:
                     row.append(0 if isinstance(default[0], int) else "null")
             wr.writerow(row)
+
+
+def _train_index_stream(n_rows, cap, rng):
+    """Row indices in the order get_input_fn's shuffle(16*batch_size).repeat() emits rows (same RNG calls)."""
+    while True:
+        buf = []
+        for i in range(n_rows):
+            if len(buf) < cap:
+                buf.append(i)
+                continue
+            j = int(rng.integers(0, cap))
+            yield buf[j]
+            buf[j] = i
+        if n_rows == 0:
+            return
+        rng.shuffle(buf)
+        yield from buf
+
+
+def get_gpu_input_fn(csv_path, engine, mode=ModeKeys.TRAIN, batch_size=32, cutoff=5, seed=None):
+    """get_input_fn with tf.decode_csv moved to the GPU: the host only selects whole records
+    (same shuffle algorithm and RNG stream as get_input_fn, so the same seed gives the same batches) and copies their
+    bytes into a pinned buffer; `GpuCsvReader` splits, unquotes, parses and thresholds on the device.  Yields
+    (PackedBatch on the device, None): the labels are inside the batch.  A record is one text line, as with
+    tf.data.TextLineDataset (a quoted field cannot contain a line break)."""
+    from ..csv_reader import GpuCsvReader
+
+    def input_fn():
+        import torch
+        data = np.fromfile(csv_path, dtype=np.uint8)
+        if data.size and data[-1] != 10:
+            data = np.concatenate([data, np.array([10], dtype=np.uint8)])
+        nl = np.flatnonzero(data == 10)
+        starts = np.concatenate([[0], nl[:-1] + 1])[1:].astype(np.int64)      # [1:] = skip(1), the header
+        lens = (nl + 1)[1:].astype(np.int64) - starts
+        n_rows = int(starts.size)
+        max_bytes = int(np.sort(lens)[-batch_size:].sum()) + 16 if n_rows else 16
+        reader = GpuCsvReader(engine, COLUMNS, DEFAULTS, LABEL_COL, cutoff, max_records=batch_size, max_bytes=max_bytes)
+        pinned = torch.empty(max_bytes, dtype=torch.uint8).pin_memory()
+        pv = pinned.numpy()
+
+        def emit(idx):
+            idx = np.asarray(idx, dtype=np.int64)
+            ln = lens[idx]
+            out_off = np.concatenate([[0], np.cumsum(ln)])
+            total = int(out_off[-1])
+            src = np.repeat(starts[idx] - out_off[:-1], ln) + np.arange(total, dtype=np.int64)
+            np.take(data, src, out=pv[:total])
+            return reader.decode(pinned[:total]), None
+
+        if mode == ModeKeys.TRAIN:
+            rng = np.random.default_rng(seed)
+            batch = []
+            for i in _train_index_stream(n_rows, 16 * batch_size, rng):
+                batch.append(i)
+                if len(batch) == batch_size:
+                    yield emit(batch)
+                    batch = []
+        else:
+            for b0 in range(0, n_rows, batch_size):
+                yield emit(np.arange(b0, min(b0 + batch_size, n_rows)))
+    return input_fn
