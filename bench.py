@@ -197,6 +197,42 @@ def run_reference(args, w, name):
     print(json.dumps(line))
 
 
+def csv_decode_bench(eng, B, iters=20):
+    """records/s of dfm_csv_decode on one batch of ML-100K-shaped CSV text (42 fields, quoted titles) resident in HBM,
+    and from pinned host text (H2D inside the timed region).  Wall clock around the call: it returns after the
+    decode finished (two stream syncs inside)."""
+    import tempfile
+
+    import torch
+    from recommender_tensorflow_b200.csv_reader import GpuCsvReader
+    from recommender_tensorflow_b200.trainers import ml_100k
+    n_unique = min(B, 4096)
+    path = os.path.join(tempfile.mkdtemp(), "bench.csv")
+    ml_100k.write_synthetic_csv(path, n_unique)
+    data = np.fromfile(path, dtype=np.uint8)
+    body = data[int(np.flatnonzero(data == 10)[0]) + 1:]
+    body = np.tile(body, (B + n_unique - 1) // n_unique)
+    nl = np.flatnonzero(body == 10)
+    body = body[:int(nl[B - 1]) + 1].copy()
+    rd = GpuCsvReader(eng, ml_100k.COLUMNS, ml_100k.DEFAULTS, ml_100k.LABEL_COL, max_records=B, max_bytes=body.size + 64)
+    dev = torch.zeros((body.size + 15) // 16 * 16, dtype=torch.uint8, device="cuda")
+    dev[:body.size] = torch.from_numpy(body).cuda()
+    pinned = torch.from_numpy(body).pin_memory()
+    out = {"records": B, "text_bytes": int(body.size), "unit": "records/s"}
+    for key, src in (("value", dev[:body.size]), ("from_pinned_host", pinned)):
+        for _ in range(3):
+            assert rd.decode(src).batch_size == B
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            rd.decode(src)
+        torch.cuda.synchronize()
+        out[key] = B * iters / (time.perf_counter() - t0)
+    out["text_GBps"] = out["value"] * body.size / B / 1e9
+    rd.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -391,6 +427,11 @@ def main():
             line["roofline_tower"] = {"bound": "tensor", "achieved": fl / t / 1e12, "peak": bf16 / 2 / 3, "unit": "TFLOP/s (fp32-equivalent)",
                                       "frac": fl / t / 1e12 / (bf16 / 6), "flops_per_step": fl,
                                       "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (tf32 rate) / 3 (three TF32 MMAs per fp32-accurate product)"}
+        if world == 1 and w["data"] == "ml100k":
+            try:      # side measurement: the CSV input path decoded on the GPU, same batch size
+                line["csv_decode"] = csv_decode_bench(eng, B)
+            except Exception as ex:
+                line["csv_decode"] = {"unavailable": repr(ex)}
         if not args.no_cpu_baseline and world == 1:
             try:
                 base, why = cpu_baseline(w, eng)
