@@ -91,6 +91,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Explicit shared-state-space accesses.  The operand stages are reached through pointers derived from the dynamic
+// shared-memory base by integer arithmetic, and the compiler then emits GENERIC LD.E/ST.E for plain C++ accesses
+// (ncu source page of the first persistent kernel: every splitter access was LD.E.128 / ST.E.128 with long-scoreboard
+// stalls); ld.shared / st.shared on 32-bit shared addresses take the short path.
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B
 //   K-major : rows of 128 B (32 fp32 of K), 8-row atoms 1024 B apart (SBO); LBO unused
 //   MN-major (32-bit operands must use SWIZZLE_128B_BASE32B, TMA mode 128B_ATOM_32B): rows of 128 B
@@ -140,6 +153,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, float* __restrict
                                               int m0, int n0, int bn, int q, int half, int lane) {
     const int row0 = m0 + q * 32;
     const int rsub = lane >> 3, cg = lane & 7;
+    const uint32_t tbs = smem_u32(tb);
     for (int c0 = half * 32; c0 < bn; c0 += 64) {
         if (n0 + c0 >= p.N) break;
         {
@@ -148,8 +162,8 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, float* __restrict
             tmem_ld32(tmem_cross + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, vx);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(tb + lane * 36 + 4 * j) =
-                    make_float4(v[4 * j] + vx[4 * j], v[4 * j + 1] + vx[4 * j + 1], v[4 * j + 2] + vx[4 * j + 2], v[4 * j + 3] + vx[4 * j + 3]);
+                sts128(tbs + (lane * 36 + 4 * j) * 4,
+                       make_float4(v[4 * j] + vx[4 * j], v[4 * j + 1] + vx[4 * j + 1], v[4 * j + 2] + vx[4 * j + 2], v[4 * j + 3] + vx[4 * j + 3]));
         }
         __syncwarp();
         const int n = n0 + c0 + cg * 4;
@@ -175,7 +189,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, float* __restrict
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + rsub, gm = row0 + r;
-            float4 x = *reinterpret_cast<const float4*>(tb + r * 36 + cg * 4);
+            float4 x = lds128(tbs + (r * 36 + cg * 4) * 4);
             if (p.epi == EPI_BIAS_RELU) {
                 x.x = fmaxf(x.x + bias4.x, 0.f); x.y = fmaxf(x.y + bias4.y, 0.f);
                 x.z = fmaxf(x.z + bias4.z, 0.f); x.w = fmaxf(x.w + bias4.w, 0.f);
@@ -326,44 +340,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_kernel(const __grid_constant
             mbar_wait(&full[s], (kb / S::STAGES) & 1);
             uint8_t* st = smem + s * S::STAGE;
             if (p.split_a && !(p.dbg & 1)) {
-                float4* hi = reinterpret_cast<float4*>(st);
-                float4* lo = reinterpret_cast<float4*>(st + S::A_BYTES);
+                const uint32_t hi = smem_u32(st), lo = smem_u32(st + S::A_BYTES);
 #pragma unroll 4
                 for (int i = t; i < S::A_BYTES / 16; i += n_split_threads) {
-                    float4 x = hi[i];
+                    float4 x = lds128(hi + i * 16);
 #if TC_TRUNC_HI
                     // kind::tf32 ignores the low 13 mantissa bits of its fp32 operands (verified by the accuracy
                     // tests: with any other input rounding this split loses 2^-11), so the landed tile IS x_hi
                     // and only x_lo = tf32_rn(x - trunc(x)) is written -> one third less shared-memory traffic.
                     float4 l = make_float4(tf32_hi(x.x - tf32_trunc(x.x)), tf32_hi(x.y - tf32_trunc(x.y)),
                                            tf32_hi(x.z - tf32_trunc(x.z)), tf32_hi(x.w - tf32_trunc(x.w)));
-                    lo[i] = l;
+                    sts128(lo + i * 16, l);
 #else
                     float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
                     float4 l = make_float4(tf32_hi(x.x - h.x), tf32_hi(x.y - h.y), tf32_hi(x.z - h.z), tf32_hi(x.w - h.w));
-                    hi[i] = h;
-                    lo[i] = l;
+                    sts128(hi + i * 16, h);
+                    sts128(lo + i * 16, l);
 #endif
                 }
             }
             if (p.split_b && !(p.dbg & 1)) {
-                float4* hi = reinterpret_cast<float4*>(st + 2 * S::A_BYTES);
-                float4* lo = reinterpret_cast<float4*>(st + 2 * S::A_BYTES + S::B_BYTES);
+                const uint32_t hi = smem_u32(st + 2 * S::A_BYTES), lo = smem_u32(st + 2 * S::A_BYTES + S::B_BYTES);
 #pragma unroll 4
                 for (int i = t; i < bn * BK * 4 / 16; i += n_split_threads) {
-                    float4 x = hi[i];
+                    float4 x = lds128(hi + i * 16);
 #if TC_TRUNC_HI
                     // kind::tf32 ignores the low 13 mantissa bits of its fp32 operands (verified by the accuracy
                     // tests: with any other input rounding this split loses 2^-11), so the landed tile IS x_hi
                     // and only x_lo = tf32_rn(x - trunc(x)) is written -> one third less shared-memory traffic.
                     float4 l = make_float4(tf32_hi(x.x - tf32_trunc(x.x)), tf32_hi(x.y - tf32_trunc(x.y)),
                                            tf32_hi(x.z - tf32_trunc(x.z)), tf32_hi(x.w - tf32_trunc(x.w)));
-                    lo[i] = l;
+                    sts128(lo + i * 16, l);
 #else
                     float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
                     float4 l = make_float4(tf32_hi(x.x - h.x), tf32_hi(x.y - h.y), tf32_hi(x.z - h.z), tf32_hi(x.w - h.w));
-                    hi[i] = h;
-                    lo[i] = l;
+                    sts128(hi + i * 16, h);
+                    sts128(lo + i * 16, l);
 #endif
                 }
             }
@@ -422,21 +434,20 @@ constexpr int P_EPI_WARPS = 8;
 template <int CAP4>
 __device__ __forceinline__ void split_tile(uint8_t* hi_bytes, uint8_t* lo_bytes, int n4, int tt) {
     constexpr int PER = (CAP4 + P_SPLIT_GROUP - 1) / P_SPLIT_GROUP;
-    float4* hi = reinterpret_cast<float4*>(hi_bytes);
-    float4* lo = reinterpret_cast<float4*>(lo_bytes);
+    const uint32_t hi = smem_u32(hi_bytes), lo = smem_u32(lo_bytes);
     float4 x[PER];
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const int i = tt + u * P_SPLIT_GROUP;
-        if (i < n4) x[u] = hi[i];
+        if (i < n4) x[u] = lds128(hi + i * 16);
     }
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const int i = tt + u * P_SPLIT_GROUP;
         if (i < n4) {
             const float4 h = make_float4(tf32_hi(x[u].x), tf32_hi(x[u].y), tf32_hi(x[u].z), tf32_hi(x[u].w));
-            hi[i] = h;
-            lo[i] = make_float4(tf32_hi(x[u].x - h.x), tf32_hi(x[u].y - h.y), tf32_hi(x[u].z - h.z), tf32_hi(x[u].w - h.w));
+            sts128(hi + i * 16, h);
+            sts128(lo + i * 16, make_float4(tf32_hi(x[u].x - h.x), tf32_hi(x[u].y - h.y), tf32_hi(x[u].z - h.z), tf32_hi(x[u].w - h.w)));
         }
     }
 }
