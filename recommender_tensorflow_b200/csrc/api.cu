@@ -61,6 +61,10 @@ struct dfm_handle {
     int dc = 0, dn = 0, K = 0, L = 0;
     int dcs = 0;                 // value slots per sample = sum of column widths (== dc without multivalent columns)
     bool has_bags = false;
+    // tiny-vocabulary columns reduced densely instead of through the sort (embed_kernels.cuh: tiny_reduce_kernel)
+    int n_tiny = 0, n_big = 0, n_tiny_rows = 0, tiny_blocks_max = 0, tiny_group_rows = 0;
+    int32_t *d_tiny_slot = nullptr, *d_key_slot = nullptr, *d_trow0 = nullptr;
+    uint32_t* d_trow_grow = nullptr; float* tiny_partial = nullptr; SegCounts* d_tiny_cnt = nullptr;
     int32_t *d_slot_col = nullptr, *d_slot_j = nullptr, *d_field_slot0 = nullptr; float* inv_cnt = nullptr;
     int hidden[DFM_MAX_HIDDEN] = {0};
     int use_linear = 1, use_mf = 1, use_dnn = 1, need_emb = 1, loss_red = 0;
@@ -214,6 +218,8 @@ static void free_all(dfm_handle* h) {
     free_ws(h->ws);
     free_ws(h->ws_own);
     if (h->h_counts) cudaFreeHost(h->h_counts);
+    { void* tp[] = {h->d_tiny_slot, h->d_key_slot, h->d_trow0, h->d_trow_grow, h->tiny_partial, h->d_tiny_cnt};
+      for (void* p : tp) if (p) cudaFree(p); }
     for (void* p : h->p2p_opened) if (p) cudaIpcCloseMemHandle(p);
     if (h->p2p_rowbuf) cudaFree(h->p2p_rowbuf);
     if (h->p2p_grecv) cudaFree(h->p2p_grecv);
@@ -354,6 +360,47 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     if (!voc_bytes.empty()) CK(cudaMemcpy(h->d_voc_bytes, voc_bytes.data(), voc_bytes.size(), cudaMemcpyHostToDevice));
     if (!voc_offs.empty()) CK(cudaMemcpy(h->d_voc_offs, voc_offs.data(), voc_offs.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_row_off, h->row_off.data(), h->row_off.size() * 4, cudaMemcpyHostToDevice));
+    {
+        const char* env = getenv("DFM_TINY");
+        std::vector<int32_t> tslot, key_slot(std::max(h->dcs, 1), -1), trow0;
+        std::vector<uint32_t> tgrow;
+        const bool enable = h->world == 1 && !h->has_bags && !(env && atoi(env) == 0);
+        for (int f = 0; f < h->dc; ++f) {
+            const uint32_t nb = h->row_off[f + 1] - h->row_off[f];
+            // the per-warp accumulators of all tiny rows must fit the shared-memory budget of tiny_reduce_kernel
+            if (enable && nb <= (uint32_t)TINY_MAX && tgrow.size() + nb <= 4096) {
+                trow0.push_back((int32_t)tgrow.size());
+                for (uint32_t b = 0; b < nb; ++b) tgrow.push_back(h->row_off[f] + b);
+                tslot.push_back(f);
+            } else {
+                key_slot[f] = h->n_big++;
+            }
+        }
+        if (tslot.size() < 2) {       // not worth a second path
+            h->n_big = h->dcs; tslot.clear(); trow0.clear(); tgrow.clear();
+        }
+        h->n_tiny = (int)tslot.size(); h->n_tiny_rows = (int)tgrow.size();
+        trow0.push_back((int32_t)tgrow.size());
+        {   // rows of the largest group of 32/LPR adjacent tiny columns = accumulator rows of one tiny_reduce block
+            const int G = 32 / std::max(1, K / 4);
+            for (int c0 = 0; c0 < h->n_tiny; c0 += G)
+                h->tiny_group_rows = std::max(h->tiny_group_rows, trow0[std::min(h->n_tiny, c0 + G)] - trow0[c0]);
+        }
+        if (h->n_tiny) {
+            h->tiny_blocks_max = (h->max_batch + TINY_SPB - 1) / TINY_SPB;
+            if (dalloc(h, &h->d_tiny_slot, tslot.size()) || dalloc(h, &h->d_key_slot, key_slot.size()) || dalloc(h, &h->d_trow0, trow0.size()) ||
+                dalloc(h, &h->d_trow_grow, tgrow.size()) || dalloc(h, &h->d_tiny_cnt, 1) ||
+                dalloc(h, &h->tiny_partial, (size_t)h->tiny_blocks_max * h->n_tiny_rows * (K + 4)))
+                return DFM_ERR_CUDA;
+            CK(cudaMemcpy(h->d_tiny_slot, tslot.data(), tslot.size() * 4, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(h->d_key_slot, key_slot.data(), key_slot.size() * 4, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(h->d_trow0, trow0.data(), trow0.size() * 4, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(h->d_trow_grow, tgrow.data(), tgrow.size() * 4, cudaMemcpyHostToDevice));
+            SegCounts sc{};
+            sc.n_rows = (uint32_t)h->n_tiny_rows;
+            CK(cudaMemcpy(h->d_tiny_cnt, &sc, sizeof sc, cudaMemcpyHostToDevice));
+        }
+    }
 
     // ---- tables: one record per row (see Table)
     h->emb_slots = opt_slots(h->od.kind);
@@ -707,8 +754,27 @@ static void launch_transform(dfm_handle* h, const BatchPtrs& bp, int B, bool wit
     transform_kernel<32><<<cdiv(B, 32), 256, (size_t)32 * h->dcs * 4, st>>>(
         bp, h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, B, h->dcs, h->has_bags ? h->d_slot_col : nullptr,
         h->has_bags ? h->d_slot_j : nullptr, h->d_row_off, (uint32_t)h->R, ids_out,
-        with_keys ? h->ws.keys[0] : nullptr, with_keys ? h->ws.vals[0] : nullptr, h->d_err);
+        with_keys ? h->ws.keys[0] : nullptr, with_keys ? h->ws.vals[0] : nullptr, h->d_err,
+        with_keys && h->n_tiny ? h->d_key_slot : nullptr, h->n_big);
     h->launches++;
+}
+
+// dense reduction + optimizer for the tiny-vocabulary columns (no-op when the model has none)
+template <int K>
+static int tiny_update(dfm_handle* h, int B, const OptDev& od, const OptDev& ol, int64_t t, cudaStream_t st) {
+    if (!h->n_tiny || B <= 0) return DFM_OK;
+    const int blocks = (B + TINY_SPB - 1) / TINY_SPB;
+    constexpr int G = 32 / (K / 4);                                   // columns per block
+    const size_t smem = (size_t)8 * h->tiny_group_rows * (K + 4) * 4;
+    static size_t smem_attr = 48 * 1024;
+    if (smem > smem_attr) { CK(cudaFuncSetAttribute(tiny_reduce_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_attr = smem; }
+    tiny_reduce_kernel<K><<<dim3(blocks, (h->n_tiny + G - 1) / G), 256, smem, st>>>(h->ids, B, h->dcs, h->d_tiny_slot, h->d_trow0, h->n_tiny, h->n_tiny_rows,
+                                                     h->need_emb ? h->dE : nullptr, h->dz, (h->dc + h->dn) * K, h->tiny_partial);
+    tiny_update_kernel<K><<<cdiv((int64_t)h->n_tiny_rows * 32, 256), 256, 0, st>>>(h->tiny_partial, blocks, h->d_trow_grow, h->n_tiny_rows, h->tb, h->emb_slots,
+                                                                                   od, ol, (bool)h->need_emb, (bool)h->use_linear, (int)t);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return DFM_OK;
 }
 
 template <int K>
@@ -1064,7 +1130,7 @@ template <int K>
 static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out, float* logits_out, cudaStream_t st) {
     if (h->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "row-sharded handle: drive the step with the dfm_shard_* entry points");
     const int dc = h->dc, d = dc + h->dn, dK = d * K;
-    const int64_t n = (int64_t)B * h->dcs;
+    const int64_t n = (int64_t)B * (h->n_tiny ? h->n_big : h->dcs);      // lookups that go through the sort
     const int64_t t = h->step + 1;
     int rc = ensure_alpha(h, t);
     if (rc) return rc;
@@ -1075,6 +1141,12 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
     ph.next();
     if ((rc = build_segments(h, h->ws, n, (uint32_t)h->R, h->key_bits, st, &ph))) return rc;   // sort + segments
     if ((rc = catchup_touched<K>(h, h->ws, n, t, st))) return rc;
+    if (h->n_tiny && any_adam(h) && t > 1) {     // every row of the tiny columns, hit or not (that IS the non-lazy semantics)
+        const OptDev pod = make_opt(h->od, h->b1p_d, h->b2p_d), pol = make_opt(h->ol, h->b1p_l, h->b2p_l);
+        catchup_touched_kernel<K><<<cdiv((int64_t)h->n_tiny_rows * (K / 4), 256), 256, 0, st>>>(h->tb, h->d_trow_grow, h->d_tiny_cnt, (int)(t - 1), h->alpha_d,
+                                                                                              h->alpha_l, pod, pol, (bool)h->need_emb, (bool)h->use_linear);
+        h->launches++;
+    }
     ph.next();
     const float scale = h->loss_red == DFM_LOSS_MEAN ? 1.0f / (float)B : 1.0f;
     if ((rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, &ph))) return rc;
@@ -1087,6 +1159,7 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
         rc = sparse_update<K, false>(h, h->ws, n, src, so.od, so.ol, t, nullptr, st, &ph);
     }
     if (rc) return rc;
+    if ((rc = tiny_update<K>(h, B, so.od, so.ol, t, st))) return rc;
     if (h->n_dense) {
         dense_apply_kernel<<<cdiv(h->n_dense, 256), 256, 0, st>>>(h->dw, h->ds1, h->ds2, h->dg, h->n_deep, h->n_dense, so.od, so.ol);
         h->launches++;

@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(256) transform_kernel(BatchPtrs bp, const ColD
                                                         const int32_t* __restrict__ slot_col, const int32_t* __restrict__ slot_j,
                                                         const uint32_t* __restrict__ row_off, uint32_t R,
                                                         int32_t* __restrict__ ids, uint32_t* __restrict__ keys,
-                                                        uint32_t* __restrict__ vals, int* err) {
+                                                        uint32_t* __restrict__ vals, int* err,
+                                                        const int32_t* __restrict__ key_slot, int n_key_slots) {
     extern __shared__ int32_t sid[];  // [TILE][n_slots]
     const int b0 = blockIdx.x * TILE;
     const int nb = min(TILE, B - b0);
@@ -219,8 +220,17 @@ __global__ void __launch_bounds__(256) transform_kernel(BatchPtrs bp, const ColD
         int slot = w % n_slots;
         ids[g0 + w] = id;
         if (keys) {
-            keys[g0 + w] = id >= 0 ? row_off[slot_col ? slot_col[slot] : slot] + (uint32_t)id : R;
-            vals[g0 + w] = (uint32_t)(g0 + w);
+            // key_slot: only the listed slots go through the sort (tiny-vocabulary columns are reduced densely, see
+            // tiny_reduce_kernel); their pairs are packed [sample][key slot], the payload keeps the full-slot numbering
+            int64_t at = g0 + w;
+            if (key_slot) {
+                const int ks = key_slot[slot];
+                at = ks >= 0 ? (int64_t)(b0 + w / n_slots) * n_key_slots + ks : -1;
+            }
+            if (at >= 0) {
+                keys[at] = id >= 0 ? row_off[slot_col ? slot_col[slot] : slot] + (uint32_t)id : R;
+                vals[at] = (uint32_t)(g0 + w);
+            }
         }
     }
 }
@@ -849,6 +859,132 @@ __global__ void iota_kernel(uint32_t* __restrict__ v, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] = (uint32_t)i;
 }
+// =============================================================================================
+// tiny-vocabulary columns (<= TINY_MAX buckets: the 19 genre flags, gender, age and release-year buckets of the
+// ML-100K schema = 22 of its 26 columns, 85 % of the lookups but only 72 table rows).  Sorting their lookups only to
+// find out that a row was hit 30 000 times is wasted work: their gradient rows are reduced DENSELY instead — a block
+// per 128 samples accumulates per-row sums in shared memory (every warp owns private accumulators and walks its
+// samples in index order; warps, then blocks, are combined in fixed order, so the sum is deterministic) — and a
+// small kernel applies the optimizer to the rows that were hit.  The sort / segment /
+// piece machinery then sees only the large columns.
+// =============================================================================================
+constexpr int TINY_MAX = 8;               // buckets of a "tiny" column
+constexpr int TINY_SPB = 512;             // samples per block (64 per warp)
+
+// Block = (128 consecutive samples) x (one group of 32/LPR adjacent tiny columns), warp = 16 of the samples in index
+// order; the lane groups of a warp take the columns of the group side by side (adjacent columns are adjacent in dE and
+// in the id row, so the reads coalesce).  Each warp owns private accumulators [row of the column group][K + 4] =
+// {g[K], g_lin, count, -, -}; warps are combined in fixed order.
+template <int K>
+__global__ void __launch_bounds__(256) tiny_reduce_kernel(const int32_t* __restrict__ ids, int B, int n_slots, const int32_t* __restrict__ tslot,
+                                                          const int32_t* __restrict__ trow0 /* [n_tiny + 1] */, int n_tiny, int n_trows,
+                                                          const float* __restrict__ dE, const float* __restrict__ dz, int dK,
+                                                          float* __restrict__ partial) {
+    constexpr int LPR = K / 4, G = 32 / LPR, RW = K + 4;
+    extern __shared__ __align__(16) float tacc[];     // [8][rows of this column group][RW]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+    const int c0 = blockIdx.y * G, c1 = min(n_tiny, c0 + G);
+    const int rbase = __ldg(trow0 + c0), per = (__ldg(trow0 + c1) - rbase) * RW;
+    for (int i = threadIdx.x; i < 8 * per; i += 256) tacc[i] = 0.f;
+    __syncthreads();
+    float* my = tacc + warp * per;
+    const int b_begin = blockIdx.x * TINY_SPB + warp * (TINY_SPB / 8);
+    const int b_end = min(B, b_begin + TINY_SPB / 8);
+    const int c = c0 + grp;
+    const bool cok = c < c1;
+    const int slot = cok ? __ldg(tslot + c) : 0, r0 = cok ? __ldg(trow0 + c) - rbase : 0;
+    constexpr int U = 8;                 // samples in flight per lane group; id, gradient row and dz are independent loads
+    for (int b = b_begin; b < b_end; b += U) {
+        int id[U];
+        float4 x[U];
+        float z[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            const bool ok = cok && b + q < b_end;
+            id[q] = ok ? __ldg(ids + (size_t)(b + q) * n_slots + slot) : -1;
+            x[q] = (ok && dE) ? __ldg(reinterpret_cast<const float4*>(dE + (size_t)(b + q) * dK + (size_t)slot * K) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+            z[q] = (ok && sub == 0) ? __ldg(dz + b + q) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+            if (id[q] >= 0) {
+                float* row = my + (r0 + id[q]) * RW;
+                float4* a4 = reinterpret_cast<float4*>(row) + sub;
+                float4 v = *a4;
+                v.x += x[q].x; v.y += x[q].y; v.z += x[q].z; v.w += x[q].w;
+                *a4 = v;
+                if (sub == 0) { row[K] += z[q]; row[K + 1] += 1.f; }
+            }
+    }
+    __syncthreads();
+    float* out = partial + ((size_t)blockIdx.x * n_trows + rbase) * RW;
+    for (int e = threadIdx.x; e < per; e += 256) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sacc += tacc[w * per + e];
+        out[e] = sacc;
+    }
+}
+
+// one WARP per row of a tiny column: the lane groups take the blocks' partial sums round-robin (in block order), a fixed
+// butterfly combines the groups, then the sparse optimizer (rows that were not hit stay as they are — the non-lazy
+// Adam decay reaches them through the catch-up, like any other idle row)
+template <int K>
+__global__ void __launch_bounds__(256) tiny_update_kernel(const float* __restrict__ partial, int n_blocks, const uint32_t* __restrict__ trow_grow,
+                                                          int n_trows, Table tb, int emb_slots, OptDev od, OptDev ol, bool has_emb, bool has_lin,
+                                                          int step) {
+    constexpr int LPR = K / 4, G = 32 / LPR, RW = K + 4;
+    const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_trows) return;                        // warp-uniform
+    const size_t per = (size_t)n_trows * RW;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    float gl = 0.f, cnt = 0.f;
+    for (int j0 = grp; j0 < n_blocks; j0 += 8 * G) {      // 8 independent loads in flight, added in block order
+        float4 t[8];
+        float tl[8], tc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int j = j0 + q * G;
+            t[q] = make_float4(0.f, 0.f, 0.f, 0.f); tl[q] = 0.f; tc[q] = 0.f;
+            if (j < n_blocks) {
+                const float* p = partial + j * per + (size_t)r * RW;
+                t[q] = __ldg(reinterpret_cast<const float4*>(p) + sub);
+                const float2 lc = __ldg(reinterpret_cast<const float2*>(p + K));
+                tl[q] = lc.x; tc[q] = lc.y;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { g.x += t[q].x; g.y += t[q].y; g.z += t[q].z; g.w += t[q].w; gl += tl[q]; cnt += tc[q]; }
+    }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+        g.x += __shfl_xor_sync(0xffffffffu, g.x, o); g.y += __shfl_xor_sync(0xffffffffu, g.y, o);
+        g.z += __shfl_xor_sync(0xffffffffu, g.z, o); g.w += __shfl_xor_sync(0xffffffffu, g.w, o);
+        gl += __shfl_xor_sync(0xffffffffu, gl, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (cnt == 0.f || grp != 0) return;
+    const size_t row = trow_grow[r];
+    if (has_emb) {
+        float4 w = tab_w(tb, row)[sub], s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+        if (emb_slots >= 1) s1 = tab_s1(tb, row)[sub];
+        if (emb_slots >= 2) s2 = tab_s2(tb, row)[sub];
+        sparse_apply(w.x, s1.x, s2.x, g.x, od);
+        sparse_apply(w.y, s1.y, s2.y, g.y, od);
+        sparse_apply(w.z, s1.z, s2.z, g.z, od);
+        sparse_apply(w.w, s1.w, s2.w, g.w, od);
+        tab_w(tb, row)[sub] = w;
+        if (emb_slots >= 1) tab_s1(tb, row)[sub] = s1;
+        if (emb_slots >= 2) tab_s2(tb, row)[sub] = s2;
+    }
+    if (sub == 0) {
+        float4 lr = *tab_lin(tb, row);
+        if (has_lin) sparse_apply(lr.x, lr.y, lr.z, gl, ol);
+        lr.w = __int_as_float(step);
+        *tab_lin(tb, row) = lr;
+    }
+}
+
 // owner side: reply[i] = {emb w[K], lin w, pad} of local row recv_rows[i]
 template <int K>
 __global__ void __launch_bounds__(256) shard_serve_kernel(const uint32_t* __restrict__ recv_rows, int64_t n,
