@@ -211,6 +211,9 @@ int dfm_shard_apply(dfm_handle* h, const float* grecv_dev, const float* dense_gr
  *   dfm_shard_p2p_forward_backward    gradient rows are stored straight into the owners' buffers         | all_reduce(dense)
  *   dfm_shard_p2p_apply
  * "barrier" = any stream-ordered collective (the host uses a 4-byte all_reduce); no payload goes through NCCL. */
+/* EVAL / PREDICT on a row-sharded model: after requests -> serve (and the two exchanges) the forward pass alone;
+ * rowbuf_dev NULL = the handle's own peer-memory row buffer (fused exchange). */
+int dfm_shard_forward(dfm_handle* h, const dfm_raw_batch* dev_batch, const float* rowbuf_dev, float* logits_dev, void* stream);
 int dfm_shard_requests_dev(dfm_handle* h, const dfm_raw_batch* dev_batch, int32_t* counts_dev_out /* device int32[world] */, void* stream);
 int dfm_shard_ipc_export(dfm_handle* h, unsigned char* handles_out /* 3 * 64 bytes */);
 int dfm_shard_ipc_import(dfm_handle* h, const unsigned char* all_handles /* world * 3 * 64 bytes, rank-major */);

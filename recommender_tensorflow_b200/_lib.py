@@ -74,6 +74,7 @@ _SIGS = {
     "dfm_shard_forward_backward": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfm_shard_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dfm_shard_forward": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfm_shard_requests_dev": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.c_void_p]),
     "dfm_shard_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dfm_shard_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -1216,7 +1216,7 @@ extern "C" int dfm_train_step(dfm_handle* h, const dfm_raw_batch* b, float* loss
 
 extern "C" int dfm_forward(dfm_handle* h, const dfm_raw_batch* b, float* logits_out, void* stream) {
     if (!h || !logits_out) return DFM_ERR_INVALID_ARG;
-    if (h->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "forward-only entry point is not built for row-sharded handles yet");
+    if (h->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "row-sharded handle: use dfm_shard_requests / serve / dfm_shard_forward");
     int rc = check_batch(h, b, false);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
@@ -1331,7 +1331,7 @@ static int shard_requests_impl(dfm_handle* h, const BatchPtrs& bp, int B, uint32
 extern "C" int dfm_shard_requests(dfm_handle* h, const dfm_raw_batch* b, uint32_t* req_rows_out_dev, int32_t* counts_host, void* stream) {
     if (!h || !counts_host) return DFM_ERR_INVALID_ARG;
     if (h->world < 2) FAIL(DFM_ERR_INVALID_ARG, "handle was not created with world > 1");
-    int rc = check_batch(h, b, true);
+    int rc = check_batch(h, b, false);      // labels are only needed by dfm_shard_forward_backward
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
@@ -1417,6 +1417,27 @@ extern "C" int dfm_shard_forward_backward(dfm_handle* h, const dfm_raw_batch* b,
     return rc;
 }
 
+// mode == EVAL / PREDICT on a row-sharded model: the rows were requested and served exactly as for a train step
+// (requests -> exchange -> serve -> exchange); this is the forward pass alone, no state changes.
+extern "C" int dfm_shard_forward(dfm_handle* h, const dfm_raw_batch* b, const float* rowbuf_dev, float* logits_dev, void* stream) {
+    if (!h || !logits_dev) return DFM_ERR_INVALID_ARG;
+    if (h->world < 2) FAIL(DFM_ERR_INVALID_ARG, "handle was not created with world > 1");
+    int rc = check_batch(h, b, false);
+    if (rc) return rc;
+    if (b->batch_size != h->shard_B) FAIL(DFM_ERR_INVALID_ARG, "batch differs from the one given to dfm_shard_requests");
+    if (!rowbuf_dev && !h->p2p_ready) FAIL(DFM_ERR_INVALID_ARG, "rowbuf_dev is null and the peer-memory exchange is not set up");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    BatchPtrs bp = make_ptrs(h, b);
+    bp.labels = nullptr;
+    const int64_t l0 = h->launches;
+    DISPATCH_K(h, rc = forward_impl<KK>(h, bp, b->batch_size, st, nullptr, 1.f, logits_dev, nullptr, rowbuf_dev ? rowbuf_dev : h->p2p_rowbuf));
+    h->last_step_launches += h->launches - l0;
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
 template <int K>
 static int shard_apply_impl(dfm_handle* h, const float* grecv, const float* dense_grad, cudaStream_t st) {
     const int64_t t = h->step + 1;
@@ -1450,7 +1471,7 @@ extern "C" int dfm_shard_apply(dfm_handle* h, const float* grecv_dev, const floa
 extern "C" int dfm_shard_requests_dev(dfm_handle* h, const dfm_raw_batch* b, int32_t* counts_dev_out, void* stream) {
     if (!h || !counts_dev_out) return DFM_ERR_INVALID_ARG;
     if (h->world < 2) FAIL(DFM_ERR_INVALID_ARG, "handle was not created with world > 1");
-    int rc = check_batch(h, b, true);
+    int rc = check_batch(h, b, false);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
@@ -1722,7 +1743,7 @@ extern "C" int dfm_train_step_host(dfm_handle* h, const dfm_raw_batch* b, float*
 
 extern "C" int dfm_forward_host(dfm_handle* h, const dfm_raw_batch* b, float* logits_out) {
     if (!h || !logits_out) return DFM_ERR_INVALID_ARG;
-    if (h->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "forward-only entry point is not built for row-sharded handles yet");
+    if (h->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "row-sharded handle: use dfm_shard_requests / serve / dfm_shard_forward");
     int rc = check_batch(h, b, false);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));

@@ -451,6 +451,11 @@ class DeepFMEngine:
         self._check(self.lib.dfm_shard_requests(self.h, C.byref(pb.raw), None, counts, C.c_void_p(stream) if stream else None))
         return list(counts)
 
+    def shard_forward(self, pb, rowbuf, logits, stream=None):
+        """forward pass alone on the served rows (rowbuf None: the handle's own peer-memory row buffer)"""
+        self._check(self.lib.dfm_shard_forward(self.h, C.byref(pb.raw), C.c_void_p(rowbuf.data_ptr()) if rowbuf is not None else None,
+                                               C.c_void_p(logits.data_ptr()), C.c_void_p(stream) if stream else None))
+
     def shard_requests_dev(self, pb, counts_dev, stream=None):
         """asynchronous: per-owner counts land in counts_dev (int32 cuda tensor [world]); no host sync"""
         self._check(self.lib.dfm_shard_requests_dev(self.h, C.byref(pb.raw), C.c_void_p(counts_dev.data_ptr()),

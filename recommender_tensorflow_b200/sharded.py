@@ -125,6 +125,25 @@ class ShardedTrainer:
         return self.dense[nd]
 
 
+    @_on_real_stream
+    def predict_logits(self, pb):
+        """EVAL / PREDICT: logits of this rank's batch (cuda tensor [B]); no state changes."""
+        torch, dist, eng, rw = self.torch, self.dist, self.eng, self.rw
+        st = torch.cuda.current_stream().cuda_stream
+        send_counts = eng.shard_requests(pb, self.req_rows, st)
+        self.cnt_send.copy_(torch.tensor(send_counts, dtype=torch.int32), non_blocking=True)
+        dist.all_to_all_single(self.cnt_recv, self.cnt_send, group=self.group)
+        recv_counts = self.cnt_recv.tolist()
+        U, n_recv = sum(send_counts), sum(recv_counts)
+        dist.all_to_all_single(self.recv_rows[:n_recv], self.req_rows[:U], recv_counts, send_counts, group=self.group)
+        eng.shard_serve(self.recv_rows, n_recv, self.reply, st)
+        dist.all_to_all_single(self.rowbuf[:U * rw], self.reply[:n_recv * rw], split_sizes(send_counts, rw),
+                               split_sizes(recv_counts, rw), group=self.group)
+        logits = torch.empty(pb.batch_size, dtype=torch.float32, device=self.rowbuf.device)
+        eng.shard_forward(pb, self.rowbuf, logits, st)
+        return logits
+
+
 class P2PShardedTrainer:
     """Same step with the three payload exchanges fused into the kernels: every rank's receive buffers are
     mapped into its peers through CUDA IPC, and the requesting / serving / gradient kernels store straight
@@ -193,6 +212,24 @@ class P2PShardedTrainer:
             for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
                 timings[n1] = timings.get(n1, 0.0) + e0.elapsed_time(e1)
         return self.dense[nd]
+
+
+    @_on_real_stream
+    def predict_logits(self, pb):
+        """EVAL / PREDICT over the fused exchange: logits of this rank's batch (cuda tensor [B]); no state changes."""
+        torch, dist, eng = self.torch, self.dist, self.eng
+        st = torch.cuda.current_stream().cuda_stream
+        eng.shard_requests_dev(pb, self.cnt_mine, st)
+        dist.all_gather_into_tensor(self.cnt_all, self.cnt_mine, group=self.group)
+        eng.shard_p2p_plan(self.cnt_all.cpu().numpy().reshape(self.W, self.W), st)
+        eng.shard_p2p_push_ids(st)
+        dist.all_reduce(self.flag, group=self.group)
+        eng.shard_p2p_serve(st)
+        dist.all_reduce(self.flag, group=self.group)
+        logits = torch.empty(pb.batch_size, dtype=torch.float32, device=self.flag.device)
+        eng.shard_forward(pb, None, logits, st)
+        dist.all_reduce(self.flag, group=self.group)       # nobody overwrites a row buffer that is still being read
+        return logits
 
 
 class VirtualCluster:
@@ -286,6 +323,51 @@ class VirtualCluster:
         if return_logits:
             return loss, torch.cat(logits).cpu().numpy()
         return loss
+
+    def predict_logits(self, pbs):
+        """EVAL / PREDICT: logits of all ranks' batches, concatenated in rank order (numpy)."""
+        torch = self.torch
+        dev = "cuda:%d" % self.engs[0].device
+        rw = self.engs[0].row_width
+        outs = []
+        if self.p2p:
+            counts = np.array([e.shard_requests_counts(pb) for e, pb in zip(self.engs, pbs)], dtype=np.int32)
+            for e in self.engs:
+                e.shard_p2p_plan(counts)
+            for e in self.engs:
+                e.shard_p2p_push_ids()
+            for e in self.engs:
+                e.sync()
+            for e in self.engs:
+                e.shard_p2p_serve()
+            for e in self.engs:
+                e.sync()
+            for e, pb in zip(self.engs, pbs):
+                lg = torch.empty(pb.batch_size, dtype=torch.float32, device=dev)
+                e.shard_forward(pb, None, lg)
+                e.sync()
+                outs.append(lg)
+        else:
+            req, counts = [], []
+            for e, pb in zip(self.engs, pbs):
+                buf = torch.empty(pb.batch_size * max(e.n_slots, 1), dtype=torch.int32, device=dev)
+                counts.append(e.shard_requests(pb, buf))
+                req.append(buf[:sum(counts[-1])])
+            recv_rows, recv_counts = route_all_to_all(req, counts)
+            replies = []
+            for e, rr in zip(self.engs, recv_rows):
+                rep = torch.empty(max(rr.numel(), 1) * rw, dtype=torch.float32, device=dev)
+                e.shard_serve(rr.contiguous(), rr.numel(), rep)
+                e.sync()
+                replies.append(rep[:rr.numel() * rw])
+            rowbufs, _ = route_all_to_all(replies, recv_counts, rw)
+            for e, pb, rb in zip(self.engs, pbs, rowbufs):
+                lg = torch.empty(pb.batch_size, dtype=torch.float32, device=dev)
+                rbc = rb.contiguous() if rb.numel() else torch.zeros(rw, dtype=torch.float32, device=dev)
+                e.shard_forward(pb, rbc, lg)
+                e.sync()
+                outs.append(lg)
+        return torch.cat(outs).cpu().numpy()
 
     def state(self, names_with_slots):
         """Global arrays reassembled from the shards (dense variables from rank 0)."""

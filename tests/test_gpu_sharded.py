@@ -150,3 +150,47 @@ def test_p2p_ipc_two_processes():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=root)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "P2P_OK" in r.stdout
+
+
+@pytest.mark.parametrize("p2p", [False, True])
+def test_sharded_forward_only_equals_single_gpu(p2p):
+    """EVAL / PREDICT on a row-sharded model (dfm_shard_forward): same weights -> the logits of the unsharded model,
+    bit for bit (the rows travel, the arithmetic is the same), before and after training steps; no state change."""
+    cats, nums = synth.criteo_columns(3000, n_cat=10, n_num=5)
+    kw = dict(embedding_size=8, hidden_units=(32, 16))
+    world, per = 2, 300
+    ref = DeepFMEngine(cats, nums, max_batch=world * per, **kw)
+    ora, w = make_pair(ref, seed=31)
+    engs = [DeepFMEngine(cats, nums, max_batch=per, rank=r, world=world, **kw) for r in range(world)]
+    for e in engs:
+        e.set_weights_sharded(w)
+    vc = VirtualCluster(engs, p2p=p2p)
+    rng = np.random.default_rng(32)
+
+    def split(feats, y=None):
+        pbs = []
+        for r, e in enumerate(engs):
+            fr = {}
+            for k, v in feats.items():
+                if isinstance(v, tuple):
+                    data, offs = v
+                    o = offs[r * per:(r + 1) * per + 1]
+                    fr[k] = (data[o[0]:o[-1]].copy(), (o - o[0]).astype(np.int32))
+                else:
+                    fr[k] = v[r * per:(r + 1) * per]
+            pbs.append(e.pack(fr, None if y is None else y[r * per:(r + 1) * per], device=True))
+        return pbs
+
+    feats, y = synth.criteo_batch(world * per, rng, key_space=5000)
+    assert np.array_equal(vc.predict_logits(split(feats)), ref.predict_logits(feats))
+    for _ in range(3):
+        f2, y2 = synth.criteo_batch(world * per, rng, key_space=5000)
+        vc.train_step(split(f2, y2))
+        ref.train_step(f2, y2)
+    before = vc.state(_names(engs[0]))
+    got, want = vc.predict_logits(split(feats)), ref.predict_logits(feats)
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-6)        # trained separately: fp32 re-association of the gradient sums
+    after = vc.state(_names(engs[0]))
+    for k in before:
+        assert np.array_equal(before[k], after[k]), k
+    assert all(e.global_step == 3 for e in engs)
