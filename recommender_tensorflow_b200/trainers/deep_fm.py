@@ -41,14 +41,21 @@ def _build_engine(params, batch_size):
     if activation_fn not in ("relu", None) and getattr(activation_fn, "__name__", "") != "relu":
         raise NotImplementedError("only the reference default activation (ReLU) is built")
     opt = get_optimizer(optimizer, learning_rate)
-    return DeepFMEngine(categorical_columns, numeric_columns, embedding_size=embedding_size, hidden_units=hidden_units,
-                        use_linear=bool(use_linear), use_mf=bool(use_mf), use_dnn=bool(use_dnn), loss_reduction="mean",
-                        opt_deep=opt, opt_linear=dict(opt), max_batch=params.get("max_batch", max(batch_size, 1)),
-                        device=params.get("device", 0), feature_dtypes=params.get("feature_dtypes", FEATURE_DTYPES),
-                        dropout=float(dropout or 0.0), dropout_seed=int(params.get("dropout_seed", 0)))
+    eng = DeepFMEngine(categorical_columns, numeric_columns, embedding_size=embedding_size, hidden_units=hidden_units,
+                       use_linear=bool(use_linear), use_mf=bool(use_mf), use_dnn=bool(use_dnn), loss_reduction="mean",
+                       opt_deep=opt, opt_linear=dict(opt), max_batch=params.get("max_batch", max(batch_size, 1)),
+                       device=params.get("device", 0), feature_dtypes=params.get("feature_dtypes", FEATURE_DTYPES),
+                       dropout=float(dropout or 0.0), dropout_seed=int(params.get("dropout_seed", 0)))
+    # the variable initialisers TF runs when the graph is first executed (truncated normal 1/sqrt(k) for the embedding
+    # tables, glorot uniform for the dense kernels, zeros for linear weights and biases); RunConfig.tf_random_seed
+    seed = params.get("tf_random_seed")
+    eng.init_random(int(seed) if seed is not None else int.from_bytes(os.urandom(4), "little"))
+    return eng
 
 
 def _batch_size(features):
+    if hasattr(features, "batch_size"):      # a PackedBatch (e.g. decoded on the GPU by get_gpu_input_fn)
+        return int(features.batch_size)
     v = next(iter(features.values()))
     return (len(v[1]) - 1) if isinstance(v, tuple) else len(v)
 
@@ -111,6 +118,13 @@ class Estimator:
     def engine(self):
         return self.params.get(_ENGINE_KEY)
 
+    def build(self, max_batch):
+        """Create the model before the first batch arrives (the GPU input path needs the engine to bind its reader)."""
+        if self.engine is None:
+            self.params[_ENGINE_KEY] = _build_engine(self.params, max_batch)
+        self._maybe_restore()
+        return self.engine
+
     def train(self, input_fn, steps=None, max_steps=None, log_every=100):
         loss = None
         for feats, labels in input_fn():
@@ -162,9 +176,17 @@ def train_and_evaluate(args):
         "categorical_columns": feature_columns["linear"],
         "use_linear": not args.exclude_linear, "use_mf": not args.exclude_mf, "use_dnn": not args.exclude_dnn,
         "embedding_size": args.embedding_size, "hidden_units": args.hidden_units, "dropout": args.dropout,
-        "max_batch": args.batch_size})
-    estimator.train(get_input_fn(args.train_csv, batch_size=args.batch_size), max_steps=args.train_steps)
-    metrics = estimator.evaluate(get_input_fn(args.test_csv, ModeKeys.EVAL, batch_size=args.batch_size))
+        "max_batch": args.batch_size, "tf_random_seed": getattr(args, "seed", None)})
+    if getattr(args, "gpu_input", False):     # tf.decode_csv on the device (csv_reader.GpuCsvReader); same record stream
+        from .ml_100k import get_gpu_input_fn
+        eng = estimator.build(args.batch_size)
+        train_fn = get_gpu_input_fn(args.train_csv, eng, batch_size=args.batch_size, seed=getattr(args, "seed", None))
+        eval_fn = get_gpu_input_fn(args.test_csv, eng, ModeKeys.EVAL, batch_size=args.batch_size)
+    else:
+        train_fn = get_input_fn(args.train_csv, batch_size=args.batch_size, seed=getattr(args, "seed", None))
+        eval_fn = get_input_fn(args.test_csv, ModeKeys.EVAL, batch_size=args.batch_size)
+    estimator.train(train_fn, max_steps=args.train_steps)
+    metrics = estimator.evaluate(eval_fn)
     print("INFO:b200:eval " + ", ".join("%s = %s" % kv for kv in sorted(metrics.items())))
     return metrics
 
@@ -173,6 +195,8 @@ if __name__ == "__main__":
     parser = ArgumentParser()
     parser.add_argument("--train-csv", default="data/ml-100k/train.csv")
     parser.add_argument("--test-csv", default="data/ml-100k/test.csv")
+    parser.add_argument("--seed", type=int, default=None, help="tf_random_seed: variable initialisers and the shuffle")
+    parser.add_argument("--gpu-input", action="store_true", help="decode the CSV records on the GPU instead of in Python")
     parser.add_argument("--job-dir", default="checkpoints/deep_fm")
     parser.add_argument("--restore", action="store_true")
     parser.add_argument("--exclude-linear", action="store_true")

@@ -3,6 +3,7 @@
 columns)), no FM term, SUM loss, Adagrad(0.001) on the dnn side and FTRL(min(0.005, 1/sqrt(n_linear)))
 on the linear side (TF-1.12 canned defaults)."""
 import math
+import os
 
 import numpy as np
 
@@ -49,7 +50,7 @@ class _CannedBase:
 
 class DNNLinearCombinedClassifier(_CannedBase):
     def __init__(self, model_dir=None, linear_feature_columns=None, dnn_feature_columns=None, dnn_hidden_units=None,
-                 dnn_dropout=None, config=None, max_batch=4096, device=0, feature_dtypes=FEATURE_DTYPES):
+                 dnn_dropout=None, config=None, max_batch=4096, device=0, feature_dtypes=FEATURE_DTYPES, tf_random_seed=None):
         linear_feature_columns = list(linear_feature_columns or [])
         dnn_feature_columns = list(dnn_feature_columns or [])
         if not linear_feature_columns and not dnn_feature_columns:
@@ -69,4 +70,6 @@ class DNNLinearCombinedClassifier(_CannedBase):
                                    opt_linear=default_optimizer("Ftrl", lin_lr), max_batch=max_batch, device=device,
                                    dropout=float(dnn_dropout or 0.0),
                                    feature_dtypes=feature_dtypes)
+        # variable initialisers (TF runs them on the first session.run; RunConfig.tf_random_seed)
+        self.engine.init_random(int(tf_random_seed) if tf_random_seed is not None else int.from_bytes(os.urandom(4), "little"))
         self.model_dir = model_dir

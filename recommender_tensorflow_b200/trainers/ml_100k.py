@@ -158,8 +158,9 @@ def get_gpu_input_fn(csv_path, engine, mode=ModeKeys.TRAIN, batch_size=32, cutof
     """get_input_fn with tf.decode_csv moved to the GPU: the host only selects whole records
     (same shuffle algorithm and RNG stream as get_input_fn, so the same seed gives the same batches) and copies their
     bytes into a pinned buffer; `GpuCsvReader` splits, unquotes, parses and thresholds on the device.  Yields
-    (PackedBatch on the device, None): the labels are inside the batch.  A record is one text line, as with
-    tf.data.TextLineDataset (a quoted field cannot contain a line break)."""
+    (PackedBatch on the device, labels): in TRAIN mode labels is None (they are inside the batch), otherwise the
+    float32 labels are read back for the metrics.  A record is one text line, as with tf.data.TextLineDataset (a
+    quoted field cannot contain a line break)."""
     from ..csv_reader import GpuCsvReader
 
     def input_fn():
@@ -183,7 +184,8 @@ def get_gpu_input_fn(csv_path, engine, mode=ModeKeys.TRAIN, batch_size=32, cutof
             total = int(out_off[-1])
             src = np.repeat(starts[idx] - out_off[:-1], ln) + np.arange(total, dtype=np.int64)
             np.take(data, src, out=pv[:total])
-            return reader.decode(pinned[:total]), None
+            pb = reader.decode(pinned[:total])
+            return pb, (None if mode == ModeKeys.TRAIN else reader.labels())
 
         if mode == ModeKeys.TRAIN:
             rng = np.random.default_rng(seed)

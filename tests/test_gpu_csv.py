@@ -138,3 +138,22 @@ def test_csv_decode_full_batch_properties():
     assert pb.batch_size == 65536
     feats, labels = _host_parse(text)
     _assert_same(rd, feats, labels, eng)
+
+
+def test_estimator_with_gpu_input_equals_host_input(tmp_path):
+    """trainers.deep_fm.train_and_evaluate --gpu-input: same record stream, same bits as the host-parsed run."""
+    from types import SimpleNamespace
+    from recommender_tensorflow_b200.trainers import deep_fm
+    train, test = str(tmp_path / "train.csv"), str(tmp_path / "test.csv")
+    ml_100k.write_synthetic_csv(train, 1500, seed=1)
+    ml_100k.write_synthetic_csv(test, 400, seed=2)
+    out = []
+    for gpu in (False, True):
+        args = SimpleNamespace(train_csv=train, test_csv=test, job_dir=str(tmp_path / ("job%d" % gpu)), restore=False, embedding_size=4,
+                               hidden_units=[16, 16], dropout=0, batch_size=64, train_steps=30, exclude_linear=False, exclude_mf=False,
+                               exclude_dnn=False, gpu_input=gpu, seed=7)
+        np.random.seed(0)
+        out.append(deep_fm.train_and_evaluate(args))
+    assert out[0]["global_step"] == out[1]["global_step"] == 30
+    for k in ("average_loss", "accuracy", "auc"):
+        assert out[0][k] == out[1][k], (k, out[0][k], out[1][k])
