@@ -85,10 +85,39 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_down_kernel(const T* __rest
     }
 }
 
+// small inputs (radix-digit counts of a small sort, segment flags of a small batch): one block walks the tiles with a
+// running carry -> one launch instead of three dependent ones
+template <typename T>
+__global__ void __launch_bounds__(1024) scan_single_block_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t n, T* __restrict__ total) {
+    __shared__ T wt[33];
+    constexpr int ITEMS = 4;
+    T carry = 0;
+    for (int64_t base = 0; base < n; base += 1024 * ITEMS) {
+        const int64_t i0 = base + (int64_t)threadIdx.x * ITEMS;
+        T v[ITEMS];
+        T s = 0;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) { v[j] = (i0 + j < n) ? in[i0 + j] : T(0); s += v[j]; }
+        T tot;
+        T ex = block_exclusive_scan<T>(s, wt, tot) + carry;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) { if (i0 + j < n) out[i0 + j] = ex; ex += v[j]; }
+        carry += tot;
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+
+constexpr int64_t SCAN_SINGLE_MAX = 4096;      // one tile; measured: at 32 K elements three launches beat one block (0.054 vs 0.066 ms per sort)
+
 template <typename T>
 static void exclusive_scan_t(const T* in, T* out, int64_t n, void* temp, T* total, cudaStream_t st, int64_t* launches) {
     if (n <= 0) {
         if (total) cudaMemsetAsync(total, 0, sizeof(T), st);
+        return;
+    }
+    if (n <= SCAN_SINGLE_MAX) {
+        scan_single_block_kernel<T><<<1, 1024, 0, st>>>(in, out, n, total);
+        if (launches) *launches += 1;
         return;
     }
     T* bs = reinterpret_cast<T*>(temp);
