@@ -120,6 +120,8 @@ struct dfm_handle {
     float *alpha_d = nullptr, *alpha_l = nullptr; int64_t alpha_cap = 0;
 
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    // small tables: the sort / segment stage runs on a side stream next to the gather and the tower (see train_impl)
+    cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool overlap_sort = false;
     HostStage stage[2];
     int64_t host_calls = 0; int last_slot = -1;
     float* h_logits_pinned = nullptr;
@@ -237,6 +239,9 @@ static void free_all(dfm_handle* h) {
     for (auto& e : h->ph_ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
 }
 
@@ -276,6 +281,9 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     h->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
 
     // ---- columns
     std::vector<float> bounds;
@@ -400,6 +408,13 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
             sc.n_rows = (uint32_t)h->n_tiny_rows;
             CK(cudaMemcpy(h->d_tiny_cnt, &sc, sizeof sc, cudaMemcpyHostToDevice));
         }
+    }
+
+    {   // With small tables every row is brought up to date at the start of the step (the literal non-lazy Adam, a few
+        // microseconds for some thousand rows), so the forward pass does not wait for the list of touched rows and the
+        // sort / segment kernels (small grids that leave most SMs idle) run beside the gather and the tower.
+        const char* env = getenv("DFM_OVERLAP_SORT");
+        h->overlap_sort = h->world == 1 && h->R_loc <= (1u << 16) && !(env && atoi(env) == 0);
     }
 
     // ---- tables: one record per row (see Table)
@@ -1139,9 +1154,19 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
     Phase ph(h, st);
     launch_transform<K>(h, bp, B, true, h->ids, st);                                        // K1
     ph.next();
-    if ((rc = build_segments(h, h->ws, n, (uint32_t)h->R, h->key_bits, st, &ph))) return rc;   // sort + segments
-    if ((rc = catchup_touched<K>(h, h->ws, n, t, st))) return rc;
-    if (h->n_tiny && any_adam(h) && t > 1) {     // every row of the tiny columns, hit or not (that IS the non-lazy semantics)
+    const bool overlap = h->overlap_sort && B >= 4096 && n > 0;
+    if (overlap) {
+        CK(cudaEventRecord(h->ev_fork, st));
+        CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        if ((rc = build_segments(h, h->ws, n, (uint32_t)h->R, h->key_bits, h->side_stream, nullptr))) return rc;   // sort + segments, side stream
+        CK(cudaEventRecord(h->ev_join, h->side_stream));
+        ph.next(); ph.next();
+        if ((rc = flush_impl<K>(h, st))) return rc;          // all rows -> step t-1
+    } else {
+        if ((rc = build_segments(h, h->ws, n, (uint32_t)h->R, h->key_bits, st, &ph))) return rc;   // sort + segments
+        if ((rc = catchup_touched<K>(h, h->ws, n, t, st))) return rc;
+    }
+    if (!overlap && h->n_tiny && any_adam(h) && t > 1) {     // every row of the tiny columns, hit or not (that IS the non-lazy semantics)
         const OptDev pod = make_opt(h->od, h->b1p_d, h->b2p_d), pol = make_opt(h->ol, h->b1p_l, h->b2p_l);
         catchup_touched_kernel<K><<<cdiv((int64_t)h->n_tiny_rows * (K / 4), 256), 256, 0, st>>>(h->tb, h->d_trow_grow, h->d_tiny_cnt, (int)(t - 1), h->alpha_d,
                                                                                               h->alpha_l, pod, pol, (bool)h->need_emb, (bool)h->use_linear);
@@ -1151,6 +1176,7 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
     const float scale = h->loss_red == DFM_LOSS_MEAN ? 1.0f / (float)B : 1.0f;
     if ((rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, &ph))) return rc;
     if ((rc = tower_backward<K>(h, bp, B, scale, loss_out, st, &ph))) return rc;
+    if (overlap) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
     if (h->has_bags) {
         GradSrc<K, true> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0, h->dcs, h->d_slot_col, h->inv_cnt};
         rc = sparse_update<K, true>(h, h->ws, n, src, so.od, so.ol, t, nullptr, st, &ph);
