@@ -121,7 +121,8 @@ struct dfm_handle {
 
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     // small tables: the sort / segment stage runs on a side stream next to the gather and the tower (see train_impl)
-    cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool overlap_sort = false;
+    cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_aux_fork = nullptr, ev_aux_join = nullptr;
+    bool overlap_sort = false; size_t splitk_off[DFM_MAX_HIDDEN] = {0};
     HostStage stage[2];
     int64_t host_calls = 0; int last_slot = -1;
     float* h_logits_pinned = nullptr;
@@ -242,6 +243,8 @@ static void free_all(dfm_handle* h) {
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_aux_fork) cudaEventDestroy(h->ev_aux_fork);
+    if (h->ev_aux_join) cudaEventDestroy(h->ev_aux_join);
     delete h;
 }
 
@@ -284,6 +287,8 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     CK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_aux_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_aux_join, cudaEventDisableTiming));
 
     // ---- columns
     std::vector<float> bounds;
@@ -504,7 +509,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
         }
     }
     h->splits = (int)std::min<int64_t>(64, std::max<int64_t>(1, (Bm + 1023) / 1024));
-    size_t splitk_elems = (size_t)h->splits * max_w;
+    size_t splitk_elems = (size_t)h->splits * max_w, tc_split_total = 0;
     // tensor-core tower (3xTF32 tcgen05): every hidden width a multiple of 32 and at least one >= 64
     if (h->use_dnn && h->L >= 1 && getenv("DFM_NO_TC") == nullptr && prop.major == 10) {
         bool ok = true, big = false;
@@ -518,9 +523,12 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
                 off_w += 4 * (int64_t)pad32((int64_t)in * h->hidden[i]);     // W hi, W lo, W^T hi, W^T lo
                 const int m_tiles = (in + 127) / 128, n_tiles = (h->hidden[i] + 255) / 256;
                 h->tc_nz[i] = std::max(1, std::min(128, h->sm_count / std::max(1, m_tiles * n_tiles)));
-                splitk_elems = std::max(splitk_elems, (size_t)h->tc_nz[i] * in * h->hidden[i]);
+                // one region per layer: the reduction of layer i's partials runs on the side stream while layer i-1's
+                // weight-gradient GEMM already writes its own
+                h->splitk_off[i] = tc_split_total; tc_split_total += pad32((int64_t)h->tc_nz[i] * in * h->hidden[i]);
                 in = h->hidden[i];
             }
+            splitk_elems = std::max(splitk_elems, tc_split_total);
             if (dalloc(h, &h->tc_w, (size_t)off_w)) return DFM_ERR_CUDA;
         }
     }
@@ -980,8 +988,17 @@ static int build_segments(dfm_handle* h, SegWS& ws, int64_t n, uint32_t limit, i
 
 // loss reduction + backward through the tower + numeric-feature gradients -> h->dg, h->dE
 template <int K>
-static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale, float* loss_out, cudaStream_t st, Phase* ph) {
+static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale, float* loss_out, cudaStream_t st, Phase* ph,
+                          cudaStream_t aux = nullptr) {
     const int dc = h->dc, d = dc + h->dn, dK = d * K;
+    // aux: side stream for the small reductions (split-K partials, bias column sums) of the tensor-core tower: they
+    // depend only on the kernel just issued and fit beside the GEMM CTAs, so they leave the critical path
+    if (!aux || !h->tc_mlp) aux = st;
+    auto fork = [&]() -> cudaError_t {
+        if (aux == st) return cudaSuccess;
+        cudaError_t e = cudaEventRecord(h->ev_aux_fork, st);
+        return e ? e : cudaStreamWaitEvent(aux, h->ev_aux_fork, 0);
+    };
     const DenseT* bo = find_dense(h, "bo"); const DenseT* bias = find_dense(h, "bias");
     const int small_blocks = std::min((B + SM_TB - 1) / SM_TB, h->small_grid);
     const int head_blocks = h->small_mlp ? small_blocks : std::min(h->fused_head ? h->fused_head_blocks : h->head_blocks, (B + 7) / 8);
@@ -1012,8 +1029,9 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
         const int H = L ? h->hidden[L - 1] : dK;
         if (h->fused_head) {   // head_bwd_kernel already produced dh_L', gWo and gb_L partials
             const DenseT* bL = find_dense(h, "b" + std::to_string(L - 1));
-            reduce_partials_kernel<<<cdiv(H, 256), 256, 0, st>>>(h->head_gpart, head_blocks, (size_t)2 * H, H, h->dg + Wo->off);
-            reduce_partials_kernel<<<cdiv(H, 256), 256, 0, st>>>(h->head_gpart + H, head_blocks, (size_t)2 * H, H, h->dg + bL->off);
+            CK(fork());
+            reduce_partials_kernel<<<cdiv(H, 256), 256, 0, aux>>>(h->head_gpart, head_blocks, (size_t)2 * H, H, h->dg + Wo->off);
+            reduce_partials_kernel<<<cdiv(H, 256), 256, 0, aux>>>(h->head_gpart + H, head_blocks, (size_t)2 * H, H, h->dg + bL->off);
             h->launches += 2;
         } else {
             launch_colsum(h, hL, H, h->dz, B, H, h->dg + Wo->off, st);   // gWo = h_L^T dz
@@ -1042,16 +1060,19 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
                 EpiArgs none{};
                 const bool tc_wgrad = h->tc_mlp && in % 32 == 0 && B >= 1024;
                 int nparts = nsplit;
+                float* part = h->splitk + (tc_wgrad ? h->splitk_off[i] : 0);
+                cudaStream_t rs = tc_wgrad ? aux : st;      // the CUDA-core fallback shares one partial buffer: keep it in order
                 if (tc_wgrad) {
-                    int rc2 = tc_gemm_mnmajor(h, h->act[i], in, h->dact[i + 1], out, h->splitk, in, out, B, h->tc_nz[i], &nparts, st);
+                    int rc2 = tc_gemm_mnmajor(h, h->act[i], in, h->dact[i + 1], out, part, in, out, B, h->tc_nz[i], &nparts, st);
                     if (rc2) return rc2;
+                    CK(fork());
                 } else {
-                    launch_sgemm<false, false, EPI_NONE>(h, h->act[i], in, h->dact[i + 1], out, h->splitk, out, in, out, B, nsplit, k_chunk, none, st);
+                    launch_sgemm<false, false, EPI_NONE>(h, h->act[i], in, h->dact[i + 1], out, part, out, in, out, B, nsplit, k_chunk, none, st);
                 }
-                reduce_partials_kernel<<<cdiv((int64_t)in * out, 256), 256, 0, st>>>(h->splitk, nparts, (size_t)in * out, (int64_t)in * out,
+                reduce_partials_kernel<<<cdiv((int64_t)in * out, 256), 256, 0, rs>>>(part, nparts, (size_t)in * out, (int64_t)in * out,
                                                                                      h->dg + W->off);
                 h->launches++;
-                if (!(h->fused_head && i == L - 1)) launch_colsum(h, h->dact[i + 1], out, nullptr, B, out, h->dg + b->off, st);
+                if (!(h->fused_head && i == L - 1)) launch_colsum(h, h->dact[i + 1], out, nullptr, B, out, h->dg + b->off, rs);
                 // dh_i [B,in] = dh_{i+1} [B,out] * W_i^T
                 if (h->tc_mlp) {
                     const float* w_hi = h->dw + W->off; const float* w_lo = nullptr;   // W [in, out] is already K-major for this GEMM
@@ -1081,6 +1102,10 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
     } else if (h->use_mf) {
         de_fm_kernel<<<cdiv((int64_t)B * dK, 256), 256, 0, st>>>(h->h0, h->s, h->dz, (int64_t)B * dK, dK, K, h->dE, 0);
         h->launches++;
+    }
+    if (aux != st) {      // join: everything below (and the optimizer) sees the reduced gradients
+        CK(cudaEventRecord(h->ev_aux_join, aux));
+        CK(cudaStreamWaitEvent(st, h->ev_aux_join, 0));
     }
     // numeric-feature gradients
     if (h->dn) {
@@ -1175,8 +1200,15 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
     ph.next();
     const float scale = h->loss_red == DFM_LOSS_MEAN ? 1.0f / (float)B : 1.0f;
     if ((rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, &ph))) return rc;
-    if ((rc = tower_backward<K>(h, bp, B, scale, loss_out, st, &ph))) return rc;
+    if ((rc = tower_backward<K>(h, bp, B, scale, loss_out, st, &ph, B >= 4096 ? h->side_stream : nullptr))) return rc;
     if (overlap) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    const bool tiny_side = h->n_tiny && B >= 4096;      // the tiny-column reduction touches other rows than the sorted path: run both at once
+    if (tiny_side) {
+        CK(cudaEventRecord(h->ev_aux_fork, st));
+        CK(cudaStreamWaitEvent(h->side_stream, h->ev_aux_fork, 0));
+        if ((rc = tiny_update<K>(h, B, so.od, so.ol, t, h->side_stream))) return rc;
+        CK(cudaEventRecord(h->ev_aux_join, h->side_stream));
+    }
     if (h->has_bags) {
         GradSrc<K, true> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0, h->dcs, h->d_slot_col, h->inv_cnt};
         rc = sparse_update<K, true>(h, h->ws, n, src, so.od, so.ol, t, nullptr, st, &ph);
@@ -1185,7 +1217,8 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
         rc = sparse_update<K, false>(h, h->ws, n, src, so.od, so.ol, t, nullptr, st, &ph);
     }
     if (rc) return rc;
-    if ((rc = tiny_update<K>(h, B, so.od, so.ol, t, st))) return rc;
+    if (tiny_side) CK(cudaStreamWaitEvent(st, h->ev_aux_join, 0));
+    else if ((rc = tiny_update<K>(h, B, so.od, so.ol, t, st))) return rc;
     if (h->n_dense) {
         dense_apply_kernel<<<cdiv(h->n_dense, 256), 256, 0, st>>>(h->dw, h->ds1, h->ds2, h->dg, h->n_deep, h->n_dense, so.od, so.ol);
         h->launches++;
