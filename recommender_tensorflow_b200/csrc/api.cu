@@ -1002,11 +1002,9 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
     const DenseT* bo = find_dense(h, "bo"); const DenseT* bias = find_dense(h, "bias");
     const int small_blocks = std::min((B + SM_TB - 1) / SM_TB, h->small_grid);
     const int head_blocks = h->small_mlp ? small_blocks : std::min(h->fused_head ? h->fused_head_blocks : h->head_blocks, (B + 7) / 8);
-    head_final_kernel<<<1, 256, 0, st>>>(h->head_part, head_blocks, scale, h->d_loss, h->d_dzsum);
+    head_final_kernel<<<1, 256, 0, st>>>(h->head_part, head_blocks, scale, h->d_loss, h->d_dzsum, loss_out,
+                                         (bo && !h->small_mlp) ? h->dg + bo->off : nullptr, bias ? h->dg + bias->off : nullptr);
     h->launches++;
-    if (loss_out) CK(cudaMemcpyAsync(loss_out, h->d_loss, 4, cudaMemcpyDeviceToDevice, st));
-    if (bo && !h->small_mlp) CK(cudaMemcpyAsync(h->dg + bo->off, h->d_dzsum, 4, cudaMemcpyDeviceToDevice, st));
-    if (bias) CK(cudaMemcpyAsync(h->dg + bias->off, h->d_dzsum, 4, cudaMemcpyDeviceToDevice, st));
     if (ph) ph->next();
     // backward through the tower
     if (h->small_mlp) {

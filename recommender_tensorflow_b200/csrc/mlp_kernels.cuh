@@ -396,8 +396,11 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 }
 
 // loss = (sum of block partials) * loss_scale ; dzsum = sum of dz  (single thread block, fixed order)
+// o1..o3: further destinations (caller's loss buffer, gradients of the output bias and of the linear bias = sum of dz):
+// written here instead of by three 4-byte device-to-device copies on the critical path of the step
 __global__ void head_final_kernel(const float* __restrict__ part, int nblocks, float loss_scale, float* __restrict__ loss_out,
-                                  float* __restrict__ dzsum_out) {
+                                  float* __restrict__ dzsum_out, float* __restrict__ loss_copy, float* __restrict__ dz_copy1,
+                                  float* __restrict__ dz_copy2) {
     __shared__ float sa[256], sc[256];
     float a = 0.f, c = 0.f;
     for (int i = threadIdx.x; i < nblocks; i += 256) { a += part[i * 2]; c += part[i * 2 + 1]; }
@@ -410,6 +413,9 @@ __global__ void head_final_kernel(const float* __restrict__ part, int nblocks, f
     if (threadIdx.x == 0) {
         if (loss_out) *loss_out = sa[0] * loss_scale;
         *dzsum_out = sc[0];
+        if (loss_copy) *loss_copy = sa[0] * loss_scale;
+        if (dz_copy1) *dz_copy1 = sc[0];
+        if (dz_copy2) *dz_copy2 = sc[0];
     }
 }
 
