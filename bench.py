@@ -295,9 +295,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    prefetch = sharded and exchange == "p2p" and os.environ.get("DFM_SHARD_PREFETCH", "1") != "0"
+
     def dev_step(i):
         if sharded:
-            loss_buf.copy_(trainer.train_step(packed_dev[i % n_batches], B * world).reshape(1))
+            kw = {"next_pb": packed_dev[(i + 1) % n_batches]} if prefetch else {}     # the next batch is known: its requests run ahead
+            loss_buf.copy_(trainer.train_step(packed_dev[i % n_batches], B * world, **kw).reshape(1))
         else:
             eng.train_step_device(packed_dev[i % n_batches], loss_out=loss_buf, stream=stream.cuda_stream)
 
@@ -323,10 +326,17 @@ def main():
 
     # ---------------- end-to-end through the host-buffer entry point (e2e)
     if sharded:
+        copied = set()
+
         def e2e_step(i):
-            j = i % n_batches
-            packed_dev[j].arena.copy_(packed_host[j].arena, non_blocking=True)     # H2D of the raw columns
-            return trainer.train_step(packed_dev[j], B * world)
+            j, jn = i % n_batches, (i + 1) % n_batches
+            if i not in copied:
+                packed_dev[j].arena.copy_(packed_host[j].arena, non_blocking=True)     # H2D of the raw columns
+            if not prefetch:
+                return trainer.train_step(packed_dev[j], B * world)
+            packed_dev[jn].arena.copy_(packed_host[jn].arena, non_blocking=True)       # next step's H2D, then its requests run ahead
+            copied.add(i + 1)
+            return trainer.train_step(packed_dev[j], B * world, next_pb=packed_dev[jn])
         with torch.cuda.stream(stream):
             for i in range(2):
                 e2e_step(i)

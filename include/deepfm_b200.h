@@ -215,6 +215,12 @@ int dfm_shard_apply(dfm_handle* h, const float* grecv_dev, const float* dense_gr
  * rowbuf_dev NULL = the handle's own peer-memory row buffer (fused exchange). */
 int dfm_shard_forward(dfm_handle* h, const dfm_raw_batch* dev_batch, const float* rowbuf_dev, float* logits_dev, void* stream);
 int dfm_shard_requests_dev(dfm_handle* h, const dfm_raw_batch* dev_batch, int32_t* counts_dev_out /* device int32[world] */, void* stream);
+/* Request prefetch: the requests of the NEXT batch (no model state involved) computed on the handle's side stream,
+ * into a second buffer set, while the current step runs; dfm_shard_adopt_prefetch (same batch) then replaces the
+ * dfm_shard_requests_dev call of that step and orders `stream` after the prefetch. */
+int dfm_shard_prefetch_requests(dfm_handle* h, const dfm_raw_batch* dev_batch, int32_t* counts_dev_out,
+                                void* after_stream /* stream that produced the batch, or NULL */);
+int dfm_shard_adopt_prefetch(dfm_handle* h, const dfm_raw_batch* dev_batch, void* stream);
 int dfm_shard_ipc_export(dfm_handle* h, unsigned char* handles_out /* 3 * 64 bytes */);
 int dfm_shard_ipc_import(dfm_handle* h, const unsigned char* all_handles /* world * 3 * 64 bytes, rank-major */);
 /* single-process hosts (several ranks on one GPU, as the tests do) wire the handles with raw pointers instead of IPC */

@@ -76,6 +76,8 @@ _SIGS = {
     "dfm_shard_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfm_shard_forward": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfm_shard_requests_dev": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.c_void_p]),
+    "dfm_shard_prefetch_requests": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.c_void_p]),
+    "dfm_shard_adopt_prefetch": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p]),
     "dfm_shard_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dfm_shard_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dfm_shard_p2p_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

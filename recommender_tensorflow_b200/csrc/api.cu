@@ -95,6 +95,9 @@ struct dfm_handle {
     uint32_t* uidx = nullptr;    // lookup -> index in the unique-row list of the local batch
     uint32_t* req_rows = nullptr;   // unique rows of the local batch as local indices at their owners (owner-major order)
     int32_t* d_counts = nullptr; int32_t* h_counts = nullptr;   // [world] unique rows per owner, [world] = total
+    // request state of the NEXT batch, computed ahead of time on the side stream (dfm_shard_prefetch_requests)
+    SegWS ws_next; int32_t* ids_next = nullptr; uint32_t *uidx_next = nullptr, *req_rows_next = nullptr; int32_t* d_counts_next = nullptr;
+    cudaEvent_t ev_prefetch = nullptr; int prefetch_B = -1;
     int64_t shard_n_req = 0, shard_n_recv = 0; int shard_B = 0; float shard_scale = 0.f;
     // fused exchange over peer memory (CUDA IPC): own receive buffers + mapped peer buffers + routing table
     float *p2p_rowbuf = nullptr, *p2p_grecv = nullptr; uint32_t* p2p_recv_rows = nullptr;
@@ -221,6 +224,9 @@ static void free_all(dfm_handle* h) {
     free_ws(h->ws);
     free_ws(h->ws_own);
     if (h->h_counts) cudaFreeHost(h->h_counts);
+    free_ws(h->ws_next);
+    { void* np[] = {h->ids_next, h->uidx_next, h->req_rows_next, h->d_counts_next}; for (void* p : np) if (p) cudaFree(p); }
+    if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
     { void* tp[] = {h->d_tiny_slot, h->d_key_slot, h->d_trow0, h->d_trow_grow, h->tiny_partial, h->d_tiny_cnt};
       for (void* p : tp) if (p) cudaFree(p); }
     for (void* p : h->p2p_opened) if (p) cudaIpcCloseMemHandle(p);
@@ -1472,6 +1478,58 @@ extern "C" int dfm_shard_forward_backward(dfm_handle* h, const dfm_raw_batch* b,
     BatchPtrs bp = make_ptrs(h, b);
     DISPATCH_K(h, rc = shard_fb_impl<KK>(h, bp, b->batch_size, rowbuf_dev, global_batch, loss_dev, logits_dev, gsum_dev, dense_grad_dev, st));
     return rc;
+}
+
+// ---- request prefetch -------------------------------------------------------------------------------------------
+// dfm_shard_requests touches no model state (transform, owner-major sort, unique rows), so the requests of batch t+1
+// can be computed while step t is still running: on the handle's side stream, into a second set of buffers.  The
+// work fills the gaps the step leaves (count exchange, barriers, small kernels).  dfm_shard_adopt_prefetch makes the
+// prefetched set the current one in place of a dfm_shard_requests[_dev] call.
+static void swap_request_state(dfm_handle* h) {
+    std::swap(h->ws, h->ws_next); std::swap(h->ids, h->ids_next); std::swap(h->uidx, h->uidx_next);
+    std::swap(h->req_rows, h->req_rows_next); std::swap(h->d_counts, h->d_counts_next);
+}
+
+extern "C" int dfm_shard_prefetch_requests(dfm_handle* h, const dfm_raw_batch* b, int32_t* counts_dev_out, void* after_stream) {
+    if (!h || !counts_dev_out) return DFM_ERR_INVALID_ARG;
+    if (h->world < 2) FAIL(DFM_ERR_INVALID_ARG, "handle was not created with world > 1");
+    int rc = check_batch(h, b, false);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    if (!h->ws_next.cap) {       // first use: the second buffer set
+        const int64_t n = (int64_t)h->max_batch * std::max(h->dcs, 1);
+        if (alloc_ws(h, h->ws_next, n, h->K) || dalloc(h, &h->ids_next, (size_t)n) || dalloc(h, &h->uidx_next, (size_t)n) ||
+            dalloc(h, &h->req_rows_next, (size_t)n) || dalloc(h, &h->d_counts_next, (size_t)h->world + 1))
+            return DFM_ERR_CUDA;
+        CK(cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming));
+    }
+    if (after_stream) {          // the batch (e.g. its H2D copy) was produced on the caller's stream
+        CK(cudaEventRecord(h->ev_prefetch, (cudaStream_t)after_stream));
+        CK(cudaStreamWaitEvent(h->side_stream, h->ev_prefetch, 0));
+    }
+    BatchPtrs bp = make_ptrs(h, b);
+    const int64_t keep_req = h->shard_n_req, keep_launches = h->last_step_launches; const int keep_B = h->shard_B;
+    swap_request_state(h);        // the kernels below capture the pointers of the second set at launch
+    DISPATCH_K(h, rc = shard_requests_impl<KK>(h, bp, b->batch_size, nullptr, nullptr, h->side_stream, counts_dev_out));
+    swap_request_state(h);
+    h->shard_n_req = keep_req; h->shard_B = keep_B; h->last_step_launches = keep_launches;
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_prefetch, h->side_stream));
+    h->prefetch_B = b->batch_size;
+    return DFM_OK;
+}
+
+extern "C" int dfm_shard_adopt_prefetch(dfm_handle* h, const dfm_raw_batch* b, void* stream) {
+    if (!h) return DFM_ERR_INVALID_ARG;
+    if (h->prefetch_B < 0) FAIL(DFM_ERR_INVALID_ARG, "no prefetched requests");
+    if (!b || b->batch_size != h->prefetch_B) FAIL(DFM_ERR_INVALID_ARG, "batch differs from the one given to dfm_shard_prefetch_requests");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    CK(cudaStreamWaitEvent(st, h->ev_prefetch, 0));
+    swap_request_state(h);
+    h->shard_n_req = -1; h->shard_B = h->prefetch_B; h->prefetch_B = -1;
+    h->last_step_launches = 0;
+    return DFM_OK;
 }
 
 // mode == EVAL / PREDICT on a row-sharded model: the rows were requested and served exactly as for a train step

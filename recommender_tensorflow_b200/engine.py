@@ -461,6 +461,15 @@ class DeepFMEngine:
         self._check(self.lib.dfm_shard_requests_dev(self.h, C.byref(pb.raw), C.c_void_p(counts_dev.data_ptr()),
                                                     C.c_void_p(stream) if stream else None))
 
+    def shard_prefetch_requests(self, pb, counts_dev, after_stream=None):
+        """requests of the NEXT batch on the handle's side stream (second buffer set); counts land in counts_dev.
+        after_stream: the stream that produced the batch (its H2D copy), the side stream waits for it."""
+        self._check(self.lib.dfm_shard_prefetch_requests(self.h, C.byref(pb.raw), C.c_void_p(counts_dev.data_ptr()),
+                                                         C.c_void_p(after_stream) if after_stream else None))
+
+    def shard_adopt_prefetch(self, pb, stream=None):
+        self._check(self.lib.dfm_shard_adopt_prefetch(self.h, C.byref(pb.raw), C.c_void_p(stream) if stream else None))
+
     def shard_ipc_export(self):
         buf = (C.c_ubyte * 192)()
         self._check(self.lib.dfm_shard_ipc_export(self.h, buf))

@@ -173,12 +173,16 @@ class P2PShardedTrainer:
         engine.shard_ipc_import(bytes(allh.cpu().numpy().tobytes()))
         self.dense = torch.zeros(max(engine.dense_size, 1) + 1, dtype=torch.float32, device=dev)
         self.cnt_mine = torch.empty(self.W, dtype=torch.int32, device=dev)
+        self.cnt_next = torch.empty(self.W, dtype=torch.int32, device=dev)
         self.cnt_all = torch.empty(self.W * self.W, dtype=torch.int32, device=dev)
         self.flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._prefetched = None        # the PackedBatch whose requests were computed ahead of time
         dist.barrier(group=group)
 
     @_on_real_stream
-    def train_step(self, pb, global_batch, timings=None):
+    def train_step(self, pb, global_batch, timings=None, next_pb=None):
+        """next_pb: the batch of the following step, if known — its requests (transform, sort, unique rows: no model
+        state) are then computed on the library's side stream while this step runs."""
         torch, dist, eng = self.torch, self.dist, self.eng
         st = torch.cuda.current_stream().cuda_stream
         marks = []
@@ -189,11 +193,19 @@ class P2PShardedTrainer:
                 e.record()
                 marks.append((name, e))
         mark("start")
-        eng.shard_requests_dev(pb, self.cnt_mine, st)
+        if self._prefetched is pb:
+            eng.shard_adopt_prefetch(pb, st)                       # orders this stream after the prefetch
+            self.cnt_mine, self.cnt_next = self.cnt_next, self.cnt_mine
+        else:
+            eng.shard_requests_dev(pb, self.cnt_mine, st)
+        self._prefetched = None
         mark("requests")
         dist.all_gather_into_tensor(self.cnt_all, self.cnt_mine, group=self.group)
         eng.shard_p2p_plan(self.cnt_all.cpu().numpy().reshape(self.W, self.W), st)
         mark("counts")
+        if next_pb is not None:
+            eng.shard_prefetch_requests(next_pb, self.cnt_next, st)
+            self._prefetched = next_pb
         eng.shard_p2p_push_ids(st)
         dist.all_reduce(self.flag, group=self.group)          # barrier: every owner has all its requests
         mark("push_ids")
@@ -249,14 +261,26 @@ class VirtualCluster:
             for e in engines:
                 e.shard_p2p_set_peers(ptrs)
 
-    def _train_step_p2p(self, pbs, return_logits):
+    def _train_step_p2p(self, pbs, return_logits, next_pbs=None):
         torch, W = self.torch, self.W
         dev = "cuda:%d" % self.engs[0].device
         global_batch = sum(pb.batch_size for pb in pbs)
         nd = self.engs[0].dense_size
-        counts = np.array([e.shard_requests_counts(pb) for e, pb in zip(self.engs, pbs)], dtype=np.int32)
+        if getattr(self, "_prefetched", None) is not None and all(a is b for a, b in zip(self._prefetched, pbs)):
+            for e, pb in zip(self.engs, pbs):
+                e.shard_adopt_prefetch(pb)
+                e.sync()
+            counts = self._cnt_next.cpu().numpy().astype(np.int32)
+        else:
+            counts = np.array([e.shard_requests_counts(pb) for e, pb in zip(self.engs, pbs)], dtype=np.int32)
+        self._prefetched = None
         for e in self.engs:
             e.shard_p2p_plan(counts)
+        if next_pbs is not None:       # requests of the next batch, on the engines' side streams, while this step runs
+            self._cnt_next = torch.empty((W, W), dtype=torch.int32, device=dev)
+            for r, (e, pb) in enumerate(zip(self.engs, next_pbs)):
+                e.shard_prefetch_requests(pb, self._cnt_next[r])
+            self._prefetched = list(next_pbs)
         for e in self.engs:
             e.shard_p2p_push_ids()
         for e in self.engs:
@@ -282,9 +306,9 @@ class VirtualCluster:
             return loss, torch.cat(logits).cpu().numpy()
         return loss
 
-    def train_step(self, pbs, return_logits=False):
+    def train_step(self, pbs, return_logits=False, next_pbs=None):
         if self.p2p:
-            return self._train_step_p2p(pbs, return_logits)
+            return self._train_step_p2p(pbs, return_logits, next_pbs)
         torch, W = self.torch, self.W
         dev = "cuda:%d" % self.engs[0].device
         rw = self.engs[0].row_width

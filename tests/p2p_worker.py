@@ -23,23 +23,29 @@ def main():
     per = 4096
     ea = DeepFMEngine(cats, nums, max_batch=per, **kw)
     eb = DeepFMEngine(cats, nums, max_batch=per, **kw)
+    ec = DeepFMEngine(cats, nums, max_batch=per, **kw)
     ea.init_random(3)
     eb.init_random(3)
-    ta, tb = ShardedTrainer(ea), P2PShardedTrainer(eb)
+    ec.init_random(3)
+    ta, tb, tc = ShardedTrainer(ea), P2PShardedTrainer(eb), P2PShardedTrainer(ec)
     rng = np.random.default_rng(100 + rank)
-    for step in range(6):
-        feats, y = synth.criteo_batch(per, rng, key_space=200000)
+    data = [synth.criteo_batch(per, rng, key_space=200000) for _ in range(6)]
+    pcs = [ec.pack(f, y, device=True) for f, y in data]
+    for step, (feats, y) in enumerate(data):
         la = float(ta.train_step(ea.pack(feats, y, device=True), per * world).item())
         lb = float(tb.train_step(eb.pack(feats, y, device=True), per * world).item())
-        assert la == lb, (step, la, lb)
+        lc = float(tc.train_step(pcs[step], per * world, next_pb=pcs[step + 1] if step + 1 < len(pcs) else None).item())   # with request prefetch
+        assert la == lb == lc, (step, la, lb, lc)
     ea.flush()
     eb.flush()
+    ec.flush()
     names = []
     for v in ea.variable_names():
         names.append(v)
         names += [v + "/" + s for s in ea.slot_names(v)]
     for n in names:
         assert np.array_equal(ea.get_tensor(n), eb.get_tensor(n)), n
+        assert np.array_equal(ea.get_tensor(n), ec.get_tensor(n)), n
     dist.barrier()
     if rank == 0:
         print("P2P_OK steps=6 loss=%r" % lb)

@@ -194,3 +194,44 @@ def test_sharded_forward_only_equals_single_gpu(p2p):
     for k in before:
         assert np.array_equal(before[k], after[k]), k
     assert all(e.global_step == 3 for e in engs)
+
+
+def test_request_prefetch_changes_nothing():
+    """dfm_shard_prefetch_requests: the next batch's requests computed on the side stream while the step runs give the
+    same bits as computing them in the step."""
+    cats, nums = synth.criteo_columns(2000, n_cat=8, n_num=4)
+    kw = dict(embedding_size=16, hidden_units=(32, 16))
+    world, per = 2, 512
+    rng = np.random.default_rng(91)
+    batches = [synth.criteo_batch(world * per, rng, key_space=4000) for _ in range(5)]
+    states = []
+    for prefetch in (False, True):
+        engs = [DeepFMEngine(cats, nums, max_batch=per, rank=r, world=world, **kw) for r in range(world)]
+        for e in engs:
+            e.init_random(5)
+        vc = VirtualCluster(engs, p2p=True)
+        packed = []
+        for feats, y in batches:
+            pbs = []
+            for r, e in enumerate(engs):
+                fr = {}
+                for k, v in feats.items():
+                    if isinstance(v, tuple):
+                        data, offs = v
+                        o = offs[r * per:(r + 1) * per + 1]
+                        fr[k] = (data[o[0]:o[-1]].copy(), (o - o[0]).astype(np.int32))
+                    else:
+                        fr[k] = v[r * per:(r + 1) * per]
+                pbs.append(e.pack(fr, y[r * per:(r + 1) * per], device=True))
+            packed.append(pbs)
+        losses = []
+        for i, pbs in enumerate(packed):
+            nxt = packed[i + 1] if prefetch and i + 1 < len(packed) else None
+            losses.append(vc.train_step(pbs, next_pbs=nxt))
+        for e in engs:
+            e.flush()
+        states.append((losses, [{n: e.get_tensor(n) for n in _names(e)} for e in engs]))
+    assert states[0][0] == states[1][0]
+    for sa, sb in zip(states[0][1], states[1][1]):
+        for n in sa:
+            assert np.array_equal(sa[n], sb[n]), n
