@@ -89,7 +89,27 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.gpu, self.samples, self.stop_flag = gpu_index, [], False
 
+    def _run_nvml(self):
+        """NVML directly (nvidia_ml_py): a query takes ~0.1 ms, so even a 20 ms timed region gets several samples."""
+        import pynvml
+        pynvml.nvmlInit()
+        hdl = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(hdl, pynvml.NVML_CLOCK_SM)
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        while not self.stop_flag:
+            sm = pynvml.nvmlDeviceGetClockInfo(hdl, pynvml.NVML_CLOCK_SM)
+            r = int(get_reasons(hdl))
+            self.samples.append([str(sm), str(mx), ""] + ["Active" if r & bits[k] else "Not Active"
+                                                          for k in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+            time.sleep(0.002)
+
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass                      # no NVML binding: fall back to polling nvidia-smi (slow: ~10 samples/s)
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
@@ -341,10 +361,20 @@ def main():
             for i in range(2):
                 e2e_step(i)
         barrier()
+        copied.clear()
+        loss_pin = torch.empty(2, dtype=torch.float32).pin_memory()
+        loss_evs = [torch.cuda.Event(), torch.cuda.Event()]
+        e2e_loss = float("nan")
         t0 = time.perf_counter()
         with torch.cuda.stream(stream):
             for i in range(args.steps):
-                e2e_loss = float(e2e_step(i).item())                                # D2H of the loss every step
+                loss_pin[i % 2:i % 2 + 1].copy_(e2e_step(i).reshape(1), non_blocking=True)   # D2H of the loss, every step ...
+                loss_evs[i % 2].record(stream)
+                if i > 0:                                                                # ... read one step late, like
+                    loss_evs[(i - 1) % 2].synchronize()                                  # dfm_train_step_host_async
+                    e2e_loss = float(loss_pin[(i - 1) % 2])
+            loss_evs[(args.steps - 1) % 2].synchronize()
+            e2e_loss = float(loss_pin[(args.steps - 1) % 2])
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
     else:
@@ -410,7 +440,7 @@ def main():
             "loss_last": last_loss,
             "e2e": {"value": B * args.steps * world / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / args.steps, "loss_last": e2e_loss,
-                    "how": ("pinned host arena -> H2D copy, sharded step, loss.item() every step; wall clock, device sync on both sides"
+                    "how": ("pinned host arena -> H2D copy, sharded step, D2H of the loss every step (read one step late); wall clock, device sync on both sides"
                             if sharded else
                             "dfm_train_step_host_async: pinned host arena -> one H2D copy per step on a copy stream, step, "
                             "D2H of the loss; double buffered, wall clock with a device sync on both sides")},

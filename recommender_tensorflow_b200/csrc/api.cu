@@ -857,7 +857,9 @@ static int ensure_alpha(dfm_handle* h, int64_t t) {
     if (t + 2 < h->alpha_cap) return DFM_OK;
     int64_t ncap = h->alpha_cap * 2;
     while (t + 2 >= ncap) ncap *= 2;
-    CK(cudaStreamSynchronize(h->stream));
+    // rare (capacity doubles): kernels of earlier steps may still append to the history on the caller's stream or on the
+    // side stream, so wait for the whole device before the arrays move
+    CK(cudaDeviceSynchronize());
     for (float** p : {&h->alpha_d, &h->alpha_l}) {
         float* np = nullptr;
         CK(cudaMalloc(&np, ncap * 4));
