@@ -419,3 +419,28 @@ def test_model_learns_a_simple_rule():
     m = get_binary_metrics(y, eng.predict_logits(feats))
     assert first > 0.5 and loss < 0.15, (first, loss)
     assert m["auc"] > 0.99 and m["accuracy"] > 0.97, m
+
+
+def test_resume_at_a_late_step_and_alpha_history_growth():
+    """dfm_set_global_step (checkpoint restore) at step 65 530, then steps across the point where the device-side
+    alpha_t history doubles (65 534): beta powers, alpha_t and the deferred catch-up keep following the oracle."""
+    cats = [fc.categorical_column_with_hash_bucket("a", 50000, "int32"), fc.categorical_column_with_hash_bucket("b", 50000, "int32")]
+    eng = DeepFMEngine(cats, (), embedding_size=8, hidden_units=(8,), max_batch=64)      # 100 000 rows: the deferred (touched-rows) path
+    ora, _ = make_pair(eng, seed=60)
+    T = 65530
+    eng._check(eng.lib.dfm_set_global_step(eng.h, T))
+    for o in (ora.o32, ora.o64):
+        o.t = T
+        for grp in ("deep", "linear"):
+            b1 = b2 = np.float32(1.0)
+            for _ in range(T):              # the float32 running products TF keeps in beta1_power / beta2_power
+                b1 = np.float32(b1 * np.float32(o.opt[grp]["beta1"]))
+                b2 = np.float32(b2 * np.float32(o.opt[grp]["beta2"]))
+            o.pow[grp] = [b1, b2]
+    rng = np.random.default_rng(61)
+    batches = []
+    for step in range(12):
+        a = (np.arange(64) if step == 0 else rng.integers(1000, 2000, 64)).astype(np.int32)   # rows of step 1 idle afterwards
+        batches.append(({"a": a, "b": rng.integers(0, 3000, 64).astype(np.int32)}, (rng.random(64) < 0.5).astype(np.float32)))
+    _run_steps(eng, ora, batches, "late-step")
+    assert eng.global_step == T + 12
