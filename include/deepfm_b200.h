@@ -279,6 +279,11 @@ const char* dfm_csv_last_error(const dfm_csv_reader* r);
  * count and the parse status need one synchronisation of the stream). */
 int dfm_csv_decode(dfm_csv_reader* r, const char* text_dev, int64_t n_bytes, int32_t* n_records_out, void* stream);
 int dfm_csv_decode_host(dfm_csv_reader* r, const char* text_host, int64_t n_bytes, int32_t* n_records_out, void* stream);
+/* File-resident mode: upload the whole CSV text once (it is split into lines on the device; line 0 is usually the
+ * header), then decode batches given as lists of line numbers — what shuffle(16*B).repeat().batch(B) of the reference's
+ * input_fn selects (trainers/ml_100k.py:53-58).  Per batch the host sends 4 bytes per record. */
+int dfm_csv_load(dfm_csv_reader* r, const char* text_host, int64_t n_bytes, int64_t* n_lines_out);
+int dfm_csv_decode_lines(dfm_csv_reader* r, const int32_t* line_idx_host, int32_t n, void* stream);
 int32_t dfm_csv_num_records(const dfm_csv_reader* r);
 const int32_t* dfm_csv_int_column(const dfm_csv_reader* r, int32_t field);     /* device int32[n_records] */
 const char*    dfm_csv_str_bytes(const dfm_csv_reader* r, int32_t field);      /* device bytes */

@@ -92,6 +92,8 @@ _SIGS = {
     "dfm_csv_last_error": (C.c_char_p, [C.c_void_p]),
     "dfm_csv_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.c_void_p]),
     "dfm_csv_decode_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.c_void_p]),
+    "dfm_csv_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "dfm_csv_decode_lines": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "dfm_csv_num_records": (C.c_int32, [C.c_void_p]),
     "dfm_csv_int_column": (C.c_void_p, [C.c_void_p, C.c_int32]),
     "dfm_csv_str_bytes": (C.c_void_p, [C.c_void_p, C.c_int32]),

@@ -72,13 +72,15 @@ __global__ void __launch_bounds__(256) csv_line_starts_kernel(const uint4* __res
 // One thread per record.  Field grammar = tf.decode_csv (RFC 4180): a field is either unquoted (no '"' inside) or
 // quoted with '""' as the escaped quote; an empty field takes the column default; the record must have exactly
 // n_fields fields.  int32 fields: optional blanks, sign, digits, optional blanks.
-__global__ void __launch_bounds__(128) csv_parse_kernel(const char* __restrict__ text, const uint32_t* __restrict__ line_start, uint32_t n_rec,
+__global__ void __launch_bounds__(128) csv_parse_kernel(const char* __restrict__ text, const uint32_t* __restrict__ line_start,
+                                                        const int32_t* __restrict__ line_idx /* null: record r is line r */, uint32_t n_rec,
                                                         CsvDev cfg, int32_t* const* __restrict__ int_out, uint32_t* const* __restrict__ str_pos,
                                                         uint32_t* const* __restrict__ str_len, uint8_t* const* __restrict__ str_flag,
                                                         float* __restrict__ labels, unsigned long long* __restrict__ err) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rec) return;
-    uint32_t p = line_start[r], e = line_start[r + 1];
+    const uint32_t li = line_idx ? (uint32_t)line_idx[r] : r;
+    uint32_t p = line_start[li], e = line_start[li + 1];
     if (e > p && text[e - 1] == '\n') --e;
     if (e > p && text[e - 1] == '\r') --e;
     int field = 0;
@@ -198,6 +200,9 @@ struct dfm_csv_reader {
     float* labels = nullptr;
     uint32_t* h_total = nullptr; unsigned long long* h_err = nullptr;      // pinned
     int32_t n_records = 0;
+    // file-resident mode (dfm_csv_load): the whole text and its line starts stay in HBM, batches are lists of line numbers
+    char* file_text = nullptr; uint32_t* file_line_start = nullptr; int64_t file_lines = 0, file_bytes = 0;
+    int32_t* d_line_idx = nullptr; int32_t* h_line_idx = nullptr;     // [max_records], pinned staging
     std::string error;
 };
 
@@ -233,6 +238,10 @@ extern "C" void dfm_csv_destroy(dfm_csv_reader* r) {
     for (auto p : r->str_off) cudaFree(p);
     for (auto p : r->str_flag) cudaFree(p);
     for (auto p : r->str_bytes) cudaFree(p);
+    if (r->file_text) cudaFree(r->file_text);
+    if (r->file_line_start) cudaFree(r->file_line_start);
+    if (r->d_line_idx) cudaFree(r->d_line_idx);
+    if (r->h_line_idx) cudaFreeHost(r->h_line_idx);
     if (r->h_total) cudaFreeHost(r->h_total);
     if (r->h_err) cudaFreeHost(r->h_err);
     delete r;
@@ -315,17 +324,14 @@ extern "C" int dfm_csv_create(const dfm_csv_config* cfg, dfm_csv_reader** out) {
     return DFM_OK;
 }
 
-static int csv_decode_impl(dfm_csv_reader* r, const char* text_dev, int64_t n_bytes, int32_t* n_records_out, cudaStream_t st) {
-    if (n_bytes < 0 || n_bytes > r->max_bytes) CSV_FAIL(r, DFM_ERR_INVALID_ARG, "dfm_csv_decode: %lld bytes exceed max_bytes", (long long)n_bytes);
-    if (reinterpret_cast<uintptr_t>(text_dev) & 15) CSV_FAIL(r, DFM_ERR_INVALID_ARG, "dfm_csv_decode: text must be 16-byte aligned (and readable up to the next multiple of 16)");
-    r->n_records = 0;
-    if (n_records_out) *n_records_out = 0;
-    if (n_bytes == 0) return DFM_OK;
+// newline scan of `text_dev` -> line_start[0..n_rec] (device), n_rec on the host (one stream sync)
+static int csv_split_lines(dfm_csv_reader* r, const char* text_dev, int64_t n_bytes, uint32_t* counts, void* scan_temp, uint32_t* line_start,
+                           int64_t max_lines, int64_t* n_rec_out, cudaStream_t st) {
     const int64_t n_chunks = (n_bytes + CSV_CHUNK - 1) / CSV_CHUNK;
     const uint4* t16 = reinterpret_cast<const uint4*>(text_dev);
-    csv_count_nl_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(t16, n_bytes, r->counts);
-    prims::exclusive_scan_u32(r->counts, r->counts, n_chunks, r->scan_temp, r->d_total, st, nullptr);
-    csv_line_starts_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(t16, n_bytes, r->counts, r->line_start, (uint32_t)r->max_records + 1);
+    csv_count_nl_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(t16, n_bytes, counts);
+    prims::exclusive_scan_u32(counts, counts, n_chunks, scan_temp, r->d_total, st, nullptr);
+    csv_line_starts_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(t16, n_bytes, counts, line_start, (uint32_t)std::min<int64_t>(max_lines + 1, 0xffffffffll));
     CSV_CK(r, cudaMemcpyAsync(r->h_total, r->d_total, 4, cudaMemcpyDeviceToHost, st));
     char last = 0;
     CSV_CK(r, cudaMemcpyAsync(&last, text_dev + n_bytes - 1, 1, cudaMemcpyDeviceToHost, st));
@@ -333,16 +339,22 @@ static int csv_decode_impl(dfm_csv_reader* r, const char* text_dev, int64_t n_by
     int64_t n_rec = *r->h_total;
     if (last != '\n') {                    // final record without a newline
         ++n_rec;
-        if (n_rec <= (int64_t)r->max_records) {
+        if (n_rec <= max_lines) {
             const uint32_t end = (uint32_t)n_bytes;
-            CSV_CK(r, cudaMemcpyAsync(r->line_start + n_rec, &end, 4, cudaMemcpyHostToDevice, st));
+            CSV_CK(r, cudaMemcpyAsync(line_start + n_rec, &end, 4, cudaMemcpyHostToDevice, st));
         }
     }
-    if (n_rec > r->max_records) CSV_FAIL(r, DFM_ERR_INVALID_ARG, "dfm_csv_decode: %lld records exceed max_records %d", (long long)n_rec, r->max_records);
+    *n_rec_out = n_rec;
+    return DFM_OK;
+}
+
+// fields of n_rec records (record i = line line_idx[i], or line i) -> the reader's output columns; one stream sync
+static int csv_parse_records(dfm_csv_reader* r, const char* text_dev, const uint32_t* line_start, const int32_t* line_idx, int64_t n_rec,
+                             int32_t* n_records_out, cudaStream_t st) {
     CSV_CK(r, cudaMemsetAsync(r->d_err, 0xff, 8, st));
     CsvDev cfg{r->n_fields, r->d_kind, r->d_slot, r->d_int_default, r->d_def_off, r->d_def_bytes, r->label_field, r->label_min};
-    csv_parse_kernel<<<(unsigned)((n_rec + 127) / 128), 128, 0, st>>>(text_dev, r->line_start, (uint32_t)n_rec, cfg, r->d_int_out, r->d_str_pos, r->d_str_off,
-                                                                      r->d_str_flag, r->labels, r->d_err);
+    csv_parse_kernel<<<(unsigned)((n_rec + 127) / 128), 128, 0, st>>>(text_dev, line_start, line_idx, (uint32_t)n_rec, cfg, r->d_int_out, r->d_str_pos,
+                                                                      r->d_str_off, r->d_str_flag, r->labels, r->d_err);
     for (int i = 0; i < r->n_str; ++i)
         prims::exclusive_scan_u32(r->str_off[i], r->str_off[i], n_rec, r->scan_temp, r->str_off[i] + n_rec, st, nullptr);
     if (r->n_str) {
@@ -362,6 +374,75 @@ static int csv_decode_impl(dfm_csv_reader* r, const char* text_dev, int64_t n_by
     r->n_records = (int32_t)n_rec;
     if (n_records_out) *n_records_out = (int32_t)n_rec;
     return DFM_OK;
+}
+
+static int csv_decode_impl(dfm_csv_reader* r, const char* text_dev, int64_t n_bytes, int32_t* n_records_out, cudaStream_t st) {
+    if (n_bytes < 0 || n_bytes > r->max_bytes) CSV_FAIL(r, DFM_ERR_INVALID_ARG, "dfm_csv_decode: %lld bytes exceed max_bytes", (long long)n_bytes);
+    if (reinterpret_cast<uintptr_t>(text_dev) & 15) CSV_FAIL(r, DFM_ERR_INVALID_ARG, "dfm_csv_decode: text must be 16-byte aligned (and readable up to the next multiple of 16)");
+    r->n_records = 0;
+    if (n_records_out) *n_records_out = 0;
+    if (n_bytes == 0) return DFM_OK;
+    int64_t n_rec = 0;
+    int rc = csv_split_lines(r, text_dev, n_bytes, r->counts, r->scan_temp, r->line_start, r->max_records, &n_rec, st);
+    if (rc) return rc;
+    if (n_rec > r->max_records) CSV_FAIL(r, DFM_ERR_INVALID_ARG, "dfm_csv_decode: %lld records exceed max_records %d", (long long)n_rec, r->max_records);
+    return csv_parse_records(r, text_dev, r->line_start, nullptr, n_rec, n_records_out, st);
+}
+
+// ---- file-resident mode ------------------------------------------------------------------------------------------
+// A training CSV is small next to HBM (ML-100K train.csv: 13 MB), so the whole text is uploaded once and split into
+// lines on the device; a batch is then just the list of line numbers the host's shuffle selected (256 KB for 65 536
+// records instead of 10 MB of text), and no byte of the file is touched by the CPU again.
+extern "C" int dfm_csv_load(dfm_csv_reader* r, const char* text_host, int64_t n_bytes, int64_t* n_lines_out) {
+    if (!r || !text_host || n_bytes <= 0) return DFM_ERR_INVALID_ARG;
+    if (n_bytes >= (int64_t)1 << 32) CSV_FAIL(r, DFM_ERR_UNSUPPORTED, "dfm_csv_load: files of 4 GiB and more are not supported");
+    CSV_CK(r, cudaSetDevice(r->device));
+    cudaStream_t st = r->stream;
+    if (r->file_text) { cudaFree(r->file_text); r->file_text = nullptr; }
+    if (r->file_line_start) { cudaFree(r->file_line_start); r->file_line_start = nullptr; }
+    const int64_t padded = (n_bytes + 15) / 16 * 16, n_chunks = padded / CSV_CHUNK;
+    CSV_CK(r, csv_alloc(&r->file_text, (size_t)padded));
+    CSV_CK(r, cudaMemsetAsync(r->file_text + padded - 16, 0, 16, st));
+    CSV_CK(r, cudaMemcpyAsync(r->file_text, text_host, (size_t)n_bytes, cudaMemcpyHostToDevice, st));
+    uint32_t* counts = nullptr; void* scan_temp = nullptr; uint32_t* starts = nullptr;
+    CSV_CK(r, csv_alloc(&counts, (size_t)n_chunks + 1));
+    CSV_CK(r, cudaMalloc(&scan_temp, prims::scan_temp_bytes(n_chunks, 4) + 256));
+    // first pass only counts the lines, so that the line-start array has the right size
+    const uint4* t16 = reinterpret_cast<const uint4*>(r->file_text);
+    csv_count_nl_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(t16, n_bytes, counts);
+    prims::exclusive_scan_u32(counts, counts, n_chunks, scan_temp, r->d_total, st, nullptr);
+    CSV_CK(r, cudaMemcpyAsync(r->h_total, r->d_total, 4, cudaMemcpyDeviceToHost, st));
+    CSV_CK(r, cudaStreamSynchronize(st));
+    const int64_t cap = (int64_t)*r->h_total + 1;
+    CSV_CK(r, csv_alloc(&starts, (size_t)cap + 2));
+    int64_t n_lines = 0;
+    int rc = csv_split_lines(r, r->file_text, n_bytes, counts, scan_temp, starts, cap, &n_lines, st);
+    CSV_CK(r, cudaStreamSynchronize(st));
+    cudaFree(counts); cudaFree(scan_temp);
+    if (rc) { cudaFree(starts); return rc; }
+    r->file_line_start = starts; r->file_lines = n_lines; r->file_bytes = n_bytes;
+    if (!r->d_line_idx) {
+        CSV_CK(r, csv_alloc(&r->d_line_idx, (size_t)r->max_records));
+        CSV_CK(r, cudaMallocHost(&r->h_line_idx, (size_t)r->max_records * 4));
+    }
+    if (n_lines_out) *n_lines_out = n_lines;
+    return DFM_OK;
+}
+
+extern "C" int dfm_csv_decode_lines(dfm_csv_reader* r, const int32_t* line_idx_host, int32_t n, void* stream) {
+    if (!r || (!line_idx_host && n)) return DFM_ERR_INVALID_ARG;
+    if (!r->file_text) CSV_FAIL(r, DFM_ERR_INVALID_ARG, "dfm_csv_decode_lines: call dfm_csv_load first");
+    if (n < 0 || n > r->max_records) CSV_FAIL(r, DFM_ERR_INVALID_ARG, "dfm_csv_decode_lines: %d records exceed max_records %d", n, r->max_records);
+    CSV_CK(r, cudaSetDevice(r->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : r->stream;
+    r->n_records = 0;
+    if (n == 0) return DFM_OK;
+    for (int32_t i = 0; i < n; ++i) {
+        if (line_idx_host[i] < 0 || line_idx_host[i] >= r->file_lines) CSV_FAIL(r, DFM_ERR_INVALID_ARG, "dfm_csv_decode_lines: line %d out of range", line_idx_host[i]);
+        r->h_line_idx[i] = line_idx_host[i];
+    }
+    CSV_CK(r, cudaMemcpyAsync(r->d_line_idx, r->h_line_idx, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    return csv_parse_records(r, r->file_text, r->file_line_start, r->d_line_idx, n, nullptr, st);
 }
 
 extern "C" int dfm_csv_decode(dfm_csv_reader* r, const char* text_dev, int64_t n_bytes, int32_t* n_records_out, void* stream) {

@@ -102,6 +102,21 @@ class GpuCsvReader:
             self._check(self.lib.dfm_csv_decode_host(self.h, C.c_void_p(buf.ctypes.data), int(buf.size), C.byref(n_rec), st))
         return self._batch(n_rec.value)
 
+    def load_file(self, source):
+        """File-resident mode: upload the whole CSV (path or bytes) once; -> number of lines (line 0 = header, if any)."""
+        data = np.fromfile(source, dtype=np.uint8) if isinstance(source, str) else np.frombuffer(bytes(source), dtype=np.uint8)
+        n = C.c_int64(0)
+        self._check(self.lib.dfm_csv_load(self.h, C.c_void_p(data.ctypes.data), int(data.size), C.byref(n)))
+        return int(n.value)
+
+    def decode_lines(self, line_idx, stream=None):
+        """Decode the given lines of the loaded file (record i of the batch = line line_idx[i]) -> PackedBatch."""
+        idx = np.ascontiguousarray(line_idx, dtype=np.int32)
+        if not stream:
+            self.eng.sync()
+        self._check(self.lib.dfm_csv_decode_lines(self.h, C.c_void_p(idx.ctypes.data), int(idx.size), C.c_void_p(stream) if stream else None))
+        return self._batch(int(idx.size))
+
     def _batch(self, n):
         eng = self.eng
         nc = max(len(eng.specs), 1)

@@ -156,35 +156,28 @@ def _train_index_stream(n_rows, cap, rng):
 
 def get_gpu_input_fn(csv_path, engine, mode=ModeKeys.TRAIN, batch_size=32, cutoff=5, seed=None):
     """get_input_fn with tf.decode_csv moved to the GPU: the host only selects whole records
-    (same shuffle algorithm and RNG stream as get_input_fn, so the same seed gives the same batches) and copies their
-    bytes into a pinned buffer; `GpuCsvReader` splits, unquotes, parses and thresholds on the device.  Yields
+    (same shuffle algorithm and RNG stream as get_input_fn, so the same seed gives the same batches); the file itself
+    is uploaded once and stays in HBM, a batch travels as 4 bytes per record (its line number); `GpuCsvReader` splits,
+    unquotes, parses and thresholds on the device.  Yields
     (PackedBatch on the device, labels): in TRAIN mode labels is None (they are inside the batch), otherwise the
     float32 labels are read back for the metrics.  A record is one text line, as with tf.data.TextLineDataset (a
     quoted field cannot contain a line break)."""
     from ..csv_reader import GpuCsvReader
 
     def input_fn():
-        import torch
         data = np.fromfile(csv_path, dtype=np.uint8)
-        if data.size and data[-1] != 10:
-            data = np.concatenate([data, np.array([10], dtype=np.uint8)])
         nl = np.flatnonzero(data == 10)
-        starts = np.concatenate([[0], nl[:-1] + 1])[1:].astype(np.int64)      # [1:] = skip(1), the header
-        lens = (nl + 1)[1:].astype(np.int64) - starts
-        n_rows = int(starts.size)
-        max_bytes = int(np.sort(lens)[-batch_size:].sum()) + 16 if n_rows else 16
+        n_lines = int(nl.size) + (1 if data.size and data[-1] != 10 else 0)
+        n_rows = max(n_lines - 1, 0)                                      # skip(1): the header
+        ends = np.concatenate([nl + 1, [data.size]])[:n_lines]
+        lens = np.diff(np.concatenate([[0], ends]))[1:]
+        max_bytes = int(np.sort(lens)[-batch_size:].sum()) + 16 if n_rows else 16    # bound on one batch's string bytes
         reader = GpuCsvReader(engine, COLUMNS, DEFAULTS, LABEL_COL, cutoff, max_records=batch_size, max_bytes=max_bytes)
-        pinned = torch.empty(max_bytes, dtype=torch.uint8).pin_memory()
-        pv = pinned.numpy()
+        if n_rows:
+            assert reader.load_file(csv_path) == n_lines                  # the file now lives in HBM, split into lines
 
         def emit(idx):
-            idx = np.asarray(idx, dtype=np.int64)
-            ln = lens[idx]
-            out_off = np.concatenate([[0], np.cumsum(ln)])
-            total = int(out_off[-1])
-            src = np.repeat(starts[idx] - out_off[:-1], ln) + np.arange(total, dtype=np.int64)
-            np.take(data, src, out=pv[:total])
-            pb = reader.decode(pinned[:total])
+            pb = reader.decode_lines(np.asarray(idx, dtype=np.int32) + 1)    # +1: line 0 is the header
             return pb, (None if mode == ModeKeys.TRAIN else reader.labels())
 
         if mode == ModeKeys.TRAIN:

@@ -157,3 +157,25 @@ def test_estimator_with_gpu_input_equals_host_input(tmp_path):
     assert out[0]["global_step"] == out[1]["global_step"] == 30
     for k in ("average_loss", "accuracy", "auc"):
         assert out[0][k] == out[1][k], (k, out[0][k], out[1][k])
+
+
+def test_csv_file_resident_decode_lines():
+    """dfm_csv_load + dfm_csv_decode_lines: the file is split into lines on the device once; a batch is a list of line
+    numbers (with repeats, in any order) and decodes to the same columns as the host parse of those lines."""
+    eng = _engine(max_batch=512)
+    rows = _rows(300, np.random.default_rng(21))
+    header = ",".join(ml_100k.COLUMNS)
+    for eol, trailing in (("\n", True), ("\r\n", False)):
+        text = eol.join([header] + rows) + (eol if trailing else "")
+        rd = GpuCsvReader(eng, ml_100k.COLUMNS, ml_100k.DEFAULTS, ml_100k.LABEL_COL, max_records=512, max_bytes=512 * 400)
+        assert rd.load_file(text.encode()) == 301
+        idx = np.random.default_rng(22).integers(0, 300, 512)
+        pb = rd.decode_lines(idx + 1)
+        assert pb.batch_size == 512
+        feats, labels = _host_parse("\n".join(rows[i] for i in idx) + "\n")
+        _assert_same(rd, feats, labels, eng)
+        with pytest.raises(Exception):
+            rd.decode_lines(np.array([301]))          # past the last line
+        with pytest.raises(ValueError):
+            rd.decode_lines(np.array([0]))            # the header is not a record: "user_id" is not an int32
+        rd.close()
