@@ -25,6 +25,7 @@ static thread_local std::string g_create_error;
 struct dfm_handle;
 struct EpiArgs;
 static int tc_setup_once();
+static bool tc_presplit();
 static int tc_gemm_kmajor(dfm_handle* h, const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
                           float* C, int ldc, int M, int N, int K, int epi, const EpiArgs& ep, cudaStream_t st);
 static int tc_gemm_mnmajor(dfm_handle* h, const float* A, int lda, const float* B, int ldb, float* Cpart, int M, int N, int K, int splits,
@@ -929,14 +930,18 @@ static int forward_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t 
             const DenseT* b = find_dense(h, "b" + std::to_string(i));
             const int out = h->hidden[i];
             const int64_t wsz = pad32((int64_t)in * out);
+            // tc_w layout per layer: [W^T hi | W^T lo | W hi | W lo], each pad32(in*out) floats
             float* wt = h->tc_w + h->tc_off[i];
-            (void)wsz;
-            // forward needs W^T [out, in] (K-major B operand); both operands are split into tf32 hi/lo in the kernel
-            tc::split_tf32_transpose_kernel<<<dim3(cdiv(out, 32), cdiv(in, 32)), dim3(32, 8), 0, st>>>(h->dw + W->off, in, out, wt, nullptr);
+            float* wt_lo = tc_presplit() ? wt + wsz : nullptr;
+            // forward needs W^T [out, in] (K-major B operand).  The weights are split into tf32 hi/lo ONCE here (the
+            // persistent GEMM is bound by shared-memory bandwidth: splitting the weight tile again in every CTA costs
+            // 24 KB of shared-memory traffic per k-block against 8 KB more TMA traffic for the ready-made lo tile);
+            // the activations are split in the kernel.
+            tc::split_tf32_transpose_kernel<<<dim3(cdiv(out, 32), cdiv(in, 32)), dim3(32, 8), 0, st>>>(h->dw + W->off, in, out, wt, wt_lo);
             h->launches += 1;
             EpiArgs ep{}; ep.bias = h->dw + b->off;
             set_dropout(h, ep, labels != nullptr, i);
-            int rc = tc_gemm_kmajor(h, h->act[i], nullptr, in, wt, nullptr, in, h->act[i + 1], out, B, out, in, EPI_BIAS_RELU, ep, st);
+            int rc = tc_gemm_kmajor(h, h->act[i], nullptr, in, wt, wt_lo, in, h->act[i + 1], out, B, out, in, EPI_BIAS_RELU, ep, st);
             if (rc) return rc;
             in = out;
         }
@@ -1082,6 +1087,14 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
                 // dh_i [B,in] = dh_{i+1} [B,out] * W_i^T
                 if (h->tc_mlp) {
                     const float* w_hi = h->dw + W->off; const float* w_lo = nullptr;   // W [in, out] is already K-major for this GEMM
+                    if (tc_presplit()) {
+                        const int64_t wsz = pad32((int64_t)in * out);
+                        float* sp_hi = h->tc_w + h->tc_off[i] + 2 * wsz;
+                        float* sp_lo = sp_hi + wsz;
+                        tc::split_tf32_kernel<<<cdiv((int64_t)in * out, 256), 256, 0, st>>>(w_hi, (int64_t)in * out, sp_hi, sp_lo);
+                        h->launches++;
+                        w_hi = sp_hi; w_lo = sp_lo;
+                    }
                     EpiArgs ep{};
                     int rc2;
                     if (i > 0) {
@@ -1910,6 +1923,11 @@ extern "C" int dfm_test_fingerprint64(const uint8_t* bytes_dev, const int32_t* o
     CK(cudaDeviceSynchronize());
     CK(cudaGetLastError());
     return DFM_OK;
+}
+
+static bool tc_presplit() {
+    static const int v = getenv("DFM_TC_PRESPLIT") ? atoi(getenv("DFM_TC_PRESPLIT")) : 1;     // 0: split the weights in every CTA (A/B runs)
+    return v != 0;
 }
 
 // ------------------------------------------------------------------------- tensor-core GEMM host
