@@ -36,10 +36,10 @@ WORKLOADS = {
                                                 buckets=1_000_000),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (tc::gemm_persist_kernel<16>, 38 % of the
-# step, 4 launches per step: 143 / 71 / 132 / 260 MB) from the ncu --set full capture in profiles/r01i_gemm_persist_full_summary.csv
-TRAFFIC = {"deepfm_ml100k_k16_h256x128_b65536": 151.6e6}
+# step, 4 launches per step: 143 / 72 / 132 / 260 MB) from the ncu --set full capture in profiles/r01k_gemm_persist_full_summary.csv
+TRAFFIC = {"deepfm_ml100k_k16_h256x128_b65536": 151.8e6}
 TRAFFIC_NOTE = ("bytes per launch (mean of the 4 launches/step) of the dominant kernel tc::gemm_persist_kernel<16>; "
-                "profiles/r01i_gemm_persist_full_summary.csv; the whole-step algorithmic bytes are bytes_per_sample x batch")
+                "profiles/r01k_gemm_persist_full_summary.csv; the whole-step algorithmic bytes are bytes_per_sample x batch")
 DEFAULT_WORKLOAD = "deepfm_ml100k_k16_h256x128_b65536"
 DEFAULT_SHARDED = "deepfm_criteo_1e7_k16_h16x16_b65536"
 
