@@ -350,30 +350,46 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     for (int i = 0; i < NH; ++i) { wo[i] = __ldg(Wo + lane + 32 * i); gw[i] = 0.f; gb[i] = 0.f; }
     const float b0 = bo[0];
     float lsum = 0.f, dsum = 0.f;
-    for (int b = blockIdx.x * 8 + warp; b < B; b += gridDim.x * 8) {
-        float h[NH];
-        float z = 0.f;
-#pragma unroll
-        for (int i = 0; i < NH; ++i) { h[i] = hL[(size_t)b * H + lane + 32 * i]; z = fmaf(h[i], wo[i], z); }
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-        z += b0;
-        if (zacc) z += zacc[b];
-        const float y = labels[b];
-        const float g = (1.f / (1.f + expf(-z)) - y) * scale;
-        if (lane == 0) {
-            logits[b] = z;
-            if (logits_out) logits_out[b] = z;
-            dz[b] = g;
-            lsum += fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));
-            dsum += g;
-        }
+    // two samples per warp trip (their loads are independent): the loop is a load -> reduce -> exp -> store chain and
+    // was latency-bound at one sample in flight per warp
+    const int stride = gridDim.x * 8;
+    for (int b = blockIdx.x * 8 + warp; b < B; b += 2 * stride) {
+        const int b2 = b + stride;
+        const bool two = b2 < B;
+        float h[2][NH];
+        float z[2] = {0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < NH; ++i) {
-            const float d = h[i] > 0.f ? g * wo[i] * drop_scale : 0.f;
-            dh[(size_t)b * H + lane + 32 * i] = d;
-            gw[i] = fmaf(h[i], g, gw[i]);
-            gb[i] += d;
+            h[0][i] = hL[(size_t)b * H + lane + 32 * i];
+            h[1][i] = two ? hL[(size_t)b2 * H + lane + 32 * i] : 0.f;
+        }
+        const float za0 = zacc ? zacc[b] : 0.f, za1 = (zacc && two) ? zacc[b2] : 0.f;
+        const float y0 = labels[b], y1 = two ? labels[b2] : 0.f;
+#pragma unroll
+        for (int i = 0; i < NH; ++i) { z[0] = fmaf(h[0][i], wo[i], z[0]); z[1] = fmaf(h[1][i], wo[i], z[1]); }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) { z[0] += __shfl_xor_sync(0xffffffffu, z[0], o); z[1] += __shfl_xor_sync(0xffffffffu, z[1], o); }
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+            if (s2 == 1 && !two) break;
+            const int bb = s2 ? b2 : b;
+            const float zz = z[s2] + b0 + (s2 ? za1 : za0);
+            const float y = s2 ? y1 : y0;
+            const float g = (1.f / (1.f + expf(-zz)) - y) * scale;
+            if (lane == 0) {
+                logits[bb] = zz;
+                if (logits_out) logits_out[bb] = zz;
+                dz[bb] = g;
+                lsum += fmaxf(zz, 0.f) - zz * y + log1pf(expf(-fabsf(zz)));
+                dsum += g;
+            }
+#pragma unroll
+            for (int i = 0; i < NH; ++i) {
+                const float d = h[s2][i] > 0.f ? g * wo[i] * drop_scale : 0.f;
+                dh[(size_t)bb * H + lane + 32 * i] = d;
+                gw[i] = fmaf(h[s2][i], g, gw[i]);
+                gb[i] += d;
+            }
         }
     }
     if (lane == 0) { sl[warp] = lsum; sd[warp] = dsum; }
