@@ -323,6 +323,8 @@ def main():
             loss_buf.copy_(trainer.train_step(packed_dev[i % n_batches], B * world, **kw).reshape(1))
         else:
             eng.train_step_device(packed_dev[i % n_batches], loss_out=loss_buf, stream=stream.cuda_stream)
+            if os.environ.get("DFM_PREFETCH", "0") == "1":      # optional lookahead (dfm_prefetch_batch): measured SLOWER here
+                eng.prefetch(packed_dev[(i + 1) % n_batches])   # (0.682 vs 0.648 ms: its kernels delay the persistent GEMM's CTAs)
 
     # ---------------- device-resident timing (value)
     with torch.cuda.stream(stream):

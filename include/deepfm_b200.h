@@ -145,6 +145,10 @@ int dfm_transform(dfm_handle* h, const dfm_raw_batch* dev_batch, int32_t* ids_ou
  * sparse + dense optimizer apply, global_step += 1.  loss_out_dev [1], logits_out_dev [B] or NULL. */
 int dfm_train_step(dfm_handle* h, const dfm_raw_batch* dev_batch, float* loss_out_dev,
                    float* logits_out_dev, void* stream);
+/* Input-pipeline lookahead: transform + sort + segments of the NEXT device batch on the handle's side stream while the
+ * current step runs; the dfm_train_step that follows on that batch adopts them (matched by first column pointer and
+ * batch size, otherwise the prefetch is dropped).  after_stream: the stream that produced the batch, or NULL. */
+int dfm_prefetch_batch(dfm_handle* h, const dfm_raw_batch* dev_batch, void* after_stream);
 /* Same, from host buffers (pinned preferred): H2D of the raw columns, the step, D2H of the loss
  * (and logits if non-NULL).  Returns after the loss is on the host. */
 int dfm_train_step_host(dfm_handle* h, const dfm_raw_batch* host_batch, float* loss_out_host,

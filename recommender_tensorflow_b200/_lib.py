@@ -57,6 +57,7 @@ _SIGS = {
     "dfm_train_step_host": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.POINTER(C.c_float), C.c_void_p]),
     "dfm_train_step_host_async": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.POINTER(C.c_float)]),
     "dfm_train_step_host_drain": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "dfm_prefetch_batch": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p]),
     "dfm_forward": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.c_void_p]),
     "dfm_forward_host": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p]),
     "dfm_flush": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -99,6 +99,8 @@ struct dfm_handle {
     // request state of the NEXT batch, computed ahead of time on the side stream (dfm_shard_prefetch_requests)
     SegWS ws_next; int32_t* ids_next = nullptr; uint32_t *uidx_next = nullptr, *req_rows_next = nullptr; int32_t* d_counts_next = nullptr;
     cudaEvent_t ev_prefetch = nullptr; int prefetch_B = -1;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};     // end of train step t on its stream, ring of two (t % 2)
+    const void* prefetch_tag = nullptr;      // unsharded prefetch (dfm_prefetch_batch): first column pointer of the prefetched batch
     int64_t shard_n_req = 0, shard_n_recv = 0; int shard_B = 0; float shard_scale = 0.f;
     // fused exchange over peer memory (CUDA IPC): own receive buffers + mapped peer buffers + routing table
     float *p2p_rowbuf = nullptr, *p2p_grecv = nullptr; uint32_t* p2p_recv_rows = nullptr;
@@ -228,6 +230,7 @@ static void free_all(dfm_handle* h) {
     free_ws(h->ws_next);
     { void* np[] = {h->ids_next, h->uidx_next, h->req_rows_next, h->d_counts_next}; for (void* p : np) if (p) cudaFree(p); }
     if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
+    for (cudaEvent_t e : h->ev_done) if (e) cudaEventDestroy(e);
     { void* tp[] = {h->d_tiny_slot, h->d_key_slot, h->d_trow0, h->d_trow_grow, h->tiny_partial, h->d_tiny_cnt};
       for (void* p : tp) if (p) cudaFree(p); }
     for (void* p : h->p2p_opened) if (p) cudaIpcCloseMemHandle(p);
@@ -1196,10 +1199,23 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
     const int64_t l0 = h->launches;
     const StepOpts so = step_opts(h);
     Phase ph(h, st);
-    launch_transform<K>(h, bp, B, true, h->ids, st);                                        // K1
+    // ids, sort and segments of this batch may have been computed ahead of time on the side stream (dfm_prefetch_batch)
+    const bool prefetched = h->prefetch_B == B && h->dc > 0 && h->prefetch_tag == bp.cat[0];
+    if (h->prefetch_B >= 0 && !prefetched) h->prefetch_B = -1;            // a different batch arrived: drop the prefetch
+    if (prefetched) {
+        CK(cudaStreamWaitEvent(st, h->ev_prefetch, 0));
+        std::swap(h->ws, h->ws_next); std::swap(h->ids, h->ids_next);
+        h->prefetch_B = -1;
+    } else {
+        launch_transform<K>(h, bp, B, true, h->ids, st);                                    // K1
+    }
     ph.next();
     const bool overlap = h->overlap_sort && B >= 4096 && n > 0;
-    if (overlap) {
+    if (prefetched) {
+        ph.next(); ph.next();
+        if (overlap) { if ((rc = flush_impl<K>(h, st))) return rc; }
+        else if ((rc = catchup_touched<K>(h, h->ws, n, t, st))) return rc;
+    } else if (overlap) {
         CK(cudaEventRecord(h->ev_fork, st));
         CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
         if ((rc = build_segments(h, h->ws, n, (uint32_t)h->R, h->key_bits, h->side_stream, nullptr))) return rc;   // sort + segments, side stream
@@ -1220,7 +1236,7 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
     const float scale = h->loss_red == DFM_LOSS_MEAN ? 1.0f / (float)B : 1.0f;
     if ((rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, &ph))) return rc;
     if ((rc = tower_backward<K>(h, bp, B, scale, loss_out, st, &ph, B >= 4096 ? h->side_stream : nullptr))) return rc;
-    if (overlap) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    if (overlap && !prefetched) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
     const bool tiny_side = h->n_tiny && B >= 4096;      // the tiny-column reduction touches other rows than the sorted path: run both at once
     if (tiny_side) {
         CK(cudaEventRecord(h->ev_aux_fork, st));
@@ -1245,6 +1261,7 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
     ph.next();
     CK(cudaGetLastError());
     commit_step(h, so, t);
+    if (h->ev_done[t & 1]) CK(cudaEventRecord(h->ev_done[t & 1], st));      // dfm_prefetch_batch orders buffer reuse on these
     h->last_step_launches = h->launches - l0;
     return DFM_OK;
 }
@@ -1290,6 +1307,44 @@ extern "C" int dfm_train_step(dfm_handle* h, const dfm_raw_batch* b, float* loss
     BatchPtrs bp = make_ptrs(h, b);
     DISPATCH_K(h, rc = train_impl<KK>(h, bp, b->batch_size, loss_out, logits_out, st));
     return rc;
+}
+
+// Input-pipeline lookahead for the unsharded step: feature transforms, sort and segments of the NEXT batch depend on
+// nothing but the batch, so they can run on the side stream while the current step is still in its tower.  The
+// following dfm_train_step on the same batch (same first column pointer and size) adopts the result.
+extern "C" int dfm_prefetch_batch(dfm_handle* h, const dfm_raw_batch* b, void* after_stream) {
+    if (!h) return DFM_ERR_INVALID_ARG;
+    if (h->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "row-sharded handle: use dfm_shard_prefetch_requests");
+    int rc = check_batch(h, b, false);
+    if (rc) return rc;
+    if (h->dc == 0) return DFM_OK;
+    CK(cudaSetDevice(h->device));
+    const int B = b->batch_size;
+    if (!h->ws_next.cap) {
+        const int64_t nmax = (int64_t)h->max_batch * std::max(h->dcs, 1);
+        if (alloc_ws(h, h->ws_next, nmax, h->K) || dalloc(h, &h->ids_next, (size_t)nmax)) return DFM_ERR_CUDA;
+        CK(cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming));
+        for (cudaEvent_t& e : h->ev_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(cudaDeviceSynchronize());        // first use: nothing recorded yet, start from a quiet device
+    } else if (h->step >= 1) {
+        // the second buffer set was last read by step (latest - 1); the prefetch may overlap the latest step only
+        CK(cudaStreamWaitEvent(h->side_stream, h->ev_done[(h->step - 1) & 1], 0));
+    }
+    if (after_stream) {
+        CK(cudaEventRecord(h->ev_prefetch, (cudaStream_t)after_stream));
+        CK(cudaStreamWaitEvent(h->side_stream, h->ev_prefetch, 0));
+    }
+    BatchPtrs bp = make_ptrs(h, b);
+    const int64_t n = (int64_t)B * (h->n_tiny ? h->n_big : h->dcs);
+    std::swap(h->ws, h->ws_next); std::swap(h->ids, h->ids_next);       // launches below capture the second buffer set
+    DISPATCH_K(h, launch_transform<KK>(h, bp, B, true, h->ids, h->side_stream));
+    rc = build_segments(h, h->ws, n, (uint32_t)h->R, h->key_bits, h->side_stream, nullptr);
+    std::swap(h->ws, h->ws_next); std::swap(h->ids, h->ids_next);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_prefetch, h->side_stream));
+    h->prefetch_B = B; h->prefetch_tag = bp.cat[0];
+    CK(cudaGetLastError());
+    return DFM_OK;
 }
 
 extern "C" int dfm_forward(dfm_handle* h, const dfm_raw_batch* b, float* logits_out, void* stream) {

@@ -403,6 +403,11 @@ class DeepFMEngine:
             return float(loss_out.item()), logits.cpu().numpy()
         return loss_out
 
+    def prefetch(self, pb, after_stream=None):
+        """Input-pipeline lookahead: compute the ids / sort / segments of the NEXT device batch on the library's side
+        stream while the current step runs; the next train_step_device(pb) adopts them."""
+        self._check(self.lib.dfm_prefetch_batch(self.h, C.byref(pb.raw), C.c_void_p(after_stream) if after_stream else None))
+
     def predict_logits(self, features):
         pb = self._as_batch(features, None)
         out = np.empty(pb.batch_size, dtype=np.float32)

@@ -444,3 +444,26 @@ def test_resume_at_a_late_step_and_alpha_history_growth():
         batches.append(({"a": a, "b": rng.integers(0, 3000, 64).astype(np.int32)}, (rng.random(64) < 0.5).astype(np.float32)))
     _run_steps(eng, ora, batches, "late-step")
     assert eng.global_step == T + 12
+
+
+@pytest.mark.parametrize("batch,hidden", [(4096, (64, 32)), (32, (16, 16)), (1024, (16, 16))])
+def test_batch_prefetch_changes_nothing(batch, hidden):
+    """dfm_prefetch_batch: ids / sort / segments of the next batch computed on the side stream while the current
+    step runs -> the same bits as computing them inside the step (also when a prefetch is dropped)."""
+    ml, rng = synth.ML100K(), np.random.default_rng(70)
+    data = [ml.batch(batch, rng) for _ in range(7)]
+    states = []
+    for prefetch in (False, True):
+        eng = _ml_engine(k=8, hidden=hidden, max_batch=batch)
+        eng.init_random(9)
+        pbs = [eng.pack(f, y, device=True) for f, y in data]
+        losses = []
+        for i, pb in enumerate(pbs):
+            losses.append(eng.train_step_device(pb))
+            if prefetch and i + 1 < len(pbs):
+                eng.prefetch(pbs[i + 1] if i != 3 else pbs[0])      # step 4 gets a prefetch for the wrong batch: dropped
+        eng.sync()
+        states.append(([float(x.item()) for x in losses], eng.state()))
+    assert states[0][0] == states[1][0]
+    for name in states[0][1]:
+        assert np.array_equal(states[0][1][name], states[1][1][name]), name
