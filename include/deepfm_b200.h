@@ -239,8 +239,17 @@ int dfm_shard_p2p_apply(dfm_handle* h, const float* dense_grad_dev, void* stream
 
 /* Building-block entry points used by the parity tests (device pointers, synchronous). */
 int dfm_test_sort_pairs(uint32_t* keys_dev, uint32_t* vals_dev, int64_t n, int32_t key_bits);
+/* algo 0: multi-launch LSD radix sort; 1: one-sweep (decoupled look-back); 2: one-sweep with the element count read
+ * from device memory by the kernels (the row-sharded owner side never tells the host how many requests arrived) */
+int dfm_test_sort_pairs_algo(uint32_t* keys_dev, uint32_t* vals_dev, int64_t n, int32_t key_bits, int32_t algo);
 int dfm_test_fingerprint64(const uint8_t* bytes_dev, const int32_t* offsets_dev, int64_t n,
                            uint64_t* out_dev);
+
+/* Non-lazy Adam replay in isolation (csrc/replay.cuh): element i (device arrays) is taken from step last[i] to step
+ * upto by `m *= b1; v *= b2; w -= alpha_t m / (sqrt(v) + eps)` per skipped step — in closed form, or step by step
+ * when force_loop != 0 (the fallback used for hyper-parameters outside the closed form's range). */
+int dfm_test_replay(const dfm_optimizer* opt, float* w_dev, float* m_dev, float* v_dev, const int32_t* last_dev, int64_t n,
+                    int32_t upto, int32_t force_loop);
 
 /* 3xTF32 tcgen05 GEMM of the DNN tower in isolation (device pointers, synchronous):
  * mode 0: C[M,N] = A[M,K] * B[N,K]^T;  mode 2: same, B pre-split into tf32 hi/lo (weight path);

@@ -101,7 +101,9 @@ _SIGS = {
     "dfm_csv_str_offsets": (C.c_void_p, [C.c_void_p, C.c_int32]),
     "dfm_csv_labels": (C.c_void_p, [C.c_void_p]),
     "dfm_test_sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]),
+    "dfm_test_sort_pairs_algo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
     "dfm_test_fingerprint64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "dfm_test_replay": (C.c_int, [C.POINTER(Optimizer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
     "dfm_test_tc_gemm": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "dfm_version": (C.c_char_p, []),
 }

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "dfm_types.cuh"
@@ -15,6 +16,7 @@
 #include "mlp_kernels.cuh"
 #include "prims.cuh"
 #include "small_mlp.cuh"
+#include "fused_small.cuh"
 #include "tc_gemm.cuh"
 
 #ifndef TC_BK
@@ -25,7 +27,19 @@ static thread_local std::string g_create_error;
 struct dfm_handle;
 struct EpiArgs;
 static int tc_setup_once();
+static int build_replay(dfm_handle* h, int64_t cap);
+static RowReplay make_rr(const dfm_handle* h, int64_t upto);
+template <int K> static int fused_set_attr(dfm_handle* h);
 static bool tc_presplit();
+// Split count of the weight-gradient GEMM (reduction over the batch).  tcgen05 aligns and TRUNCATES the products it
+// folds into the fp32 TMEM accumulator: measured bias ~3e-8 x (products in the chain) relative to the accumulated
+// magnitude (1.9e-5 after an 8 192-row chain of random operands, tests/test_gpu_tc_gemm.py; an fp32 reference: 3.5e-7).
+// Shorter chains + round-to-nearest adds of the partials bound it; 2 048 rows keeps the partial traffic of the
+// default split (one CTA per SM) and was measured equal, on the configs[2] step, to 512-row chains (which cost 0.06 ms).
+static inline int tc_wgrad_splits(int64_t K, int requested) {
+    const int64_t need = (K + 2047) / 2048;
+    return (int)std::min<int64_t>(std::max<int64_t>(requested, need), 1024);
+}
 static int tc_gemm_kmajor(dfm_handle* h, const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
                           float* C, int ldc, int M, int N, int K, int epi, const EpiArgs& ep, cudaStream_t st);
 static int tc_gemm_mnmajor(dfm_handle* h, const float* A, int lda, const float* B, int ldb, float* Cpart, int M, int N, int K, int splits,
@@ -39,6 +53,7 @@ struct SegWS {
     unsigned long long* flags = nullptr; void* scan_temp = nullptr; unsigned long long* seg_total = nullptr;
     SegCounts* seg_cnt = nullptr;
     uint32_t *row_start = nullptr, *row_piece0 = nullptr, *piece_start = nullptr, *urow = nullptr, *uval = nullptr, *hot_list = nullptr;
+    uint32_t* pos_row = nullptr;     // sharded requester: unique-row index of every sorted position
     float* piece_sum = nullptr;
     int cur = 0;     // which keys/vals buffer holds the sorted list
     const uint32_t* skeys() const { return keys[cur]; }
@@ -48,6 +63,15 @@ struct SegWS {
 struct DenseT {
     std::string name;
     int64_t off, rows, cols;
+};
+
+// alpha_t = lr sqrt(1 - beta2^t) / (1 - beta1^t) with TF's float32 running products is a deterministic function of t:
+// the whole sequence (and the replay tables built from it) exists ahead of time
+struct ReplayHost {
+    std::vector<float> alpha;          // [cap + H + 1], alpha[0] unused
+    int H = 0; bool adam = false, closed = false;
+    float* d_alpha = nullptr; float4* d_T4 = nullptr; float* d_U = nullptr; float4* d_PQ = nullptr;
+    ReplayTab tab{};
 };
 
 struct HostStage {          // one in-flight host batch (double buffered)
@@ -122,8 +146,11 @@ struct dfm_handle {
 
     // step state
     int64_t step = 0, flushed_step = 0;
-    float b1p_d = 1.f, b2p_d = 1.f, b1p_l = 1.f, b2p_l = 1.f;
-    float *alpha_d = nullptr, *alpha_l = nullptr; int64_t alpha_cap = 0;
+    // alpha_t sequence + closed-form replay tables of the non-lazy Adam (replay.cuh), one set per optimizer group
+    ReplayHost rp_d, rp_l; bool rp_same = false; int64_t alpha_cap = 0;
+    // fused small-tower step (fused_small.cuh): gather + FM + tower forward/backward in one kernel
+    bool fused = false; size_t fused_smem = 0; int fused_grid = 0, n_numacc = 0;
+    float *num_partial = nullptr, *num_scratch = nullptr; unsigned int* fused_done = nullptr;
 
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     // small tables: the sort / segment stage runs on a side stream next to the gather and the tower (see train_impl)
@@ -167,15 +194,22 @@ static inline float __int_as_float_host(int v) { float f; memcpy(&f, &v, 4); ret
 
 static int opt_slots(int kind) { return kind == DFM_OPT_ADAM ? 2 : kind == DFM_OPT_ADAGRAD ? 1 : kind == DFM_OPT_FTRL ? 2 : kind == DFM_OPT_RMSPROP ? 2 : 0; }
 
-static OptDev make_opt(const dfm_optimizer& o, float b1p, float b2p) {
+static OptDev make_opt(const dfm_optimizer& o, float alpha) {
     OptDev d{};
     d.kind = o.kind; d.lr = o.lr; d.b1 = o.beta1; d.b2 = o.beta2; d.eps = o.eps;
     d.omb1 = 1.0f - o.beta1;
     d.omb2 = 1.0f - o.beta2;
-    d.alpha = 0.f;
-    if (o.kind == DFM_OPT_ADAM) d.alpha = o.lr * sqrtf(1.0f - b2p) / (1.0f - b1p);   // float32 like TF
+    d.alpha = o.kind == DFM_OPT_ADAM ? alpha : 0.f;
     d.safe_early = (o.kind == DFM_OPT_ADAM && o.beta1 < 0.95f * sqrtf(o.beta2)) ? 1 : 0;
     return d;
+}
+
+static void free_replay(ReplayHost& r) {
+    if (r.d_alpha) cudaFree(r.d_alpha);
+    if (r.d_T4) cudaFree(r.d_T4);
+    if (r.d_U) cudaFree(r.d_U);
+    if (r.d_PQ) cudaFree(r.d_PQ);
+    r.d_alpha = nullptr; r.d_T4 = nullptr; r.d_U = nullptr; r.d_PQ = nullptr;
 }
 
 template <typename T>
@@ -184,10 +218,11 @@ static int dalloc(dfm_handle* h, T** p, size_t count) {
     return DFM_OK;
 }
 
-static int alloc_ws(dfm_handle* h, SegWS& ws, int64_t n, int K) {
+static int alloc_ws(dfm_handle* h, SegWS& ws, int64_t n, int K, bool with_pos_row = false) {
     ws.cap = n;
+    if (with_pos_row && dalloc(h, &ws.pos_row, n)) return DFM_ERR_CUDA;
     for (int i = 0; i < 2; ++i) { if (dalloc(h, &ws.keys[i], n)) return DFM_ERR_CUDA; if (dalloc(h, &ws.vals[i], n)) return DFM_ERR_CUDA; }
-    CK(cudaMalloc(&ws.sort_temp, prims::sort_temp_bytes(n)));
+    CK(cudaMalloc(&ws.sort_temp, std::max(prims::sort_temp_bytes(n), prims::onesweep_temp_bytes(n))));
     if (dalloc(h, &ws.flags, n)) return DFM_ERR_CUDA;
     CK(cudaMalloc(&ws.scan_temp, prims::scan_temp_bytes(n, 8) + 64));
     if (dalloc(h, &ws.seg_total, 1)) return DFM_ERR_CUDA;
@@ -205,7 +240,7 @@ static int alloc_ws(dfm_handle* h, SegWS& ws, int64_t n, int K) {
 
 static void free_ws(SegWS& ws) {
     void* ptrs[] = {ws.keys[0], ws.keys[1], ws.vals[0], ws.vals[1], ws.sort_temp, ws.flags, ws.scan_temp, ws.seg_total, ws.seg_cnt,
-                    ws.row_start, ws.row_piece0, ws.piece_start, ws.urow, ws.uval, ws.hot_list, ws.piece_sum};
+                    ws.row_start, ws.row_piece0, ws.piece_start, ws.urow, ws.uval, ws.hot_list, ws.piece_sum, ws.pos_row};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -221,11 +256,12 @@ static void free_all(dfm_handle* h) {
     cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, h->d_row_off, h->tb.rec, h->dw,
                     h->ds1, h->ds2, h->dg, h->ids, h->h0, h->s, h->zacc, h->logits, h->dz, h->dE, h->splitk, h->colpart, h->head_part,
-                    h->d_loss, h->d_dzsum, h->d_err, h->alpha_d, h->alpha_l, h->up_partial, h->w0_partial, h->tc_w, h->head_gpart, h->d_slot_col, h->d_slot_j, h->d_field_slot0, h->inv_cnt, h->uidx,
+                    h->d_loss, h->d_dzsum, h->d_err, h->num_partial, h->num_scratch, h->fused_done, h->up_partial, h->w0_partial, h->tc_w, h->head_gpart, h->d_slot_col, h->d_slot_j, h->d_field_slot0, h->inv_cnt, h->uidx,
                     h->req_rows, h->d_counts};
     for (void* p : ptrs) if (p) cudaFree(p);
     free_ws(h->ws);
     free_ws(h->ws_own);
+    free_replay(h->rp_d); free_replay(h->rp_l);
     if (h->h_counts) cudaFreeHost(h->h_counts);
     free_ws(h->ws_next);
     { void* np[] = {h->ids_next, h->uidx_next, h->req_rows_next, h->d_counts_next}; for (void* p : np) if (p) cudaFree(p); }
@@ -273,6 +309,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
         FAIL(DFM_ERR_UNSUPPORTED, "embedding_size must be one of 4, 8, 16, 32, 64, 128");
     if (cfg->n_hidden < 0 || cfg->n_hidden > DFM_MAX_HIDDEN) FAIL(DFM_ERR_INVALID_ARG, "too many hidden layers");
     if (cfg->max_batch <= 0) FAIL(DFM_ERR_INVALID_ARG, "max_batch must be positive");
+    if (cfg->max_batch > (1 << (32 - PAYLOAD_SLOT_BITS))) FAIL(DFM_ERR_UNSUPPORTED, "max_batch must be <= 2^24");
     if (cfg->world > 1 && (cfg->rank < 0 || cfg->rank >= cfg->world)) FAIL(DFM_ERR_INVALID_ARG, "rank must be in [0, world)");
     h->dc = cfg->n_cat; h->dn = cfg->n_num; h->K = K; h->L = cfg->use_dnn ? cfg->n_hidden : 0;
     for (int i = 0; i < h->L; ++i) {
@@ -387,7 +424,20 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
         const char* env = getenv("DFM_TINY");
         std::vector<int32_t> tslot, key_slot(std::max(h->dcs, 1), -1), trow0;
         std::vector<uint32_t> tgrow;
-        const bool enable = h->world == 1 && !h->has_bags && !(env && atoi(env) == 0);
+        // fused small-tower step (fused_small.cuh): its sparse optimizer rebuilds the lookup gradients on the fly, the
+        // dense tiny-column reduction (which reads a dE buffer) is not used with it
+        bool fused_candidate = false;
+        if (cfg->use_dnn && h->need_emb && !h->has_bags && h->L >= 1 && h->L <= SM_MAXL && K <= 32 && getenv("DFM_NO_FUSED") == nullptr &&
+            getenv("DFM_NO_SMALL_MLP") == nullptr) {
+            const int H1 = h->hidden[0];
+            fused_candidate = (H1 == 8 || H1 == 16 || H1 == 32);
+            for (int i = 0; i < h->L; ++i) fused_candidate = fused_candidate && h->hidden[i] <= SM_MAXH;
+            const int D = (h->dc + h->dn) * K;
+            fused_candidate = fused_candidate && D <= (256 / (H1 / 4)) * FS_NC && h->dn * (K + H1 + 2) <= 256 * FS_NUMACC &&
+                              h->dc * FS_TS <= 512;
+        }
+        h->fused = fused_candidate;      // confirmed below once the shared-memory footprint is known
+        const bool enable = h->world == 1 && !h->has_bags && !fused_candidate && !(env && atoi(env) == 0);
         for (int f = 0; f < h->dc; ++f) {
             const uint32_t nb = h->row_off[f + 1] - h->row_off[f];
             // the per-warp accumulators of all tiny rows must fit the shared-memory budget of tiny_reduce_kernel
@@ -480,7 +530,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     CK(cudaFuncSetAttribute(transform_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 4 * DFM_MAX_CAT * 4));
     if (n >= (1ll << 31)) FAIL(DFM_ERR_UNSUPPORTED, "max_batch * n_cat must be < 2^31");
     if (dalloc(h, &h->ids, n)) return DFM_ERR_CUDA;
-    if (alloc_ws(h, h->ws, n, K)) return DFM_ERR_CUDA;
+    if (alloc_ws(h, h->ws, n, K, h->world > 1)) return DFM_ERR_CUDA;
     if (h->world > 1) {
         // owner side: every rank may send up to its whole unique list; 2x the per-rank lookups + slack, checked at run time
         if (alloc_ws(h, h->ws_own, 2 * n + 4096, K)) return DFM_ERR_CUDA;
@@ -498,10 +548,22 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
             memset(h->h_route, 0, sizeof(PeerRoute));
         }
     }
+    if (h->fused) {       // does the fused kernel's tile fit in shared memory?
+        SmallMlpDesc probe{};
+        probe.L = h->L; probe.D = dK;
+        int sum = 0, upc = 0;
+        for (int i = 0; i < h->L; ++i) { probe.H[i] = h->hidden[i]; sum += h->hidden[i]; }
+        for (int i = 0; i < h->L; ++i) upc += (int)pad32(h->hidden[i]) + (i + 1 < h->L ? (int)pad32((int64_t)h->hidden[i] * h->hidden[i + 1]) : 0);
+        upc += (int)pad32(h->hidden[h->L - 1]) + 32;
+        probe.up_count = upc; probe.act_stride = sum | 1;
+        if (fused_smem_floats(probe, K, h->dc, h->dn) * 4 > 200 * 1024) h->fused = false;
+    }
     if (h->need_emb) {
-        if (dalloc(h, &h->h0, Bm * dK)) return DFM_ERR_CUDA;
+        if (!h->fused) {      // the fused step never materialises input_layer or its gradient
+            if (dalloc(h, &h->h0, Bm * dK)) return DFM_ERR_CUDA;
+            if (dalloc(h, &h->dE, Bm * dK)) return DFM_ERR_CUDA;
+        }
         if (dalloc(h, &h->s, Bm * K)) return DFM_ERR_CUDA;
-        if (dalloc(h, &h->dE, Bm * dK)) return DFM_ERR_CUDA;
     }
     if (dalloc(h, &h->zacc, Bm)) return DFM_ERR_CUDA;
     if (dalloc(h, &h->logits, Bm)) return DFM_ERR_CUDA;
@@ -532,7 +594,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
                 h->tc_off[i] = off_w;
                 off_w += 4 * (int64_t)pad32((int64_t)in * h->hidden[i]);     // W hi, W lo, W^T hi, W^T lo
                 const int m_tiles = (in + 127) / 128, n_tiles = (h->hidden[i] + 255) / 256;
-                h->tc_nz[i] = std::max(1, std::min(128, h->sm_count / std::max(1, m_tiles * n_tiles)));
+                h->tc_nz[i] = tc_wgrad_splits(h->max_batch, std::max(1, std::min(128, h->sm_count / std::max(1, m_tiles * n_tiles))));
                 // one region per layer: the reduction of layer i's partials runs on the side stream while layer i-1's
                 // weight-gradient GEMM already writes its own
                 h->splitk_off[i] = tc_split_total; tc_split_total += pad32((int64_t)h->tc_nz[i] * in * h->hidden[i]);
@@ -568,7 +630,30 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
             m.up_count = m.off_bo + 32 - m.off_b[0];
             m.act_stride = sum | 1;
             h->small_smem = small_mlp_fwd_smem(m);
-            if (h->small_smem <= 200 * 1024) {
+            if (h->fused) {
+                h->fused_smem = fused_smem_floats(m, K, h->dc, h->dn) * 4;
+                if (h->fused_smem > 200 * 1024) FAIL(DFM_ERR_UNSUPPORTED, "internal: fused tile estimate was too small");
+                h->small_mlp = true;            // (weights-in-shared-memory tower; selects the small-tower buffers below)
+                h->fused_grid = 2 * h->sm_count;    // persistent, two CTAs per SM
+                h->n_numacc = h->dn * (K + m.H[0] + 2);
+                const size_t g = (size_t)h->fused_grid;
+                if (dalloc(h, &h->up_partial, g * m.up_count)) return DFM_ERR_CUDA;
+                if (dalloc(h, &h->w0_partial, g * (size_t)dK * m.H[0])) return DFM_ERR_CUDA;
+                if (dalloc(h, &h->num_partial, g * (size_t)std::max(h->n_numacc, 1))) return DFM_ERR_CUDA;
+                if (dalloc(h, &h->num_scratch, (size_t)std::max(h->n_numacc, 1))) return DFM_ERR_CUDA;
+                if (dalloc(h, &h->fused_done, 1)) return DFM_ERR_CUDA;
+                CK(cudaMemset(h->fused_done, 0, 4));
+                CK(cudaFree(h->head_part)); h->head_part = nullptr;
+                if (dalloc(h, &h->head_part, g * 2)) return DFM_ERR_CUDA;
+                int rcf = DFM_OK;
+                switch (K) {
+                    case 4: rcf = fused_set_attr<4>(h); break;
+                    case 8: rcf = fused_set_attr<8>(h); break;
+                    case 16: rcf = fused_set_attr<16>(h); break;
+                    default: rcf = fused_set_attr<32>(h); break;
+                }
+                if (rcf) return rcf;
+            } else if (h->small_smem <= 200 * 1024) {
                 h->small_mlp = true;
                 const int tiles = (int)((Bm + SM_TB - 1) / SM_TB);
                 h->small_grid = std::min(tiles, 2 * h->sm_count);
@@ -597,11 +682,10 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     if (dalloc(h, &h->d_dzsum, 1)) return DFM_ERR_CUDA;
     if (dalloc(h, &h->d_err, 1)) return DFM_ERR_CUDA;
     CK(cudaMemset(h->d_err, 0, 4));
-    h->alpha_cap = 1 << 16;
-    if (dalloc(h, &h->alpha_d, (size_t)h->alpha_cap)) return DFM_ERR_CUDA;
-    if (dalloc(h, &h->alpha_l, (size_t)h->alpha_cap)) return DFM_ERR_CUDA;
-    CK(cudaMemset(h->alpha_d, 0, h->alpha_cap * 4));
-    CK(cudaMemset(h->alpha_l, 0, h->alpha_cap * 4));
+    {
+        int rc = build_replay(h, 1 << 14);
+        if (rc) return rc;
+    }
     for (auto& s : h->stage) {
         CK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -804,14 +888,14 @@ static int tiny_update(dfm_handle* h, int B, const OptDev& od, const OptDev& ol,
     tiny_reduce_kernel<K><<<dim3(blocks, (h->n_tiny + G - 1) / G), 256, smem, st>>>(h->ids, B, h->dcs, h->d_tiny_slot, h->d_trow0, h->n_tiny, h->n_tiny_rows,
                                                      h->need_emb ? h->dE : nullptr, h->dz, (h->dc + h->dn) * K, h->tiny_partial);
     tiny_update_kernel<K><<<cdiv((int64_t)h->n_tiny_rows * 32, 256), 256, 0, st>>>(h->tiny_partial, blocks, h->d_trow_grow, h->n_tiny_rows, h->tb, h->emb_slots,
-                                                                                   od, ol, (bool)h->need_emb, (bool)h->use_linear, (int)t);
+                                                                                   od, ol, (bool)h->need_emb, (bool)h->use_linear, (int)t, make_rr(h, t - 1));
     h->launches += 2;
     CK(cudaGetLastError());
     return DFM_OK;
 }
 
 template <int K>
-static void launch_gather(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t st, const float* rowbuf = nullptr) {
+static void launch_gather(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t st, const float* rowbuf = nullptr, int64_t upto = -1) {
     float* num_emb = nullptr; float* num_lin = nullptr; float* bias = nullptr;
     for (const DenseT& dt : h->dense) {
         if (dt.name == "num_emb") num_emb = h->dw + dt.off;
@@ -823,7 +907,8 @@ static void launch_gather(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_
     kern<<<grid, 256, 0, st>>>(h->ids, B, h->dc, h->dn, h->dcs, h->has_bags ? h->d_field_slot0 : nullptr,
                                               h->has_bags ? h->inv_cnt : nullptr, h->d_row_off, h->tb, bp,
                                               num_emb, num_lin, bias, h->use_linear, h->use_mf, h->need_emb, h->h0, h->s, h->zacc,
-                                              rowbuf ? h->uidx : nullptr, rowbuf, K + 4);
+                                              rowbuf ? h->uidx : nullptr, rowbuf, K + 4, make_rr(h, rowbuf ? -1 : upto),
+                                              make_opt(h->od, 0.f), make_opt(h->ol, 0.f));
     h->launches++;
 }
 
@@ -857,36 +942,88 @@ static void launch_colsum(dfm_handle* h, const float* X, int ldx, const float* w
     h->launches += 2;
 }
 
+// (Re)builds the alpha_t sequence and the replay tables of both optimizer groups for steps < cap.
+static int build_replay_group(dfm_handle* h, ReplayHost& r, const dfm_optimizer& o, int64_t cap) {
+    free_replay(r);
+    r = ReplayHost{};
+    r.adam = o.kind == DFM_OPT_ADAM;
+    if (!r.adam) return DFM_OK;
+    const double b1 = (double)o.beta1, b2 = (double)o.beta2, q = sqrt(b2);
+    // closed form: b1^H < 1e-10 within 4096 terms and the series in (1 - q^i) converging fast enough for 4 terms
+    if (b1 > 0.0 && b1 < 1.0 && b2 > 0.0 && b2 < 1.0 && getenv("DFM_REPLAY_LOOP") == nullptr) {
+        const double hh = ceil(log(1e-10) / log(b1));
+        if (hh <= 4096.0 && (1.0 - q) / (1.0 - b1) <= 0.01) { r.closed = true; r.H = std::max(1, (int)hh); }
+    }
+    const size_t n = (size_t)cap + r.H + 1;
+    r.alpha.assign(n, 0.f);
+    float p1 = 1.f, p2 = 1.f;                       // TF's float32 beta1_power / beta2_power
+    for (size_t t = 1; t < n; ++t) {
+        p1 *= o.beta1; p2 *= o.beta2;
+        r.alpha[t] = o.lr * sqrtf(1.0f - p2) / (1.0f - p1);
+    }
+    CK(cudaMalloc(&r.d_alpha, n * 4));
+    CK(cudaMemcpy(r.d_alpha, r.alpha.data(), n * 4, cudaMemcpyHostToDevice));
+    if (r.closed) {
+        CK(cudaMalloc(&r.d_T4, (size_t)cap * sizeof(float4)));
+        CK(cudaMalloc(&r.d_U, (size_t)cap * 12 * 4));
+        std::vector<float4> pq(REPLAY_PQ_N);
+        for (int g = 0; g < REPLAY_PQ_N; ++g) pq[g] = make_float4((float)pow(b1, g), (float)pow(b2, g), (float)(-expm1((double)g * log(q))), 0.f);
+        CK(cudaMalloc(&r.d_PQ, sizeof(float4) * REPLAY_PQ_N));
+        CK(cudaMemcpy(r.d_PQ, pq.data(), sizeof(float4) * REPLAY_PQ_N, cudaMemcpyHostToDevice));
+        replay_tables_kernel<<<cdiv(cap, 128), 128, 0, h->stream>>>(r.d_alpha, (int)cap, r.H, b1, q, r.d_T4, r.d_U);
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
+    }
+    r.tab.T4 = r.d_T4; r.tab.U = r.d_U; r.tab.alpha = r.d_alpha; r.tab.PQ = r.d_PQ;
+    r.tab.l2b1 = (float)log2(b1); r.tab.l2b2 = (float)log2(b2); r.tab.lnq = (float)log(q);
+    r.tab.closed = r.closed ? 1 : 0;
+    return DFM_OK;
+}
+
+static int build_replay(dfm_handle* h, int64_t cap) {
+    int rc = build_replay_group(h, h->rp_d, h->od, cap);
+    if (rc) return rc;
+    if ((rc = build_replay_group(h, h->rp_l, h->ol, cap))) return rc;
+    h->rp_same = h->rp_d.adam && h->rp_l.adam && h->od.lr == h->ol.lr && h->od.beta1 == h->ol.beta1 && h->od.beta2 == h->ol.beta2 &&
+                 h->od.eps == h->ol.eps;
+    h->alpha_cap = cap;
+    return DFM_OK;
+}
+
 static int ensure_alpha(dfm_handle* h, int64_t t) {
     if (t + 2 < h->alpha_cap) return DFM_OK;
     int64_t ncap = h->alpha_cap * 2;
     while (t + 2 >= ncap) ncap *= 2;
-    // rare (capacity doubles): kernels of earlier steps may still append to the history on the caller's stream or on the
-    // side stream, so wait for the whole device before the arrays move
+    // rare (capacity doubles): kernels of earlier steps may still read the tables on the caller's stream or on the
+    // side stream, so wait for the whole device before they move
     CK(cudaDeviceSynchronize());
-    for (float** p : {&h->alpha_d, &h->alpha_l}) {
-        float* np = nullptr;
-        CK(cudaMalloc(&np, ncap * 4));
-        CK(cudaMemset(np, 0, ncap * 4));
-        CK(cudaMemcpy(np, *p, h->alpha_cap * 4, cudaMemcpyDeviceToDevice));
-        CK(cudaFree(*p));
-        *p = np;
-    }
-    h->alpha_cap = ncap;
-    return DFM_OK;
+    return build_replay(h, ncap);
 }
 
 static bool any_adam(const dfm_handle* h) {
     return (h->need_emb && h->od.kind == DFM_OPT_ADAM) || (h->use_linear && h->ol.kind == DFM_OPT_ADAM);
 }
 
+static float alpha_at(const ReplayHost& r, int64_t t) { return (r.adam && t >= 0 && (size_t)t < r.alpha.size()) ? r.alpha[(size_t)t] : 0.f; }
+
+// the replay descriptor of a kernel that must see the rows as of step `upto` (< 0 or no Adam group: nothing to replay)
+static RowReplay make_rr(const dfm_handle* h, int64_t upto) {
+    RowReplay rr{};
+    rr.rd = h->rp_d.tab; rr.rl = h->rp_l.tab;
+    rr.emb_adam = (h->need_emb && h->od.kind == DFM_OPT_ADAM) ? 1 : 0;
+    rr.lin_adam = (h->use_linear && h->ol.kind == DFM_OPT_ADAM) ? 1 : 0;
+    rr.same = h->rp_same ? 1 : 0;
+    rr.upto = (rr.emb_adam || rr.lin_adam) ? (int)upto : -1;
+    if (upto <= 0) rr.upto = -1;       // step 0: nothing has ever been applied
+    return rr;
+}
+
 template <int K>
 static int flush_impl(dfm_handle* h, cudaStream_t st) {
     if (!any_adam(h) || h->flushed_step == h->step || h->R_loc == 0) { h->flushed_step = h->step; return DFM_OK; }
-    OptDev od = make_opt(h->od, h->b1p_d, h->b2p_d), ol = make_opt(h->ol, h->b1p_l, h->b2p_l);
+    OptDev od = make_opt(h->od, alpha_at(h->rp_d, h->step)), ol = make_opt(h->ol, alpha_at(h->rp_l, h->step));
     unsigned grid = (unsigned)std::min<uint64_t>((h->R_loc + (256 / (K / 4)) - 1) / (256 / (K / 4)), (uint64_t)h->sm_count * 16);
-    catchup_all_kernel<K><<<grid, 256, 0, st>>>(h->tb, h->R_loc, (int)h->step, h->alpha_d, h->alpha_l, od, ol,
-                                                (bool)h->need_emb, (bool)h->use_linear);
+    catchup_all_kernel<K><<<grid, 256, 0, st>>>(h->tb, h->R_loc, make_rr(h, h->step), od, ol, (bool)h->need_emb);
     h->launches++;
     CK(cudaGetLastError());
     h->flushed_step = h->step;
@@ -903,9 +1040,9 @@ static void set_dropout(const dfm_handle* h, EpiArgs& ep, bool train, int layer)
 
 template <int K>
 static int forward_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t st, const float* labels, float scale,
-                        float* logits_out, Phase* ph, const float* rowbuf = nullptr) {
+                        float* logits_out, Phase* ph, const float* rowbuf = nullptr, int64_t upto = -1) {
     const int d = h->dc + h->dn, dK = d * K;
-    launch_gather<K>(h, bp, B, st, rowbuf);
+    launch_gather<K>(h, bp, B, st, rowbuf, upto);
     if (ph) ph->next();
     const float* hL = nullptr; int H = 0;
     const DenseT* Wo = find_dense(h, "Wo"); const DenseT* bo = find_dense(h, "bo");
@@ -982,23 +1119,40 @@ static int forward_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t 
     return DFM_OK;
 }
 
-// sort the (key, payload) pairs in ws.keys[0]/vals[0] and derive unique rows / pieces
-static int build_segments(dfm_handle* h, SegWS& ws, int64_t n, uint32_t limit, int bits, cudaStream_t st, Phase* ph) {
+// sort the (key, payload) pairs in ws.keys[0]/vals[0] and derive unique rows / pieces.
+// Default: one-sweep radix sort (one launch per 8-bit digit) + single-pass segment builder; n_dev != nullptr: the pair
+// count lives in device memory (n is then its upper bound).  DFM_OLD_SORT=1: the multi-launch sort / scan kernels.
+static int build_segments(dfm_handle* h, SegWS& ws, int64_t n, uint32_t limit, int bits, cudaStream_t st, Phase* ph,
+                          const uint32_t* n_dev = nullptr) {
+    static const bool old_sort = getenv("DFM_OLD_SORT") != nullptr;
     ws.cur = 0;
-    if (n > 0) ws.cur = prims::radix_sort_pairs(ws.keys, ws.vals, n, bits, ws.sort_temp, st, &h->launches);
-    if (ph) ph->next();
-    if (n > 0) {
-        seg_flag_kernel<<<cdiv(n, 256), 256, 0, st>>>(ws.skeys(), n, limit, ws.flags, ws.seg_cnt);
-        h->launches++;
-        prims::exclusive_scan_u64(reinterpret_cast<const uint64_t*>(ws.flags), reinterpret_cast<uint64_t*>(ws.flags), n, ws.scan_temp,
-                                  reinterpret_cast<uint64_t*>(ws.seg_total), st, &h->launches);
-        seg_fill_kernel<<<cdiv(n, 256), 256, 0, st>>>(ws.skeys(), ws.svals(), n, limit, ws.flags, ws.seg_total, ws.seg_cnt, ws.row_start,
-                                                      ws.row_piece0, ws.piece_start, ws.urow, ws.uval);
-        h->launches++;
-    } else {
-        CK(cudaMemsetAsync(ws.seg_cnt, 0, sizeof(SegCounts), st));
+    if (old_sort && !n_dev && !ws.pos_row) {
+        if (n > 0) ws.cur = prims::radix_sort_pairs(ws.keys, ws.vals, n, bits, ws.sort_temp, st, &h->launches);
+        if (ph) ph->next();
+        if (n > 0) {
+            seg_flag_kernel<<<cdiv(n, 256), 256, 0, st>>>(ws.skeys(), n, limit, ws.flags, ws.seg_cnt);
+            h->launches++;
+            prims::exclusive_scan_u64(reinterpret_cast<const uint64_t*>(ws.flags), reinterpret_cast<uint64_t*>(ws.flags), n, ws.scan_temp,
+                                      reinterpret_cast<uint64_t*>(ws.seg_total), st, &h->launches);
+            seg_fill_kernel<<<cdiv(n, 256), 256, 0, st>>>(ws.skeys(), ws.svals(), n, limit, ws.flags, ws.seg_total, ws.seg_cnt, ws.row_start,
+                                                          ws.row_piece0, ws.piece_start, ws.urow, ws.uval);
+            h->launches++;
+        } else {
+            CK(cudaMemsetAsync(ws.seg_cnt, 0, sizeof(SegCounts), st));
+        }
+        if (ph) ph->next();
+        return DFM_OK;
     }
+    if (n > 0) ws.cur = prims::onesweep_sort_pairs(ws.keys, ws.vals, n, n_dev, bits, ws.sort_temp, st, &h->launches);
     if (ph) ph->next();
+    const int64_t tiles = std::max<int64_t>((n + SB_TILE - 1) / SB_TILE, 1);
+    CK(cudaMemsetAsync(ws.flags, 0, (size_t)tiles * 8, st));              // look-back status words
+    CK(cudaMemsetAsync(ws.seg_total, 0, 8, st));                          // tile ticket
+    seg_build_kernel<<<(unsigned)tiles, 256, 0, st>>>(ws.skeys(), ws.svals(), n, n_dev, limit, ws.flags, reinterpret_cast<uint32_t*>(ws.seg_total),
+                                                      ws.seg_cnt, ws.row_start, ws.row_piece0, ws.piece_start, ws.urow, ws.uval, ws.pos_row);
+    h->launches++;
+    if (ph) ph->next();
+    CK(cudaGetLastError());
     return DFM_OK;
 }
 
@@ -1143,54 +1297,219 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
 }
 
 // deterministic segmented reduction of the sparse gradients (+ optimizer, or gradient rows out when gsum != nullptr)
-template <int K, bool BAGS>
-static int sparse_update(dfm_handle* h, SegWS& ws, int64_t n, const GradSrc<K, BAGS>& src, const OptDev& od, const OptDev& ol, int64_t t,
+template <int K, typename SRC>
+static int sparse_update(dfm_handle* h, SegWS& ws, int64_t n, const SRC& src, const OptDev& od, const OptDev& ol, int64_t t,
                          float* gsum, cudaStream_t st, Phase* ph, const PeerRoute* route = nullptr) {
     const unsigned row_grid = (unsigned)h->sm_count * 8;
     if (n > 0) {
         hot_pieces_kernel<<<row_grid, 256, 0, st>>>(ws.row_start, ws.row_piece0, ws.seg_cnt, ws.hot_list);
-        piece_reduce_kernel<K, BAGS><<<row_grid, 256, 0, st>>>(ws.svals(), ws.piece_start, ws.hot_list, ws.seg_cnt, src, ws.piece_sum);
+        piece_reduce_kernel<K, SRC><<<row_grid, 256, 0, st>>>(ws.svals(), ws.piece_start, ws.hot_list, ws.seg_cnt, src, ws.piece_sum);
         h->launches += 2;
     }
     if (ph) ph->next();
-    row_update_kernel<K, BAGS><<<n > 0 ? row_grid : 1, 256, 0, st>>>(ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0, ws.piece_start, ws.seg_cnt, src,
-                                                               ws.piece_sum, h->tb, h->emb_slots, od, ol, (bool)h->need_emb,
-                                                               (bool)h->use_linear, (int)t, h->alpha_d, h->alpha_l, gsum, K + 4, route);
+    // rows are rewritten here: the non-lazy Adam decay they skipped since their last write is replayed first (to step t-1)
+    constexpr bool kBags = std::is_same<SRC, GradSrc<K, true>>::value;
+    static const bool staged_ok = getenv("DFM_NO_STAGED_APPLY") == nullptr;
+    if (!gsum && !route && !kBags && staged_ok) {
+        // table records + first gradient operand staged by cp.async, a few iterations ahead (row_apply.cuh)
+        if constexpr (std::is_same<SRC, GradSrc<K, false>>::value) {
+            using S2 = StageSrcPlain<K>;
+            static bool attr = false;
+            if (!attr) { CK(cudaFuncSetAttribute(row_apply_kernel<K, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RowApplyCfg<K, S2>::SMEM)); attr = true; }
+            S2 s2{}; s2.s = src;
+            row_apply_kernel<K, S2><<<n > 0 ? (unsigned)h->sm_count * 3 : 1, 256, RowApplyCfg<K, S2>::SMEM, st>>>(
+                ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0, ws.piece_start, ws.seg_cnt, s2, ws.piece_sum, h->tb, h->emb_slots, od, ol,
+                (bool)h->need_emb, (bool)h->use_linear, (int)t, make_rr(h, t - 1));
+        } else if constexpr (!kBags) {
+            static bool attr = false;
+            if (!attr) { CK(cudaFuncSetAttribute(row_apply_kernel<K, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, RowApplyCfg<K, SRC>::SMEM)); attr = true; }
+            row_apply_kernel<K, SRC><<<n > 0 ? (unsigned)h->sm_count * 3 : 1, 256, RowApplyCfg<K, SRC>::SMEM, st>>>(
+                ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0, ws.piece_start, ws.seg_cnt, src, ws.piece_sum, h->tb, h->emb_slots, od, ol,
+                (bool)h->need_emb, (bool)h->use_linear, (int)t, make_rr(h, t - 1));
+        }
+    } else {
+        row_update_kernel<K, SRC><<<n > 0 ? row_grid : 1, 256, 0, st>>>(ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0, ws.piece_start, ws.seg_cnt, src,
+                                                                   ws.piece_sum, h->tb, h->emb_slots, od, ol, (bool)h->need_emb,
+                                                                   (bool)h->use_linear, (int)t, make_rr(h, gsum ? -1 : t - 1), gsum, K + 4, route);
+    }
     h->launches++;
     if (ph) ph->next();
     CK(cudaGetLastError());
     return DFM_OK;
 }
 
-struct StepOpts { float b1p_d, b2p_d, b1p_l, b2p_l; OptDev od, ol; };
+struct StepOpts { OptDev od, ol; };
 static StepOpts step_opts(const dfm_handle* h) {
     StepOpts o;
-    // beta powers as seen by step t (TF multiplies them after each apply, starting from beta)
-    o.b1p_d = h->b1p_d * h->od.beta1; o.b2p_d = h->b2p_d * h->od.beta2;
-    o.b1p_l = h->b1p_l * h->ol.beta1; o.b2p_l = h->b2p_l * h->ol.beta2;
-    o.od = make_opt(h->od, o.b1p_d, o.b2p_d); o.ol = make_opt(h->ol, o.b1p_l, o.b2p_l);
+    const int64_t t = h->step + 1;         // alpha_t as seen by step t (TF multiplies the beta powers after each apply)
+    o.od = make_opt(h->od, alpha_at(h->rp_d, t)); o.ol = make_opt(h->ol, alpha_at(h->rp_l, t));
     return o;
 }
-static void commit_step(dfm_handle* h, const StepOpts& o, int64_t t) {
-    h->step = t;
-    h->b1p_d = o.b1p_d; h->b2p_d = o.b2p_d; h->b1p_l = o.b1p_l; h->b2p_l = o.b2p_l;
+static void commit_step(dfm_handle* h, const StepOpts&, int64_t t) { h->step = t; }
+
+// ---- fused small-tower step (fused_small.cuh)
+template <int K>
+static int launch_fused(dfm_handle* h, const BatchPtrs& bp, int B, const float* labels, float scale, float* logits_out,
+                        const float* rowbuf, int64_t upto, cudaStream_t st) {
+    FusedArgs a{};
+    a.ids = h->ids; a.B = B; a.dc = h->dc; a.dn = h->dn; a.n_slots = h->dcs;
+    a.row_off = h->d_row_off; a.tb = h->tb; a.bp = bp; a.dw = h->dw;
+    const DenseT* ne = find_dense(h, "num_emb"); const DenseT* nl = find_dense(h, "num_lin"); const DenseT* bs = find_dense(h, "bias");
+    a.off_num_emb = ne ? (int)ne->off : -1; a.off_num_lin = nl ? (int)nl->off : -1; a.off_bias = bs ? (int)bs->off : -1;
+    a.use_linear = h->use_linear; a.use_mf = h->use_mf;
+    a.m = h->sm;
+    const int train = labels ? 1 : 0;
+    if (train && h->dropout > 0.f) {
+        a.m.drop_keep = 1.f - h->dropout; a.m.drop_inv = 1.f / (1.f - h->dropout);
+        a.m.drop_seed = h->dropout_seed; a.m.drop_step = (uint64_t)(h->step + 1); a.m.drop_row0 = (int64_t)h->rank * h->max_batch;
+    }
+    a.labels = labels; a.scale = scale; a.train = train;
+    a.rr = make_rr(h, rowbuf ? -1 : upto);
+    a.od = make_opt(h->od, 0.f); a.ol = make_opt(h->ol, 0.f);
+    a.uidx = rowbuf ? h->uidx : nullptr; a.rowbuf = rowbuf; a.rowbuf_stride = K + 4;
+    a.logits = h->logits; a.logits_out = logits_out; a.dz_out = h->dz; a.dh1_out = h->dact[1]; a.s_out = h->s;
+    a.up_partial = h->up_partial; a.w0_partial = h->w0_partial; a.num_partial = h->num_partial; a.head_part = h->head_part;
+    a.D = h->sm.D; a.n_numacc = h->n_numacc;
+    a.es_stride = fs_es_stride(h->sm.D);
+    const int grid = std::min((B + FS_TS - 1) / FS_TS, h->fused_grid);
+    const int H1 = h->sm.H[0];
+    const int need_nc = ((h->dc + h->dn) + (256 / (H1 / 4)) / K - 1) / ((256 / (H1 / 4)) / K);     // ceil(d / fields per column group)
+    // NC (dW0 columns per thread) is a compile-time bound: exact instantiations for the shapes BASELINE.json names
+    // (Criteo k=16 [16,..]: 10, ML-100K k=16: 7, ML-100K k=4: 2), the generic bound otherwise
+#define FUSED_GO(HH, NCC)                                                                                              \
+    do {                                                                                                               \
+        if (rowbuf) fused_small_kernel<K, HH, true, NCC><<<grid, 256, h->fused_smem, st>>>(a);                         \
+        else fused_small_kernel<K, HH, false, NCC><<<grid, 256, h->fused_smem, st>>>(a);                               \
+    } while (0)
+    bool done = false;
+    if constexpr (K == 16) {
+        if (H1 == 16 && need_nc <= 7) { FUSED_GO(16, 7); done = true; }
+        else if (H1 == 16 && need_nc <= 10) { FUSED_GO(16, 10); done = true; }
+    }
+    if constexpr (K == 4) {
+        if (H1 == 16 && need_nc <= 2) { FUSED_GO(16, 2); done = true; }
+    }
+    if (!done) { if (H1 == 8) FUSED_GO(8, FS_NC); else if (H1 == 16) FUSED_GO(16, FS_NC); else FUSED_GO(32, FS_NC); }
+#undef FUSED_GO
+    h->launches++;
+    CK(cudaGetLastError());
+    return DFM_OK;
 }
 
 template <int K>
-static int catchup_touched(dfm_handle* h, SegWS& ws, int64_t n, int64_t t, cudaStream_t st) {
-    // non-lazy Adam: bring the touched rows up to step t-1
-    if (n > 0 && any_adam(h) && t > 1) {
-        const OptDev pod = make_opt(h->od, h->b1p_d, h->b2p_d), pol = make_opt(h->ol, h->b1p_l, h->b2p_l);
-        catchup_touched_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(h->tb, ws.urow, ws.seg_cnt, (int)(t - 1),
-                                                                             h->alpha_d, h->alpha_l, pod, pol, (bool)h->need_emb, (bool)h->use_linear);
-        h->launches++;
-    }
+static int fused_set_attr(dfm_handle* h) {
+    const int smem = (int)h->fused_smem;
+#define FUSED_ATTR(HH, NCC)                                                                                                            \
+    CK(cudaFuncSetAttribute(fused_small_kernel<K, HH, false, NCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                \
+    CK(cudaFuncSetAttribute(fused_small_kernel<K, HH, true, NCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FUSED_ATTR(8, FS_NC) FUSED_ATTR(16, FS_NC) FUSED_ATTR(32, FS_NC)
+    if constexpr (K == 16) { FUSED_ATTR(16, 7) FUSED_ATTR(16, 10) }
+    if constexpr (K == 4) { FUSED_ATTR(16, 2) }
+#undef FUSED_ATTR
     return DFM_OK;
+}
+
+// per-CTA partials of the fused kernel -> dense gradient buffer, loss, dz sum (one launch)
+static int launch_fused_reduce(dfm_handle* h, int B, float scale, float* loss_out, cudaStream_t st) {
+    const DenseT* ne = find_dense(h, "num_emb"); const DenseT* nl = find_dense(h, "num_lin"); const DenseT* bs = find_dense(h, "bias");
+    FusedReduceArgs r{};
+    r.up_partial = h->up_partial; r.w0_partial = h->w0_partial; r.num_partial = h->num_partial; r.head_part = h->head_part;
+    r.n_cta = std::min((B + FS_TS - 1) / FS_TS, h->fused_grid);
+    r.up_count = h->sm.up_count; r.up_begin = h->sm.up_begin; r.off_W0 = h->sm.off_W[0]; r.w0_count = h->sm.D * h->sm.H[0];
+    r.n_numacc = h->n_numacc;
+    r.dg = h->dg; r.num_scratch = h->num_scratch; r.done = h->fused_done;
+    r.dw = h->dw; r.off_num_emb = ne ? (int)ne->off : -1; r.off_num_lin = nl ? (int)nl->off : -1; r.off_bias = bs ? (int)bs->off : -1;
+    r.dc = h->dc; r.dn = h->dn; r.K = h->K; r.H1 = h->sm.H[0]; r.use_mf = h->use_mf;
+    r.loss_scale = scale; r.loss_out = h->d_loss; r.loss_copy = loss_out; r.dzsum_out = h->d_dzsum;
+    const int total = r.up_count + r.w0_count + r.n_numacc;
+    fused_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(r);
+    h->launches++;
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+template <int K, int H1>
+static GradSrcFused<K, H1> fused_src(const dfm_handle* h, const float* erow) {
+    GradSrcFused<K, H1> src{};
+    src.dh1 = h->dact[1]; src.s = h->use_mf ? h->s : nullptr; src.dz = h->dz; src.W0 = h->dw + h->sm.off_W[0];
+    src.n_slots = h->dcs; src.erow = erow; src.erow_stride = K + 4;
+    return src;
+}
+
+template <int K>
+static int fused_sparse_update(dfm_handle* h, SegWS& ws, int64_t n, const StepOpts& so, int64_t t, float* gsum, const float* erow,
+                               cudaStream_t st, Phase* ph, const PeerRoute* route = nullptr) {
+    if constexpr (K <= 32) {
+        switch (h->sm.H[0]) {
+            case 8: return sparse_update<K, GradSrcFused<K, 8>>(h, ws, n, fused_src<K, 8>(h, erow), so.od, so.ol, t, gsum, st, ph, route);
+            case 16: return sparse_update<K, GradSrcFused<K, 16>>(h, ws, n, fused_src<K, 16>(h, erow), so.od, so.ol, t, gsum, st, ph, route);
+            default: return sparse_update<K, GradSrcFused<K, 32>>(h, ws, n, fused_src<K, 32>(h, erow), so.od, so.ol, t, gsum, st, ph, route);
+        }
+    }
+    return DFM_ERR_UNSUPPORTED;
+}
+
+template <int K>
+static int train_fused(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out, float* logits_out, cudaStream_t st) {
+    if constexpr (K <= 32) {
+        const int64_t n = (int64_t)B * h->dcs;
+        const int64_t t = h->step + 1;
+        int rc = ensure_alpha(h, t);
+        if (rc) return rc;
+        const int64_t l0 = h->launches;
+        const StepOpts so = step_opts(h);
+        Phase ph(h, st);
+        const bool prefetched = h->prefetch_B == B && h->dc > 0 && h->prefetch_tag == bp.cat[0];
+        if (h->prefetch_B >= 0 && !prefetched) h->prefetch_B = -1;
+        if (prefetched) {
+            CK(cudaStreamWaitEvent(st, h->ev_prefetch, 0));
+            std::swap(h->ws, h->ws_next); std::swap(h->ids, h->ids_next);
+            h->prefetch_B = -1;
+        } else {
+            launch_transform<K>(h, bp, B, true, h->ids, st);                                    // K1
+        }
+        ph.next();
+        // The forward pass reads the table rows as stored and replays the deferred Adam decay in registers, so it does
+        // not need the list of touched rows: sort + segments (many small dependent launches) run on the side stream
+        // beside the fused kernel and are joined in front of the sparse optimizer.
+        const bool side = !prefetched && n > 0 && B >= 1024 && !h->profiling;
+        if (side) {
+            CK(cudaEventRecord(h->ev_fork, st));
+            CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+            if ((rc = build_segments(h, h->ws, n, (uint32_t)h->R, h->key_bits, h->side_stream, nullptr))) return rc;
+            CK(cudaEventRecord(h->ev_join, h->side_stream));
+            ph.next(); ph.next();
+        } else if (!prefetched) {
+            if ((rc = build_segments(h, h->ws, n, (uint32_t)h->R, h->key_bits, st, &ph))) return rc;
+        } else {
+            ph.next(); ph.next();
+        }
+        ph.next();                                                                               // (no catch-up pass)
+        const float scale = h->loss_red == DFM_LOSS_MEAN ? 1.0f / (float)B : 1.0f;
+        if ((rc = launch_fused<K>(h, bp, B, bp.labels, scale, logits_out, nullptr, t - 1, st))) return rc;
+        ph.next(); ph.next();                                                                    // gather + tower forward/backward top
+        if ((rc = launch_fused_reduce(h, B, scale, loss_out, st))) return rc;
+        ph.next(); ph.next();                                                                    // loss, dense gradients
+        if (side) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+        if ((rc = fused_sparse_update<K>(h, h->ws, n, so, t, nullptr, nullptr, st, &ph))) return rc;
+        if (h->n_dense) {
+            dense_apply_kernel<<<cdiv(h->n_dense, 256), 256, 0, st>>>(h->dw, h->ds1, h->ds2, h->dg, h->n_deep, h->n_dense, so.od, so.ol);
+            h->launches++;
+        }
+        ph.next();
+        CK(cudaGetLastError());
+        commit_step(h, so, t);
+        if (h->ev_done[t & 1]) CK(cudaEventRecord(h->ev_done[t & 1], st));
+        h->last_step_launches = h->launches - l0;
+        return DFM_OK;
+    }
+    return DFM_ERR_UNSUPPORTED;
 }
 
 template <int K>
 static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out, float* logits_out, cudaStream_t st) {
     if (h->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "row-sharded handle: drive the step with the dfm_shard_* entry points");
+    if (h->fused) return train_fused<K>(h, bp, B, loss_out, logits_out, st);
     const int dc = h->dc, d = dc + h->dn, dK = d * K;
     const int64_t n = (int64_t)B * (h->n_tiny ? h->n_big : h->dcs);      // lookups that go through the sort
     const int64_t t = h->step + 1;
@@ -1210,33 +1529,26 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
         launch_transform<K>(h, bp, B, true, h->ids, st);                                    // K1
     }
     ph.next();
-    const bool overlap = h->overlap_sort && B >= 4096 && n > 0;
+    // The gather replays the deferred non-lazy Adam decay of the rows it reads in registers (replay.cuh), so the forward
+    // pass never waits for the list of touched rows: with batches large enough to matter the sort / segment stage (small
+    // grids that leave most SMs idle) runs on the side stream beside the gather and the tower.
+    const bool overlap = h->overlap_sort && B >= 4096 && n > 0 && !prefetched;
     if (prefetched) {
         ph.next(); ph.next();
-        if (overlap) { if ((rc = flush_impl<K>(h, st))) return rc; }
-        else if ((rc = catchup_touched<K>(h, h->ws, n, t, st))) return rc;
     } else if (overlap) {
         CK(cudaEventRecord(h->ev_fork, st));
         CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
         if ((rc = build_segments(h, h->ws, n, (uint32_t)h->R, h->key_bits, h->side_stream, nullptr))) return rc;   // sort + segments, side stream
         CK(cudaEventRecord(h->ev_join, h->side_stream));
         ph.next(); ph.next();
-        if ((rc = flush_impl<K>(h, st))) return rc;          // all rows -> step t-1
     } else {
         if ((rc = build_segments(h, h->ws, n, (uint32_t)h->R, h->key_bits, st, &ph))) return rc;   // sort + segments
-        if ((rc = catchup_touched<K>(h, h->ws, n, t, st))) return rc;
-    }
-    if (!overlap && h->n_tiny && any_adam(h) && t > 1) {     // every row of the tiny columns, hit or not (that IS the non-lazy semantics)
-        const OptDev pod = make_opt(h->od, h->b1p_d, h->b2p_d), pol = make_opt(h->ol, h->b1p_l, h->b2p_l);
-        catchup_touched_kernel<K><<<cdiv((int64_t)h->n_tiny_rows * (K / 4), 256), 256, 0, st>>>(h->tb, h->d_trow_grow, h->d_tiny_cnt, (int)(t - 1), h->alpha_d,
-                                                                                              h->alpha_l, pod, pol, (bool)h->need_emb, (bool)h->use_linear);
-        h->launches++;
     }
     ph.next();
     const float scale = h->loss_red == DFM_LOSS_MEAN ? 1.0f / (float)B : 1.0f;
-    if ((rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, &ph))) return rc;
+    if ((rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, &ph, nullptr, t - 1))) return rc;
     if ((rc = tower_backward<K>(h, bp, B, scale, loss_out, st, &ph, B >= 4096 ? h->side_stream : nullptr))) return rc;
-    if (overlap && !prefetched) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    if (overlap) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
     const bool tiny_side = h->n_tiny && B >= 4096;      // the tiny-column reduction touches other rows than the sorted path: run both at once
     if (tiny_side) {
         CK(cudaEventRecord(h->ev_aux_fork, st));
@@ -1245,11 +1557,15 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
         CK(cudaEventRecord(h->ev_aux_join, h->side_stream));
     }
     if (h->has_bags) {
-        GradSrc<K, true> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0, h->dcs, h->d_slot_col, h->inv_cnt};
-        rc = sparse_update<K, true>(h, h->ws, n, src, so.od, so.ol, t, nullptr, st, &ph);
+        GradSrc<K, true> src{};
+        src.dE = h->need_emb ? h->dE : nullptr; src.dz = h->dz; src.dc = dc; src.dK = dK; src.flat = nullptr; src.flat_stride = 0;
+        src.n_slots = h->dcs; src.slot_field = h->d_slot_col; src.inv_cnt = h->inv_cnt;
+        rc = sparse_update<K, GradSrc<K, true>>(h, h->ws, n, src, so.od, so.ol, t, nullptr, st, &ph);
     } else {
-        GradSrc<K, false> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0, h->dcs, nullptr, nullptr};
-        rc = sparse_update<K, false>(h, h->ws, n, src, so.od, so.ol, t, nullptr, st, &ph);
+        GradSrc<K, false> src{};
+        src.dE = h->need_emb ? h->dE : nullptr; src.dz = h->dz; src.dc = dc; src.dK = dK; src.flat = nullptr; src.flat_stride = 0;
+        src.n_slots = h->dcs; src.slot_field = nullptr; src.inv_cnt = nullptr;
+        rc = sparse_update<K, GradSrc<K, false>>(h, h->ws, n, src, so.od, so.ol, t, nullptr, st, &ph);
     }
     if (rc) return rc;
     if (tiny_side) CK(cudaStreamWaitEvent(st, h->ev_aux_join, 0));
@@ -1264,6 +1580,15 @@ static int train_impl(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out
     if (h->ev_done[t & 1]) CK(cudaEventRecord(h->ev_done[t & 1], st));      // dfm_prefetch_batch orders buffer reuse on these
     h->last_step_launches = h->launches - l0;
     return DFM_OK;
+}
+
+// mode == EVAL / PREDICT: forward pass alone on the rows as of the latest step (replayed in registers, nothing written)
+template <int K>
+static int eval_forward(dfm_handle* h, const BatchPtrs& bp, int B, float* logits_out, const float* rowbuf, cudaStream_t st) {
+    if (h->fused) {
+        if constexpr (K <= 32) return launch_fused<K>(h, bp, B, nullptr, 1.f, logits_out, rowbuf, h->step, st);
+    }
+    return forward_impl<K>(h, bp, B, st, nullptr, 1.f, logits_out, nullptr, rowbuf, h->step);
 }
 
 #define DISPATCH_K(h, CALL)                                          \
@@ -1356,10 +1681,10 @@ extern "C" int dfm_forward(dfm_handle* h, const dfm_raw_batch* b, float* logits_
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     BatchPtrs bp = make_ptrs(h, b);
     bp.labels = nullptr;
-    DISPATCH_K(h, rc = flush_impl<KK>(h, st));
+    rc = ensure_alpha(h, h->step);
     if (rc) return rc;
     launch_transform<4>(h, bp, b->batch_size, false, h->ids, st);
-    DISPATCH_K(h, rc = forward_impl<KK>(h, bp, b->batch_size, st, nullptr, 1.f, logits_out, nullptr));
+    DISPATCH_K(h, rc = eval_forward<KK>(h, bp, b->batch_size, logits_out, nullptr, st));
     if (rc) return rc;
     CK(cudaGetLastError());
     return DFM_OK;
@@ -1397,10 +1722,7 @@ extern "C" int dfm_set_global_step(dfm_handle* h, int64_t step) {
     CK(cudaStreamSynchronize(h->stream));
     int rc = ensure_alpha(h, step + 1);
     if (rc) return rc;
-    float b1d = 1.f, b2d = 1.f, b1l = 1.f, b2l = 1.f;
-    for (int64_t i = 0; i < step; ++i) { b1d *= h->od.beta1; b2d *= h->od.beta2; b1l *= h->ol.beta1; b2l *= h->ol.beta2; }
-    h->b1p_d = b1d; h->b2p_d = b2d; h->b1p_l = b1l; h->b2p_l = b2l;
-    h->step = step; h->flushed_step = step;
+    h->step = step; h->flushed_step = step;      // alpha_t / beta powers are functions of the step (build_replay)
     if (h->R_loc) {
         fill_strided_kernel<<<cdiv((int64_t)h->R_loc, 256), 256, 0, h->stream>>>(h->tb.rec + h->tb.lin_off + 3, h->R_loc, 1, h->tb.stride,
                                                                                   __int_as_float_host((int)step));
@@ -1440,7 +1762,7 @@ static int shard_requests_impl(dfm_handle* h, const BatchPtrs& bp, int B, uint32
     if ((rc = build_segments(h, h->ws, n, limit, h->key_bits, st, nullptr))) return rc;
     CK(cudaMemsetAsync(h->d_counts, 0, ((size_t)W + 1) * 4, st));
     if (n > 0) {
-        shard_uniq_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->ws.skeys(), h->ws.svals(), n, limit, h->Rl, W, h->ws.flags, h->uidx, h->req_rows, h->d_counts);
+        shard_uniq_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->ws.skeys(), h->ws.svals(), n, limit, h->Rl, W, h->dcs, h->ws.pos_row, h->uidx, h->req_rows, h->d_counts);
         h->launches++;
     }
     if (!counts_host) {    // asynchronous variant: the counts stay on the device, dfm_shard_p2p_plan learns them from the matrix
@@ -1486,14 +1808,17 @@ static int shard_serve_impl(dfm_handle* h, const uint32_t* recv_rows, int64_t n_
         iota_kernel<<<cdiv(n_recv, 256), 256, 0, st>>>(h->ws_own.vals[0], n_recv);
         h->launches++;
     }
+    // the rows are served as of step t-1 (deferred Adam decay replayed in registers, nothing written); the sorted list
+    // of the received ids is what dfm_shard_apply reduces the gradient rows by
     int rc = build_segments(h, h->ws_own, n_recv, (uint32_t)h->R_loc, bits, st, nullptr);
     if (rc) return rc;
-    if ((rc = catchup_touched<K>(h, h->ws_own, n_recv, t, st))) return rc;
     if (n_recv > 0) {
+        const RowReplay rr = make_rr(h, t - 1);
+        const OptDev od = make_opt(h->od, 0.f), ol = make_opt(h->ol, 0.f);
         if (route) shard_serve_p2p_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(recv_rows, n_recv, h->tb, (bool)h->need_emb,
-                                                                                        (bool)h->use_linear, route);
+                                                                                        (bool)h->use_linear, route, rr, od, ol);
         else shard_serve_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(recv_rows, n_recv, h->tb, (bool)h->need_emb,
-                                                                              (bool)h->use_linear, reply, K + 4);
+                                                                              (bool)h->use_linear, reply, K + 4, rr, od, ol);
         h->launches++;
     }
     h->shard_n_recv = n_recv;
@@ -1520,17 +1845,29 @@ static int shard_fb_impl(dfm_handle* h, const BatchPtrs& bp, int B, const float*
     const int64_t l0 = h->launches;
     const StepOpts so = step_opts(h);
     const float scale = h->loss_red == DFM_LOSS_MEAN ? 1.0f / (float)global_batch : 1.0f;
-    int rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, nullptr, rowbuf);
-    if (rc) return rc;
-    if ((rc = tower_backward<K>(h, bp, B, scale, loss_out, st, nullptr))) return rc;
-    if (h->has_bags) {
-        GradSrc<K, true> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0, h->dcs, h->d_slot_col, h->inv_cnt};
-        rc = sparse_update<K, true>(h, h->ws, n, src, so.od, so.ol, t, gsum, st, nullptr, route);
+    int rc;
+    if (h->fused) {
+        if constexpr (K <= 32) {
+            if ((rc = launch_fused<K>(h, bp, B, bp.labels, scale, logits_out, rowbuf, -1, st))) return rc;
+            if ((rc = launch_fused_reduce(h, B, scale, loss_out, st))) return rc;
+            if ((rc = fused_sparse_update<K>(h, h->ws, n, so, t, gsum, rowbuf, st, nullptr, route))) return rc;
+        }
     } else {
-        GradSrc<K, false> src{h->need_emb ? h->dE : nullptr, h->dz, dc, dK, nullptr, 0, h->dcs, nullptr, nullptr};
-        rc = sparse_update<K, false>(h, h->ws, n, src, so.od, so.ol, t, gsum, st, nullptr, route);
+        if ((rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, nullptr, rowbuf))) return rc;
+        if ((rc = tower_backward<K>(h, bp, B, scale, loss_out, st, nullptr))) return rc;
+        if (h->has_bags) {
+            GradSrc<K, true> src{};
+            src.dE = h->need_emb ? h->dE : nullptr; src.dz = h->dz; src.dc = dc; src.dK = dK; src.flat = nullptr; src.flat_stride = 0;
+            src.n_slots = h->dcs; src.slot_field = h->d_slot_col; src.inv_cnt = h->inv_cnt;
+            rc = sparse_update<K, GradSrc<K, true>>(h, h->ws, n, src, so.od, so.ol, t, gsum, st, nullptr, route);
+        } else {
+            GradSrc<K, false> src{};
+            src.dE = h->need_emb ? h->dE : nullptr; src.dz = h->dz; src.dc = dc; src.dK = dK; src.flat = nullptr; src.flat_stride = 0;
+            src.n_slots = h->dcs; src.slot_field = nullptr; src.inv_cnt = nullptr;
+            rc = sparse_update<K, GradSrc<K, false>>(h, h->ws, n, src, so.od, so.ol, t, gsum, st, nullptr, route);
+        }
+        if (rc) return rc;
     }
-    if (rc) return rc;
     if (h->n_dense && dense_grad) CK(cudaMemcpyAsync(dense_grad, h->dg, (size_t)h->n_dense * 4, cudaMemcpyDeviceToDevice, st));
     h->last_step_launches += h->launches - l0;
     return DFM_OK;
@@ -1568,7 +1905,7 @@ extern "C" int dfm_shard_prefetch_requests(dfm_handle* h, const dfm_raw_batch* b
     CK(cudaSetDevice(h->device));
     if (!h->ws_next.cap) {       // first use: the second buffer set
         const int64_t n = (int64_t)h->max_batch * std::max(h->dcs, 1);
-        if (alloc_ws(h, h->ws_next, n, h->K) || dalloc(h, &h->ids_next, (size_t)n) || dalloc(h, &h->uidx_next, (size_t)n) ||
+        if (alloc_ws(h, h->ws_next, n, h->K, true) || dalloc(h, &h->ids_next, (size_t)n) || dalloc(h, &h->uidx_next, (size_t)n) ||
             dalloc(h, &h->req_rows_next, (size_t)n) || dalloc(h, &h->d_counts_next, (size_t)h->world + 1))
             return DFM_ERR_CUDA;
         CK(cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming));
@@ -1616,7 +1953,7 @@ extern "C" int dfm_shard_forward(dfm_handle* h, const dfm_raw_batch* b, const fl
     BatchPtrs bp = make_ptrs(h, b);
     bp.labels = nullptr;
     const int64_t l0 = h->launches;
-    DISPATCH_K(h, rc = forward_impl<KK>(h, bp, b->batch_size, st, nullptr, 1.f, logits_dev, nullptr, rowbuf_dev ? rowbuf_dev : h->p2p_rowbuf));
+    DISPATCH_K(h, rc = eval_forward<KK>(h, bp, b->batch_size, logits_dev, rowbuf_dev ? rowbuf_dev : h->p2p_rowbuf, st));
     h->last_step_launches += h->launches - l0;
     if (rc) return rc;
     CK(cudaGetLastError());
@@ -1628,8 +1965,10 @@ static int shard_apply_impl(dfm_handle* h, const float* grecv, const float* dens
     const int64_t t = h->step + 1;
     const int64_t l0 = h->launches;
     const StepOpts so = step_opts(h);
-    GradSrc<K, false> src{nullptr, nullptr, 1, 0, grecv, K + 4, 1, nullptr, nullptr};
-    int rc = sparse_update<K, false>(h, h->ws_own, h->shard_n_recv, src, so.od, so.ol, t, nullptr, st, nullptr);
+    GradSrc<K, false> src{};
+    src.dE = nullptr; src.dz = nullptr; src.dc = 1; src.dK = 0; src.flat = grecv; src.flat_stride = K + 4; src.n_slots = 1;
+    src.slot_field = nullptr; src.inv_cnt = nullptr;
+    int rc = sparse_update<K, GradSrc<K, false>>(h, h->ws_own, h->shard_n_recv, src, so.od, so.ol, t, nullptr, st, nullptr);
     if (rc) return rc;
     if (h->n_dense) {
         dense_apply_kernel<<<cdiv(h->n_dense, 256), 256, 0, st>>>(h->dw, h->ds1, h->ds2, dense_grad ? dense_grad : h->dg, h->n_deep, h->n_dense, so.od, so.ol);
@@ -1940,10 +2279,10 @@ extern "C" int dfm_forward_host(dfm_handle* h, const dfm_raw_batch* b, float* lo
     if (rc) return rc;
     CK(cudaEventRecord(sg.copied, h->copy_stream));
     CK(cudaStreamWaitEvent(h->stream, sg.copied, 0));
-    DISPATCH_K(h, rc = flush_impl<KK>(h, h->stream));
+    rc = ensure_alpha(h, h->step);
     if (rc) return rc;
     launch_transform<4>(h, bp, b->batch_size, false, h->ids, h->stream);
-    DISPATCH_K(h, rc = forward_impl<KK>(h, bp, b->batch_size, h->stream, nullptr, 1.f, nullptr, nullptr));
+    DISPATCH_K(h, rc = eval_forward<KK>(h, bp, b->batch_size, nullptr, nullptr, h->stream));
     if (rc) return rc;
     CK(cudaMemcpyAsync(logits_out, h->logits, (size_t)b->batch_size * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1971,11 +2310,73 @@ extern "C" int dfm_test_sort_pairs(uint32_t* keys_dev, uint32_t* vals_dev, int64
     return DFM_OK;
 }
 
+// algo 0: multi-launch LSD sort; 1: one-sweep; 2: one-sweep with the element count in device memory (grids sized for
+// a larger bound, as on the row-sharded owner side)
+extern "C" int dfm_test_sort_pairs_algo(uint32_t* keys_dev, uint32_t* vals_dev, int64_t n, int32_t key_bits, int32_t algo) {
+    dfm_handle* h = nullptr;
+    if (n <= 0) return DFM_OK;
+    if (algo == 0) return dfm_test_sort_pairs(keys_dev, vals_dev, n, key_bits);
+    const int64_t n_max = algo == 2 ? n + 100000 : n;
+    uint32_t *k[2] = {keys_dev, nullptr}, *v[2] = {vals_dev, nullptr};
+    void* temp = nullptr; uint32_t* n_dev = nullptr;
+    CK(cudaMalloc(&k[1], n * 4));
+    CK(cudaMalloc(&v[1], n * 4));
+    CK(cudaMalloc(&temp, prims::onesweep_temp_bytes(n_max)));
+    if (algo == 2) {
+        const uint32_t nn = (uint32_t)n;
+        CK(cudaMalloc(&n_dev, 4));
+        CK(cudaMemcpy(n_dev, &nn, 4, cudaMemcpyHostToDevice));
+    }
+    int cur = prims::onesweep_sort_pairs(k, v, n_max, n_dev, key_bits, temp, 0, nullptr);
+    if (cur == 1) {
+        CK(cudaMemcpyAsync(keys_dev, k[1], n * 4, cudaMemcpyDeviceToDevice, 0));
+        CK(cudaMemcpyAsync(vals_dev, v[1], n * 4, cudaMemcpyDeviceToDevice, 0));
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(k[1]); cudaFree(v[1]); cudaFree(temp); if (n_dev) cudaFree(n_dev);
+    CK(e);
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
 extern "C" int dfm_test_fingerprint64(const uint8_t* bytes_dev, const int32_t* offsets_dev, int64_t n, uint64_t* out_dev) {
     dfm_handle* h = nullptr;
     if (n <= 0) return DFM_OK;
     fingerprint_kernel<<<cdiv(n, 256), 256>>>(bytes_dev, offsets_dev, n, out_dev);
     CK(cudaDeviceSynchronize());
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+// test hook: non-lazy Adam replay of n independent elements (device arrays) from step last[i] to step upto
+__global__ void test_replay_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, const int32_t* __restrict__ last,
+                                   int64_t n, RowReplay rr, OptDev od) {
+    const ReplayStep rs = replay_step_load(rr.rd, rr.upto);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 w4 = make_float4(w[i], 0.f, 0.f, 0.f), m4 = make_float4(m[i], 0.f, 0.f, 0.f), v4 = make_float4(v[i], 0.f, 0.f, 0.f);
+    float4 lr = make_float4(0.f, 0.f, 0.f, __int_as_float(last[i]));
+    replay_row(w4, m4, v4, lr, false, rr, rs, od, od);
+    w[i] = w4.x; m[i] = m4.x; v[i] = v4.x;
+}
+
+extern "C" int dfm_test_replay(const dfm_optimizer* opt, float* w_dev, float* m_dev, float* v_dev, const int32_t* last_dev, int64_t n,
+                               int32_t upto, int32_t force_loop) {
+    dfm_handle* h = nullptr;
+    if (!opt || n < 0 || upto < 0) return DFM_ERR_INVALID_ARG;
+    if (n == 0) return DFM_OK;
+    dfm_handle tmp;                          // only the stream (0) and the error string are used
+    ReplayHost r;
+    if (force_loop) setenv("DFM_REPLAY_LOOP", "1", 1);
+    int rc = build_replay_group(&tmp, r, *opt, (int64_t)upto + 2);
+    if (force_loop) unsetenv("DFM_REPLAY_LOOP");
+    if (rc) { g_create_error = tmp.err; free_replay(r); return rc; }
+    RowReplay rr{};
+    rr.rd = r.tab; rr.rl = r.tab; rr.upto = upto; rr.emb_adam = 1; rr.lin_adam = 0; rr.same = 1;
+    test_replay_kernel<<<cdiv(n, 256), 256>>>(w_dev, m_dev, v_dev, last_dev, n, rr, make_opt(*opt, 0.f));
+    cudaError_t e = cudaDeviceSynchronize();
+    free_replay(r);
+    CK(e);
     CK(cudaGetLastError());
     return DFM_OK;
 }
@@ -2027,6 +2428,7 @@ static int tc_gemm_mnmajor(dfm_handle* h, const float* A, int lda, const float* 
     CUtensorMap ma, mb;
     bool ok = tc::make_map_3d(&ma, A, K, M, lda, TC_BK, tc::BM / 32) && tc::make_map_3d(&mb, B, K, N, ldb, TC_BK, BN / 32);
     if (!ok) FAIL(DFM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    splits = tc_wgrad_splits(K, splits);
     int kps = ((K + splits - 1) / splits + TC_BK - 1) / TC_BK * TC_BK;
     int nz = (K + kps - 1) / kps;
     if (k_per_split_out) *k_per_split_out = nz;
@@ -2135,8 +2537,9 @@ extern "C" int dfm_test_tc_gemm(int32_t mode, const float* A, const float* B, fl
     } else {
         float* part = nullptr;
         int nz = 0;
-        CK(cudaMalloc(&part, (size_t)std::max(splits, 1) * M * N * 4 + 16));
-        rc = tc_gemm_mnmajor(nullptr, A, M, B, N, part, M, N, K, std::max(splits, 1), &nz, 0);
+        const int eff = tc_wgrad_splits(K, std::max(splits, 1));
+        CK(cudaMalloc(&part, (size_t)eff * M * N * 4 + 16));
+        rc = tc_gemm_mnmajor(nullptr, A, M, B, N, part, M, N, K, eff, &nz, 0);
         if (rc == DFM_OK) reduce_partials_kernel<<<cdiv((int64_t)M * N, 256), 256>>>(part, nz, (size_t)M * N, (int64_t)M * N, C);
         CK(cudaDeviceSynchronize());
         cudaFree(part);

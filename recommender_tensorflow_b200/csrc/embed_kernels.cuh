@@ -3,8 +3,16 @@
 #pragma once
 #include "dfm_types.cuh"
 #include "farmhash.cuh"
+#include "replay.cuh"
 
 __device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+// payload of a (row, lookup) sort pair: sample index and value slot of the lookup, packed so that neither a division
+// nor the slot count is needed to take it apart (at most 256 value slots per sample, 2^24 samples per batch)
+constexpr int PAYLOAD_SLOT_BITS = 8;
+__host__ __device__ __forceinline__ uint32_t payload_pack(uint32_t b, uint32_t slot) { return (b << PAYLOAD_SLOT_BITS) | slot; }
+__host__ __device__ __forceinline__ uint32_t payload_sample(uint32_t v) { return v >> PAYLOAD_SLOT_BITS; }
+__host__ __device__ __forceinline__ uint32_t payload_slot(uint32_t v) { return v & ((1u << PAYLOAD_SLOT_BITS) - 1u); }
 
 // =============================================================================================
 // optimizer arithmetic, in the float32 op order of the TF-1.12 kernels
@@ -129,6 +137,59 @@ __device__ __forceinline__ void adam_replay1(float& w, float& m, float& v, int l
     w = w4.x; m = m4.x; v = v4.x;
 }
 
+// Both optimizer groups of one step as the row kernels see them.  Every kernel that reads a table row (gather, serve)
+// or rewrites it (row_update, tiny_update, flush) replays the non-lazy Adam decay of that row IN REGISTERS from the
+// stored state (replay.cuh); only the kernels that rewrite the row anyway store the result.  There is no separate
+// catch-up pass over the touched rows any more.
+struct RowReplay {
+    ReplayTab rd, rl;     // embedding / linear group
+    int upto;             // rows are brought to this step; < 0: nothing to replay
+    int emb_adam, lin_adam;
+    int same;             // both groups share hyper-parameters: one coefficient set serves both
+};
+
+// w, m, v: this lane's float4 slice of the embedding row and its Adam slots; lr = {lin w, lin m, lin v, last_step}.
+// lin_lane: this lane also owns the linear weight.  Afterwards lr.w = upto (callers that store the row store it).
+__device__ __forceinline__ void replay_row(float4& w, float4& m, float4& v, float4& lr, bool lin_lane, const RowReplay& rr,
+                                           const ReplayStep& rs, const OptDev& od, const OptDev& ol) {
+    const int last = __float_as_int(lr.w);
+    if (rr.upto < 0 || last >= rr.upto) return;
+    bool lin_done = !(rr.lin_adam && lin_lane);
+    if (rr.emb_adam) {
+        if (rr.rd.closed) {
+            const ReplayCoef c = replay_coef(rr.rd, rs, last);
+            replay_elem(w.x, m.x, v.x, c, od.eps); replay_elem(w.y, m.y, v.y, c, od.eps);
+            replay_elem(w.z, m.z, v.z, c, od.eps); replay_elem(w.w, m.w, v.w, c, od.eps);
+            if (!lin_done && rr.same) { replay_elem(lr.x, lr.y, lr.z, c, ol.eps); lin_done = true; }
+        } else {
+            adam_replay4(w, m, v, last, rr.upto, rr.rd.alpha, od);
+        }
+    }
+    if (!lin_done) {
+        if (rr.rl.closed) {
+            const ReplayStep sl = (rr.same && rr.rd.closed) ? rs : replay_step_load(rr.rl, rr.upto);
+            const ReplayCoef c = replay_coef(rr.rl, sl, last);
+            replay_elem(lr.x, lr.y, lr.z, c, ol.eps);
+        } else {
+            adam_replay1(lr.x, lr.y, lr.z, last, rr.upto, rr.rl.alpha, ol);
+        }
+    }
+    lr.w = __int_as_float(rr.upto);
+}
+
+// this lane's slice of an embedding row + the linear weight, as of step rr.upto (read-only: nothing is written back)
+__device__ __forceinline__ void load_row_current(const Table& tb, size_t row, int sub, bool has_emb, const RowReplay& rr,
+                                                 const ReplayStep& rs, const OptDev& od, const OptDev& ol, float4& w, float& lw) {
+    float4 lr = __ldg(tab_lin(tb, row));
+    w = has_emb ? __ldg(tab_w(tb, row) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rr.upto >= 0 && __float_as_int(lr.w) < rr.upto) {
+        float4 m = w, v = w;
+        if (rr.emb_adam) { m = __ldg(tab_s1(tb, row) + sub); v = __ldg(tab_s2(tb, row) + sub); }
+        replay_row(w, m, v, lr, sub == 0, rr, rs, od, ol);
+    }
+    lw = lr.x;
+}
+
 // =============================================================================================
 // K1: feature-column transforms -> ids [B, dc] + sort keys (global row index) + payload
 // =============================================================================================
@@ -189,7 +250,7 @@ __device__ __forceinline__ int32_t transform_one(const BatchPtrs& bp, const ColD
 // column `width`).  Phase 1: work item w -> (slot w / TILE, sample w % TILE), so a warp reads 32 consecutive
 // samples of ONE column (coalesced for single-valued columns, uniform column kind) and the columns of a sample are
 // transformed in parallel by different warps (a hashed string column costs ~100x an identity column).
-// Phase 2 writes ids / keys / payload sample-major: ids [B, n_slots], payload = b * n_slots + slot.
+// Phase 2 writes ids / keys / payload sample-major: ids [B, n_slots], payload = payload_pack(b, slot).
 template <int TILE>
 __global__ void __launch_bounds__(256) transform_kernel(BatchPtrs bp, const ColDev* __restrict__ cols,
                                                         const float* __restrict__ bounds,
@@ -229,7 +290,7 @@ __global__ void __launch_bounds__(256) transform_kernel(BatchPtrs bp, const ColD
             }
             if (at >= 0) {
                 keys[at] = id >= 0 ? row_off[slot_col ? slot_col[slot] : slot] + (uint32_t)id : R;
-                vals[at] = (uint32_t)(g0 + w);
+                vals[at] = payload_pack((uint32_t)(b0 + w / n_slots), (uint32_t)slot);
             }
         }
     }
@@ -298,122 +359,154 @@ __global__ void seg_fill_kernel(const uint32_t* __restrict__ keys, const uint32_
     }
 }
 
+// Single-pass segment builder: flags + scan + fill of the three kernels above in ONE launch.  Tiles are handed out by
+// an atomic ticket; a tile publishes its (rows, pieces) count and obtains the counts of all earlier tiles by decoupled
+// look-back along 64-bit status words {prefix flag, aggregate flag, rows:31, pieces:31}.  The element count may live in
+// device memory (n_dev), so the row-sharded owner can segment what its peers pushed without a host round trip.
+constexpr int SB_ITEMS = 8, SB_TILE = 256 * SB_ITEMS;
+constexpr unsigned long long SB_PREFIX = 1ull << 63, SB_AGG = 1ull << 62;
+__global__ void __launch_bounds__(256) seg_build_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n_host,
+                                                        const uint32_t* __restrict__ n_dev, uint32_t R, unsigned long long* status,
+                                                        uint32_t* __restrict__ ticket, SegCounts* __restrict__ cnt,
+                                                        uint32_t* __restrict__ row_start, uint32_t* __restrict__ row_piece0,
+                                                        uint32_t* __restrict__ piece_start, uint32_t* __restrict__ urow, uint32_t* __restrict__ uval,
+                                                        uint32_t* __restrict__ pos_row /* optional: unique-row index of every sorted position */) {
+    __shared__ unsigned long long wtot[33];
+    __shared__ unsigned long long s_excl;
+    __shared__ uint32_t s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t n = n_dev ? (int64_t)*reinterpret_cast<const volatile uint32_t*>(n_dev) : n_host;
+    if (tile * SB_TILE >= n) {
+        if (tile == 0 && tid == 0) {      // empty list
+            cnt->n_rows = 0; cnt->n_pieces = 0; cnt->n_valid = 0; cnt->n_hot = 0;
+            row_start[0] = 0; row_piece0[0] = 0; piece_start[0] = 0;
+        }
+        return;
+    }
+    const int64_t i0 = tile * SB_TILE + (int64_t)tid * SB_ITEMS;
+    uint32_t k[SB_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j) k[j] = (i0 + j < n) ? keys[i0 + j] : 0xffffffffu;
+    uint32_t prev = (i0 > 0 && i0 < n) ? keys[i0 - 1] : 0xffffffffu;
+    uint32_t rows = 0, pieces = 0, rmask = 0, pmask = 0, vmask = 0;
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j) {
+        const int64_t i = i0 + j;
+        const bool valid = i < n && k[j] < R;
+        const bool rh = valid && (i == 0 || k[j] != prev);
+        const bool ph = valid && (rh || (i % PIECE_C) == 0);
+        rows += rh; pieces += ph;
+        rmask |= (uint32_t)rh << j; pmask |= (uint32_t)ph << j; vmask |= (uint32_t)valid << j;
+        prev = k[j];
+    }
+    // block exclusive scan of the packed (rows << 32 | pieces) counts
+    const unsigned long long mine = ((unsigned long long)rows << 32) | pieces;
+    unsigned long long inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long w = lane < 8 ? wtot[lane] : 0ull;
+        unsigned long long winc = w;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < 8) wtot[lane] = winc - w;
+        if (lane == 7) wtot[32] = winc;
+    }
+    __syncthreads();
+    const unsigned long long tile_tot = wtot[32];
+    if (tid == 0) {
+        volatile unsigned long long* st = status;
+        auto enc = [](unsigned long long v) { return ((v >> 32) << 31) | (v & 0x7fffffffull); };
+        auto dec = [](unsigned long long e) { return (((e >> 31) & 0x7fffffffull) << 32) | (e & 0x7fffffffull); };
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            st[0] = SB_PREFIX | enc(tile_tot);
+        } else {
+            st[tile] = SB_AGG | enc(tile_tot);
+            for (int64_t tt = tile - 1; tt >= 0; --tt) {
+                unsigned long long e;
+                do { e = st[tt]; } while ((e & (SB_PREFIX | SB_AGG)) == 0ull);
+                excl += dec(e);
+                if (e & SB_PREFIX) break;
+            }
+            st[tile] = SB_PREFIX | enc(excl + tile_tot);
+        }
+        s_excl = excl;
+    }
+    __syncthreads();
+    unsigned long long run = s_excl + wtot[warp] + (inc - mine);
+    uint32_t ridx = (uint32_t)(run >> 32), pidx = (uint32_t)(run & 0xffffffffu);
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j) {
+        if ((pmask >> j) & 1u) {
+            const uint32_t i = (uint32_t)(i0 + j);
+            piece_start[pidx] = i;
+            if ((rmask >> j) & 1u) {
+                row_start[ridx] = i;
+                row_piece0[ridx] = pidx;
+                urow[ridx] = k[j];
+                uval[ridx] = vals[i];
+                ++ridx;
+            }
+            ++pidx;
+        }
+        if (pos_row && ((vmask >> j) & 1u)) pos_row[i0 + j] = ridx - 1;
+    }
+    // the last tile closes the lists: totals, number of valid (non-empty-bag) lookups, sentinels
+    if ((tile + 1) * SB_TILE >= n && tid == 0) {
+        const unsigned long long tot = s_excl + tile_tot;
+        const uint32_t Ur = (uint32_t)(tot >> 32), P = (uint32_t)(tot & 0xffffffffu);
+        int64_t lo = 0, hi = n;                        // keys are sorted, the invalid ones (>= R) last
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (keys[mid] < R) lo = mid + 1; else hi = mid;
+        }
+        const uint32_t nv = (uint32_t)lo;
+        cnt->n_rows = Ur; cnt->n_pieces = P; cnt->n_valid = nv; cnt->n_hot = 0;
+        row_start[Ur] = nv; row_piece0[Ur] = P; piece_start[P] = nv;
+    }
+}
+
 // =============================================================================================
-// non-lazy Adam catch-up (exact deferred update) of the rows this batch touches, and full flush
+// non-lazy Adam: materialise the deferred decay of EVERY row (dfm_flush: before a checkpoint / dfm_get_tensor)
 // =============================================================================================
 // table layout: see Table (dfm_types.cuh).  The two optimizers share the step index, so the one last_step
 // in the linear float4 serves both the embedding row and the linear weight.
 template <int K>
-__device__ __forceinline__ void catchup_group(const Table& tb, size_t row,
-                                              bool act, int sub, int upto, const float* __restrict__ alpha_d,
-                                              const float* __restrict__ alpha_l, const OptDev& od, const OptDev& ol,
-                                              bool has_emb, bool has_lin) {
-    constexpr int LPR = K / 4;
-    float4 lr = make_float4(0.f, 0.f, 0.f, 0.f);
-    int last = upto;
-    if (act) {
-        lr = *tab_lin(tb, row);
-        last = __float_as_int(lr.w);
-    }
-    const bool work = act && last < upto;
-    if (work && has_emb && od.kind == DFM_OPT_ADAM) {
-        float4 *pw = tab_w(tb, row) + sub, *pm = tab_s1(tb, row) + sub, *pv = tab_s2(tb, row) + sub;
-        float4 m = *pm, v = *pv;
-        // rows that were never touched (m = v = 0) do not move under non-lazy Adam: nothing to read or write
-        const bool idle = m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f && v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f;
-        if (!idle) {
-            float4 w = *pw;
-            adam_replay4(w, m, v, last, upto, alpha_d, od);
-            *pw = w; *pm = m; *pv = v;
-        }
-    }
-    __syncwarp();  // every lane of the group has read last_step before lane 0 rewrites it
-    if (work && sub == 0) {
-        // NOTE: last_step is always advanced, also for idle rows, so that a later replay never starts before
-        // the step at which the row first receives a gradient.
-        if (has_lin && ol.kind == DFM_OPT_ADAM) adam_replay1(lr.x, lr.y, lr.z, last, upto, alpha_l, ol);
-        lr.w = __int_as_float(upto);
-        *tab_lin(tb, row) = lr;
-    }
-}
-
-// rows touched by the current batch (unique list from the sort stage): bring them to step `upto`.
-// Each lane group handles RPG rows per trip; the last_step record and the m, v slots of a row are requested
-// together (both depend only on the compact row id), so one dependent-load level covers the whole row.
-template <int K>
-__global__ void __launch_bounds__(256) catchup_touched_kernel(Table tb,
-                                                              const uint32_t* __restrict__ urow,
-                                                              const SegCounts* __restrict__ cnt, int upto,
-                                                              const float* __restrict__ alpha_d,
-                                                              const float* __restrict__ alpha_l, OptDev od, OptDev ol,
-                                                              bool has_emb, bool has_lin) {
-    constexpr int LPR = K / 4;
-    constexpr int RPG = 2;
-    const int sub = threadIdx.x % LPR;
-    const uint32_t U = cnt->n_rows;
-    const uint32_t gpb = blockDim.x / LPR;
-    const uint32_t stride = gridDim.x * gpb;
-    const bool emb_adam = has_emb && od.kind == DFM_OPT_ADAM;
-    for (uint32_t base = blockIdx.x * gpb; base < U; base += stride * RPG) {  // block-uniform trip count
-        bool act[RPG], work[RPG], idle[RPG];
-        size_t row[RPG];
-        float4 lr[RPG], m[RPG], v[RPG];
-        int last[RPG];
-#pragma unroll
-        for (int j = 0; j < RPG; ++j) {
-            uint32_t u = base + j * stride + threadIdx.x / LPR;
-            act[j] = u < U;
-            row[j] = act[j] ? (size_t)__ldg(urow + u) : 0;
-        }
-#pragma unroll
-        for (int j = 0; j < RPG; ++j) {
-            lr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            m[j] = lr[j]; v[j] = lr[j];
-            if (act[j]) {
-                lr[j] = *tab_lin(tb, row[j]);
-                if (emb_adam) { m[j] = tab_s1(tb, row[j])[sub]; v[j] = tab_s2(tb, row[j])[sub]; }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < RPG; ++j) {
-            last[j] = act[j] ? __float_as_int(lr[j].w) : upto;
-            work[j] = act[j] && last[j] < upto;
-            // rows that were never touched (m = v = 0) do not move under non-lazy Adam: nothing more to read or write
-            idle[j] = m[j].x == 0.f && m[j].y == 0.f && m[j].z == 0.f && m[j].w == 0.f && v[j].x == 0.f && v[j].y == 0.f &&
-                      v[j].z == 0.f && v[j].w == 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < RPG; ++j) {
-            if (work[j] && emb_adam && !idle[j]) {
-                float4 w = tab_w(tb, row[j])[sub];
-                adam_replay4(w, m[j], v[j], last[j], upto, alpha_d, od);
-                tab_w(tb, row[j])[sub] = w; tab_s1(tb, row[j])[sub] = m[j]; tab_s2(tb, row[j])[sub] = v[j];
-            }
-        }
-        __syncwarp();  // every lane of a group has read last_step before lane 0 rewrites it
-#pragma unroll
-        for (int j = 0; j < RPG; ++j) {
-            if (work[j] && sub == 0) {
-                if (has_lin && ol.kind == DFM_OPT_ADAM) adam_replay1(lr[j].x, lr[j].y, lr[j].z, last[j], upto, alpha_l, ol);
-                lr[j].w = __int_as_float(upto);
-                *tab_lin(tb, row[j]) = lr[j];
-            }
-        }
-    }
-}
-
-// every row of the tables (dfm_flush)
-template <int K>
-__global__ void __launch_bounds__(256) catchup_all_kernel(Table tb,
-                                                          uint64_t R, int upto, const float* __restrict__ alpha_d,
-                                                          const float* __restrict__ alpha_l, OptDev od, OptDev ol,
-                                                          bool has_emb, bool has_lin) {
+__global__ void __launch_bounds__(256) catchup_all_kernel(Table tb, uint64_t R, RowReplay rr, OptDev od, OptDev ol, bool has_emb) {
     constexpr int LPR = K / 4;
     const int sub = threadIdx.x % LPR;
     const uint64_t gpb = blockDim.x / LPR;
-    for (uint64_t base = (uint64_t)blockIdx.x * gpb; base < R; base += (uint64_t)gridDim.x * gpb) {
-        uint64_t row = base + threadIdx.x / LPR;
-        catchup_group<K>(tb, (size_t)row, row < R, sub, upto, alpha_d, alpha_l, od, ol, has_emb, has_lin);
+    const ReplayStep rs = replay_step_load(rr.rd.closed ? rr.rd : rr.rl, rr.upto);
+    for (uint64_t base = (uint64_t)blockIdx.x * gpb; base < R; base += (uint64_t)gridDim.x * gpb) {   // block-uniform trip count
+        const uint64_t row = base + threadIdx.x / LPR;
+        float4 lr = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool work = false;
+        if (row < R) { lr = *tab_lin(tb, row); work = __float_as_int(lr.w) < rr.upto; }
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f), m = w, v = w;
+        bool idle = true;
+        if (work && has_emb && rr.emb_adam) {
+            m = tab_s1(tb, row)[sub]; v = tab_s2(tb, row)[sub];
+            // slices that were never touched (m = v = 0) do not move under non-lazy Adam: nothing more to read or write
+            idle = m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f && v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f;
+            if (!idle) w = tab_w(tb, row)[sub];
+        }
+        if (work) replay_row(w, m, v, lr, sub == 0, rr, rs, od, ol);
+        if (work && !idle) { tab_w(tb, row)[sub] = w; tab_s1(tb, row)[sub] = m; tab_s2(tb, row)[sub] = v; }
+        __syncwarp();  // every lane of a group has read last_step before lane 0 rewrites it
+        // last_step is always advanced, also for idle rows
+        if (work && sub == 0) *tab_lin(tb, row) = lr;
     }
 }
 
@@ -436,7 +529,8 @@ __global__ void __launch_bounds__(256) gather_fm_kernel(const int32_t* __restric
                                                         const float* __restrict__ bias, int use_linear, int use_mf,
                                                         int need_emb, float* __restrict__ h0, float* __restrict__ s_out,
                                                         float* __restrict__ zacc, const uint32_t* __restrict__ uidx,
-                                                        const float* __restrict__ rowbuf, int rowbuf_stride) {
+                                                        const float* __restrict__ rowbuf, int rowbuf_stride,
+                                                        RowReplay rr, OptDev od, OptDev ol) {
     constexpr int LPR = K / 4;       // lanes per row
     constexpr int FPR = 32 / LPR;    // fields per warp round
     const int lane = threadIdx.x & 31;
@@ -444,6 +538,7 @@ __global__ void __launch_bounds__(256) gather_fm_kernel(const int32_t* __restric
     const int warps_per_block = blockDim.x >> 5;
     const int d = dc + dn;
     const float b0 = (use_linear && bias) ? bias[0] : 0.f;
+    const ReplayStep rs = replay_step_load(rr.rd.closed ? rr.rd : rr.rl, rr.upto);
     for (int b = blockIdx.x * warps_per_block + (threadIdx.x >> 5); b < B; b += gridDim.x * warps_per_block) {
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
         float lin = 0.f;
@@ -465,9 +560,13 @@ __global__ void __launch_bounds__(256) gather_fm_kernel(const int32_t* __restric
                             if (need_emb) add4(e, __ldg(reinterpret_cast<const float4*>(rp) + sub));
                             if (use_linear && sub == 0) lsum += __ldg(rp + K);
                         } else {
+                            // the row as of the previous step: the deferred non-lazy Adam decay is replayed in registers
+                            // (nothing is written back here; the optimizer kernel replays again when it rewrites the row)
                             size_t row = (size_t)row_off[f] + (uint32_t)id;
-                            if (need_emb) add4(e, __ldg(tab_w(tb, row) + sub));
-                            if (use_linear && sub == 0) lsum += __ldg(reinterpret_cast<const float*>(tab_lin(tb, row)));
+                            float4 w; float lw;
+                            load_row_current(tb, row, sub, need_emb != 0, rr, rs, od, ol, w, lw);
+                            if (need_emb) add4(e, w);
+                            if (use_linear && sub == 0) lsum += lw;
                         }
                     }
                 }
@@ -527,12 +626,15 @@ __global__ void __launch_bounds__(256) gather_fm_kernel(const int32_t* __restric
 // backward GEMM epilogue or by de_fm_kernel) and dz[b] for the linear weight.
 template <int K, bool BAGS>
 struct GradSrc {
+    static constexpr bool SUB_E = false;
+    __device__ __forceinline__ bool sub_e() const { return false; }
+    const float* erow = nullptr; int erow_stride = 0;     // (unused here; see GradSrcFused)
     const float* dE;    // [B, d*K] or nullptr
     const float* dz;    // [B]
     int dc, dK;         // dK = d*K
     const float* flat;  // sharded owner side: gradient rows [n][flat_stride] = {g[K], g_lin, pad}, payload = row of `flat`
     int flat_stride;
-    int n_slots;                // lookups per sample (payload = b * n_slots + slot)
+    int n_slots;                // lookups per sample
     const int32_t* slot_field;  // BAGS: slot -> field
     const float* inv_cnt;       // BAGS: [B, dc] 1 / (present slots) of every field
     __device__ __forceinline__ void fetch(uint32_t val, int sub, bool want_lin, float4& g, float& gl) const {
@@ -542,7 +644,7 @@ struct GradSrc {
             gl = want_lin ? __ldg(rp + K) : 0.f;
             return;
         }
-        uint32_t b = val / (uint32_t)n_slots, f = val - b * (uint32_t)n_slots;
+        uint32_t b = payload_sample(val), f = payload_slot(val);
         if (BAGS) f = (uint32_t)__ldg(slot_field + f);
         g = dE ? __ldg(reinterpret_cast<const float4*>(dE + (size_t)b * dK + (size_t)f * K) + sub)
                : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -569,11 +671,11 @@ __global__ void __launch_bounds__(256) hot_pieces_kernel(const uint32_t* __restr
 // level 1: one warp per piece of a hot row.  The 128/K lane groups stride over the piece's entries
 // (4 independent loads in flight per group), then a fixed butterfly combines them -> the summation
 // order is a function of the sorted order only.
-template <int K, bool BAGS>
+template <int K, typename SRC>
 __global__ void __launch_bounds__(256) piece_reduce_kernel(const uint32_t* __restrict__ svals,
                                                            const uint32_t* __restrict__ piece_start,
                                                            const uint32_t* __restrict__ hot_list,
-                                                           const SegCounts* __restrict__ cnt, GradSrc<K, BAGS> src,
+                                                           const SegCounts* __restrict__ cnt, SRC src,
                                                            float* __restrict__ piece_sum /*[slots][K+4]*/) {
     constexpr int LPR = K / 4, G = 32 / LPR;
     const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
@@ -620,26 +722,22 @@ __global__ void __launch_bounds__(256) piece_reduce_kernel(const uint32_t* __res
 template <int K>
 __host__ __device__ constexpr int rt_tile_floats() { return 8 * (32 / (K / 4)) * (K + 4); }   // 8 warps x rows per warp x row width
 
-template <int K, bool BAGS>
+template <int K, typename SRC>
 __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restrict__ urow, const uint32_t* __restrict__ uval,
                                                          const uint32_t* __restrict__ svals,
                                                          const uint32_t* __restrict__ row_start,
                                                          const uint32_t* __restrict__ row_piece0,
                                                          const uint32_t* __restrict__ piece_start,
-                                                         const SegCounts* __restrict__ cnt, GradSrc<K, BAGS> src,
+                                                         const SegCounts* __restrict__ cnt, SRC src,
                                                          const float* __restrict__ piece_sum,
                                                          Table tb, int emb_slots, OptDev od, OptDev ol,
-                                                         bool has_emb, bool has_lin, int step,
-                                                         float* __restrict__ alpha_d, float* __restrict__ alpha_l,
+                                                         bool has_emb, bool has_lin, int step, RowReplay rr,
                                                          float* __restrict__ gsum_out, int gsum_stride,
                                                          const PeerRoute* __restrict__ rt) {
     constexpr int LPR = K / 4;
     const int sub = threadIdx.x % LPR;
     const uint32_t gpb = blockDim.x / LPR;
-    if (!gsum_out && blockIdx.x == 0 && threadIdx.x == 0) {  // alpha_t history for later replays
-        alpha_d[step] = od.alpha;
-        alpha_l[step] = ol.alpha;
-    }
+    const ReplayStep rs = replay_step_load(rr.rd.closed ? rr.rd : rr.rl, rr.upto);
     const uint32_t U = cnt->n_rows;
     // row mapping: within one trip the lane groups of a warp take rows n_warps apart
     const uint32_t TG = gridDim.x * gpb, gid = blockIdx.x * gpb + threadIdx.x / LPR;
@@ -662,7 +760,7 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
                 if (emb_slots >= 1) s1 = tab_s1(tb, row)[sub];
                 if (emb_slots >= 2) s2 = tab_s2(tb, row)[sub];
             }
-            if (sub == 0) lr = *tab_lin(tb, row);
+            lr = *tab_lin(tb, row);        // every lane of the group (one broadcast load): last_step drives the replay
         }
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         float gl = 0.f;
@@ -750,6 +848,14 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
                 if (lane / LPR == src_lane / LPR) { g = a; gl = al; }
             }
         }
+        if (SRC::SUB_E) {
+            // the fused source delivers {sum(dz s + dh0), sum(dz)}; the piece paths keep sum(dz) on lane 0 of the group only
+            gl = __shfl_sync(0xffffffffu, gl, (int)(threadIdx.x & 31) - sub);
+            if (gsum_out && act && src.sub_e()) {     // sharded requester: E = the row as it was fetched from its owner
+                const float4 e = __ldg(reinterpret_cast<const float4*>(src.erow + (size_t)u * src.erow_stride) + sub);
+                g.x = fmaf(-gl, e.x, g.x); g.y = fmaf(-gl, e.y, g.y); g.z = fmaf(-gl, e.z, g.z); g.w = fmaf(-gl, e.w, g.w);
+            }
+        }
         if (rt) {   // fused exchange: the gradient rows go straight into their owners' receive buffers over NVLink
             constexpr int RW = K + 4, RW4 = RW / 4;
             const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -784,6 +890,12 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
             if (sub == 0) gp[K] = gl;
             continue;
         }
+        // non-lazy Adam: first the decay steps this row skipped since it was last written (replayed in registers) ...
+        replay_row(w, s1, s2, lr, sub == 0, rr, rs, od, ol);
+        if (SRC::SUB_E && src.sub_e()) {      // dE = sum(dz s + dh0) - sum(dz) * E,  E = the row as the forward pass saw it
+            g.x = fmaf(-gl, w.x, g.x); g.y = fmaf(-gl, w.y, g.y); g.z = fmaf(-gl, w.z, g.z); g.w = fmaf(-gl, w.w, g.w);
+        }
+        // ... then this step's gradient
         if (has_emb) {
             sparse_apply(w.x, s1.x, s2.x, g.x, od);
             sparse_apply(w.y, s1.y, s2.y, g.y, od);
@@ -793,6 +905,8 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
             if (emb_slots >= 1) tab_s1(tb, row)[sub] = s1;
             if (emb_slots >= 2) tab_s2(tb, row)[sub] = s2;
         }
+        // (the lanes of a group read last_step in ONE warp-wide load instruction, before the full-mask ballot above:
+        //  lane 0's store below cannot overtake them)
         if (sub == 0) {
             if (has_lin) sparse_apply(lr.x, lr.y, lr.z, gl, ol);
             lr.w = __int_as_float(step);
@@ -827,8 +941,8 @@ __global__ void shard_rekey_kernel(uint32_t* __restrict__ keys, int64_t n, uint3
 }
 // per sorted position: lookup -> unique index; per unique row: local row id for its owner + per-owner counts
 __global__ void __launch_bounds__(256) shard_uniq_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svals, int64_t n,
-                                                         uint32_t limit, uint32_t Rl, uint32_t W,
-                                                         const unsigned long long* __restrict__ scanned, uint32_t* __restrict__ uidx,
+                                                         uint32_t limit, uint32_t Rl, uint32_t W, int n_slots,
+                                                         const uint32_t* __restrict__ pos_row, uint32_t* __restrict__ uidx,
                                                          uint32_t* __restrict__ req_rows, int32_t* __restrict__ counts) {
     // per-owner counts are aggregated per block in shared memory first: the sorted keys put (almost) every
     // lookup of a block on the same owner, and same-address global atomics serialise in L2
@@ -839,12 +953,11 @@ __global__ void __launch_bounds__(256) shard_uniq_kernel(const uint32_t* __restr
     if (i < n) {
         uint32_t k = skeys[i];
         if (k >= limit) {
-            uidx[svals[i]] = 0xffffffffu;
+            uidx[(size_t)payload_sample(svals[i]) * n_slots + payload_slot(svals[i])] = 0xffffffffu;
         } else {
             bool rh = (i == 0) || (k != skeys[i - 1]);
-            uint32_t ridx = (uint32_t)(scanned[i] >> 32);
-            if (!rh) ridx -= 1;
-            uidx[svals[i]] = ridx;
+            const uint32_t ridx = pos_row[i];
+            uidx[(size_t)payload_sample(svals[i]) * n_slots + payload_slot(svals[i])] = ridx;
             if (rh) {
                 req_rows[ridx] = k % Rl;
                 uint32_t o = k / Rl;
@@ -932,8 +1045,9 @@ __global__ void __launch_bounds__(256) tiny_reduce_kernel(const int32_t* __restr
 template <int K>
 __global__ void __launch_bounds__(256) tiny_update_kernel(const float* __restrict__ partial, int n_blocks, const uint32_t* __restrict__ trow_grow,
                                                           int n_trows, Table tb, int emb_slots, OptDev od, OptDev ol, bool has_emb, bool has_lin,
-                                                          int step) {
+                                                          int step, RowReplay rr) {
     constexpr int LPR = K / 4, G = 32 / LPR, RW = K + 4;
+    const ReplayStep rs = replay_step_load(rr.rd.closed ? rr.rd : rr.rl, rr.upto);
     const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= n_trows) return;                        // warp-uniform
@@ -965,10 +1079,15 @@ __global__ void __launch_bounds__(256) tiny_update_kernel(const float* __restric
     }
     if (cnt == 0.f || grp != 0) return;
     const size_t row = trow_grow[r];
+    float4 lr = *tab_lin(tb, row);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f), s1 = w, s2 = w;
     if (has_emb) {
-        float4 w = tab_w(tb, row)[sub], s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+        w = tab_w(tb, row)[sub];
         if (emb_slots >= 1) s1 = tab_s1(tb, row)[sub];
         if (emb_slots >= 2) s2 = tab_s2(tb, row)[sub];
+    }
+    replay_row(w, s1, s2, lr, sub == 0, rr, rs, od, ol);       // decay steps skipped since the row was last written
+    if (has_emb) {
         sparse_apply(w.x, s1.x, s2.x, g.x, od);
         sparse_apply(w.y, s1.y, s2.y, g.y, od);
         sparse_apply(w.z, s1.z, s2.z, g.z, od);
@@ -978,7 +1097,6 @@ __global__ void __launch_bounds__(256) tiny_update_kernel(const float* __restric
         if (emb_slots >= 2) tab_s2(tb, row)[sub] = s2;
     }
     if (sub == 0) {
-        float4 lr = *tab_lin(tb, row);
         if (has_lin) sparse_apply(lr.x, lr.y, lr.z, gl, ol);
         lr.w = __int_as_float(step);
         *tab_lin(tb, row) = lr;
@@ -989,16 +1107,19 @@ __global__ void __launch_bounds__(256) tiny_update_kernel(const float* __restric
 template <int K>
 __global__ void __launch_bounds__(256) shard_serve_kernel(const uint32_t* __restrict__ recv_rows, int64_t n,
                                                           Table tb, bool has_emb, bool has_lin,
-                                                          float* __restrict__ reply, int reply_stride) {
+                                                          float* __restrict__ reply, int reply_stride,
+                                                          RowReplay rr, OptDev od, OptDev ol) {
     constexpr int LPR = K / 4;
     const int sub = threadIdx.x % LPR;
     const int64_t gpb = blockDim.x / LPR;
+    const ReplayStep rs = replay_step_load(rr.rd.closed ? rr.rd : rr.rl, rr.upto);
     for (int64_t i = (int64_t)blockIdx.x * gpb + threadIdx.x / LPR; i < n; i += (int64_t)gridDim.x * gpb) {
         size_t row = recv_rows[i];
         float* rp = reply + (size_t)i * reply_stride;
-        float4 e = has_emb ? __ldg(tab_w(tb, row) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 e; float lw;
+        load_row_current(tb, row, sub, has_emb, rr, rs, od, ol, e, lw);     // replayed in registers, not written back
         reinterpret_cast<float4*>(rp)[sub] = e;
-        if (sub == 0) rp[K] = has_lin ? __ldg(reinterpret_cast<const float*>(tab_lin(tb, row))) : 0.f;
+        if (sub == 0) rp[K] = has_lin ? lw : 0.f;
     }
 }
 
@@ -1010,10 +1131,11 @@ __global__ void __launch_bounds__(256) shard_serve_kernel(const uint32_t* __rest
 template <int K>
 __global__ void __launch_bounds__(256) shard_serve_p2p_kernel(const uint32_t* __restrict__ recv_rows, int64_t n,
                                                               Table tb, bool has_emb, bool has_lin,
-                                                              const PeerRoute* __restrict__ rt) {
+                                                              const PeerRoute* __restrict__ rt, RowReplay rr, OptDev od, OptDev ol) {
     constexpr int LPR = K / 4, RPP = 32 / LPR, CH = (1024 / K < 32 ? 1024 / K : 32) /* rows per chunk, bounded by shared memory */, PASSES = CH / RPP, RW = K + 4, RW4 = RW / 4;
     __shared__ __align__(16) float tile[8][CH * RW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+    const ReplayStep rs = replay_step_load(rr.rd.closed ? rr.rd : rr.rl, rr.upto);
     float* tl = tile[warp];
     const int64_t n_chunks = (n + CH - 1) / CH;
     for (int64_t chunk = (int64_t)blockIdx.x * 8 + warp; chunk < n_chunks; chunk += (int64_t)gridDim.x * 8) {
@@ -1027,8 +1149,8 @@ __global__ void __launch_bounds__(256) shard_serve_p2p_kernel(const uint32_t* __
             e[p] = make_float4(0.f, 0.f, 0.f, 0.f); l[p] = 0.f;
             if (r < cnt) {
                 const size_t row = __ldg(recv_rows + i0 + r);
-                if (has_emb) e[p] = __ldg(tab_w(tb, row) + sub);
-                if (sub == 0 && has_lin) l[p] = __ldg(reinterpret_cast<const float*>(tab_lin(tb, row)));
+                load_row_current(tb, row, sub, has_emb, rr, rs, od, ol, e[p], l[p]);
+                if (!has_lin) l[p] = 0.f;
             }
         }
 #pragma unroll

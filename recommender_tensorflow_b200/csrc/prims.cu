@@ -250,3 +250,196 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], int64_t n, int bits, 
 }
 
 }  // namespace prims
+
+// =====================================================================================================================
+// One-sweep LSD radix sort (8-bit digits) with decoupled look-back, and a single-pass segment builder.
+//
+// The multi-launch sort above costs (histogram + 3 scan launches + scatter) per digit = 15-20 dependent launches of
+// small grids, 0.20 ms for the 1.7 M (row, lookup) pairs of a Criteo-shaped batch although it moves only ~110 MB.
+// Here ONE kernel builds the digit histograms of all passes, and every pass is ONE kernel: a tile (4096 pairs) ranks
+// its keys, publishes its per-digit counts, learns the counts of all earlier tiles by looking back along a chain of
+// status words (tile i publishes "aggregate" first, then "inclusive prefix"; a reader walks back until it meets a
+// prefix) and scatters.  Tiles are handed out by an atomic ticket, so a tile only ever waits for tiles that started
+// before it (forward progress without a co-residency assumption).  The element count may live in DEVICE memory
+// (n_dev): the row-sharded owner side sorts what its peers pushed without the host ever learning how much arrived.
+// =====================================================================================================================
+namespace prims {
+
+constexpr int OS_THREADS = 256;
+constexpr int OS_ITEMS = 16;
+constexpr int OS_TILE = OS_THREADS * OS_ITEMS;     // 4096 pairs per tile
+constexpr int OS_RADIX = 256;
+constexpr int OS_MAX_PASSES = 4;
+constexpr uint32_t OS_AGG = 1u << 30, OS_PREFIX = 2u << 30, OS_VALUE = (1u << 30) - 1u;
+
+static inline int64_t os_tiles(int64_t n) { return (n + OS_TILE - 1) / OS_TILE; }
+
+// temp layout: [hist 4 x 256][tickets 8][status 4 x tiles_max x 256]   (uint32)
+size_t onesweep_temp_bytes(int64_t n_max) {
+    return ((size_t)OS_MAX_PASSES * OS_RADIX + 8 + (size_t)OS_MAX_PASSES * std::max<int64_t>(os_tiles(n_max), 1) * OS_RADIX) * 4 + 256;
+}
+
+__device__ __forceinline__ int64_t os_count(int64_t n_host, const uint32_t* __restrict__ n_dev) {
+    return n_dev ? (int64_t)*reinterpret_cast<const volatile uint32_t*>(n_dev) : n_host;
+}
+
+// digit histograms of all passes + clears the look-back status words of the tiles this sort will use
+__global__ void __launch_bounds__(OS_THREADS) os_hist_kernel(const uint32_t* __restrict__ keys, int64_t n_host, const uint32_t* __restrict__ n_dev,
+                                                             int passes, uint32_t* __restrict__ hist, uint32_t* __restrict__ status,
+                                                             int64_t tiles_max) {
+    __shared__ uint32_t sh[OS_MAX_PASSES][OS_RADIX];
+    const int64_t n = os_count(n_host, n_dev);
+    const int64_t tiles = (n + OS_TILE - 1) / OS_TILE;
+    const int64_t gtid = (int64_t)blockIdx.x * OS_THREADS + threadIdx.x, gsz = (int64_t)gridDim.x * OS_THREADS;
+    for (int p = 0; p < passes; ++p)
+        for (int64_t i = gtid; i < tiles * OS_RADIX; i += gsz) status[(size_t)p * tiles_max * OS_RADIX + i] = 0u;
+    for (int i = threadIdx.x; i < OS_MAX_PASSES * OS_RADIX; i += OS_THREADS) (&sh[0][0])[i] = 0u;
+    __syncthreads();
+    for (int64_t i = gtid; i < n; i += gsz) {
+        const uint32_t k = keys[i];
+        for (int p = 0; p < passes; ++p) atomicAdd(&sh[p][(k >> (8 * p)) & 255u], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * OS_RADIX; i += OS_THREADS) {
+        const uint32_t c = (&sh[0][0])[i];
+        if (c) atomicAdd(hist + i, c);
+    }
+}
+
+__global__ void __launch_bounds__(OS_THREADS) os_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                                int64_t n_host, const uint32_t* __restrict__ n_dev, int shift,
+                                                                const uint32_t* __restrict__ hist_p, uint32_t* status_p,
+                                                                uint32_t* __restrict__ ticket_p) {
+    constexpr int NW = OS_THREADS / 32;
+    __shared__ uint32_t wcnt[NW][OS_RADIX];
+    __shared__ uint32_t skey[OS_TILE], sval[OS_TILE];
+    __shared__ uint32_t dstart[OS_RADIX], gdelta[OS_RADIX];
+    __shared__ uint32_t scan_tmp[33];
+    __shared__ uint32_t s_tile;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) s_tile = atomicAdd(ticket_p, 1u);
+    for (int i = tid; i < NW * OS_RADIX; i += OS_THREADS) (&wcnt[0][0])[i] = 0u;
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t n = os_count(n_host, n_dev);
+    if (tile * OS_TILE >= n) return;                      // block-uniform
+    // global base of every digit = exclusive scan of this pass's histogram (thread d owns digit d)
+    uint32_t base_d;
+    {
+        uint32_t tot;
+        base_d = block_exclusive_scan<uint32_t>(hist_p[tid], scan_tmp, tot);
+    }
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int64_t base = tile * OS_TILE + (int64_t)warp * 32 * OS_ITEMS + lane;
+    uint32_t k[OS_ITEMS], v[OS_ITEMS];
+    uint16_t rank[OS_ITEMS];
+#pragma unroll
+    for (int j = 0; j < OS_ITEMS; ++j) {
+        const int64_t idx = base + j * 32;
+        const bool valid = idx < n;
+        k[j] = valid ? keys_in[idx] : 0u;
+        v[j] = valid ? vals_in[idx] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < OS_ITEMS; ++j) {
+        const int64_t idx = base + j * 32;
+        const bool valid = idx < n;
+        const uint32_t d = valid ? ((k[j] >> shift) & 255u) : (uint32_t)OS_RADIX;   // tail items form their own group
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t r = __popc(peers & lt_mask);
+        uint32_t old = 0;
+        if (valid && r == 0) {
+            old = wcnt[warp][d];
+            wcnt[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+        rank[j] = (uint16_t)(old + r);
+        __syncwarp();
+    }
+    __syncthreads();
+    // thread d: exclusive prefix over the warps of this tile, tile count, look-back over the earlier tiles
+    uint32_t run = 0, goff;
+    {
+        const int d = tid;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t c = wcnt[w][d];
+            wcnt[w][d] = run;
+            run += c;
+        }
+        volatile uint32_t* st = status_p;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            st[d] = OS_PREFIX | run;
+        } else {
+            st[(size_t)tile * OS_RADIX + d] = OS_AGG | run;
+            for (int64_t tt = tile - 1; tt >= 0; --tt) {
+                uint32_t s;
+                do { s = st[(size_t)tt * OS_RADIX + d]; } while (s == 0u);
+                excl += s & OS_VALUE;
+                if (s & OS_PREFIX) break;
+            }
+            st[(size_t)tile * OS_RADIX + d] = OS_PREFIX | (excl + run);
+        }
+        goff = base_d + excl;
+    }
+    // Tile-local sort through shared memory, then a coalesced scatter: in digit order the 4096 pairs of a tile form
+    // <= 256 runs, each contiguous in the output, so consecutive threads write consecutive addresses.  (Writing every
+    // pair straight to its final position cost one 32-byte L2 sector transaction per 4-byte element: 54 us per pass for
+    // 1.7 M pairs, 10 % issue-active - profiles/r02d.)
+    {
+        uint32_t tot;
+        const uint32_t lstart = block_exclusive_scan<uint32_t>(run, scan_tmp, tot);     // first local position of digit `tid`
+#pragma unroll
+        for (int w = 0; w < NW; ++w) wcnt[w][tid] += lstart;
+        dstart[tid] = lstart;
+        gdelta[tid] = goff - lstart;                  // global position = gdelta[digit] + local position
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < OS_ITEMS; ++j) {
+        const int64_t idx = base + j * 32;
+        if (idx < n) {
+            const uint32_t d = (k[j] >> shift) & 255u;
+            const uint32_t lp = wcnt[warp][d] + rank[j];
+            skey[lp] = k[j];
+            sval[lp] = v[j];
+        }
+    }
+    __syncthreads();
+    const int nvalid = (int)min((int64_t)OS_TILE, n - tile * OS_TILE);
+#pragma unroll
+    for (int j = 0; j < OS_ITEMS; ++j) {
+        const int lp = tid + j * OS_THREADS;
+        if (lp < nvalid) {
+            const uint32_t kk = skey[lp];
+            const uint32_t pos = gdelta[(kk >> shift) & 255u] + (uint32_t)lp;
+            keys_out[pos] = kk;
+            vals_out[pos] = sval[lp];
+        }
+    }
+}
+
+int onesweep_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], int64_t n_max, const uint32_t* n_dev, int bits, void* temp,
+                        cudaStream_t st, int64_t* launches) {
+    if (n_max <= 0 || bits <= 0) return 0;
+    const int passes = std::min(OS_MAX_PASSES, (bits + 7) / 8);
+    const int64_t tiles_max = std::max<int64_t>(os_tiles(n_max), 1);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(temp);
+    uint32_t* tickets = hist + OS_MAX_PASSES * OS_RADIX;
+    uint32_t* status = tickets + 8;
+    cudaMemsetAsync(hist, 0, (OS_MAX_PASSES * OS_RADIX + 8) * 4, st);
+    const unsigned hgrid = (unsigned)std::min<int64_t>(tiles_max, 592);
+    os_hist_kernel<<<hgrid, OS_THREADS, 0, st>>>(keys[0], n_max, n_dev, passes, hist, status, tiles_max);
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        os_scatter_kernel<<<(unsigned)tiles_max, OS_THREADS, 0, st>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n_max, n_dev, 8 * p,
+                                                                       hist + p * OS_RADIX, status + (size_t)p * tiles_max * OS_RADIX, tickets + p);
+        cur ^= 1;
+    }
+    if (launches) *launches += 1 + passes;
+    return cur;
+}
+
+}  // namespace prims

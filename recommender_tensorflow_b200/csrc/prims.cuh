@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 
 namespace prims {
 
@@ -38,5 +39,11 @@ void exclusive_scan_u64(const uint64_t* in, uint64_t* out, int64_t n, void* temp
 // returns the index (0/1) of the buffer pair that holds the sorted output.
 int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], int64_t n, int bits, void* temp,
                      cudaStream_t st, int64_t* launches);
+
+// One-sweep variant (decoupled look-back, 8-bit digits): one histogram launch + one launch per digit.  The element count
+// may live in device memory (n_dev != nullptr; n_max then bounds it and sizes the grids).
+size_t onesweep_temp_bytes(int64_t n_max);
+int onesweep_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], int64_t n_max, const uint32_t* n_dev, int bits, void* temp,
+                        cudaStream_t st, int64_t* launches);
 
 }  // namespace prims

@@ -39,6 +39,22 @@ def test_kmajor_fp32_accuracy(mode, M, N, K):
     assert err <= max(4 * err32, 3e-6 * scale), (err, scale, err32)
 
 
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("M,N,K", [(65536, 256, 416), (65536, 128, 256), (65536, 416, 256), (65536, 256, 128), (19000, 256, 416)])
+def test_kmajor_persistent_regime(mode, M, N, K):
+    """The regime bench.py runs in: 512 x (1..4) tiles of 128 x 128 on 148 persistent CTAs = 3.5..14 tiles per CTA, so
+    the double-buffered TMEM accumulators wrap their phase bits and the TMA ring runs across tile boundaries
+    (configs[2]: B = 65 536, tower 416 -> 256 -> 128 and its backward-data GEMMs)."""
+    err, scale, err32 = _run(mode, M, N, K, seed=M + N + K)
+    assert err <= max(4 * err32, 3e-6 * scale), (err, scale, err32)
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(416, 256, 65536, 8), (256, 128, 65536, 8)])
+def test_mnmajor_weight_gradient_full_batch(M, N, K, splits):
+    err, scale, err32 = _run(1, M, N, K, splits, seed=7)
+    assert err <= max(4 * err32, 3e-6 * scale), (err, scale, err32)
+
+
 @pytest.mark.parametrize("M,N,K,splits", [(128, 128, 64, 1), (128, 256, 4096, 4), (416, 256, 8192, 8), (256, 128, 1000, 3)])
 def test_mnmajor_weight_gradient(M, N, K, splits):
     err, scale, err32 = _run(1, M, N, K, splits)
