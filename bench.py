@@ -3,10 +3,14 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl b200|reference]
 
-A "step" is one pass of the hot path (transform -> gather/FM -> tower -> loss -> backward ->
-sorted sparse reduction -> optimizers) over one batch of synthetic input.  `value` times the
-device-resident path (inputs already in HBM); `e2e` times the same steps through the host-buffer
-C-ABI entry point (H2D of the raw columns + D2H of the loss inside the timed region).
+A "step" is one pass of the hot path (transform -> gather/FM -> tower -> loss -> backward -> sorted sparse reduction ->
+optimizers) over one batch of synthetic input.  `value` times the device-resident path (inputs already in HBM); `e2e`
+times the same steps through the host-buffer C-ABI entry point (H2D of the raw columns + D2H of the loss inside the timed
+region).
+
+ONE workload for the whole 1 -> 8 series: the Criteo-shaped DeepFM (26 x 1e7 hashed rows, 13 numerics, k = 16, hidden
+[16,16], 65 536 samples per GPU per step) — unsharded on one GPU, row-sharded (weak scaling) on N > 1.  At N = 1 the
+line also carries `secondary` blocks for BASELINE configs[2] / [1] / [0], and every line a `zipf` block (Zipf(1.05) ids).
 """
 import argparse
 import json
@@ -24,24 +28,31 @@ sys.path.insert(0, ROOT)
 METRIC = "DeepFM train samples/sec (fwd+bwd+sparse Adam)"
 
 WORKLOADS = {
-    # BASELINE.json configs[2]: the DeepFM config quoted for 1 B200
-    "deepfm_ml100k_k16_h256x128_b65536": dict(data="ml100k", k=16, hidden=(256, 128), batch=65536, model="deepfm"),
-    # configs[0] / configs[1]
-    "deepfm_ml100k_k4_h16x16_b32": dict(data="ml100k", k=4, hidden=(16, 16), batch=32, model="deepfm"),
-    "wide_deep_ml100k_k4_h16x16_b4096": dict(data="ml100k", k=4, hidden=(16, 16), batch=4096, model="wide_deep"),
-    # configs[3] on one GPU (26 x 1e7 rows, k=16: 16.6 GB of tables + 33 GB of Adam slots)
+    # BASELINE.json configs[3] (and its single-GPU form: 26 x 1e7 rows, k=16: 16.6 GB of tables + 33 GB of Adam slots)
     "deepfm_criteo_1e7_k16_h16x16_b65536": dict(data="criteo", k=16, hidden=(16, 16), batch=65536, model="deepfm",
                                                 buckets=10_000_000),
     "deepfm_criteo_1e6_k16_h16x16_b65536": dict(data="criteo", k=16, hidden=(16, 16), batch=65536, model="deepfm",
                                                 buckets=1_000_000),
+    # BASELINE.json configs[4]: k = 64, global batch 262 144, tables sharded over 8 GPUs, data-parallel [256,128] tower.
+    # 26 x 1e8 rows x (64 + 2 x 64 Adam) fp32 = 2.0 TB does not fit 8 x 180 GB: 5e6 buckets per field
+    # PER GPU are used (4e7 per field = 1.04e9 rows = 865 GB of 832-byte records at 8 GPUs), batch 32 768 per GPU.
+    "deepfm_criteo_k64_h256x128_b262144": dict(data="criteo", k=64, hidden=(256, 128), batch=32768, model="deepfm",
+                                               buckets_per_gpu=5_000_000),
+    # BASELINE.json configs[2]: the DeepFM config with a tensor-core tower
+    "deepfm_ml100k_k16_h256x128_b65536": dict(data="ml100k", k=16, hidden=(256, 128), batch=65536, model="deepfm"),
+    # configs[0] / configs[1]
+    "deepfm_ml100k_k4_h16x16_b32": dict(data="ml100k", k=4, hidden=(16, 16), batch=32, model="deepfm"),
+    "wide_deep_ml100k_k4_h16x16_b4096": dict(data="ml100k", k=4, hidden=(16, 16), batch=4096, model="wide_deep"),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (tc::gemm_persist_kernel<16>, 38 % of the
-# step, 4 launches per step: 143 / 72 / 132 / 260 MB) from the ncu --set full capture in profiles/r01k_gemm_persist_full_summary.csv
-TRAFFIC = {"deepfm_ml100k_k16_h256x128_b65536": 151.8e6}
-TRAFFIC_NOTE = ("bytes per launch (mean of the 4 launches/step) of the dominant kernel tc::gemm_persist_kernel<16>; "
-                "profiles/r01k_gemm_persist_full_summary.csv; the whole-step algorithmic bytes are bytes_per_sample x batch")
-DEFAULT_WORKLOAD = "deepfm_ml100k_k16_h256x128_b65536"
-DEFAULT_SHARDED = "deepfm_criteo_1e7_k16_h16x16_b65536"
+DEFAULT_WORKLOAD = "deepfm_criteo_1e7_k16_h16x16_b65536"
+SECONDARY = ["deepfm_ml100k_k16_h256x128_b65536", "wide_deep_ml100k_k4_h16x16_b4096", "deepfm_ml100k_k4_h16x16_b32"]
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (ncu --set full, profiles/)
+TRAFFIC = {
+    "deepfm_criteo_1e7_k16_h16x16_b65536": (827.3e6, "row_apply_kernel<16, GradSrcFused<16,16>> (sparse optimizer over the 1.70 M unique rows: "
+                                            "478 MB read + 349 MB written per launch; profiles/r02d_criteo_kernels_full_summary.txt); "
+                                            "algorithmic bytes of that kernel alone: 1.70 M rows x (208 B read + 208 B written) = 709 MB"),
+    "deepfm_ml100k_k16_h256x128_b65536": (151.8e6, "mean of the 4 launches/step of tc::gemm_persist_kernel<16>; profiles/r01k_gemm_persist_full_summary.csv"),
+}
 
 
 def bytes_per_sample(dc, dn, k, slots_emb, slots_lin):
@@ -52,16 +63,20 @@ def bytes_per_sample(dc, dn, k, slots_emb, slots_lin):
     return inputs + gather + update
 
 
-def make_columns(w):
+def workload_buckets(w, world):
+    return w["buckets"] if "buckets" in w else w["buckets_per_gpu"] * max(world, 1)
+
+
+def make_columns(w, world=1):
     from recommender_tensorflow_b200 import synth
     from recommender_tensorflow_b200.trainers import ml_100k
     if w["data"] == "ml100k":
         return ml_100k.get_feature_columns()["linear"], [], ml_100k.FEATURE_DTYPES
-    cats, nums = synth.criteo_columns(w["buckets"])
+    cats, nums = synth.criteo_columns(workload_buckets(w, world))
     return cats, nums, {}
 
 
-def make_batches(w, n_batches, seed):
+def make_batches(w, n_batches, seed, zipf=None):
     from recommender_tensorflow_b200 import synth
     rng = np.random.default_rng(seed)
     out = []
@@ -71,7 +86,7 @@ def make_batches(w, n_batches, seed):
             out.append(ml.fast_batch(w["batch"], rng))
     else:
         for _ in range(n_batches):
-            out.append(synth.criteo_batch(w["batch"], rng))
+            out.append(synth.criteo_batch(w["batch"], rng, zipf_alpha=zipf))
     return out
 
 
@@ -134,15 +149,38 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
-def cpu_baseline(w, cats_specs_engine, seconds_target=12.0, threads=None):
+# ------------------------------------------------------------------------------------------- reference (CPU) arm
+class _EngLike:
+    pass
+
+
+def _eng_like(w, world=1):
+    """what tests.util.oracle_cfg needs from an engine, without creating one (no CUDA)"""
+    cats, nums, dtypes = make_columns(w, world)
+    e = _EngLike()
+    cats = sorted(cats, key=lambda c: c.name + "_embedding")
+    e.specs = []
+    for c in cats:
+        s = c.spec()
+        if s["kind"] == "bucketized":
+            s["dtype"] = dtypes.get(s["source"], "float32")
+        e.specs.append(s)
+    e.num_columns = sorted(nums, key=lambda c: c.name)
+    e.k, e.hidden = w["k"], list(w["hidden"])
+    o = optimizers(w)
+    e.use_linear, e.use_mf, e.use_dnn = True, o["use_mf"], True
+    e.loss_reduction, e.opt_deep, e.opt_linear = o["loss_reduction"], o["opt_deep"], o["opt_linear"]
+    return e
+
+
+def cpu_baseline(w, seconds_target=12.0, threads=None, max_steps=200):
     """Restated reference (torch-CPU oracle, NOT TensorFlow) timed on the host cores on a bounded sample."""
     import torch
     from oracle.deepfm import OracleDeepFM, init_weights
     from tests.util import oracle_cfg
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    eng_like = cats_specs_engine
-    cfg = oracle_cfg(eng_like)
+    cfg = oracle_cfg(_eng_like(w))
     nb = sum(int(s["num_buckets"]) for s in cfg["cat"])
     shrunk = ""
     if nb > 5_000_000:   # the literal non-lazy CPU step walks the whole table every step: bound the sample
@@ -152,8 +190,7 @@ def cpu_baseline(w, cats_specs_engine, seconds_target=12.0, threads=None):
         shrunk = "; hash buckets capped at 1e5/field for the CPU sample (the literal non-lazy Adam walks whole tables)"
     ora = OracleDeepFM(cfg, init_weights(cfg, 0))
     bs = min(w["batch"], 4096)
-    ww = dict(w, batch=bs)
-    batches = make_batches(ww, 4, 99)
+    batches = make_batches(dict(w, batch=bs), 4, 99)
     feats = []
     for f, y in batches:   # oracle takes object arrays of bytes for strings
         ff = {}
@@ -171,11 +208,12 @@ def cpu_baseline(w, cats_specs_engine, seconds_target=12.0, threads=None):
         ora.train_step_raw(*feats[n % len(feats)])
         n += 1
         dt = time.perf_counter() - t0
-        if dt > seconds_target or n >= 200:
+        if dt > seconds_target or n >= max_steps:
             break
     return {"value": bs * n / dt, "unit": "samples/s", "cores": threads, "kind": "port", "ms_per_cpu_step": dt / n * 1e3, "cpu_batch": bs,
+            "cpu_steps": n,
             "sample": "%d steps of batch %d of the same workload, torch-CPU float32 restatement of the TF-1.12 step "
-                      "(incl. literal non-lazy Adam); not TensorFlow%s" % (n, bs, shrunk)}, None
+                      "(incl. literal non-lazy Adam); not TensorFlow%s" % (n, bs, shrunk)}
 
 
 def run_reference(args, w, name):
@@ -183,38 +221,31 @@ def run_reference(args, w, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from recommender_tensorflow_b200 import feature_column  # noqa: F401  (descriptors only, no CUDA)
-
-    class EngLike:
-        pass
-    cats, nums, dtypes = make_columns(w)
-    e = EngLike()
-    cats = sorted(cats, key=lambda c: c.name + "_embedding")
-    e.specs = []
-    for c in cats:
-        s = c.spec()
-        if s["kind"] == "bucketized":
-            s["dtype"] = dtypes.get(s["source"], "float32")
-        e.specs.append(s)
-    e.num_columns = sorted(nums, key=lambda c: c.name)
-    e.k, e.hidden = w["k"], list(w["hidden"])
-    o = optimizers(w)
-    e.use_linear, e.use_mf, e.use_dnn = True, o["use_mf"], True
-    e.loss_reduction, e.opt_deep, e.opt_linear = o["loss_reduction"], o["opt_deep"], o["opt_linear"]
     per_step_budget = 60.0 / max(1, args.steps + args.warmup)
-    base, why = cpu_baseline(w, e, seconds_target=max(5.0, min(30.0, per_step_budget * args.steps)))
-    if base is None:
-        print(json.dumps({"impl": "reference", "unavailable": why}))
-        return
-    line = {"metric": METRIC, "value": base["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": base["ms_per_cpu_step"] * w["batch"] / base["cpu_batch"], "higher_is_better": True,
+    base = cpu_baseline(w, seconds_target=max(5.0, min(30.0, per_step_budget * args.steps)))
+    line = {"metric": METRIC, "value": base["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": base["cpu_steps"],
+            "warmup": 1, "ms_per_step": base["ms_per_cpu_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": name, "batch_per_gpu": w["batch"], "embedding_size": w["k"], "hidden_units": list(w["hidden"]),
                        "note": "CPU arm: restated reference (oracle port, torch-CPU); TensorFlow 1.12 is not installable in this image; "
-                               "ms_per_step is the CPU time for one batch of the workload's size extrapolated from the bounded sample"},
+                               "steps / ms_per_step are the CPU steps actually run, each on a bounded sample of cpu_batch samples "
+                               "(value = cpu_batch x steps / time)"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def cpu_baseline_subprocess(name):
+    """the CPU leg in its own process: the GPU arm never loads anything under oracle/"""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", name, "--steps", "1", "--warmup", "0"],
+                           capture_output=True, text=True, timeout=240, env=dict(os.environ, RANK="0", WORLD_SIZE="1", CUDA_VISIBLE_DEVICES=""))
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"unavailable": (r.stderr or r.stdout)[-300:]}
+    except Exception as ex:
+        return {"unavailable": repr(ex)}
 
 
 def csv_decode_bench(eng, B, iters=20):
@@ -253,58 +284,48 @@ def csv_decode_bench(eng, B, iters=20):
     return out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default=None, help="default: %s at N=1, %s (row-sharded, weak scaling) at N>1"
-                    % (DEFAULT_WORKLOAD, DEFAULT_SHARDED))
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--profile-phases", action="store_true", help="print a per-phase device-time breakdown to stderr")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    world_env = int(os.environ.get("WORLD_SIZE", "1"))
-    name = args.workload or (DEFAULT_SHARDED if max(world_env, args.gpus) > 1 else DEFAULT_WORKLOAD)
-    w = WORKLOADS[name]
-    if args.impl == "reference":
-        run_reference(args, w, name)
-        return
-
+# ------------------------------------------------------------------------------------------- one measured workload
+def measure(name, args, world, rank, local, peaks, primary=True, zipf=None):
+    """Times one workload on this rank's GPU (all ranks call it for the primary workload).  Returns the JSON dict on
+    rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
+    from recommender_tensorflow_b200 import synth
     from recommender_tensorflow_b200.engine import DeepFMEngine
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    cats, nums, dtypes = make_columns(w)
+    w = WORKLOADS[name]
+    steps, warmup = (args.steps, args.warmup) if primary else (min(args.steps, 20), min(args.warmup, 5))
+    if zipf:
+        steps, warmup = min(steps, 10), 3
+    cats, nums, dtypes = make_columns(w, world)
     B = w["batch"]
     sharded = world > 1 and w["data"] == "criteo"
-    eng = DeepFMEngine(cats, nums, embedding_size=w["k"], hidden_units=w["hidden"], max_batch=B, device=local,
-                       feature_dtypes=dtypes, rank=rank if sharded else 0, world=world if sharded else 1, **optimizers(w))
-    eng.init_random(1234 + rank)
+    kw = dict(embedding_size=w["k"], hidden_units=w["hidden"], max_batch=B, device=local, feature_dtypes=dtypes, **optimizers(w))
+    eng = DeepFMEngine(cats, nums, rank=rank if sharded else 0, world=world if sharded else 1, **kw)
+    eng.init_random(1234)            # same dense tower on every rank; the table shards differ by construction (own rows)
+    exchange = os.environ.get("DFM_SHARD_EXCHANGE", "xchg")     # "xchg": kernel stores + flags in peer memory; "nccl": all_to_all
+    parity = None
     if sharded:
-        # the replicated dense tower must start identical on every rank
-        for nm in eng.variable_names():
-            if nm not in ("emb", "lin"):
-                t = torch.from_numpy(eng.get_tensor(nm)).cuda()
-                dist.broadcast(t, 0)
-                eng.set_tensor(nm, t.cpu().numpy())
-        from recommender_tensorflow_b200.sharded import P2PShardedTrainer, ShardedTrainer
-        exchange = os.environ.get("DFM_SHARD_EXCHANGE", "p2p")     # "p2p": stores over IPC-mapped peer memory; "nccl": all_to_all
-        trainer = P2PShardedTrainer(eng) if exchange == "p2p" else ShardedTrainer(eng)
-    n_batches = 8
-    host_batches = make_batches(w, n_batches, 777 + rank)
-    packed_host = [eng.pack(f, y) for f, y in host_batches]
-    packed_dev = [eng.pack(f, y, device=True) for f, y in host_batches]
+        from recommender_tensorflow_b200.sharded import ShardedTrainer, XchgTrainer
+        if primary and not zipf and os.environ.get("DFM_PARITY_CHECK", "1") != "0":
+            parity = parity_check(w, kw, cats, nums, rank, world, local)
+        trainer = XchgTrainer(eng) if exchange == "xchg" else ShardedTrainer(eng)
+
+    # ---- inputs: fresh ids in every batch.  Criteo-shaped batches are generated on the device (32 of them); the
+    # Zipf(1.05) variant and the ML-100K-shaped batches come from the numpy generators (8 batches)
+    if w["data"] == "criteo" and not zipf:
+        n_batches = 32
+        packed_dev = synth.criteo_device_batches(eng, B, n_batches, 777 + rank)
+        packed_host = []
+        for pb in packed_dev[:8]:
+            host = torch.empty(pb.arena.numel(), dtype=torch.uint8).pin_memory()
+            host.copy_(pb.arena)
+            packed_host.append(eng.repack_like(pb, host))
+    else:
+        n_batches = 8
+        host_batches = make_batches(w, n_batches, 777 + rank, zipf=zipf)
+        packed_host = [eng.pack(f, y) for f, y in host_batches]
+        packed_dev = [eng.pack(f, y, device=True) for f, y in host_batches]
     h2d_bytes = packed_host[0].nbytes
 
     stream = torch.cuda.Stream()
@@ -315,20 +336,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    prefetch = sharded and exchange == "p2p" and os.environ.get("DFM_SHARD_PREFETCH", "1") != "0"
-
     def dev_step(i):
         if sharded:
-            kw = {"next_pb": packed_dev[(i + 1) % n_batches]} if prefetch else {}     # the next batch is known: its requests run ahead
-            loss_buf.copy_(trainer.train_step(packed_dev[i % n_batches], B * world, **kw).reshape(1))
+            loss_buf.copy_(trainer.train_step(packed_dev[i % n_batches], B * world).reshape(1))
         else:
             eng.train_step_device(packed_dev[i % n_batches], loss_out=loss_buf, stream=stream.cuda_stream)
-            if os.environ.get("DFM_PREFETCH", "0") == "1":      # optional lookahead (dfm_prefetch_batch): measured SLOWER here
-                eng.prefetch(packed_dev[(i + 1) % n_batches])   # (0.682 vs 0.648 ms: its kernels delay the persistent GEMM's CTAs)
 
     # ---------------- device-resident timing (value)
     with torch.cuda.stream(stream):
-        for i in range(args.warmup):
+        for i in range(warmup):
             dev_step(i)
     barrier()
     sampler = ClockSampler(local)
@@ -336,57 +352,53 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         ev0.record(stream)
-        for i in range(args.steps):
-            dev_step(args.warmup + i)
+        for i in range(steps):
+            dev_step(warmup + i)
         ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = eng.last_step_launches * args.steps
+    launches = eng.last_step_launches * steps
     eng.sync()
     torch.cuda.synchronize()
     last_loss = float(loss_buf.item())
+    unique_rows = eng.last_unique_rows
 
     # ---------------- end-to-end through the host-buffer entry point (e2e)
+    nh = len(packed_host)
     if sharded:
-        copied = set()
+        stage = [torch.empty_like(packed_dev[0].arena), torch.empty_like(packed_dev[0].arena)]
+        staged = [eng.repack_like(packed_dev[0], a) for a in stage]
 
         def e2e_step(i):
-            j, jn = i % n_batches, (i + 1) % n_batches
-            if i not in copied:
-                packed_dev[j].arena.copy_(packed_host[j].arena, non_blocking=True)     # H2D of the raw columns
-            if not prefetch:
-                return trainer.train_step(packed_dev[j], B * world)
-            packed_dev[jn].arena.copy_(packed_host[jn].arena, non_blocking=True)       # next step's H2D, then its requests run ahead
-            copied.add(i + 1)
-            return trainer.train_step(packed_dev[j], B * world, next_pb=packed_dev[jn])
+            staged[i % 2].arena.copy_(packed_host[i % nh].arena, non_blocking=True)      # H2D of the raw columns
+            return trainer.train_step(staged[i % 2], B * world)
         with torch.cuda.stream(stream):
             for i in range(2):
                 e2e_step(i)
         barrier()
-        copied.clear()
         loss_pin = torch.empty(2, dtype=torch.float32).pin_memory()
         loss_evs = [torch.cuda.Event(), torch.cuda.Event()]
         e2e_loss = float("nan")
         t0 = time.perf_counter()
         with torch.cuda.stream(stream):
-            for i in range(args.steps):
+            for i in range(steps):
                 loss_pin[i % 2:i % 2 + 1].copy_(e2e_step(i).reshape(1), non_blocking=True)   # D2H of the loss, every step ...
                 loss_evs[i % 2].record(stream)
                 if i > 0:                                                                # ... read one step late, like
                     loss_evs[(i - 1) % 2].synchronize()                                  # dfm_train_step_host_async
                     e2e_loss = float(loss_pin[(i - 1) % 2])
-            loss_evs[(args.steps - 1) % 2].synchronize()
-            e2e_loss = float(loss_pin[(args.steps - 1) % 2])
-        torch.cuda.synchronize()
+            loss_evs[(steps - 1) % 2].synchronize()
+            e2e_loss = float(loss_pin[(steps - 1) % 2])
+        barrier()
         e2e_s = time.perf_counter() - t0
     else:
         for i in range(3):
-            eng.train_step_async(packed_host[i % n_batches])
+            eng.train_step_async(packed_host[i % nh])
         eng.drain()
         barrier()
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            eng.train_step_async(packed_host[i % n_batches])     # H2D + step; returns the previous step's loss (D2H)
+        for i in range(steps):
+            eng.train_step_async(packed_host[i % nh])     # H2D + step; returns the previous step's loss (D2H)
         e2e_loss = eng.drain()
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
@@ -405,54 +417,56 @@ def main():
             for i in range(5):
                 trainer.train_step(packed_dev[i % n_batches], B * world, timings=phases)
         phases = {k: v / 5 for k, v in phases.items()}
-    if not sharded:
+    else:
         eng.set_profiling(True)
         eng.train_step_device(packed_dev[0], loss_out=loss_buf)
         eng.sync()
         phases = eng.phase_ms()
         eng.set_profiling(False)
 
+    line = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         se = {"Adam": 2, "Adagrad": 1, "Ftrl": 2, "SGD": 0}
         o = optimizers(w)
         bps = bytes_per_sample(len(cats), len(nums), w["k"], se[o["opt_deep"]["name"]], se[o["opt_linear"]["name"]])
-        total_samples = B * args.steps * world
-        value = total_samples / (ms * 1e-3)
+        value = B * steps * world / (ms * 1e-3)
         achieved = value / world * bps / 1e9
+        traffic = TRAFFIC.get(name) if not zipf else None
         line = {
-            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "b200",
             "config": {"workload": name, "batch_per_gpu": B, "embedding_size": w["k"], "hidden_units": list(w["hidden"]),
                        "n_cat": len(cats), "n_num": len(nums), "table_rows": int(eng.row_offsets[-1]),
+                       "ids": ("Zipf(%.2f) keys" % zipf) if zipf else "uniform 32-bit keys, fresh in every batch",
                        "optimizer": o["opt_deep"]["name"] + ("/" + o["opt_linear"]["name"] if w["model"] == "wide_deep" else " (TF non-lazy, exact deferred)"),
-                       "l2": "per-step working set (activations + gradients) exceeds L2; inputs rotate over %d batches" % n_batches,
+                       "l2": "per-step working set (%s) exceeds L2; inputs rotate over %d batches" % (
+                           "%.0f MB of table records" % (unique_rows * 256e-6) if w["data"] == "criteo" else "activations + gradients", n_batches),
                        "parallelism": "single GPU" if world == 1 else (
-                           "tables row-sharded over %d GPUs (ids / rows / gradient rows exchanged by %s), data-parallel tower "
-                           "(all_reduce); global batch %d" % (world, "kernel stores into IPC-mapped peer memory over NVLink"
-                                                              if exchange == "p2p" else "NCCL all_to_all", B * world) if sharded else "replicas x%d" % world)},
+                           "tables row-sharded over %d GPUs (ids / rows / gradient rows / dense gradients exchanged by %s), data-parallel "
+                           "tower; global batch %d" % (world, "kernel stores into IPC-mapped peer memory over NVLink, flag-synchronised: no collective "
+                                                       "and no host sync inside the step" if exchange == "xchg" else "NCCL all_to_all / all_gather", B * world)
+                           if sharded else "replicas x%d" % world)},
             "gpu_launches": int(launches),
             "loss_last": last_loss,
-            "e2e": {"value": B * args.steps * world / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / args.steps, "loss_last": e2e_loss,
-                    "how": ("pinned host arena -> H2D copy, sharded step, D2H of the loss every step (read one step late); wall clock, device sync on both sides"
-                            if sharded else
+            "unique_rows_per_step": int(unique_rows), "unique_row_ratio": unique_rows / float(B * max(len(cats), 1)),
+            "e2e": {"value": B * steps * world / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / steps, "loss_last": e2e_loss,
+                    "how": ("pinned host arena -> H2D copy, sharded step (launches only), D2H of the loss every step (read one step late); "
+                            "wall clock, barrier + device sync on both sides" if sharded else
                             "dfm_train_step_host_async: pinned host arena -> one H2D copy per step on a copy stream, step, "
                             "D2H of the loss; double buffered, wall clock with a device sync on both sides")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": TRAFFIC.get(name), "traffic_note": TRAFFIC_NOTE if name in TRAFFIC else None,
+                         "traffic": traffic[0] if traffic else None, "traffic_note": traffic[1] if traffic else None,
                          "bytes_per_sample": bps, "peak_source": peak_kind,
                          "scope": "whole step (all kernels of one train step; SURVEY.md 8d bytes/sample x batch / step time)"},
             "phases_ms": phases,
             "clocks": sampler.summary(),
         }
+        if parity is not None:
+            line["parity_check"] = parity
         if sharded:
             # algorithmic NVLink bytes per sample of the sharded step (ids out, rows back, gradient rows out)
             nvb = len(cats) * (4 + 2 * 4 * (w["k"] + 1)) * (world - 1) / world
@@ -460,28 +474,134 @@ def main():
             line["roofline_nvlink"] = {"bound": "nvlink", "achieved": ach, "peak": 770.0, "unit": "GB/s per GPU per direction", "frac": ach / 770.0,
                                        "bytes_per_sample": nvb, "peak_source": "B200_PROFILING.md measured peer copy (770 GB/s per direction)"}
         if w["hidden"] and max(w["hidden"]) >= 64 and phases and not sharded:
-            # the tower GEMMs (3xTF32 on tcgen05): algorithmic fp32 flops of the tower vs the tf32 tensor peak / 3
+            # the tower GEMMs (3xTF32 on tcgen05): algorithmic fp32 flops of the tower vs the tf32 tensor peak / 3.  The
+            # step is tensor-bound here: 3 x flops at the measured tf32 rate is the floor, not the HBM figure above
             d_in = (len(cats) + len(nums)) * w["k"]
             dims = [d_in] + list(w["hidden"])
             fl = 3 * 2 * B * (sum(a * b for a, b in zip(dims[:-1], dims[1:])) + dims[-1])
-            t = (phases["mlp_fwd"] + phases["mlp_bwd"]) * 1e-3
+            tt = (phases["mlp_fwd"] + phases["mlp_bwd"]) * 1e-3
             bf16 = float(peaks.get("bf16_tflops", 1590.0))
-            line["roofline_tower"] = {"bound": "tensor", "achieved": fl / t / 1e12, "peak": bf16 / 2 / 3, "unit": "TFLOP/s (fp32-equivalent)",
-                                      "frac": fl / t / 1e12 / (bf16 / 6), "flops_per_step": fl,
+            line["roofline_tower"] = {"bound": "tensor", "achieved": fl / tt / 1e12, "peak": bf16 / 2 / 3, "unit": "TFLOP/s (fp32-equivalent)",
+                                      "frac": fl / tt / 1e12 / (bf16 / 6), "flops_per_step": fl,
+                                      "tensor_floor_ms": fl / (bf16 / 6 * 1e12) * 1e3,
                                       "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (tf32 rate) / 3 (three TF32 MMAs per fp32-accurate product)"}
-        if world == 1 and w["data"] == "ml100k":
-            try:      # side measurement: the CSV input path decoded on the GPU, same batch size
-                line["csv_decode"] = csv_decode_bench(eng, B)
+    eng.close()
+    del packed_dev, packed_host
+    torch.cuda.empty_cache()
+    return line
+
+
+def parity_check(w, kw, cats, nums, rank, world, local):
+    """N > 1: three untimed steps through the NCCL all_to_all trainer and through the fused, flag-synchronised exchange
+    from identical state on identical batches; the line carries whether the global loss and the checksum of every
+    shard (tables + optimizer slots + dense tower) are equal bit for bit."""
+    import torch
+    import torch.distributed as dist
+    from recommender_tensorflow_b200 import synth
+    from recommender_tensorflow_b200.engine import DeepFMEngine
+    from recommender_tensorflow_b200.sharded import ShardedTrainer, XchgTrainer
+    B = w["batch"]
+    out = {"steps": 3}
+    engs = [DeepFMEngine(cats, nums, rank=rank, world=world, **kw) for _ in range(2)]
+    for e in engs:
+        e.init_random(4321)
+    ta, tb = ShardedTrainer(engs[0]), XchgTrainer(engs[1])
+    pbs = synth.criteo_device_batches(engs[0], B, 3, 555 + rank)
+    la, lb = [], []
+    for pb in pbs:
+        la.append(float(ta.train_step(pb, B * world).item()))
+    for pb in pbs:
+        lb.append(float(tb.train_step(pb, B * world).item()))
+    torch.cuda.synchronize()
+    ca, cb = engs[0].state_checksum(), engs[1].state_checksum()
+    flags = torch.tensor([int(la == lb), int(ca == cb)], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    out.update({"loss_bits_equal": bool(flags[0].item()), "shard_checksum_equal": bool(flags[1].item()),
+                "loss_nccl": la, "loss_xchg": lb, "checksum_rank0": "%016x" % cb,
+                "what": "ShardedTrainer (NCCL all_to_all + all_gather) vs XchgTrainer (peer-memory stores + flags), same seed, same batches; "
+                        "checksum = sum of the 32-bit patterns of every table record and dense parameter / slot on the rank, ANDed over ranks"})
+    for e in engs:
+        e.close()
+    del pbs
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default=None, help="default: %s at every N (row-sharded, weak scaling, at N>1)" % DEFAULT_WORKLOAD)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[2]/[1]/[0] blocks at N=1")
+    ap.add_argument("--no-zipf", action="store_true", help="skip the Zipf(1.05) block")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    name = args.workload or DEFAULT_WORKLOAD
+    w = WORKLOADS[name]
+    if args.impl == "reference":
+        run_reference(args, w, name)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    line = measure(name, args, world, rank, local, peaks, primary=True)
+    if w["data"] == "criteo" and not args.no_zipf:
+        try:      # SURVEY.md 8d: the same workload with Zipf(1.05) ids (hot rows, per-destination dedup, owner imbalance)
+            z = measure(name, args, world, rank, local, peaks, primary=False, zipf=1.05)
+            if rank == 0:
+                line["zipf"] = {k: z[k] for k in ("value", "ms_per_step", "steps", "unique_rows_per_step", "unique_row_ratio", "e2e", "roofline",
+                                                  "phases_ms", "loss_last") if k in z}
+                line["zipf"]["ids"] = z["config"]["ids"]
+                if "roofline_nvlink" in z:
+                    line["zipf"]["roofline_nvlink"] = z["roofline_nvlink"]
+        except Exception as ex:
+            if rank == 0:
+                line["zipf"] = {"unavailable": repr(ex)}
+    if rank == 0:
+        if world == 1 and not args.no_secondary and args.workload is None:
+            line["secondary"] = []
+            for sname in SECONDARY:
+                try:
+                    s = measure(sname, args, 1, 0, local, peaks, primary=False)
+                    keep = {k: s[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "gpu_launches", "e2e", "roofline", "phases_ms", "loss_last")}
+                    keep["config"] = s["config"]
+                    if "roofline_tower" in s:
+                        keep["roofline_tower"] = s["roofline_tower"]
+                    line["secondary"].append(keep)
+                except Exception as ex:
+                    line["secondary"].append({"config": {"workload": sname}, "unavailable": repr(ex)})
+            try:      # side measurement: the CSV input path decoded on the GPU (SURVEY.md 8f-2)
+                from recommender_tensorflow_b200.engine import DeepFMEngine
+                from recommender_tensorflow_b200.trainers import ml_100k
+                e2 = DeepFMEngine(ml_100k.get_feature_columns()["linear"], (), embedding_size=4, hidden_units=(16, 16), max_batch=65536,
+                                  device=local, feature_dtypes=ml_100k.FEATURE_DTYPES)
+                line["csv_decode"] = csv_decode_bench(e2, 65536)
+                e2.close()
             except Exception as ex:
                 line["csv_decode"] = {"unavailable": repr(ex)}
         if not args.no_cpu_baseline and world == 1:
-            try:
-                base, why = cpu_baseline(w, eng)
-                line["cpu_baseline"] = base if base else {"unavailable": why}
-            except Exception as ex:   # the baseline is a side measurement; never lose the GPU line
-                line["cpu_baseline"] = {"unavailable": repr(ex)}
+            line["cpu_baseline"] = cpu_baseline_subprocess(name)
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

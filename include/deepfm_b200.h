@@ -168,6 +168,12 @@ int dfm_flush(dfm_handle* h, void* stream);
 int dfm_sync(dfm_handle* h);
 
 int64_t dfm_global_step(const dfm_handle* h);
+/* Order-independent checksum (sum of the 32-bit patterns mod 2^64) of the whole trained state on this handle: table
+ * records (weights, optimizer slots, last_step; deferred decay materialised first) and dense parameters + slots.
+ * bench.py's multi-GPU parity_check compares it between the collective and the fused exchange. */
+int dfm_state_checksum(dfm_handle* h, uint64_t* out_host);
+/* unique table rows touched by the last step's batch (synchronises) */
+int64_t dfm_last_unique_rows(dfm_handle* h);
 /* Checkpoint restore (trainers/deep_fm.py:147-148 --restore; tf.train.Saver restores global_step and the
  * Adam beta powers): call after loading every variable and slot with dfm_set_tensor. */
 int dfm_set_global_step(dfm_handle* h, int64_t step);
@@ -205,37 +211,41 @@ int dfm_shard_forward_backward(dfm_handle* h, const dfm_raw_batch* dev_batch, co
                                float* loss_dev, float* logits_dev, float* gsum_dev, float* dense_grad_dev, void* stream);
 int dfm_shard_apply(dfm_handle* h, const float* grecv_dev, const float* dense_grad_dev, void* stream);
 
-/* ---- The same sharded step with the three exchanges FUSED into the kernels over NVLink peer memory.
- * Every rank's receive buffers (row ids, rows, gradient rows) live in the library and are mapped into the
- * other ranks through CUDA IPC (dfm_shard_ipc_export / _import, handles exchanged by the host once).  Per step:
- *   dfm_shard_requests_dev -> all_gather(counts) -> dfm_shard_p2p_plan    (W x W count matrix -> routing table; the
- *                                     matrix read-back is the only host synchronisation of the step)
- *   dfm_shard_p2p_push_ids            requesters store their unique row ids into the owners' buffers    | barrier
- *   dfm_shard_p2p_serve               owners catch up and store each row into the requester's row buffer | barrier
- *   dfm_shard_p2p_forward_backward    gradient rows are stored straight into the owners' buffers         | all_reduce(dense)
- *   dfm_shard_p2p_apply
- * "barrier" = any stream-ordered collective (the host uses a 4-byte all_reduce); no payload goes through NCCL. */
-/* EVAL / PREDICT on a row-sharded model: after requests -> serve (and the two exchanges) the forward pass alone;
- * rowbuf_dev NULL = the handle's own peer-memory row buffer (fused exchange). */
+/* EVAL / PREDICT on a row-sharded model (collective path): after requests -> serve (and the two exchanges) the
+ * forward pass alone on rowbuf_dev. */
 int dfm_shard_forward(dfm_handle* h, const dfm_raw_batch* dev_batch, const float* rowbuf_dev, float* logits_dev, void* stream);
-int dfm_shard_requests_dev(dfm_handle* h, const dfm_raw_batch* dev_batch, int32_t* counts_dev_out /* device int32[world] */, void* stream);
-/* Request prefetch: the requests of the NEXT batch (no model state involved) computed on the handle's side stream,
- * into a second buffer set, while the current step runs; dfm_shard_adopt_prefetch (same batch) then replaces the
- * dfm_shard_requests_dev call of that step and orders `stream` after the prefetch. */
-int dfm_shard_prefetch_requests(dfm_handle* h, const dfm_raw_batch* dev_batch, int32_t* counts_dev_out,
-                                void* after_stream /* stream that produced the batch, or NULL */);
-int dfm_shard_adopt_prefetch(dfm_handle* h, const dfm_raw_batch* dev_batch, void* stream);
-int dfm_shard_ipc_export(dfm_handle* h, unsigned char* handles_out /* 3 * 64 bytes */);
-int dfm_shard_ipc_import(dfm_handle* h, const unsigned char* all_handles /* world * 3 * 64 bytes, rank-major */);
-/* single-process hosts (several ranks on one GPU, as the tests do) wire the handles with raw pointers instead of IPC */
-int dfm_shard_p2p_buffers(dfm_handle* h, void** out3 /* {rows, gradient rows, row ids} */);
-int dfm_shard_p2p_set_peers(dfm_handle* h, void* const* ptrs /* world * 3, rank-major */);
-int dfm_shard_p2p_plan(dfm_handle* h, const int32_t* counts /* [world * world], source-major */, int64_t* n_recv_out, void* stream);
-int dfm_shard_p2p_push_ids(dfm_handle* h, void* stream);
-int dfm_shard_p2p_serve(dfm_handle* h, void* stream);
-int dfm_shard_p2p_forward_backward(dfm_handle* h, const dfm_raw_batch* dev_batch, int64_t global_batch, float* loss_dev,
-                                   float* logits_dev, float* dense_grad_dev, void* stream);
-int dfm_shard_p2p_apply(dfm_handle* h, const float* dense_grad_dev, void* stream);
+
+/* ---- The same sharded step with the exchanges FUSED into the kernels over NVLink peer memory and synchronised by
+ * flags in that memory (csrc/xchg.cuh): no collective, no host round trip, no count exchange.  Every rank owns one
+ * exchange region (fixed-capacity id / gradient-row segments per (source, owner), a row buffer, dense-gradient slots,
+ * flags) that is mapped into the other ranks through CUDA IPC (dfm_xchg_export / _import, handles exchanged by the host
+ * ONCE).  Producer kernels store into the consumer's region and stamp its flag (st.release.sys); the consumer's
+ * stream carries a one-warp wait kernel (ld.acquire.sys) in front of the kernel that reads the payload.
+ *   dfm_xchg_begin              K1 + owner-major unique rows of the local batch; ids -> the owners' regions
+ *   dfm_xchg_serve              | wait ids  | rows as of step t-1 -> the requesters' row buffers (train != 0: the
+ *                                            received ids are also sorted, on the handle's side stream, for the apply)
+ *   dfm_xchg_forward_backward   | wait rows | forward / loss / backward; per-unique-row gradient sums -> the owners'
+ *                                            regions; dense gradients + loss share -> every rank's dense slots
+ *   dfm_xchg_apply              | wait gradient rows | ordered reduction by row + sparse optimizer
+ *                               | wait dense         | sum of the slots in rank order + dense optimizer; step += 1;
+ *                                                      loss_out_dev [1] = global loss
+ *   dfm_xchg_train_step         the four phases back to back (one process per GPU: launches only)
+ *   dfm_xchg_forward            EVAL / PREDICT: after begin + serve(train = 0), the forward pass alone
+ * A host that runs all ranks in one process on one GPU (the tests) calls the phases rank by rank, so that a flag is
+ * always set before the kernel that waits for it starts.  A wait gives up after 4 s (a peer died): dfm_sync then
+ * reports DFM_ERR_PEER. */
+#define DFM_ERR_PEER          -8
+int dfm_xchg_export(dfm_handle* h, unsigned char* handle_out /* 64 bytes */);
+int dfm_xchg_import(dfm_handle* h, const unsigned char* all_handles /* world * 64 bytes, rank order */);
+int dfm_xchg_buffer(dfm_handle* h, void** region_out);
+int dfm_xchg_set_peers(dfm_handle* h, void* const* regions /* world, rank order */);
+int dfm_xchg_begin(dfm_handle* h, const dfm_raw_batch* dev_batch, void* stream);
+int dfm_xchg_serve(dfm_handle* h, int32_t train, void* stream);
+int dfm_xchg_forward_backward(dfm_handle* h, const dfm_raw_batch* dev_batch, int64_t global_batch, float* logits_dev, void* stream);
+int dfm_xchg_apply(dfm_handle* h, float* loss_out_dev, void* stream);
+int dfm_xchg_train_step(dfm_handle* h, const dfm_raw_batch* dev_batch, int64_t global_batch, float* loss_out_dev, float* logits_dev,
+                        void* stream);
+int dfm_xchg_forward(dfm_handle* h, const dfm_raw_batch* dev_batch, float* logits_dev, void* stream);
 
 /* Building-block entry points used by the parity tests (device pointers, synchronous). */
 int dfm_test_sort_pairs(uint32_t* keys_dev, uint32_t* vals_dev, int64_t n, int32_t key_bits);

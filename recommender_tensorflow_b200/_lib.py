@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdeepfm_b200.so")
 
 DFM_OK = 0
-ERRORS = {-1: "INVALID_ARG", -2: "CUDA", -3: "OUT_OF_RANGE", -4: "UNSUPPORTED", -5: "NCCL", -6: "NOT_FOUND"}
+ERRORS = {-1: "INVALID_ARG", -2: "CUDA", -3: "OUT_OF_RANGE", -4: "UNSUPPORTED", -5: "NCCL", -6: "NOT_FOUND", -7: "PARSE", -8: "PEER"}
 MAX_CAT, MAX_NUM, MAX_HIDDEN = 64, 64, 8
 
 COL_KIND = {"hash": 0, "bucketized": 1, "vocab": 2, "identity": 3}
@@ -63,6 +63,8 @@ _SIGS = {
     "dfm_flush": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dfm_sync": (C.c_int, [C.c_void_p]),
     "dfm_global_step": (C.c_int64, [C.c_void_p]),
+    "dfm_state_checksum": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "dfm_last_unique_rows": (C.c_int64, [C.c_void_p]),
     "dfm_set_global_step": (C.c_int, [C.c_void_p, C.c_int64]),
     "dfm_last_step_launches": (C.c_int64, [C.c_void_p]),
     "dfm_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -76,18 +78,16 @@ _SIGS = {
                                              C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfm_shard_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfm_shard_forward": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.c_void_p, C.c_void_p]),
-    "dfm_shard_requests_dev": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.c_void_p]),
-    "dfm_shard_prefetch_requests": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.c_void_p]),
-    "dfm_shard_adopt_prefetch": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p]),
-    "dfm_shard_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "dfm_shard_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "dfm_shard_p2p_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
-    "dfm_shard_p2p_set_peers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
-    "dfm_shard_p2p_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
-    "dfm_shard_p2p_push_ids": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "dfm_shard_p2p_serve": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "dfm_shard_p2p_forward_backward": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "dfm_shard_p2p_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dfm_xchg_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dfm_xchg_import": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dfm_xchg_buffer": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dfm_xchg_set_peers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dfm_xchg_begin": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p]),
+    "dfm_xchg_serve": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "dfm_xchg_forward_backward": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_int64, C.c_void_p, C.c_void_p]),
+    "dfm_xchg_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dfm_xchg_train_step": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dfm_xchg_forward": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.c_void_p]),
     "dfm_csv_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "dfm_csv_destroy": (None, [C.c_void_p]),
     "dfm_csv_last_error": (C.c_char_p, [C.c_void_p]),

@@ -18,6 +18,7 @@
 #include "small_mlp.cuh"
 #include "fused_small.cuh"
 #include "tc_gemm.cuh"
+#include "xchg.cuh"
 
 #ifndef TC_BK
 #define TC_BK 32   // k-block depth of the tcgen05 GEMMs (16 gives a deeper TMA ring; measured equal, smem bandwidth is the limit)
@@ -120,17 +121,19 @@ struct dfm_handle {
     uint32_t* uidx = nullptr;    // lookup -> index in the unique-row list of the local batch
     uint32_t* req_rows = nullptr;   // unique rows of the local batch as local indices at their owners (owner-major order)
     int32_t* d_counts = nullptr; int32_t* h_counts = nullptr;   // [world] unique rows per owner, [world] = total
-    // request state of the NEXT batch, computed ahead of time on the side stream (dfm_shard_prefetch_requests)
+    // state of the NEXT batch, computed ahead of time on the side stream (dfm_prefetch_batch)
     SegWS ws_next; int32_t* ids_next = nullptr; uint32_t *uidx_next = nullptr, *req_rows_next = nullptr; int32_t* d_counts_next = nullptr;
     cudaEvent_t ev_prefetch = nullptr; int prefetch_B = -1;
     cudaEvent_t ev_done[2] = {nullptr, nullptr};     // end of train step t on its stream, ring of two (t % 2)
     const void* prefetch_tag = nullptr;      // unsharded prefetch (dfm_prefetch_batch): first column pointer of the prefetched batch
     int64_t shard_n_req = 0, shard_n_recv = 0; int shard_B = 0; float shard_scale = 0.f;
-    // fused exchange over peer memory (CUDA IPC): own receive buffers + mapped peer buffers + routing table
-    float *p2p_rowbuf = nullptr, *p2p_grecv = nullptr; uint32_t* p2p_recv_rows = nullptr;
-    PeerRoute* h_route = nullptr; PeerRoute* d_route = nullptr; bool p2p_ready = false;
-    void* p2p_opened[3 * MAX_PEERS] = {nullptr};
-    OptDev shard_od{}, shard_ol{};
+    // flag-synchronised exchange over peer memory (xchg.cuh): own region + mapped peer regions
+    uint8_t* xreg = nullptr; size_t xreg_bytes = 0; XchgDev xd{}; bool x_ready = false;
+    void* x_opened[MAX_PEERS] = {nullptr};
+    uint32_t x_epoch = 0; unsigned int* x_ticket = nullptr;      // exchange rounds so far; tickets of the producer kernels
+    PeerRoute* d_xroute = nullptr; uint32_t* d_nrecv = nullptr; float* d_dense_total = nullptr; float* d_loss_part = nullptr;
+    bool xchg_pending = false;
+    cudaEvent_t ev_xfork = nullptr, ev_xjoin = nullptr; int x_B = -1; int64_t x_global_batch = 0; bool x_train = false;
     float *h0 = nullptr, *s = nullptr, *zacc = nullptr, *logits = nullptr, *dz = nullptr, *dE = nullptr;
     float* act[DFM_MAX_HIDDEN + 1] = {nullptr};
     float* dact[DFM_MAX_HIDDEN + 1] = {nullptr};
@@ -269,12 +272,10 @@ static void free_all(dfm_handle* h) {
     for (cudaEvent_t e : h->ev_done) if (e) cudaEventDestroy(e);
     { void* tp[] = {h->d_tiny_slot, h->d_key_slot, h->d_trow0, h->d_trow_grow, h->tiny_partial, h->d_tiny_cnt};
       for (void* p : tp) if (p) cudaFree(p); }
-    for (void* p : h->p2p_opened) if (p) cudaIpcCloseMemHandle(p);
-    if (h->p2p_rowbuf) cudaFree(h->p2p_rowbuf);
-    if (h->p2p_grecv) cudaFree(h->p2p_grecv);
-    if (h->p2p_recv_rows) cudaFree(h->p2p_recv_rows);
-    if (h->d_route) cudaFree(h->d_route);
-    if (h->h_route) cudaFreeHost(h->h_route);
+    for (void* p : h->x_opened) if (p) cudaIpcCloseMemHandle(p);
+    { void* xp[] = {h->xreg, h->x_ticket, h->d_xroute, h->d_nrecv, h->d_dense_total, h->d_loss_part}; for (void* p : xp) if (p) cudaFree(p); }
+    if (h->ev_xfork) cudaEventDestroy(h->ev_xfork);
+    if (h->ev_xjoin) cudaEventDestroy(h->ev_xjoin);
     for (int i = 1; i <= DFM_MAX_HIDDEN; ++i) { if (h->act[i]) cudaFree(h->act[i]); if (h->dact[i]) cudaFree(h->dact[i]); }
     for (auto& s : h->stage) {
         if (s.d_arena) cudaFree(s.d_arena);
@@ -538,15 +539,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
         if (dalloc(h, &h->req_rows, n)) return DFM_ERR_CUDA;
         if (dalloc(h, &h->d_counts, (size_t)h->world + 1)) return DFM_ERR_CUDA;
         CK(cudaMallocHost(&h->h_counts, ((size_t)h->world + 1) * sizeof(int32_t)));
-        if (h->world <= MAX_PEERS) {
-            const size_t rw = (size_t)K + 4;
-            if (dalloc(h, &h->p2p_rowbuf, (size_t)n * rw)) return DFM_ERR_CUDA;
-            if (dalloc(h, &h->p2p_grecv, (size_t)h->ws_own.cap * rw)) return DFM_ERR_CUDA;
-            if (dalloc(h, &h->p2p_recv_rows, (size_t)h->ws_own.cap)) return DFM_ERR_CUDA;
-            if (dalloc(h, &h->d_route, 1)) return DFM_ERR_CUDA;
-            CK(cudaMallocHost(&h->h_route, sizeof(PeerRoute)));
-            memset(h->h_route, 0, sizeof(PeerRoute));
-        }
+        h->xchg_pending = h->world <= MAX_PEERS;      // the exchange region is allocated below, once the dense size is known
     }
     if (h->fused) {       // does the fused kernel's tile fit in shared memory?
         SmallMlpDesc probe{};
@@ -694,6 +687,28 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     for (auto& e : h->ph_ev) CK(cudaEventCreate(&e));
     CK(cudaFuncSetAttribute(numeric_grad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->num_rows_per_chunk * (DFM_MAX_NUM + 1) * 4));
 
+    if (h->xchg_pending) {
+        // exchange region (xchg.cuh): fixed-capacity segments per (source, owner), rows, dense slots, flags
+        XchgDev& x = h->xd;
+        x.W = h->world; x.me = h->rank; x.cap = (uint32_t)n; x.rw = K + 4; x.nd1 = (int)((h->n_dense + 1 + 3) / 4 * 4);
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+        for (int par = 0; par < 2; ++par) x.off_ids[par] = take((size_t)x.W * x.cap * 4);
+        for (int par = 0; par < 2; ++par) x.off_hdr[par] = take((size_t)MAX_PEERS * 16);
+        x.off_grads = take((size_t)x.W * x.cap * x.rw * 4);
+        x.off_rows = take((size_t)x.cap * x.rw * 4);
+        x.off_dense = take((size_t)x.W * x.nd1 * 4);
+        x.off_flags = take((size_t)4 * MAX_PEERS * 4);
+        h->xreg_bytes = off;
+        CK(cudaMalloc(&h->xreg, off));
+        CK(cudaMemset(h->xreg + x.off_hdr[0], 0, off - x.off_hdr[0] > (x.off_grads - x.off_hdr[0]) ? (x.off_grads - x.off_hdr[0]) : 0));
+        CK(cudaMemset(h->xreg + x.off_dense, 0, off - x.off_dense));
+        if (dalloc(h, &h->x_ticket, 16) || dalloc(h, &h->d_xroute, 1) || dalloc(h, &h->d_nrecv, 4) ||
+            dalloc(h, &h->d_dense_total, (size_t)x.nd1) || dalloc(h, &h->d_loss_part, 4)) return DFM_ERR_CUDA;
+        CK(cudaMemset(h->x_ticket, 0, 16 * 4));
+        CK(cudaEventCreateWithFlags(&h->ev_xfork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_xjoin, cudaEventDisableTiming));
+    }
     // optimizer slot initial values (Adagrad / FTRL accumulators start at init_acc)
     auto init_acc = [&](const dfm_optimizer& o) { return (o.kind == DFM_OPT_ADAGRAD || o.kind == DFM_OPT_FTRL || o.kind == DFM_OPT_RMSPROP) ? o.init_acc : 0.f; };
     if (init_acc(h->od) != 0.f) {
@@ -815,7 +830,8 @@ extern "C" int dfm_init_random(dfm_handle* h, uint64_t seed) {
     if (h->need_emb && h->R_loc) {
         uint64_t tot = h->R_loc * (uint64_t)h->K;
         init_trunc_normal_kernel<<<cdiv((int64_t)tot, 256), 256, 0, st>>>(h->tb.rec, h->R_loc, h->K, h->tb.stride,
-                                                                          1.0f / sqrtf((float)h->K), seed * 0x9E3779B97F4A7C15ULL + 1);
+                                                                          1.0f / sqrtf((float)h->K), seed * 0x9E3779B97F4A7C15ULL + 1,
+                                                                          (uint64_t)h->world, (uint64_t)(h->world > 1 ? h->rank : 0));
     }
     int idx = 0;
     for (const DenseT& dt : h->dense) {
@@ -1317,13 +1333,15 @@ static int sparse_update(dfm_handle* h, SegWS& ws, int64_t n, const SRC& src, co
             static bool attr = false;
             if (!attr) { CK(cudaFuncSetAttribute(row_apply_kernel<K, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RowApplyCfg<K, S2>::SMEM)); attr = true; }
             S2 s2{}; s2.s = src;
-            row_apply_kernel<K, S2><<<n > 0 ? (unsigned)h->sm_count * 3 : 1, 256, RowApplyCfg<K, S2>::SMEM, st>>>(
+            row_apply_kernel<K, S2><<<n > 0 ? (unsigned)h->sm_count * 2 : 1, 256, RowApplyCfg<K, S2>::SMEM, st>>>(
                 ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0, ws.piece_start, ws.seg_cnt, s2, ws.piece_sum, h->tb, h->emb_slots, od, ol,
                 (bool)h->need_emb, (bool)h->use_linear, (int)t, make_rr(h, t - 1));
         } else if constexpr (!kBags) {
-            static bool attr = false;
-            if (!attr) { CK(cudaFuncSetAttribute(row_apply_kernel<K, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, RowApplyCfg<K, SRC>::SMEM)); attr = true; }
-            row_apply_kernel<K, SRC><<<n > 0 ? (unsigned)h->sm_count * 3 : 1, 256, RowApplyCfg<K, SRC>::SMEM, st>>>(
+            const int smem = RowApplyCfg<K, SRC>::SMEM + src.aux_floats() * 4;
+            if (smem > 200 * 1024) FAIL(DFM_ERR_UNSUPPORTED, "internal: staged sparse apply does not fit in shared memory");
+            static int attr = 0;
+            if (attr < smem) { CK(cudaFuncSetAttribute(row_apply_kernel<K, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = smem; }
+            row_apply_kernel<K, SRC><<<n > 0 ? (unsigned)h->sm_count * 2 : 1, 256, smem, st>>>(
                 ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0, ws.piece_start, ws.seg_cnt, src, ws.piece_sum, h->tb, h->emb_slots, od, ol,
                 (bool)h->need_emb, (bool)h->use_linear, (int)t, make_rr(h, t - 1));
         }
@@ -1433,6 +1451,7 @@ static GradSrcFused<K, H1> fused_src(const dfm_handle* h, const float* erow) {
     GradSrcFused<K, H1> src{};
     src.dh1 = h->dact[1]; src.s = h->use_mf ? h->s : nullptr; src.dz = h->dz; src.W0 = h->dw + h->sm.off_W[0];
     src.n_slots = h->dcs; src.erow = erow; src.erow_stride = K + 4;
+    src.n_w0 = h->sm.D * H1;
     return src;
 }
 
@@ -1639,7 +1658,7 @@ extern "C" int dfm_train_step(dfm_handle* h, const dfm_raw_batch* b, float* loss
 // following dfm_train_step on the same batch (same first column pointer and size) adopts the result.
 extern "C" int dfm_prefetch_batch(dfm_handle* h, const dfm_raw_batch* b, void* after_stream) {
     if (!h) return DFM_ERR_INVALID_ARG;
-    if (h->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "row-sharded handle: use dfm_shard_prefetch_requests");
+    if (h->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "row-sharded handle: no batch prefetch");
     int rc = check_batch(h, b, false);
     if (rc) return rc;
     if (h->dc == 0) return DFM_OK;
@@ -1706,12 +1725,52 @@ extern "C" int dfm_sync(dfm_handle* h) {
     }
     if (e) {
         CK(cudaMemset(h->d_err, 0, 4));
+        if (e & 2) FAIL(DFM_ERR_PEER, "exchange: a peer's flag did not arrive within 4 s");
+        if (e & 4) FAIL(DFM_ERR_UNSUPPORTED, "exchange: more rows for one owner than its segment / workspace holds (raise max_batch)");
         FAIL(DFM_ERR_OUT_OF_RANGE, "identity column value outside [0, num_buckets)");
     }
     return DFM_OK;
 }
 
 extern "C" int64_t dfm_global_step(const dfm_handle* h) { return h ? h->step : -1; }
+
+// order-independent checksum (sum of the 32-bit patterns, mod 2^64) of everything the handle trains: table records
+// (weights, optimizer slots, last_step) after materialising the deferred decay, and the dense parameters + slots
+__global__ void checksum_kernel(const uint32_t* __restrict__ p, size_t n, unsigned long long* __restrict__ out) {
+    unsigned long long acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += p[i];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+extern "C" int dfm_state_checksum(dfm_handle* h, uint64_t* out_host) {
+    if (!h || !out_host) return DFM_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = dfm_flush(h, h->stream);
+    if (rc) return rc;
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, 8));
+    CK(cudaMemsetAsync(d, 0, 8, h->stream));
+    const size_t nrec = (size_t)h->R_loc * h->tb.stride;
+    if (nrec) checksum_kernel<<<(unsigned)h->sm_count * 8, 256, 0, h->stream>>>(reinterpret_cast<const uint32_t*>(h->tb.rec), nrec, d);
+    for (const float* p : {h->dw, h->ds1, h->ds2})
+        if (h->n_dense) checksum_kernel<<<4, 256, 0, h->stream>>>(reinterpret_cast<const uint32_t*>(p), (size_t)h->n_dense, d);
+    unsigned long long v = 0;
+    CK(cudaMemcpyAsync(&v, d, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    *out_host = v;
+    return DFM_OK;
+}
+// unique table rows touched by the last step's batch (requester-side list when sharded); synchronises the handle's stream
+extern "C" int64_t dfm_last_unique_rows(dfm_handle* h) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    SegCounts sc{};
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(&sc, h->ws.seg_cnt, sizeof sc, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)sc.n_rows;
+}
 
 // Restore point: variables + slots were loaded with dfm_set_tensor from a checkpoint taken at `step`
 // (tables fully materialised, i.e. after dfm_flush).  Rebuilds what TF keeps in beta1_power / beta2_power /
@@ -1748,8 +1807,7 @@ extern "C" int dfm_num_slots(const dfm_handle* h) { return h ? h->dcs : -1; }
 extern "C" int64_t dfm_dense_size(const dfm_handle* h) { return h ? h->n_dense : -1; }
 
 template <int K>
-static int shard_requests_impl(dfm_handle* h, const BatchPtrs& bp, int B, uint32_t* req_rows_out, int32_t* counts_host, cudaStream_t st,
-                               int32_t* counts_dev_out = nullptr) {
+static int shard_requests_impl(dfm_handle* h, const BatchPtrs& bp, int B, uint32_t* req_rows_out, int32_t* counts_host, cudaStream_t st) {
     const int64_t n = (int64_t)B * h->dcs;
     const int64_t t = h->step + 1;
     int rc = ensure_alpha(h, t);
@@ -1764,13 +1822,6 @@ static int shard_requests_impl(dfm_handle* h, const BatchPtrs& bp, int B, uint32
     if (n > 0) {
         shard_uniq_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->ws.skeys(), h->ws.svals(), n, limit, h->Rl, W, h->dcs, h->ws.pos_row, h->uidx, h->req_rows, h->d_counts);
         h->launches++;
-    }
-    if (!counts_host) {    // asynchronous variant: the counts stay on the device, dfm_shard_p2p_plan learns them from the matrix
-        CK(cudaMemcpyAsync(counts_dev_out, h->d_counts, (size_t)W * 4, cudaMemcpyDeviceToDevice, st));
-        h->shard_n_req = -1; h->shard_B = B;
-        h->last_step_launches += h->launches - l0;
-        CK(cudaGetLastError());
-        return DFM_OK;
     }
     CK(cudaMemcpyAsync(h->h_counts, h->d_counts, (size_t)W * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1796,8 +1847,7 @@ extern "C" int dfm_shard_requests(dfm_handle* h, const dfm_raw_batch* b, uint32_
 }
 
 template <int K>
-static int shard_serve_impl(dfm_handle* h, const uint32_t* recv_rows, int64_t n_recv, float* reply, cudaStream_t st,
-                            const PeerRoute* route = nullptr) {
+static int shard_serve_impl(dfm_handle* h, const uint32_t* recv_rows, int64_t n_recv, float* reply, cudaStream_t st) {
     if (n_recv > h->ws_own.cap) FAIL(DFM_ERR_UNSUPPORTED, "more row requests than the owner workspace holds (raise max_batch)");
     const int64_t l0 = h->launches;
     const int64_t t = h->step + 1;
@@ -1815,10 +1865,8 @@ static int shard_serve_impl(dfm_handle* h, const uint32_t* recv_rows, int64_t n_
     if (n_recv > 0) {
         const RowReplay rr = make_rr(h, t - 1);
         const OptDev od = make_opt(h->od, 0.f), ol = make_opt(h->ol, 0.f);
-        if (route) shard_serve_p2p_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(recv_rows, n_recv, h->tb, (bool)h->need_emb,
-                                                                                        (bool)h->use_linear, route, rr, od, ol);
-        else shard_serve_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(recv_rows, n_recv, h->tb, (bool)h->need_emb,
-                                                                              (bool)h->use_linear, reply, K + 4, rr, od, ol);
+        shard_serve_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(recv_rows, n_recv, h->tb, (bool)h->need_emb,
+                                                                         (bool)h->use_linear, reply, K + 4, rr, od, ol);
         h->launches++;
     }
     h->shard_n_recv = n_recv;
@@ -1887,58 +1935,6 @@ extern "C" int dfm_shard_forward_backward(dfm_handle* h, const dfm_raw_batch* b,
     return rc;
 }
 
-// ---- request prefetch -------------------------------------------------------------------------------------------
-// dfm_shard_requests touches no model state (transform, owner-major sort, unique rows), so the requests of batch t+1
-// can be computed while step t is still running: on the handle's side stream, into a second set of buffers.  The
-// work fills the gaps the step leaves (count exchange, barriers, small kernels).  dfm_shard_adopt_prefetch makes the
-// prefetched set the current one in place of a dfm_shard_requests[_dev] call.
-static void swap_request_state(dfm_handle* h) {
-    std::swap(h->ws, h->ws_next); std::swap(h->ids, h->ids_next); std::swap(h->uidx, h->uidx_next);
-    std::swap(h->req_rows, h->req_rows_next); std::swap(h->d_counts, h->d_counts_next);
-}
-
-extern "C" int dfm_shard_prefetch_requests(dfm_handle* h, const dfm_raw_batch* b, int32_t* counts_dev_out, void* after_stream) {
-    if (!h || !counts_dev_out) return DFM_ERR_INVALID_ARG;
-    if (h->world < 2) FAIL(DFM_ERR_INVALID_ARG, "handle was not created with world > 1");
-    int rc = check_batch(h, b, false);
-    if (rc) return rc;
-    CK(cudaSetDevice(h->device));
-    if (!h->ws_next.cap) {       // first use: the second buffer set
-        const int64_t n = (int64_t)h->max_batch * std::max(h->dcs, 1);
-        if (alloc_ws(h, h->ws_next, n, h->K, true) || dalloc(h, &h->ids_next, (size_t)n) || dalloc(h, &h->uidx_next, (size_t)n) ||
-            dalloc(h, &h->req_rows_next, (size_t)n) || dalloc(h, &h->d_counts_next, (size_t)h->world + 1))
-            return DFM_ERR_CUDA;
-        CK(cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming));
-    }
-    if (after_stream) {          // the batch (e.g. its H2D copy) was produced on the caller's stream
-        CK(cudaEventRecord(h->ev_prefetch, (cudaStream_t)after_stream));
-        CK(cudaStreamWaitEvent(h->side_stream, h->ev_prefetch, 0));
-    }
-    BatchPtrs bp = make_ptrs(h, b);
-    const int64_t keep_req = h->shard_n_req, keep_launches = h->last_step_launches; const int keep_B = h->shard_B;
-    swap_request_state(h);        // the kernels below capture the pointers of the second set at launch
-    DISPATCH_K(h, rc = shard_requests_impl<KK>(h, bp, b->batch_size, nullptr, nullptr, h->side_stream, counts_dev_out));
-    swap_request_state(h);
-    h->shard_n_req = keep_req; h->shard_B = keep_B; h->last_step_launches = keep_launches;
-    if (rc) return rc;
-    CK(cudaEventRecord(h->ev_prefetch, h->side_stream));
-    h->prefetch_B = b->batch_size;
-    return DFM_OK;
-}
-
-extern "C" int dfm_shard_adopt_prefetch(dfm_handle* h, const dfm_raw_batch* b, void* stream) {
-    if (!h) return DFM_ERR_INVALID_ARG;
-    if (h->prefetch_B < 0) FAIL(DFM_ERR_INVALID_ARG, "no prefetched requests");
-    if (!b || b->batch_size != h->prefetch_B) FAIL(DFM_ERR_INVALID_ARG, "batch differs from the one given to dfm_shard_prefetch_requests");
-    CK(cudaSetDevice(h->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    CK(cudaStreamWaitEvent(st, h->ev_prefetch, 0));
-    swap_request_state(h);
-    h->shard_n_req = -1; h->shard_B = h->prefetch_B; h->prefetch_B = -1;
-    h->last_step_launches = 0;
-    return DFM_OK;
-}
-
 // mode == EVAL / PREDICT on a row-sharded model: the rows were requested and served exactly as for a train step
 // (requests -> exchange -> serve -> exchange); this is the forward pass alone, no state changes.
 extern "C" int dfm_shard_forward(dfm_handle* h, const dfm_raw_batch* b, const float* rowbuf_dev, float* logits_dev, void* stream) {
@@ -1947,13 +1943,13 @@ extern "C" int dfm_shard_forward(dfm_handle* h, const dfm_raw_batch* b, const fl
     int rc = check_batch(h, b, false);
     if (rc) return rc;
     if (b->batch_size != h->shard_B) FAIL(DFM_ERR_INVALID_ARG, "batch differs from the one given to dfm_shard_requests");
-    if (!rowbuf_dev && !h->p2p_ready) FAIL(DFM_ERR_INVALID_ARG, "rowbuf_dev is null and the peer-memory exchange is not set up");
+    if (!rowbuf_dev) FAIL(DFM_ERR_INVALID_ARG, "rowbuf_dev is null");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     BatchPtrs bp = make_ptrs(h, b);
     bp.labels = nullptr;
     const int64_t l0 = h->launches;
-    DISPATCH_K(h, rc = eval_forward<KK>(h, bp, b->batch_size, logits_dev, rowbuf_dev ? rowbuf_dev : h->p2p_rowbuf, st));
+    DISPATCH_K(h, rc = eval_forward<KK>(h, bp, b->batch_size, logits_dev, rowbuf_dev, st));
     h->last_step_launches += h->launches - l0;
     if (rc) return rc;
     CK(cudaGetLastError());
@@ -1990,153 +1986,239 @@ extern "C" int dfm_shard_apply(dfm_handle* h, const float* grecv_dev, const floa
     return rc;
 }
 
-// Same as dfm_shard_requests without the host round trip: the per-owner counts are left in counts_dev_out (device,
-// int32[world]) for the host's all_gather; the fused-exchange path reads them back once, as the W x W matrix.
-extern "C" int dfm_shard_requests_dev(dfm_handle* h, const dfm_raw_batch* b, int32_t* counts_dev_out, void* stream) {
-    if (!h || !counts_dev_out) return DFM_ERR_INVALID_ARG;
-    if (h->world < 2) FAIL(DFM_ERR_INVALID_ARG, "handle was not created with world > 1");
-    int rc = check_batch(h, b, false);
-    if (rc) return rc;
-    CK(cudaSetDevice(h->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    BatchPtrs bp = make_ptrs(h, b);
-    DISPATCH_K(h, rc = shard_requests_impl<KK>(h, bp, b->batch_size, nullptr, nullptr, st, counts_dev_out));
-    return rc;
-}
-
-// ---- fused exchange over NVLink peer memory -------------------------------------------------------
-// The three receive buffers of every rank (row ids, rows, gradient rows) are cudaMalloc'ed by the library and
-// mapped into every other rank's address space through CUDA IPC.  The requests, the served rows and the
-// gradient rows are then STORED by the producing kernel directly at their destination on the peer GPU; the
-// host only exchanges the W x W count matrix and places stream-ordered barriers (a tiny all-reduce).
-extern "C" int dfm_shard_ipc_export(dfm_handle* h, unsigned char* out /* 3 * 64 bytes */) {
+// ---- flag-synchronised exchange over NVLink peer memory (xchg.cuh) ---------------------------------
+extern "C" int dfm_xchg_export(dfm_handle* h, unsigned char* out /* 64 bytes */) {
     if (!h || !out) return DFM_ERR_INVALID_ARG;
-    if (h->world < 2 || !h->p2p_rowbuf) FAIL(DFM_ERR_UNSUPPORTED, "handle has no peer-exchange buffers");
+    if (h->world < 2 || !h->xreg) FAIL(DFM_ERR_UNSUPPORTED, "handle has no exchange region");
     CK(cudaSetDevice(h->device));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    void* bufs[3] = {h->p2p_rowbuf, h->p2p_grecv, h->p2p_recv_rows};
-    for (int i = 0; i < 3; ++i) {
-        cudaIpcMemHandle_t mh;
-        CK(cudaIpcGetMemHandle(&mh, bufs[i]));
-        memcpy(out + 64 * i, &mh, 64);
-    }
+    cudaIpcMemHandle_t mh;
+    CK(cudaIpcGetMemHandle(&mh, h->xreg));
+    memcpy(out, &mh, 64);
     return DFM_OK;
 }
 
-// Raw device pointers of this rank's receive buffers {rows, gradient rows, row ids} and the peer table.  A host that
-// runs several ranks inside ONE process (the single-GPU emulation used by the tests) wires the handles together with
-// these two calls; separate processes use the IPC pair, which ends in the same table.
-extern "C" int dfm_shard_p2p_buffers(dfm_handle* h, void** out3) {
-    if (!h || !out3) return DFM_ERR_INVALID_ARG;
-    if (h->world < 2 || !h->p2p_rowbuf) FAIL(DFM_ERR_UNSUPPORTED, "handle has no peer-exchange buffers");
-    out3[0] = h->p2p_rowbuf; out3[1] = h->p2p_grecv; out3[2] = h->p2p_recv_rows;
+// Raw device pointer of this rank's exchange region / the table of all ranks' regions.  A host that runs several
+// ranks inside ONE process (the single-GPU emulation used by the tests) wires the handles together with these two
+// calls; separate processes use the IPC pair, which ends in the same table.
+extern "C" int dfm_xchg_buffer(dfm_handle* h, void** out) {
+    if (!h || !out) return DFM_ERR_INVALID_ARG;
+    if (h->world < 2 || !h->xreg) FAIL(DFM_ERR_UNSUPPORTED, "handle has no exchange region");
+    *out = h->xreg;
     return DFM_OK;
 }
 
-extern "C" int dfm_shard_p2p_set_peers(dfm_handle* h, void* const* ptrs /* world * 3, rank-major */) {
-    if (!h || !ptrs) return DFM_ERR_INVALID_ARG;
-    if (h->world < 2 || !h->p2p_rowbuf) FAIL(DFM_ERR_UNSUPPORTED, "handle has no peer-exchange buffers");
-    PeerRoute* r = h->h_route;
-    r->W = h->world; r->me = h->rank;
+extern "C" int dfm_xchg_set_peers(dfm_handle* h, void* const* regions /* world, rank order */) {
+    if (!h || !regions) return DFM_ERR_INVALID_ARG;
+    if (h->world < 2 || !h->xreg) FAIL(DFM_ERR_UNSUPPORTED, "handle has no exchange region");
     for (int p = 0; p < h->world; ++p) {
-        const bool me = p == h->rank;
-        r->peer_rowbuf[p] = me ? h->p2p_rowbuf : reinterpret_cast<float*>(ptrs[p * 3 + 0]);
-        r->peer_grecv[p] = me ? h->p2p_grecv : reinterpret_cast<float*>(ptrs[p * 3 + 1]);
-        r->peer_recv_rows[p] = me ? h->p2p_recv_rows : reinterpret_cast<uint32_t*>(ptrs[p * 3 + 2]);
-        if (!r->peer_rowbuf[p] || !r->peer_grecv[p] || !r->peer_recv_rows[p]) FAIL(DFM_ERR_INVALID_ARG, "null peer buffer");
+        h->xd.peer[p] = p == h->rank ? h->xreg : reinterpret_cast<uint8_t*>(regions[p]);
+        if (!h->xd.peer[p]) FAIL(DFM_ERR_INVALID_ARG, "null peer region");
     }
-    h->p2p_ready = true;
+    h->x_ready = true;
     return DFM_OK;
 }
 
-extern "C" int dfm_shard_ipc_import(dfm_handle* h, const unsigned char* all /* world * 3 * 64 bytes, rank-major */) {
+extern "C" int dfm_xchg_import(dfm_handle* h, const unsigned char* all /* world * 64 bytes, rank order */) {
     if (!h || !all) return DFM_ERR_INVALID_ARG;
-    if (h->world < 2 || !h->p2p_rowbuf) FAIL(DFM_ERR_UNSUPPORTED, "handle has no peer-exchange buffers");
+    if (h->world < 2 || !h->xreg) FAIL(DFM_ERR_UNSUPPORTED, "handle has no exchange region");
     CK(cudaSetDevice(h->device));
-    void* ptrs[3 * MAX_PEERS] = {nullptr};
+    void* ptrs[MAX_PEERS] = {nullptr};
     for (int p = 0; p < h->world; ++p) {
-        if (p == h->rank) continue;
-        for (int i = 0; i < 3; ++i) {
+        if (p == h->rank) { ptrs[p] = h->xreg; continue; }
+        if (!h->x_opened[p]) {
             cudaIpcMemHandle_t mh;
-            memcpy(&mh, all + ((size_t)p * 3 + i) * 64, 64);
-            if (h->p2p_opened[p * 3 + i]) { ptrs[p * 3 + i] = h->p2p_opened[p * 3 + i]; continue; }
-            CK(cudaIpcOpenMemHandle(&ptrs[p * 3 + i], mh, cudaIpcMemLazyEnablePeerAccess));
-            h->p2p_opened[p * 3 + i] = ptrs[p * 3 + i];
+            memcpy(&mh, all + (size_t)p * 64, 64);
+            CK(cudaIpcOpenMemHandle(&h->x_opened[p], mh, cudaIpcMemLazyEnablePeerAccess));
         }
+        ptrs[p] = h->x_opened[p];
     }
-    ptrs[h->rank * 3 + 0] = h->p2p_rowbuf; ptrs[h->rank * 3 + 1] = h->p2p_grecv; ptrs[h->rank * 3 + 2] = h->p2p_recv_rows;
-    return dfm_shard_p2p_set_peers(h, ptrs);
+    return dfm_xchg_set_peers(h, ptrs);
 }
 
-// counts[s * W + o] = unique rows source s requests from owner o (all_gather of every rank's dfm_shard_requests counts)
-extern "C" int dfm_shard_p2p_plan(dfm_handle* h, const int32_t* counts, int64_t* n_recv_out, void* stream) {
-    if (!h || !counts) return DFM_ERR_INVALID_ARG;
-    if (!h->p2p_ready) FAIL(DFM_ERR_INVALID_ARG, "call dfm_shard_ipc_import first");
-    CK(cudaSetDevice(h->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    const int W = h->world, me = h->rank;
-    PeerRoute* r = h->h_route;
-    CK(cudaStreamSynchronize(st));     // the previous step's copy of the table must have been consumed
-    uint32_t acc = 0;
-    for (int o = 0; o < W; ++o) { r->send_off[o] = acc; acc += (uint32_t)counts[me * W + o]; }
-    r->send_off[W] = acc;
-    for (int o = 0; o < W; ++o) { uint32_t d = 0; for (int s2 = 0; s2 < me; ++s2) d += (uint32_t)counts[s2 * W + o]; r->dst_off[o] = d; }
-    acc = 0;
-    for (int s2 = 0; s2 < W; ++s2) { r->recv_off[s2] = acc; acc += (uint32_t)counts[s2 * W + me]; }
-    r->recv_off[W] = acc;
-    for (int s2 = 0; s2 < W; ++s2) { uint32_t d = 0; for (int o = 0; o < me; ++o) d += (uint32_t)counts[s2 * W + o]; r->reply_off[s2] = d; }
-    if ((int64_t)acc > h->ws_own.cap) FAIL(DFM_ERR_UNSUPPORTED, "more row requests than the owner workspace holds (raise max_batch)");
-    if (h->shard_n_req < 0) h->shard_n_req = r->send_off[W];      // dfm_shard_requests_dev: the matrix is the first the host sees
-    if ((int64_t)r->send_off[W] != h->shard_n_req) FAIL(DFM_ERR_INVALID_ARG, "count matrix does not match dfm_shard_requests");
-    if (h->shard_n_req > (int64_t)h->ws.cap) FAIL(DFM_ERR_INVALID_ARG, "count matrix exceeds the batch workspace");
-    CK(cudaMemcpyAsync(h->d_route, r, sizeof(PeerRoute), cudaMemcpyHostToDevice, st));
-    h->shard_n_recv = acc;
-    if (n_recv_out) *n_recv_out = acc;
-    return DFM_OK;
-}
-
-extern "C" int dfm_shard_p2p_push_ids(dfm_handle* h, void* stream) {
-    if (!h || !h->p2p_ready) return DFM_ERR_INVALID_ARG;
-    CK(cudaSetDevice(h->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    if (h->shard_n_req > 0) {
-        p2p_push_ids_kernel<<<cdiv(h->shard_n_req, 256), 256, 0, st>>>(h->req_rows, (uint32_t)h->shard_n_req, h->d_route);
-        h->launches++; h->last_step_launches++;
-    }
+static int xchg_wait(dfm_handle* h, int kind, cudaStream_t st) {
+    xchg_wait_kernel<<<1, 32, 0, st>>>(h->xd, kind, h->x_epoch, h->d_err);
+    h->launches++;
     CK(cudaGetLastError());
     return DFM_OK;
 }
 
-extern "C" int dfm_shard_p2p_serve(dfm_handle* h, void* stream) {
-    if (!h || !h->p2p_ready) return DFM_ERR_INVALID_ARG;
-    CK(cudaSetDevice(h->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    int rc = DFM_OK;
-    DISPATCH_K(h, rc = shard_serve_impl<KK>(h, h->p2p_recv_rows, h->shard_n_recv, nullptr, st, h->d_route));
-    return rc;
+// phase 1: transform + owner-major unique rows of the local batch, ids pushed into the owners' regions
+template <int K>
+static int xchg_begin_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t st) {
+    const int64_t n = (int64_t)B * h->dcs;
+    int rc = ensure_alpha(h, h->step + 1);
+    if (rc) return rc;
+    h->last_step_launches = 0;
+    const int64_t l0 = h->launches;
+    const uint32_t W = (uint32_t)h->world, limit = W * h->Rl;
+    launch_transform<K>(h, bp, B, true, h->ids, st);
+    if (n > 0) { shard_rekey_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->ws.keys[0], n, (uint32_t)h->R, W, h->Rl); h->launches++; }
+    if ((rc = build_segments(h, h->ws, n, limit, h->key_bits, st, nullptr))) return rc;
+    CK(cudaMemsetAsync(h->d_counts, 0, ((size_t)W + 1) * 4, st));
+    if (n > 0) {
+        shard_uniq_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->ws.skeys(), h->ws.svals(), n, limit, h->Rl, W, h->dcs, h->ws.pos_row, h->uidx, h->req_rows, h->d_counts);
+        h->launches++;
+    }
+    h->x_epoch += 1;
+    xchg_push_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(std::max<int64_t>(n, 1), 256), (int64_t)h->sm_count * 8)), 256, 0, st>>>(
+        h->xd, (int)(h->x_epoch & 1), h->x_epoch, h->req_rows, h->d_counts, h->d_xroute, h->x_ticket + 0, h->d_err);
+    h->launches++;
+    h->x_B = B; h->shard_B = B;
+    h->last_step_launches += h->launches - l0;
+    CK(cudaGetLastError());
+    return DFM_OK;
 }
 
-extern "C" int dfm_shard_p2p_forward_backward(dfm_handle* h, const dfm_raw_batch* b, int64_t global_batch, float* loss_dev,
-                                              float* logits_dev, float* dense_grad_dev, void* stream) {
-    if (!h || global_batch <= 0 || !h->p2p_ready) return DFM_ERR_INVALID_ARG;
-    int rc = check_batch(h, b, true);
+// phase 2: serve the rows my peers asked for; on the side stream, sort their ids for the gradient reduction
+template <int K>
+static int xchg_serve_impl(dfm_handle* h, bool train, cudaStream_t st) {
+    const int64_t l0 = h->launches;
+    const int64_t t = h->step + 1;
+    const int par = (int)(h->x_epoch & 1);
+    int rc = xchg_wait(h, XF_IDS, st);
     if (rc) return rc;
-    if (b->batch_size != h->shard_B) FAIL(DFM_ERR_INVALID_ARG, "batch differs from the one given to dfm_shard_requests");
+    if (train) {       // owner-side sort + segments of the received ids: beside the serve / forward / backward kernels
+        CK(cudaEventRecord(h->ev_xfork, st));
+        CK(cudaStreamWaitEvent(h->side_stream, h->ev_xfork, 0));
+        int bits = 1;
+        while ((1ull << bits) <= h->R_loc) ++bits;
+        xchg_owner_keys_kernel<<<(unsigned)h->sm_count * 4, 256, 0, h->side_stream>>>(h->xd, par, h->ws_own.keys[0], h->ws_own.vals[0], (uint32_t)h->ws_own.cap,
+                                                                                       h->d_nrecv, h->d_err);
+        h->launches++;
+        if ((rc = build_segments(h, h->ws_own, h->ws_own.cap, (uint32_t)h->R_loc, bits, h->side_stream, nullptr, h->d_nrecv))) return rc;
+        CK(cudaEventRecord(h->ev_xjoin, h->side_stream));
+    }
+    xchg_serve_kernel<K><<<(unsigned)h->sm_count * 8, 256, 0, st>>>(h->xd, par, h->x_epoch, h->tb, (bool)h->need_emb, (bool)h->use_linear,
+                                                                    make_rr(h, t - 1), make_opt(h->od, 0.f), make_opt(h->ol, 0.f), h->x_ticket + 1);
+    h->launches++;
+    h->last_step_launches += h->launches - l0;
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+// phase 3: forward / loss / backward from the served rows; gradient rows straight into the owners' regions; dense push
+template <int K>
+static int xchg_fb_impl(dfm_handle* h, const BatchPtrs& bp, int B, int64_t global_batch, float* logits_out, cudaStream_t st) {
+    const int64_t l0 = h->launches;
+    int rc = xchg_wait(h, XF_ROWS, st);
+    if (rc) return rc;
+    float* rowbuf = reinterpret_cast<float*>(h->xreg + h->xd.off_rows);
+    if ((rc = shard_fb_impl<K>(h, bp, B, rowbuf, global_batch, h->d_loss_part, logits_out, rowbuf /*non-null: gradient-row mode*/, nullptr, st, h->d_xroute)))
+        return rc;
+    xchg_signal_kernel<<<1, 32, 0, st>>>(h->xd, XF_GRADS, h->x_epoch, h->x_ticket + 2);
+    xchg_dense_push_kernel<<<dim3(cdiv(h->n_dense + 1, 256), (unsigned)h->world), 256, 0, st>>>(h->xd, h->x_epoch, h->dg, (int)h->n_dense, h->d_loss_part,
+                                                                                              h->x_ticket + 3);
+    h->launches += 2;
+    h->last_step_launches += h->launches - l0;
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+// phase 4: ordered reduction of the received gradient rows + sparse optimizer; dense all-reduce (rank order) + dense optimizer
+template <int K>
+static int xchg_apply_impl(dfm_handle* h, float* loss_out, cudaStream_t st) {
+    const int64_t l0 = h->launches;
+    const int64_t t = h->step + 1;
+    const StepOpts so = step_opts(h);
+    int rc = xchg_wait(h, XF_GRADS, st);
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(st, h->ev_xjoin, 0));
+    GradSrc<K, false> src{};
+    src.dE = nullptr; src.dz = nullptr; src.dc = 1; src.dK = 0; src.flat = reinterpret_cast<const float*>(h->xreg + h->xd.off_grads);
+    src.flat_stride = K + 4; src.n_slots = 1; src.slot_field = nullptr; src.inv_cnt = nullptr;
+    if ((rc = sparse_update<K, GradSrc<K, false>>(h, h->ws_own, h->ws_own.cap, src, so.od, so.ol, t, nullptr, st, nullptr))) return rc;
+    if ((rc = xchg_wait(h, XF_DENSE, st))) return rc;
+    xchg_dense_sum_kernel<<<cdiv(h->n_dense + 1, 256), 256, 0, st>>>(h->xd, (int)h->n_dense, h->d_dense_total, loss_out);
+    h->launches++;
+    if (h->n_dense) {
+        dense_apply_kernel<<<cdiv(h->n_dense, 256), 256, 0, st>>>(h->dw, h->ds1, h->ds2, h->d_dense_total, h->n_deep, h->n_dense, so.od, so.ol);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    commit_step(h, so, t);
+    h->last_step_launches += h->launches - l0;
+    return DFM_OK;
+}
+
+static int xchg_check(dfm_handle* h) {
+    if (h->world < 2 || !h->xreg) FAIL(DFM_ERR_INVALID_ARG, "handle was not created with 1 < world <= 16");
+    if (!h->x_ready) FAIL(DFM_ERR_INVALID_ARG, "call dfm_xchg_import / dfm_xchg_set_peers first");
+    return DFM_OK;
+}
+
+extern "C" int dfm_xchg_begin(dfm_handle* h, const dfm_raw_batch* b, void* stream) {
+    if (!h) return DFM_ERR_INVALID_ARG;
+    int rc = xchg_check(h);
+    if (rc) return rc;
+    if ((rc = check_batch(h, b, false))) return rc;
     CK(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     BatchPtrs bp = make_ptrs(h, b);
-    DISPATCH_K(h, rc = shard_fb_impl<KK>(h, bp, b->batch_size, h->p2p_rowbuf, global_batch, loss_dev, logits_dev, h->p2p_grecv /*non-null: gsum mode*/,
-                                         dense_grad_dev, st, h->d_route));
+    DISPATCH_K(h, rc = xchg_begin_impl<KK>(h, bp, b->batch_size, st));
     return rc;
 }
 
-extern "C" int dfm_shard_p2p_apply(dfm_handle* h, const float* dense_grad_dev, void* stream) {
-    if (!h || !h->p2p_ready) return DFM_ERR_INVALID_ARG;
+extern "C" int dfm_xchg_serve(dfm_handle* h, int32_t train, void* stream) {
+    if (!h) return DFM_ERR_INVALID_ARG;
+    int rc = xchg_check(h);
+    if (rc) return rc;
     CK(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    int rc = DFM_OK;
-    DISPATCH_K(h, rc = shard_apply_impl<KK>(h, h->p2p_grecv, dense_grad_dev, st));
+    DISPATCH_K(h, rc = xchg_serve_impl<KK>(h, train != 0, st));
     return rc;
+}
+
+extern "C" int dfm_xchg_forward_backward(dfm_handle* h, const dfm_raw_batch* b, int64_t global_batch, float* logits_dev, void* stream) {
+    if (!h || global_batch <= 0) return DFM_ERR_INVALID_ARG;
+    int rc = xchg_check(h);
+    if (rc) return rc;
+    if ((rc = check_batch(h, b, true))) return rc;
+    if (b->batch_size != h->x_B) FAIL(DFM_ERR_INVALID_ARG, "batch differs from the one given to dfm_xchg_begin");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    BatchPtrs bp = make_ptrs(h, b);
+    DISPATCH_K(h, rc = xchg_fb_impl<KK>(h, bp, b->batch_size, global_batch, logits_dev, st));
+    return rc;
+}
+
+extern "C" int dfm_xchg_apply(dfm_handle* h, float* loss_out_dev, void* stream) {
+    if (!h) return DFM_ERR_INVALID_ARG;
+    int rc = xchg_check(h);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    DISPATCH_K(h, rc = xchg_apply_impl<KK>(h, loss_out_dev, st));
+    return rc;
+}
+
+// mode == EVAL / PREDICT: after dfm_xchg_begin + dfm_xchg_serve(train = 0) the forward pass alone on the served rows
+extern "C" int dfm_xchg_forward(dfm_handle* h, const dfm_raw_batch* b, float* logits_dev, void* stream) {
+    if (!h || !logits_dev) return DFM_ERR_INVALID_ARG;
+    int rc = xchg_check(h);
+    if (rc) return rc;
+    if ((rc = check_batch(h, b, false))) return rc;
+    if (b->batch_size != h->x_B) FAIL(DFM_ERR_INVALID_ARG, "batch differs from the one given to dfm_xchg_begin");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    BatchPtrs bp = make_ptrs(h, b);
+    bp.labels = nullptr;
+    const int64_t l0 = h->launches;
+    if ((rc = xchg_wait(h, XF_ROWS, st))) return rc;
+    DISPATCH_K(h, rc = eval_forward<KK>(h, bp, b->batch_size, logits_dev, reinterpret_cast<float*>(h->xreg + h->xd.off_rows), st));
+    h->last_step_launches += h->launches - l0;
+    return rc;
+}
+
+// One whole step for a one-process-per-GPU host: the four phases back to back on `stream`, nothing but kernel
+// launches (no collective, no host synchronisation); the peers' kernels meet through the flags.
+extern "C" int dfm_xchg_train_step(dfm_handle* h, const dfm_raw_batch* b, int64_t global_batch, float* loss_out_dev, float* logits_dev,
+                                   void* stream) {
+    int rc = dfm_xchg_begin(h, b, stream);
+    if (rc) return rc;
+    if ((rc = dfm_xchg_serve(h, 1, stream))) return rc;
+    if ((rc = dfm_xchg_forward_backward(h, b, global_batch, logits_dev, stream))) return rc;
+    return dfm_xchg_apply(h, loss_out_dev, stream);
 }
 
 // --------------------------------------------------------------------------- host entry points

@@ -1122,67 +1122,3 @@ __global__ void __launch_bounds__(256) shard_serve_kernel(const uint32_t* __rest
         if (sub == 0) rp[K] = has_lin ? lw : 0.f;
     }
 }
-
-// Owner side of the fused exchange: same rows, but stored straight into the requesters' row buffers over NVLink.
-// Entry i of the receive list goes to row (reply_off[src] + i - recv_off[src]) of source src's buffer, so consecutive
-// entries of one source are CONTIGUOUS at the destination.  A warp therefore stages 32 rows in shared memory and
-// writes them as full 512-byte store instructions (32 rows per chunk; 16 at K = 64) (NVLink moves 64-byte row fragments with holes at a fraction of the
-// bandwidth of full lines); only the chunks that straddle two sources take the row-by-row path.
-template <int K>
-__global__ void __launch_bounds__(256) shard_serve_p2p_kernel(const uint32_t* __restrict__ recv_rows, int64_t n,
-                                                              Table tb, bool has_emb, bool has_lin,
-                                                              const PeerRoute* __restrict__ rt, RowReplay rr, OptDev od, OptDev ol) {
-    constexpr int LPR = K / 4, RPP = 32 / LPR, CH = (1024 / K < 32 ? 1024 / K : 32) /* rows per chunk, bounded by shared memory */, PASSES = CH / RPP, RW = K + 4, RW4 = RW / 4;
-    __shared__ __align__(16) float tile[8][CH * RW];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
-    const ReplayStep rs = replay_step_load(rr.rd.closed ? rr.rd : rr.rl, rr.upto);
-    float* tl = tile[warp];
-    const int64_t n_chunks = (n + CH - 1) / CH;
-    for (int64_t chunk = (int64_t)blockIdx.x * 8 + warp; chunk < n_chunks; chunk += (int64_t)gridDim.x * 8) {
-        const int64_t i0 = chunk * CH;
-        const int cnt = (int)min((int64_t)CH, n - i0);
-        float4 e[PASSES];
-        float l[PASSES];
-#pragma unroll
-        for (int p = 0; p < PASSES; ++p) {
-            const int r = p * RPP + grp;
-            e[p] = make_float4(0.f, 0.f, 0.f, 0.f); l[p] = 0.f;
-            if (r < cnt) {
-                const size_t row = __ldg(recv_rows + i0 + r);
-                load_row_current(tb, row, sub, has_emb, rr, rs, od, ol, e[p], l[p]);
-                if (!has_lin) l[p] = 0.f;
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < PASSES; ++p) {
-            const int r = p * RPP + grp;
-            reinterpret_cast<float4*>(tl + r * RW)[sub] = e[p];
-            if (sub == 0) *reinterpret_cast<float4*>(tl + r * RW + K) = make_float4(l[p], 0.f, 0.f, 0.f);
-        }
-        __syncwarp();
-        const int s_first = route_find(rt->recv_off, rt->W, (uint32_t)i0);
-        const int s_last = route_find(rt->recv_off, rt->W, (uint32_t)(i0 + cnt - 1));
-        if (s_first == s_last) {
-            float4* dst = reinterpret_cast<float4*>(rt->peer_rowbuf[s_first] + (size_t)(rt->reply_off[s_first] + ((uint32_t)i0 - rt->recv_off[s_first])) * RW);
-            const float4* src4 = reinterpret_cast<const float4*>(tl);
-            for (int j = lane; j < cnt * RW4; j += 32) dst[j] = src4[j];
-        } else {
-            for (int r = 0; r < cnt; ++r) {
-                const uint32_t i = (uint32_t)(i0 + r);
-                const int sr = route_find(rt->recv_off, rt->W, i);
-                float4* dst = reinterpret_cast<float4*>(rt->peer_rowbuf[sr] + (size_t)(rt->reply_off[sr] + (i - rt->recv_off[sr])) * RW);
-                if (lane < RW4) dst[lane] = reinterpret_cast<const float4*>(tl + r * RW)[lane];
-            }
-        }
-        __syncwarp();
-    }
-}
-
-// fused exchange, step 1: every requester stores its unique local-row ids into the owners' receive buffers
-__global__ void p2p_push_ids_kernel(const uint32_t* __restrict__ req_rows, uint32_t U, const PeerRoute* __restrict__ rt) {
-    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u < U) {
-        const int o = route_find(rt->send_off, rt->W, u);
-        rt->peer_recv_rows[o][rt->dst_off[o] + (u - rt->send_off[o])] = req_rows[u];
-    }
-}

@@ -583,8 +583,13 @@ struct GradSrcFused {
         if (s) cp_async16(dst + H1 + sub * 4, s + (size_t)b * K + sub * 4);
         if (sub == LPR - 1) cp_async4(dst + H1 + K, dz + b);
     }
-    __device__ __forceinline__ void consume(const float* st, uint32_t val, int sub, float4& g, float& gl) const {
-        const uint32_t b = payload_sample(val), f = payload_slot(val);
+    int n_w0;                   // floats of W0 = D * H1 (copied to shared memory once per CTA by row_apply_kernel)
+    int aux_floats() const { return n_w0; }
+    __device__ __forceinline__ void aux_load(float* dst, int tid) const {
+        for (int i = tid * 4; i < n_w0; i += 256 * 4) *reinterpret_cast<float4*>(dst + i) = __ldg(reinterpret_cast<const float4*>(W0 + i));
+    }
+    __device__ __forceinline__ void consume(const float* st, const float* w0s, uint32_t val, int sub, float4& g, float& gl) const {
+        const uint32_t f = payload_slot(val);
         const float z = st[H1 + K];
         gl = z;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -592,13 +597,13 @@ struct GradSrcFused {
             const float4 sv = *reinterpret_cast<const float4*>(st + H1 + sub * 4);
             acc[0] = z * sv.x; acc[1] = z * sv.y; acc[2] = z * sv.z; acc[3] = z * sv.w;
         }
-        const float4* wr = reinterpret_cast<const float4*>(W0 + ((size_t)f * K + sub * 4) * H1);
-#pragma unroll 1
-        for (int o4 = 0; o4 < H1 / 4; ++o4) {       // 4 weight loads in flight per trip (16 would cost 64 registers)
+        const float4* wr = reinterpret_cast<const float4*>(w0s + ((size_t)f * K + sub * 4) * H1);
+#pragma unroll
+        for (int o4 = 0; o4 < H1 / 4; ++o4) {
             const float4 d = *reinterpret_cast<const float4*>(st + o4 * 4);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                const float4 w = __ldg(wr + kk * (H1 / 4) + o4);
+                const float4 w = wr[kk * (H1 / 4) + o4];
                 acc[kk] = fmaf(d.x, w.x, fmaf(d.y, w.y, fmaf(d.z, w.z, fmaf(d.w, w.w, acc[kk]))));
             }
         }

@@ -468,15 +468,19 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 __device__ __forceinline__ float u01(uint64_t h) { return ((h >> 40) + 0.5f) * (1.0f / 16777216.0f); }
 
 // truncated normal(0, sigma) cut at 2 sigma (rejection on a counter stream), strided destination
-__global__ void init_trunc_normal_kernel(float* __restrict__ dst, uint64_t rows, int K, int row_stride, float sigma, uint64_t seed) {
+// (row_mul, row_add): the stream is keyed on the GLOBAL row g = local * row_mul + row_add, so a row-sharded model
+// initialised with seed S holds exactly the rows of the unsharded model initialised with seed S
+__global__ void init_trunc_normal_kernel(float* __restrict__ dst, uint64_t rows, int K, int row_stride, float sigma, uint64_t seed,
+                                         uint64_t row_mul, uint64_t row_add) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * (uint64_t)K) return;
     uint64_t r = i / K;
     int c = (int)(i % K);
+    const uint64_t gi = (r * row_mul + row_add) * (uint64_t)K + c;
     float z = 0.f;
     for (uint64_t att = 0; att < 64; ++att) {
-        uint64_t h1 = splitmix64(seed ^ (i * 64 + att) * 2);
-        uint64_t h2 = splitmix64(seed ^ ((i * 64 + att) * 2 + 1));
+        uint64_t h1 = splitmix64(seed ^ (gi * 64 + att) * 2);
+        uint64_t h2 = splitmix64(seed ^ ((gi * 64 + att) * 2 + 1));
         z = sqrtf(-2.f * logf(u01(h1))) * cospif(2.f * u01(h2));
         if (fabsf(z) <= 2.f) break;
         z = 0.f;

@@ -4,7 +4,9 @@
 // Why: ncu on row_update_kernel at the Criteo shape (1.7 M unique rows of 256 bytes, profiles/r02b) showed 25 % occupancy,
 // 32 % issue-active and 1.8 TB/s: every lane group held one row's loads in registers, so an SM had ~14 KB in flight —
 // a quarter of what HBM latency needs.  cp.async costs no registers: each warp keeps NST-1 iterations (8 rows each at
-// K = 16) in flight, ~130 KB per SM, and the arithmetic of iteration i overlaps the traffic of i+1, i+2.
+// K = 16) in flight, ~90 KB per SM, and the arithmetic of iteration i overlaps the traffic of i+1, i+2.  The dense
+// operand of the fused step's gradient source (W0, 40 KB at the Criteo shape) is copied to shared memory once per CTA:
+// read through L1 it cost 16 dependent L2-latency loads per row (profiles/r02d: long-scoreboard stalls on LDG).
 //
 // Work split: a lane group (K/4 lanes) owns one row end to end, a warp owns 32/(K/4) consecutive rows per iteration, and
 // every warp runs its own pipeline (no block-wide barriers: a group's data is copied by its own lanes).
@@ -42,7 +44,9 @@ struct StageSrcPlain {
             if (sub == LPR - 1) cp_async4(dst + K, s.dz + b);
         }
     }
-    __device__ __forceinline__ void consume(const float* st, uint32_t, int sub, float4& g, float& gl) const {
+    int aux_floats() const { return 0; }                              // no per-CTA shared-memory operand
+    __device__ __forceinline__ void aux_load(float*, int) const {}
+    __device__ __forceinline__ void consume(const float* st, const float*, uint32_t, int sub, float4& g, float& gl) const {
         g = (s.flat || s.dE) ? *reinterpret_cast<const float4*>(st + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         gl = st[K];
     }
@@ -55,11 +59,11 @@ struct RowApplyCfg {
     static constexpr int RSMAX = 3 * K + 4;                       // record floats staged (w | lin4 | slot1 | slot2)
     static constexpr int SLOT = RSMAX + SRC::STAGE_F + 4;         // + meta {row, first lookup, begin, end}
     static constexpr int NST = K >= 16 ? 3 : 2;                   // pipeline stages per warp
-    static constexpr int SMEM = 8 * NST * G * SLOT * 4;
+    static constexpr int SMEM = 8 * NST * G * SLOT * 4;      // + SRC::aux_floats() * 4 (per-CTA operand, e.g. W0 of the fused step)
 };
 
 template <int K, typename SRC>
-__global__ void __launch_bounds__(256, 3) row_apply_kernel(const uint32_t* __restrict__ urow, const uint32_t* __restrict__ uval,
+__global__ void __launch_bounds__(256, 2) row_apply_kernel(const uint32_t* __restrict__ urow, const uint32_t* __restrict__ uval,
                                                            const uint32_t* __restrict__ svals, const uint32_t* __restrict__ row_start,
                                                            const uint32_t* __restrict__ row_piece0, const uint32_t* __restrict__ piece_start,
                                                            const SegCounts* __restrict__ cnt, SRC src, const float* __restrict__ piece_sum,
@@ -71,6 +75,9 @@ __global__ void __launch_bounds__(256, 3) row_apply_kernel(const uint32_t* __res
     extern __shared__ __align__(16) float ra_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, grp = lane / LPR;
     float* wbase = ra_smem + ((size_t)warp * NST * G + grp) * SLOT;      // this lane group's slot of stage 0
+    float* aux = ra_smem + (size_t)8 * NST * G * SLOT;                   // per-CTA operand of the gradient source
+    src.aux_load(aux, threadIdx.x);
+    __syncthreads();
     const ReplayStep rs = replay_step_load(rr.rd.closed ? rr.rd : rr.rl, rr.upto);
     const uint32_t U = cnt->n_rows;
     const uint32_t nw = gridDim.x * 8, gw = blockIdx.x * 8 + warp;
@@ -140,7 +147,7 @@ __global__ void __launch_bounds__(256, 3) row_apply_kernel(const uint32_t* __res
         bool coop = false;
         if (!act) {
         } else if (end - beg <= (uint32_t)DIRECT_T) {
-            src.consume(slot + RSMAX, v0, sub, g, gl);            // first lookup of the row: staged with the record
+            src.consume(slot + RSMAX, aux, v0, sub, g, gl);       // first lookup of the row: staged with the record
             for (uint32_t i = beg + 1; i < end; i += 4) {         // further lookups of the same row (rare with large tables)
                 uint32_t v[4];
                 float4 t[4];

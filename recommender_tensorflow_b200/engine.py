@@ -36,9 +36,10 @@ def _torch():
 class PackedBatch:
     """Raw feature columns of one batch laid out back to back in one arena (host pinned or device)."""
 
-    def __init__(self, arena, base_ptr, raw, keep, nbytes, batch_size, on_device):
+    def __init__(self, arena, base_ptr, raw, keep, nbytes, batch_size, on_device, layout=None):
         self.arena, self.base_ptr, self.raw, self._keep = arena, base_ptr, raw, keep
         self.nbytes, self.batch_size, self.on_device = nbytes, batch_size, on_device
+        self.layout = layout or []        # [(kind, index, byte offset, bytes)] of the columns inside the arena
 
 
 class DeepFMEngine:
@@ -128,6 +129,16 @@ class DeepFMEngine:
     @property
     def global_step(self):
         return int(self.lib.dfm_global_step(self.h))
+
+    def state_checksum(self):
+        """order-independent 64-bit checksum of the whole trained state on this handle (flushes first)"""
+        v = C.c_uint64(0)
+        self._check(self.lib.dfm_state_checksum(self.h, C.byref(v)))
+        return int(v.value)
+
+    @property
+    def last_unique_rows(self):
+        return int(self.lib.dfm_last_unique_rows(self.h))
 
     @property
     def last_step_launches(self):
@@ -349,7 +360,29 @@ class DeepFMEngine:
         raw = _lib.RawBatch(B, C.cast(cat, C.POINTER(C.c_void_p)), C.cast(off, C.POINTER(C.c_void_p)),
                             C.cast(num, C.POINTER(C.c_void_p)), lab)
         keep += [cat, off, num]
-        return PackedBatch(arena, base, raw, keep, total, B, device)
+        layout = [(kind, idx, o, a.nbytes) for (kind, idx, a), o in zip(segs, offs)]
+        return PackedBatch(arena, base, raw, keep, total, B, device, layout)
+
+    def repack_like(self, pb, arena):
+        """A PackedBatch over another arena (torch uint8 tensor, host pinned or device) with pb's column layout."""
+        base = arena.data_ptr()
+        nc, nn = max(len(self.specs), 1), max(len(self.num_columns), 1)
+        cat = (C.c_void_p * nc)()
+        off = (C.c_void_p * nc)()
+        num = (C.c_void_p * nn)()
+        lab = None
+        for kind, idx, o, _ in pb.layout:
+            if kind == "cat":
+                cat[idx] = base + o
+            elif kind == "off":
+                off[idx] = base + o
+            elif kind == "num":
+                num[idx] = base + o
+            else:
+                lab = base + o
+        raw = _lib.RawBatch(pb.batch_size, C.cast(cat, C.POINTER(C.c_void_p)), C.cast(off, C.POINTER(C.c_void_p)),
+                            C.cast(num, C.POINTER(C.c_void_p)), lab)
+        return PackedBatch(arena, base, raw, [cat, off, num], pb.nbytes, pb.batch_size, arena.is_cuda, pb.layout)
 
     def _as_batch(self, features, labels, device=False):
         if isinstance(features, PackedBatch):
@@ -450,72 +483,58 @@ class DeepFMEngine:
         self._check(self.lib.dfm_shard_apply(self.h, C.c_void_p(grecv.data_ptr()), C.c_void_p(dense_grad.data_ptr()),
                                              C.c_void_p(stream) if stream else None))
 
-    # ---- fused exchange over peer memory (include/deepfm_b200.h: dfm_shard_p2p_*) ----
     def shard_requests_counts(self, pb, stream=None):
         counts = (C.c_int32 * self.world)()
         self._check(self.lib.dfm_shard_requests(self.h, C.byref(pb.raw), None, counts, C.c_void_p(stream) if stream else None))
         return list(counts)
 
     def shard_forward(self, pb, rowbuf, logits, stream=None):
-        """forward pass alone on the served rows (rowbuf None: the handle's own peer-memory row buffer)"""
-        self._check(self.lib.dfm_shard_forward(self.h, C.byref(pb.raw), C.c_void_p(rowbuf.data_ptr()) if rowbuf is not None else None,
+        """forward pass alone on the served rows (collective path)"""
+        self._check(self.lib.dfm_shard_forward(self.h, C.byref(pb.raw), C.c_void_p(rowbuf.data_ptr()),
                                                C.c_void_p(logits.data_ptr()), C.c_void_p(stream) if stream else None))
 
-    def shard_requests_dev(self, pb, counts_dev, stream=None):
-        """asynchronous: per-owner counts land in counts_dev (int32 cuda tensor [world]); no host sync"""
-        self._check(self.lib.dfm_shard_requests_dev(self.h, C.byref(pb.raw), C.c_void_p(counts_dev.data_ptr()),
-                                                    C.c_void_p(stream) if stream else None))
-
-    def shard_prefetch_requests(self, pb, counts_dev, after_stream=None):
-        """requests of the NEXT batch on the handle's side stream (second buffer set); counts land in counts_dev.
-        after_stream: the stream that produced the batch (its H2D copy), the side stream waits for it."""
-        self._check(self.lib.dfm_shard_prefetch_requests(self.h, C.byref(pb.raw), C.c_void_p(counts_dev.data_ptr()),
-                                                         C.c_void_p(after_stream) if after_stream else None))
-
-    def shard_adopt_prefetch(self, pb, stream=None):
-        self._check(self.lib.dfm_shard_adopt_prefetch(self.h, C.byref(pb.raw), C.c_void_p(stream) if stream else None))
-
-    def shard_ipc_export(self):
-        buf = (C.c_ubyte * 192)()
-        self._check(self.lib.dfm_shard_ipc_export(self.h, buf))
+    # ---- flag-synchronised exchange over peer memory (include/deepfm_b200.h: dfm_xchg_*) ----
+    def xchg_export(self):
+        buf = (C.c_ubyte * 64)()
+        self._check(self.lib.dfm_xchg_export(self.h, buf))
         return bytes(buf)
 
-    def shard_ipc_import(self, all_handles):
-        assert len(all_handles) == self.world * 192
+    def xchg_import(self, all_handles):
+        assert len(all_handles) == self.world * 64
         buf = (C.c_ubyte * len(all_handles)).from_buffer_copy(all_handles)
-        self._check(self.lib.dfm_shard_ipc_import(self.h, buf))
+        self._check(self.lib.dfm_xchg_import(self.h, buf))
 
-    def shard_p2p_buffers(self):
-        out = (C.c_void_p * 3)()
-        self._check(self.lib.dfm_shard_p2p_buffers(self.h, out))
-        return [int(p) for p in out]
+    def xchg_buffer(self):
+        out = C.c_void_p()
+        self._check(self.lib.dfm_xchg_buffer(self.h, C.byref(out)))
+        return int(out.value)
 
-    def shard_p2p_set_peers(self, ptrs):
+    def xchg_set_peers(self, ptrs):
         arr = (C.c_void_p * len(ptrs))(*ptrs)
-        self._check(self.lib.dfm_shard_p2p_set_peers(self.h, arr))
+        self._check(self.lib.dfm_xchg_set_peers(self.h, arr))
 
-    def shard_p2p_plan(self, counts_matrix, stream=None):
-        """counts_matrix: [world, world] int32, [s, o] = unique rows rank s requests from owner o. -> n_recv"""
-        m = np.ascontiguousarray(counts_matrix, dtype=np.int32)
-        assert m.shape == (self.world, self.world)
-        n = C.c_int64(0)
-        self._check(self.lib.dfm_shard_p2p_plan(self.h, m.ctypes.data_as(C.c_void_p), C.byref(n), C.c_void_p(stream) if stream else None))
-        return n.value
+    def xchg_begin(self, pb, stream=None):
+        self._check(self.lib.dfm_xchg_begin(self.h, C.byref(pb.raw), C.c_void_p(stream) if stream else None))
 
-    def shard_p2p_push_ids(self, stream=None):
-        self._check(self.lib.dfm_shard_p2p_push_ids(self.h, C.c_void_p(stream) if stream else None))
+    def xchg_serve(self, train=True, stream=None):
+        self._check(self.lib.dfm_xchg_serve(self.h, int(bool(train)), C.c_void_p(stream) if stream else None))
 
-    def shard_p2p_serve(self, stream=None):
-        self._check(self.lib.dfm_shard_p2p_serve(self.h, C.c_void_p(stream) if stream else None))
+    def xchg_forward_backward(self, pb, global_batch, logits=None, stream=None):
+        self._check(self.lib.dfm_xchg_forward_backward(self.h, C.byref(pb.raw), int(global_batch),
+                                                       C.c_void_p(logits.data_ptr()) if logits is not None else None,
+                                                       C.c_void_p(stream) if stream else None))
 
-    def shard_p2p_forward_backward(self, pb, global_batch, loss, logits, dense_grad, stream=None):
-        self._check(self.lib.dfm_shard_p2p_forward_backward(
-            self.h, C.byref(pb.raw), int(global_batch), C.c_void_p(loss.data_ptr()),
-            C.c_void_p(logits.data_ptr()) if logits is not None else None, C.c_void_p(dense_grad.data_ptr()),
-            C.c_void_p(stream) if stream else None))
+    def xchg_apply(self, loss_out, stream=None):
+        self._check(self.lib.dfm_xchg_apply(self.h, C.c_void_p(loss_out.data_ptr()), C.c_void_p(stream) if stream else None))
 
-    def shard_p2p_apply(self, dense_grad, stream=None):
-        self._check(self.lib.dfm_shard_p2p_apply(self.h, C.c_void_p(dense_grad.data_ptr()), C.c_void_p(stream) if stream else None))
+    def xchg_train_step(self, pb, global_batch, loss_out, logits=None, stream=None):
+        """one whole sharded step: launches only (no collective, no host synchronisation)"""
+        self._check(self.lib.dfm_xchg_train_step(self.h, C.byref(pb.raw), int(global_batch), C.c_void_p(loss_out.data_ptr()),
+                                                 C.c_void_p(logits.data_ptr()) if logits is not None else None,
+                                                 C.c_void_p(stream) if stream else None))
+
+    def xchg_forward(self, pb, logits, stream=None):
+        self._check(self.lib.dfm_xchg_forward(self.h, C.byref(pb.raw), C.c_void_p(logits.data_ptr()), C.c_void_p(stream) if stream else None))
 
     def set_weights_sharded(self, weights):
         """Load GLOBAL arrays: table rows are sliced to the rows this rank owns (g % world == rank)."""

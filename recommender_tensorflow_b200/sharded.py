@@ -9,9 +9,11 @@ routing logic):
     all_to_all(counts) -> all_to_all(row ids) -> [serve] -> all_to_all(rows) -> [forward/backward]
     -> all_to_all(gradient rows) + all_reduce(dense grads, loss) -> [apply]
 
-`VirtualCluster` runs the same phases for `world` engines inside ONE process on one GPU, routing the
-buffers with plain tensor copies; it is how the sharded path is checked against the single-GPU
-result without a multi-GPU box (B200_PROFILING.md: emulate ranks in one process, never as
+`XchgTrainer` is the default: the same step with the exchanges fused into the kernels over NVLink peer memory and
+synchronised by flags (no collective at all, csrc/xchg.cuh); `ShardedTrainer` above is the NCCL baseline it is
+checked against.  `VirtualCluster` runs either set of phases for `world` engines inside ONE process on one GPU,
+routing the buffers with plain tensor copies or wiring the exchange regions by raw pointers; it is how the sharded
+path is checked against the single-GPU result without a multi-GPU box (B200_PROFILING.md: emulate ranks in one process, never as
 co-running kernels that wait on each other).
 """
 import numpy as np
@@ -75,6 +77,7 @@ class ShardedTrainer:
         self.gsum = torch.empty(n * rw, dtype=torch.float32, device=dev)
         self.grecv = torch.empty((2 * n + 4096) * rw, dtype=torch.float32, device=dev)
         self.dense = torch.zeros(max(engine.dense_size, 1) + 1, dtype=torch.float32, device=dev)   # [+1]: loss rides along
+        self.dense_all = torch.zeros((self.W, max(engine.dense_size, 1) + 1), dtype=torch.float32, device=dev)
         self.cnt_send = torch.empty(self.W, dtype=torch.int32, device=dev)
         self.cnt_recv = torch.empty(self.W, dtype=torch.int32, device=dev)
         self.rw = rw
@@ -114,7 +117,12 @@ class ShardedTrainer:
         dist.all_to_all_single(self.grecv[:n_recv * rw], self.gsum[:U * rw], split_sizes(recv_counts, rw),
                                split_sizes(send_counts, rw), group=self.group)
         mark("a2a_grads")
-        dist.all_reduce(self.dense, group=self.group)
+        # the tower's all-reduce as all_gather + a sum in RANK ORDER: every replica adds the same numbers in the same
+        # order (bit-identical replicas, and bit-identical to the fused exchange, whatever NCCL's reduction tree is)
+        dist.all_gather_into_tensor(self.dense_all, self.dense, group=self.group)
+        self.dense.copy_(self.dense_all[0])
+        for r in range(1, self.W):
+            self.dense.add_(self.dense_all[r])
         mark("allreduce")
         eng.shard_apply(self.grecv, self.dense, st)
         mark("apply")
@@ -144,21 +152,22 @@ class ShardedTrainer:
         return logits
 
 
-class P2PShardedTrainer:
-    """Same step with the three payload exchanges fused into the kernels: every rank's receive buffers are
-    mapped into its peers through CUDA IPC, and the requesting / serving / gradient kernels store straight
-    into the destination GPU over NVLink.  NCCL carries only the W x W count matrix, two 4-byte barriers and
-    the dense-gradient all_reduce (which doubles as the barrier before `apply`).
+class XchgTrainer:
+    """One process per GPU.  The exchanges are fused into the kernels: every rank's exchange region (fixed-capacity id /
+    gradient-row segments per (source, owner), a row buffer, dense-gradient slots, flags) is mapped into its peers
+    through CUDA IPC; the producing kernels store straight into the destination GPU over NVLink and stamp a flag there,
+    the consuming stream waits on that flag with a one-warp kernel (csrc/xchg.cuh).  A train step is ONE C-ABI call that
+    only launches kernels: no collective, no host synchronisation, no count exchange.  NCCL is used once, at
+    construction, to exchange the 64-byte IPC handles.
 
-    Ordering (every call below is stream-ordered; "bar" = a collective every rank must enter):
-        push_ids | bar1 | serve | bar2 | forward_backward | all_reduce(dense) | apply
-    * within a step: a rank reads its id buffer only after bar1, its row buffer only after bar2 and its gradient
-      buffer only after the dense all_reduce, i.e. after every peer has finished the kernel that stores into it
-      (a peer enters the collective only after that kernel, and kernel completion makes its peer stores visible);
-    * across steps: a peer's push_ids(t+1) follows its all_reduce(t), which completes only after I entered it, i.e.
-      after my serve(t) read the ids; its serve(t+1) follows bar1(t+1), which I enter after my forward_backward(t)
-      read the rows; its forward_backward(t+1) follows bar2(t+1), which I enter after my apply(t) read the
-      gradient rows.  So no buffer is overwritten before its reader is done and no double buffering is needed."""
+    Ordering ("e" = exchange round, incremented by every train / predict call on every rank alike):
+        push ids(e) | wait ids | serve(e) | wait rows | forward_backward(e): gradient rows, dense push |
+        wait gradient rows | sparse apply | wait dense | dense apply
+    Buffer reuse.  ids / headers are double buffered by the parity of e: an owner may still be sorting the ids of round e
+    (side stream) when a fast peer already pushes round e+1, but round e+2 cannot start on any rank before this owner
+    has finished apply(e+1), i.e. all of round e.  Rows, gradient rows and dense slots are single buffered: their next
+    writer is a peer's serve(e+1) / forward_backward(e+1), which wait for MY ids(e+1) / MY rows(e+1); I produce those
+    only after my forward_backward(e) / apply(e) - the readers of the old contents - in stream order."""
 
     def __init__(self, engine, group=None):
         import torch
@@ -167,80 +176,47 @@ class P2PShardedTrainer:
         self.eng, self.group = engine, group
         self.W, self.rank = engine.world, engine.rank
         dev = "cuda:%d" % engine.device
-        mine = torch.frombuffer(bytearray(engine.shard_ipc_export()), dtype=torch.uint8).to(dev)
-        allh = torch.empty(self.W * 192, dtype=torch.uint8, device=dev)
+        mine = torch.frombuffer(bytearray(engine.xchg_export()), dtype=torch.uint8).to(dev)
+        allh = torch.empty(self.W * 64, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(allh, mine, group=group)
-        engine.shard_ipc_import(bytes(allh.cpu().numpy().tobytes()))
-        self.dense = torch.zeros(max(engine.dense_size, 1) + 1, dtype=torch.float32, device=dev)
-        self.cnt_mine = torch.empty(self.W, dtype=torch.int32, device=dev)
-        self.cnt_next = torch.empty(self.W, dtype=torch.int32, device=dev)
-        self.cnt_all = torch.empty(self.W * self.W, dtype=torch.int32, device=dev)
-        self.flag = torch.zeros(1, dtype=torch.float32, device=dev)
-        self._prefetched = None        # the PackedBatch whose requests were computed ahead of time
-        dist.barrier(group=group)
+        engine.xchg_import(bytes(allh.cpu().numpy().tobytes()))
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        dist.barrier(group=group)          # every rank has mapped every region before the first store
 
     @_on_real_stream
     def train_step(self, pb, global_batch, timings=None, next_pb=None):
-        """next_pb: the batch of the following step, if known — its requests (transform, sort, unique rows: no model
-        state) are then computed on the library's side stream while this step runs."""
-        torch, dist, eng = self.torch, self.dist, self.eng
+        """Enqueue one sharded train step on torch's current stream; returns the global loss (0-dim cuda tensor, valid
+        once the stream reaches it).  timings (dict): per-phase device milliseconds (adds events, debug)."""
+        torch, eng = self.torch, self.eng
         st = torch.cuda.current_stream().cuda_stream
+        if timings is None:
+            eng.xchg_train_step(pb, global_batch, self.loss, None, st)
+            return self.loss[0]
         marks = []
 
         def mark(name):
-            if timings is not None:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record()
-                marks.append((name, e))
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
         mark("start")
-        if self._prefetched is pb:
-            eng.shard_adopt_prefetch(pb, st)                       # orders this stream after the prefetch
-            self.cnt_mine, self.cnt_next = self.cnt_next, self.cnt_mine
-        else:
-            eng.shard_requests_dev(pb, self.cnt_mine, st)
-        self._prefetched = None
-        mark("requests")
-        dist.all_gather_into_tensor(self.cnt_all, self.cnt_mine, group=self.group)
-        eng.shard_p2p_plan(self.cnt_all.cpu().numpy().reshape(self.W, self.W), st)
-        mark("counts")
-        if next_pb is not None:
-            eng.shard_prefetch_requests(next_pb, self.cnt_next, st)
-            self._prefetched = next_pb
-        eng.shard_p2p_push_ids(st)
-        dist.all_reduce(self.flag, group=self.group)          # barrier: every owner has all its requests
-        mark("push_ids")
-        eng.shard_p2p_serve(st)
-        dist.all_reduce(self.flag, group=self.group)          # barrier: every requester has all its rows
-        mark("serve")
-        nd = eng.dense_size
-        eng.shard_p2p_forward_backward(pb, global_batch, self.dense[nd:nd + 1], None, self.dense, st)
-        mark("fwd_bwd")
-        dist.all_reduce(self.dense, group=self.group)         # dense grads + loss; also the barrier before apply
-        mark("allreduce")
-        eng.shard_p2p_apply(self.dense, st)
-        mark("apply")
-        if timings is not None:
-            torch.cuda.synchronize()
-            for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
-                timings[n1] = timings.get(n1, 0.0) + e0.elapsed_time(e1)
-        return self.dense[nd]
-
+        eng.xchg_begin(pb, st); mark("requests+push")
+        eng.xchg_serve(True, st); mark("serve")
+        eng.xchg_forward_backward(pb, global_batch, None, st); mark("fwd_bwd")
+        eng.xchg_apply(self.loss, st); mark("apply")
+        torch.cuda.synchronize()
+        for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+            timings[n1] = timings.get(n1, 0.0) + e0.elapsed_time(e1)
+        return self.loss[0]
 
     @_on_real_stream
     def predict_logits(self, pb):
-        """EVAL / PREDICT over the fused exchange: logits of this rank's batch (cuda tensor [B]); no state changes."""
-        torch, dist, eng = self.torch, self.dist, self.eng
+        """EVAL / PREDICT: logits of this rank's batch (cuda tensor [B]); no state changes."""
+        torch, eng = self.torch, self.eng
         st = torch.cuda.current_stream().cuda_stream
-        eng.shard_requests_dev(pb, self.cnt_mine, st)
-        dist.all_gather_into_tensor(self.cnt_all, self.cnt_mine, group=self.group)
-        eng.shard_p2p_plan(self.cnt_all.cpu().numpy().reshape(self.W, self.W), st)
-        eng.shard_p2p_push_ids(st)
-        dist.all_reduce(self.flag, group=self.group)
-        eng.shard_p2p_serve(st)
-        dist.all_reduce(self.flag, group=self.group)
-        logits = torch.empty(pb.batch_size, dtype=torch.float32, device=self.flag.device)
-        eng.shard_forward(pb, None, logits, st)
-        dist.all_reduce(self.flag, group=self.group)       # nobody overwrites a row buffer that is still being read
+        logits = torch.empty(pb.batch_size, dtype=torch.float32, device=self.loss.device)
+        eng.xchg_begin(pb, st)
+        eng.xchg_serve(False, st)
+        eng.xchg_forward(pb, logits, st)
         return logits
 
 
@@ -253,62 +229,49 @@ class VirtualCluster:
         self.torch = torch
         self.engs = engines
         self.W = len(engines)
-        self.p2p = p2p
+        self.p2p = p2p            # True: the flag-synchronised fused exchange (dfm_xchg_*), wired by raw pointers
         if p2p:
-            ptrs = []
+            ptrs = [e.xchg_buffer() for e in engines]
             for e in engines:
-                ptrs += e.shard_p2p_buffers()
-            for e in engines:
-                e.shard_p2p_set_peers(ptrs)
+                e.xchg_set_peers(ptrs)
 
-    def _train_step_p2p(self, pbs, return_logits, next_pbs=None):
-        torch, W = self.torch, self.W
+    def _train_step_p2p(self, pbs, return_logits):
+        """The phases rank by rank (every flag is set before the kernel that waits for it is launched: kernels that
+        wait on one another must never share a GPU)."""
+        torch = self.torch
         dev = "cuda:%d" % self.engs[0].device
         global_batch = sum(pb.batch_size for pb in pbs)
-        nd = self.engs[0].dense_size
-        if getattr(self, "_prefetched", None) is not None and all(a is b for a, b in zip(self._prefetched, pbs)):
-            for e, pb in zip(self.engs, pbs):
-                e.shard_adopt_prefetch(pb)
-                e.sync()
-            counts = self._cnt_next.cpu().numpy().astype(np.int32)
-        else:
-            counts = np.array([e.shard_requests_counts(pb) for e, pb in zip(self.engs, pbs)], dtype=np.int32)
-        self._prefetched = None
-        for e in self.engs:
-            e.shard_p2p_plan(counts)
-        if next_pbs is not None:       # requests of the next batch, on the engines' side streams, while this step runs
-            self._cnt_next = torch.empty((W, W), dtype=torch.int32, device=dev)
-            for r, (e, pb) in enumerate(zip(self.engs, next_pbs)):
-                e.shard_prefetch_requests(pb, self._cnt_next[r])
-            self._prefetched = list(next_pbs)
-        for e in self.engs:
-            e.shard_p2p_push_ids()
-        for e in self.engs:
-            e.sync()
-        for e in self.engs:
-            e.shard_p2p_serve()
-        for e in self.engs:
-            e.sync()
-        denses, logits = [], []
         for e, pb in zip(self.engs, pbs):
-            dn = torch.zeros(nd + 1, dtype=torch.float32, device=dev)
+            e.xchg_begin(pb)
+        for e in self.engs:
+            e.sync()
+        for e in self.engs:
+            e.xchg_serve(True)
+        for e in self.engs:
+            e.sync()
+        logits = []
+        for e, pb in zip(self.engs, pbs):
             lg = torch.empty(pb.batch_size, dtype=torch.float32, device=dev)
-            e.shard_p2p_forward_backward(pb, global_batch, dn[nd:nd + 1], lg, dn)
-            denses.append(dn); logits.append(lg)
+            e.xchg_forward_backward(pb, global_batch, lg)
+            logits.append(lg)
         for e in self.engs:
             e.sync()
-        total = torch.stack(denses).sum(0)
+        losses = []
         for e in self.engs:
-            e.shard_p2p_apply(total)
+            ls = torch.zeros(1, dtype=torch.float32, device=dev)
+            e.xchg_apply(ls)
+            losses.append(ls)
+        for e in self.engs:
             e.sync()
-        loss = float(total[nd].item())
+        vals = [float(x.item()) for x in losses]
+        assert all(v == vals[0] for v in vals), "ranks disagree on the global loss: %r" % (vals,)
         if return_logits:
-            return loss, torch.cat(logits).cpu().numpy()
-        return loss
+            return vals[0], torch.cat(logits).cpu().numpy()
+        return vals[0]
 
-    def train_step(self, pbs, return_logits=False, next_pbs=None):
+    def train_step(self, pbs, return_logits=False):
         if self.p2p:
-            return self._train_step_p2p(pbs, return_logits, next_pbs)
+            return self._train_step_p2p(pbs, return_logits)
         torch, W = self.torch, self.W
         dev = "cuda:%d" % self.engs[0].device
         rw = self.engs[0].row_width
@@ -338,7 +301,9 @@ class VirtualCluster:
             e.sync()
             gsums.append(gs[:U * rw]); denses.append(dn); logits.append(lg)
         grecv, _ = route_all_to_all(gsums, counts, rw)
-        total = torch.stack(denses).sum(0)            # all_reduce (rank order)
+        total = denses[0].clone()                     # all_reduce, summed in rank order
+        for dn in denses[1:]:
+            total += dn
         for e, gr in zip(self.engs, grecv):
             grc = gr.contiguous() if gr.numel() else torch.zeros(rw, dtype=torch.float32, device=dev)
             e.shard_apply(grc, total)
@@ -355,20 +320,17 @@ class VirtualCluster:
         rw = self.engs[0].row_width
         outs = []
         if self.p2p:
-            counts = np.array([e.shard_requests_counts(pb) for e, pb in zip(self.engs, pbs)], dtype=np.int32)
-            for e in self.engs:
-                e.shard_p2p_plan(counts)
-            for e in self.engs:
-                e.shard_p2p_push_ids()
+            for e, pb in zip(self.engs, pbs):
+                e.xchg_begin(pb)
             for e in self.engs:
                 e.sync()
             for e in self.engs:
-                e.shard_p2p_serve()
+                e.xchg_serve(False)
             for e in self.engs:
                 e.sync()
             for e, pb in zip(self.engs, pbs):
                 lg = torch.empty(pb.batch_size, dtype=torch.float32, device=dev)
-                e.shard_forward(pb, None, lg)
+                e.xchg_forward(pb, lg)
                 e.sync()
                 outs.append(lg)
         else:

@@ -89,3 +89,33 @@ def criteo_columns(buckets_per_field, n_cat=26, n_num=13):
     cats = [fc.categorical_column_with_hash_bucket("C%d" % (f + 1), buckets_per_field) for f in range(n_cat)]
     nums = [fc.numeric_column("I%d" % (j + 1)) for j in range(n_num)]
     return cats, nums
+
+
+def criteo_device_batches(engine, batch_size, n_batches, seed, n_cat=26, n_num=13):
+    """n_batches Criteo-shaped PackedBatches generated ON THE DEVICE (torch ops: uniform 32-bit keys rendered as
+    8-hex-char strings, log1p(Poisson) numerics, Bernoulli(0.25) labels), every one with fresh ids.  The arena layout
+    is the one engine.pack() produces for a host batch of the same shape; only the key bytes, the numeric columns and
+    the labels differ from batch to batch (the string offsets are the same arange * 8)."""
+    import torch
+    rng = np.random.default_rng(seed)
+    feats, y = criteo_batch(batch_size, rng, n_cat, n_num)
+    tmpl = engine.pack(feats, y, device=True)
+    dev = tmpl.arena.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    hexlut = torch.tensor(list(b"0123456789abcdef"), dtype=torch.uint8, device=dev)
+    shifts = torch.arange(7, -1, -1, device=dev, dtype=torch.int64) * 4
+    out = [tmpl]
+    for _ in range(n_batches - 1):
+        arena = tmpl.arena.clone()
+        for kind, idx, off, nbytes in tmpl.layout:
+            if kind == "cat":
+                keys = torch.randint(0, 1 << 32, (batch_size,), generator=g, device=dev, dtype=torch.int64)
+                arena[off:off + nbytes] = hexlut[((keys[:, None] >> shifts[None, :]) & 15)].reshape(-1)
+            elif kind == "num":
+                lam = torch.full((batch_size,), 3.0 + idx, device=dev)
+                arena[off:off + nbytes] = torch.log1p(torch.poisson(lam, generator=g)).to(torch.float32).view(torch.uint8).reshape(-1)
+            elif kind == "lab":
+                arena[off:off + nbytes] = (torch.rand(batch_size, generator=g, device=dev) < 0.25).to(torch.float32).view(torch.uint8).reshape(-1)
+        out.append(engine.repack_like(tmpl, arena))
+    return out

@@ -1,5 +1,6 @@
 """Worker for test_p2p_ipc_two_processes (launched with torchrun, one rank per GPU): runs the same steps through
-ShardedTrainer (NCCL all_to_all) and P2PShardedTrainer (stores over IPC-mapped peer memory) and requires equal bits."""
+ShardedTrainer (NCCL all_to_all) and XchgTrainer (kernel stores into IPC-mapped peer memory, flag-synchronised, no
+collective inside the step) and requires equal bits; then checks EVAL / PREDICT through both."""
 import os
 import sys
 
@@ -10,7 +11,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from recommender_tensorflow_b200 import synth  # noqa: E402
 from recommender_tensorflow_b200.engine import DeepFMEngine  # noqa: E402
-from recommender_tensorflow_b200.sharded import P2PShardedTrainer, ShardedTrainer  # noqa: E402
+from recommender_tensorflow_b200.sharded import ShardedTrainer, XchgTrainer  # noqa: E402
 
 
 def main():
@@ -23,32 +24,39 @@ def main():
     per = 4096
     ea = DeepFMEngine(cats, nums, max_batch=per, **kw)
     eb = DeepFMEngine(cats, nums, max_batch=per, **kw)
-    ec = DeepFMEngine(cats, nums, max_batch=per, **kw)
     ea.init_random(3)
     eb.init_random(3)
-    ec.init_random(3)
-    ta, tb, tc = ShardedTrainer(ea), P2PShardedTrainer(eb), P2PShardedTrainer(ec)
+    ta, tb = ShardedTrainer(ea), XchgTrainer(eb)
     rng = np.random.default_rng(100 + rank)
-    data = [synth.criteo_batch(per, rng, key_space=200000) for _ in range(6)]
-    pcs = [ec.pack(f, y, device=True) for f, y in data]
-    for step, (feats, y) in enumerate(data):
-        la = float(ta.train_step(ea.pack(feats, y, device=True), per * world).item())
-        lb = float(tb.train_step(eb.pack(feats, y, device=True), per * world).item())
-        lc = float(tc.train_step(pcs[step], per * world, next_pb=pcs[step + 1] if step + 1 < len(pcs) else None).item())   # with request prefetch
-        assert la == lb == lc, (step, la, lb, lc)
+    data = [synth.criteo_batch(per, rng, key_space=200000) for _ in range(8)]
+    pbs = [eb.pack(f, y, device=True) for f, y in data]
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        for step, (feats, y) in enumerate(data[:6]):
+            la = float(ta.train_step(ea.pack(feats, y, device=True), per * world).item())
+            lb = float(tb.train_step(pbs[step], per * world).item())
+            assert la == lb, (step, la, lb)
+        # back-to-back steps without any host synchronisation in between (the flags alone order the ranks)
+        for step in (6, 7):
+            ta.train_step(ea.pack(*data[step], device=True), per * world)
+        for step in (6, 7):
+            tb.train_step(pbs[step], per * world)
+        za = ta.predict_logits(pbs[0]).cpu().numpy()
+        zb = tb.predict_logits(pbs[0]).cpu().numpy()
+    torch.cuda.synchronize()
+    eb.sync()
+    assert np.array_equal(za, zb)
     ea.flush()
     eb.flush()
-    ec.flush()
     names = []
     for v in ea.variable_names():
         names.append(v)
         names += [v + "/" + s for s in ea.slot_names(v)]
     for n in names:
         assert np.array_equal(ea.get_tensor(n), eb.get_tensor(n)), n
-        assert np.array_equal(ea.get_tensor(n), ec.get_tensor(n)), n
     dist.barrier()
     if rank == 0:
-        print("P2P_OK steps=6 loss=%r" % lb)
+        print("P2P_OK steps=8 loss=%r" % lb)
     dist.destroy_process_group()
 
 

@@ -155,16 +155,38 @@ def test_deepfm_tensor_core_tower(hidden, batch):
 
 def test_deepfm_cfg2_full_batch_65536():
     """BASELINE configs[2] AT ITS OWN BATCH SIZE: k=16, hidden [256,128], B = 65 536 -> 1 024 / 512 tiles on 148
-    persistent CTAs (about 7 tiles per CTA: TMEM accumulator sets and the TMA ring wrap), 3 steps, loss / logits /
-    every weight and optimizer slot against the oracle."""
+    persistent CTAs (about 7 tiles per CTA: TMEM accumulator sets and the TMA ring wrap), 3 steps.
+
+    The tcgen05 tower (3xTF32, truncating TMEM accumulation) carries ~5x the rounding noise of an fp32 CUDA-core sum
+    (tests/test_gpu_tc_gemm.py, tools/debug_cfg2.py); Adam then turns the noise of a near-zero gradient element
+    (update ~ lr g / (|g| + eps-hat), slope up to lr / eps-hat = 3e3) and of a ReLU unit that flips at |pre-activation|
+    < 1e-6 into weight differences that no element-wise bar can hold - for the float32 oracle against its float64
+    twin just as for the CUDA path.  So the step is pinned in three parts:
+      (1) loss / logits of every step against the oracle: 1e-5 relative + 8x the float32 oracle's own deviation;
+      (2) every optimizer slot (m, v: linear / quadratic in the gradients, no amplification) against the oracle:
+          1e-5 relative + 8x the oracle's own worst deviation on that tensor;
+      (3) every weight against the reference update formula applied to the engine's OWN slots,
+          w_t = w_{t-1} - alpha_t m_t / (sqrt(v_t) + eps) for all rows (non-lazy Adam), to 2e-6 relative."""
     eng = _ml_engine(k=16, hidden=(256, 128), max_batch=65536)
     ora, _ = make_pair(eng, seed=21)
     ml, rng = synth.ML100K(), np.random.default_rng(22)
-    # The tcgen05 tower accumulates in TMEM with truncation (a bias of ~0.5 ulp per K=8 fold, test_gpu_tc_gemm.py), so
-    # its gradients carry ~5x the rounding noise of an fp32 CUDA-core sum; Adam then amplifies the noise of near-zero
-    # gradient elements (update ~ lr g / (|g| + eps-hat)) for the float32 oracle and the CUDA path alike.  Allowance on
-    # the logits after an update: 1e-5 relative + 8x the float32 oracle's own deviation from float64 (4x elsewhere).
-    _run_steps(eng, ora, [ml.batch(65536, rng) for _ in range(3)], "cfg2-B65536", noise=8.0, tc_noise=8.0)
+    prev = eng.state()
+    for i in range(3):
+        feats, y = ml.batch(65536, rng)
+        loss, logits = eng.train_step(feats, y, return_logits=True)
+        rloss, rlogits = ora.train_step_raw(feats, y)
+        assert_step_close(loss, logits, ora, rloss, rlogits, RTOL, "cfg2-B65536 step %d" % i, noise=8.0)          # (1)
+        st, r32, r64 = eng.state(), ora.state(), ora.state64()
+        slots = {k: v for k, v in r32.items() if "/" in k}
+        assert_state_close(st, slots, RTOL, 1e-7, "cfg2-B65536 step %d slots" % i, {k: r64[k] for k in slots}, tc_noise=8.0)   # (2)
+        alpha = np.float32(ora.o32._alpha("deep"))
+        for name in [k for k in r32 if "/" not in k]:                                                              # (3)
+            m, v = st[name + "/m"].astype(np.float32), st[name + "/v"].astype(np.float32)
+            want = prev[name].astype(np.float32) - (alpha * m) / (np.sqrt(v) + np.float32(1e-8))
+            got = st[name]
+            assert np.allclose(got, want, rtol=2e-6, atol=2e-9), (name, i, float(np.abs(got - want).max()))
+        prev = st
+    assert eng.global_step == 3
 
 
 def test_deferred_adam_gap_1000_nontrivial_slots():

@@ -99,8 +99,9 @@ def test_sharded_multi_hot_world2(p2p):
 
 
 def test_p2p_exchange_bit_identical_to_collectives():
-    """The fused peer-memory exchange only changes WHERE rows travel, never a value: after the same steps the
-    shards of a p2p cluster equal the shards of the all_to_all cluster bit for bit."""
+    """The fused peer-memory exchange (dfm_xchg_*: stores into the peers' regions, flags, no collective) only changes
+    WHERE rows travel, never a value: after the same steps the shards of a fused-exchange cluster equal the shards of
+    the all_to_all cluster bit for bit."""
     cats, nums = synth.criteo_columns(2000, n_cat=8, n_num=4)
     kw = dict(embedding_size=16, hidden_units=(32, 16))
     world, per = 4, 512
@@ -135,8 +136,9 @@ def test_p2p_exchange_bit_identical_to_collectives():
 
 
 def test_p2p_ipc_two_processes():
-    """Real thing: two processes, two GPUs, receive buffers mapped through CUDA IPC; the P2P trainer must match
-    the NCCL all_to_all trainer bit for bit (tests/p2p_worker.py).  Needs >= 2 GPUs."""
+    """Real thing: two processes, two GPUs, exchange regions mapped through CUDA IPC, kernels meeting through flags in
+    peer memory; the fused-exchange trainer must match the NCCL all_to_all trainer bit for bit
+    (tests/p2p_worker.py).  Needs >= 2 GPUs."""
     import os
     import subprocess
     import sys
@@ -196,42 +198,19 @@ def test_sharded_forward_only_equals_single_gpu(p2p):
     assert all(e.global_step == 3 for e in engs)
 
 
-def test_request_prefetch_changes_nothing():
-    """dfm_shard_prefetch_requests: the next batch's requests computed on the side stream while the step runs give the
-    same bits as computing them in the step."""
-    cats, nums = synth.criteo_columns(2000, n_cat=8, n_num=4)
-    kw = dict(embedding_size=16, hidden_units=(32, 16))
-    world, per = 2, 512
-    rng = np.random.default_rng(91)
-    batches = [synth.criteo_batch(world * per, rng, key_space=4000) for _ in range(5)]
-    states = []
-    for prefetch in (False, True):
-        engs = [DeepFMEngine(cats, nums, max_batch=per, rank=r, world=world, **kw) for r in range(world)]
-        for e in engs:
-            e.init_random(5)
-        vc = VirtualCluster(engs, p2p=True)
-        packed = []
-        for feats, y in batches:
-            pbs = []
-            for r, e in enumerate(engs):
-                fr = {}
-                for k, v in feats.items():
-                    if isinstance(v, tuple):
-                        data, offs = v
-                        o = offs[r * per:(r + 1) * per + 1]
-                        fr[k] = (data[o[0]:o[-1]].copy(), (o - o[0]).astype(np.int32))
-                    else:
-                        fr[k] = v[r * per:(r + 1) * per]
-                pbs.append(e.pack(fr, y[r * per:(r + 1) * per], device=True))
-            packed.append(pbs)
-        losses = []
-        for i, pbs in enumerate(packed):
-            nxt = packed[i + 1] if prefetch and i + 1 < len(packed) else None
-            losses.append(vc.train_step(pbs, next_pbs=nxt))
-        for e in engs:
-            e.flush()
-        states.append((losses, [{n: e.get_tensor(n) for n in _names(e)} for e in engs]))
-    assert states[0][0] == states[1][0]
-    for sa, sb in zip(states[0][1], states[1][1]):
-        for n in sa:
-            assert np.array_equal(sa[n], sb[n]), n
+def test_init_random_is_keyed_on_global_rows():
+    """dfm_init_random(seed) on a row-sharded model gives exactly the rows of the unsharded model with the same seed
+    (and the same dense tower on every rank): `eng.init_random(s)` on every rank is all a multi-GPU host has to do."""
+    cats, nums = synth.criteo_columns(777, n_cat=5, n_num=3)
+    kw = dict(embedding_size=8, hidden_units=(16, 16), max_batch=64)
+    ref = DeepFMEngine(cats, nums, **kw)
+    ref.init_random(42)
+    world = 3
+    engs = [DeepFMEngine(cats, nums, rank=r, world=world, **kw) for r in range(world)]
+    for e in engs:
+        e.init_random(42)
+    full = ref.get_tensor("emb")
+    for r, e in enumerate(engs):
+        assert np.array_equal(e.get_tensor("emb"), full[r::world])
+        for n in ("W0", "W1", "Wo", "num_emb"):
+            assert np.array_equal(e.get_tensor(n), ref.get_tensor(n)), n
