@@ -1162,11 +1162,12 @@ static int build_segments(dfm_handle* h, SegWS& ws, int64_t n, uint32_t limit, i
     if (n > 0) ws.cur = prims::onesweep_sort_pairs(ws.keys, ws.vals, n, n_dev, bits, ws.sort_temp, st, &h->launches);
     if (ph) ph->next();
     const int64_t tiles = std::max<int64_t>((n + SB_TILE - 1) / SB_TILE, 1);
-    CK(cudaMemsetAsync(ws.flags, 0, (size_t)tiles * 8, st));              // look-back status words
-    CK(cudaMemsetAsync(ws.seg_total, 0, 8, st));                          // tile ticket
-    seg_build_kernel<<<(unsigned)tiles, 256, 0, st>>>(ws.skeys(), ws.svals(), n, n_dev, limit, ws.flags, reinterpret_cast<uint32_t*>(ws.seg_total),
-                                                      ws.seg_cnt, ws.row_start, ws.row_piece0, ws.piece_start, ws.urow, ws.uval, ws.pos_row);
-    h->launches++;
+    CK(cudaMemsetAsync(ws.seg_total, 0, 8, st));                          // ticket of the count kernel
+    seg_count_kernel<<<(unsigned)tiles, 256, 0, st>>>(ws.skeys(), n, n_dev, limit, ws.flags, reinterpret_cast<unsigned int*>(ws.seg_total), ws.seg_cnt,
+                                                      ws.row_start, ws.row_piece0, ws.piece_start);
+    seg_fill_kernel2<<<(unsigned)tiles, 256, 0, st>>>(ws.skeys(), ws.svals(), n, n_dev, limit, ws.flags, ws.row_start, ws.row_piece0, ws.piece_start,
+                                                      ws.urow, ws.uval, ws.pos_row);
+    h->launches += 2;
     if (ph) ph->next();
     CK(cudaGetLastError());
     return DFM_OK;
@@ -1344,6 +1345,24 @@ static int sparse_update(dfm_handle* h, SegWS& ws, int64_t n, const SRC& src, co
             row_apply_kernel<K, SRC><<<n > 0 ? (unsigned)h->sm_count * 2 : 1, 256, smem, st>>>(
                 ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0, ws.piece_start, ws.seg_cnt, src, ws.piece_sum, h->tb, h->emb_slots, od, ol,
                 (bool)h->need_emb, (bool)h->use_linear, (int)t, make_rr(h, t - 1));
+        }
+    } else if (gsum && route && !kBags && staged_ok) {
+        // requester side of the fused exchange: staged gradient operands, rows leave as coalesced stores over NVLink
+        if constexpr (std::is_same<SRC, GradSrc<K, false>>::value) {
+            using S2 = StageSrcPlain<K>;
+            const int smem = RowGsumCfg<K, S2>::SMEM;
+            static int attr = 0;
+            if (attr < smem) { CK(cudaFuncSetAttribute(row_gsum_kernel<K, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = smem; }
+            S2 s2{}; s2.s = src;
+            row_gsum_kernel<K, S2><<<n > 0 ? (unsigned)h->sm_count * 2 : 1, 256, smem, st>>>(ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0,
+                                                                                           ws.piece_start, ws.seg_cnt, s2, ws.piece_sum, route);
+        } else if constexpr (!kBags) {
+            const int smem = RowGsumCfg<K, SRC>::SMEM + src.aux_floats() * 4;
+            if (smem > 200 * 1024) FAIL(DFM_ERR_UNSUPPORTED, "internal: staged gradient-row kernel does not fit in shared memory");
+            static int attr = 0;
+            if (attr < smem) { CK(cudaFuncSetAttribute(row_gsum_kernel<K, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = smem; }
+            row_gsum_kernel<K, SRC><<<n > 0 ? (unsigned)h->sm_count * 2 : 1, 256, smem, st>>>(ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0,
+                                                                                            ws.piece_start, ws.seg_cnt, src, ws.piece_sum, route);
         }
     } else {
         row_update_kernel<K, SRC><<<n > 0 ? row_grid : 1, 256, 0, st>>>(ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0, ws.piece_start, ws.seg_cnt, src,

@@ -359,39 +359,22 @@ __global__ void seg_fill_kernel(const uint32_t* __restrict__ keys, const uint32_
     }
 }
 
-// Single-pass segment builder: flags + scan + fill of the three kernels above in ONE launch.  Tiles are handed out by
-// an atomic ticket; a tile publishes its (rows, pieces) count and obtains the counts of all earlier tiles by decoupled
-// look-back along 64-bit status words {prefix flag, aggregate flag, rows:31, pieces:31}.  The element count may live in
-// device memory (n_dev), so the row-sharded owner can segment what its peers pushed without a host round trip.
+// Two-launch segment builder (flags + scan + fill of the three kernels above were 5 launches):
+//   seg_count_kernel  every tile of 2048 sorted pairs counts its row heads / piece heads; the LAST block to finish
+//                     turns the per-tile counts into exclusive prefixes (one thread walks 32 tiles at a time) and
+//                     closes the lists (totals, number of valid lookups, sentinels)
+//   seg_fill_kernel2  every tile re-derives its flags, scans them inside the block and writes row_start / row_piece0 /
+//                     piece_start / urow / uval (+ pos_row for the sharded requester)
+// A single-launch version with decoupled look-back measured 67 us for 832 tiles (the chain starts cold: every tile
+// publishes at the same moment), this one needs no spinning.  The element count may live in device memory (n_dev).
 constexpr int SB_ITEMS = 8, SB_TILE = 256 * SB_ITEMS;
-constexpr unsigned long long SB_PREFIX = 1ull << 63, SB_AGG = 1ull << 62;
-__global__ void __launch_bounds__(256) seg_build_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n_host,
-                                                        const uint32_t* __restrict__ n_dev, uint32_t R, unsigned long long* status,
-                                                        uint32_t* __restrict__ ticket, SegCounts* __restrict__ cnt,
-                                                        uint32_t* __restrict__ row_start, uint32_t* __restrict__ row_piece0,
-                                                        uint32_t* __restrict__ piece_start, uint32_t* __restrict__ urow, uint32_t* __restrict__ uval,
-                                                        uint32_t* __restrict__ pos_row /* optional: unique-row index of every sorted position */) {
-    __shared__ unsigned long long wtot[33];
-    __shared__ unsigned long long s_excl;
-    __shared__ uint32_t s_tile;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const int64_t tile = s_tile;
-    const int64_t n = n_dev ? (int64_t)*reinterpret_cast<const volatile uint32_t*>(n_dev) : n_host;
-    if (tile * SB_TILE >= n) {
-        if (tile == 0 && tid == 0) {      // empty list
-            cnt->n_rows = 0; cnt->n_pieces = 0; cnt->n_valid = 0; cnt->n_hot = 0;
-            row_start[0] = 0; row_piece0[0] = 0; piece_start[0] = 0;
-        }
-        return;
-    }
-    const int64_t i0 = tile * SB_TILE + (int64_t)tid * SB_ITEMS;
-    uint32_t k[SB_ITEMS];
+
+__device__ __forceinline__ void seg_tile_flags(const uint32_t* __restrict__ keys, int64_t i0, int64_t n, uint32_t R, uint32_t (&k)[SB_ITEMS],
+                                               uint32_t& rows, uint32_t& pieces, uint32_t& rmask, uint32_t& pmask, uint32_t& vmask) {
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j) k[j] = (i0 + j < n) ? keys[i0 + j] : 0xffffffffu;
     uint32_t prev = (i0 > 0 && i0 < n) ? keys[i0 - 1] : 0xffffffffu;
-    uint32_t rows = 0, pieces = 0, rmask = 0, pmask = 0, vmask = 0;
+    rows = 0; pieces = 0; rmask = 0; pmask = 0; vmask = 0;
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j) {
         const int64_t i = i0 + j;
@@ -402,7 +385,82 @@ __global__ void __launch_bounds__(256) seg_build_kernel(const uint32_t* __restri
         rmask |= (uint32_t)rh << j; pmask |= (uint32_t)ph << j; vmask |= (uint32_t)valid << j;
         prev = k[j];
     }
-    // block exclusive scan of the packed (rows << 32 | pieces) counts
+}
+
+__global__ void __launch_bounds__(256) seg_count_kernel(const uint32_t* __restrict__ keys, int64_t n_host, const uint32_t* __restrict__ n_dev,
+                                                        uint32_t R, unsigned long long* tile_cnt, unsigned int* __restrict__ ticket,
+                                                        SegCounts* __restrict__ cnt, uint32_t* __restrict__ row_start,
+                                                        uint32_t* __restrict__ row_piece0, uint32_t* __restrict__ piece_start) {
+    __shared__ unsigned long long wsum[8];
+    __shared__ bool last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n = n_dev ? (int64_t)*reinterpret_cast<const volatile uint32_t*>(n_dev) : n_host;
+    const int64_t tiles = (n + SB_TILE - 1) / SB_TILE;
+    const int64_t tile = blockIdx.x;
+    if (tile < tiles) {
+        uint32_t k[SB_ITEMS], rows, pieces, rmask, pmask, vmask;
+        seg_tile_flags(keys, tile * SB_TILE + (int64_t)tid * SB_ITEMS, n, R, k, rows, pieces, rmask, pmask, vmask);
+        unsigned long long v = ((unsigned long long)rows << 32) | pieces;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) wsum[warp] = v;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long t = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += wsum[w];
+            tile_cnt[tile] = t;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (warp != 0) return;
+    // warp 0: exclusive prefix over the tiles, 32 at a time
+    unsigned long long run = 0;
+    for (int64_t t0 = 0; t0 < tiles; t0 += 32) {
+        const int64_t t = t0 + lane;
+        const unsigned long long c = t < tiles ? __ldcg(tile_cnt + t) : 0ull;
+        unsigned long long inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += x;
+        }
+        if (t < tiles) tile_cnt[t] = run + inc - c;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) {
+        const uint32_t Ur = (uint32_t)(run >> 32), P = (uint32_t)(run & 0xffffffffu);
+        int64_t lo = 0, hi = n;                        // keys are sorted, the invalid ones (>= R) last
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (keys[mid] < R) lo = mid + 1; else hi = mid;
+        }
+        const uint32_t nv = (uint32_t)lo;
+        cnt->n_rows = Ur; cnt->n_pieces = P; cnt->n_valid = nv; cnt->n_hot = 0;
+        row_start[Ur] = nv; row_piece0[Ur] = P; piece_start[P] = nv;
+        *ticket = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) seg_fill_kernel2(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n_host,
+                                                        const uint32_t* __restrict__ n_dev, uint32_t R,
+                                                        const unsigned long long* __restrict__ tile_cnt,
+                                                        uint32_t* __restrict__ row_start, uint32_t* __restrict__ row_piece0,
+                                                        uint32_t* __restrict__ piece_start, uint32_t* __restrict__ urow, uint32_t* __restrict__ uval,
+                                                        uint32_t* __restrict__ pos_row /* optional: unique-row index of every sorted position */) {
+    __shared__ unsigned long long wtot[33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n = n_dev ? (int64_t)*reinterpret_cast<const volatile uint32_t*>(n_dev) : n_host;
+    const int64_t tile = blockIdx.x;
+    if (tile * SB_TILE >= n) return;
+    const int64_t i0 = tile * SB_TILE + (int64_t)tid * SB_ITEMS;
+    uint32_t k[SB_ITEMS], rows, pieces, rmask, pmask, vmask;
+    seg_tile_flags(keys, i0, n, R, k, rows, pieces, rmask, pmask, vmask);
     const unsigned long long mine = ((unsigned long long)rows << 32) | pieces;
     unsigned long long inc = mine;
 #pragma unroll
@@ -421,31 +479,9 @@ __global__ void __launch_bounds__(256) seg_build_kernel(const uint32_t* __restri
             if (lane >= o) winc += t;
         }
         if (lane < 8) wtot[lane] = winc - w;
-        if (lane == 7) wtot[32] = winc;
     }
     __syncthreads();
-    const unsigned long long tile_tot = wtot[32];
-    if (tid == 0) {
-        volatile unsigned long long* st = status;
-        auto enc = [](unsigned long long v) { return ((v >> 32) << 31) | (v & 0x7fffffffull); };
-        auto dec = [](unsigned long long e) { return (((e >> 31) & 0x7fffffffull) << 32) | (e & 0x7fffffffull); };
-        unsigned long long excl = 0;
-        if (tile == 0) {
-            st[0] = SB_PREFIX | enc(tile_tot);
-        } else {
-            st[tile] = SB_AGG | enc(tile_tot);
-            for (int64_t tt = tile - 1; tt >= 0; --tt) {
-                unsigned long long e;
-                do { e = st[tt]; } while ((e & (SB_PREFIX | SB_AGG)) == 0ull);
-                excl += dec(e);
-                if (e & SB_PREFIX) break;
-            }
-            st[tile] = SB_PREFIX | enc(excl + tile_tot);
-        }
-        s_excl = excl;
-    }
-    __syncthreads();
-    unsigned long long run = s_excl + wtot[warp] + (inc - mine);
+    const unsigned long long run = __ldg(tile_cnt + tile) + wtot[warp] + (inc - mine);
     uint32_t ridx = (uint32_t)(run >> 32), pidx = (uint32_t)(run & 0xffffffffu);
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j) {
@@ -462,19 +498,6 @@ __global__ void __launch_bounds__(256) seg_build_kernel(const uint32_t* __restri
             ++pidx;
         }
         if (pos_row && ((vmask >> j) & 1u)) pos_row[i0 + j] = ridx - 1;
-    }
-    // the last tile closes the lists: totals, number of valid (non-empty-bag) lookups, sentinels
-    if ((tile + 1) * SB_TILE >= n && tid == 0) {
-        const unsigned long long tot = s_excl + tile_tot;
-        const uint32_t Ur = (uint32_t)(tot >> 32), P = (uint32_t)(tot & 0xffffffffu);
-        int64_t lo = 0, hi = n;                        // keys are sorted, the invalid ones (>= R) last
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (keys[mid] < R) lo = mid + 1; else hi = mid;
-        }
-        const uint32_t nv = (uint32_t)lo;
-        cnt->n_rows = Ur; cnt->n_pieces = P; cnt->n_valid = nv; cnt->n_hot = 0;
-        row_start[Ur] = nv; row_piece0[Ur] = P; piece_start[P] = nv;
     }
 }
 
