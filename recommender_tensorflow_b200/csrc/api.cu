@@ -17,6 +17,7 @@
 #include "prims.cuh"
 #include "small_mlp.cuh"
 #include "fused_small.cuh"
+#include "fused_rows_args.cuh"
 #include "tc_gemm.cuh"
 #include "xchg.cuh"
 
@@ -55,6 +56,7 @@ struct SegWS {
     SegCounts* seg_cnt = nullptr;
     uint32_t *row_start = nullptr, *row_piece0 = nullptr, *piece_start = nullptr, *urow = nullptr, *uval = nullptr, *hot_list = nullptr;
     uint32_t* pos_row = nullptr;     // sharded requester: unique-row index of every sorted position
+    uint32_t* n_compact = nullptr;   // record-staged step: {lookups that go through the sort, once-only lookups} of the step
     float* piece_sum = nullptr;
     int cur = 0;     // which keys/vals buffer holds the sorted list
     const uint32_t* skeys() const { return keys[cur]; }
@@ -154,6 +156,10 @@ struct dfm_handle {
     // fused small-tower step (fused_small.cuh): gather + FM + tower forward/backward in one kernel
     bool fused = false; size_t fused_smem = 0; int fused_grid = 0, n_numacc = 0;
     float *num_partial = nullptr, *num_scratch = nullptr; unsigned int* fused_done = nullptr;
+    // record-staged step with the in-kernel optimizer for once-only rows (fused_rows.cuh)
+    bool fused_rows = false; size_t fr_smem = 0; uint32_t* claim = nullptr; uint32_t claim_mask = 0; size_t claim_bytes = 0;
+    bool claim_live = false;          // this step's claim table is filled: once-only rows are applied by fused_rows_kernel
+    bool last_step_rows = false;
 
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     // small tables: the sort / segment stage runs on a side stream next to the gather and the tower (see train_impl)
@@ -236,6 +242,7 @@ static int alloc_ws(dfm_handle* h, SegWS& ws, int64_t n, int K, bool with_pos_ro
     if (dalloc(h, &ws.piece_start, n + 1)) return DFM_ERR_CUDA;
     if (dalloc(h, &ws.urow, n + 1)) return DFM_ERR_CUDA;
     if (dalloc(h, &ws.uval, n + 1)) return DFM_ERR_CUDA;
+    if (dalloc(h, &ws.n_compact, 2)) return DFM_ERR_CUDA;
     if (dalloc(h, &ws.hot_list, (size_t)(2 * (n / 32 + 2)))) return DFM_ERR_CUDA;
     if (dalloc(h, &ws.piece_sum, (size_t)(2 * (n / 32 + 2)) * (K + 4))) return DFM_ERR_CUDA;
     return DFM_OK;
@@ -243,7 +250,7 @@ static int alloc_ws(dfm_handle* h, SegWS& ws, int64_t n, int K, bool with_pos_ro
 
 static void free_ws(SegWS& ws) {
     void* ptrs[] = {ws.keys[0], ws.keys[1], ws.vals[0], ws.vals[1], ws.sort_temp, ws.flags, ws.scan_temp, ws.seg_total, ws.seg_cnt,
-                    ws.row_start, ws.row_piece0, ws.piece_start, ws.urow, ws.uval, ws.hot_list, ws.piece_sum, ws.pos_row};
+                    ws.row_start, ws.row_piece0, ws.piece_start, ws.urow, ws.uval, ws.hot_list, ws.piece_sum, ws.pos_row, ws.n_compact};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -259,7 +266,7 @@ static void free_all(dfm_handle* h) {
     cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, h->d_row_off, h->tb.rec, h->dw,
                     h->ds1, h->ds2, h->dg, h->ids, h->h0, h->s, h->zacc, h->logits, h->dz, h->dE, h->splitk, h->colpart, h->head_part,
-                    h->d_loss, h->d_dzsum, h->d_err, h->num_partial, h->num_scratch, h->fused_done, h->up_partial, h->w0_partial, h->tc_w, h->head_gpart, h->d_slot_col, h->d_slot_j, h->d_field_slot0, h->inv_cnt, h->uidx,
+                    h->d_loss, h->d_dzsum, h->d_err, h->num_partial, h->num_scratch, h->fused_done, h->claim, h->up_partial, h->w0_partial, h->tc_w, h->head_gpart, h->d_slot_col, h->d_slot_j, h->d_field_slot0, h->inv_cnt, h->uidx,
                     h->req_rows, h->d_counts};
     for (void* p : ptrs) if (p) cudaFree(p);
     free_ws(h->ws);
@@ -646,6 +653,21 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
                     default: rcf = fused_set_attr<32>(h); break;
                 }
                 if (rcf) return rcf;
+                // record-staged variant: the shapes BASELINE.json names (k = 16, first hidden layer 16), unsharded
+                const int rs = K + 4 + h->emb_slots * K;
+                if (fused_rows_supported(K, m.H[0], h->dc, h->dn) && h->world == 1 && !h->has_bags && h->dropout == 0.f && h->need_emb &&
+                    getenv("DFM_NO_FUSED_ROWS") == nullptr) {
+                    h->fr_smem = fused_rows_smem_bytes(m, K, h->dc, h->dn, rs);
+                    if (h->fr_smem <= 227 * 1024) {
+                        h->fused_rows = true;
+                        CK(fused_rows_set_attr((int)h->fr_smem));
+                        uint64_t slots = 1024;
+                        while (slots < (uint64_t)h->R && slots < (1ull << 27)) slots <<= 1;
+                        h->claim_mask = (uint32_t)(slots - 1);
+                        h->claim_bytes = (size_t)(slots / 4);
+                        if (dalloc(h, &h->claim, h->claim_bytes / 4)) return DFM_ERR_CUDA;
+                    }
+                }
             } else if (h->small_smem <= 200 * 1024) {
                 h->small_mlp = true;
                 const int tiles = (int)((Bm + SM_TB - 1) / SM_TB);
@@ -882,13 +904,14 @@ struct Phase {
 };
 
 template <int K>
-static void launch_transform(dfm_handle* h, const BatchPtrs& bp, int B, bool with_keys, int32_t* ids_out, cudaStream_t st) {
+static void launch_transform(dfm_handle* h, const BatchPtrs& bp, int B, bool with_keys, int32_t* ids_out, cudaStream_t st,
+                             bool with_claim = false) {
     if (h->dc == 0) return;
     transform_kernel<32><<<cdiv(B, 32), 256, (size_t)32 * h->dcs * 4, st>>>(
         bp, h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, B, h->dcs, h->has_bags ? h->d_slot_col : nullptr,
         h->has_bags ? h->d_slot_j : nullptr, h->d_row_off, (uint32_t)h->R, ids_out,
-        with_keys ? h->ws.keys[0] : nullptr, with_keys ? h->ws.vals[0] : nullptr, h->d_err,
-        with_keys && h->n_tiny ? h->d_key_slot : nullptr, h->n_big);
+        with_keys ? h->ws.keys[with_claim ? 1 : 0] : nullptr, with_keys ? h->ws.vals[with_claim ? 1 : 0] : nullptr, h->d_err,
+        with_keys && h->n_tiny ? h->d_key_slot : nullptr, h->n_big, with_claim ? h->claim : nullptr, h->claim_mask);
     h->launches++;
 }
 
@@ -1375,6 +1398,7 @@ static int sparse_update(dfm_handle* h, SegWS& ws, int64_t n, const SRC& src, co
     return DFM_OK;
 }
 
+
 struct StepOpts { OptDev od, ol; };
 static StepOpts step_opts(const dfm_handle* h) {
     StepOpts o;
@@ -1386,8 +1410,8 @@ static void commit_step(dfm_handle* h, const StepOpts&, int64_t t) { h->step = t
 
 // ---- fused small-tower step (fused_small.cuh)
 template <int K>
-static int launch_fused(dfm_handle* h, const BatchPtrs& bp, int B, const float* labels, float scale, float* logits_out,
-                        const float* rowbuf, int64_t upto, cudaStream_t st) {
+static FusedArgs make_fused_args(dfm_handle* h, const BatchPtrs& bp, int B, const float* labels, float scale, float* logits_out,
+                                 const float* rowbuf, int64_t upto) {
     FusedArgs a{};
     a.ids = h->ids; a.B = B; a.dc = h->dc; a.dn = h->dn; a.n_slots = h->dcs;
     a.row_off = h->d_row_off; a.tb = h->tb; a.bp = bp; a.dw = h->dw;
@@ -1408,6 +1432,35 @@ static int launch_fused(dfm_handle* h, const BatchPtrs& bp, int B, const float* 
     a.up_partial = h->up_partial; a.w0_partial = h->w0_partial; a.num_partial = h->num_partial; a.head_part = h->head_part;
     a.D = h->sm.D; a.n_numacc = h->n_numacc;
     a.es_stride = fs_es_stride(h->sm.D);
+    return a;
+}
+
+// record-staged step (fused_rows.cuh): gather + tower forward/backward + the optimizer of once-only rows in one kernel
+template <int K>
+static int launch_fused_rows(dfm_handle* h, const BatchPtrs& bp, int B, const float* labels, float scale, float* logits_out, int64_t upto,
+                             const StepOpts* so, int64_t t, cudaStream_t st) {
+    if constexpr (K == 16) {
+        FusedRowsArgs A{};
+        A.f = make_fused_args<K>(h, bp, B, labels, scale, logits_out, nullptr, upto);
+        A.claim = (so && h->claim_live) ? h->claim : nullptr; A.claim_mask = h->claim_mask;
+        A.emb_slots = h->emb_slots;
+        A.rs = K + 4 + h->emb_slots * K;
+        A.sst = fr_sst(h->dc, h->dn, K, A.rs);
+        A.step = (int)t;
+        if (so) { A.od_t = so->od; A.ol_t = so->ol; }
+        A.numg_partial = h->num_partial;
+        const int grid = fused_rows_grid(B, h->sm_count);
+        CK(fused_rows_launch(A, grid, h->fr_smem, st));
+        h->launches++;
+        return DFM_OK;
+    }
+    return DFM_ERR_UNSUPPORTED;
+}
+
+template <int K>
+static int launch_fused(dfm_handle* h, const BatchPtrs& bp, int B, const float* labels, float scale, float* logits_out,
+                        const float* rowbuf, int64_t upto, cudaStream_t st) {
+    FusedArgs a = make_fused_args<K>(h, bp, B, labels, scale, logits_out, rowbuf, upto);
     const int grid = std::min((B + FS_TS - 1) / FS_TS, h->fused_grid);
     const int H1 = h->sm.H[0];
     const int need_nc = ((h->dc + h->dn) + (256 / (H1 / 4)) / K - 1) / ((256 / (H1 / 4)) / K);     // ceil(d / fields per column group)
@@ -1447,13 +1500,14 @@ static int fused_set_attr(dfm_handle* h) {
 }
 
 // per-CTA partials of the fused kernel -> dense gradient buffer, loss, dz sum (one launch)
-static int launch_fused_reduce(dfm_handle* h, int B, float scale, float* loss_out, cudaStream_t st) {
+static int launch_fused_reduce(dfm_handle* h, int B, float scale, float* loss_out, cudaStream_t st, bool rows = false) {
     const DenseT* ne = find_dense(h, "num_emb"); const DenseT* nl = find_dense(h, "num_lin"); const DenseT* bs = find_dense(h, "bias");
     FusedReduceArgs r{};
     r.up_partial = h->up_partial; r.w0_partial = h->w0_partial; r.num_partial = h->num_partial; r.head_part = h->head_part;
-    r.n_cta = std::min((B + FS_TS - 1) / FS_TS, h->fused_grid);
+    r.n_cta = rows ? fused_rows_grid(B, h->sm_count) : std::min((B + FS_TS - 1) / FS_TS, h->fused_grid);
     r.up_count = h->sm.up_count; r.up_begin = h->sm.up_begin; r.off_W0 = h->sm.off_W[0]; r.w0_count = h->sm.D * h->sm.H[0];
-    r.n_numacc = h->n_numacc;
+    r.n_numacc = rows ? h->dn * h->K + h->dn : h->n_numacc;
+    r.direct_num = rows ? 1 : 0;
     r.dg = h->dg; r.num_scratch = h->num_scratch; r.done = h->fused_done;
     r.dw = h->dw; r.off_num_emb = ne ? (int)ne->off : -1; r.off_num_lin = nl ? (int)nl->off : -1; r.off_bias = bs ? (int)bs->off : -1;
     r.dc = h->dc; r.dn = h->dn; r.K = h->K; r.H1 = h->sm.H[0]; r.use_mf = h->use_mf;
@@ -1499,13 +1553,19 @@ static int train_fused(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_ou
         Phase ph(h, st);
         const bool prefetched = h->prefetch_B == B && h->dc > 0 && h->prefetch_tag == bp.cat[0];
         if (h->prefetch_B >= 0 && !prefetched) h->prefetch_B = -1;
+        // record-staged step: once-only rows are updated inside the kernel (the claim table is filled by the transform,
+        // so a prefetched batch - ids computed earlier, no claims - takes the older kernel)
+        static const bool inline_ok = getenv("DFM_NO_INLINE_APPLY") == nullptr;
+        const bool rows = h->fused_rows && !prefetched && inline_ok;
         if (prefetched) {
             CK(cudaStreamWaitEvent(st, h->ev_prefetch, 0));
             std::swap(h->ws, h->ws_next); std::swap(h->ids, h->ids_next);
             h->prefetch_B = -1;
         } else {
-            launch_transform<K>(h, bp, B, true, h->ids, st);                                    // K1
+            if (rows) CK(cudaMemsetAsync(h->claim, 0, h->claim_bytes, st));
+            launch_transform<K>(h, bp, B, true, h->ids, st, rows);                              // K1 (+ claim table; pairs into buffer 1)
         }
+        h->claim_live = rows; h->last_step_rows = rows;
         ph.next();
         // The forward pass reads the table rows as stored and replays the deferred Adam decay in registers, so it does
         // not need the list of touched rows: sort + segments (many small dependent launches) run on the side stream
@@ -1514,22 +1574,29 @@ static int train_fused(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_ou
         if (side) {
             CK(cudaEventRecord(h->ev_fork, st));
             CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-            if ((rc = build_segments(h, h->ws, n, (uint32_t)h->R, h->key_bits, h->side_stream, nullptr))) return rc;
+            if (rows) CK(fused_rows_compact(h->ws.keys[1], h->ws.vals[1], n, (uint32_t)h->R, h->claim, h->claim_mask, h->ws.keys[0], h->ws.vals[0],
+                                            reinterpret_cast<uint32_t*>(h->ws.flags), h->ws.n_compact, h->side_stream, &h->launches));
+            if ((rc = build_segments(h, h->ws, n, (uint32_t)h->R, h->key_bits, h->side_stream, nullptr, rows ? h->ws.n_compact : nullptr))) return rc;
             CK(cudaEventRecord(h->ev_join, h->side_stream));
             ph.next(); ph.next();
         } else if (!prefetched) {
-            if ((rc = build_segments(h, h->ws, n, (uint32_t)h->R, h->key_bits, st, &ph))) return rc;
+            if (rows) CK(fused_rows_compact(h->ws.keys[1], h->ws.vals[1], n, (uint32_t)h->R, h->claim, h->claim_mask, h->ws.keys[0], h->ws.vals[0],
+                                            reinterpret_cast<uint32_t*>(h->ws.flags), h->ws.n_compact, st, &h->launches));
+            if ((rc = build_segments(h, h->ws, n, (uint32_t)h->R, h->key_bits, st, &ph, rows ? h->ws.n_compact : nullptr))) return rc;
         } else {
             ph.next(); ph.next();
         }
         ph.next();                                                                               // (no catch-up pass)
         const float scale = h->loss_red == DFM_LOSS_MEAN ? 1.0f / (float)B : 1.0f;
-        if ((rc = launch_fused<K>(h, bp, B, bp.labels, scale, logits_out, nullptr, t - 1, st))) return rc;
+        if (h->fused_rows) rc = launch_fused_rows<K>(h, bp, B, bp.labels, scale, logits_out, t - 1, &so, t, st);
+        else rc = launch_fused<K>(h, bp, B, bp.labels, scale, logits_out, nullptr, t - 1, st);
+        if (rc) return rc;
         ph.next(); ph.next();                                                                    // gather + tower forward/backward top
-        if ((rc = launch_fused_reduce(h, B, scale, loss_out, st))) return rc;
+        if ((rc = launch_fused_reduce(h, B, scale, loss_out, st, h->fused_rows))) return rc;
         ph.next(); ph.next();                                                                    // loss, dense gradients
         if (side) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
         if ((rc = fused_sparse_update<K>(h, h->ws, n, so, t, nullptr, nullptr, st, &ph))) return rc;
+        h->claim_live = false;
         if (h->n_dense) {
             dense_apply_kernel<<<cdiv(h->n_dense, 256), 256, 0, st>>>(h->dw, h->ds1, h->ds2, h->dg, h->n_deep, h->n_dense, so.od, so.ol);
             h->launches++;
@@ -1788,7 +1855,13 @@ extern "C" int64_t dfm_last_unique_rows(dfm_handle* h) {
     SegCounts sc{};
     cudaDeviceSynchronize();
     if (cudaMemcpy(&sc, h->ws.seg_cnt, sizeof sc, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    return (int64_t)sc.n_rows;
+    int64_t once = 0;
+    if (h->last_step_rows) {      // record-staged step: the sorted list holds only the rows looked up more than once
+        uint32_t nc[2] = {0, 0};
+        if (cudaMemcpy(nc, h->ws.n_compact, sizeof nc, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        once = nc[1];
+    }
+    return (int64_t)sc.n_rows + once;
 }
 
 // Restore point: variables + slots were loaded with dfm_set_tensor from a checkpoint taken at `step`

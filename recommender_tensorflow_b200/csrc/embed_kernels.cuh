@@ -14,6 +14,19 @@ __host__ __device__ __forceinline__ uint32_t payload_pack(uint32_t b, uint32_t s
 __host__ __device__ __forceinline__ uint32_t payload_sample(uint32_t v) { return v >> PAYLOAD_SLOT_BITS; }
 __host__ __device__ __forceinline__ uint32_t payload_slot(uint32_t v) { return v & ((1u << PAYLOAD_SLOT_BITS) - 1u); }
 
+// Claim table of one step: 2 bits per slot (slot = global row & mask), 01 = looked up once in the batch, 11 = more than
+// once.  transform_kernel marks, fused_rows_kernel (applies the gradient of once-only rows itself) and row_apply_kernel
+// (skips them) test; a slot shared by two rows of the batch reads "more than once" for both, which is always safe.
+__device__ __forceinline__ void claim_mark(uint32_t* __restrict__ claim, uint32_t mask, uint32_t row) {
+    const uint32_t s = row & mask, sh = (s & 15u) * 2u;
+    const uint32_t old = atomicOr(claim + (s >> 4), 1u << sh);
+    if ((old >> sh) & 1u) atomicOr(claim + (s >> 4), 2u << sh);
+}
+__device__ __forceinline__ bool claim_once(const uint32_t* __restrict__ claim, uint32_t mask, uint32_t row) {
+    const uint32_t s = row & mask;
+    return ((__ldg(claim + (s >> 4)) >> ((s & 15u) * 2u)) & 3u) == 1u;
+}
+
 // =============================================================================================
 // optimizer arithmetic, in the float32 op order of the TF-1.12 kernels
 // =============================================================================================
@@ -260,7 +273,8 @@ __global__ void __launch_bounds__(256) transform_kernel(BatchPtrs bp, const ColD
                                                         const uint32_t* __restrict__ row_off, uint32_t R,
                                                         int32_t* __restrict__ ids, uint32_t* __restrict__ keys,
                                                         uint32_t* __restrict__ vals, int* err,
-                                                        const int32_t* __restrict__ key_slot, int n_key_slots) {
+                                                        const int32_t* __restrict__ key_slot, int n_key_slots,
+                                                        uint32_t* __restrict__ claim = nullptr, uint32_t claim_mask = 0) {
     extern __shared__ int32_t sid[];  // [TILE][n_slots]
     const int b0 = blockIdx.x * TILE;
     const int nb = min(TILE, B - b0);
@@ -280,6 +294,7 @@ __global__ void __launch_bounds__(256) transform_kernel(BatchPtrs bp, const ColD
         int32_t id = sid[w];
         int slot = w % n_slots;
         ids[g0 + w] = id;
+        if (claim && id >= 0) claim_mark(claim, claim_mask, row_off[slot_col ? slot_col[slot] : slot] + (uint32_t)id);
         if (keys) {
             // key_slot: only the listed slots go through the sort (tiny-vocabulary columns are reduced densely, see
             // tiny_reduce_kernel); their pairs are packed [sample][key slot], the payload keeps the full-slot numbering
@@ -296,7 +311,7 @@ __global__ void __launch_bounds__(256) transform_kernel(BatchPtrs bp, const ColD
     }
 }
 
-__global__ void fingerprint_kernel(const uint8_t* __restrict__ bytes, const int32_t* __restrict__ offs, int64_t n,
+static __global__ void fingerprint_kernel(const uint8_t* __restrict__ bytes, const int32_t* __restrict__ offs, int64_t n,
                                    uint64_t* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = fh::fp64_mem(bytes + offs[i], offs[i + 1] - offs[i]);
@@ -313,7 +328,7 @@ __device__ __forceinline__ void seg_heads(const uint32_t* __restrict__ keys, int
     ph = valid && (rh || (i % PIECE_C) == 0);
 }
 
-__global__ void seg_flag_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t R,
+static __global__ void seg_flag_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t R,
                                 unsigned long long* __restrict__ flags, SegCounts* __restrict__ cnt) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -328,7 +343,7 @@ __global__ void seg_flag_kernel(const uint32_t* __restrict__ keys, int64_t n, ui
     }
 }
 
-__global__ void seg_fill_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n, uint32_t R,
+static __global__ void seg_fill_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n, uint32_t R,
                                 const unsigned long long* __restrict__ scanned,
                                 const unsigned long long* __restrict__ total, SegCounts* __restrict__ cnt,
                                 uint32_t* __restrict__ row_start, uint32_t* __restrict__ row_piece0,
@@ -387,7 +402,7 @@ __device__ __forceinline__ void seg_tile_flags(const uint32_t* __restrict__ keys
     }
 }
 
-__global__ void __launch_bounds__(256) seg_count_kernel(const uint32_t* __restrict__ keys, int64_t n_host, const uint32_t* __restrict__ n_dev,
+static __global__ void __launch_bounds__(256) seg_count_kernel(const uint32_t* __restrict__ keys, int64_t n_host, const uint32_t* __restrict__ n_dev,
                                                         uint32_t R, unsigned long long* tile_cnt, unsigned int* __restrict__ ticket,
                                                         SegCounts* __restrict__ cnt, uint32_t* __restrict__ row_start,
                                                         uint32_t* __restrict__ row_piece0, uint32_t* __restrict__ piece_start) {
@@ -447,7 +462,7 @@ __global__ void __launch_bounds__(256) seg_count_kernel(const uint32_t* __restri
     }
 }
 
-__global__ void __launch_bounds__(256) seg_fill_kernel2(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n_host,
+static __global__ void __launch_bounds__(256) seg_fill_kernel2(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n_host,
                                                         const uint32_t* __restrict__ n_dev, uint32_t R,
                                                         const unsigned long long* __restrict__ tile_cnt,
                                                         uint32_t* __restrict__ row_start, uint32_t* __restrict__ row_piece0,
@@ -680,7 +695,7 @@ struct GradSrc {
 };
 
 // list the pieces of hot rows (rows with > DIRECT_T lookups); order is irrelevant, every piece sum goes to its own slot
-__global__ void __launch_bounds__(256) hot_pieces_kernel(const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ row_piece0,
+static __global__ void __launch_bounds__(256) hot_pieces_kernel(const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ row_piece0,
                                                          SegCounts* __restrict__ cnt, uint32_t* __restrict__ hot_list) {
     const uint32_t U = cnt->n_rows;
     for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += gridDim.x * blockDim.x) {
@@ -940,7 +955,7 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
 
 // dE = dz * (s - E) when there is no DNN tower (otherwise the last backward GEMM epilogue does it);
 // accumulate != 0 adds to an existing dE (hidden_units == [] case).
-__global__ void de_fm_kernel(const float* __restrict__ h0, const float* __restrict__ s, const float* __restrict__ dz,
+static __global__ void de_fm_kernel(const float* __restrict__ h0, const float* __restrict__ s, const float* __restrict__ dz,
                              int64_t total, int dK, int K, float* __restrict__ dE, int accumulate) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < total) {
@@ -955,7 +970,7 @@ __global__ void de_fm_kernel(const float* __restrict__ h0, const float* __restri
 // row sharding: rank r owns global rows {g : g % W == r}, stored at local index g / W
 // =============================================================================================
 // global-row sort key -> owner-major key  owner * Rl + local  (Rl = ceil(R / W)); empty bags -> W * Rl
-__global__ void shard_rekey_kernel(uint32_t* __restrict__ keys, int64_t n, uint32_t R, uint32_t W, uint32_t Rl) {
+static __global__ void shard_rekey_kernel(uint32_t* __restrict__ keys, int64_t n, uint32_t R, uint32_t W, uint32_t Rl) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         uint32_t g = keys[i];
@@ -963,7 +978,7 @@ __global__ void shard_rekey_kernel(uint32_t* __restrict__ keys, int64_t n, uint3
     }
 }
 // per sorted position: lookup -> unique index; per unique row: local row id for its owner + per-owner counts
-__global__ void __launch_bounds__(256) shard_uniq_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svals, int64_t n,
+static __global__ void __launch_bounds__(256) shard_uniq_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svals, int64_t n,
                                                          uint32_t limit, uint32_t Rl, uint32_t W, int n_slots,
                                                          const uint32_t* __restrict__ pos_row, uint32_t* __restrict__ uidx,
                                                          uint32_t* __restrict__ req_rows, int32_t* __restrict__ counts) {
@@ -991,7 +1006,7 @@ __global__ void __launch_bounds__(256) shard_uniq_kernel(const uint32_t* __restr
     __syncthreads();
     if (W <= 64 && threadIdx.x < W && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sc[threadIdx.x]);
 }
-__global__ void iota_kernel(uint32_t* __restrict__ v, int64_t n) {
+static __global__ void iota_kernel(uint32_t* __restrict__ v, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] = (uint32_t)i;
 }

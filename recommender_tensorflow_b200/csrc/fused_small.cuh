@@ -495,16 +495,24 @@ struct FusedReduceArgs {
     float* dg; float* num_scratch; unsigned int* done;
     const float* dw; int off_num_emb, off_num_lin, off_bias, dc, dn, K, H1, use_mf;
     float loss_scale; float *loss_out, *loss_copy, *dzsum_out;
+    int direct_num;       // fused_rows_kernel: num_partial holds [dn*K | dn] finished numeric gradients per CTA (n_numacc = dn*K + dn)
 };
 
-__global__ void __launch_bounds__(256) fused_reduce_kernel(FusedReduceArgs r) {
+static __global__ void __launch_bounds__(256) fused_reduce_kernel(FusedReduceArgs r) {
     const int total = r.up_count + r.w0_count + r.n_numacc;
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i < total) {
         const float* p; size_t stride; float* dst;
         if (i < r.up_count) { p = r.up_partial + i; stride = r.up_count; dst = r.dg + r.up_begin + i; }
         else if (i < r.up_count + r.w0_count) { p = r.w0_partial + (i - r.up_count); stride = r.w0_count; dst = r.dg + r.off_W0 + (i - r.up_count); }
-        else { p = r.num_partial + (i - r.up_count - r.w0_count); stride = r.n_numacc; dst = r.num_scratch + (i - r.up_count - r.w0_count); }
+        else {
+            const int q = i - r.up_count - r.w0_count;
+            p = r.num_partial + q; stride = r.n_numacc; dst = r.num_scratch + q;
+            if (r.direct_num) {
+                if (q < r.dn * r.K) dst = r.off_num_emb >= 0 ? r.dg + r.off_num_emb + q : nullptr;
+                else dst = r.off_num_lin >= 0 ? r.dg + r.off_num_lin + (q - r.dn * r.K) : nullptr;
+            }
+        }
         float s = 0.f;
         int c = 0;
         for (; c + 8 <= r.n_cta; c += 8) {        // 8 independent loads in flight, added in CTA order
@@ -515,7 +523,7 @@ __global__ void __launch_bounds__(256) fused_reduce_kernel(FusedReduceArgs r) {
             for (int u = 0; u < 8; ++u) s += t[u];
         }
         for (; c < r.n_cta; ++c) s += __ldg(p + (size_t)c * stride);
-        *dst = s;
+        if (dst) *dst = s;
     }
     __shared__ float sa[256], sc[256];
     __shared__ bool last;
@@ -535,7 +543,7 @@ __global__ void __launch_bounds__(256) fused_reduce_kernel(FusedReduceArgs r) {
             if (r.off_bias >= 0) r.dg[r.off_bias] = sc[0];
         }
     }
-    if (r.dn <= 0) return;
+    if (r.dn <= 0 || r.direct_num) return;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) last = atomicAdd(r.done, 1u) == gridDim.x - 1;

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 }
 
 // out[i] = sum_z partial[z*stride + i]   (fixed order -> deterministic split-K)
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nz, size_t stride, int64_t count,
+static __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nz, size_t stride, int64_t count,
                                        float* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -228,7 +228,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nz
 
 // weighted column sums: part[chunk][j] = sum_{b in chunk} w[b] * X[b*ldx + j]   (w == nullptr -> 1)
 // block = 32 columns x 8 row phases; rows of a chunk are walked in a fixed order.
-__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ w,
+static __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ w,
                                                              int B, int N, int rows_per_chunk, float* __restrict__ part) {
     __shared__ float sm[8][33];
     const int col = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
 // part layout per chunk: [dn*K] then [dn].  One CTA per chunk of rows: the x columns of the chunk are staged in
 // shared memory, thread t owns output t and walks the rows in order (deterministic); the numeric part of a dE row
 // is contiguous, so the dn*K threads read it coalesced.
-__global__ void __launch_bounds__(256) numeric_grad_partial_kernel(BatchPtrs bp, const float* __restrict__ dE, int dK, int dc, int dn,
+static __global__ void __launch_bounds__(256) numeric_grad_partial_kernel(BatchPtrs bp, const float* __restrict__ dE, int dK, int dc, int dn,
                                                                    int K, const float* __restrict__ dz, int B, int rows_per_chunk,
                                                                    float* __restrict__ part) {
     extern __shared__ float xs[];           // [rows_per_chunk][dn + 1]: x columns, then dz
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) numeric_grad_partial_kernel(BatchPtrs bp,
 
 // head: z = zacc + h_L . Wo + bo ; loss_b = max(z,0) - z*y + log1p(exp(-|z|)) ; dz = (sigmoid(z)-y)*scale
 // one warp per sample; per-block partial sums of loss and dz (fixed order inside the block).
-__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ zacc, const float* __restrict__ hL, int H,
+static __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ zacc, const float* __restrict__ hL, int H,
                                                    const float* __restrict__ Wo, const float* __restrict__ bo,
                                                    const float* __restrict__ labels, int B, float scale,
                                                    float* __restrict__ logits, float* __restrict__ logits_out,
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 // loss = (sum of block partials) * loss_scale ; dzsum = sum of dz  (single thread block, fixed order)
 // o1..o3: further destinations (caller's loss buffer, gradients of the output bias and of the linear bias = sum of dz):
 // written here instead of by three 4-byte device-to-device copies on the critical path of the step
-__global__ void head_final_kernel(const float* __restrict__ part, int nblocks, float loss_scale, float* __restrict__ loss_out,
+static __global__ void head_final_kernel(const float* __restrict__ part, int nblocks, float loss_scale, float* __restrict__ loss_out,
                                   float* __restrict__ dzsum_out, float* __restrict__ loss_copy, float* __restrict__ dz_copy1,
                                   float* __restrict__ dz_copy2) {
     __shared__ float sa[256], sc[256];
@@ -436,7 +436,7 @@ __global__ void head_final_kernel(const float* __restrict__ part, int nblocks, f
 }
 
 // dh_L'[b,j] = dz[b] * Wo[j] * (h_L[b,j] > 0)
-__global__ void dh_last_kernel(const float* __restrict__ hL, const float* __restrict__ Wo, const float* __restrict__ dz,
+static __global__ void dh_last_kernel(const float* __restrict__ hL, const float* __restrict__ Wo, const float* __restrict__ dz,
                                int64_t total, int H, float* __restrict__ dh, float drop_scale) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < total) {
@@ -448,7 +448,7 @@ __global__ void dh_last_kernel(const float* __restrict__ hL, const float* __rest
 
 // dense optimizer apply over the packed dense-parameter buffer.  Elements [0, n_deep) use the deep
 // optimizer, [n_deep, n) the linear one (num_lin, bias).
-__global__ void dense_apply_kernel(float* __restrict__ w, float* __restrict__ s1, float* __restrict__ s2,
+static __global__ void dense_apply_kernel(float* __restrict__ w, float* __restrict__ s1, float* __restrict__ s2,
                                    const float* __restrict__ g, int64_t n_deep, int64_t n, OptDev od, OptDev ol) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -470,7 +470,7 @@ __device__ __forceinline__ float u01(uint64_t h) { return ((h >> 40) + 0.5f) * (
 // truncated normal(0, sigma) cut at 2 sigma (rejection on a counter stream), strided destination
 // (row_mul, row_add): the stream is keyed on the GLOBAL row g = local * row_mul + row_add, so a row-sharded model
 // initialised with seed S holds exactly the rows of the unsharded model initialised with seed S
-__global__ void init_trunc_normal_kernel(float* __restrict__ dst, uint64_t rows, int K, int row_stride, float sigma, uint64_t seed,
+static __global__ void init_trunc_normal_kernel(float* __restrict__ dst, uint64_t rows, int K, int row_stride, float sigma, uint64_t seed,
                                          uint64_t row_mul, uint64_t row_add) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * (uint64_t)K) return;
@@ -487,11 +487,11 @@ __global__ void init_trunc_normal_kernel(float* __restrict__ dst, uint64_t rows,
     }
     dst[r * (uint64_t)row_stride + c] = z * sigma;
 }
-__global__ void init_uniform_kernel(float* __restrict__ dst, int64_t n, float lim, uint64_t seed) {
+static __global__ void init_uniform_kernel(float* __restrict__ dst, int64_t n, float lim, uint64_t seed) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = (2.f * u01(splitmix64(seed ^ (uint64_t)i)) - 1.f) * lim;
 }
-__global__ void fill_strided_kernel(float* __restrict__ dst, uint64_t rows, int width, int row_stride, float val) {
+static __global__ void fill_strided_kernel(float* __restrict__ dst, uint64_t rows, int width, int row_stride, float val) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows * (uint64_t)width) dst[(i / width) * (uint64_t)row_stride + (i % width)] = val;
 }

@@ -75,7 +75,7 @@ __device__ __forceinline__ void replay_elem(float& w, float& m, float& v, const 
 }
 
 // T_n / U_{n,k} for every step s < cap from the alpha sequence (float64 accumulation; alpha holds cap + H + 1 entries)
-__global__ void replay_tables_kernel(const float* __restrict__ alpha, int cap, int H, double b1, double q,
+static __global__ void replay_tables_kernel(const float* __restrict__ alpha, int cap, int H, double b1, double q,
                                      float4* __restrict__ T4, float* __restrict__ U) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= cap) return;

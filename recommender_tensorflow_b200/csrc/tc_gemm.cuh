@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_persist_kernel(const __grid
 }
 
 // x -> (hi, lo) element-wise over a weight tensor (weights are static within a step)
-__global__ void split_tf32_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
+static __global__ void split_tf32_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         float v = x[i], h = tf32_hi(v);
@@ -622,7 +622,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int64_t n, float*
     }
 }
 // W [rows, cols] -> W^T hi / lo [cols, rows]
-__global__ void split_tf32_transpose_kernel(const float* __restrict__ x, int rows, int cols, float* __restrict__ hi, float* __restrict__ lo) {
+static __global__ void split_tf32_transpose_kernel(const float* __restrict__ x, int rows, int cols, float* __restrict__ hi, float* __restrict__ lo) {
     __shared__ float tile[32][33];
     int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
