@@ -162,6 +162,19 @@ int dfm_train_step_host_drain(dfm_handle* h, float* last_loss_host);
 int dfm_forward(dfm_handle* h, const dfm_raw_batch* dev_batch, float* logits_out_dev, void* stream);
 int dfm_forward_host(dfm_handle* h, const dfm_raw_batch* host_batch, float* logits_out_host);
 
+/* ---- layer_summary side outputs (reference: trainers/model_utils.py:4-6 `layer_summary`, called at trainers/deep_fm.py:43
+ * (linear logit), :89 (MF logit), :105 (every hidden layer, after dropout in TRAIN mode), :110 (DNN logit), :115 (logits)).
+ * One call recomputes those tensors for a device batch with a forward pass on the weights as of the latest step and
+ * reduces each to tf.nn.zero_fraction + the fields of TensorFlow's HistogramProto over its default bucket limits.
+ * Tensor order: linear (if use_linear), mf (if use_mf), hidden layer 0..L-1 and dnn logit (if use_dnn), logits.
+ * bucket_counts: [max_tensors][n limits] (may be NULL); train_mode != 0 applies the dropout mask of the NEXT train step. */
+typedef struct dfm_tensor_summary { double min, max, num, sum, sum_squares, zero_fraction; } dfm_tensor_summary;
+int dfm_summary_bucket_limits(double* limits_out, int32_t* n_out);
+int dfm_layer_summary(dfm_handle* h, const dfm_raw_batch* dev_batch, int32_t train_mode, dfm_tensor_summary* out, int64_t* bucket_counts,
+                      int32_t max_tensors, int32_t* n_tensors);
+/* host copy of a tensor summarised by the last call: 0 linear, 1 mf, 2 hidden [B, sum of hidden_units], 3 dnn logit, 4 logits */
+int dfm_layer_summary_tensor(dfm_handle* h, int32_t which, int64_t n, float* out_host);
+
 /* Materialise deferred non-lazy Adam decay on every table row (before checkpoint / compare). */
 int dfm_flush(dfm_handle* h, void* stream);
 /* Wait for the handle's work and report sticky device-side errors (e.g. DFM_ERR_OUT_OF_RANGE). */

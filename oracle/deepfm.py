@@ -165,6 +165,27 @@ class OracleDeepFM:
             cache["acts"] = acts
         return (z, cache) if keep else z
 
+    def layer_tensors(self, ids, x=None, train=True):
+        """The tensors the reference hands to layer_summary (trainers/deep_fm.py:43,89,105,110,115), by TF name scope."""
+        W = {n: v.w for n, v in self.vars.items()}
+        z, c = self.forward(ids, x, keep=True, train=train)
+        out = {}
+        if self.use_linear:
+            vm = c["valid"].to(self.dt)
+            z_lin = (W["lin"][c["rows"]] * vm).sum(1)
+            if self.dn:
+                z_lin = z_lin + c["x"] @ W["num_lin"]
+            out["linear/linear"] = z_lin + W["bias"][0]
+        if self.use_mf:
+            s, E = c["s"], c["E"]
+            out["mf/logits"] = 0.5 * (s * s - (E * E).sum(1)).sum(1)
+        if self.use_dnn:
+            for i in range(len(self.hidden)):
+                out["dnn/dnn/hiddenlayer_%d" % i] = c["acts"][i + 1]
+            out["dnn/dnn/logits"] = (c["acts"][-1] @ W["Wo"])[:, 0] + W["bo"][0]
+        out["deep_fm/logits"] = z
+        return {k: v.detach().numpy() for k, v in out.items()}
+
     @staticmethod
     def loss_vec(z, y):
         return torch.clamp(z, min=0) - z * y + torch.log1p(torch.exp(-torch.abs(z)))

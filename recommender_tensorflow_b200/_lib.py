@@ -60,6 +60,9 @@ _SIGS = {
     "dfm_prefetch_batch": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p]),
     "dfm_forward": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.c_void_p]),
     "dfm_forward_host": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p]),
+    "dfm_summary_bucket_limits": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "dfm_layer_summary": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "dfm_layer_summary_tensor": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "dfm_flush": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dfm_sync": (C.c_int, [C.c_void_p]),
     "dfm_global_step": (C.c_int64, [C.c_void_p]),

@@ -11,6 +11,7 @@
 #include <type_traits>
 #include <vector>
 
+#include <cfloat>
 #include "dfm_types.cuh"
 #include "embed_kernels.cuh"
 #include "mlp_kernels.cuh"
@@ -18,6 +19,7 @@
 #include "small_mlp.cuh"
 #include "fused_small.cuh"
 #include "fused_rows_args.cuh"
+#include "summary.cuh"
 #include "tc_gemm.cuh"
 #include "xchg.cuh"
 
@@ -158,6 +160,9 @@ struct dfm_handle {
     float *num_partial = nullptr, *num_scratch = nullptr; unsigned int* fused_done = nullptr;
     // record-staged step with the in-kernel optimizer for once-only rows (fused_rows.cuh)
     bool fused_rows = false; size_t fr_smem = 0; uint32_t* claim = nullptr; uint32_t claim_mask = 0; size_t claim_bytes = 0;
+    // layer_summary workspace (summary.cuh), allocated on first use
+    float *sum_h0 = nullptr, *sum_s = nullptr, *sum_lin = nullptr, *sum_mf = nullptr, *sum_hidden = nullptr, *sum_dnn = nullptr, *sum_logits = nullptr;
+    double* sum_limits = nullptr; SummaryStats* sum_stats = nullptr; unsigned long long* sum_buckets = nullptr;
     bool claim_live = false;          // this step's claim table is filled: once-only rows are applied by fused_rows_kernel
     bool last_step_rows = false;
 
@@ -266,7 +271,7 @@ static void free_all(dfm_handle* h) {
     cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, h->d_row_off, h->tb.rec, h->dw,
                     h->ds1, h->ds2, h->dg, h->ids, h->h0, h->s, h->zacc, h->logits, h->dz, h->dE, h->splitk, h->colpart, h->head_part,
-                    h->d_loss, h->d_dzsum, h->d_err, h->num_partial, h->num_scratch, h->fused_done, h->claim, h->up_partial, h->w0_partial, h->tc_w, h->head_gpart, h->d_slot_col, h->d_slot_j, h->d_field_slot0, h->inv_cnt, h->uidx,
+                    h->d_loss, h->d_dzsum, h->d_err, h->num_partial, h->num_scratch, h->fused_done, h->claim, h->sum_h0, h->sum_s, h->sum_lin, h->sum_mf, h->sum_hidden, h->sum_dnn, h->sum_logits, h->sum_limits, h->sum_stats, h->sum_buckets, h->up_partial, h->w0_partial, h->tc_w, h->head_gpart, h->d_slot_col, h->d_slot_j, h->d_field_slot0, h->inv_cnt, h->uidx,
                     h->req_rows, h->d_counts};
     for (void* p : ptrs) if (p) cudaFree(p);
     free_ws(h->ws);
@@ -1792,6 +1797,147 @@ extern "C" int dfm_forward(dfm_handle* h, const dfm_raw_batch* b, float* logits_
     DISPATCH_K(h, rc = eval_forward<KK>(h, bp, b->batch_size, logits_out, nullptr, st));
     if (rc) return rc;
     CK(cudaGetLastError());
+    return DFM_OK;
+}
+
+// ---- layer_summary side outputs (summary.cuh; trainers/model_utils.py:4-6 and its call sites in trainers/deep_fm.py)
+static std::vector<double> summary_limits() {      // core/lib/histogram/histogram.cc InitDefaultBucketsInner
+    std::vector<double> pos, out;
+    for (double v = 1.0e-12; v < 1.0e20; v *= 1.1) pos.push_back(v);
+    pos.push_back(DBL_MAX);
+    for (size_t i = pos.size(); i-- > 0;) out.push_back(-pos[i]);
+    out.push_back(0.0);
+    out.insert(out.end(), pos.begin(), pos.end());
+    return out;
+}
+extern "C" int dfm_summary_bucket_limits(double* limits_out, int32_t* n_out) {
+    const std::vector<double> l = summary_limits();
+    if (n_out) *n_out = (int32_t)l.size();
+    if (limits_out) memcpy(limits_out, l.data(), l.size() * sizeof(double));
+    return DFM_OK;
+}
+static __global__ void summary_total_kernel(const float* lin, const float* mf, const float* dnn, int B, float* out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) out[b] = (lin ? lin[b] : 0.f) + (mf ? mf[b] : 0.f) + (dnn ? dnn[b] : 0.f);
+}
+template <int K>
+static int summary_gather(dfm_handle* h, const BatchPtrs& bp, int B, int use_linear, int use_mf, float* zacc, cudaStream_t st) {
+    float* num_emb = nullptr; float* num_lin = nullptr; float* bias = nullptr;
+    for (const DenseT& dt : h->dense) {
+        if (dt.name == "num_emb") num_emb = h->dw + dt.off;
+        if (dt.name == "num_lin") num_lin = h->dw + dt.off;
+        if (dt.name == "bias") bias = h->dw + dt.off;
+    }
+    unsigned grid = std::min<unsigned>(cdiv(B, 8), (unsigned)h->sm_count * 16);
+    auto kern = h->has_bags ? gather_fm_kernel<K, true> : gather_fm_kernel<K, false>;
+    kern<<<grid, 256, 0, st>>>(h->ids, B, h->dc, h->dn, h->dcs, h->has_bags ? h->d_field_slot0 : nullptr, h->has_bags ? h->inv_cnt : nullptr,
+                               h->d_row_off, h->tb, bp, num_emb, num_lin, bias, use_linear, use_mf, h->need_emb, h->sum_h0, h->sum_s, zacc,
+                               nullptr, nullptr, K + 4, make_rr(h, h->step), make_opt(h->od, 0.f), make_opt(h->ol, 0.f));
+    h->launches++;
+    CK(cudaGetLastError());
+    return DFM_OK;
+}
+extern "C" int dfm_layer_summary(dfm_handle* h, const dfm_raw_batch* b, int32_t train_mode, dfm_tensor_summary* out, int64_t* bucket_counts,
+                                 int32_t max_tensors, int32_t* n_tensors) {
+    if (!h || !out || !n_tensors) return DFM_ERR_INVALID_ARG;
+    if (h->world > 1) FAIL(DFM_ERR_UNSUPPORTED, "layer summaries of a row-sharded handle are not built");
+    int rc = check_batch(h, b, false);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int B = b->batch_size, K = h->K, dK = (h->dc + h->dn) * K;
+    const int T = (h->use_linear ? 1 : 0) + (h->use_mf ? 1 : 0) + (h->use_dnn ? h->L + 1 : 0) + 1;
+    if (T > max_tensors) FAIL(DFM_ERR_INVALID_ARG, "dfm_layer_summary: out[] is too small for the tensors of this model");
+    int hid = 0, maxdim = dK;
+    for (int i = 0; i < h->L; ++i) { hid += h->hidden[i]; maxdim = std::max(maxdim, h->hidden[i]); }
+    const std::vector<double> limits = summary_limits();
+    const int NL = (int)limits.size();
+    if (!h->sum_logits) {
+        const size_t Bm = (size_t)h->max_batch;
+        if (h->need_emb && dalloc(h, &h->sum_h0, Bm * dK)) return DFM_ERR_CUDA;
+        if (dalloc(h, &h->sum_s, Bm * K)) return DFM_ERR_CUDA;
+        if (dalloc(h, &h->sum_lin, Bm)) return DFM_ERR_CUDA;
+        if (dalloc(h, &h->sum_mf, Bm)) return DFM_ERR_CUDA;
+        if (h->use_dnn && dalloc(h, &h->sum_hidden, Bm * std::max(hid, 1))) return DFM_ERR_CUDA;
+        if (dalloc(h, &h->sum_dnn, Bm)) return DFM_ERR_CUDA;
+        if (dalloc(h, &h->sum_limits, (size_t)NL)) return DFM_ERR_CUDA;
+        if (dalloc(h, &h->sum_stats, (size_t)DFM_MAX_HIDDEN + 4)) return DFM_ERR_CUDA;
+        if (dalloc(h, &h->sum_buckets, (size_t)(DFM_MAX_HIDDEN + 4) * NL)) return DFM_ERR_CUDA;
+        if (dalloc(h, &h->sum_logits, Bm)) return DFM_ERR_CUDA;
+        CK(cudaMemcpy(h->sum_limits, limits.data(), NL * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    BatchPtrs bp = make_ptrs(h, b);
+    bp.labels = nullptr;
+    rc = ensure_alpha(h, h->step + 1);
+    if (rc) return rc;
+    launch_transform<4>(h, bp, B, false, h->ids, st);
+    if (h->use_linear) DISPATCH_K(h, rc = summary_gather<KK>(h, bp, B, 1, 0, h->sum_lin, st));
+    if (rc) return rc;
+    if (h->use_mf || h->use_dnn) DISPATCH_K(h, rc = summary_gather<KK>(h, bp, B, 0, h->use_mf, h->sum_mf, st));
+    if (rc) return rc;
+    if (h->use_dnn) {
+        SummaryTowerArgs a{};
+        a.h0 = h->sum_h0; a.dK = dK; a.dw = h->dw; a.L = h->L; a.B = B; a.maxdim = maxdim; a.hid_stride = hid;
+        for (int i = 0; i < h->L; ++i) {
+            a.H[i] = h->hidden[i];
+            a.off_W[i] = (int)find_dense(h, "W" + std::to_string(i))->off; a.off_b[i] = (int)find_dense(h, "b" + std::to_string(i))->off;
+        }
+        a.off_Wo = (int)find_dense(h, "Wo")->off; a.off_bo = (int)find_dense(h, "bo")->off;
+        if (train_mode && h->dropout > 0.f) {
+            a.drop_keep = 1.f - h->dropout; a.drop_inv = 1.f / (1.f - h->dropout);
+            a.drop_seed = h->dropout_seed; a.drop_step = (uint64_t)(h->step + 1); a.drop_row0 = (int64_t)h->rank * h->max_batch;
+        }
+        a.hidden_out = h->sum_hidden; a.dnn_logit = h->sum_dnn;
+        const int smem = 4 * 2 * maxdim * 4;
+        if (smem > 200 * 1024) FAIL(DFM_ERR_UNSUPPORTED, "layer summary: layer too wide for the diagnostic tower kernel");
+        static int attr = 0;
+        if (attr < smem) { CK(cudaFuncSetAttribute(summary_tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = smem; }
+        summary_tower_kernel<<<std::min((B + 3) / 4, h->sm_count * 8), 128, smem, st>>>(a);
+        h->launches++;
+    }
+    summary_total_kernel<<<cdiv(B, 256), 256, 0, st>>>(h->use_linear ? h->sum_lin : nullptr, h->use_mf ? h->sum_mf : nullptr,
+                                                       h->use_dnn ? h->sum_dnn : nullptr, B, h->sum_logits);
+    // reduce every tensor: {fraction of zeros, HistogramProto fields}
+    std::vector<SummaryStats> init((size_t)T);
+    for (auto& x : init) { x.sum = 0; x.sum_sq = 0; x.num = 0; x.zeros = 0; x.min = __int_as_float_host(0x7f800000); x.max = __int_as_float_host((int)0x807fffff); }
+    CK(cudaMemcpyAsync(h->sum_stats, init.data(), T * sizeof(SummaryStats), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(h->sum_buckets, 0, (size_t)T * NL * sizeof(unsigned long long), st));
+    int ti = 0;
+    auto reduce = [&](const float* base, int cols, int64_t stride) {
+        const int64_t n = (int64_t)B * cols;
+        summary_reduce_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, st>>>(
+            base, B, cols, stride, h->sum_limits, NL, h->sum_stats + ti, h->sum_buckets + (size_t)ti * NL);
+        ++ti;
+    };
+    if (h->use_linear) reduce(h->sum_lin, 1, 1);
+    if (h->use_mf) reduce(h->sum_mf, 1, 1);
+    if (h->use_dnn) {
+        int col = 0;
+        for (int i = 0; i < h->L; ++i) { reduce(h->sum_hidden + col, h->hidden[i], hid); col += h->hidden[i]; }
+        reduce(h->sum_dnn, 1, 1);
+    }
+    reduce(h->sum_logits, 1, 1);
+    CK(cudaGetLastError());
+    std::vector<SummaryStats> res((size_t)T);
+    CK(cudaMemcpyAsync(res.data(), h->sum_stats, T * sizeof(SummaryStats), cudaMemcpyDeviceToHost, st));
+    if (bucket_counts) CK(cudaMemcpyAsync(bucket_counts, h->sum_buckets, (size_t)T * NL * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    auto dec = [](float f) { int i; memcpy(&i, &f, 4); if (i < 0) i ^= 0x7fffffff; float r; memcpy(&r, &i, 4); return r; };
+    for (int i = 0; i < T; ++i) {
+        out[i].min = dec(res[i].min); out[i].max = dec(res[i].max); out[i].num = (double)res[i].num;
+        out[i].sum = res[i].sum; out[i].sum_squares = res[i].sum_sq;
+        out[i].zero_fraction = res[i].num ? (double)res[i].zeros / (double)res[i].num : 0.0;
+    }
+    *n_tensors = T;
+    return DFM_OK;
+}
+// device copies of the summarised tensors of the last dfm_layer_summary call (tests): 0 linear, 1 mf, 2 hidden [B, sum H], 3 dnn logit, 4 logits
+extern "C" int dfm_layer_summary_tensor(dfm_handle* h, int32_t which, int64_t n, float* out_host) {
+    if (!h || !out_host || !h->sum_logits) return DFM_ERR_INVALID_ARG;
+    const float* src = which == 0 ? h->sum_lin : which == 1 ? h->sum_mf : which == 2 ? h->sum_hidden : which == 3 ? h->sum_dnn : h->sum_logits;
+    if (!src) return DFM_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(out_host, src, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return DFM_OK;
 }
 

@@ -6,6 +6,8 @@ libdeepfm_b200.so.  torch is used only as the pinned/device memory allocator.
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 
 from . import _lib
@@ -256,7 +258,18 @@ class DeepFMEngine:
                 t = self._SLOT_TF[sl]
                 t = t[grp["name"]] if isinstance(t, dict) else t
                 out[tf_name + "/" + t] = self.get_tensor(g + "/" + sl, r0, n).reshape(shape)
-        np.savez(path, **out)
+        # TF keeps the running products beta1_power / beta2_power as variables; here they are a function of global_step
+        # (dfm_set_global_step rebuilds them with the same float32 running product), stored for inspection / exchange
+        for grp_name, grp in (("deep", self.opt_deep), ("linear", self.opt_linear)):
+            if grp["name"] == "Adam":
+                b1p, b2p = np.float32(1.0), np.float32(1.0)
+                for _ in range(int(self.global_step)):
+                    b1p, b2p = np.float32(b1p * np.float32(grp["beta1"])), np.float32(b2p * np.float32(grp["beta2"]))
+                out["beta1_power/" + grp_name], out["beta2_power/" + grp_name] = b1p, b2p
+        # written next to the target and renamed into place: a crash mid-write never leaves a truncated model.ckpt-N.npz
+        tmp = path + ".tmp.npz"
+        np.savez(tmp, **out)
+        os.replace(tmp, path)
         return path
 
     def load_checkpoint(self, path, scheme="deep_fm"):
@@ -451,6 +464,55 @@ class DeepFMEngine:
             self.sync()
             return t.cpu().numpy()
         self._check(self.lib.dfm_forward_host(self.h, C.byref(pb.raw), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    # ------------------------------------------------------------------ layer_summary side outputs
+    def summary_names(self):
+        """TF name scopes of the tensors trainers/deep_fm.py passes to layer_summary, in the library's order."""
+        names = []
+        if self.use_linear:
+            names.append("linear/linear")
+        if self.use_mf:
+            names.append("mf/logits")
+        if self.use_dnn:
+            names += ["dnn/dnn/hiddenlayer_%d" % i for i in range(len(self.hidden))] + ["dnn/dnn/logits"]
+        return names + ["deep_fm/logits"]
+
+    @staticmethod
+    def summary_bucket_limits():
+        n = C.c_int32(0)
+        lib = _lib.load()
+        lib.dfm_summary_bucket_limits(None, C.byref(n))
+        lim = np.empty(n.value, dtype=np.float64)
+        lib.dfm_summary_bucket_limits(lim.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n))
+        return lim
+
+    def layer_summary(self, features, train=True):
+        """trainers/model_utils.py:4-6 for every tensor the reference summarises (trainers/deep_fm.py:43,89,105,110,115),
+        computed on the device for this batch with the weights as of the latest step (call it BEFORE the train step whose
+        summaries it stands for).  -> {scope: {"fraction_of_zero_values": f, "activation": HistogramProto fields}}"""
+        pb = features if isinstance(features, PackedBatch) else self.pack(features, None, device=True)
+        names = self.summary_names()
+        limits = self.summary_bucket_limits()
+        stats = np.zeros((len(names), 6), dtype=np.float64)
+        buckets = np.zeros((len(names), limits.size), dtype=np.int64)
+        n = C.c_int32(0)
+        self._check(self.lib.dfm_layer_summary(self.h, C.byref(pb.raw), int(bool(train)), stats.ctypes.data_as(C.c_void_p),
+                                               buckets.ctypes.data_as(C.c_void_p), len(names), C.byref(n)))
+        assert n.value == len(names)
+        out = {}
+        for i, name in enumerate(names):
+            nz = np.nonzero(buckets[i])[0]
+            out[name] = {"fraction_of_zero_values": float(stats[i, 5]),
+                         "activation": {"min": float(stats[i, 0]), "max": float(stats[i, 1]), "num": float(stats[i, 2]),
+                                        "sum": float(stats[i, 3]), "sum_squares": float(stats[i, 4]),
+                                        "bucket_limit": limits[nz].tolist(), "bucket": buckets[i, nz].astype(np.float64).tolist()}}
+        return out
+
+    def summary_tensor(self, which, n):
+        """host copy of a tensor of the last layer_summary call (0 linear, 1 mf, 2 hidden, 3 dnn logit, 4 logits)"""
+        out = np.empty(int(n), dtype=np.float32)
+        self._check(self.lib.dfm_layer_summary_tensor(self.h, int(which), int(n), out.ctypes.data_as(C.c_void_p)))
         return out
 
     # ------------------------------------------------------------------ row sharding (world > 1)

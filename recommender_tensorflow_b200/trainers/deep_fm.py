@@ -81,6 +81,8 @@ class Estimator:
     evaluate / predict loops around model_fn, checkpoints as .npz (variables + optimizer slots)."""
 
     KEEP_CHECKPOINT_MAX = 5      # trainers/conf_utils.py:6-10
+    SAVE_CHECKPOINTS_SECS = 60   # trainers/conf_utils.py:6-10 (RunConfig(save_checkpoints_secs=60))
+    SAVE_SUMMARY_STEPS = 100     # RunConfig default: layer_summary side outputs every 100 steps
 
     def __init__(self, model_fn, model_dir=None, config=None, params=None):
         self.model_fn, self.model_dir, self.config, self.params = model_fn, model_dir, config, dict(params or {})
@@ -125,8 +127,20 @@ class Estimator:
         self._maybe_restore()
         return self.engine
 
+    def write_summaries(self, feats):
+        """trainers/model_utils.py:4-6: zero fraction + histogram of every summarised tensor -> model_dir/summaries.jsonl"""
+        if not self.model_dir or not self.SAVE_SUMMARY_STEPS:
+            return
+        import json
+        os.makedirs(self.model_dir, exist_ok=True)
+        rec = {"step": self.engine.global_step + 1, "summaries": self.engine.layer_summary(feats, train=True)}
+        with open(os.path.join(self.model_dir, "summaries.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
+
     def train(self, input_fn, steps=None, max_steps=None, log_every=100):
+        import time
         loss = None
+        last_save = time.time()
         for feats, labels in input_fn():
             if self.engine is None:
                 self.params[_ENGINE_KEY] = _build_engine(self.params, _batch_size(feats))
@@ -134,8 +148,13 @@ class Estimator:
             eng = self.engine
             if max_steps is not None and eng.global_step >= max_steps:
                 break
+            if self.SAVE_SUMMARY_STEPS and eng.global_step % self.SAVE_SUMMARY_STEPS == 0:
+                self.write_summaries(feats)
             spec = self.model_fn(feats, labels, ModeKeys.TRAIN, self.params)
             loss = spec.loss
+            if self.SAVE_CHECKPOINTS_SECS and time.time() - last_save >= self.SAVE_CHECKPOINTS_SECS:
+                self.save_checkpoint()
+                last_save = time.time()
             if log_every and spec.global_step % log_every == 0:
                 print("INFO:b200:loss = %.6f, step = %d" % (loss, spec.global_step))
             if steps is not None:
@@ -154,6 +173,8 @@ class Estimator:
             spec = self.model_fn(feats, labels, ModeKeys.EVAL, self.params)
             ys.append(np.asarray(labels, dtype=np.float32).reshape(-1))
             zs.append(spec.predictions["logits"].reshape(-1))
+        if not ys:
+            raise ValueError("evaluate(): input_fn yielded no batches")
         m = get_binary_metrics(np.concatenate(ys), np.concatenate(zs))
         m["global_step"] = self.engine.global_step
         return m
@@ -161,6 +182,13 @@ class Estimator:
     def predict(self, input_fn):
         for item in input_fn():
             feats = item[0] if isinstance(item, tuple) and len(item) == 2 and isinstance(item[0], dict) else item
+            if self.engine is None:
+                self.params[_ENGINE_KEY] = _build_engine(self.params, _batch_size(feats))
+            if not self._restored:
+                # tf.estimator.Estimator.predict restores the latest checkpoint and fails when there is none
+                if self.engine.global_step == 0 and self.latest_checkpoint() is None:
+                    raise ValueError("Could not find trained model in model_dir: %s." % self.model_dir)
+                self._maybe_restore()
             spec = self.model_fn(feats, None, ModeKeys.PREDICT, self.params)
             n = spec.predictions["logits"].shape[0]
             for i in range(n):

@@ -367,6 +367,56 @@ def test_canned_estimator_mirrors(tmp_path):
         assert 0.0 <= m["auc"] <= 1.0 and np.isfinite(m["average_loss"])
 
 
+def test_canned_estimators_initialise_train_and_resume(tmp_path):
+    """The canned mirrors run TF's variable initialisers (a zero tower would stay dead under ReLU), learn, and resume
+    from model_dir like an Estimator: a fresh instance on the same model_dir predicts what the trained one predicted."""
+    from recommender_tensorflow_b200.trainers import deep, linear_deep, ml_100k
+    csv_path = str(tmp_path / "train.csv")
+    ml_100k.write_synthetic_csv(csv_path, 2000)
+    fcs = ml_100k.get_feature_columns(embedding_size=4)
+    builders = {
+        "deep": lambda d: deep.DNNClassifier([16, 16], fcs["deep"], model_dir=d, max_batch=64, tf_random_seed=3),
+        "linear_deep": lambda d: linear_deep.DNNLinearCombinedClassifier(model_dir=d, linear_feature_columns=fcs["linear"], dnn_feature_columns=fcs["deep"],
+                                                                        dnn_hidden_units=[16, 16], max_batch=64, tf_random_seed=3)}
+    for name, build in builders.items():
+        d = str(tmp_path / name)
+        est = build(d)
+        w0 = est.engine.get_tensor("W0")
+        assert np.abs(w0).max() > 0 and np.abs(est.engine.get_tensor("emb")).max() > 0, "initialisers did not run"
+        eval_fn = ml_100k.get_input_fn(csv_path, ml_100k.ModeKeys.EVAL, batch_size=64)
+        before = est.evaluate(eval_fn)
+        est.train(ml_100k.get_input_fn(csv_path, batch_size=32, seed=0), max_steps=300)
+        after = est.evaluate(eval_fn)
+        assert np.abs(est.engine.get_tensor("W0") - w0).max() > 0, "the tower did not train"
+        assert after["average_loss"] < before["average_loss"], (name, before["average_loss"], after["average_loss"])
+        fresh = build(d)                                           # same model_dir: resumes from model.ckpt-300.npz
+        again = fresh.evaluate(eval_fn)
+        assert fresh.engine.global_step == 300 and again["average_loss"] == after["average_loss"] and again["auc"] == after["auc"]
+
+
+def test_estimator_predict_restores_or_raises(tmp_path):
+    """tf.estimator.Estimator.predict restores the latest checkpoint of model_dir and fails when there is none."""
+    from recommender_tensorflow_b200.trainers import deep_fm, ml_100k
+    csv_path = str(tmp_path / "train.csv")
+    ml_100k.write_synthetic_csv(csv_path, 600)
+    fcs = ml_100k.get_feature_columns(embedding_size=4)
+    params = {"categorical_columns": fcs["linear"], "embedding_size": 4, "hidden_units": [16, 16], "max_batch": 64, "tf_random_seed": 5}
+    d = str(tmp_path / "job")
+    est = deep_fm.Estimator(deep_fm.model_fn, model_dir=d, params=params)
+    est.train(ml_100k.get_input_fn(csv_path, batch_size=32, seed=0), max_steps=20)
+    eval_fn = ml_100k.get_input_fn(csv_path, ml_100k.ModeKeys.EVAL, batch_size=64)
+    want = [p["logits"][0] for p in est.predict(eval_fn)]
+    fresh = deep_fm.Estimator(deep_fm.model_fn, model_dir=d, params=params)
+    got = [p["logits"][0] for p in fresh.predict(eval_fn)]
+    assert fresh.engine.global_step == 20 and got == want
+    empty = deep_fm.Estimator(deep_fm.model_fn, model_dir=str(tmp_path / "nothing"), params=params)
+    with pytest.raises(ValueError):
+        next(iter(empty.predict(eval_fn)))
+    import json, os
+    recs = [json.loads(l) for l in open(os.path.join(d, "summaries.jsonl"))]          # layer_summary side outputs, step 1
+    assert recs and recs[0]["step"] == 1 and "deep_fm/logits" in recs[0]["summaries"]
+
+
 # ------------------------------------------------------------------ edge cases and full-size properties
 def test_edge_batches():
     """batch of 1, a batch whose hashed / vocab columns are all empty bags, and a full max_batch."""
