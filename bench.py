@@ -301,14 +301,26 @@ def measure(name, args, world, rank, local, peaks, primary=True, zipf=None):
     B = w["batch"]
     sharded = world > 1 and w["data"] == "criteo"
     kw = dict(embedding_size=w["k"], hidden_units=w["hidden"], max_batch=B, device=local, feature_dtypes=dtypes, **optimizers(w))
-    eng = DeepFMEngine(cats, nums, rank=rank if sharded else 0, world=world if sharded else 1, **kw)
-    eng.init_random(1234)            # same dense tower on every rank; the table shards differ by construction (own rows)
     exchange = os.environ.get("DFM_SHARD_EXCHANGE", "xchg")     # "xchg": kernel stores + flags in peer memory; "nccl": all_to_all
     parity = None
+    if sharded and primary and not zipf and os.environ.get("DFM_PARITY_CHECK", "1") != "0":
+        # two more engines live during the check: it runs before the timed engine exists, on tables cut to <= 16 GB per GPU
+        from recommender_tensorflow_b200 import synth as _synth
+        rec_bytes = (3 * w["k"] + 4 + 15) // 16 * 16 * 4
+        rows_gpu = 26 * workload_buckets(w, world) // world
+        pc, pn = cats, nums
+        note = None
+        if rows_gpu * rec_bytes > 16e9:
+            small = int(16e9 // rec_bytes // 26) * world
+            pc, pn = _synth.criteo_columns(small)
+            note = "tables cut to %d buckets per field for the check (two extra engines must fit beside nothing else)" % small
+        parity = parity_check(w, kw, pc, pn, rank, world, local)
+        if note:
+            parity["note"] = note
+    eng = DeepFMEngine(cats, nums, rank=rank if sharded else 0, world=world if sharded else 1, **kw)
+    eng.init_random(1234)            # same dense tower on every rank; the table shards differ by construction (own rows)
     if sharded:
         from recommender_tensorflow_b200.sharded import ShardedTrainer, XchgTrainer
-        if primary and not zipf and os.environ.get("DFM_PARITY_CHECK", "1") != "0":
-            parity = parity_check(w, kw, cats, nums, rank, world, local)
         trainer = XchgTrainer(eng) if exchange == "xchg" else ShardedTrainer(eng)
 
     # ---- inputs: fresh ids in every batch.  Criteo-shaped batches are generated on the device (32 of them); the
