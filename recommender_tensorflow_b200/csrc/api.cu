@@ -165,6 +165,7 @@ struct dfm_handle {
     double* sum_limits = nullptr; SummaryStats* sum_stats = nullptr; unsigned long long* sum_buckets = nullptr;
     bool claim_live = false;          // this step's claim table is filled: once-only rows are applied by fused_rows_kernel
     bool last_step_rows = false;
+    bool fr_side = false;             // this step's sort runs on the side stream beside fused_rows_kernel
 
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     // small tables: the sort / segment stage runs on a side stream next to the gather and the tower (see train_impl)
@@ -667,7 +668,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
                         h->fused_rows = true;
                         CK(fused_rows_set_attr((int)h->fr_smem));
                         uint64_t slots = 1024;
-                        while (slots < (uint64_t)h->R && slots < (1ull << 27)) slots <<= 1;
+                        while (slots < (uint64_t)h->R && slots < (1ull << 26)) slots <<= 1;      // 16 MB at most: L2 resident
                         h->claim_mask = (uint32_t)(slots - 1);
                         h->claim_bytes = (size_t)(slots / 4);
                         if (dalloc(h, &h->claim, h->claim_bytes / 4)) return DFM_ERR_CUDA;
@@ -1454,7 +1455,7 @@ static int launch_fused_rows(dfm_handle* h, const BatchPtrs& bp, int B, const fl
         A.step = (int)t;
         if (so) { A.od_t = so->od; A.ol_t = so->ol; }
         A.numg_partial = h->num_partial;
-        const int grid = fused_rows_grid(B, h->sm_count);
+        const int grid = fused_rows_grid(B, h->sm_count, h->fr_side);
         CK(fused_rows_launch(A, grid, h->fr_smem, st));
         h->launches++;
         return DFM_OK;
@@ -1509,7 +1510,7 @@ static int launch_fused_reduce(dfm_handle* h, int B, float scale, float* loss_ou
     const DenseT* ne = find_dense(h, "num_emb"); const DenseT* nl = find_dense(h, "num_lin"); const DenseT* bs = find_dense(h, "bias");
     FusedReduceArgs r{};
     r.up_partial = h->up_partial; r.w0_partial = h->w0_partial; r.num_partial = h->num_partial; r.head_part = h->head_part;
-    r.n_cta = rows ? fused_rows_grid(B, h->sm_count) : std::min((B + FS_TS - 1) / FS_TS, h->fused_grid);
+    r.n_cta = rows ? fused_rows_grid(B, h->sm_count, h->fr_side) : std::min((B + FS_TS - 1) / FS_TS, h->fused_grid);
     r.up_count = h->sm.up_count; r.up_begin = h->sm.up_begin; r.off_W0 = h->sm.off_W[0]; r.w0_count = h->sm.D * h->sm.H[0];
     r.n_numacc = rows ? h->dn * h->K + h->dn : h->n_numacc;
     r.direct_num = rows ? 1 : 0;
@@ -1576,6 +1577,7 @@ static int train_fused(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_ou
         // not need the list of touched rows: sort + segments (many small dependent launches) run on the side stream
         // beside the fused kernel and are joined in front of the sparse optimizer.
         const bool side = !prefetched && n > 0 && B >= 1024 && !h->profiling;
+        h->fr_side = side && rows;
         if (side) {
             CK(cudaEventRecord(h->ev_fork, st));
             CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));

@@ -30,6 +30,7 @@
 // sqrt / reciprocal (relative error <= 2^-21 on a displacement of ~lr, i.e. ~1e-10 on w; the IEEE sequence cost 20 % of the
 // kernel's instructions, profiles/r02u).
 #include <algorithm>
+#include <cstdlib>
 
 #include "fused_rows_args.cuh"
 #include "tc_gemm.cuh"
@@ -54,6 +55,21 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(FR_CW * 32) : "memory"); }
 constexpr int FR_P3W = 8;                      // warps that run the small upper part of the tower (P3)
 __device__ __forceinline__ void bar_p3() { asm volatile("bar.sync 2, %0;" ::"n"(FR_P3W * 32) : "memory"); }
+
+// wait with back-off (producer warps: a slot frees once per tile, thousands of cycles apart; a hot try_wait loop would
+// take issue slots from the consumer warps of the same scheduler - 16 % of the kernel's instructions in profiles/r02aj)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = tc::smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done) __nanosleep(200);
+        if (spins > (1u << 24)) __trap();
+    }
+}
 
 // D = A(16x8, row) * B(8x8, col) + C on tf32 operands held as fp32 bit patterns whose low 13 bits are zero
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2], const float (&c)[4]) {
@@ -159,7 +175,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int s = it % FR_NSLOT;
-            if (it >= FR_NSLOT) tc::mbar_wait(&empty[s], ((it / FR_NSLOT) & 1) ^ 1);
+            if (it >= FR_NSLOT) mbar_wait_backoff(&empty[s], ((it / FR_NSLOT) & 1) ^ 1);
             float* slot = slots + (size_t)s * FR_TS * SST;
             uint32_t row[FR_NR], cw[FR_NR];
 #pragma unroll
@@ -807,7 +823,13 @@ size_t fused_rows_smem_bytes(const SmallMlpDesc& m, int K, int dc, int dn, int r
     return f * 4 + 2 * FR_NSLOT * 8 + 64;
 }
 
-int fused_rows_grid(int B, int sm_count) { return std::min((B + FR_TS - 1) / FR_TS, sm_count); }
+int fused_rows_grid(int B, int sm_count, bool side_stream_busy) {
+    // The kernel fills an SM (registers, 224 KB of shared memory), so nothing else runs beside it: with the compaction /
+    // sort / segment kernels of the repeated lookups on the side stream, 8 SMs are left to them (measured on the
+    // Criteo-shaped step: 0.865 -> 0.819 ms uniform ids, 1.045 -> 0.965 ms Zipf(1.05); 16 SMs: 0.859 / 0.966).  DFM_FR_RESERVE overrides.
+    static const int reserve = getenv("DFM_FR_RESERVE") ? atoi(getenv("DFM_FR_RESERVE")) : 8;
+    return std::max(1, std::min((B + FR_TS - 1) / FR_TS, sm_count - (side_stream_busy ? reserve : 0)));
+}
 
 template <int ES>
 static cudaError_t fr_attr(int smem_bytes) {

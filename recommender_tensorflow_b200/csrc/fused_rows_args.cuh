@@ -29,7 +29,7 @@ __host__ __device__ inline int fr_sst(int dc, int dn, int K, int rs) {
 // host interface (fused_rows.cu)
 bool fused_rows_supported(int K, int H1, int dc, int dn);                     // shape limits of the instantiated kernel
 size_t fused_rows_smem_bytes(const SmallMlpDesc& m, int K, int dc, int dn, int rs);
-int fused_rows_grid(int B, int sm_count);                                     // CTAs (= per-CTA partial sets) of a launch
+int fused_rows_grid(int B, int sm_count, bool side_stream_busy);                                     // CTAs (= per-CTA partial sets) of a launch
 // Deterministic stream compaction of the step's (row, lookup) pairs: only the lookups whose claim state is "more than
 // once" go through the sort / ordered reduction.  n_out[0] = pairs kept, n_out[1] = once-only lookups.  scratch: n / 2048 + 2 words.
 cudaError_t fused_rows_compact(const uint32_t* keys_in, const uint32_t* vals_in, int64_t n, uint32_t R, const uint32_t* claim, uint32_t claim_mask,
