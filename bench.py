@@ -348,16 +348,19 @@ def measure(name, args, world, rank, local, peaks, primary=True, zipf=None):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def dev_step(i):
+    prefetch = sharded and exchange == "xchg" and os.environ.get("DFM_SHARD_PREFETCH", "1") != "0"
+
+    def dev_step(i, last=False):
         if sharded:
-            loss_buf.copy_(trainer.train_step(packed_dev[i % n_batches], B * world).reshape(1))
+            nxt = packed_dev[(i + 1) % n_batches] if prefetch and not last else None      # requests of the next batch beside apply
+            loss_buf.copy_(trainer.train_step(packed_dev[i % n_batches], B * world, next_pb=nxt).reshape(1))
         else:
             eng.train_step_device(packed_dev[i % n_batches], loss_out=loss_buf, stream=stream.cuda_stream)
 
     # ---------------- device-resident timing (value)
     with torch.cuda.stream(stream):
         for i in range(warmup):
-            dev_step(i)
+            dev_step(i, last=i == warmup - 1)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -365,7 +368,7 @@ def measure(name, args, world, rank, local, peaks, primary=True, zipf=None):
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for i in range(steps):
-            dev_step(warmup + i)
+            dev_step(warmup + i, last=i == steps - 1)
         ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -378,23 +381,35 @@ def measure(name, args, world, rank, local, peaks, primary=True, zipf=None):
     # ---------------- end-to-end through the host-buffer entry point (e2e)
     nh = len(packed_host)
     if sharded:
-        stage = [torch.empty_like(packed_dev[0].arena), torch.empty_like(packed_dev[0].arena)]
+        stage = [torch.empty_like(packed_dev[0].arena) for _ in range(3)]
         staged = [eng.repack_like(packed_dev[0], a) for a in stage]
 
-        def e2e_step(i):
-            staged[i % 2].arena.copy_(packed_host[i % nh].arena, non_blocking=True)      # H2D of the raw columns
-            return trainer.train_step(staged[i % 2], B * world)
+        copied = set()
+
+        def e2e_copy(i):
+            if i not in copied:
+                staged[i % 3].arena.copy_(packed_host[i % nh].arena, non_blocking=True)  # H2D of the raw columns of step i
+                copied.add(i)
+
+        def e2e_step(i, last=False):
+            e2e_copy(i)
+            nxt = None
+            if prefetch and not last:
+                e2e_copy(i + 1)                      # the next step's columns: copied now, their requests run beside this apply
+                nxt = staged[(i + 1) % 3]
+            return trainer.train_step(staged[i % 3], B * world, next_pb=nxt)
         with torch.cuda.stream(stream):
             for i in range(2):
-                e2e_step(i)
+                e2e_step(i, last=i == 1)
         barrier()
+        copied.clear()
         loss_pin = torch.empty(2, dtype=torch.float32).pin_memory()
         loss_evs = [torch.cuda.Event(), torch.cuda.Event()]
         e2e_loss = float("nan")
         t0 = time.perf_counter()
         with torch.cuda.stream(stream):
             for i in range(steps):
-                loss_pin[i % 2:i % 2 + 1].copy_(e2e_step(i).reshape(1), non_blocking=True)   # D2H of the loss, every step ...
+                loss_pin[i % 2:i % 2 + 1].copy_(e2e_step(i, last=i == steps - 1).reshape(1), non_blocking=True)   # D2H of the loss, every step ...
                 loss_evs[i % 2].record(stream)
                 if i > 0:                                                                # ... read one step late, like
                     loss_evs[(i - 1) % 2].synchronize()                                  # dfm_train_step_host_async

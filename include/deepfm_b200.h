@@ -258,6 +258,9 @@ int dfm_xchg_forward_backward(dfm_handle* h, const dfm_raw_batch* dev_batch, int
 int dfm_xchg_apply(dfm_handle* h, float* loss_out_dev, void* stream);
 int dfm_xchg_train_step(dfm_handle* h, const dfm_raw_batch* dev_batch, int64_t global_batch, float* loss_out_dev, float* logits_dev,
                         void* stream);
+/* the step + the requests of next_batch (may be NULL) issued beside this step's owner-side apply; the next call must train next_batch */
+int dfm_xchg_train_step_next(dfm_handle* h, const dfm_raw_batch* dev_batch, const dfm_raw_batch* next_batch, int64_t global_batch,
+                             float* loss_out_dev, float* logits_dev, void* stream);
 int dfm_xchg_forward(dfm_handle* h, const dfm_raw_batch* dev_batch, float* logits_dev, void* stream);
 
 /* Building-block entry points used by the parity tests (device pointers, synchronous). */

@@ -90,6 +90,7 @@ _SIGS = {
     "dfm_xchg_forward_backward": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_int64, C.c_void_p, C.c_void_p]),
     "dfm_xchg_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfm_xchg_train_step": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dfm_xchg_train_step_next": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.POINTER(RawBatch), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfm_xchg_forward": (C.c_int, [C.c_void_p, C.POINTER(RawBatch), C.c_void_p, C.c_void_p]),
     "dfm_csv_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "dfm_csv_destroy": (None, [C.c_void_p]),

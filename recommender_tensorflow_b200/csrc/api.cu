@@ -137,6 +137,7 @@ struct dfm_handle {
     uint32_t x_epoch = 0; unsigned int* x_ticket = nullptr;      // exchange rounds so far; tickets of the producer kernels
     PeerRoute* d_xroute = nullptr; uint32_t* d_nrecv = nullptr; float* d_dense_total = nullptr; float* d_loss_part = nullptr;
     bool xchg_pending = false;
+    cudaEvent_t ev_xpf_fork = nullptr, ev_xpf_done = nullptr; bool x_pf_valid = false; const void* x_pf_tag = nullptr; int x_pf_B = -1;
     cudaEvent_t ev_xfork = nullptr, ev_xjoin = nullptr; int x_B = -1; int64_t x_global_batch = 0; bool x_train = false;
     float *h0 = nullptr, *s = nullptr, *zacc = nullptr, *logits = nullptr, *dz = nullptr, *dE = nullptr;
     float* act[DFM_MAX_HIDDEN + 1] = {nullptr};
@@ -287,6 +288,8 @@ static void free_all(dfm_handle* h) {
       for (void* p : tp) if (p) cudaFree(p); }
     for (void* p : h->x_opened) if (p) cudaIpcCloseMemHandle(p);
     { void* xp[] = {h->xreg, h->x_ticket, h->d_xroute, h->d_nrecv, h->d_dense_total, h->d_loss_part}; for (void* p : xp) if (p) cudaFree(p); }
+    if (h->ev_xpf_fork) cudaEventDestroy(h->ev_xpf_fork);
+    if (h->ev_xpf_done) cudaEventDestroy(h->ev_xpf_done);
     if (h->ev_xfork) cudaEventDestroy(h->ev_xfork);
     if (h->ev_xjoin) cudaEventDestroy(h->ev_xjoin);
     for (int i = 1; i <= DFM_MAX_HIDDEN; ++i) { if (h->act[i]) cudaFree(h->act[i]); if (h->dact[i]) cudaFree(h->dact[i]); }
@@ -734,6 +737,8 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
         if (dalloc(h, &h->x_ticket, 16) || dalloc(h, &h->d_xroute, 1) || dalloc(h, &h->d_nrecv, 4) ||
             dalloc(h, &h->d_dense_total, (size_t)x.nd1) || dalloc(h, &h->d_loss_part, 4)) return DFM_ERR_CUDA;
         CK(cudaMemset(h->x_ticket, 0, 16 * 4));
+        CK(cudaEventCreateWithFlags(&h->ev_xpf_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_xpf_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_xfork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_xjoin, cudaEventDisableTiming));
     }
@@ -2310,6 +2315,8 @@ static int xchg_begin_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream
     return DFM_OK;
 }
 
+extern "C" int dfm_xchg_train_step_next(dfm_handle* h, const dfm_raw_batch* b, const dfm_raw_batch* next_b, int64_t global_batch,
+                                        float* loss_out_dev, float* logits_dev, void* stream);
 // phase 2: serve the rows my peers asked for; on the side stream, sort their ids for the gradient reduction
 template <int K>
 static int xchg_serve_impl(dfm_handle* h, bool train, cudaStream_t st) {
@@ -2454,11 +2461,39 @@ extern "C" int dfm_xchg_forward(dfm_handle* h, const dfm_raw_batch* b, float* lo
 // launches (no collective, no host synchronisation); the peers' kernels meet through the flags.
 extern "C" int dfm_xchg_train_step(dfm_handle* h, const dfm_raw_batch* b, int64_t global_batch, float* loss_out_dev, float* logits_dev,
                                    void* stream) {
-    int rc = dfm_xchg_begin(h, b, stream);
+    return dfm_xchg_train_step_next(h, b, nullptr, global_batch, loss_out_dev, logits_dev, stream);
+}
+
+// The same step with the requests of the NEXT batch (transform, owner-major sort, unique rows, push of the ids: no model
+// state involved) issued on the side stream as soon as this step's forward / backward has read the request buffers, i.e.
+// beside this step's owner-side apply.  The next call must be given that batch (every rank alike: the exchange round was
+// opened); it then skips its own begin phase.  Results are bit-identical to the unprefetched sequence.
+extern "C" int dfm_xchg_train_step_next(dfm_handle* h, const dfm_raw_batch* b, const dfm_raw_batch* next_b, int64_t global_batch,
+                                        float* loss_out_dev, float* logits_dev, void* stream) {
+    if (!h || !b) return DFM_ERR_INVALID_ARG;
+    int rc = xchg_check(h);
     if (rc) return rc;
-    if ((rc = dfm_xchg_serve(h, 1, stream))) return rc;
-    if ((rc = dfm_xchg_forward_backward(h, b, global_batch, logits_dev, stream))) return rc;
-    return dfm_xchg_apply(h, loss_out_dev, stream);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (h->x_pf_valid) {
+        if (b->batch_size != h->x_pf_B || (h->dc > 0 && b->cat_data[0] != h->x_pf_tag))
+            FAIL(DFM_ERR_INVALID_ARG, "dfm_xchg_train_step_next: the batch announced as next_batch must be trained next");
+        h->x_pf_valid = false;
+        CK(cudaStreamWaitEvent(st, h->ev_xpf_done, 0));
+    } else if ((rc = dfm_xchg_begin(h, b, st))) {
+        return rc;
+    }
+    if ((rc = dfm_xchg_serve(h, 1, st))) return rc;
+    if ((rc = dfm_xchg_forward_backward(h, b, global_batch, logits_dev, st))) return rc;
+    if (next_b) CK(cudaEventRecord(h->ev_xpf_fork, st));       // the request buffers of this step have been consumed
+    if ((rc = dfm_xchg_apply(h, loss_out_dev, st))) return rc;
+    if (next_b) {
+        CK(cudaStreamWaitEvent(h->side_stream, h->ev_xpf_fork, 0));
+        if ((rc = dfm_xchg_begin(h, next_b, h->side_stream))) return rc;
+        CK(cudaEventRecord(h->ev_xpf_done, h->side_stream));
+        h->x_pf_valid = true; h->x_pf_B = next_b->batch_size; h->x_pf_tag = h->dc > 0 ? next_b->cat_data[0] : nullptr;
+    }
+    return DFM_OK;
 }
 
 // --------------------------------------------------------------------------- host entry points

@@ -589,11 +589,13 @@ class DeepFMEngine:
     def xchg_apply(self, loss_out, stream=None):
         self._check(self.lib.dfm_xchg_apply(self.h, C.c_void_p(loss_out.data_ptr()), C.c_void_p(stream) if stream else None))
 
-    def xchg_train_step(self, pb, global_batch, loss_out, logits=None, stream=None):
-        """one whole sharded step: launches only (no collective, no host synchronisation)"""
-        self._check(self.lib.dfm_xchg_train_step(self.h, C.byref(pb.raw), int(global_batch), C.c_void_p(loss_out.data_ptr()),
-                                                 C.c_void_p(logits.data_ptr()) if logits is not None else None,
-                                                 C.c_void_p(stream) if stream else None))
+    def xchg_train_step(self, pb, global_batch, loss_out, logits=None, stream=None, next_pb=None):
+        """one whole sharded step: launches only (no collective, no host synchronisation).  next_pb: the batch of the NEXT
+        step; its requests are computed beside this step's apply phase (the next call must then be given that batch)."""
+        self._check(self.lib.dfm_xchg_train_step_next(self.h, C.byref(pb.raw), C.byref(next_pb.raw) if next_pb is not None else None,
+                                                      int(global_batch), C.c_void_p(loss_out.data_ptr()),
+                                                      C.c_void_p(logits.data_ptr()) if logits is not None else None,
+                                                      C.c_void_p(stream) if stream else None))
 
     def xchg_forward(self, pb, logits, stream=None):
         self._check(self.lib.dfm_xchg_forward(self.h, C.byref(pb.raw), C.c_void_p(logits.data_ptr()), C.c_void_p(stream) if stream else None))

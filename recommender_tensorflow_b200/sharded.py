@@ -190,7 +190,7 @@ class XchgTrainer:
         torch, eng = self.torch, self.eng
         st = torch.cuda.current_stream().cuda_stream
         if timings is None:
-            eng.xchg_train_step(pb, global_batch, self.loss, None, st)
+            eng.xchg_train_step(pb, global_batch, self.loss, None, st, next_pb=next_pb)
             return self.loss[0]
         marks = []
 

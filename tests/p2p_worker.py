@@ -39,8 +39,9 @@ def main():
         # back-to-back steps without any host synchronisation in between (the flags alone order the ranks)
         for step in (6, 7):
             ta.train_step(ea.pack(*data[step], device=True), per * world)
-        for step in (6, 7):
-            tb.train_step(pbs[step], per * world)
+        # ... the fused exchange with the NEXT batch's requests issued beside each apply phase (dfm_xchg_train_step_next)
+        tb.train_step(pbs[6], per * world, next_pb=pbs[7])
+        tb.train_step(pbs[7], per * world)
         za = ta.predict_logits(pbs[0]).cpu().numpy()
         zb = tb.predict_logits(pbs[0]).cpu().numpy()
     torch.cuda.synchronize()
