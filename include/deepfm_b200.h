@@ -103,6 +103,9 @@ typedef struct {
      * TF's RNG stream is not reproducible, the oracle restates this one. */
     float             dropout;
     uint64_t          dropout_seed;
+    /* params["activation"] (trainers/deep_fm.py:22,100; default tf.nn.relu): DFM_ACT_*.  Anything but ReLU runs the
+     * general CUDA-core tower (the fused and tensor-core towers are built around the ReLU mask). */
+    int32_t           activation;
 } dfm_config;
 
 /* One batch of raw (un-hashed) feature columns = what input_fn's parse_csv yields
@@ -114,6 +117,11 @@ typedef struct {
     const float* const*   num_data;     /* [n_num]: float32[B] */
     const float*          labels;       /* [B] 0/1 (rating >= cutoff, trainers/ml_100k.py:48); NULL for forward */
 } dfm_raw_batch;
+
+#define DFM_ACT_RELU 0
+#define DFM_ACT_TANH 1
+#define DFM_ACT_SIGMOID 2
+#define DFM_ACT_IDENTITY 3
 
 typedef struct dfm_handle dfm_handle;
 

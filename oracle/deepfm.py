@@ -81,6 +81,8 @@ class OracleDeepFM:
         self.red = cfg.get("loss_reduction", "mean")
         self.dropout = float(cfg.get("dropout", 0.0))
         self.dropout_seed = int(cfg.get("dropout_seed", 0))
+        # params["activation"] of model_fn (trainers/deep_fm.py:22, handed to tf.layers.dense at :100; default tf.nn.relu)
+        self.activation = cfg.get("activation", "relu") or "identity"
         self.opt = {"deep": cfg.get("opt_deep", default_opt()),
                     "linear": cfg.get("opt_linear", default_opt())}
         self.nb = [num_buckets(s) for s in self.cat]
@@ -153,14 +155,19 @@ class OracleDeepFM:
             cache["s"] = s
         if self.use_dnn:
             h = E.reshape(B, -1)
-            acts = [h]
+            acts, pre, masks = [h], [], []
+            fwd = {"relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, "identity": lambda v: v}[self.activation]
             for i in range(len(self.hidden)):
-                h = torch.relu(h @ W["W%d" % i] + W["b%d" % i])
+                h = fwd(h @ W["W%d" % i] + W["b%d" % i])
+                pre.append(h)                                   # activation output before dropout
+                mk = None
                 if train and self.dropout > 0:
                     keepp = np.float32(1.0) - np.float32(self.dropout)
-                    mk = dropout_mask(self.dropout_seed, self.t + 1, i, B, h.shape[1], keepp)
-                    h = h * torch.as_tensor(mk, dtype=dt)
+                    mk = torch.as_tensor(dropout_mask(self.dropout_seed, self.t + 1, i, B, h.shape[1], keepp), dtype=dt)
+                    h = h * mk
+                masks.append(mk)
                 acts.append(h)
+            cache["pre"], cache["masks"] = pre, masks
             z = z + (h @ W["Wo"])[:, 0] + W["bo"][0]
             cache["acts"] = acts
         return (z, cache) if keep else z
@@ -220,10 +227,13 @@ class OracleDeepFM:
                 dh = dz[:, None] * W["Wo"][:, 0][None, :]
                 g["Wo"] = acts[L].t() @ dz[:, None]
                 g["bo"] = dz.sum().reshape(1)
-                dscale = 1.0 / float(np.float32(1.0) - np.float32(self.dropout)) if self.dropout > 0 else 1.0
+                fprime = {"relu": lambda yv: (yv > 0).to(self.dt), "tanh": lambda yv: 1 - yv * yv,
+                          "sigmoid": lambda yv: yv * (1 - yv), "identity": lambda yv: torch.ones_like(yv)}[self.activation]
                 for i in reversed(range(L)):
-                    # acts[i+1] is post-dropout: > 0 means ReLU active AND kept; kept elements carry 1/keep
-                    dh = dh * (acts[i + 1] > 0).to(self.dt) * dscale
+                    # derivative of the activation in terms of its output, times the dropout factor (0 or 1/keep)
+                    dh = dh * fprime(c["pre"][i])
+                    if c["masks"][i] is not None:
+                        dh = dh * c["masks"][i]
                     g["W%d" % i] = acts[i].t() @ dh
                     g["b%d" % i] = dh.sum(0)
                     dh = dh @ W["W%d" % i].t()

@@ -101,6 +101,7 @@ struct dfm_handle {
     dfm_optimizer od{}, ol{};
     int max_batch = 0, device = 0, rank = 0, world = 1;
     float dropout = 0.f; uint64_t dropout_seed = 0;
+    int activation = 0;          // DFM_ACT_*; != ReLU: general CUDA-core tower only
     std::vector<ColDev> cols;
     std::vector<std::string> col_names;
     std::vector<uint32_t> row_off;   // [dc+1]
@@ -342,6 +343,8 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     h->max_batch = cfg->max_batch; h->device = cfg->device; h->rank = cfg->rank; h->world = std::max(1, cfg->world);
     if (!(cfg->dropout >= 0.f && cfg->dropout < 1.f)) FAIL(DFM_ERR_INVALID_ARG, "dropout must be in [0, 1)");
     h->dropout = cfg->dropout; h->dropout_seed = cfg->dropout_seed;
+    if (cfg->activation < DFM_ACT_RELU || cfg->activation > DFM_ACT_IDENTITY) FAIL(DFM_ERR_INVALID_ARG, "activation must be one of DFM_ACT_*");
+    h->activation = cfg->activation;
     CK(cudaSetDevice(h->device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
@@ -444,7 +447,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
         // fused small-tower step (fused_small.cuh): its sparse optimizer rebuilds the lookup gradients on the fly, the
         // dense tiny-column reduction (which reads a dE buffer) is not used with it
         bool fused_candidate = false;
-        if (cfg->use_dnn && h->need_emb && !h->has_bags && h->L >= 1 && h->L <= SM_MAXL && K <= 32 && getenv("DFM_NO_FUSED") == nullptr &&
+        if (cfg->use_dnn && h->activation == DFM_ACT_RELU && h->need_emb && !h->has_bags && h->L >= 1 && h->L <= SM_MAXL && K <= 32 && getenv("DFM_NO_FUSED") == nullptr &&
             getenv("DFM_NO_SMALL_MLP") == nullptr) {
             const int H1 = h->hidden[0];
             fused_candidate = (H1 == 8 || H1 == 16 || H1 == 32);
@@ -592,7 +595,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     h->splits = (int)std::min<int64_t>(64, std::max<int64_t>(1, (Bm + 1023) / 1024));
     size_t splitk_elems = (size_t)h->splits * max_w, tc_split_total = 0;
     // tensor-core tower (3xTF32 tcgen05): every hidden width a multiple of 32 and at least one >= 64
-    if (h->use_dnn && h->L >= 1 && getenv("DFM_NO_TC") == nullptr && prop.major == 10) {
+    if (h->use_dnn && h->activation == DFM_ACT_RELU && h->L >= 1 && getenv("DFM_NO_TC") == nullptr && prop.major == 10) {
         bool ok = true, big = false;
         for (int i = 0; i < h->L; ++i) { ok = ok && (h->hidden[i] % 32 == 0); big = big || h->hidden[i] >= 64; }
         if (ok && big && tc_setup_once() > 0) {
@@ -620,7 +623,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
     h->head_blocks = (int)std::min<int64_t>(h->sm_count * 8, std::max<int64_t>(1, (Bm + 7) / 8));
     if (dalloc(h, &h->head_part, (size_t)h->head_blocks * 2)) return DFM_ERR_CUDA;
     // fused small-MLP path: every hidden layer <= 32 wide (not a real GEMM)
-    if (h->use_dnn && h->L >= 1 && h->L <= SM_MAXL && getenv("DFM_NO_SMALL_MLP") == nullptr) {
+    if (h->use_dnn && h->activation == DFM_ACT_RELU && h->L >= 1 && h->L <= SM_MAXL && getenv("DFM_NO_SMALL_MLP") == nullptr) {
         bool ok = (h->hidden[0] == 8 || h->hidden[0] == 16 || h->hidden[0] == 32);
         int sum = 0;
         for (int i = 0; i < h->L; ++i) { ok = ok && h->hidden[i] <= SM_MAXH; sum += h->hidden[i]; }
@@ -696,7 +699,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
             }
         }
     }
-    if (h->use_dnn && !h->small_mlp && h->L >= 1 && h->hidden[h->L - 1] % 32 == 0 && h->hidden[h->L - 1] <= 256 &&
+    if (h->use_dnn && h->activation == DFM_ACT_RELU && !h->small_mlp && h->L >= 1 && h->hidden[h->L - 1] % 32 == 0 && h->hidden[h->L - 1] <= 256 &&
         getenv("DFM_NO_FUSED_HEAD") == nullptr) {
         h->fused_head = true;
         h->fused_head_blocks = std::min(h->head_blocks, 2 * h->sm_count);
@@ -1141,7 +1144,7 @@ static int forward_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream_t 
         for (int i = 0; i < h->L; ++i) {
             const DenseT* W = find_dense(h, "W" + std::to_string(i));
             const DenseT* b = find_dense(h, "b" + std::to_string(i));
-            EpiArgs ep{}; ep.bias = h->dw + b->off;
+            EpiArgs ep{}; ep.bias = h->dw + b->off; ep.act_kind = h->activation;
             set_dropout(h, ep, labels != nullptr, i);
             launch_sgemm<true, false, EPI_BIAS_RELU>(h, h->act[i], in, h->dw + W->off, h->hidden[i], h->act[i + 1], h->hidden[i], B,
                                                      h->hidden[i], in, 1, (in + 15) / 16 * 16, ep, st);
@@ -1265,7 +1268,7 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
         } else {
             if (!h->fused_head) {
                 dh_last_kernel<<<cdiv((int64_t)B * H, 256), 256, 0, st>>>(hL, h->dw + Wo->off, h->dz, (int64_t)B * H, H, h->dact[L],
-                                                                          h->dropout > 0.f ? 1.f / (1.f - h->dropout) : 1.f);
+                                                                          h->dropout > 0.f ? 1.f / (1.f - h->dropout) : 1.f, h->activation);
                 h->launches++;
             }
             const int splits = std::max(1, std::min(h->splits, (B + 1023) / 1024));
@@ -1315,7 +1318,7 @@ static int tower_backward(dfm_handle* h, const BatchPtrs& bp, int B, float scale
                     }
                     if (rc2) return rc2;
                 } else if (i > 0) {
-                    EpiArgs ep{}; ep.act = h->act[i]; ep.ld_act = in;
+                    EpiArgs ep{}; ep.act = h->act[i]; ep.ld_act = in; ep.act_kind = h->activation;
                     ep.bwd_scale = h->dropout > 0.f ? 1.f / (1.f - h->dropout) : 0.f;
                     launch_sgemm<true, true, EPI_MASK>(h, h->dact[i + 1], out, h->dw + W->off, out, h->dact[i], in, B, in, out, 1,
                                                        (out + 15) / 16 * 16, ep, st);
@@ -1894,7 +1897,7 @@ extern "C" int dfm_layer_summary(dfm_handle* h, const dfm_raw_batch* b, int32_t 
             a.drop_keep = 1.f - h->dropout; a.drop_inv = 1.f / (1.f - h->dropout);
             a.drop_seed = h->dropout_seed; a.drop_step = (uint64_t)(h->step + 1); a.drop_row0 = (int64_t)h->rank * h->max_batch;
         }
-        a.hidden_out = h->sum_hidden; a.dnn_logit = h->sum_dnn;
+        a.hidden_out = h->sum_hidden; a.dnn_logit = h->sum_dnn; a.act_kind = h->activation;
         const int smem = 4 * 2 * maxdim * 4;
         if (smem > 200 * 1024) FAIL(DFM_ERR_UNSUPPORTED, "layer summary: layer too wide for the diagnostic tower kernel");
         static int attr = 0;

@@ -23,7 +23,30 @@ __device__ __forceinline__ float dfm_drop(uint64_t key, uint64_t idx, float keep
     return u < keep ? inv_keep : 0.f;
 }
 
+// params["activation"] of the reference (trainers/deep_fm.py:22,100).  Forward value and derivative expressed in the
+// layer's OUTPUT y (that is what the backward pass has at hand); with dropout the stored output is y * mask / keep:
+// a stored zero is a dropped unit (for tanh / identity also the measure-zero case of an exactly zero pre-activation).
+__device__ __forceinline__ float act_fwd(int kind, float x) {
+    switch (kind) {
+        case 1: return tanhf(x);
+        case 2: return 1.f / (1.f + expf(-x));
+        case 3: return x;
+        default: return fmaxf(x, 0.f);
+    }
+}
+__device__ __forceinline__ float act_bwd(int kind, float y_stored, float g, float drop_scale /* 1 / keep, <= 0: no dropout */) {
+    if (kind == 0) return y_stored > 0.f ? (drop_scale > 0.f ? g * drop_scale : g) : 0.f;
+    float y = y_stored, sc = 1.f;
+    if (drop_scale > 0.f) {
+        if (y_stored == 0.f) return 0.f;
+        y = y_stored / drop_scale; sc = drop_scale;
+    }
+    const float d = kind == 1 ? 1.f - y * y : kind == 2 ? y * (1.f - y) : 1.f;
+    return g * sc * d;
+}
+
 struct EpiArgs {
+    int      act_kind;   // DFM_ACT_* (0 = ReLU)
     float    drop_keep;  // EPI_BIAS_RELU: > 0 -> dropout after the activation (keep probability)
     float    drop_inv;   //                1 / keep
     uint64_t drop_key;
@@ -197,9 +220,9 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
                 if (n >= N) continue;
                 float x = v[c];
                 if (EPI == EPI_BIAS_RELU) {
-                    x = fmaxf(x + ep.bias[n], 0.f);
+                    x = act_fwd(ep.act_kind, x + ep.bias[n]);
                     if (ep.drop_keep > 0.f) x *= dfm_drop(ep.drop_key, (uint64_t)(ep.drop_row0 + gm) * N + n, ep.drop_keep, ep.drop_inv);
-                } else if (EPI == EPI_MASK) x = ep.act[(size_t)gm * ep.ld_act + n] > 0.f ? (ep.bwd_scale > 0.f ? x * ep.bwd_scale : x) : 0.f;
+                } else if (EPI == EPI_MASK) x = act_bwd(ep.act_kind, ep.act[(size_t)gm * ep.ld_act + n], x, ep.bwd_scale);
                 else if (EPI == EPI_DE) {
                     if (ep.s) x += dzm * (ep.s[(size_t)gm * ep.K + (n % ep.K)] - ep.act[(size_t)gm * ep.ld_act + n]);
                 }
@@ -437,12 +460,13 @@ static __global__ void head_final_kernel(const float* __restrict__ part, int nbl
 
 // dh_L'[b,j] = dz[b] * Wo[j] * (h_L[b,j] > 0)
 static __global__ void dh_last_kernel(const float* __restrict__ hL, const float* __restrict__ Wo, const float* __restrict__ dz,
-                               int64_t total, int H, float* __restrict__ dh, float drop_scale) {
+                               int64_t total, int H, float* __restrict__ dh, float drop_scale, int act_kind = 0) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < total) {
         int64_t b = i / H;
         int j = (int)(i - b * H);
-        dh[i] = !hL ? dz[b] * Wo[j] : (hL[i] > 0.f ? dz[b] * Wo[j] * drop_scale : 0.f);   // hL == nullptr: no ReLU in front (hidden_units == [])
+        // hL == nullptr: no activation in front (hidden_units == []); drop_scale == 1: no dropout
+        dh[i] = !hL ? dz[b] * Wo[j] : act_bwd(act_kind, hL[i], dz[b] * Wo[j], drop_scale != 1.f ? drop_scale : (act_kind ? 0.f : 1.f));
     }
 }
 

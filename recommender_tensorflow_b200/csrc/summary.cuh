@@ -15,6 +15,7 @@ struct SummaryTowerArgs {
     int L; int H[DFM_MAX_HIDDEN]; int off_W[DFM_MAX_HIDDEN]; int off_b[DFM_MAX_HIDDEN]; int off_Wo, off_bo;
     int B, maxdim, hid_stride;               // hid_stride = sum of H
     float drop_keep, drop_inv; uint64_t drop_seed, drop_step; int64_t drop_row0;     // keep == 0: no dropout
+    int act_kind;                            // DFM_ACT_*
     float* hidden_out;                       // [B, hid_stride]: layer i at column offset sum_{j<i} H[j]
     float* dnn_logit;                        // [B]
 };
@@ -38,7 +39,7 @@ static __global__ void __launch_bounds__(128) summary_tower_kernel(SummaryTowerA
             for (int o = lane; o < out; o += 32) {
                 float v = 0.f;
                 for (int j = 0; j < in; ++j) v = fmaf(x[j], __ldg(W + (size_t)j * out + o), v);
-                v = fmaxf(v + bb[o], 0.f);
+                v = act_fwd(a.act_kind, v + bb[o]);
                 if (a.drop_keep > 0.f) v *= dfm_drop(key, (uint64_t)(a.drop_row0 + b) * out + o, a.drop_keep, a.drop_inv);
                 y[o] = v;
                 a.hidden_out[(size_t)b * a.hid_stride + col + o] = v;

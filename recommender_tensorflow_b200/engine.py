@@ -48,8 +48,13 @@ class DeepFMEngine:
     def __init__(self, categorical_columns, numeric_columns=(), embedding_size=4, hidden_units=(16, 16),
                  use_linear=True, use_mf=True, use_dnn=True, loss_reduction="mean", opt_deep=None,
                  opt_linear=None, max_batch=65536, device=0, feature_dtypes=None, sort_columns=True, rank=0, world=1, dropout=0.0, dropout_seed=0,
-                 multivalent=None):
+                 multivalent=None, activation="relu"):
         self.lib = _lib.load()
+        # params["activation"] (trainers/deep_fm.py:22): a name, None (identity) or a callable named like a tf.nn activation
+        act = activation if (activation is None or isinstance(activation, str)) else getattr(activation, "__name__", str(activation))
+        if act not in _lib.ACTIVATIONS:
+            raise ValueError("activation %r is not one of %s" % (activation, sorted(k for k in _lib.ACTIVATIONS if k)))
+        self.activation = "identity" if act in (None, "linear") else act
         cats = list(categorical_columns)
         nums = list(numeric_columns)
         if sort_columns:   # tf.feature_column.input_layer / linear_model iterate columns sorted by name
@@ -101,7 +106,8 @@ class DeepFMEngine:
         cfg = _lib.Config(len(cats), C.cast(cols, C.POINTER(_lib.Column)), len(nums), self.k, len(self.hidden),
                           C.cast(hid, C.POINTER(C.c_int32)), int(self.use_linear), int(self.use_mf), int(self.use_dnn),
                           _lib.LOSS_RED[loss_reduction], _opt_struct(self.opt_deep), _opt_struct(self.opt_linear),
-                          self.max_batch, self.device, self.rank, self.world, None, self.dropout, self.dropout_seed)
+                          self.max_batch, self.device, self.rank, self.world, None, self.dropout, self.dropout_seed,
+                          _lib.ACTIVATIONS[self.activation])
         self._keep += [cols, hid]
         handle = C.c_void_p()
         rc = self.lib.dfm_create(C.byref(cfg), C.byref(handle))

@@ -38,14 +38,14 @@ def _build_engine(params, batch_size):
         raise ValueError("At least 1 feature column of categorical_columns or numeric_columns must be specified.")
     if not (use_linear or use_mf or use_dnn):
         raise ValueError("At least 1 of linear, mf or dnn component must be used.")
-    if activation_fn not in ("relu", None) and getattr(activation_fn, "__name__", "") != "relu":
-        raise NotImplementedError("only the reference default activation (ReLU) is built")
+    # params["activation"]: a tf.nn callable in the reference (default tf.nn.relu); here its name, a callable named
+    # relu / tanh / sigmoid / identity, or None (tf.layers.dense without activation)
     opt = get_optimizer(optimizer, learning_rate)
     eng = DeepFMEngine(categorical_columns, numeric_columns, embedding_size=embedding_size, hidden_units=hidden_units,
                        use_linear=bool(use_linear), use_mf=bool(use_mf), use_dnn=bool(use_dnn), loss_reduction="mean",
                        opt_deep=opt, opt_linear=dict(opt), max_batch=params.get("max_batch", max(batch_size, 1)),
                        device=params.get("device", 0), feature_dtypes=params.get("feature_dtypes", FEATURE_DTYPES),
-                       dropout=float(dropout or 0.0), dropout_seed=int(params.get("dropout_seed", 0)))
+                       dropout=float(dropout or 0.0), dropout_seed=int(params.get("dropout_seed", 0)), activation=activation_fn)
     # the variable initialisers TF runs when the graph is first executed (truncated normal 1/sqrt(k) for the embedding
     # tables, glorot uniform for the dense kernels, zeros for linear weights and biases); RunConfig.tf_random_seed
     seed = params.get("tf_random_seed")

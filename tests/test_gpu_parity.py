@@ -219,6 +219,32 @@ def test_other_optimizers_of_get_optimizer(name):
     _run_steps(eng, ora, [ml.batch(300, rng) for _ in range(4)], "opt-" + name)
 
 
+@pytest.mark.parametrize("activation,dropout", [("tanh", 0.0), ("sigmoid", 0.0), ("identity", 0.0), (None, 0.0), ("tanh", 0.2), ("sigmoid", 0.3)])
+def test_activation_param(activation, dropout):
+    """params["activation"] (trainers/deep_fm.py:22,100): anything but ReLU runs the general tower; forward, backward,
+    every weight and slot against the oracle, with and without dropout."""
+    eng = _ml_engine(k=8, hidden=(24, 16), max_batch=512, activation=activation, dropout=dropout, dropout_seed=11)
+    assert eng.activation == (activation or "identity")
+    ora, _ = make_pair(eng, seed=44)
+    ml, rng = synth.ML100K(), np.random.default_rng(45)
+    _run_steps(eng, ora, [ml.batch(300, rng) for _ in range(4)], "act-%s-%s" % (activation, dropout))
+
+
+def test_activation_through_model_fn_and_bad_name():
+    from recommender_tensorflow_b200.trainers import deep_fm, ml_100k
+
+    def tanh(x):            # a callable named like the tf.nn function, as the reference passes it
+        return np.tanh(x)
+    fcs = ml_100k.get_feature_columns(embedding_size=4)
+    params = {"categorical_columns": fcs["linear"], "embedding_size": 4, "hidden_units": [16, 16], "activation": tanh, "max_batch": 64,
+              "tf_random_seed": 1}
+    feats, y = synth.ML100K().batch(64, np.random.default_rng(3))
+    spec = deep_fm.model_fn(feats, y, ml_100k.ModeKeys.TRAIN, params)
+    assert np.isfinite(spec.loss) and params[deep_fm._ENGINE_KEY].activation == "tanh"
+    with pytest.raises(ValueError):
+        _ml_engine(activation="swish")
+
+
 @pytest.mark.parametrize("hidden", [(16, 16), (64, 32), (20, 12)])
 def test_dropout_all_tower_paths(hidden):
     """trainers/deep_fm.py:102-103 dropout after every hidden layer (reference CLI default 0.1): fused small-MLP,

@@ -26,8 +26,8 @@ def _data(B=16, seed=0):
 
 
 def test_backward_matches_autograd_fp64():
-    for red in ("mean", "sum"):
-        cfg = _cfg(loss_reduction=red)
+    for red, act in (("mean", "relu"), ("sum", "relu"), ("mean", "tanh"), ("mean", "sigmoid"), ("sum", "identity")):
+        cfg = _cfg(loss_reduction=red, activation=act)
         w = init_weights(cfg, 3)
         w["lin"] = np.random.default_rng(0).standard_normal(w["lin"].shape).astype(np.float32) * 0.1
         m = OracleDeepFM(cfg, w, dtype=torch.float64)

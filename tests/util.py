@@ -23,7 +23,7 @@ def oracle_cfg(engine, **over):
                hidden=list(engine.hidden), use_linear=engine.use_linear, use_mf=engine.use_mf,
                use_dnn=engine.use_dnn, loss_reduction=engine.loss_reduction, opt_deep=o(engine.opt_deep),
                opt_linear=o(engine.opt_linear), dropout=getattr(engine, "dropout", 0.0),
-               dropout_seed=getattr(engine, "dropout_seed", 0))
+               dropout_seed=getattr(engine, "dropout_seed", 0), activation=getattr(engine, "activation", "relu"))
     cfg.update(over)
     return cfg
 
