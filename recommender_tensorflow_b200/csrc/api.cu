@@ -168,6 +168,8 @@ struct dfm_handle {
     bool claim_live = false;          // this step's claim table is filled: once-only rows are applied by fused_rows_kernel
     bool last_step_rows = false;
     bool fr_side = false;             // this step's sort runs on the side stream beside fused_rows_kernel
+    // row-sharded requester on the record-staged kernel (row-buffer mode)
+    bool fused_rows_rb = false; size_t fr_smem_rb = 0; uint8_t* once_lk = nullptr; bool fr_rb_live = false;
 
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     // small tables: the sort / segment stage runs on a side stream next to the gather and the tower (see train_impl)
@@ -274,7 +276,7 @@ static void free_all(dfm_handle* h) {
     cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cols, h->d_bounds, h->d_voc_bytes, h->d_voc_offs, h->d_row_off, h->tb.rec, h->dw,
                     h->ds1, h->ds2, h->dg, h->ids, h->h0, h->s, h->zacc, h->logits, h->dz, h->dE, h->splitk, h->colpart, h->head_part,
-                    h->d_loss, h->d_dzsum, h->d_err, h->num_partial, h->num_scratch, h->fused_done, h->claim, h->sum_h0, h->sum_s, h->sum_lin, h->sum_mf, h->sum_hidden, h->sum_dnn, h->sum_logits, h->sum_limits, h->sum_stats, h->sum_buckets, h->up_partial, h->w0_partial, h->tc_w, h->head_gpart, h->d_slot_col, h->d_slot_j, h->d_field_slot0, h->inv_cnt, h->uidx,
+                    h->d_loss, h->d_dzsum, h->d_err, h->num_partial, h->num_scratch, h->fused_done, h->claim, h->once_lk, h->sum_h0, h->sum_s, h->sum_lin, h->sum_mf, h->sum_hidden, h->sum_dnn, h->sum_logits, h->sum_limits, h->sum_stats, h->sum_buckets, h->up_partial, h->w0_partial, h->tc_w, h->head_gpart, h->d_slot_col, h->d_slot_j, h->d_field_slot0, h->inv_cnt, h->uidx,
                     h->req_rows, h->d_counts};
     for (void* p : ptrs) if (p) cudaFree(p);
     free_ws(h->ws);
@@ -667,6 +669,15 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
                 if (rcf) return rcf;
                 // record-staged variant: the shapes BASELINE.json names (k = 16, first hidden layer 16), unsharded
                 const int rs = K + 4 + h->emb_slots * K;
+                if (fused_rows_supported(K, m.H[0], h->dc, h->dn) && h->world > 1 && !h->has_bags && h->dropout == 0.f && h->need_emb &&
+                    getenv("DFM_NO_FUSED_ROWS") == nullptr && getenv("DFM_NO_STAGED_APPLY") == nullptr) {
+                    h->fr_smem_rb = fused_rows_smem_bytes(m, K, h->dc, h->dn, K + 4);
+                    if (h->fr_smem_rb <= 227 * 1024) {
+                        h->fused_rows_rb = true;
+                        CK(fused_rows_set_attr((int)h->fr_smem_rb));
+                        if (dalloc(h, &h->once_lk, (size_t)h->max_batch * h->dcs)) return DFM_ERR_CUDA;
+                    }
+                }
                 if (fused_rows_supported(K, m.H[0], h->dc, h->dn) && h->world == 1 && !h->has_bags && h->dropout == 0.f && h->need_emb &&
                     getenv("DFM_NO_FUSED_ROWS") == nullptr) {
                     h->fr_smem = fused_rows_smem_bytes(m, K, h->dc, h->dn, rs);
@@ -1392,19 +1403,20 @@ static int sparse_update(dfm_handle* h, SegWS& ws, int64_t n, const SRC& src, co
             if (attr < smem) { CK(cudaFuncSetAttribute(row_gsum_kernel<K, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = smem; }
             S2 s2{}; s2.s = src;
             row_gsum_kernel<K, S2><<<n > 0 ? (unsigned)h->sm_count * 2 : 1, 256, smem, st>>>(ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0,
-                                                                                           ws.piece_start, ws.seg_cnt, s2, ws.piece_sum, route);
+                                                                                           ws.piece_start, ws.seg_cnt, s2, ws.piece_sum, route, h->fr_rb_live);
         } else if constexpr (!kBags) {
             const int smem = RowGsumCfg<K, SRC>::SMEM + src.aux_floats() * 4;
             if (smem > 200 * 1024) FAIL(DFM_ERR_UNSUPPORTED, "internal: staged gradient-row kernel does not fit in shared memory");
             static int attr = 0;
             if (attr < smem) { CK(cudaFuncSetAttribute(row_gsum_kernel<K, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = smem; }
             row_gsum_kernel<K, SRC><<<n > 0 ? (unsigned)h->sm_count * 2 : 1, 256, smem, st>>>(ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0,
-                                                                                            ws.piece_start, ws.seg_cnt, src, ws.piece_sum, route);
+                                                                                            ws.piece_start, ws.seg_cnt, src, ws.piece_sum, route, h->fr_rb_live);
         }
     } else {
         row_update_kernel<K, SRC><<<n > 0 ? row_grid : 1, 256, 0, st>>>(ws.urow, ws.uval, ws.svals(), ws.row_start, ws.row_piece0, ws.piece_start, ws.seg_cnt, src,
                                                                    ws.piece_sum, h->tb, h->emb_slots, od, ol, (bool)h->need_emb,
-                                                                   (bool)h->use_linear, (int)t, make_rr(h, gsum ? -1 : t - 1), gsum, K + 4, route);
+                                                                   (bool)h->use_linear, (int)t, make_rr(h, gsum ? -1 : t - 1), gsum, K + 4, route,
+                                                                   h->fr_rb_live && gsum && !route);
     }
     h->launches++;
     if (ph) ph->next();
@@ -1452,19 +1464,21 @@ static FusedArgs make_fused_args(dfm_handle* h, const BatchPtrs& bp, int B, cons
 // record-staged step (fused_rows.cuh): gather + tower forward/backward + the optimizer of once-only rows in one kernel
 template <int K>
 static int launch_fused_rows(dfm_handle* h, const BatchPtrs& bp, int B, const float* labels, float scale, float* logits_out, int64_t upto,
-                             const StepOpts* so, int64_t t, cudaStream_t st) {
+                             const StepOpts* so, int64_t t, cudaStream_t st, const float* rowbuf = nullptr, float* gsum = nullptr,
+                             const PeerRoute* route = nullptr) {
     if constexpr (K == 16) {
         FusedRowsArgs A{};
-        A.f = make_fused_args<K>(h, bp, B, labels, scale, logits_out, nullptr, upto);
+        A.f = make_fused_args<K>(h, bp, B, labels, scale, logits_out, rowbuf, upto);
         A.claim = (so && h->claim_live) ? h->claim : nullptr; A.claim_mask = h->claim_mask;
-        A.emb_slots = h->emb_slots;
-        A.rs = K + 4 + h->emb_slots * K;
+        A.emb_slots = rowbuf ? 0 : h->emb_slots;
+        A.rowbuf_mode = rowbuf ? 1 : 0; A.once_lk = h->once_lk; A.route = route; A.gsum = gsum;
+        A.rs = K + 4 + A.emb_slots * K;
         A.sst = fr_sst(h->dc, h->dn, K, A.rs);
         A.step = (int)t;
         if (so) { A.od_t = so->od; A.ol_t = so->ol; }
         A.numg_partial = h->num_partial;
-        const int grid = fused_rows_grid(B, h->sm_count, h->fr_side);
-        CK(fused_rows_launch(A, grid, h->fr_smem, st));
+        const int grid = fused_rows_grid(B, h->sm_count, rowbuf ? false : h->fr_side);
+        CK(fused_rows_launch(A, grid, rowbuf ? h->fr_smem_rb : h->fr_smem, st));
         h->launches++;
         return DFM_OK;
     }
@@ -1518,7 +1532,7 @@ static int launch_fused_reduce(dfm_handle* h, int B, float scale, float* loss_ou
     const DenseT* ne = find_dense(h, "num_emb"); const DenseT* nl = find_dense(h, "num_lin"); const DenseT* bs = find_dense(h, "bias");
     FusedReduceArgs r{};
     r.up_partial = h->up_partial; r.w0_partial = h->w0_partial; r.num_partial = h->num_partial; r.head_part = h->head_part;
-    r.n_cta = rows ? fused_rows_grid(B, h->sm_count, h->fr_side) : std::min((B + FS_TS - 1) / FS_TS, h->fused_grid);
+    r.n_cta = rows ? fused_rows_grid(B, h->sm_count, h->fr_rb_live ? false : h->fr_side) : std::min((B + FS_TS - 1) / FS_TS, h->fused_grid);
     r.up_count = h->sm.up_count; r.up_begin = h->sm.up_begin; r.off_W0 = h->sm.off_W[0]; r.w0_count = h->sm.D * h->sm.H[0];
     r.n_numacc = rows ? h->dn * h->K + h->dn : h->n_numacc;
     r.direct_num = rows ? 1 : 0;
@@ -2068,7 +2082,7 @@ static int shard_requests_impl(dfm_handle* h, const BatchPtrs& bp, int B, uint32
     if ((rc = build_segments(h, h->ws, n, limit, h->key_bits, st, nullptr))) return rc;
     CK(cudaMemsetAsync(h->d_counts, 0, ((size_t)W + 1) * 4, st));
     if (n > 0) {
-        shard_uniq_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->ws.skeys(), h->ws.svals(), n, limit, h->Rl, W, h->dcs, h->ws.pos_row, h->uidx, h->req_rows, h->d_counts);
+        shard_uniq_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->ws.skeys(), h->ws.svals(), n, limit, h->Rl, W, h->dcs, h->ws.pos_row, h->uidx, h->req_rows, h->d_counts, h->once_lk);
         h->launches++;
     }
     CK(cudaMemcpyAsync(h->h_counts, h->d_counts, (size_t)W * 4, cudaMemcpyDeviceToHost, st));
@@ -2144,9 +2158,16 @@ static int shard_fb_impl(dfm_handle* h, const BatchPtrs& bp, int B, const float*
     int rc;
     if (h->fused) {
         if constexpr (K <= 32) {
-            if ((rc = launch_fused<K>(h, bp, B, bp.labels, scale, logits_out, rowbuf, -1, st))) return rc;
-            if ((rc = launch_fused_reduce(h, B, scale, loss_out, st))) return rc;
-            if ((rc = fused_sparse_update<K>(h, h->ws, n, so, t, gsum, rowbuf, st, nullptr, route))) return rc;
+            // record-staged kernel in row-buffer mode: the gradient rows of the rows looked up once leave from inside it
+            const bool rb = h->fused_rows_rb && gsum != nullptr;
+            h->fr_rb_live = rb;
+            if (rb) rc = launch_fused_rows<K>(h, bp, B, bp.labels, scale, logits_out, -1, &so, t, st, rowbuf, route ? nullptr : gsum, route);
+            else rc = launch_fused<K>(h, bp, B, bp.labels, scale, logits_out, rowbuf, -1, st);
+            if (rc) return rc;
+            if ((rc = launch_fused_reduce(h, B, scale, loss_out, st, rb))) return rc;
+            rc = fused_sparse_update<K>(h, h->ws, n, so, t, gsum, rowbuf, st, nullptr, route);
+            h->fr_rb_live = false;
+            if (rc) return rc;
         }
     } else {
         if ((rc = forward_impl<K>(h, bp, B, st, bp.labels, scale, logits_out, nullptr, rowbuf))) return rc;
@@ -2305,7 +2326,7 @@ static int xchg_begin_impl(dfm_handle* h, const BatchPtrs& bp, int B, cudaStream
     if ((rc = build_segments(h, h->ws, n, limit, h->key_bits, st, nullptr))) return rc;
     CK(cudaMemsetAsync(h->d_counts, 0, ((size_t)W + 1) * 4, st));
     if (n > 0) {
-        shard_uniq_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->ws.skeys(), h->ws.svals(), n, limit, h->Rl, W, h->dcs, h->ws.pos_row, h->uidx, h->req_rows, h->d_counts);
+        shard_uniq_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->ws.skeys(), h->ws.svals(), n, limit, h->Rl, W, h->dcs, h->ws.pos_row, h->uidx, h->req_rows, h->d_counts, h->once_lk);
         h->launches++;
     }
     h->x_epoch += 1;

@@ -771,7 +771,8 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
                                                          Table tb, int emb_slots, OptDev od, OptDev ol,
                                                          bool has_emb, bool has_lin, int step, RowReplay rr,
                                                          float* __restrict__ gsum_out, int gsum_stride,
-                                                         const PeerRoute* __restrict__ rt) {
+                                                         const PeerRoute* __restrict__ rt, bool skip_single = false) {
+    // skip_single: rows with exactly one lookup were already written by fused_rows_kernel (row-buffer mode)
     constexpr int LPR = K / 4;
     const int sub = threadIdx.x % LPR;
     const uint32_t gpb = blockDim.x / LPR;
@@ -787,9 +788,10 @@ __global__ void __launch_bounds__(256) row_update_kernel(const uint32_t* __restr
     for (uint32_t ubase = 0; ubase < U; ubase += TG) {   // block-uniform trip count
         const uint32_t u = ubase + uoff;
         bool coop = false;
-        const bool act = u < U;
+        bool act = u < U;
         uint32_t beg = 0, end = 0, row = 0, v0 = 0xffffffffu;
         if (act) { beg = row_start[u]; end = row_start[u + 1]; row = __ldg(urow + u); v0 = __ldg(uval + u); }
+        if (skip_single && end - beg == 1) { act = false; end = beg; }
         // issue the table-record loads now: they only depend on the row id and overlap the gradient gather below
         float4 w = make_float4(0.f, 0.f, 0.f, 0.f), s1 = w, s2 = w, lr = w;
         if (act && !gsum_out) {
@@ -981,7 +983,9 @@ static __global__ void shard_rekey_kernel(uint32_t* __restrict__ keys, int64_t n
 static __global__ void __launch_bounds__(256) shard_uniq_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svals, int64_t n,
                                                          uint32_t limit, uint32_t Rl, uint32_t W, int n_slots,
                                                          const uint32_t* __restrict__ pos_row, uint32_t* __restrict__ uidx,
-                                                         uint32_t* __restrict__ req_rows, int32_t* __restrict__ counts) {
+                                                         uint32_t* __restrict__ req_rows, int32_t* __restrict__ counts,
+                                                         uint8_t* __restrict__ once_lk = nullptr) {
+    // once_lk[lookup] = 1: the lookup's row is looked up exactly once in this rank's batch
     // per-owner counts are aggregated per block in shared memory first: the sorted keys put (almost) every
     // lookup of a block on the same owner, and same-address global atomics serialise in L2
     __shared__ int sc[64];
@@ -996,6 +1000,7 @@ static __global__ void __launch_bounds__(256) shard_uniq_kernel(const uint32_t* 
             bool rh = (i == 0) || (k != skeys[i - 1]);
             const uint32_t ridx = pos_row[i];
             uidx[(size_t)payload_sample(svals[i]) * n_slots + payload_slot(svals[i])] = ridx;
+            if (once_lk) once_lk[(size_t)payload_sample(svals[i]) * n_slots + payload_slot(svals[i])] = (rh && (i + 1 >= n || skeys[i + 1] != k)) ? 1 : 0;
             if (rh) {
                 req_rows[ridx] = k % Rl;
                 uint32_t o = k / Rl;

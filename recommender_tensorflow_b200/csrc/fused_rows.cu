@@ -104,8 +104,14 @@ __device__ __forceinline__ void mma3(float (&cm)[4], float (&cx)[4], const uint3
     mma_tf32(cx, ah, bl, cx);
 }
 
-template <int K, int H1, int ES>
+// RB (row-buffer mode, the row-sharded requester): the rows were fetched from their owners into a row buffer
+// [unique row][w[K] | lin, pad] (ES = 0 records of K + 4 floats, nothing to replay), the table lives elsewhere: the
+// gradient row of a row looked up once in the local batch is stored straight into its owner's gradient segment (peer
+// memory over NVLink, or the local send buffer of the collective path); rows looked up several times are left to
+// row_gsum_kernel / row_update_kernel, which skip the single ones.
+template <int K, int H1, int ES, bool RB>
 __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs A) {
+    static_assert(!RB || ES == 0, "row-buffer records carry no optimizer slots");
     static_assert(K == 16 && H1 == 16, "instantiated for embedding_size 16 / first hidden layer 16");
     constexpr int NT = FR_CW * 32;                               // consumer threads
     const FusedArgs& a = A.f;
@@ -167,7 +173,14 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                 idn[q] = -1;
                 if (tile < ntiles && r < r1) {
                     const int64_t gi = (int64_t)tile * nrows + r;
-                    if (gi < (int64_t)a.B * dc) idn[q] = __ldg(a.ids + gi);
+                    if (gi < (int64_t)a.B * dc) {
+                        if (RB) {          // unique-row index of the lookup (~0: no row) + "looked up once" flag in bit 30
+                            const uint32_t u = __ldg(a.uidx + gi);
+                            idn[q] = u == 0xffffffffu ? -1 : (int32_t)(u | (__ldg(A.once_lk + gi) ? 0x40000000u : 0u));
+                        } else {
+                            idn[q] = __ldg(a.ids + gi);
+                        }
+                    }
                 }
             }
         };
@@ -182,9 +195,9 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
             for (int q = 0; q < FR_NR; ++q) {
                 const int r = r0 + lane + 32 * q;
                 row[q] = 0xffffffffu; cw[q] = 0;
-                if (r < r1 && idn[q] >= 0) row[q] = __ldg(a.row_off + r % dc) + (uint32_t)idn[q];
+                if (r < r1 && idn[q] >= 0) row[q] = RB ? ((uint32_t)idn[q] & 0x3fffffffu) : __ldg(a.row_off + r % dc) + (uint32_t)idn[q];
             }
-            if (train && A.claim) {
+            if (!RB && train && A.claim) {
 #pragma unroll
                 for (int q = 0; q < FR_NR; ++q)
                     if (row[q] != 0xffffffffu) cw[q] = __ldg(A.claim + ((row[q] & A.claim_mask) >> 4));
@@ -197,7 +210,8 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                     uint32_t one = 0;
                     if (row[q] != 0xffffffffu) {
                         ++nvalid;
-                        one = ((cw[q] >> (((row[q] & A.claim_mask) & 15u) * 2u)) & 3u) == 1u ? 1u : 0u;
+                        if (RB) one = ((uint32_t)idn[q] >> 30) & 1u;
+                        else one = ((cw[q] >> (((row[q] & A.claim_mask) & 15u) * 2u)) & 3u) == 1u ? 1u : 0u;
                     } else {
                         const int sl = r / dc, f = r - sl * dc;
                         float* dst = slot + (size_t)sl * SST + f * RS;
@@ -221,7 +235,8 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                 const int r = r0 + lane + 32 * q;
                 if (r < r1 && row[q] != 0xffffffffu) {
                     const int sl = r / dc, f = r - sl * dc;
-                    bulk_load(slot + (size_t)sl * SST + f * RS, a.tb.rec + (size_t)row[q] * a.tb.stride, rsb, &full[s]);
+                    const float* srcp = RB ? a.rowbuf + (size_t)row[q] * a.rowbuf_stride : a.tb.rec + (size_t)row[q] * a.tb.stride;
+                    bulk_load(slot + (size_t)sl * SST + f * RS, srcp, rsb, &full[s]);
                 }
             }
             load_ids(tile + gridDim.x);                     // in flight while the consumers work
@@ -238,7 +253,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
     const ReplayStep rs = replay_step_load(a.rr.rd.closed ? a.rr.rd : a.rr.rl, a.rr.upto);
     const int g = lane >> 2, t = lane & 3;                   // MMA fragment coordinates (also: P1 field group / float4 slice)
     const bool use_mf = a.use_mf != 0, use_lin = a.use_linear != 0;
-    const bool inline_apply = train && A.claim != nullptr;
+    const bool inline_apply = train && (RB || A.claim != nullptr);
     float wacc[FR_NF][2][4];                                 // dW0 of this warp's fields: [field][unit tile][fragment]
 #pragma unroll
     for (int i = 0; i < FR_NF; ++i) {
@@ -629,7 +644,28 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                         }
                         __syncwarp();
                         float4 gr = *reinterpret_cast<const float4*>(gst + g * K + ((t ^ (g >> 1)) & 3) * 4);    // lane = (sample g, slice t)
-                        if (f < dc) {
+                        if (RB && f < dc) {
+                            if (onc[g * dc + f]) {
+                                const float* rec = slot + (size_t)g * SST + off;
+                                if (use_mf) {
+                                    const float4 w = *reinterpret_cast<const float4*>(rec + t * 4);
+                                    const float4 sv = *reinterpret_cast<const float4*>(ss + g * K + t * 4);
+                                    gr.x = fmaf(dzr, sv.x - w.x, gr.x); gr.y = fmaf(dzr, sv.y - w.y, gr.y);
+                                    gr.z = fmaf(dzr, sv.z - w.z, gr.z); gr.w = fmaf(dzr, sv.w - w.w, gr.w);
+                                }
+                                const uint32_t u = rix[g * dc + f];
+                                float* dst;
+                                if (A.route) {
+                                    const PeerRoute* rt = A.route;
+                                    const int o = route_find(rt->send_off, rt->W, u);
+                                    dst = rt->peer_grecv[o] + (size_t)(rt->dst_off[o] + (u - rt->send_off[o])) * (K + 4);
+                                } else {
+                                    dst = A.gsum + (size_t)u * (K + 4);
+                                }
+                                *reinterpret_cast<float4*>(dst + t * 4) = gr;
+                                if (t == 0) *reinterpret_cast<float4*>(dst + K) = make_float4(dzr, 0.f, 0.f, 0.f);
+                            }
+                        } else if (f < dc) {
                             if (onc[g * dc + f]) {
                                 float* rec = slot + (size_t)g * SST + off;
                                 float4 w = *reinterpret_cast<const float4*>(rec + t * 4);
@@ -831,21 +867,26 @@ int fused_rows_grid(int B, int sm_count, bool side_stream_busy) {
     return std::max(1, std::min((B + FR_TS - 1) / FR_TS, sm_count - (side_stream_busy ? reserve : 0)));
 }
 
-template <int ES>
+template <int ES, bool RB>
 static cudaError_t fr_attr(int smem_bytes) {
-    return cudaFuncSetAttribute(fused_rows_kernel<16, 16, ES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    return cudaFuncSetAttribute(fused_rows_kernel<16, 16, ES, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 }
 cudaError_t fused_rows_set_attr(int smem_bytes) {
-    cudaError_t e = fr_attr<0>(smem_bytes);
-    if (!e) e = fr_attr<1>(smem_bytes);
-    if (!e) e = fr_attr<2>(smem_bytes);
+    cudaError_t e = fr_attr<0, false>(smem_bytes);
+    if (!e) e = fr_attr<1, false>(smem_bytes);
+    if (!e) e = fr_attr<2, false>(smem_bytes);
+    if (!e) e = fr_attr<0, true>(smem_bytes);
     return e;
 }
 cudaError_t fused_rows_launch(const FusedRowsArgs& A, int grid, size_t smem_bytes, cudaStream_t st) {
+    if (A.rowbuf_mode) {
+        fused_rows_kernel<16, 16, 0, true><<<grid, FR_THREADS, smem_bytes, st>>>(A);
+        return cudaGetLastError();
+    }
     switch (A.emb_slots) {
-        case 0: fused_rows_kernel<16, 16, 0><<<grid, FR_THREADS, smem_bytes, st>>>(A); break;
-        case 1: fused_rows_kernel<16, 16, 1><<<grid, FR_THREADS, smem_bytes, st>>>(A); break;
-        default: fused_rows_kernel<16, 16, 2><<<grid, FR_THREADS, smem_bytes, st>>>(A); break;
+        case 0: fused_rows_kernel<16, 16, 0, false><<<grid, FR_THREADS, smem_bytes, st>>>(A); break;
+        case 1: fused_rows_kernel<16, 16, 1, false><<<grid, FR_THREADS, smem_bytes, st>>>(A); break;
+        default: fused_rows_kernel<16, 16, 2, false><<<grid, FR_THREADS, smem_bytes, st>>>(A); break;
     }
     return cudaGetLastError();
 }

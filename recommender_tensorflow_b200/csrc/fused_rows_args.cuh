@@ -20,6 +20,9 @@ struct FusedRowsArgs {
     int step;                // the step being applied
     OptDev od_t, ol_t;       // this step's optimizer constants (alpha_t)
     float* numg_partial;     // [grid][dn * K + dn] gradients of numeric_embeddings / numeric linear weights
+    // row-buffer mode (row-sharded requester): records come from f.rowbuf[f.uidx[lookup]], gradient rows of the rows
+    // looked up once go to route (peer memory) or, route == nullptr, to gsum[unique row]
+    int rowbuf_mode; const uint8_t* once_lk; const PeerRoute* route; float* gsum;
 };
 
 __host__ __device__ inline int fr_sst(int dc, int dn, int K, int rs) {

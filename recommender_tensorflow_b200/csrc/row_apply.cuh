@@ -275,7 +275,8 @@ __global__ void __launch_bounds__(256, 2) row_gsum_kernel(const uint32_t* __rest
                                                           const uint32_t* __restrict__ svals, const uint32_t* __restrict__ row_start,
                                                           const uint32_t* __restrict__ row_piece0, const uint32_t* __restrict__ piece_start,
                                                           const SegCounts* __restrict__ cnt, SRC src, const float* __restrict__ piece_sum,
-                                                          const PeerRoute* __restrict__ rt) {
+                                                          const PeerRoute* __restrict__ rt, bool skip_single = false) {
+    // skip_single: rows with exactly one lookup were already stored by fused_rows_kernel (row-buffer mode)
     using C = RowGsumCfg<K, SRC>;
     constexpr int LPR = C::LPR, G = C::G, SLOT = C::SLOT, NST = C::NST, RW = K + 4, RW4 = RW / 4;
     extern __shared__ __align__(16) float ra_smem[];
@@ -298,6 +299,7 @@ __global__ void __launch_bounds__(256, 2) row_gsum_kernel(const uint32_t* __rest
     do {                                                                                                                 \
         m_v0 = 0xffffffffu; m_beg = 0; m_end = 0;                                                                        \
         if (it_meta < n_it && u_meta < U) { m_v0 = __ldg(uval + u_meta); m_beg = __ldg(row_start + u_meta); m_end = __ldg(row_start + u_meta + 1); } \
+        if (skip_single && m_end - m_beg == 1) m_end = m_beg;                                                            \
     } while (0)
 #define RG_ISSUE()                                                                                                       \
     do {                                                                                                                 \
@@ -414,19 +416,23 @@ __global__ void __launch_bounds__(256, 2) row_gsum_kernel(const uint32_t* __rest
                 g.x = fmaf(-gl, e.x, g.x); g.y = fmaf(-gl, e.y, g.y); g.z = fmaf(-gl, e.z, g.z); g.w = fmaf(-gl, e.w, g.w);
             }
         }
-        // the warp's rows -> one contiguous store into their owner's gradient segment
+        // the warp's rows -> one contiguous store into their owner's gradient segment (rows left out by skip_single are
+        // not touched: fused_rows_kernel stored them)
+        const unsigned rowmask = __ballot_sync(0xffffffffu, act && sub == 0);
         reinterpret_cast<float4*>(otile + grp * RW)[sub] = g;
         if (sub == 0) *reinterpret_cast<float4*>(otile + grp * RW + K) = make_float4(gl, 0.f, 0.f, 0.f);
         __syncwarp();
         const uint32_t u0 = u - grp;                              // first row of this warp's chunk
-        if (u0 < U) {
+        if (u0 < U && rowmask) {
             const uint32_t n_rows = min((uint32_t)G, U - u0);
             const int o0 = route_find(rt->send_off, rt->W, u0), o1 = route_find(rt->send_off, rt->W, u0 + n_rows - 1);
             if (o0 == o1) {
                 float4* dst = reinterpret_cast<float4*>(rt->peer_grecv[o0] + (size_t)(rt->dst_off[o0] + (u0 - rt->send_off[o0])) * RW);
-                for (uint32_t j = lane; j < n_rows * RW4; j += 32) dst[j] = reinterpret_cast<const float4*>(otile)[j];
+                for (uint32_t j = lane; j < n_rows * RW4; j += 32)
+                    if ((rowmask >> ((j / RW4) * LPR)) & 1u) dst[j] = reinterpret_cast<const float4*>(otile)[j];
             } else {
                 for (uint32_t q = 0; q < n_rows; ++q) {
+                    if (!((rowmask >> (q * LPR)) & 1u)) continue;
                     const uint32_t uu = u0 + q;
                     const int o = route_find(rt->send_off, rt->W, uu);
                     float4* dst = reinterpret_cast<float4*>(rt->peer_grecv[o] + (size_t)(rt->dst_off[o] + (uu - rt->send_off[o])) * RW);
