@@ -289,6 +289,64 @@ class DeepFMEngine:
                 self.set_tensor(g + "/" + sl, data[tf_name + "/" + t].reshape(n, -1), r0)
         self._check(self.lib.dfm_set_global_step(self.h, int(data["global_step"])))
 
+    # -- row-sharded handles (world > 1): one shard file per rank, merged on the host when an unsharded checkpoint is wanted
+    def _shard_tensor_names(self):
+        names = []
+        for v in self.variable_names():
+            names.append(v)
+            names += [v + "/" + sl for sl in self.slot_names(v)]
+        return names
+
+    def save_checkpoint_shard(self, path):
+        """This rank's rows of every table (+ slots), the replicated dense tower and global_step as one .npz (flushes the
+        deferred Adam).  Table tensors hold the LOCAL rows: global row g lives on rank g % world at index g // world."""
+        out = {"global_step": np.int64(self.global_step), "rank": np.int64(self.rank), "world": np.int64(self.world)}
+        for n in self._shard_tensor_names():
+            out[n] = self.get_tensor(n)
+        tmp = path + ".tmp.npz"
+        np.savez(tmp, **out)
+        os.replace(tmp, path)
+        return path
+
+    def load_checkpoint_shard(self, path):
+        data = np.load(path)
+        if int(data["rank"]) != self.rank or int(data["world"]) != self.world:
+            raise ValueError("shard %s belongs to rank %d of %d" % (path, int(data["rank"]), int(data["world"])))
+        for n in self._shard_tensor_names():
+            self.set_tensor(n, data[n])
+        self._check(self.lib.dfm_set_global_step(self.h, int(data["global_step"])))
+
+    def merge_checkpoint_shards(self, shard_paths, out_path, scheme="deep_fm"):
+        """Host-side gather of the rows: the shard files of every rank -> ONE checkpoint under the TF-1.12 variable names,
+        loadable by an unsharded engine of the same model (load_checkpoint).  `self` only supplies the variable map."""
+        shards = sorted((np.load(p) for p in shard_paths), key=lambda d: int(d["rank"]))
+        world = int(shards[0]["world"])
+        if [int(d["rank"]) for d in shards] != list(range(world)):
+            raise ValueError("need exactly one shard per rank 0..%d" % (world - 1))
+        R = int(self.row_offsets[-1])
+
+        def full(name):
+            base = name.split("/")[0]
+            if base not in ("emb", "lin"):
+                return shards[0][name]                      # replicated
+            width = shards[0][name].shape[1]
+            g = np.empty((R, width), dtype=np.float32)
+            for r, d in enumerate(shards):
+                g[r::world] = d[name][:len(range(r, R, world))]
+            return g
+        out = {"global_step": np.int64(int(shards[0]["global_step"]))}
+        for tf_name, (gname, r0, n, shape) in self.tf_variable_map(scheme).items():
+            out[tf_name] = full(gname)[r0:r0 + n].reshape(shape)
+            grp = self.opt_linear if gname in ("lin", "num_lin", "bias") else self.opt_deep
+            for sl in self.slot_names(gname):
+                t = self._SLOT_TF[sl]
+                t = t[grp["name"]] if isinstance(t, dict) else t
+                out[tf_name + "/" + t] = full(gname + "/" + sl)[r0:r0 + n].reshape(shape)
+        tmp = out_path + ".tmp.npz"
+        np.savez(tmp, **out)
+        os.replace(tmp, out_path)
+        return out_path
+
     def init_random(self, seed=0):
         self._check(self.lib.dfm_init_random(self.h, seed))
 

@@ -214,3 +214,58 @@ def test_init_random_is_keyed_on_global_rows():
         assert np.array_equal(e.get_tensor("emb"), full[r::world])
         for n in ("W0", "W1", "Wo", "num_emb"):
             assert np.array_equal(e.get_tensor(n), ref.get_tensor(n)), n
+
+
+def test_sharded_checkpoint_shards_resume_and_merge(tmp_path):
+    """A row-sharded run checkpoints one shard file per rank; fresh sharded engines resume from them bit for bit, and the
+    host-side merge of the shards is a TF-named checkpoint an unsharded engine loads (same logits as the sharded model)."""
+    cats, nums = synth.criteo_columns(700, n_cat=26, n_num=13)
+    kw = dict(embedding_size=16, hidden_units=(16, 16))
+    world, per = 2, 256
+    engs = [DeepFMEngine(cats, nums, max_batch=per, rank=r, world=world, **kw) for r in range(world)]
+    for e in engs:
+        e.init_random(9)
+    vc = VirtualCluster(engs, p2p=True)
+    rng = np.random.default_rng(90)
+
+    def split(feats, y):
+        pbs = []
+        for r, e in enumerate(engs):
+            fr = {}
+            for k, v in feats.items():
+                if isinstance(v, tuple):
+                    data, offs = v
+                    o = offs[r * per:(r + 1) * per + 1]
+                    fr[k] = (data[o[0]:o[-1]].copy(), (o - o[0]).astype(np.int32))
+                else:
+                    fr[k] = v[r * per:(r + 1) * per]
+            pbs.append((fr, y[r * per:(r + 1) * per]))
+        return pbs
+    batches = [synth.criteo_batch(world * per, rng, key_space=5000) for _ in range(4)]
+    for feats, y in batches[:3]:
+        vc.train_step([e.pack(f, yy, device=True) for e, (f, yy) in zip(engs, split(feats, y))])
+    paths = [e.save_checkpoint_shard(str(tmp_path / ("model.ckpt-3.shard-%d-of-%d.npz" % (r, world)))) for r, e in enumerate(engs)]
+    sums = [e.state_checksum() for e in engs]
+    loss_next = vc.train_step([e.pack(f, yy, device=True) for e, (f, yy) in zip(engs, split(*batches[3]))])
+    # resume: fresh sharded engines from the shard files
+    engs2 = [DeepFMEngine(cats, nums, max_batch=per, rank=r, world=world, **kw) for r in range(world)]
+    for e, p in zip(engs2, paths):
+        e.load_checkpoint_shard(p)
+    assert [e.state_checksum() for e in engs2] == sums and all(e.global_step == 3 for e in engs2)
+    vc2 = VirtualCluster(engs2, p2p=True)
+    loss2 = vc2.train_step([e.pack(f, yy, device=True) for e, (f, yy) in zip(engs2, split(*batches[3]))])
+    assert loss2 == loss_next
+    with pytest.raises(ValueError):
+        engs2[0].load_checkpoint_shard(paths[1])
+    # merge: one unsharded checkpoint under TF names
+    engs3 = [DeepFMEngine(cats, nums, max_batch=per, rank=r, world=world, **kw) for r in range(world)]
+    for e, p in zip(engs3, paths):
+        e.load_checkpoint_shard(p)
+    merged = engs3[0].merge_checkpoint_shards(paths, str(tmp_path / "model.ckpt-3.npz"))
+    single = DeepFMEngine(cats, nums, max_batch=world * per, **kw)
+    single.load_checkpoint(merged)
+    assert single.global_step == 3
+    feats, y = batches[3]
+    z_single = single.predict_logits(feats)
+    z_sharded = VirtualCluster(engs3, p2p=True).predict_logits([e.pack(f, None, device=True) for e, (f, _) in zip(engs3, split(feats, y))])
+    assert np.array_equal(z_single, np.asarray(z_sharded).reshape(-1))
