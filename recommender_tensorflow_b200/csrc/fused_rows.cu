@@ -30,7 +30,9 @@
 // sqrt / reciprocal (relative error <= 2^-21 on a displacement of ~lr, i.e. ~1e-10 on w; the IEEE sequence cost 20 % of the
 // kernel's instructions, profiles/r02u).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "fused_rows_args.cuh"
 #include "tc_gemm.cuh"
@@ -56,35 +58,36 @@ __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;"
 constexpr int FR_P3W = 8;                      // warps that run the small upper part of the tower (P3)
 __device__ __forceinline__ void bar_p3() { asm volatile("bar.sync 2, %0;" ::"n"(FR_P3W * 32) : "memory"); }
 
-// wait with back-off (producer warps: a slot frees once per tile, thousands of cycles apart; a hot try_wait loop would
-// take issue slots from the consumer warps of the same scheduler - 16 % of the kernel's instructions in profiles/r02aj)
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = tc::smem_u32(bar);
-    uint32_t done = 0;
-    for (uint32_t spins = 0; !done; ++spins) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (!done) __nanosleep(200);
-        if (spins > (1u << 24)) __trap();
-    }
-}
+// "slot s may be refilled": one hardware barrier per slot (ids 3 ..), consumers arrive without waiting, the producer
+// warps wait in bar.sync and issue nothing meanwhile (an mbarrier try_wait loop, even with nanosleep back-off, was 23 %
+// of the kernel's issued instructions in profiles/r02au).  The rounds of one barrier cannot mix: the consumers' arrival
+// for tile it + NSLOT needs the producers' copies of that tile, which are issued after their wait for tile it returned.
+constexpr int FR_BAR_SLOT = 3;
+__device__ __forceinline__ void slot_free_arrive(int s) { asm volatile("bar.arrive %0, %1;" ::"r"(FR_BAR_SLOT + s), "n"(FR_THREADS) : "memory"); }
+__device__ __forceinline__ void slot_free_wait(int s) { asm volatile("bar.sync %0, %1;" ::"r"(FR_BAR_SLOT + s), "n"(FR_THREADS) : "memory"); }
 
+// non-blocking: has the phase with this parity completed?  (acquire: the bulk copies it counted are visible afterwards)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(tc::smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
 // D = A(16x8, row) * B(8x8, col) + C on tf32 operands held as fp32 bit patterns whose low 13 bits are zero
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2], const float (&c)[4]) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %11, %12, %13};"
                  : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
 }
-__device__ __forceinline__ uint32_t cvt_tf32(float x) {        // round to nearest, low 13 bits zero
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// fp32 -> tf32 hi / lo operands of the 3xTF32 products.  cvt.rna.tf32.f32 is emulated on sm_100a (add 0x1000, infinity test,
+// select, mask: 9 instructions per split, 14 % of this kernel's instruction stream in profiles/r02au).  mma.sync reads only
+// the upper 19 bits of a tf32 operand, so "bits + 0x1000" IS the round-to-nearest (ties away) operand; the mask is only
+// needed where hi is used as a number, i.e. in the subtraction.  Same values as cvt.rna for every finite input below 2^127.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = cvt_tf32(x);
-    lo = cvt_tf32(x - __uint_as_float(hi));
+    hi = __float_as_uint(x) + 0x1000u;
+    lo = __float_as_uint(x - __uint_as_float(hi & 0xffffe000u)) + 0x1000u;
 }
 // sparse optimizer step of one element inside the kernel (see the note on the Adam displacement above)
 __device__ __forceinline__ void apply_elem(float& w, float& s1, float& s2, float g, const OptDev& o) {
@@ -128,7 +131,8 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
     uint32_t* rowix = reinterpret_cast<uint32_t*>(slots + (size_t)FR_NSLOT * FR_TS * SST);   // [NSLOT][TS*dc] global row (~0: no row)
     uint32_t* once = rowix + FR_NSLOT * nrows;                   // [NSLOT][TS*dc] 1: this kernel applies the row's gradient
     float* xsb = reinterpret_cast<float*>(once + FR_NSLOT * nrows);              // [NSLOT][TS][dn]
-    float* part = xsb + FR_NSLOT * FR_TS * (dn > 0 ? dn : 1);    // [CW][TS][H1] layer-0 partials; later the warps' dE staging
+    float* ysb = xsb + FR_NSLOT * FR_TS * (dn > 0 ? dn : 1);     // [NSLOT][TS] labels (a global load would sit on P3's critical path)
+    float* part = ysb + FR_NSLOT * FR_TS;                        // [CW][TS][H1] layer-0 partials; later the warps' dE staging
     part += (4 - ((size_t)(part - smem) & 3)) & 3;
     float* p1 = part + FR_CW * FR_TS * H1;                       // [CW][2K + 4] FM / linear partials of P1
     float* dh1s = p1 + FR_CW * (2 * K + 4);                      // [TS][H1]
@@ -143,13 +147,12 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
     const int n_gnum = dn * K + dn;
     uint64_t* bars = reinterpret_cast<uint64_t*>(gnum + n_gnum + ((size_t)(gnum - smem + n_gnum) & 1));
     uint64_t* full = bars;                                       // [NSLOT] records landed
-    uint64_t* empty = bars + FR_NSLOT;                           // [NSLOT] slot may be refilled
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int train = a.train;
     const int ntiles = (a.B + FR_TS - 1) / FR_TS;
     if (tid == 0) {
-        for (int s = 0; s < FR_NSLOT; ++s) { tc::mbar_init(&full[s], FR_PW); tc::mbar_init(&empty[s], NT); }
+        for (int s = 0; s < FR_NSLOT; ++s) tc::mbar_init(&full[s], FR_PW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < D * H1; i += FR_THREADS) W0s[(i / H1) * FR_W0S + (i % H1)] = a.dw[m.off_W[0] + i];
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int s = it % FR_NSLOT;
-            if (it >= FR_NSLOT) mbar_wait_backoff(&empty[s], ((it / FR_NSLOT) & 1) ^ 1);
+            if (it >= FR_NSLOT) slot_free_wait(s);
             float* slot = slots + (size_t)s * FR_TS * SST;
             uint32_t row[FR_NR], cw[FR_NR];
 #pragma unroll
@@ -225,6 +228,10 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                 const int j = q / FR_TS, sl = q - j * FR_TS, b = tile * FR_TS + sl;
                 xsb[(s * FR_TS + sl) * dn + j] = b < a.B ? __ldg(a.bp.num[j] + b) : 0.f;
             }
+            if (pw == FR_PW - 1 && lane < FR_TS) {
+                const int b = tile * FR_TS + lane;
+                ysb[s * FR_TS + lane] = (train && b < a.B) ? __ldg(a.labels + b) : 0.f;
+            }
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
             __syncwarp();                                   // this warp's meta data is written before its arrival ...
@@ -241,6 +248,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
             }
             load_ids(tile + gridDim.x);                     // in flight while the consumers work
         }
+        for (int q = max(it - FR_NSLOT, 0); q < it; ++q) slot_free_wait(q % FR_NSLOT);     // pair the consumers' last arrivals
         return;
     }
 
@@ -271,9 +279,10 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
         const uint32_t* rix = rowix + s * nrows;
         const uint32_t* onc = once + s * nrows;
         const float* xs = xsb + (size_t)s * FR_TS * dn;
+        const float* ys = ysb + s * FR_TS;
         tc::mbar_wait(&full[s], (it / FR_NSLOT) & 1);
         // ------------------------------------------------------------------ P1: two warps per sample: replay in place, FM / linear partial sums
-        {
+        if (!(A.ablate & 64)) {
             const int sl = warp >> 1, half = warp & 1, sub = t;
             float* srow = slot + (size_t)sl * SST;
             float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), qv = sv;
@@ -284,7 +293,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                     float* rec = srow + f * RS;
                     float4 e = *reinterpret_cast<const float4*>(rec + sub * 4);
                     float4 lr = *reinterpret_cast<const float4*>(rec + K);
-                    if (a.rr.upto >= 0 && __float_as_int(lr.w) < a.rr.upto) {
+                    if (a.rr.upto >= 0 && __float_as_int(lr.w) < a.rr.upto && !(A.ablate & 1)) {
                         float4 mm = make_float4(0.f, 0.f, 0.f, 0.f), vv = mm;
                         if (ES >= 1) mm = *reinterpret_cast<const float4*>(rec + K + 4 + sub * 4);
                         if (ES >= 2) vv = *reinterpret_cast<const float4*>(rec + 2 * K + 4 + sub * 4);
@@ -330,7 +339,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
         // ------------------------------------------------------------------ P2: H^T = W0^T E^T, k-steps round-robin over the warps
         {
             float cm[4] = {0.f, 0.f, 0.f, 0.f}, cx[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int ks = warp; ks < D / 8; ks += FR_CW) {
+            for (int ks = warp; ks < ((A.ablate & 2) ? 0 : D / 8); ks += FR_CW) {
                 const int col0 = ks * 8, f = col0 / K;
                 const int off = f < dc ? f * RS + (col0 - f * K) : dc * RS + (col0 - dc * K);
                 const float* w0 = W0s + (size_t)(col0 + t) * FR_W0S + g;
@@ -354,7 +363,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
         // ------------------------------------------------------------------ P3 (warps 0..7): rest of the tower, head, loss, backward to dh1'
         const bool p3_fast = m.L == 2 && m.H[1] == 16;       // the reference default tower [16, 16]: a sample lives in one half-warp
         if (p3_fast) {
-            if (warp < 4) {
+            if (warp < 4 && !(A.ablate & 4)) {
                 // thread = (sample sl, unit o); every cross-thread dependence stays inside a half-warp: no block barriers
                 const int sl = tid >> 4, o = tid & 15, b = b0 + sl;
                 const unsigned hm = 0xffffffffu;
@@ -397,7 +406,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                 z += zlf;
                 float gz = 0.f, lterm = 0.f;
                 if (b < a.B && train) {
-                    const float y = a.labels[b];
+                    const float y = ys[sl];
                     lterm = fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));
                     gz = (1.f / (1.f + expf(-z)) - y) * a.scale;
                 }
@@ -423,7 +432,42 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                     if (b < a.B) a.dh1_out[(size_t)b * H1 + o] = v;
                 }
             }
-        } else if (warp < FR_P3W) {
+        }
+        // The tower above layer 0 is small and serial (4 or 8 warps, ~2.8 K cycles per tile); the other consumer warps use
+        // that window to replay the deferred Adam of the NEXT tile's records in place, if they have landed.  A replayed
+        // record carries last_step = upto, so P1 of that tile skips it: same arithmetic on the same values, only earlier.
+        {
+            const int p3w = p3_fast ? 4 : FR_P3W;
+            const int nt = tile + gridDim.x;
+            if (!RB && warp >= p3w && nt < ntiles && a.rr.upto >= 0 && !(A.ablate & 1)) {
+                const int s1 = (it + 1) % FR_NSLOT;
+                uint32_t ok = lane == 0 ? (mbar_test(&full[s1], ((it + 1) / FR_NSLOT) & 1) ? 1u : 0u) : 0u;
+                ok = __shfl_sync(0xffffffffu, ok, 0);
+                if (ok) {
+                    float* slot1 = slots + (size_t)s1 * FR_TS * SST;
+                    const uint32_t* rix1 = rowix + s1 * nrows;
+                    for (int r = (warp - p3w) * 8 + g; r < nrows; r += (FR_CW - p3w) * 8) {
+                        if (rix1[r] != 0xffffffffu) {
+                            const int sl = r / dc, f = r - sl * dc;
+                            float* rec = slot1 + (size_t)sl * SST + f * RS;
+                            float4 lr = *reinterpret_cast<const float4*>(rec + K);
+                            if (__float_as_int(lr.w) < a.rr.upto) {
+                                float4 e = *reinterpret_cast<const float4*>(rec + t * 4);
+                                float4 mm = make_float4(0.f, 0.f, 0.f, 0.f), vv = mm;
+                                if (ES >= 1) mm = *reinterpret_cast<const float4*>(rec + K + 4 + t * 4);
+                                if (ES >= 2) vv = *reinterpret_cast<const float4*>(rec + 2 * K + 4 + t * 4);
+                                replay_row(e, mm, vv, lr, t == 0, a.rr, rs, a.od, a.ol);
+                                *reinterpret_cast<float4*>(rec + t * 4) = e;
+                                if (ES >= 1) *reinterpret_cast<float4*>(rec + K + 4 + t * 4) = mm;
+                                if (ES >= 2) *reinterpret_cast<float4*>(rec + 2 * K + 4 + t * 4) = vv;
+                                if (t == 0) *reinterpret_cast<float4*>(rec + K) = lr;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (!p3_fast && warp < FR_P3W) {
             constexpr int PT = FR_P3W * 32;
             if (tid < FR_TS * H1) {
                 const int sl = tid / H1, o = tid - sl * H1;
@@ -478,7 +522,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                     a.logits[b] = z;
                     if (a.logits_out) a.logits_out[b] = z;
                     if (train) {
-                        const float y = a.labels[b];
+                        const float y = ys[sl];
                         lterm = fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));
                         gz = (1.f / (1.f + expf(-z)) - y) * a.scale;
                         a.dz_out[b] = gz;
@@ -599,8 +643,8 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
             const float dzr = dzs[g];                         // row-wise view of the update: lane = (sample g, float4 slice t)
 #pragma unroll
             for (int i = 0; i < FR_NF; ++i) {
-                const int f = warp + FR_CW * i;
-                if (f < d) {                                  // warp-uniform
+                const int f = A.p4f[warp * FR_NF + i];        // dW0 fields of this warp (fixed: register accumulators)
+                if (f < d && !(A.ablate & 8)) {               // warp-uniform
                     const int off = f < dc ? f * RS : dc * RS + (f - dc) * K;
                     // dW0[f*K.., :] += E_f^T dh1'
                     {
@@ -620,11 +664,20 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                             for (int q = 0; q < 4; ++q) wacc[i][n][q] += dm[q] + dx[q];
                         }
                     }
+                }
+            }
+            // dE + update tasks are dealt separately from the dW0 fields so that the warps finish together (39 fields over
+            // 16 warps as "field f -> warp f mod 16" left the three-field warps 23 % over the mean: fr_balance)
+#pragma unroll
+            for (int i = 0; i < FR_N5; ++i) {
+                const int f = A.p5f[warp * FR_N5 + i];
+                if (f < d) {                                  // warp-uniform
+                    const int off = f < dc ? f * RS : dc * RS + (f - dc) * K;
                     if (f >= dc || inline_apply) {
                         // dE_f^T = W0_f dh1'^T  (fragment: k = g, g + 8; samples 2t, 2t + 1)
                         float cm[4] = {0.f, 0.f, 0.f, 0.f}, cx[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                        for (int kk = 0; kk < 2; ++kk) {
+                        for (int kk = 0; kk < ((A.ablate & 16) ? 0 : 2); ++kk) {
                             const float* w0 = W0s + (size_t)(f * K + g) * FR_W0S + kk * 8 + t;
                             uint32_t ah[4], al[4];
                             split_tf32(w0[0], ah[0], al[0]);
@@ -666,7 +719,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                                 if (t == 0) *reinterpret_cast<float4*>(dst + K) = make_float4(dzr, 0.f, 0.f, 0.f);
                             }
                         } else if (f < dc) {
-                            if (onc[g * dc + f]) {
+                            if (onc[g * dc + f] && !(A.ablate & 32)) {
                                 float* rec = slot + (size_t)g * SST + off;
                                 float4 w = *reinterpret_cast<const float4*>(rec + t * 4);
                                 float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
@@ -677,10 +730,13 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                                     gr.x = fmaf(dzr, sv.x - w.x, gr.x); gr.y = fmaf(dzr, sv.y - w.y, gr.y);
                                     gr.z = fmaf(dzr, sv.z - w.z, gr.z); gr.w = fmaf(dzr, sv.w - w.w, gr.w);
                                 }
+                                if (!(A.ablate & 256)) {
                                 apply_elem(w.x, s1.x, s2.x, gr.x, A.od_t); apply_elem(w.y, s1.y, s2.y, gr.y, A.od_t);
                                 apply_elem(w.z, s1.z, s2.z, gr.z, A.od_t); apply_elem(w.w, s1.w, s2.w, gr.w, A.od_t);
+                                }
                                 // the record goes straight back to the table (4 lanes = 64 contiguous bytes per store)
                                 float* grec = a.tb.rec + (size_t)rix[g * dc + f] * a.tb.stride;
+                                if (A.ablate & 128) grec = gst;
                                 *reinterpret_cast<float4*>(grec + t * 4) = w;
                                 if (ES >= 1) *reinterpret_cast<float4*>(grec + K + 4 + t * 4) = s1;
                                 if (ES >= 2) *reinterpret_cast<float4*>(grec + 2 * K + 4 + t * 4) = s2;
@@ -722,7 +778,9 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
             }
         }
         // this thread is done with the slot (the scratch of the tile is protected by the barrier after the next tile's P1)
-        tc::mbar_arrive(&empty[s]);
+        __syncwarp();
+        fence_async_smem();                                   // this thread's writes to the slot precede the next bulk copies into it
+        slot_free_arrive(s);
     }
     if (train) {
         const int acc_tid = (m.L == 2 && m.H[1] == 16) ? 128 + 48 : FR_TS * H1;   // the thread that accumulated the loss / dz sums
@@ -733,7 +791,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
         float* wp = a.w0_partial + (size_t)blockIdx.x * D * H1;
 #pragma unroll
         for (int i = 0; i < FR_NF; ++i) {
-            const int f = warp + FR_CW * i;
+            const int f = A.p4f[warp * FR_NF + i];
             if (f < d) {
 #pragma unroll
                 for (int n = 0; n < 2; ++n) {
@@ -850,10 +908,36 @@ cudaError_t fused_rows_compact(const uint32_t* keys_in, const uint32_t* vals_in,
 bool fused_rows_supported(int K, int H1, int dc, int dn) {
     return K == 16 && H1 == 16 && dc > 0 && FR_TS * dc <= 32 * FR_NR * FR_PW && dc + dn <= FR_CW * FR_NF;
 }
+// Deals the per-field tasks of P4 / P5 to the consumer warps: longest task first onto the least loaded warp that still has
+// a free place (at most FR_NF dW0 fields - register accumulators - and FR_N5 dE tasks per warp).  Costs are warp
+// instructions per tile and task, counted on the SASS (DFM_FR_COST="dE+update,dE numeric,dW0" overrides them).
+void fr_balance(FusedRowsArgs& A, int dc, int dn, bool cat_tasks) {
+    static int cost[3] = {0, 0, 0};
+    if (!cost[0]) {
+        cost[0] = 150; cost[1] = 100; cost[2] = 45;
+        if (const char* e = getenv("DFM_FR_COST")) sscanf(e, "%d,%d,%d", &cost[0], &cost[1], &cost[2]);
+    }
+    A.ablate = getenv("DFM_FR_ABLATE") ? atoi(getenv("DFM_FR_ABLATE")) : 0;
+    const int c_cat = A.rowbuf_mode ? (cost[0] * 2) / 3 : cost[0];
+    int load[FR_CW] = {}, n4[FR_CW] = {}, n5[FR_CW] = {};
+    memset(A.p4f, 0xff, sizeof(A.p4f));
+    memset(A.p5f, 0xff, sizeof(A.p5f));
+    auto place = [&](int f, int c, int* cnt, int cap, uint8_t* tab, int per) {
+        int best = -1;
+        for (int w = 0; w < FR_CW; ++w)
+            if (cnt[w] < cap && (best < 0 || load[w] < load[best])) best = w;
+        tab[best * per + cnt[best]++] = (uint8_t)f;
+        load[best] += c;
+    };
+    if (cat_tasks)
+        for (int f = 0; f < dc; ++f) place(f, c_cat, n5, FR_N5, A.p5f, FR_N5);
+    for (int f = dc; f < dc + dn; ++f) place(f, cost[1], n5, FR_N5, A.p5f, FR_N5);
+    for (int f = 0; f < dc + dn; ++f) place(f, cost[2], n4, FR_NF, A.p4f, FR_NF);
+}
 size_t fused_rows_smem_bytes(const SmallMlpDesc& m, int K, int dc, int dn, int rs) {
     size_t f = (size_t)m.D * FR_W0S + 2 * (size_t)m.up_count + 8;
     f += (size_t)FR_NSLOT * FR_TS * fr_sst(dc, dn, K, rs);
-    f += (size_t)FR_NSLOT * (2 * FR_TS * dc + FR_TS * (dn > 0 ? dn : 1) + 8);
+    f += (size_t)FR_NSLOT * (2 * FR_TS * dc + FR_TS * (dn > 0 ? dn : 1) + FR_TS + 8);
     f += (size_t)FR_CW * FR_TS * m.H[0] + (size_t)FR_CW * (2 * K + 4) + (size_t)FR_TS * m.H[0] + 2 * (size_t)FR_TS * m.act_stride + 3 * FR_TS +
          (size_t)FR_TS * K + (size_t)(dn * K + dn) + 16;
     return f * 4 + 2 * FR_NSLOT * 8 + 64;

@@ -9,7 +9,8 @@ constexpr int FR_THREADS = (FR_CW + FR_PW) * 32;
 constexpr int FR_NSLOT = 3;                    // tile slots: loading / computing / draining its stores
 constexpr int FR_W0S = 20;                     // floats per W0 row in shared memory (H1 = 16 padded: conflict-free A fragments)
 constexpr int FR_NR = 2;                       // rows per producer lane and tile (FR_TS * dc <= 32 * FR_NR * FR_PW)
-constexpr int FR_NF = 3;                       // fields per consumer warp (d <= 48)
+constexpr int FR_NF = 3;                       // dW0 fields per consumer warp (d <= 48)
+constexpr int FR_N5 = 4;                       // dE / update tasks per consumer warp
 
 struct FusedRowsArgs {
     FusedArgs f;
@@ -23,6 +24,8 @@ struct FusedRowsArgs {
     // row-buffer mode (row-sharded requester): records come from f.rowbuf[f.uidx[lookup]], gradient rows of the rows
     // looked up once go to route (peer memory) or, route == nullptr, to gsum[unique row]
     int rowbuf_mode; const uint8_t* once_lk; const PeerRoute* route; float* gsum;
+    int ablate;              // DFM_FR_ABLATE (timing experiments only, results are wrong): 1 no replay, 2 no P2, 4 no P3, 8 no P4, 16 no dE product, 32 no update / stores, 64 no P1
+    uint8_t p4f[FR_CW * FR_NF], p5f[FR_CW * FR_N5];    // fields of each consumer warp's P4 / P5 tasks (0xff: none), fr_balance
 };
 
 __host__ __device__ inline int fr_sst(int dc, int dn, int K, int rs) {
@@ -37,5 +40,6 @@ int fused_rows_grid(int B, int sm_count, bool side_stream_busy);                
 // once" go through the sort / ordered reduction.  n_out[0] = pairs kept, n_out[1] = once-only lookups.  scratch: n / 2048 + 2 words.
 cudaError_t fused_rows_compact(const uint32_t* keys_in, const uint32_t* vals_in, int64_t n, uint32_t R, const uint32_t* claim, uint32_t claim_mask,
                                uint32_t* keys_out, uint32_t* vals_out, uint32_t* scratch, uint32_t* n_out, cudaStream_t st, int64_t* launches);
+void fr_balance(FusedRowsArgs& A, int dc, int dn, bool cat_tasks);   // cat_tasks: the kernel applies / forwards the once-only rows' gradients
 cudaError_t fused_rows_set_attr(int smem_bytes);
 cudaError_t fused_rows_launch(const FusedRowsArgs& A, int grid, size_t smem_bytes, cudaStream_t st);
