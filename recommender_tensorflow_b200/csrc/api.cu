@@ -406,6 +406,7 @@ static int create_impl(const dfm_config* cfg, dfm_handle* h) {
             default: FAIL(DFM_ERR_INVALID_ARG, "unknown column kind");
         }
         d.nb = nb;
+        d.nb_rcp = nb >= 2 ? (uint64_t)(((unsigned __int128)1 << 64) / nb) : 0;
         h->cols.push_back(d);
         h->col_names.push_back(c.name ? c.name : "");
         if (R > 0xffffffffull) FAIL(DFM_ERR_UNSUPPORTED, "more than 2^32 table rows on one device");

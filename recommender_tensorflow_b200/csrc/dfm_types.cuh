@@ -7,6 +7,7 @@
 struct ColDev {
     int32_t  kind, dtype;
     uint64_t nb;            // bucket count used for the modulo (hash) / range check (identity)
+    uint64_t nb_rcp;        // floor(2^64 / nb) (nb >= 2; 0: use the plain modulo): fingerprint % nb without a 64-bit division
     int32_t  bnd_off, bnd_cnt;
     int32_t  voc_off, voc_cnt, num_oov, width;   // width: value slots per sample (multivalent column), >= 1
 };

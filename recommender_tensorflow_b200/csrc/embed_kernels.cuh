@@ -206,6 +206,14 @@ __device__ __forceinline__ void load_row_current(const Table& tb, size_t row, in
 // =============================================================================================
 // K1: feature-column transforms -> ids [B, dc] + sort keys (global row index) + payload
 // =============================================================================================
+// h % nb by Barrett reduction: q = floor(h * floor(2^64 / nb) / 2^64) is the quotient or one less (h / nb - h rcp / 2^64 < 1),
+// so one conditional subtraction makes the remainder exact; the generic 64-bit modulo is a ~150-instruction routine and
+// was a third of transform_kernel's instruction stream on the Criteo-shaped batch (26 hashed columns).
+__device__ __forceinline__ uint64_t mod_buckets(uint64_t h, const ColDev& c) {
+    if (c.nb_rcp == 0) return h % c.nb;
+    uint64_t r = h - __umul64hi(h, c.nb_rcp) * c.nb;
+    return r >= c.nb ? r - c.nb : r;
+}
 __device__ __forceinline__ int32_t transform_one(const BatchPtrs& bp, const ColDev& c, int f, int b,
                                                  const float* __restrict__ bounds,
                                                  const uint8_t* __restrict__ voc_bytes,
@@ -218,13 +226,13 @@ __device__ __forceinline__ int32_t transform_one(const BatchPtrs& bp, const ColD
                 int len = e - s;
                 if (len <= 0) return -1;
                 uint64_t h = fh::fp64_mem(reinterpret_cast<const uint8_t*>(bp.cat[f]) + s, len);
-                return (int32_t)(h % c.nb);
+                return (int32_t)mod_buckets(h, c);
             } else {
                 int32_t v = reinterpret_cast<const int32_t*>(bp.cat[f])[b];
                 if (v == -1) return -1;
                 uint64_t lo, hi;
                 int len = fh::itoa16(v, lo, hi);
-                return (int32_t)(fh::fp64_short(lo, hi, len) % c.nb);
+                return (int32_t)mod_buckets(fh::fp64_short(lo, hi, len), c);
             }
         }
         case DFM_COL_BUCKETIZED: {
@@ -290,23 +298,43 @@ __global__ void __launch_bounds__(256) transform_kernel(BatchPtrs bp, const ColD
     __syncthreads();
     const int nloc = nb * n_slots;
     const int64_t g0 = (int64_t)b0 * n_slots;
-    for (int w = threadIdx.x; w < nloc; w += blockDim.x) {
-        int32_t id = sid[w];
-        int slot = w % n_slots;
-        ids[g0 + w] = id;
-        if (claim && id >= 0) claim_mark(claim, claim_mask, row_off[slot_col ? slot_col[slot] : slot] + (uint32_t)id);
-        if (keys) {
-            // key_slot: only the listed slots go through the sort (tiny-vocabulary columns are reduced densely, see
-            // tiny_reduce_kernel); their pairs are packed [sample][key slot], the payload keeps the full-slot numbering
-            int64_t at = g0 + w;
-            if (key_slot) {
-                const int ks = key_slot[slot];
-                at = ks >= 0 ? (int64_t)(b0 + w / n_slots) * n_key_slots + ks : -1;
+    // four items per thread and round: the claim marks are L2 atomics whose old value decides about a second one, and a
+    // warp stalls at the first use of a pending result, so the first atomics of a round are all issued before any is tested
+    for (int w0 = threadIdx.x; w0 < nloc; w0 += 4 * blockDim.x) {
+        uint32_t crow[4], cold[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int w = w0 + u * blockDim.x;
+            crow[u] = 0xffffffffu; cold[u] = 0;
+            if (w < nloc) {
+                int32_t id = sid[w];
+                int slot = w % n_slots;
+                ids[g0 + w] = id;
+                const uint32_t grow = id >= 0 ? row_off[slot_col ? slot_col[slot] : slot] + (uint32_t)id : R;
+                if (claim && id >= 0) {
+                    const uint32_t s = grow & claim_mask;
+                    crow[u] = s;
+                    cold[u] = atomicOr(claim + (s >> 4), 1u << ((s & 15u) * 2u));
+                }
+                if (keys) {
+                    // key_slot: only the listed slots go through the sort (tiny-vocabulary columns are reduced densely, see
+                    // tiny_reduce_kernel); their pairs are packed [sample][key slot], the payload keeps the full-slot numbering
+                    int64_t at = g0 + w;
+                    if (key_slot) {
+                        const int ks = key_slot[slot];
+                        at = ks >= 0 ? (int64_t)(b0 + w / n_slots) * n_key_slots + ks : -1;
+                    }
+                    if (at >= 0) {
+                        keys[at] = grow;
+                        vals[at] = payload_pack((uint32_t)(b0 + w / n_slots), (uint32_t)slot);
+                    }
+                }
             }
-            if (at >= 0) {
-                keys[at] = id >= 0 ? row_off[slot_col ? slot_col[slot] : slot] + (uint32_t)id : R;
-                vals[at] = payload_pack((uint32_t)(b0 + w / n_slots), (uint32_t)slot);
-            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t sh = (crow[u] & 15u) * 2u;
+            if (crow[u] != 0xffffffffu && ((cold[u] >> sh) & 1u)) atomicOr(claim + (crow[u] >> 4), 2u << sh);
         }
     }
 }

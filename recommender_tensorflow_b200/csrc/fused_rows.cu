@@ -283,12 +283,12 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
         tc::mbar_wait(&full[s], (it / FR_NSLOT) & 1);
         // ------------------------------------------------------------------ P1: two warps per sample: replay in place, FM / linear partial sums
         if (!(A.ablate & 64)) {
-            const int sl = warp >> 1, half = warp & 1, sub = t;
+            const int sl = warp / FR_WPS, half = warp - sl * FR_WPS, sub = t;     // FR_WPS warps share a sample: fields half*8+g, +8*FR_WPS, ..
             float* srow = slot + (size_t)sl * SST;
             float4 sv = make_float4(0.f, 0.f, 0.f, 0.f), qv = sv;
             float lin = 0.f;
 #pragma unroll 2
-            for (int f = half * 8 + g; f < dc; f += 16) {
+            for (int f = half * 8 + g; f < dc; f += 8 * FR_WPS) {
                 if (rix[sl * dc + f] != 0xffffffffu) {
                     float* rec = srow + f * RS;
                     float4 e = *reinterpret_cast<const float4*>(rec + sub * 4);
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                     if (sub == 0) lin += lr.x;
                 }
             }
-            for (int j = half * 8 + g; j < dn; j += 16) {
+            for (int j = half * 8 + g; j < dn; j += 8 * FR_WPS) {
                 const float x = xs[sl * dn + j];
                 float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (num_emb) {
@@ -370,16 +370,17 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                 float* ar = acts + sl * m.act_stride;
                 float* dr = dacts + sl * m.act_stride;
                 // field sums of the two half-sample warps -> s (kept for the FM gradient), FM + linear logit
-                const float* pa = p1 + (2 * sl) * (2 * K + 4);
-                const float* pb = pa + (2 * K + 4);
-                const float sk = pa[o] + pb[o];
+                const float* pa = p1 + (FR_WPS * sl) * (2 * K + 4);
+                float sk = pa[o], qk = pa[K + o], lk = pa[2 * K];
+#pragma unroll
+                for (int w = 1; w < FR_WPS; ++w) { sk += pa[w * (2 * K + 4) + o]; qk += pa[w * (2 * K + 4) + K + o]; lk += pa[w * (2 * K + 4) + 2 * K]; }
                 ss[sl * K + o] = sk;
                 if (b < a.B && a.s_out) a.s_out[(size_t)b * K + o] = sk;
-                float tq = sk * sk - (pa[K + o] + pb[K + o]);
+                float tq = sk * sk - qk;
 #pragma unroll
                 for (int x = 8; x >= 1; x >>= 1) tq += __shfl_xor_sync(hm, tq, x);
                 float zlf = 0.f;
-                if (use_lin) zlf += (pa[2 * K] + pb[2 * K]) + bias0;
+                if (use_lin) zlf += lk + bias0;
                 if (use_mf) zlf += 0.5f * tq;
                 // layer 0 (partials of P2 in warp order), layer 1, head
                 float h1 = UP(m.off_b[0])[o];
@@ -478,17 +479,18 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
             } else {
                 // field sums of the two half-sample warps -> s (kept for the FM gradient), FM + linear logit
                 const int q = tid - FR_TS * H1, sl = q / K, k = q - sl * K;
-                const float* pa = p1 + (2 * sl) * (2 * K + 4);
-                const float* pb = pa + (2 * K + 4);
-                const float sk = pa[k] + pb[k];
+                const float* pa = p1 + (FR_WPS * sl) * (2 * K + 4);
+                float sk = pa[k], qk = pa[K + k], lk = pa[2 * K];
+#pragma unroll
+                for (int w = 1; w < FR_WPS; ++w) { sk += pa[w * (2 * K + 4) + k]; qk += pa[w * (2 * K + 4) + K + k]; lk += pa[w * (2 * K + 4) + 2 * K]; }
                 ss[sl * K + k] = sk;
                 if (b0 + sl < a.B && a.s_out) a.s_out[(size_t)(b0 + sl) * K + k] = sk;
-                float tq = sk * sk - (pa[K + k] + pb[K + k]);
+                float tq = sk * sk - qk;
 #pragma unroll
                 for (int o = 8; o >= 1; o >>= 1) tq += __shfl_xor_sync(0xffffffffu, tq, o);
                 if (k == 0) {
                     float z = 0.f;
-                    if (use_lin) z += (pa[2 * K] + pb[2 * K]) + bias0;
+                    if (use_lin) z += lk + bias0;
                     if (use_mf) z += 0.5f * tq;
                     zs[sl] = z;
                 }

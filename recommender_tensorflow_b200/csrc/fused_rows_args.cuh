@@ -3,14 +3,19 @@
 #include "fused_small.cuh"
 
 constexpr int FR_TS = 8;                       // samples per tile
-constexpr int FR_CW = 16;                      // consumer warps
+#ifndef FR_CW_N
+#define FR_CW_N 16
+#endif
+constexpr int FR_CW = FR_CW_N;                 // consumer warps: 16 (96 registers per thread); -DFR_CW_N=24 (72 registers, 540 bytes of
+                                               // spill traffic per thread) measured SLOWER: kernel 0.65 -> 0.75 ms (gpurun_out/r02bb.txt)
+constexpr int FR_WPS = FR_CW / 8;              // consumer warps per sample in P1 (FR_TS = 8)
 constexpr int FR_PW = 4;                       // producer warps (bulk-copy issue is serial within a warp)
 constexpr int FR_THREADS = (FR_CW + FR_PW) * 32;
 constexpr int FR_NSLOT = 3;                    // tile slots: loading / computing / draining its stores
 constexpr int FR_W0S = 20;                     // floats per W0 row in shared memory (H1 = 16 padded: conflict-free A fragments)
 constexpr int FR_NR = 2;                       // rows per producer lane and tile (FR_TS * dc <= 32 * FR_NR * FR_PW)
-constexpr int FR_NF = 3;                       // dW0 fields per consumer warp (d <= 48)
-constexpr int FR_N5 = 4;                       // dE / update tasks per consumer warp
+constexpr int FR_NF = FR_CW == 16 ? 3 : 2;     // dW0 fields per consumer warp (d <= 48)
+constexpr int FR_N5 = FR_CW == 16 ? 4 : 3;     // dE / update tasks per consumer warp
 
 struct FusedRowsArgs {
     FusedArgs f;
