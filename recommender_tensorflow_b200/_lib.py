@@ -71,6 +71,7 @@ _SIGS = {
     "dfm_last_unique_rows": (C.c_int64, [C.c_void_p]),
     "dfm_set_global_step": (C.c_int, [C.c_void_p, C.c_int64]),
     "dfm_last_step_launches": (C.c_int64, [C.c_void_p]),
+    "dfm_graph_steps": (C.c_int64, [C.c_void_p]),
     "dfm_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "dfm_phase_ms": (C.c_float, [C.c_void_p, C.c_char_p]),
     "dfm_shard_row_width": (C.c_int, [C.c_void_p]),

@@ -181,6 +181,8 @@ struct dfm_handle {
 
     int64_t launches = 0, last_step_launches = 0;
     bool profiling = false;
+    // small-batch steps replay as one CUDA graph (train_step_graphed)
+    cudaGraphExec_t gexec = nullptr; int64_t graph_steps = 0, graph_rebuilds = 0;
     static constexpr int NPH = 11;
     cudaEvent_t ph_ev[NPH + 1] = {nullptr};
     float ph_ms[NPH] = {0};
@@ -286,6 +288,7 @@ static void free_all(dfm_handle* h) {
     free_ws(h->ws_next);
     { void* np[] = {h->ids_next, h->uidx_next, h->req_rows_next, h->d_counts_next}; for (void* p : np) if (p) cudaFree(p); }
     if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
     for (cudaEvent_t e : h->ev_done) if (e) cudaEventDestroy(e);
     { void* tp[] = {h->d_tiny_slot, h->d_key_slot, h->d_trow0, h->d_trow_grow, h->tiny_partial, h->d_tiny_cnt};
       for (void* p : tp) if (p) cudaFree(p); }
@@ -1208,6 +1211,19 @@ static int build_segments(dfm_handle* h, SegWS& ws, int64_t n, uint32_t limit, i
         if (ph) ph->next();
         return DFM_OK;
     }
+    static const bool small_ok = getenv("DFM_NO_SMALL_SEGMENTS") == nullptr;
+    if (small_ok && !n_dev && n <= SS_MAX) {         // small batches: sort + segments in one single-CTA launch
+        int m = 64;
+        while (m < n) m <<= 1;
+        static bool attr_set = false;
+        if (!attr_set) { CK(cudaFuncSetAttribute(small_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_MAX * 12)); attr_set = true; }
+        small_segments_kernel<<<1, SS_THREADS, (size_t)m * 12, st>>>(ws.keys[0], ws.vals[0], (int)n, m, limit, ws.seg_cnt, ws.row_start, ws.row_piece0,
+                                                                     ws.piece_start, ws.urow, ws.uval, ws.pos_row);
+        h->launches++;
+        if (ph) { ph->next(); ph->next(); }
+        CK(cudaGetLastError());
+        return DFM_OK;
+    }
     if (n > 0) ws.cur = prims::onesweep_sort_pairs(ws.keys, ws.vals, n, n_dev, bits, ws.sort_temp, st, &h->launches);
     if (ph) ph->next();
     const int64_t tiles = std::max<int64_t>((n + SB_TILE - 1) / SB_TILE, 1);
@@ -1759,6 +1775,50 @@ extern "C" int dfm_transform(dfm_handle* h, const dfm_raw_batch* b, int32_t* ids
     return DFM_OK;
 }
 
+// Small batches are launch-bound (BASELINE configs[0] / [1]: ~22 kernels of a few microseconds each per step), so their
+// step is replayed as ONE CUDA graph.  The per-step scalars (alpha_t, step number, replay horizon, dropout key) are plain
+// kernel arguments, so every step is stream-captured through the ordinary host path - nothing executes during a capture -
+// and the instantiated graph is updated in place from the capture (cudaGraphExecUpdate: same topology, new arguments)
+// and launched once; only a change of topology (another batch size or path) re-instantiates.
+static bool graph_step_ok(const dfm_handle* h, int B) {
+    static const int max_b = getenv("DFM_GRAPH_MAX_BATCH") ? atoi(getenv("DFM_GRAPH_MAX_BATCH")) : 8192;
+    return B <= max_b && h->world == 1 && !h->profiling && h->prefetch_B < 0 && !h->ws_next.cap;
+}
+static int train_step_graphed(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out, float* logits_out, cudaStream_t st) {
+    int rc = ensure_alpha(h, h->step + 1);               // growth allocates and synchronises: outside the capture
+    if (rc) return rc;
+    static const bool replay_only = getenv("DFM_GRAPH_REPLAY_ONLY") != nullptr;     // timing experiment: stale arguments
+    if (replay_only && h->gexec && h->graph_steps > 2) { CK(cudaGraphLaunch(h->gexec, st)); h->graph_steps++; return DFM_OK; }
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    DISPATCH_K(h, rc = train_impl<KK>(h, bp, B, loss_out, logits_out, st));
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &g);
+    if (rc || ce != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        if (rc) return rc;
+        FAIL(DFM_ERR_CUDA, "stream capture of the train step failed");
+    }
+    if (h->gexec) {
+        cudaGraphExecUpdateResultInfo info{};
+        if (cudaGraphExecUpdate(h->gexec, g, &info) != cudaSuccess) {
+            cudaGetLastError();
+            cudaGraphExecDestroy(h->gexec);
+            h->gexec = nullptr;
+        }
+    }
+    if (!h->gexec) {
+        const cudaError_t ie = cudaGraphInstantiate(&h->gexec, g, 0);
+        if (ie != cudaSuccess) { cudaGraphDestroy(g); h->gexec = nullptr; CK(ie); }
+        h->graph_rebuilds++;
+    }
+    cudaGraphDestroy(g);
+    CK(cudaGraphLaunch(h->gexec, st));
+    h->graph_steps++;
+    return DFM_OK;
+}
+extern "C" int64_t dfm_graph_steps(const dfm_handle* h) { return h ? h->graph_steps : -1; }
+
 extern "C" int dfm_train_step(dfm_handle* h, const dfm_raw_batch* b, float* loss_out, float* logits_out, void* stream) {
     if (!h) return DFM_ERR_INVALID_ARG;
     int rc = check_batch(h, b, true);
@@ -1766,6 +1826,8 @@ extern "C" int dfm_train_step(dfm_handle* h, const dfm_raw_batch* b, float* loss
     CK(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     BatchPtrs bp = make_ptrs(h, b);
+    static const bool graphs = getenv("DFM_NO_GRAPH") == nullptr;
+    if (graphs && graph_step_ok(h, b->batch_size)) return train_step_graphed(h, bp, b->batch_size, loss_out, logits_out, st);
     DISPATCH_K(h, rc = train_impl<KK>(h, bp, b->batch_size, loss_out, logits_out, st));
     return rc;
 }

@@ -544,6 +544,105 @@ static __global__ void __launch_bounds__(256) seg_fill_kernel2(const uint32_t* _
     }
 }
 
+// Small batches (BASELINE configs[0] / [1]: 128 .. 16 384 pairs): sort + segments in ONE single-CTA launch instead of
+// histogram + one launch per digit + count + fill (5-6 dependent launches of a few microseconds each; the step is a
+// chain of such launches).  The pairs are sorted in shared memory by a bitonic network over (key << 32 | position) -
+// distinct composites, so the order is the stable order of the radix sort and everything downstream is bit-identical -
+// and the segment lists are written exactly as seg_count_kernel / seg_fill_kernel2 write them.
+constexpr int SS_MAX = 16384, SS_THREADS = 1024;
+static __global__ void __launch_bounds__(SS_THREADS) small_segments_kernel(uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int n, int m /* power of two >= max(n, 64) */,
+                                                                    uint32_t R, SegCounts* __restrict__ cnt, uint32_t* __restrict__ row_start,
+                                                                    uint32_t* __restrict__ row_piece0, uint32_t* __restrict__ piece_start,
+                                                                    uint32_t* __restrict__ urow, uint32_t* __restrict__ uval, uint32_t* __restrict__ pos_row) {
+    extern __shared__ __align__(16) unsigned long long ss_comp[];      // [m] composites, then [m] payloads
+    uint32_t* sv = reinterpret_cast<uint32_t*>(ss_comp + m);
+    __shared__ unsigned long long wtot[33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < m; i += SS_THREADS) {
+        ss_comp[i] = i < n ? (((unsigned long long)keys[i] << 32) | (unsigned)i) : ~0ull;
+        sv[i] = i < n ? vals[i] : 0u;
+    }
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int p = tid; p < (m >> 1); p += SS_THREADS) {
+                const int l = 2 * p - (p & (j - 1)), r = l + j;
+                const unsigned long long a = ss_comp[l], b = ss_comp[r];
+                const bool up = (l & k) == 0;
+                if ((a > b) == up) { ss_comp[l] = b; ss_comp[r] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    // this thread's contiguous run of positions: flags, block-wide exclusive scan of (row heads, piece heads), lists
+    const int per = (m + SS_THREADS - 1) / SS_THREADS;
+    const int i0 = tid * per;
+    uint32_t rows = 0, pieces = 0, valid_cnt = 0;
+    for (int j = 0; j < per; ++j) {
+        const int i = i0 + j;
+        if (i < n) {
+            const uint32_t k = (uint32_t)(ss_comp[i] >> 32);
+            const uint32_t prev = i > 0 ? (uint32_t)(ss_comp[i - 1] >> 32) : 0xffffffffu;
+            const bool valid = k < R, rh = valid && (i == 0 || k != prev), ph = valid && (rh || (i % PIECE_C) == 0);
+            rows += rh; pieces += ph; valid_cnt += valid;
+        }
+    }
+    const unsigned long long mine = ((unsigned long long)rows << 32) | pieces;
+    unsigned long long inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    uint32_t vsum = valid_cnt;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+    __shared__ uint32_t wvalid[32];
+    if (lane == 31) wtot[warp] = inc;
+    if (lane == 0) wvalid[warp] = vsum;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long w = wtot[lane];
+        unsigned long long winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        wtot[lane] = winc - w;
+        if (lane == 31) wtot[32] = winc;
+        uint32_t v = wvalid[lane];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) wvalid[0] = v;
+    }
+    __syncthreads();
+    const unsigned long long run = wtot[warp] + (inc - mine);
+    uint32_t ridx = (uint32_t)(run >> 32), pidx = (uint32_t)(run & 0xffffffffu);
+    for (int j = 0; j < per; ++j) {
+        const int i = i0 + j;
+        if (i < n) {
+            const unsigned long long c = ss_comp[i];
+            const uint32_t k = (uint32_t)(c >> 32), v = sv[(uint32_t)c];
+            const uint32_t prev = i > 0 ? (uint32_t)(ss_comp[i - 1] >> 32) : 0xffffffffu;
+            const bool valid = k < R, rh = valid && (i == 0 || k != prev), ph = valid && (rh || (i % PIECE_C) == 0);
+            keys[i] = k; vals[i] = v;
+            if (ph) {
+                piece_start[pidx] = (uint32_t)i;
+                if (rh) { row_start[ridx] = (uint32_t)i; row_piece0[ridx] = pidx; urow[ridx] = k; uval[ridx] = v; ++ridx; }
+                ++pidx;
+            }
+            if (pos_row && valid) pos_row[i] = ridx - 1;
+        }
+    }
+    if (tid == 0) {
+        const unsigned long long tot = wtot[32];
+        const uint32_t Ur = (uint32_t)(tot >> 32), P = (uint32_t)(tot & 0xffffffffu), nv = wvalid[0];
+        cnt->n_rows = Ur; cnt->n_pieces = P; cnt->n_valid = nv; cnt->n_hot = 0;
+        row_start[Ur] = nv; row_piece0[Ur] = P; piece_start[P] = nv;
+    }
+}
+
 // =============================================================================================
 // non-lazy Adam: materialise the deferred decay of EVERY row (dfm_flush: before a checkpoint / dfm_get_tensor)
 // =============================================================================================

@@ -152,6 +152,11 @@ class DeepFMEngine:
     def last_step_launches(self):
         return int(self.lib.dfm_last_step_launches(self.h))
 
+    @property
+    def graph_steps(self):
+        """train steps replayed as a single CUDA graph (small batches)"""
+        return int(self.lib.dfm_graph_steps(self.h))
+
     def sync(self):
         self._check(self.lib.dfm_sync(self.h))
 
