@@ -2650,7 +2650,9 @@ static int enqueue_host_step(dfm_handle* h, const dfm_raw_batch* b, int slot) {
     if (rc) return rc;
     CK(cudaEventRecord(sg.copied, h->copy_stream));
     CK(cudaStreamWaitEvent(h->stream, sg.copied, 0));
-    DISPATCH_K(h, rc = train_impl<KK>(h, bp, b->batch_size, nullptr, nullptr, h->stream));
+    static const bool graphs = getenv("DFM_NO_GRAPH") == nullptr;
+    if (graphs && graph_step_ok(h, b->batch_size)) rc = train_step_graphed(h, bp, b->batch_size, nullptr, nullptr, h->stream);
+    else DISPATCH_K(h, rc = train_impl<KK>(h, bp, b->batch_size, nullptr, nullptr, h->stream));
     if (rc) return rc;
     CK(cudaMemcpyAsync(sg.h_loss, h->d_loss, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaEventRecord(sg.done, h->stream));
