@@ -947,10 +947,24 @@ size_t fused_rows_smem_bytes(const SmallMlpDesc& m, int K, int dc, int dn, int r
 
 int fused_rows_grid(int B, int sm_count, bool side_stream_busy) {
     // The kernel fills an SM (registers, 224 KB of shared memory), so nothing else runs beside it: with the compaction /
-    // sort / segment kernels of the repeated lookups on the side stream, 8 SMs are left to them (measured on the
-    // Criteo-shaped step: 0.865 -> 0.819 ms uniform ids, 1.045 -> 0.965 ms Zipf(1.05); 16 SMs: 0.859 / 0.966).  DFM_FR_RESERVE overrides.
-    static const int reserve = getenv("DFM_FR_RESERVE") ? atoi(getenv("DFM_FR_RESERVE")) : 8;
-    return std::max(1, std::min((B + FR_TS - 1) / FR_TS, sm_count - (side_stream_busy ? reserve : 0)));
+    // sort / segment kernels of the repeated lookups on the side stream, a few SMs are left to them (measured on the
+    // Criteo-shaped step: none reserved 0.865 ms, 8 reserved 0.819, 16 reserved 0.859).  Every CTA walks ceil(tiles / grid)
+    // tiles, so between 4 and 12 reserved SMs the count with the fewest tiles per CTA is taken, the larger reserve on a tie
+    // (B = 65 536 on 148 SMs: 4 reserved = 57 tiles per CTA, 8 reserved = 59: step 0.839 -> 0.814 ms).  DFM_FR_RESERVE overrides.
+    static const int reserve_env = getenv("DFM_FR_RESERVE") ? atoi(getenv("DFM_FR_RESERVE")) : -1;
+    const int tiles = (B + FR_TS - 1) / FR_TS;
+    int reserve = 0;
+    if (side_stream_busy) {
+        reserve = reserve_env;
+        if (reserve < 0) {
+            int best_per = 1 << 30;
+            for (int r = 12; r >= 4; --r) {
+                const int g = std::max(1, sm_count - r), per = (tiles + g - 1) / g;
+                if (per < best_per) { best_per = per; reserve = r; }
+            }
+        }
+    }
+    return std::max(1, std::min(tiles, sm_count - reserve));
 }
 
 template <int ES, bool RB>
