@@ -411,11 +411,17 @@ static __global__ void seg_fill_kernel(const uint32_t* __restrict__ keys, const 
 // A single-launch version with decoupled look-back measured 67 us for 832 tiles (the chain starts cold: every tile
 // publishes at the same moment), this one needs no spinning.  The element count may live in device memory (n_dev).
 constexpr int SB_ITEMS = 8, SB_TILE = 256 * SB_ITEMS;
+static_assert(SB_ITEMS == 8, "seg_tile_flags loads a thread's run as two uint4");
 
 __device__ __forceinline__ void seg_tile_flags(const uint32_t* __restrict__ keys, int64_t i0, int64_t n, uint32_t R, uint32_t (&k)[SB_ITEMS],
                                                uint32_t& rows, uint32_t& pieces, uint32_t& rmask, uint32_t& pmask, uint32_t& vmask) {
+    if (i0 + SB_ITEMS <= n) {        // a thread's run is 32 contiguous, 32-byte aligned bytes: two vector loads instead of eight scalar ones
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(keys + i0)), b = __ldg(reinterpret_cast<const uint4*>(keys + i0) + 1);
+        k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+    } else {
 #pragma unroll
-    for (int j = 0; j < SB_ITEMS; ++j) k[j] = (i0 + j < n) ? keys[i0 + j] : 0xffffffffu;
+        for (int j = 0; j < SB_ITEMS; ++j) k[j] = (i0 + j < n) ? keys[i0 + j] : 0xffffffffu;
+    }
     uint32_t prev = (i0 > 0 && i0 < n) ? keys[i0 - 1] : 0xffffffffu;
     rows = 0; pieces = 0; rmask = 0; pmask = 0; vmask = 0;
 #pragma unroll
@@ -435,6 +441,7 @@ static __global__ void __launch_bounds__(256) seg_count_kernel(const uint32_t* _
                                                         SegCounts* __restrict__ cnt, uint32_t* __restrict__ row_start,
                                                         uint32_t* __restrict__ row_piece0, uint32_t* __restrict__ piece_start) {
     __shared__ unsigned long long wsum[8];
+    __shared__ uint32_t winv[8];
     __shared__ bool last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n = n_dev ? (int64_t)*reinterpret_cast<const volatile uint32_t*>(n_dev) : n_host;
@@ -444,15 +451,21 @@ static __global__ void __launch_bounds__(256) seg_count_kernel(const uint32_t* _
         uint32_t k[SB_ITEMS], rows, pieces, rmask, pmask, vmask;
         seg_tile_flags(keys, tile * SB_TILE + (int64_t)tid * SB_ITEMS, n, R, k, rows, pieces, rmask, pmask, vmask);
         unsigned long long v = ((unsigned long long)rows << 32) | pieces;
+        // lookups without a row (keys >= R, sorted last): counted here so that the closing thread needs no binary search
+        // over the keys (21 dependent global loads, ~8 of this kernel's 20 us)
+        const int64_t i0 = tile * SB_TILE + (int64_t)tid * SB_ITEMS;
+        uint32_t inval = (uint32_t)max((int64_t)0, min((int64_t)SB_ITEMS, n - i0)) - __popc(vmask);
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) wsum[warp] = v;
+        for (int o = 16; o >= 1; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); inval += __shfl_xor_sync(0xffffffffu, inval, o); }
+        if (lane == 0) { wsum[warp] = v; winv[warp] = inval; }
         __syncthreads();
         if (tid == 0) {
             unsigned long long t = 0;
+            uint32_t iv = 0;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) t += wsum[w];
+            for (int w = 0; w < 8; ++w) { t += wsum[w]; iv += winv[w]; }
             tile_cnt[tile] = t;
+            if (iv) atomicAdd(ticket + 1, iv);
         }
     }
     __threadfence();
@@ -461,32 +474,49 @@ static __global__ void __launch_bounds__(256) seg_count_kernel(const uint32_t* _
     __syncthreads();
     if (!last) return;
     __threadfence();
-    if (warp != 0) return;
-    // warp 0: exclusive prefix over the tiles, 32 at a time
+    // the last block: exclusive prefix over the tile counts, 8 tiles per thread and 2048 per round (one warp walking 32
+    // tiles at a time made 26 dependent L2 round trips for the 832 tiles of a 1.7 M pair list: most of this kernel's time)
+    __shared__ unsigned long long ptot[9];
     unsigned long long run = 0;
-    for (int64_t t0 = 0; t0 < tiles; t0 += 32) {
-        const int64_t t = t0 + lane;
-        const unsigned long long c = t < tiles ? __ldcg(tile_cnt + t) : 0ull;
-        unsigned long long inc = c;
+    for (int64_t c0 = 0; c0 < tiles; c0 += 256 * 8) {
+        const int64_t tb = c0 + (int64_t)tid * 8;
+        unsigned long long c[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = tb + j < tiles ? __ldcg(tile_cnt + tb + j) : 0ull; sum += c[j]; }
+        unsigned long long inc = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned long long x = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += x;
         }
-        if (t < tiles) tile_cnt[t] = run + inc - c;
-        run += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    if (lane == 0) {
-        const uint32_t Ur = (uint32_t)(run >> 32), P = (uint32_t)(run & 0xffffffffu);
-        int64_t lo = 0, hi = n;                        // keys are sorted, the invalid ones (>= R) last
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (keys[mid] < R) lo = mid + 1; else hi = mid;
+        if (lane == 31) ptot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long w = lane < 8 ? ptot[lane] : 0ull;
+            unsigned long long winc = w;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const unsigned long long x = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += x;
+            }
+            if (lane < 8) ptot[lane] = winc - w;
+            if (lane == 7) ptot[8] = winc;
         }
-        const uint32_t nv = (uint32_t)lo;
+        __syncthreads();
+        unsigned long long ex = run + ptot[warp] + (inc - sum);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (tb + j < tiles) { tile_cnt[tb + j] = ex; ex += c[j]; }
+        run += ptot[8];
+        __syncthreads();
+    }
+    if (tid != 0) return;
+    {
+        const uint32_t Ur = (uint32_t)(run >> 32), P = (uint32_t)(run & 0xffffffffu);
+        const uint32_t nv = (uint32_t)n - __ldcg(ticket + 1);      // the invalid keys (>= R) sort last
         cnt->n_rows = Ur; cnt->n_pieces = P; cnt->n_valid = nv; cnt->n_hot = 0;
         row_start[Ur] = nv; row_piece0[Ur] = P; piece_start[P] = nv;
-        *ticket = 0;
+        ticket[0] = 0; ticket[1] = 0;
     }
 }
 
@@ -524,24 +554,60 @@ static __global__ void __launch_bounds__(256) seg_fill_kernel2(const uint32_t* _
         if (lane < 8) wtot[lane] = winc - w;
     }
     __syncthreads();
-    const unsigned long long run = __ldg(tile_cnt + tile) + wtot[warp] + (inc - mine);
-    uint32_t ridx = (uint32_t)(run >> 32), pidx = (uint32_t)(run & 0xffffffffu);
+    // The lists of a tile are contiguous in the output (ranks follow positions), but a thread's 8 entries would go out as
+    // 4-byte stores 32 bytes apart (5 lists: 23 % of the stall samples on the LSU queue, 7 % issue-active, 47 us for 1.7 M
+    // pairs, profiles/r02br): they are staged in shared memory and written by consecutive threads instead.
+    __shared__ uint32_t s_rs[SB_TILE], s_rp[SB_TILE], s_ur[SB_TILE], s_uv[SB_TILE], s_ps[SB_TILE];
+    __shared__ unsigned long long s_tot;
+    const unsigned long long tile_base = __ldg(tile_cnt + tile);
+    const unsigned long long loc = wtot[warp] + (inc - mine);                  // exclusive (rows, pieces) before this thread, inside the tile
+    if (tid == 255) s_tot = loc + mine;
+    const int64_t t0 = tile * SB_TILE;
+    for (int q = tid; q < SB_TILE; q += 256) s_uv[q] = t0 + q < n ? __ldg(vals + t0 + q) : 0u;      // coalesced payloads of the tile
+    __syncthreads();
+    uint32_t myv[SB_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j) myv[j] = s_uv[tid * SB_ITEMS + j];
+    __syncthreads();                                                            // s_uv is rewritten in compacted order below
+    uint32_t lr = (uint32_t)(loc >> 32), lp = (uint32_t)(loc & 0xffffffffu);
+    const uint32_t r_tile = (uint32_t)(tile_base >> 32), p_tile = (uint32_t)(tile_base & 0xffffffffu);
+    uint32_t pr[SB_ITEMS];
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j) {
         if ((pmask >> j) & 1u) {
             const uint32_t i = (uint32_t)(i0 + j);
-            piece_start[pidx] = i;
+            s_ps[lp] = i;
             if ((rmask >> j) & 1u) {
-                row_start[ridx] = i;
-                row_piece0[ridx] = pidx;
-                urow[ridx] = k[j];
-                uval[ridx] = vals[i];
-                ++ridx;
+                s_rs[lr] = i;
+                s_rp[lr] = p_tile + lp;
+                s_ur[lr] = k[j];
+                s_uv[lr] = myv[j];
+                ++lr;
             }
-            ++pidx;
+            ++lp;
         }
-        if (pos_row && ((vmask >> j) & 1u)) pos_row[i0 + j] = ridx - 1;
+        pr[j] = r_tile + lr - 1;
     }
+    if (pos_row) {
+        if (vmask == 0xffu) {
+            uint4* d = reinterpret_cast<uint4*>(pos_row + i0);
+            d[0] = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+            d[1] = make_uint4(pr[4], pr[5], pr[6], pr[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < SB_ITEMS; ++j)
+                if ((vmask >> j) & 1u) pos_row[i0 + j] = pr[j];
+        }
+    }
+    __syncthreads();
+    const uint32_t nr = (uint32_t)(s_tot >> 32), np = (uint32_t)(s_tot & 0xffffffffu);
+    for (uint32_t q = tid; q < nr; q += 256) {
+        row_start[r_tile + q] = s_rs[q];
+        row_piece0[r_tile + q] = s_rp[q];
+        urow[r_tile + q] = s_ur[q];
+        uval[r_tile + q] = s_uv[q];
+    }
+    for (uint32_t q = tid; q < np; q += 256) piece_start[p_tile + q] = s_ps[q];
 }
 
 // Small batches (BASELINE configs[0] / [1]: 128 .. 16 384 pairs): sort + segments in ONE single-CTA launch instead of
