@@ -1639,11 +1639,25 @@ static int train_fused(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_ou
         else rc = launch_fused<K>(h, bp, B, bp.labels, scale, logits_out, nullptr, t - 1, st);
         if (rc) return rc;
         ph.next(); ph.next();                                                                    // gather + tower forward/backward top
+        // The sparse optimizer of the repeated rows needs the per-sample vectors of the kernel above and the side stream's
+        // segments, not the dense reduction: it stays on the side stream, beside fused_reduce, and is joined in front of
+        // dense_apply (it reads W0).
+        static const bool tail_overlap = getenv("DFM_NO_TAIL_OVERLAP") == nullptr;
+        const bool side_tail = side && tail_overlap;
+        if (side_tail) {
+            CK(cudaEventRecord(h->ev_aux_fork, st));
+            CK(cudaStreamWaitEvent(h->side_stream, h->ev_aux_fork, 0));
+            if ((rc = fused_sparse_update<K>(h, h->ws, n, so, t, nullptr, nullptr, h->side_stream, nullptr))) return rc;
+            CK(cudaEventRecord(h->ev_aux_join, h->side_stream));
+        }
         if ((rc = launch_fused_reduce(h, B, scale, loss_out, st, h->fused_rows))) return rc;
         ph.next(); ph.next();                                                                    // loss, dense gradients
-        if (side) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
-        if ((rc = fused_sparse_update<K>(h, h->ws, n, so, t, nullptr, nullptr, st, &ph))) return rc;
+        if (!side_tail) {
+            if (side) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+            if ((rc = fused_sparse_update<K>(h, h->ws, n, so, t, nullptr, nullptr, st, &ph))) return rc;
+        }
         h->claim_live = false;
+        if (side_tail) CK(cudaStreamWaitEvent(st, h->ev_aux_join, 0));      // row_apply rebuilds gradients from W0: before the dense update
         if (h->n_dense) {
             dense_apply_kernel<<<cdiv(h->n_dense, 256), 256, 0, st>>>(h->dw, h->ds1, h->ds2, h->dg, h->n_deep, h->n_dense, so.od, so.ol);
             h->launches++;
@@ -1789,7 +1803,11 @@ static int train_step_graphed(dfm_handle* h, const BatchPtrs& bp, int B, float* 
     if (rc) return rc;
     static const bool replay_only = getenv("DFM_GRAPH_REPLAY_ONLY") != nullptr;     // timing experiment: stale arguments
     if (replay_only && h->gexec && h->graph_steps > 2) { CK(cudaGraphLaunch(h->gexec, st)); h->graph_steps++; return DFM_OK; }
-    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();                               // a stream that cannot be captured (legacy default stream): ordinary launches
+        DISPATCH_K(h, rc = train_impl<KK>(h, bp, B, loss_out, logits_out, st));
+        return rc;
+    }
     DISPATCH_K(h, rc = train_impl<KK>(h, bp, B, loss_out, logits_out, st));
     cudaGraph_t g = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(st, &g);
