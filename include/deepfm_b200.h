@@ -200,7 +200,7 @@ int64_t dfm_last_unique_rows(dfm_handle* h);
 int dfm_set_global_step(dfm_handle* h, int64_t step);
 /* number of kernels the last train step launched (bench.py's gpu_launches) */
 int64_t dfm_last_step_launches(const dfm_handle* h);
-/* train steps replayed as one CUDA graph so far (dfm_train_step with batch_size <= 8192 on an unsharded handle captures
+/* train steps replayed as one CUDA graph so far (dfm_train_step with batch_size <= 131072 on an unsharded handle captures
  * the step's kernels and launches them as a single graph: one session.run(train_op) = one launch; DFM_NO_GRAPH=1 disables) */
 int64_t dfm_graph_steps(const dfm_handle* h);
 /* device time (ms) spent in the named phase during the last *timed* step; enable with

@@ -63,17 +63,32 @@ def test_graph_and_small_segments_change_nothing():
             assert all(int(g) == 0 for _, g in other)
 
 
-def test_graph_path_is_taken_only_for_small_batches():
+def test_graph_path_counts_and_threshold():
+    """Every step at or below DFM_GRAPH_MAX_BATCH (default 131 072: every unsharded step) replays as one graph, another
+    batch size re-instantiates instead of reusing the graph blindly, and batches above the threshold take ordinary launches."""
     eng = _ml_engine(k=4, hidden=(16, 16), max_batch=16384)
     make_pair(eng, seed=33)
     ml, rng = synth.ML100K(), np.random.default_rng(34)
     eng.train_step(*ml.batch(32, rng))
     eng.train_step_device(eng.pack(*ml.batch(4096, rng), device=True))
-    n_small = eng.graph_steps
-    eng.train_step(*ml.batch(16000, rng))           # above the graph threshold: ordinary launches
-    eng.train_step(*ml.batch(100, rng))             # another topology: the graph is rebuilt, not reused blindly
+    eng.train_step(*ml.batch(16000, rng))
+    eng.train_step(*ml.batch(100, rng))
+    assert np.isfinite(eng.train_step(*ml.batch(32, rng)))
     if os.environ.get("DFM_NO_GRAPH"):
         assert eng.graph_steps == 0
-    else:
-        assert n_small == 2 and eng.graph_steps == 3
-    assert np.isfinite(eng.train_step(*ml.batch(32, rng)))
+    elif "DFM_GRAPH_MAX_BATCH" not in os.environ:
+        assert eng.graph_steps == 5
+    script = SCRIPT.split("out = []")[0] + r"""
+eng = _ml_engine(k=4, hidden=(16, 16), max_batch=4096)
+make_pair(eng, seed=35)
+ml, rng = synth.ML100K(), np.random.default_rng(36)
+eng.train_step(*ml.batch(32, rng)); a = eng.graph_steps
+eng.train_step(*ml.batch(3000, rng)); b = eng.graph_steps
+print("RESULT %d %d" % (a, b))
+"""
+    env = dict(os.environ)
+    env.pop("DFM_NO_GRAPH", None)
+    env["DFM_GRAPH_MAX_BATCH"] = "1000"
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1] == "RESULT 1 1"
