@@ -384,25 +384,45 @@ def measure(name, args, world, rank, local, peaks, primary=True, zipf=None):
         stage = [torch.empty_like(packed_dev[0].arena) for _ in range(3)]
         staged = [eng.repack_like(packed_dev[0], a) for a in stage]
 
-        copied = set()
+        # H2D copies run on their own stream, one step ahead of their first use: the columns of step i + 2 are copied while
+        # step i computes (its tail already issues the requests of step i + 1, whose columns arrived during step i - 1).
+        # Ring of three arenas: arena (i + 2) % 3 was last read by step i - 1, so the copy waits for that step's event.
+        copy_stream = torch.cuda.Stream()
+        copied = {}
+        step_done = {}
 
         def e2e_copy(i):
             if i not in copied:
-                staged[i % 3].arena.copy_(packed_host[i % nh].arena, non_blocking=True)  # H2D of the raw columns of step i
-                copied.add(i)
+                if i - 3 in step_done:
+                    copy_stream.wait_event(step_done[i - 3])
+                with torch.cuda.stream(copy_stream):
+                    staged[i % 3].arena.copy_(packed_host[i % nh].arena, non_blocking=True)  # H2D of the raw columns of step i
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                copied[i] = ev
 
         def e2e_step(i, last=False):
             e2e_copy(i)
             nxt = None
             if prefetch and not last:
-                e2e_copy(i + 1)                      # the next step's columns: copied now, their requests run beside this apply
+                e2e_copy(i + 1)
                 nxt = staged[(i + 1) % 3]
-            return trainer.train_step(staged[i % 3], B * world, next_pb=nxt)
+            stream.wait_event(copied[i])
+            if nxt is not None:
+                stream.wait_event(copied[i + 1])
+            out = trainer.train_step(staged[i % 3], B * world, next_pb=nxt)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            step_done[i] = ev
+            if not last:
+                e2e_copy(i + 2)                      # in flight beside step i
+            return out
         with torch.cuda.stream(stream):
             for i in range(2):
                 e2e_step(i, last=i == 1)
         barrier()
         copied.clear()
+        step_done.clear()
         loss_pin = torch.empty(2, dtype=torch.float32).pin_memory()
         loss_evs = [torch.cuda.Event(), torch.cuda.Event()]
         e2e_loss = float("nan")
@@ -481,7 +501,7 @@ def measure(name, args, world, rank, local, peaks, primary=True, zipf=None):
             "unique_rows_per_step": int(unique_rows), "unique_row_ratio": unique_rows / float(B * max(len(cats), 1)),
             "e2e": {"value": B * steps * world / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / steps, "loss_last": e2e_loss,
-                    "how": ("pinned host arena -> H2D copy, sharded step (launches only), D2H of the loss every step (read one step late); "
+                    "how": ("pinned host arena -> H2D copy of every step's columns on a copy stream (three device arenas, two steps ahead), sharded step (launches only), D2H of the loss every step (read one step late); "
                             "wall clock, barrier + device sync on both sides" if sharded else
                             "dfm_train_step_host_async: pinned host arena -> one H2D copy per step on a copy stream, step, "
                             "D2H of the loss; double buffered, wall clock with a device sync on both sides")},
