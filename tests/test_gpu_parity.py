@@ -99,6 +99,36 @@ def test_transform_ml100k_bit_exact():
     assert (ids[:50] == ref_py).all()
 
 
+def test_hash_bucket_sizes_bit_exact():
+    """fingerprint % buckets on the device is a Barrett reduction with a per-column reciprocal (embed_kernels.cuh:
+    mod_buckets); bucket counts from 1 to 5e7 incl. powers of two and their neighbours, string and int32 keys, against
+    the oracle's plain 64-bit modulo (C and pure Python)."""
+    from recommender_tensorflow_b200 import feature_column as fc
+    sizes = [1, 2, 3, 5, 97, 255, 256, 257, 1000, 65535, 65536, 65537, (1 << 20) + 7, 9_999_991, 10_000_000, 50_000_017]
+    cols, dtypes = [], {}
+    for i, nb in enumerate(sizes):
+        cols.append(fc.categorical_column_with_hash_bucket("s%d" % i, nb))
+        cols.append(fc.categorical_column_with_hash_bucket("i%d" % i, nb, dtype="int32"))
+        dtypes["i%d" % i] = "int32"
+    eng = DeepFMEngine(cols, (), embedding_size=4, hidden_units=(16,), max_batch=4096, use_mf=False, use_dnn=False,
+                       feature_dtypes=dtypes)
+    rng = np.random.default_rng(77)
+    B = 4096
+    feats = {}
+    for i in range(len(sizes)):
+        lens = rng.integers(1, 40, B)
+        feats["s%d" % i] = np.array([bytes(rng.integers(33, 127, int(n), dtype=np.uint8)) for n in lens], dtype=object)
+        v = rng.integers(-2**31, 2**31 - 1, B).astype(np.int32)
+        v[v == -1] = 12345
+        feats["i%d" % i] = v
+    ids = eng.transform(feats)
+    ref = transforms.transform(eng.specs, feats)
+    assert (ids == ref).all()
+    ref_py = transforms.transform(eng.specs, {k: v[:40] for k, v in feats.items()}, use_c=False)
+    assert (ids[:40] == ref_py).all()
+    assert (ids >= 0).all() and (ids < np.asarray(eng.num_buckets)[None, :]).all()
+
+
 def test_identity_out_of_range_is_an_error():
     from recommender_tensorflow_b200._lib import DfmError
     eng = _ml_engine()

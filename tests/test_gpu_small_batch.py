@@ -24,7 +24,10 @@ from recommender_tensorflow_b200 import synth
 from tests.test_gpu_parity import _ml_engine
 from tests.util import make_pair
 out = []
-for k, hidden, batch in ((4, (16, 16), 32), (4, (16, 16), 3000), (16, (64, 32), 700)):
+# (row, lookup) pairs per step: 26 x batch for k = 4 (52, 832, 2 054, 16 380: single-CTA builder; 16 406, 78 000: radix sort),
+# 4 x batch for k = 16 (tiny-vocabulary columns bypass the sort)
+for k, hidden, batch in ((4, (16, 16), 32), (4, (16, 16), 2), (4, (16, 16), 79), (4, (16, 16), 630), (4, (16, 16), 631),
+                         (4, (16, 16), 3000), (16, (64, 32), 700)):
     eng = _ml_engine(k=k, hidden=hidden, max_batch=4096)
     make_pair(eng, seed=31)
     ml, rng = synth.ML100K(), np.random.default_rng(32)
