@@ -1802,8 +1802,6 @@ static bool graph_step_ok(const dfm_handle* h, int B) {
 static int train_step_graphed(dfm_handle* h, const BatchPtrs& bp, int B, float* loss_out, float* logits_out, cudaStream_t st) {
     int rc = ensure_alpha(h, h->step + 1);               // growth allocates and synchronises: outside the capture
     if (rc) return rc;
-    static const bool replay_only = getenv("DFM_GRAPH_REPLAY_ONLY") != nullptr;     // timing experiment: stale arguments
-    if (replay_only && h->gexec && h->graph_steps > 2) { CK(cudaGraphLaunch(h->gexec, st)); h->graph_steps++; return DFM_OK; }
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
         cudaGetLastError();                               // a stream that cannot be captured (legacy default stream): ordinary launches
         DISPATCH_K(h, rc = train_impl<KK>(h, bp, B, loss_out, logits_out, st));
