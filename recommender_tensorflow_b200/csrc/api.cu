@@ -1494,6 +1494,7 @@ static int launch_fused_rows(dfm_handle* h, const BatchPtrs& bp, int B, const fl
         A.step = (int)t;
         if (so) { A.od_t = so->od; A.ol_t = so->ol; }
         A.numg_partial = h->num_partial;
+        fr_layout(A, h->sm, K, h->dc, h->dn);
         fr_balance(A, h->dc, h->dn, A.f.train && (A.rowbuf_mode || A.claim != nullptr));
         const int grid = fused_rows_grid(B, h->sm_count, rowbuf ? false : h->fr_side);
         CK(fused_rows_launch(A, grid, rowbuf ? h->fr_smem_rb : h->fr_smem, st));

@@ -124,28 +124,30 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
     constexpr int RS = K + 4 + ES * K;                           // floats per staged record
     const int SST = A.sst;
     const int nrows = FR_TS * dc;
+    // Shared-memory carve-up: the offsets come from the host (fr_layout).  Computed here they are chains of a dozen
+    // dependent integer operations on kernel parameters, and the compiler re-derives them inside the tile loop rather
+    // than hold fifteen pointers in registers: 15 % of the kernel's instructions in profiles/r02bc were this arithmetic.
+    const FrLayout& L = A.lay;
     float* W0s = smem;                                           // [D][FR_W0S]
-    float* ups = W0s + (size_t)D * FR_W0S;
-    float* gup = ups + m.up_count;
-    float* slots = gup + m.up_count + ((4 - ((2 * m.up_count) & 3)) & 3);        // [NSLOT][TS][SST]
-    uint32_t* rowix = reinterpret_cast<uint32_t*>(slots + (size_t)FR_NSLOT * FR_TS * SST);   // [NSLOT][TS*dc] global row (~0: no row)
-    uint32_t* once = rowix + FR_NSLOT * nrows;                   // [NSLOT][TS*dc] 1: this kernel applies the row's gradient
-    float* xsb = reinterpret_cast<float*>(once + FR_NSLOT * nrows);              // [NSLOT][TS][dn]
-    float* ysb = xsb + FR_NSLOT * FR_TS * (dn > 0 ? dn : 1);     // [NSLOT][TS] labels (a global load would sit on P3's critical path)
-    float* part = ysb + FR_NSLOT * FR_TS;                        // [CW][TS][H1] layer-0 partials; later the warps' dE staging
-    part += (4 - ((size_t)(part - smem) & 3)) & 3;
-    float* p1 = part + FR_CW * FR_TS * H1;                       // [CW][2K + 4] FM / linear partials of P1
-    float* dh1s = p1 + FR_CW * (2 * K + 4);                      // [TS][H1]
-    float* acts = dh1s + FR_TS * H1;                             // [TS][act_stride]
-    float* dacts = acts + FR_TS * m.act_stride;
-    float* zs = dacts + FR_TS * m.act_stride;                    // [TS]
-    float* dzs = zs + FR_TS;
-    float* red = dzs + FR_TS;
-    float* ss = red + FR_TS;                                     // [TS][K]
-    ss += (4 - ((size_t)(ss - smem) & 3)) & 3;
-    float* gnum = ss + FR_TS * K;                                // [dn*K | dn] numeric_embeddings / numeric linear gradients of this CTA
+    float* ups = smem + L.ups;
+    float* gup = smem + L.gup;
+    float* slots = smem + L.slots;                               // [NSLOT][TS][SST]
+    uint32_t* rowix = reinterpret_cast<uint32_t*>(smem + L.rowix);               // [NSLOT][TS*dc] global row (~0: no row)
+    uint32_t* once = reinterpret_cast<uint32_t*>(smem + L.once);                 // [NSLOT][TS*dc] 1: this kernel applies the row's gradient
+    float* xsb = smem + L.xsb;                                   // [NSLOT][TS][dn]
+    float* ysb = smem + L.ysb;                                   // [NSLOT][TS] labels (a global load would sit on P3's critical path)
+    float* part = smem + L.part;                                 // [CW][TS][H1] layer-0 partials; later the warps' dE staging
+    float* p1 = smem + L.p1;                                     // [CW][2K + 4] FM / linear partials of P1
+    float* dh1s = smem + L.dh1s;                                 // [TS][H1]
+    float* acts = smem + L.acts;                                 // [TS][act_stride]
+    float* dacts = smem + L.dacts;
+    float* zs = smem + L.zs;                                     // [TS]
+    float* dzs = smem + L.dzs;
+    float* red = smem + L.red;
+    float* ss = smem + L.ss;                                     // [TS][K]
+    float* gnum = smem + L.gnum;                                 // [dn*K | dn] numeric_embeddings / numeric linear gradients of this CTA
     const int n_gnum = dn * K + dn;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(gnum + n_gnum + ((size_t)(gnum - smem + n_gnum) & 1));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
     uint64_t* full = bars;                                       // [NSLOT] records landed
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -935,6 +937,33 @@ void fr_balance(FusedRowsArgs& A, int dc, int dn, bool cat_tasks) {
         for (int f = 0; f < dc; ++f) place(f, c_cat, n5, FR_N5, A.p5f, FR_N5);
     for (int f = dc; f < dc + dn; ++f) place(f, cost[1], n5, FR_N5, A.p5f, FR_N5);
     for (int f = 0; f < dc + dn; ++f) place(f, cost[2], n4, FR_NF, A.p4f, FR_NF);
+}
+// offsets (in floats from the start of dynamic shared memory) of the kernel's arrays; fused_rows_smem_bytes bounds the total
+void fr_layout(FusedRowsArgs& A, const SmallMlpDesc& m, int K, int dc, int dn) {
+    FrLayout& L = A.lay;
+    const int H1 = m.H[0], nrows = FR_TS * dc, n_gnum = dn * K + dn;
+    int o = m.D * FR_W0S;
+    L.ups = o; o += m.up_count;
+    L.gup = o; o += m.up_count + ((4 - ((2 * m.up_count) & 3)) & 3);
+    L.slots = o; o += FR_NSLOT * FR_TS * A.sst;
+    L.rowix = o; o += FR_NSLOT * nrows;
+    L.once = o; o += FR_NSLOT * nrows;
+    L.xsb = o; o += FR_NSLOT * FR_TS * (dn > 0 ? dn : 1);
+    L.ysb = o; o += FR_NSLOT * FR_TS;
+    o += (4 - (o & 3)) & 3;
+    L.part = o; o += FR_CW * FR_TS * H1;
+    L.p1 = o; o += FR_CW * (2 * K + 4);
+    L.dh1s = o; o += FR_TS * H1;
+    L.acts = o; o += FR_TS * m.act_stride;
+    L.dacts = o; o += FR_TS * m.act_stride;
+    L.zs = o; o += FR_TS;
+    L.dzs = o; o += FR_TS;
+    L.red = o; o += FR_TS;
+    o += (4 - (o & 3)) & 3;
+    L.ss = o; o += FR_TS * K;
+    L.gnum = o; o += n_gnum;
+    o += o & 1;
+    L.bars = o;
 }
 size_t fused_rows_smem_bytes(const SmallMlpDesc& m, int K, int dc, int dn, int rs) {
     size_t f = (size_t)m.D * FR_W0S + 2 * (size_t)m.up_count + 8;

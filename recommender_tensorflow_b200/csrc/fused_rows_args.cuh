@@ -17,8 +17,11 @@ constexpr int FR_NR = 2;                       // rows per producer lane and til
 constexpr int FR_NF = FR_CW == 16 ? 3 : 2;     // dW0 fields per consumer warp (d <= 48)
 constexpr int FR_N5 = FR_CW == 16 ? 4 : 3;     // dE / update tasks per consumer warp
 
+struct FrLayout { int ups, gup, slots, rowix, once, xsb, ysb, part, p1, dh1s, acts, dacts, zs, dzs, red, ss, gnum, bars; };
+
 struct FusedRowsArgs {
     FusedArgs f;
+    FrLayout lay;            // shared-memory offsets in floats (fr_layout)
     const uint32_t* claim; uint32_t claim_mask;    // 2 bits per slot; nullptr: no in-kernel optimizer (every row goes the sorted way)
     int rs;                  // floats per staged record: K + 4 + emb_slots * K
     int sst;                 // floats per sample in a tile slot (dc records + dn numeric embeddings, = 4 mod 32)
@@ -45,6 +48,7 @@ int fused_rows_grid(int B, int sm_count, bool side_stream_busy);                
 // once" go through the sort / ordered reduction.  n_out[0] = pairs kept, n_out[1] = once-only lookups.  scratch: n / 2048 + 2 words.
 cudaError_t fused_rows_compact(const uint32_t* keys_in, const uint32_t* vals_in, int64_t n, uint32_t R, const uint32_t* claim, uint32_t claim_mask,
                                uint32_t* keys_out, uint32_t* vals_out, uint32_t* scratch, uint32_t* n_out, cudaStream_t st, int64_t* launches);
+void fr_layout(FusedRowsArgs& A, const SmallMlpDesc& m, int K, int dc, int dn);      // needs A.sst
 void fr_balance(FusedRowsArgs& A, int dc, int dn, bool cat_tasks);   // cat_tasks: the kernel applies / forwards the once-only rows' gradients
 cudaError_t fused_rows_set_attr(int smem_bytes);
 cudaError_t fused_rows_launch(const FusedRowsArgs& A, int grid, size_t smem_bytes, cudaStream_t st);
