@@ -90,13 +90,31 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
     lo = __float_as_uint(x - __uint_as_float(hi & 0xffffe000u)) + 0x1000u;
 }
 // sparse optimizer step of one element inside the kernel (see the note on the Adam displacement above)
+// FAST: instantiation for Adam everywhere with the closed-form replay - the other optimizers (IEEE divisions / square
+// roots) and the step-by-step replay fallback (double-precision pow) are not compiled in at all
+template <bool FAST>
 __device__ __forceinline__ void apply_elem(float& w, float& s1, float& s2, float g, const OptDev& o) {
-    if (o.kind == DFM_OPT_ADAM) {
+    if (FAST || o.kind == DFM_OPT_ADAM) {
         s1 = __fadd_rn(__fmul_rn(s1, o.b1), __fmul_rn(g, o.omb1));
         s2 = __fadd_rn(__fmul_rn(s2, o.b2), __fmul_rn(__fmul_rn(g, g), o.omb2));
         w -= fast_upd(s1, s2, o.alpha, o.eps);
     } else {
         other_apply(w, s1, s2, g, o);
+    }
+}
+template <bool FAST>
+__device__ __forceinline__ void fr_replay_row(float4& w, float4& m, float4& v, float4& lr, bool lin_lane, const RowReplay& rr,
+                                              const ReplayStep& rs, const OptDev& od, const OptDev& ol) {
+    if constexpr (FAST) {      // replay_row's common case: same arithmetic, same order
+        const int last = __float_as_int(lr.w);
+        if (rr.upto < 0 || last >= rr.upto) return;
+        const ReplayCoef c = replay_coef(rr.rd, rs, last);
+        replay_elem(w.x, m.x, v.x, c, od.eps); replay_elem(w.y, m.y, v.y, c, od.eps);
+        replay_elem(w.z, m.z, v.z, c, od.eps); replay_elem(w.w, m.w, v.w, c, od.eps);
+        if (rr.lin_adam && lin_lane) replay_elem(lr.x, lr.y, lr.z, c, ol.eps);
+        lr.w = __int_as_float(rr.upto);
+    } else {
+        replay_row(w, m, v, lr, lin_lane, rr, rs, od, ol);
     }
 }
 // 3xTF32 product: main += a_hi b_hi;  cross += a_lo b_hi + a_hi b_lo
@@ -112,7 +130,7 @@ __device__ __forceinline__ void mma3(float (&cm)[4], float (&cx)[4], const uint3
 // gradient row of a row looked up once in the local batch is stored straight into its owner's gradient segment (peer
 // memory over NVLink, or the local send buffer of the collective path); rows looked up several times are left to
 // row_gsum_kernel / row_update_kernel, which skip the single ones.
-template <int K, int H1, int ES, bool RB>
+template <int K, int H1, int ES, bool RB, bool FAST>
 __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs A) {
     static_assert(!RB || ES == 0, "row-buffer records carry no optimizer slots");
     static_assert(K == 16 && H1 == 16, "instantiated for embedding_size 16 / first hidden layer 16");
@@ -299,7 +317,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                         float4 mm = make_float4(0.f, 0.f, 0.f, 0.f), vv = mm;
                         if (ES >= 1) mm = *reinterpret_cast<const float4*>(rec + K + 4 + sub * 4);
                         if (ES >= 2) vv = *reinterpret_cast<const float4*>(rec + 2 * K + 4 + sub * 4);
-                        replay_row(e, mm, vv, lr, sub == 0, a.rr, rs, a.od, a.ol);
+                        fr_replay_row<FAST>(e, mm, vv, lr, sub == 0, a.rr, rs, a.od, a.ol);
                         *reinterpret_cast<float4*>(rec + sub * 4) = e;
                         if (ES >= 1) *reinterpret_cast<float4*>(rec + K + 4 + sub * 4) = mm;
                         if (ES >= 2) *reinterpret_cast<float4*>(rec + 2 * K + 4 + sub * 4) = vv;
@@ -459,7 +477,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                                 float4 mm = make_float4(0.f, 0.f, 0.f, 0.f), vv = mm;
                                 if (ES >= 1) mm = *reinterpret_cast<const float4*>(rec + K + 4 + t * 4);
                                 if (ES >= 2) vv = *reinterpret_cast<const float4*>(rec + 2 * K + 4 + t * 4);
-                                replay_row(e, mm, vv, lr, t == 0, a.rr, rs, a.od, a.ol);
+                                fr_replay_row<FAST>(e, mm, vv, lr, t == 0, a.rr, rs, a.od, a.ol);
                                 *reinterpret_cast<float4*>(rec + t * 4) = e;
                                 if (ES >= 1) *reinterpret_cast<float4*>(rec + K + 4 + t * 4) = mm;
                                 if (ES >= 2) *reinterpret_cast<float4*>(rec + 2 * K + 4 + t * 4) = vv;
@@ -735,8 +753,8 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                                     gr.z = fmaf(dzr, sv.z - w.z, gr.z); gr.w = fmaf(dzr, sv.w - w.w, gr.w);
                                 }
                                 if (!(A.ablate & 256)) {
-                                apply_elem(w.x, s1.x, s2.x, gr.x, A.od_t); apply_elem(w.y, s1.y, s2.y, gr.y, A.od_t);
-                                apply_elem(w.z, s1.z, s2.z, gr.z, A.od_t); apply_elem(w.w, s1.w, s2.w, gr.w, A.od_t);
+                                apply_elem<FAST>(w.x, s1.x, s2.x, gr.x, A.od_t); apply_elem<FAST>(w.y, s1.y, s2.y, gr.y, A.od_t);
+                                apply_elem<FAST>(w.z, s1.z, s2.z, gr.z, A.od_t); apply_elem<FAST>(w.w, s1.w, s2.w, gr.w, A.od_t);
                                 }
                                 // the record goes straight back to the table (4 lanes = 64 contiguous bytes per store)
                                 float* grec = a.tb.rec + (size_t)rix[g * dc + f] * a.tb.stride;
@@ -746,7 +764,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) fused_rows_kernel(FusedRowsArgs
                                 if (ES >= 2) *reinterpret_cast<float4*>(grec + 2 * K + 4 + t * 4) = s2;
                                 if (t == 0) {
                                     float4 lr = *reinterpret_cast<const float4*>(rec + K);
-                                    if (use_lin) apply_elem(lr.x, lr.y, lr.z, dzr, A.ol_t);
+                                    if (use_lin) apply_elem<FAST>(lr.x, lr.y, lr.z, dzr, A.ol_t);
                                     lr.w = __int_as_float(A.step);
                                     *reinterpret_cast<float4*>(grec + K) = lr;
                                 }
@@ -998,7 +1016,8 @@ int fused_rows_grid(int B, int sm_count, bool side_stream_busy) {
 
 template <int ES, bool RB>
 static cudaError_t fr_attr(int smem_bytes) {
-    return cudaFuncSetAttribute(fused_rows_kernel<16, 16, ES, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(fused_rows_kernel<16, 16, ES, RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    return e ? e : cudaFuncSetAttribute(fused_rows_kernel<16, 16, ES, RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 }
 cudaError_t fused_rows_set_attr(int smem_bytes) {
     cudaError_t e = fr_attr<0, false>(smem_bytes);
@@ -1007,15 +1026,25 @@ cudaError_t fused_rows_set_attr(int smem_bytes) {
     if (!e) e = fr_attr<0, true>(smem_bytes);
     return e;
 }
+template <int ES, bool RB>
+static void fr_go(const FusedRowsArgs& A, int grid, size_t smem_bytes, cudaStream_t st) {
+    // FAST: every optimizer step the kernel takes is Adam and every replay is the closed form (row-buffer mode does neither)
+    const RowReplay& rr = A.f.rr;
+    const bool replay_fast = rr.upto < 0 || (rr.emb_adam && rr.rd.closed && (rr.same || !rr.lin_adam));
+    const bool apply_fast = RB || !A.f.train || A.claim == nullptr || (A.od_t.kind == DFM_OPT_ADAM && (!A.f.use_linear || A.ol_t.kind == DFM_OPT_ADAM));
+    static const bool allow = getenv("DFM_FR_NO_FAST") == nullptr;
+    if (allow && replay_fast && apply_fast) fused_rows_kernel<16, 16, ES, RB, true><<<grid, FR_THREADS, smem_bytes, st>>>(A);
+    else fused_rows_kernel<16, 16, ES, RB, false><<<grid, FR_THREADS, smem_bytes, st>>>(A);
+}
 cudaError_t fused_rows_launch(const FusedRowsArgs& A, int grid, size_t smem_bytes, cudaStream_t st) {
     if (A.rowbuf_mode) {
-        fused_rows_kernel<16, 16, 0, true><<<grid, FR_THREADS, smem_bytes, st>>>(A);
+        fr_go<0, true>(A, grid, smem_bytes, st);
         return cudaGetLastError();
     }
     switch (A.emb_slots) {
-        case 0: fused_rows_kernel<16, 16, 0, false><<<grid, FR_THREADS, smem_bytes, st>>>(A); break;
-        case 1: fused_rows_kernel<16, 16, 1, false><<<grid, FR_THREADS, smem_bytes, st>>>(A); break;
-        default: fused_rows_kernel<16, 16, 2, false><<<grid, FR_THREADS, smem_bytes, st>>>(A); break;
+        case 0: fr_go<0, false>(A, grid, smem_bytes, st); break;
+        case 1: fr_go<1, false>(A, grid, smem_bytes, st); break;
+        default: fr_go<2, false>(A, grid, smem_bytes, st); break;
     }
     return cudaGetLastError();
 }
