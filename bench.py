@@ -48,9 +48,10 @@ DEFAULT_WORKLOAD = "deepfm_criteo_1e7_k16_h16x16_b65536"
 SECONDARY = ["deepfm_ml100k_k16_h256x128_b65536", "wide_deep_ml100k_k4_h16x16_b4096", "deepfm_ml100k_k4_h16x16_b32"]
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (ncu --set full, profiles/)
 TRAFFIC = {
-    "deepfm_criteo_1e7_k16_h16x16_b65536": (901.6e6, "fused_rows_kernel<16,16,2> (gather + tower + in-kernel optimizer of the once-only rows: 551 MB read + "
-                                            "351 MB written per launch; profiles/r02aj_fused_rows_full_summary.txt); algorithmic record traffic of "
-                                            "that kernel: 1.70 M rows x 256 B in + 1.68 M rows x 208 B out = 785 MB -> traffic / algorithmic = 1.15"),
+    "deepfm_criteo_1e7_k16_h16x16_b65536": (851.8e6, "fused_rows_kernel<16,16,2> (gather + tower + in-kernel optimizer of the once-only rows: 504.5 MB read + "
+                                            "347.3 MB written per launch; profiles/r02bc_fused_rows_full_summary.txt, captured before the last two "
+                                            "instruction-stream changes of the kernel, which move no bytes); algorithmic record traffic of "
+                                            "that kernel: 1.70 M rows x 256 B in + 1.68 M rows x 208 B out = 785 MB -> traffic / algorithmic = 1.09"),
     "deepfm_ml100k_k16_h256x128_b65536": (151.8e6, "mean of the 4 launches/step of tc::gemm_persist_kernel<16>; profiles/r01k_gemm_persist_full_summary.csv"),
 }
 
